@@ -1,0 +1,192 @@
+/*
+ * stfb200.h -- C ABI of libstfb200.so: hand-written sm_100a kernels for the STF-Unet hot path.
+ *
+ * The reference (XiangFeng-Wen/STF-Unet) is pure Python: every operator on the hot path is a
+ * torch / torchvision library call and there is no FFI to mirror.  Each entry point below
+ * therefore cites the reference *call site* whose library operator it replaces
+ * (paths are relative to the reference checkout).
+ *
+ * Conventions
+ *   - every function returns 0 on success, a negative STFB_E* code otherwise; it never throws,
+ *     never exits, never allocates or frees device memory, never synchronises the device;
+ *     stfb_last_error() returns a thread-local message for the last failure.
+ *   - all pointers are device pointers owned by the caller unless the name says `host`.
+ *   - `stream` is a cudaStream_t passed as void*; kernels are enqueued on it and are safe for
+ *     CUDA-graph capture (exception: none).
+ *   - activations are NHWC ("pixel rows x channels"); dtype codes: 0 = fp32, 1 = bf16.
+ *     Accumulation is always fp32 (fp64 for BatchNorm / loss reductions).
+ *   - there is NO CPU fallback: without a CUDA device the launch functions return STFB_ENODEV.
+ */
+#ifndef STFB200_H_
+#define STFB200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define STFB_OK 0
+#define STFB_EINVAL (-1)   /* bad shape / dtype / alignment / null pointer      */
+#define STFB_ECUDA (-2)    /* CUDA runtime error at launch                        */
+#define STFB_ENODEV (-3)   /* no sm_100 device                                    */
+#define STFB_ENOTSUP (-4)  /* shape not supported by the requested kernel family  */
+
+#define STFB_F32 0
+#define STFB_BF16 1
+
+/* conv gather modes */
+#define STFB_CONV_FWD 0        /* iy = oy*stride - pad + ky                       (Conv2d forward, ConvTranspose2d dgrad) */
+#define STFB_CONV_TRANSPOSED 1 /* iy = (oy + pad - ky)/stride when divisible      (ConvTranspose2d forward, Conv2d dgrad) */
+
+/* conv kernel families (stfb_conv_params.impl) */
+#define STFB_IMPL_AUTO 0
+#define STFB_IMPL_SIMT 1       /* fp32-FFMA implicit GEMM (fp32-accurate mode and odd shapes) */
+#define STFB_IMPL_TCGEN05 2    /* bf16 tcgen05/TMEM implicit GEMM fed by TMA                  */
+
+int stfb_version(void);
+const char* stfb_last_error(void);
+/* number of kernels launched through this library by the calling process (bench "gpu_launches") */
+unsigned long long stfb_launch_count(void);
+
+/* ------------------------------------------------------------------------------------------------
+ * Implicit-GEMM convolution:  y[m, co] = epilogue( sum_{ky,kx,ci} X[gather(m,ky,kx), ci] * Wp[(ky,kx,ci), co] )
+ *   m = (n, oy, ox) output pixel; X is the channel concat of x (C1 channels) and x2 (C2, may be 0/NULL).
+ *   epilogue: v += bias[co] + bias2[co]; v = v*scale[co] + shift[co]; v += residual[m, co]; relu.
+ * Replaces: nn.Conv2d (src/stf_lstm_unet.py:13,16,46,105,137 ; src/unet.py:12,15,37 ; torchvision
+ *   BasicBlock convs behind src/stf_lstm_unet.py:111-114), torch.cat + conv (src/stf_lstm_unet.py:60-63,
+ *   src/unet.py:48-54), nn.ConvTranspose2d (src/stf_lstm_unet.py:43,135 ; src/unet.py:28-34) via
+ *   STFB_CONV_TRANSPOSED, the nn.LSTM gate GEMMs (src/stf_lstm_unet.py:124-127) as 1x1 convs, the folded
+ *   eval-mode nn.BatchNorm2d + ReLU + residual add (src/stf_lstm_unet.py:29-35), and every dgrad of these.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct stfb_conv_params {
+  const void* x;        /* [N, H, W, C1]  x_dtype                                  */
+  const void* x2;       /* [N, H, W, C2]  or NULL                                  */
+  const void* w;        /* packed weights [kh*kw*(C1+C2), ldw] in x_dtype (see stfb_pack_weight) */
+  void* y;              /* [N, Ho, Wo, Cout] y_dtype                               */
+  const float* bias;    /* [Cout] or NULL                                          */
+  const float* bias2;   /* [Cout] or NULL                                          */
+  const float* scale;   /* [Cout] or NULL (folded BatchNorm)                       */
+  const float* shift;   /* [Cout] or NULL                                          */
+  const void* residual; /* [N, Ho, Wo, Cout] y_dtype or NULL (may alias y)         */
+  int N, H, W, C1, C2;
+  int Ho, Wo, Cout;
+  int kh, kw, stride, pad;
+  int ldw;              /* row stride (elements) of w; >= Cout                     */
+  int mode;             /* STFB_CONV_FWD / STFB_CONV_TRANSPOSED                    */
+  int relu;
+  int x_dtype, y_dtype; /* (f32,f32) (bf16,bf16) (bf16,f32)                        */
+  int impl;             /* STFB_IMPL_*                                             */
+} stfb_conv_params;
+
+int stfb_conv2d(const stfb_conv_params* p, void* stream);
+/* 1 if the tcgen05 kernel family supports this problem (host-only check, no launch). */
+int stfb_conv2d_tcgen05_supported(const stfb_conv_params* p);
+
+/* Weight gradient:  dW[cp][cg_off + cg][ky][kx] += sum_pix P[pix, cp] * G[gather(pix,ky,kx), cg]
+ *   P = per-pixel tensor [N, Hp, Wp, Cp] (dy of a Conv2d; x of a ConvTranspose2d),
+ *   G = gathered tensor  [N, Hg, Wg, Cg] (x of a Conv2d;  dy of a ConvTranspose2d), gather iy = py*stride - pad + ky.
+ *   dW is fp32 in the reference parameter layout ([Cout,Cin,kh,kw] for Conv2d, [Cin,Cout,kh,kw] for
+ *   ConvTranspose2d, [4C,C] for the LSTM matrices) and is ACCUMULATED into (caller zeroes it).
+ * Replaces: autograd of the operators listed above (loss.backward(), train_utils/train_and_eval.py:397-404). */
+int stfb_conv2d_wgrad(const void* P, const void* G, float* dW, int N, int Hp, int Wp, int Cp, int Hg, int Wg, int Cg,
+                      int cg_off, int cg_total, int kh, int kw, int stride, int pad, int dtype, void* stream);
+
+/* Parameter layout [D0][D1][kh][kw] fp32 -> GEMM layout [(ky,kx,k)][n] in dtype.
+ *   k_is_dim1 = 1: k = D1 index, n = D0 index (Conv2d forward, ConvTranspose2d dgrad, LSTM x @ W^T)
+ *   k_is_dim1 = 0: k = D0 index, n = D1 index (Conv2d dgrad, ConvTranspose2d forward, LSTM dgates @ W) */
+int stfb_pack_weight(const float* w, void* wp, int D0, int D1, int kh, int kw, int k_is_dim1, int dtype, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * BatchNorm2d (eps, momentum as nn.BatchNorm2d defaults 1e-5 / 0.1; torchvision BasicBlock bn1/bn2,
+ * src/stf_lstm_unet.py:14,17,108 ; src/unet.py:13,16).  Rows are grouped: group g = rows [g*R, (g+1)*R);
+ * the STF encoder runs with G = T groups because the reference calls each BN once per time step
+ * (src/stf_lstm_unet.py:168-186) -- statistics are per group, running stats get G sequential updates.
+ * ---------------------------------------------------------------------------------------------- */
+/* sums[g][c] = sum x, sums[G*C + g*C + c] = sum x^2 (fp64, zeroed inside) */
+int stfb_bn_stats(const void* x, double* sums, int G, long long R, int C, int dtype, void* stream);
+/* train: batch stats -> scale/shift/mean/invstd [G][C]; running_mean/var updated G times in place,
+ * num_batches_tracked += G.   */
+int stfb_bn_finalize_train(const double* sums, const float* gamma, const float* beta, float* running_mean,
+                           float* running_var, long long* num_batches_tracked, float* scale, float* shift,
+                           float* mean, float* invstd, int G, long long R, int C, float eps, float momentum,
+                           void* stream);
+/* eval: scale = gamma/sqrt(running_var+eps), shift = beta - running_mean*scale  ([C]) */
+int stfb_bn_fold_eval(const float* gamma, const float* beta, const float* running_mean, const float* running_var,
+                      float* scale, float* shift, int C, float eps, void* stream);
+/* y = relu?( x*scale[g][c] + shift[g][c] + residual ) */
+int stfb_bn_apply(const void* x, const float* scale, const float* shift, const void* residual, void* y, int G,
+                  long long R, int C, int relu, int dtype, void* stream);
+/* backward, step 1: dz = dy * (y > 0 if relu); red[g][c] = sum dz, red[G*C + g*C + c] = sum dz*xhat (fp64, zeroed inside) */
+int stfb_bn_bwd_reduce(const void* dy, const void* y, const void* x, const float* mean, const float* invstd,
+                       double* red, int G, long long R, int C, int relu, int dtype, void* stream);
+/* backward, step 2: dgamma[c] += sum_g red2, dbeta[c] += sum_g red1; coef[g][c][3] = {gamma*invstd, red1/R, red2/R} */
+int stfb_bn_bwd_finalize(const double* red, const float* gamma, const float* invstd, float* dgamma, float* dbeta,
+                         float* coef, int G, long long R, int C, void* stream);
+/* backward, step 3: dx = coef0 * (dz - coef1 - xhat*coef2); if dres != NULL: dres = dz (+ dres when accum_dres:
+ * the residual input of a block already carries the gradient of its other consumers) */
+int stfb_bn_bwd_apply(const void* dy, const void* y, const void* x, const float* mean, const float* invstd,
+                      const float* coef, void* dx, void* dres, int accum_dres, int G, long long R, int C, int relu,
+                      int dtype, void* stream);
+/* out[c] += sum_rows x[row][c]  (bias gradients: Conv2d/ConvTranspose2d bias, LSTM bias_ih/bias_hh) */
+int stfb_colsum(const void* x, float* out, long long R, int C, int dtype, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * MaxPool2d(k, stride 2, pad) NHWC, -inf padding, floor mode (src/stf_lstm_unet.py:110,180 k=3 pad=1;
+ * src/unet.py:25 k=2 pad=0).  Backward routes to the first maximum in scan order (PyTorch tie rule).
+ * ---------------------------------------------------------------------------------------------- */
+int stfb_maxpool_fwd(const void* x, void* y, int N, int H, int W, int C, int Ho, int Wo, int k, int stride, int pad,
+                     int dtype, void* stream);
+int stfb_maxpool_bwd(const void* x, const void* dy, void* dx, int N, int H, int W, int C, int Ho, int Wo, int k,
+                     int stride, int pad, int dtype, void* stream);
+
+/* Bilinear resize, align_corners=True (F.interpolate at src/stf_lstm_unet.py:57,191-194), NHWC. */
+int stfb_bilinear_fwd(const void* x, void* y, int N, int H, int W, int C, int Ho, int Wo, int dtype, void* stream);
+/* dx must be zeroed by the caller (fp32 accumulate): dx[N,H,W,C] fp32 += scatter(dy) */
+int stfb_bilinear_bwd(const void* dy, float* dx, int N, int H, int W, int C, int Ho, int Wo, int dtype, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Per-pixel LSTM cell (nn.LSTM(C, C, batch_first=True) applied to [B*h*w, T, C],
+ * src/stf_lstm_unet.py:124-127, :216-242).  gates = pre-activations [R][4C] fp32 in PyTorch order i,f,g,o
+ * (already containing W_ih x + b_ih + W_hh h + b_hh, produced by stfb_conv2d as 1x1 GEMMs).
+ * ---------------------------------------------------------------------------------------------- */
+/* c_prev may be NULL (t = 0, zero state).  acts (dtype, [R][4C]) may be NULL in eval mode.
+ * c_out fp32 [R][C]; h_out dtype [R][C]. */
+int stfb_lstm_cell_fwd(const float* gates, const float* c_prev, void* acts, float* c_out, void* h_out, long long R,
+                       int C, int dtype, void* stream);
+/* dh fp32 [R][C]; dc fp32 [R][C] in/out (dc_t in, dc_{t-1} out; pass zeros at t = T-1);
+ * dgates dtype [R][4C] out. c_prev may be NULL (t = 0). */
+int stfb_lstm_cell_bwd(const float* dh, float* dc, const void* acts, const float* c_prev, const float* c_cur,
+                       void* dgates, long long R, int C, int dtype, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Layout adapters at the API boundary (reference tensors are NCHW fp32).
+ * ---------------------------------------------------------------------------------------------- */
+/* x [B, T, C, H, W] fp32  ->  y [T*B, H, W, C] dtype  (time-major image order n = t*B + b) */
+int stfb_pack_series(const float* x, void* y, int B, int T, int C, int H, int W, int dtype, void* stream);
+/* y NHWC dtype [N,H,W,C] -> out NCHW fp32 [N,C,H,W] */
+int stfb_nhwc_to_nchw(const void* y, float* out, int N, int H, int W, int C, int dtype, void* stream);
+/* g NCHW fp32 -> NHWC dtype */
+int stfb_nchw_to_nhwc(const float* g, void* out, int N, int H, int W, int C, int dtype, void* stream);
+/* dst[i] += src[i]  (gradient accumulation where a tensor has two consumers, e.g. the UNet skip + pool) */
+int stfb_add_inplace(void* dst, const void* src, long long n, int dtype, void* stream);
+/* dst[i] = (dtype) src[i]  /  dst[i] = (float) src[i] */
+int stfb_cast(const void* src, int src_dtype, void* dst, int dst_dtype, long long n, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * criterion = cross_entropy(mean) + multiclass softmax-Dice  (train_utils/train_and_eval.py:299-313,
+ * train_utils/dice_coefficient_loss.py:5-55).  logits NCHW fp32 [B,C,h,w], target int64 [B,h,w] in [0,C).
+ * stats fp64 [B*C*3 + 1] scratch (zeroed inside): per (b,c) {sum p*t, sum p, sum t}, then total NLL.
+ * loss_out fp32 [3] = {total, ce, dice_loss}.
+ * ---------------------------------------------------------------------------------------------- */
+int stfb_ce_dice_fwd(const float* logits, const long long* target, double* stats, float* loss_out, int B, int C,
+                     int HW, float eps, void* stream);
+/* dlogits = dloss[0] * d(total)/d(logits); dloss is a device fp32 scalar (NULL = 1.0). */
+int stfb_ce_dice_bwd(const float* logits, const long long* target, const double* stats, const float* dloss,
+                     float* dlogits, int B, int C, int HW, float eps, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* STFB200_H_ */

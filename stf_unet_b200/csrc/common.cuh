@@ -1,0 +1,98 @@
+// Shared helpers for libstfb200 kernels (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdarg.h>
+#include "../../include/stfb200.h"
+
+namespace stfb {
+
+void set_error(const char* fmt, ...);
+int check_device();          // STFB_OK or STFB_ENODEV (cached)
+int num_sms();
+void count_launch(int n = 1);
+int post_launch(const char* what);   // cudaGetLastError -> status
+
+#define STFB_REQUIRE(cond, ...)                 \
+  do {                                          \
+    if (!(cond)) {                              \
+      stfb::set_error(__VA_ARGS__);             \
+      return STFB_EINVAL;                       \
+    }                                           \
+  } while (0)
+
+#define STFB_DEVICE_OR_RETURN()                 \
+  do {                                          \
+    int _st = stfb::check_device();             \
+    if (_st != STFB_OK) return _st;             \
+  } while (0)
+
+// ---- 4-element vector load/store with conversion to float ------------------------------------
+struct f4 { float v[4]; };
+
+__device__ __forceinline__ f4 ld4(const float* p) {
+  float4 t = *reinterpret_cast<const float4*>(p);
+  return f4{{t.x, t.y, t.z, t.w}};
+}
+__device__ __forceinline__ f4 ld4(const __nv_bfloat16* p) {
+  uint2 t = *reinterpret_cast<const uint2*>(p);
+  __nv_bfloat162 a = *reinterpret_cast<__nv_bfloat162*>(&t.x);
+  __nv_bfloat162 b = *reinterpret_cast<__nv_bfloat162*>(&t.y);
+  float2 fa = __bfloat1622float2(a), fb = __bfloat1622float2(b);
+  return f4{{fa.x, fa.y, fb.x, fb.y}};
+}
+__device__ __forceinline__ void st4(float* p, const f4& a) {
+  *reinterpret_cast<float4*>(p) = make_float4(a.v[0], a.v[1], a.v[2], a.v[3]);
+}
+__device__ __forceinline__ void st4(__nv_bfloat16* p, const f4& a) {
+  __nv_bfloat162 lo = __floats2bfloat162_rn(a.v[0], a.v[1]);
+  __nv_bfloat162 hi = __floats2bfloat162_rn(a.v[2], a.v[3]);
+  uint2 t;
+  t.x = *reinterpret_cast<uint32_t*>(&lo);
+  t.y = *reinterpret_cast<uint32_t*>(&hi);
+  *reinterpret_cast<uint2*>(p) = t;
+}
+__device__ __forceinline__ float ld1(const float* p) { return *p; }
+__device__ __forceinline__ float ld1(const __nv_bfloat16* p) { return __bfloat162float(*p); }
+__device__ __forceinline__ void st1(float* p, float v) { *p = v; }
+__device__ __forceinline__ void st1(__nv_bfloat16* p, float v) { *p = __float2bfloat16_rn(v); }
+
+// 8-element (16 B) bf16 / 2x16 B fp32 loads
+struct f8 { float v[8]; };
+__device__ __forceinline__ f8 ld8(const float* p) {
+  float4 a = *reinterpret_cast<const float4*>(p);
+  float4 b = *reinterpret_cast<const float4*>(p + 4);
+  return f8{{a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w}};
+}
+__device__ __forceinline__ f8 ld8(const __nv_bfloat16* p) {
+  uint4 t = *reinterpret_cast<const uint4*>(p);
+  f8 r;
+  const uint32_t w[4] = {t.x, t.y, t.z, t.w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    __nv_bfloat162 h = *reinterpret_cast<const __nv_bfloat162*>(&w[i]);
+    float2 f = __bfloat1622float2(h);
+    r.v[2 * i] = f.x;
+    r.v[2 * i + 1] = f.y;
+  }
+  return r;
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+__device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + expf(-x)); }
+
+static inline int ceil_div(long long a, long long b) { return (int)((a + b - 1) / b); }
+
+}  // namespace stfb

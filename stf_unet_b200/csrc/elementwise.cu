@@ -1,0 +1,810 @@
+// Memory-bound kernels of the STF-Unet hot path: BatchNorm statistics / apply / backward, column sums,
+// max-pool, bilinear resize, LSTM cell update, layout adapters.  All NHWC, 4-wide vector accesses along the
+// channel axis when C % 4 == 0, warp-shuffle-free smem column reductions with fp64 global accumulation.
+#include "common.cuh"
+
+namespace stfb {
+
+static inline bool aligned_to(const void* q, int b) { return (reinterpret_cast<uintptr_t>(q) % b) == 0; }
+static inline int grid_for(long long work, int threads = 256, int max_waves = 16) {
+  long long b = (work + threads - 1) / threads;
+  long long cap = (long long)max_waves * num_sms();
+  if (b > cap) b = cap;
+  if (b < 1) b = 1;
+  return (int)b;
+}
+
+// =================================================================================================
+// column reductions over rows grouped in G contiguous groups of R rows
+// =================================================================================================
+struct ColRedArgs {
+  const void* a;       // MODE 0: x        MODE 1: dy      MODE 2: x
+  const void* b;       //                  MODE 1: y (relu mask) or NULL
+  const void* c;       //                  MODE 1: x (pre-BN)
+  const float* mean;   // [G][C]  (MODE 1)
+  const float* invstd; // [G][C]  (MODE 1)
+  double* out;         // [2][G][C]  (MODE 0/1)
+  float* outf;         // [C]        (MODE 2)
+  int G;
+  long long R;
+  int C;
+  int relu;
+  long long rows_per_block;
+  int tpr;             // threads per row (power of two <= 256)
+};
+
+template <typename T, int VEC, int MODE>
+__global__ void __launch_bounds__(256) colreduce_kernel(const ColRedArgs A) {
+  __shared__ float red[256 * VEC * 2];
+  const int tid = threadIdx.x;
+  const int g = blockIdx.y;
+  const int tpr = A.tpr, lanes = 256 / tpr;
+  const int cl = tid % tpr, rl = tid / tpr;
+  const int CVn = A.C / VEC;
+  const long long r0 = (long long)blockIdx.x * A.rows_per_block;
+  const long long r1 = min(A.R, r0 + A.rows_per_block);
+  const T* __restrict__ pa = reinterpret_cast<const T*>(A.a);
+  const T* __restrict__ pb = reinterpret_cast<const T*>(A.b);
+  const T* __restrict__ pc = reinterpret_cast<const T*>(A.c);
+
+  for (int cv0 = 0; cv0 < CVn; cv0 += tpr) {
+    const int cv = cv0 + cl;
+    const bool active = cv < CVn;
+    float s[VEC], q[VEC];
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) s[j] = q[j] = 0.f;
+    if (active) {
+      const int c = cv * VEC;
+      float mu[VEC], is[VEC];
+      if (MODE == 1) {
+#pragma unroll
+        for (int j = 0; j < VEC; ++j) {
+          mu[j] = A.mean[g * A.C + c + j];
+          is[j] = A.invstd[g * A.C + c + j];
+        }
+      }
+      for (long long r = r0 + rl; r < r1; r += lanes) {
+        const long long off = ((long long)g * A.R + r) * A.C + c;
+        float va[VEC], vb[VEC], vc[VEC];
+        if (VEC == 4) {
+          f4 t = ld4(pa + off);
+#pragma unroll
+          for (int j = 0; j < VEC; ++j) va[j] = t.v[j];
+          if (MODE == 1) {
+            f4 u = ld4(pc + off);
+#pragma unroll
+            for (int j = 0; j < VEC; ++j) vc[j] = u.v[j];
+            if (A.relu) {
+              f4 w = ld4(pb + off);
+#pragma unroll
+              for (int j = 0; j < VEC; ++j) vb[j] = w.v[j];
+            }
+          }
+        } else {
+          va[0] = ld1(pa + off);
+          if (MODE == 1) {
+            vc[0] = ld1(pc + off);
+            if (A.relu) vb[0] = ld1(pb + off);
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < VEC; ++j) {
+          if (MODE == 0) {
+            s[j] += va[j];
+            q[j] = fmaf(va[j], va[j], q[j]);
+          } else if (MODE == 1) {
+            const float dz = (A.relu && !(vb[j] > 0.f)) ? 0.f : va[j];
+            s[j] += dz;
+            q[j] = fmaf(dz, (vc[j] - mu[j]) * is[j], q[j]);
+          } else {
+            s[j] += va[j];
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) {
+      red[(tid * VEC + j) * 2] = s[j];
+      red[(tid * VEC + j) * 2 + 1] = q[j];
+    }
+    __syncthreads();
+    if (rl == 0 && active) {
+#pragma unroll
+      for (int j = 0; j < VEC; ++j) {
+        double ds = 0.0, dq = 0.0;
+        for (int l = 0; l < lanes; ++l) {
+          ds += (double)red[((l * tpr + cl) * VEC + j) * 2];
+          dq += (double)red[((l * tpr + cl) * VEC + j) * 2 + 1];
+        }
+        const int c = cv * VEC + j;
+        if (MODE == 2) {
+          atomicAdd(A.outf + c, (float)ds);
+        } else {
+          atomicAdd(A.out + (long long)g * A.C + c, ds);
+          atomicAdd(A.out + (long long)(A.G + g) * A.C + c, dq);
+        }
+      }
+    }
+    __syncthreads();
+  }
+}
+
+template <int MODE>
+static int launch_colreduce(ColRedArgs A, int dtype, bool vec_ok, cudaStream_t st, const char* what) {
+  if (A.R == 0 || A.G == 0) return STFB_OK;
+  const int VEC = vec_ok ? 4 : 1;
+  const int CVn = A.C / VEC;
+  int tpr = 1;
+  while (tpr * 2 <= CVn && tpr * 2 <= 256) tpr *= 2;
+  A.tpr = tpr;
+  const int lanes = 256 / tpr;
+  long long rpb = (long long)lanes * 32;
+  const long long maxblocks = 16LL * num_sms();
+  while (((A.R + rpb - 1) / rpb) * A.G > maxblocks && rpb < (long long)lanes * 128) rpb *= 2;
+  A.rows_per_block = rpb;
+  dim3 grid((unsigned)((A.R + rpb - 1) / rpb), (unsigned)A.G);
+  if (dtype == STFB_F32) {
+    if (vec_ok) colreduce_kernel<float, 4, MODE><<<grid, 256, 0, st>>>(A);
+    else colreduce_kernel<float, 1, MODE><<<grid, 256, 0, st>>>(A);
+  } else {
+    if (vec_ok) colreduce_kernel<__nv_bfloat16, 4, MODE><<<grid, 256, 0, st>>>(A);
+    else colreduce_kernel<__nv_bfloat16, 1, MODE><<<grid, 256, 0, st>>>(A);
+  }
+  return post_launch(what);
+}
+
+// =================================================================================================
+// BatchNorm finalize / fold / apply / backward apply
+// =================================================================================================
+__global__ void bn_finalize_train_kernel(const double* __restrict__ sums, const float* __restrict__ gamma,
+                                         const float* __restrict__ beta, float* running_mean, float* running_var,
+                                         long long* nbt, float* scale, float* shift, float* mean, float* invstd, int G,
+                                         long long R, int C, float eps, float momentum) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c == 0 && nbt) *nbt += G;
+  if (c >= C) return;
+  float rm = running_mean ? running_mean[c] : 0.f, rv = running_var ? running_var[c] : 1.f;
+  const double n = (double)R;
+  for (int g = 0; g < G; ++g) {
+    const double m = sums[(long long)g * C + c] / n;
+    double var = sums[(long long)(G + g) * C + c] / n - m * m;
+    if (var < 0.0) var = 0.0;
+    const float is = (float)(1.0 / sqrt(var + (double)eps));
+    const float sc = gamma[c] * is;
+    scale[g * C + c] = sc;
+    shift[g * C + c] = beta[c] - (float)m * sc;
+    mean[g * C + c] = (float)m;
+    invstd[g * C + c] = is;
+    const double unbiased = R > 1 ? var * n / (n - 1.0) : var;
+    rm = (1.f - momentum) * rm + momentum * (float)m;
+    rv = (1.f - momentum) * rv + momentum * (float)unbiased;
+  }
+  if (running_mean) running_mean[c] = rm;
+  if (running_var) running_var[c] = rv;
+}
+
+__global__ void bn_fold_eval_kernel(const float* __restrict__ gamma, const float* __restrict__ beta,
+                                    const float* __restrict__ rm, const float* __restrict__ rv, float* scale,
+                                    float* shift, int C, float eps) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const float sc = gamma[c] / sqrtf(rv[c] + eps);
+  scale[c] = sc;
+  shift[c] = beta[c] - rm[c] * sc;
+}
+
+template <typename T, int VEC>
+__global__ void bn_apply_kernel(const T* __restrict__ x, const float* __restrict__ scale, const float* __restrict__ shift,
+                                const T* res, T* y, long long R, int C, long long total_vec, int relu) {
+  const int CVn = C / VEC;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total_vec; i += (long long)gridDim.x * blockDim.x) {
+    const long long row = i / CVn;
+    const int c = (int)(i - row * CVn) * VEC;
+    const int g = (int)(row / R);
+    const long long off = row * C + c;
+    if (VEC == 4) {
+      f4 v = ld4(x + off);
+      const float4 sc = *reinterpret_cast<const float4*>(scale + g * C + c);
+      const float4 sh = *reinterpret_cast<const float4*>(shift + g * C + c);
+      v.v[0] = fmaf(v.v[0], sc.x, sh.x); v.v[1] = fmaf(v.v[1], sc.y, sh.y);
+      v.v[2] = fmaf(v.v[2], sc.z, sh.z); v.v[3] = fmaf(v.v[3], sc.w, sh.w);
+      if (res) {
+        f4 r = ld4(res + off);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) v.v[j] += r.v[j];
+      }
+      if (relu) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) v.v[j] = fmaxf(v.v[j], 0.f);
+      }
+      st4(y + off, v);
+    } else {
+      float v = fmaf(ld1(x + off), scale[g * C + c], shift[g * C + c]);
+      if (res) v += ld1(res + off);
+      if (relu) v = fmaxf(v, 0.f);
+      st1(y + off, v);
+    }
+  }
+}
+
+__global__ void bn_bwd_finalize_kernel(const double* __restrict__ red, const float* __restrict__ gamma,
+                                       const float* __restrict__ invstd, float* dgamma, float* dbeta, float* coef, int G,
+                                       long long R, int C) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  double dg = 0.0, db = 0.0;
+  const double n = (double)R;
+  for (int g = 0; g < G; ++g) {
+    const double s1 = red[(long long)g * C + c], s2 = red[(long long)(G + g) * C + c];
+    db += s1;
+    dg += s2;
+    float* k = coef + ((long long)g * C + c) * 3;
+    k[0] = gamma[c] * invstd[g * C + c];
+    k[1] = (float)(s1 / n);
+    k[2] = (float)(s2 / n);
+  }
+  if (dgamma) dgamma[c] += (float)dg;
+  if (dbeta) dbeta[c] += (float)db;
+}
+
+template <typename T, int VEC>
+__global__ void bn_bwd_apply_kernel(const T* __restrict__ dy, const T* __restrict__ y, const T* __restrict__ x,
+                                    const float* __restrict__ mean, const float* __restrict__ invstd,
+                                    const float* __restrict__ coef, T* dx, T* dres, long long R, int C,
+                                    long long total_vec, int relu, int accum_dres) {
+  const int CVn = C / VEC;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total_vec; i += (long long)gridDim.x * blockDim.x) {
+    const long long row = i / CVn;
+    const int c = (int)(i - row * CVn) * VEC;
+    const int g = (int)(row / R);
+    const long long off = row * C + c;
+    float d[VEC], xv[VEC], yv[VEC];
+    if (VEC == 4) {
+      f4 a = ld4(dy + off), b = ld4(x + off);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) { d[j] = a.v[j]; xv[j] = b.v[j]; }
+      if (relu) {
+        f4 m = ld4(y + off);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) yv[j] = m.v[j];
+      }
+    } else {
+      d[0] = ld1(dy + off);
+      xv[0] = ld1(x + off);
+      if (relu) yv[0] = ld1(y + off);
+    }
+    float o[VEC];
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) {
+      const int gc = g * C + c + j;
+      const float dz = (relu && !(yv[j] > 0.f)) ? 0.f : d[j];
+      d[j] = dz;
+      const float xh = (xv[j] - mean[gc]) * invstd[gc];
+      const float* k = coef + (long long)gc * 3;
+      o[j] = k[0] * (dz - k[1] - xh * k[2]);
+    }
+    if (VEC == 4) {
+      st4(dx + off, f4{{o[0], o[1], o[2], o[3]}});
+      if (dres) {
+        if (accum_dres) {
+          f4 old = ld4(dres + off);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) d[j] += old.v[j];
+        }
+        st4(dres + off, f4{{d[0], d[1], d[2], d[3]}});
+      }
+    } else {
+      st1(dx + off, o[0]);
+      if (dres) st1(dres + off, accum_dres ? d[0] + ld1(dres + off) : d[0]);
+    }
+  }
+}
+
+// =================================================================================================
+// max-pool
+// =================================================================================================
+template <typename T, int VEC>
+__global__ void maxpool_fwd_kernel(const T* __restrict__ x, T* __restrict__ y, int N, int H, int W, int C, int Ho, int Wo,
+                                   int k, int stride, int pad, long long total_vec) {
+  const int CVn = C / VEC;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total_vec; i += (long long)gridDim.x * blockDim.x) {
+    const int cv = (int)(i % CVn);
+    long long r = i / CVn;
+    const int ox = (int)(r % Wo); r /= Wo;
+    const int oy = (int)(r % Ho);
+    const int n = (int)(r / Ho);
+    float best[VEC];
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) best[j] = -INFINITY;
+    for (int ky = 0; ky < k; ++ky) {
+      const int iy = oy * stride - pad + ky;
+      if (iy < 0 || iy >= H) continue;
+      for (int kx = 0; kx < k; ++kx) {
+        const int ix = ox * stride - pad + kx;
+        if (ix < 0 || ix >= W) continue;
+        const long long off = (((long long)n * H + iy) * W + ix) * C + cv * VEC;
+        if (VEC == 4) {
+          f4 v = ld4(x + off);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) best[j] = fmaxf(best[j], v.v[j]);
+        } else {
+          best[0] = fmaxf(best[0], ld1(x + off));
+        }
+      }
+    }
+    const long long oo = (((long long)n * Ho + oy) * Wo + ox) * C + cv * VEC;
+    if (VEC == 4) st4(y + oo, f4{{best[0], best[1], best[2], best[3]}});
+    else st1(y + oo, best[0]);
+  }
+}
+
+// gather form: each input element sums dy of the windows whose FIRST maximum (scan order ky, kx) it is.
+template <typename T, int VEC>
+__global__ void maxpool_bwd_kernel(const T* __restrict__ x, const T* __restrict__ dy, T* __restrict__ dx, int N, int H, int W,
+                                   int C, int Ho, int Wo, int k, int stride, int pad, long long total_vec) {
+  const int CVn = C / VEC;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total_vec; i += (long long)gridDim.x * blockDim.x) {
+    const int cv = (int)(i % CVn);
+    long long r = i / CVn;
+    const int ix = (int)(r % W); r /= W;
+    const int iy = (int)(r % H);
+    const int n = (int)(r / H);
+    float acc[VEC];
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) acc[j] = 0.f;
+    // windows containing (iy, ix): oy*stride - pad <= iy <= oy*stride - pad + k - 1
+    int oy_lo = iy + pad - k + 1; oy_lo = oy_lo <= 0 ? 0 : (oy_lo + stride - 1) / stride;
+    int oy_hi = (iy + pad) / stride; if (oy_hi > Ho - 1) oy_hi = Ho - 1;
+    int ox_lo = ix + pad - k + 1; ox_lo = ox_lo <= 0 ? 0 : (ox_lo + stride - 1) / stride;
+    int ox_hi = (ix + pad) / stride; if (ox_hi > Wo - 1) ox_hi = Wo - 1;
+    for (int oy = oy_lo; oy <= oy_hi; ++oy) {
+      for (int ox = ox_lo; ox <= ox_hi; ++ox) {
+        float best[VEC];
+        int arg[VEC];
+#pragma unroll
+        for (int j = 0; j < VEC; ++j) { best[j] = -INFINITY; arg[j] = -1; }
+        for (int ky = 0; ky < k; ++ky) {
+          const int yy = oy * stride - pad + ky;
+          if (yy < 0 || yy >= H) continue;
+          for (int kx = 0; kx < k; ++kx) {
+            const int xx = ox * stride - pad + kx;
+            if (xx < 0 || xx >= W) continue;
+            const long long off = (((long long)n * H + yy) * W + xx) * C + cv * VEC;
+            float v[VEC];
+            if (VEC == 4) {
+              f4 t = ld4(x + off);
+#pragma unroll
+              for (int j = 0; j < 4; ++j) v[j] = t.v[j];
+            } else {
+              v[0] = ld1(x + off);
+            }
+#pragma unroll
+            for (int j = 0; j < VEC; ++j) {
+              if (v[j] > best[j] || arg[j] < 0) { best[j] = v[j]; arg[j] = yy * W + xx; }
+            }
+          }
+        }
+        const long long oo = (((long long)n * Ho + oy) * Wo + ox) * C + cv * VEC;
+        float g[VEC];
+        if (VEC == 4) {
+          f4 t = ld4(dy + oo);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) g[j] = t.v[j];
+        } else {
+          g[0] = ld1(dy + oo);
+        }
+#pragma unroll
+        for (int j = 0; j < VEC; ++j)
+          if (arg[j] == iy * W + ix) acc[j] += g[j];
+      }
+    }
+    const long long io = (((long long)n * H + iy) * W + ix) * C + cv * VEC;
+    if (VEC == 4) st4(dx + io, f4{{acc[0], acc[1], acc[2], acc[3]}});
+    else st1(dx + io, acc[0]);
+  }
+}
+
+// =================================================================================================
+// bilinear, align_corners=True
+// =================================================================================================
+__device__ __forceinline__ void bilin_coords(int o, int in, float scale, int& i0, int& i1, float& l1) {
+  const float src = scale * (float)o;
+  i0 = (int)src;
+  if (i0 > in - 1) i0 = in - 1;
+  i1 = i0 + (i0 < in - 1 ? 1 : 0);
+  l1 = src - (float)i0;
+}
+
+template <typename T>
+__global__ void bilinear_fwd_kernel(const T* __restrict__ x, T* __restrict__ y, int N, int H, int W, int C, int Ho, int Wo,
+                                    float sy, float sx, long long total) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C);
+    long long r = i / C;
+    const int ox = (int)(r % Wo); r /= Wo;
+    const int oy = (int)(r % Ho);
+    const int n = (int)(r / Ho);
+    int y0, y1, x0, x1; float ly, lx;
+    bilin_coords(oy, H, sy, y0, y1, ly);
+    bilin_coords(ox, W, sx, x0, x1, lx);
+    const T* b = x + (long long)n * H * W * C + c;
+    const float v00 = ld1(b + ((long long)y0 * W + x0) * C), v01 = ld1(b + ((long long)y0 * W + x1) * C);
+    const float v10 = ld1(b + ((long long)y1 * W + x0) * C), v11 = ld1(b + ((long long)y1 * W + x1) * C);
+    const float v = (1.f - ly) * ((1.f - lx) * v00 + lx * v01) + ly * ((1.f - lx) * v10 + lx * v11);
+    st1(y + i, v);
+  }
+}
+
+template <typename T>
+__global__ void bilinear_bwd_kernel(const T* __restrict__ dy, float* __restrict__ dx, int N, int H, int W, int C, int Ho,
+                                    int Wo, float sy, float sx, long long total) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C);
+    long long r = i / C;
+    const int ox = (int)(r % Wo); r /= Wo;
+    const int oy = (int)(r % Ho);
+    const int n = (int)(r / Ho);
+    int y0, y1, x0, x1; float ly, lx;
+    bilin_coords(oy, H, sy, y0, y1, ly);
+    bilin_coords(ox, W, sx, x0, x1, lx);
+    const float g = ld1(dy + i);
+    float* b = dx + (long long)n * H * W * C + c;
+    atomicAdd(b + ((long long)y0 * W + x0) * C, g * (1.f - ly) * (1.f - lx));
+    atomicAdd(b + ((long long)y0 * W + x1) * C, g * (1.f - ly) * lx);
+    atomicAdd(b + ((long long)y1 * W + x0) * C, g * ly * (1.f - lx));
+    atomicAdd(b + ((long long)y1 * W + x1) * C, g * ly * lx);
+  }
+}
+
+// =================================================================================================
+// LSTM cell (PyTorch gate order i, f, g, o)
+// =================================================================================================
+template <typename T>
+__global__ void lstm_cell_fwd_kernel(const float* __restrict__ gates, const float* __restrict__ c_prev, T* acts, float* c_out,
+                                     T* h_out, long long R, int C, long long total_vec) {
+  const int CVn = C / 4;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total_vec; i += (long long)gridDim.x * blockDim.x) {
+    const long long row = i / CVn;
+    const int c = (int)(i - row * CVn) * 4;
+    const float* gp = gates + row * 4 * C + c;
+    const f4 gi = ld4(gp), gf = ld4(gp + C), gg = ld4(gp + 2 * C), go = ld4(gp + 3 * C);
+    f4 cp{{0.f, 0.f, 0.f, 0.f}};
+    if (c_prev) cp = ld4(c_prev + row * C + c);
+    f4 ai, af, ag, ao, cn, hn;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      ai.v[j] = sigmoidf_(gi.v[j]);
+      af.v[j] = sigmoidf_(gf.v[j]);
+      ag.v[j] = tanhf(gg.v[j]);
+      ao.v[j] = sigmoidf_(go.v[j]);
+      cn.v[j] = af.v[j] * cp.v[j] + ai.v[j] * ag.v[j];
+      hn.v[j] = ao.v[j] * tanhf(cn.v[j]);
+    }
+    if (acts) {
+      T* ap = acts + row * 4 * C + c;
+      st4(ap, ai); st4(ap + C, af); st4(ap + 2 * C, ag); st4(ap + 3 * C, ao);
+    }
+    st4(c_out + row * C + c, cn);
+    st4(h_out + row * C + c, hn);
+  }
+}
+
+template <typename T>
+__global__ void lstm_cell_bwd_kernel(const float* __restrict__ dh, float* dc, const T* __restrict__ acts,
+                                     const float* __restrict__ c_prev, const float* __restrict__ c_cur, T* dgates, long long R,
+                                     int C, long long total_vec) {
+  const int CVn = C / 4;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total_vec; i += (long long)gridDim.x * blockDim.x) {
+    const long long row = i / CVn;
+    const int c = (int)(i - row * CVn) * 4;
+    const T* ap = acts + row * 4 * C + c;
+    const f4 ai = ld4(ap), af = ld4(ap + C), ag = ld4(ap + 2 * C), ao = ld4(ap + 3 * C);
+    const f4 vdh = ld4(dh + row * C + c), vdc = ld4(dc + row * C + c), cc = ld4(c_cur + row * C + c);
+    f4 cp{{0.f, 0.f, 0.f, 0.f}};
+    if (c_prev) cp = ld4(c_prev + row * C + c);
+    f4 di, df, dg, dO, dcp;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float tc = tanhf(cc.v[j]);
+      dO.v[j] = vdh.v[j] * tc * ao.v[j] * (1.f - ao.v[j]);
+      const float dct = vdc.v[j] + vdh.v[j] * ao.v[j] * (1.f - tc * tc);
+      di.v[j] = dct * ag.v[j] * ai.v[j] * (1.f - ai.v[j]);
+      df.v[j] = dct * cp.v[j] * af.v[j] * (1.f - af.v[j]);
+      dg.v[j] = dct * ai.v[j] * (1.f - ag.v[j] * ag.v[j]);
+      dcp.v[j] = dct * af.v[j];
+    }
+    T* gp = dgates + row * 4 * C + c;
+    st4(gp, di); st4(gp + C, df); st4(gp + 2 * C, dg); st4(gp + 3 * C, dO);
+    st4(dc + row * C + c, dcp);
+  }
+}
+
+// =================================================================================================
+// layout adapters
+// =================================================================================================
+template <typename T>
+__global__ void pack_series_kernel(const float* __restrict__ x, T* __restrict__ y, int B, int Tn, int C, int H, int W,
+                                   long long total) {
+  // destination order (t, b, yy, xx, c)
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C);
+    long long r = i / C;
+    const int xx = (int)(r % W); r /= W;
+    const int yy = (int)(r % H); r /= H;
+    const int b = (int)(r % B);
+    const int t = (int)(r / B);
+    st1(y + i, x[((((long long)b * Tn + t) * C + c) * H + yy) * W + xx]);
+  }
+}
+
+template <typename T>
+__global__ void nhwc_to_nchw_kernel(const T* __restrict__ y, float* __restrict__ out, int N, int HW, int C, long long total) {
+  // destination order (n, c, p): coalesced writes
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int p = (int)(i % HW);
+    long long r = i / HW;
+    const int c = (int)(r % C);
+    const long long n = r / C;
+    out[i] = ld1(y + (n * HW + p) * C + c);
+  }
+}
+
+template <typename T>
+__global__ void nchw_to_nhwc_kernel(const float* __restrict__ g, T* __restrict__ out, int N, int HW, int C, long long total) {
+  // destination order (n, p, c)
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C);
+    long long r = i / C;
+    const int p = (int)(r % HW);
+    const long long n = r / HW;
+    st1(out + i, g[(n * C + c) * HW + p]);
+  }
+}
+
+template <typename T>
+__global__ void add_inplace_kernel(T* __restrict__ d, const T* __restrict__ s, long long n) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    st1(d + i, ld1(d + i) + ld1(s + i));
+}
+
+template <typename TS, typename TD>
+__global__ void cast_kernel(const TS* __restrict__ s, TD* __restrict__ d, long long n) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    st1(d + i, ld1(s + i));
+}
+
+}  // namespace stfb
+
+using namespace stfb;
+
+#define DT_OK(d) ((d) == STFB_F32 || (d) == STFB_BF16)
+#define DISPATCH_T(dtype, ...)                                   \
+  do {                                                           \
+    if ((dtype) == STFB_F32) { using T = float; __VA_ARGS__; }   \
+    else { using T = __nv_bfloat16; __VA_ARGS__; }               \
+  } while (0)
+
+static bool vec4_ok(int C, int dtype, std::initializer_list<const void*> ptrs) {
+  if (C % 4 != 0) return false;
+  const int b = dtype == STFB_BF16 ? 8 : 16;
+  for (const void* p : ptrs)
+    if (p && !aligned_to(p, b)) return false;
+  return true;
+}
+
+extern "C" int stfb_bn_stats(const void* x, double* sums, int G, long long R, int C, int dtype, void* stream) {
+  STFB_REQUIRE(x && sums && G > 0 && R >= 0 && C > 0 && DT_OK(dtype), "bn_stats: bad arguments");
+  STFB_DEVICE_OR_RETURN();
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  cudaMemsetAsync(sums, 0, sizeof(double) * 2 * G * C, s);
+  ColRedArgs A{};
+  A.a = x; A.out = sums; A.G = G; A.R = R; A.C = C;
+  return launch_colreduce<0>(A, dtype, vec4_ok(C, dtype, {x}), s, "bn_stats");
+}
+
+extern "C" int stfb_bn_finalize_train(const double* sums, const float* gamma, const float* beta, float* running_mean,
+                                      float* running_var, long long* nbt, float* scale, float* shift, float* mean,
+                                      float* invstd, int G, long long R, int C, float eps, float momentum, void* stream) {
+  STFB_REQUIRE(sums && gamma && beta && scale && shift && mean && invstd && G > 0 && R > 0 && C > 0, "bn_finalize_train: bad arguments");
+  STFB_DEVICE_OR_RETURN();
+  bn_finalize_train_kernel<<<ceil_div(C, 128), 128, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      sums, gamma, beta, running_mean, running_var, nbt, scale, shift, mean, invstd, G, R, C, eps, momentum);
+  return post_launch("bn_finalize_train");
+}
+
+extern "C" int stfb_bn_fold_eval(const float* gamma, const float* beta, const float* rm, const float* rv, float* scale,
+                                 float* shift, int C, float eps, void* stream) {
+  STFB_REQUIRE(gamma && beta && rm && rv && scale && shift && C > 0, "bn_fold_eval: bad arguments");
+  STFB_DEVICE_OR_RETURN();
+  bn_fold_eval_kernel<<<ceil_div(C, 128), 128, 0, reinterpret_cast<cudaStream_t>(stream)>>>(gamma, beta, rm, rv, scale, shift, C, eps);
+  return post_launch("bn_fold_eval");
+}
+
+extern "C" int stfb_bn_apply(const void* x, const float* scale, const float* shift, const void* residual, void* y, int G,
+                             long long R, int C, int relu, int dtype, void* stream) {
+  STFB_REQUIRE(x && scale && shift && y && G > 0 && R >= 0 && C > 0 && DT_OK(dtype), "bn_apply: bad arguments");
+  STFB_DEVICE_OR_RETURN();
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  const long long rows = (long long)G * R;
+  if (rows == 0) return STFB_OK;
+  const bool v = vec4_ok(C, dtype, {x, residual, y}) && aligned_to(scale, 16) && aligned_to(shift, 16);
+  const long long tv = rows * (C / (v ? 4 : 1));
+  DISPATCH_T(dtype, {
+    if (v) bn_apply_kernel<T, 4><<<grid_for(tv), 256, 0, s>>>((const T*)x, scale, shift, (const T*)residual, (T*)y, R, C, tv, relu);
+    else bn_apply_kernel<T, 1><<<grid_for(tv), 256, 0, s>>>((const T*)x, scale, shift, (const T*)residual, (T*)y, R, C, tv, relu);
+  });
+  return post_launch("bn_apply");
+}
+
+extern "C" int stfb_bn_bwd_reduce(const void* dy, const void* y, const void* x, const float* mean, const float* invstd,
+                                  double* red, int G, long long R, int C, int relu, int dtype, void* stream) {
+  STFB_REQUIRE(dy && x && mean && invstd && red && G > 0 && R >= 0 && C > 0 && DT_OK(dtype), "bn_bwd_reduce: bad arguments");
+  STFB_REQUIRE(!relu || y, "bn_bwd_reduce: relu needs y");
+  STFB_DEVICE_OR_RETURN();
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  cudaMemsetAsync(red, 0, sizeof(double) * 2 * G * C, s);
+  ColRedArgs A{};
+  A.a = dy; A.b = y; A.c = x; A.mean = mean; A.invstd = invstd; A.out = red; A.G = G; A.R = R; A.C = C; A.relu = relu;
+  return launch_colreduce<1>(A, dtype, vec4_ok(C, dtype, {dy, y, x}), s, "bn_bwd_reduce");
+}
+
+extern "C" int stfb_bn_bwd_finalize(const double* red, const float* gamma, const float* invstd, float* dgamma, float* dbeta,
+                                    float* coef, int G, long long R, int C, void* stream) {
+  STFB_REQUIRE(red && gamma && invstd && coef && G > 0 && R > 0 && C > 0, "bn_bwd_finalize: bad arguments");
+  STFB_DEVICE_OR_RETURN();
+  bn_bwd_finalize_kernel<<<ceil_div(C, 128), 128, 0, reinterpret_cast<cudaStream_t>(stream)>>>(red, gamma, invstd, dgamma, dbeta, coef, G, R, C);
+  return post_launch("bn_bwd_finalize");
+}
+
+extern "C" int stfb_bn_bwd_apply(const void* dy, const void* y, const void* x, const float* mean, const float* invstd,
+                                 const float* coef, void* dx, void* dres, int accum_dres, int G, long long R, int C, int relu,
+                                 int dtype, void* stream) {
+  STFB_REQUIRE(dy && x && mean && invstd && coef && dx && G > 0 && R >= 0 && C > 0 && DT_OK(dtype), "bn_bwd_apply: bad arguments");
+  STFB_REQUIRE(!relu || y, "bn_bwd_apply: relu needs y");
+  STFB_DEVICE_OR_RETURN();
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  const long long rows = (long long)G * R;
+  if (rows == 0) return STFB_OK;
+  const bool v = vec4_ok(C, dtype, {dy, y, x, dx, dres});
+  const long long tv = rows * (C / (v ? 4 : 1));
+  DISPATCH_T(dtype, {
+    if (v) bn_bwd_apply_kernel<T, 4><<<grid_for(tv), 256, 0, s>>>((const T*)dy, (const T*)y, (const T*)x, mean, invstd, coef, (T*)dx, (T*)dres, R, C, tv, relu, accum_dres);
+    else bn_bwd_apply_kernel<T, 1><<<grid_for(tv), 256, 0, s>>>((const T*)dy, (const T*)y, (const T*)x, mean, invstd, coef, (T*)dx, (T*)dres, R, C, tv, relu, accum_dres);
+  });
+  return post_launch("bn_bwd_apply");
+}
+
+extern "C" int stfb_colsum(const void* x, float* out, long long R, int C, int dtype, void* stream) {
+  STFB_REQUIRE(x && out && R >= 0 && C > 0 && DT_OK(dtype), "colsum: bad arguments");
+  STFB_DEVICE_OR_RETURN();
+  ColRedArgs A{};
+  A.a = x; A.outf = out; A.G = 1; A.R = R; A.C = C;
+  return launch_colreduce<2>(A, dtype, vec4_ok(C, dtype, {x}), reinterpret_cast<cudaStream_t>(stream), "colsum");
+}
+
+extern "C" int stfb_maxpool_fwd(const void* x, void* y, int N, int H, int W, int C, int Ho, int Wo, int k, int stride, int pad,
+                                int dtype, void* stream) {
+  STFB_REQUIRE(x && y && N >= 0 && H > 0 && W > 0 && C > 0 && k > 0 && stride > 0 && pad >= 0 && 2 * pad <= k && DT_OK(dtype), "maxpool_fwd: bad arguments");
+  STFB_REQUIRE(Ho == (H + 2 * pad - k) / stride + 1 && Wo == (W + 2 * pad - k) / stride + 1, "maxpool_fwd: bad output size");
+  STFB_DEVICE_OR_RETURN();
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  const bool v = vec4_ok(C, dtype, {x, y});
+  const long long tv = (long long)N * Ho * Wo * (C / (v ? 4 : 1));
+  if (tv == 0) return STFB_OK;
+  DISPATCH_T(dtype, {
+    if (v) maxpool_fwd_kernel<T, 4><<<grid_for(tv), 256, 0, s>>>((const T*)x, (T*)y, N, H, W, C, Ho, Wo, k, stride, pad, tv);
+    else maxpool_fwd_kernel<T, 1><<<grid_for(tv), 256, 0, s>>>((const T*)x, (T*)y, N, H, W, C, Ho, Wo, k, stride, pad, tv);
+  });
+  return post_launch("maxpool_fwd");
+}
+
+extern "C" int stfb_maxpool_bwd(const void* x, const void* dy, void* dx, int N, int H, int W, int C, int Ho, int Wo, int k,
+                                int stride, int pad, int dtype, void* stream) {
+  STFB_REQUIRE(x && dy && dx && N >= 0 && H > 0 && W > 0 && C > 0 && k > 0 && stride > 0 && pad >= 0 && DT_OK(dtype), "maxpool_bwd: bad arguments");
+  STFB_DEVICE_OR_RETURN();
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  const bool v = vec4_ok(C, dtype, {x, dy, dx});
+  const long long tv = (long long)N * H * W * (C / (v ? 4 : 1));
+  if (tv == 0) return STFB_OK;
+  DISPATCH_T(dtype, {
+    if (v) maxpool_bwd_kernel<T, 4><<<grid_for(tv), 256, 0, s>>>((const T*)x, (const T*)dy, (T*)dx, N, H, W, C, Ho, Wo, k, stride, pad, tv);
+    else maxpool_bwd_kernel<T, 1><<<grid_for(tv), 256, 0, s>>>((const T*)x, (const T*)dy, (T*)dx, N, H, W, C, Ho, Wo, k, stride, pad, tv);
+  });
+  return post_launch("maxpool_bwd");
+}
+
+extern "C" int stfb_bilinear_fwd(const void* x, void* y, int N, int H, int W, int C, int Ho, int Wo, int dtype, void* stream) {
+  STFB_REQUIRE(x && y && N >= 0 && H > 0 && W > 0 && C > 0 && Ho > 0 && Wo > 0 && DT_OK(dtype), "bilinear_fwd: bad arguments");
+  STFB_DEVICE_OR_RETURN();
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  const float sy = Ho > 1 ? (float)(H - 1) / (float)(Ho - 1) : 0.f, sx = Wo > 1 ? (float)(W - 1) / (float)(Wo - 1) : 0.f;
+  const long long total = (long long)N * Ho * Wo * C;
+  if (total == 0) return STFB_OK;
+  DISPATCH_T(dtype, { bilinear_fwd_kernel<T><<<grid_for(total), 256, 0, s>>>((const T*)x, (T*)y, N, H, W, C, Ho, Wo, sy, sx, total); });
+  return post_launch("bilinear_fwd");
+}
+
+extern "C" int stfb_bilinear_bwd(const void* dy, float* dx, int N, int H, int W, int C, int Ho, int Wo, int dtype, void* stream) {
+  STFB_REQUIRE(dy && dx && N >= 0 && H > 0 && W > 0 && C > 0 && Ho > 0 && Wo > 0 && DT_OK(dtype), "bilinear_bwd: bad arguments");
+  STFB_DEVICE_OR_RETURN();
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  const float sy = Ho > 1 ? (float)(H - 1) / (float)(Ho - 1) : 0.f, sx = Wo > 1 ? (float)(W - 1) / (float)(Wo - 1) : 0.f;
+  const long long total = (long long)N * Ho * Wo * C;
+  if (total == 0) return STFB_OK;
+  DISPATCH_T(dtype, { bilinear_bwd_kernel<T><<<grid_for(total), 256, 0, s>>>((const T*)dy, dx, N, H, W, C, Ho, Wo, sy, sx, total); });
+  return post_launch("bilinear_bwd");
+}
+
+extern "C" int stfb_lstm_cell_fwd(const float* gates, const float* c_prev, void* acts, float* c_out, void* h_out, long long R,
+                                  int C, int dtype, void* stream) {
+  STFB_REQUIRE(gates && c_out && h_out && R >= 0 && C > 0 && C % 4 == 0 && DT_OK(dtype), "lstm_cell_fwd: bad arguments (C %% 4 == 0 required)");
+  STFB_DEVICE_OR_RETURN();
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  const long long tv = R * (C / 4);
+  if (tv == 0) return STFB_OK;
+  DISPATCH_T(dtype, { lstm_cell_fwd_kernel<T><<<grid_for(tv), 256, 0, s>>>(gates, c_prev, (T*)acts, c_out, (T*)h_out, R, C, tv); });
+  return post_launch("lstm_cell_fwd");
+}
+
+extern "C" int stfb_lstm_cell_bwd(const float* dh, float* dc, const void* acts, const float* c_prev, const float* c_cur,
+                                  void* dgates, long long R, int C, int dtype, void* stream) {
+  STFB_REQUIRE(dh && dc && acts && c_cur && dgates && R >= 0 && C > 0 && C % 4 == 0 && DT_OK(dtype), "lstm_cell_bwd: bad arguments");
+  STFB_DEVICE_OR_RETURN();
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  const long long tv = R * (C / 4);
+  if (tv == 0) return STFB_OK;
+  DISPATCH_T(dtype, { lstm_cell_bwd_kernel<T><<<grid_for(tv), 256, 0, s>>>(dh, dc, (const T*)acts, c_prev, c_cur, (T*)dgates, R, C, tv); });
+  return post_launch("lstm_cell_bwd");
+}
+
+extern "C" int stfb_pack_series(const float* x, void* y, int B, int T_, int C, int H, int W, int dtype, void* stream) {
+  STFB_REQUIRE(x && y && B >= 0 && T_ > 0 && C > 0 && H > 0 && W > 0 && DT_OK(dtype), "pack_series: bad arguments");
+  STFB_DEVICE_OR_RETURN();
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  const long long total = (long long)B * T_ * C * H * W;
+  if (total == 0) return STFB_OK;
+  DISPATCH_T(dtype, { pack_series_kernel<T><<<grid_for(total), 256, 0, s>>>(x, (T*)y, B, T_, C, H, W, total); });
+  return post_launch("pack_series");
+}
+
+extern "C" int stfb_nhwc_to_nchw(const void* y, float* out, int N, int H, int W, int C, int dtype, void* stream) {
+  STFB_REQUIRE(y && out && N >= 0 && H > 0 && W > 0 && C > 0 && DT_OK(dtype), "nhwc_to_nchw: bad arguments");
+  STFB_DEVICE_OR_RETURN();
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  const long long total = (long long)N * H * W * C;
+  if (total == 0) return STFB_OK;
+  DISPATCH_T(dtype, { nhwc_to_nchw_kernel<T><<<grid_for(total), 256, 0, s>>>((const T*)y, out, N, H * W, C, total); });
+  return post_launch("nhwc_to_nchw");
+}
+
+extern "C" int stfb_nchw_to_nhwc(const float* g, void* out, int N, int H, int W, int C, int dtype, void* stream) {
+  STFB_REQUIRE(g && out && N >= 0 && H > 0 && W > 0 && C > 0 && DT_OK(dtype), "nchw_to_nhwc: bad arguments");
+  STFB_DEVICE_OR_RETURN();
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  const long long total = (long long)N * H * W * C;
+  if (total == 0) return STFB_OK;
+  DISPATCH_T(dtype, { nchw_to_nhwc_kernel<T><<<grid_for(total), 256, 0, s>>>(g, (T*)out, N, H * W, C, total); });
+  return post_launch("nchw_to_nhwc");
+}
+
+extern "C" int stfb_cast(const void* src, int sd, void* dst, int dd, long long n, void* stream) {
+  STFB_REQUIRE(src && dst && n >= 0 && DT_OK(sd) && DT_OK(dd), "cast: bad arguments");
+  STFB_DEVICE_OR_RETURN();
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  if (n == 0) return STFB_OK;
+  const int g = grid_for(n);
+  if (sd == STFB_F32 && dd == STFB_BF16) cast_kernel<float, __nv_bfloat16><<<g, 256, 0, s>>>((const float*)src, (__nv_bfloat16*)dst, n);
+  else if (sd == STFB_BF16 && dd == STFB_F32) cast_kernel<__nv_bfloat16, float><<<g, 256, 0, s>>>((const __nv_bfloat16*)src, (float*)dst, n);
+  else if (sd == STFB_F32) cast_kernel<float, float><<<g, 256, 0, s>>>((const float*)src, (float*)dst, n);
+  else cast_kernel<__nv_bfloat16, __nv_bfloat16><<<g, 256, 0, s>>>((const __nv_bfloat16*)src, (__nv_bfloat16*)dst, n);
+  return post_launch("cast");
+}
+
+extern "C" int stfb_add_inplace(void* dst, const void* src, long long n, int dtype, void* stream) {
+  STFB_REQUIRE(dst && src && n >= 0 && DT_OK(dtype), "add_inplace: bad arguments");
+  STFB_DEVICE_OR_RETURN();
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  if (n == 0) return STFB_OK;
+  DISPATCH_T(dtype, { add_inplace_kernel<T><<<grid_for(n), 256, 0, s>>>((T*)dst, (const T*)src, n); });
+  return post_launch("add_inplace");
+}

@@ -1,0 +1,527 @@
+// fp32-FFMA implicit-GEMM convolution family (forward gather, transposed gather, weight gradient).
+//
+// This is the fp32-accurate kernel family (north_star: fp32 logits rel-err <= 1e-4 cannot ride bf16
+// tensor cores) and the catch-all for shapes the tcgen05 family does not take (7x7 stem with Cin=1,
+// stride-2 convs, transposed convs, Cout=2 head).  Activations NHWC, fp32 accumulate, fused epilogue.
+#include "common.cuh"
+
+namespace stfb {
+
+constexpr int BM = 128;   // output pixels per CTA
+constexpr int BK = 16;    // reduction slice
+constexpr int NTHREADS = 256;
+
+struct ConvArgs {
+  stfb_conv_params p;
+  long long M;   // N*Ho*Wo
+  int Cin;       // C1 + C2
+  int Ktot;      // kh*kw*Cin
+  int fastA;     // 16-channel slices never straddle a tap / source and are 16B-aligned
+  int vecB;      // weight rows can be read 4 at a time
+  int vecY;      // outputs can be written 4 at a time
+};
+
+template <typename TI, typename TO, int TN>
+__global__ void __launch_bounds__(NTHREADS) igemm_simt_kernel(const ConvArgs a) {
+  constexpr int BN = 16 * TN;
+  __shared__ __align__(16) float As[2][BK][BM];
+  __shared__ __align__(16) float Bs[2][BK][BN];
+
+  const stfb_conv_params& p = a.p;
+  const int tid = threadIdx.x;
+  const long long m0 = (long long)blockIdx.x * BM;
+  const int n0 = blockIdx.y * BN;
+  const int tn = tid % 16, tm = tid / 16;
+
+  // ---- A loader: row r of the tile, 8 consecutive k ----
+  const int ar = tid % BM, ah = tid / BM;
+  const long long am = m0 + ar;
+  const bool arow_ok = am < a.M;
+  int an = 0, aoy = 0, aox = 0;
+  if (arow_ok) {
+    const int hw = p.Ho * p.Wo;
+    an = (int)(am / hw);
+    const int rem = (int)(am - (long long)an * hw);
+    aoy = rem / p.Wo;
+    aox = rem - aoy * p.Wo;
+  }
+  const TI* __restrict__ x1 = reinterpret_cast<const TI*>(p.x);
+  const TI* __restrict__ x2 = reinterpret_cast<const TI*>(p.x2);
+  const TI* __restrict__ wp = reinterpret_cast<const TI*>(p.w);
+
+  // ---- B loader: row kk, TN consecutive columns ----
+  const int bk = tid / 16, bn = (tid % 16) * TN;
+
+  float areg[8];
+  float breg[TN];
+
+  auto gather_coords = [&](int ky, int kx, int& iy, int& ix) -> bool {
+    if (p.mode == STFB_CONV_FWD) {
+      iy = aoy * p.stride - p.pad + ky;
+      ix = aox * p.stride - p.pad + kx;
+      return iy >= 0 && iy < p.H && ix >= 0 && ix < p.W;
+    } else {
+      const int ty = aoy + p.pad - ky, tx = aox + p.pad - kx;
+      if (ty < 0 || tx < 0) return false;
+      iy = ty / p.stride;
+      ix = tx / p.stride;
+      return (iy * p.stride == ty) && (ix * p.stride == tx) && iy < p.H && ix < p.W;
+    }
+  };
+
+  auto load_tiles = [&](int kt) {
+    const int k0 = kt * BK;
+    // A
+    if (a.fastA) {
+      const int tap = k0 / a.Cin, ci0 = k0 - tap * a.Cin + ah * 8;
+      const int ky = tap / p.kw, kx = tap - ky * p.kw;
+      int iy, ix;
+      bool ok = arow_ok && gather_coords(ky, kx, iy, ix);
+      if (ok) {
+        const long long pix = ((long long)an * p.H + iy) * p.W + ix;
+        f8 v = (ci0 < p.C1) ? ld8(x1 + pix * p.C1 + ci0) : ld8(x2 + pix * p.C2 + (ci0 - p.C1));
+#pragma unroll
+        for (int j = 0; j < 8; ++j) areg[j] = v.v[j];
+      } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) areg[j] = 0.f;
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int k = k0 + ah * 8 + j;
+        float v = 0.f;
+        if (arow_ok && k < a.Ktot) {
+          const int tap = k / a.Cin, ci = k - tap * a.Cin;
+          const int ky = tap / p.kw, kx = tap - ky * p.kw;
+          int iy, ix;
+          if (gather_coords(ky, kx, iy, ix)) {
+            const long long pix = ((long long)an * p.H + iy) * p.W + ix;
+            v = (ci < p.C1) ? ld1(x1 + pix * p.C1 + ci) : ld1(x2 + pix * p.C2 + (ci - p.C1));
+          }
+        }
+        areg[j] = v;
+      }
+    }
+    // B
+    const int k = k0 + bk;
+    if (k < a.Ktot) {
+      const TI* row = wp + (long long)k * p.ldw + n0 + bn;
+      if (a.vecB && n0 + bn + TN <= p.Cout) {
+#pragma unroll
+        for (int j = 0; j < TN; j += 4) {
+          f4 v = ld4(row + j);
+          breg[j] = v.v[0]; breg[j + 1] = v.v[1]; breg[j + 2] = v.v[2]; breg[j + 3] = v.v[3];
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < TN; ++j) breg[j] = (n0 + bn + j < p.Cout) ? ld1(row + j) : 0.f;
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < TN; ++j) breg[j] = 0.f;
+    }
+  };
+  auto store_tiles = [&](int buf) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) As[buf][ah * 8 + j][ar] = areg[j];
+#pragma unroll
+    for (int j = 0; j < TN; ++j) Bs[buf][bk][bn + j] = breg[j];
+  };
+
+  float acc[8][TN];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < TN; ++j) acc[i][j] = 0.f;
+
+  const int nk = (a.Ktot + BK - 1) / BK;
+  load_tiles(0);
+  store_tiles(0);
+  __syncthreads();
+  for (int kt = 0; kt < nk; ++kt) {
+    const int buf = kt & 1;
+    if (kt + 1 < nk) load_tiles(kt + 1);
+#pragma unroll
+    for (int kk = 0; kk < BK; ++kk) {
+      float av[8], bv[TN];
+      const float4 a0 = *reinterpret_cast<const float4*>(&As[buf][kk][tm * 8]);
+      const float4 a1 = *reinterpret_cast<const float4*>(&As[buf][kk][tm * 8 + 4]);
+      av[0] = a0.x; av[1] = a0.y; av[2] = a0.z; av[3] = a0.w;
+      av[4] = a1.x; av[5] = a1.y; av[6] = a1.z; av[7] = a1.w;
+#pragma unroll
+      for (int j = 0; j < TN; j += 4) {
+        const float4 b0 = *reinterpret_cast<const float4*>(&Bs[buf][kk][tn * TN + j]);
+        bv[j] = b0.x; bv[j + 1] = b0.y; bv[j + 2] = b0.z; bv[j + 3] = b0.w;
+      }
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < TN; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+    }
+    if (kt + 1 < nk) store_tiles(buf ^ 1);
+    __syncthreads();
+  }
+
+  // ---- fused epilogue ----
+  TO* __restrict__ y = reinterpret_cast<TO*>(p.y);
+  const TO* res = reinterpret_cast<const TO*>(p.residual);
+  const int c0 = n0 + tn * TN;
+  float cb[TN], cs[TN], ct[TN];
+#pragma unroll
+  for (int j = 0; j < TN; ++j) {
+    const int c = c0 + j;
+    const bool ok = c < p.Cout;
+    cb[j] = 0.f;
+    if (ok && p.bias) cb[j] += p.bias[c];
+    if (ok && p.bias2) cb[j] += p.bias2[c];
+    cs[j] = (ok && p.scale) ? p.scale[c] : 1.f;
+    ct[j] = (ok && p.shift) ? p.shift[c] : 0.f;
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const long long m = m0 + tm * 8 + i;
+    if (m >= a.M) continue;
+    const long long off = m * p.Cout + c0;
+    if (a.vecY && c0 + TN <= p.Cout) {
+#pragma unroll
+      for (int j = 0; j < TN; j += 4) {
+        f4 v;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) v.v[q] = (acc[i][j + q] + cb[j + q]) * cs[j + q] + ct[j + q];
+        if (res) {
+          f4 r = ld4(res + off + j);
+#pragma unroll
+          for (int q = 0; q < 4; ++q) v.v[q] += r.v[q];
+        }
+        if (p.relu) {
+#pragma unroll
+          for (int q = 0; q < 4; ++q) v.v[q] = fmaxf(v.v[q], 0.f);
+        }
+        st4(y + off + j, v);
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < TN; ++j) {
+        if (c0 + j < p.Cout) {
+          float v = (acc[i][j] + cb[j]) * cs[j] + ct[j];
+          if (res) v += ld1(res + off + j);
+          if (p.relu) v = fmaxf(v, 0.f);
+          st1(y + off + j, v);
+        }
+      }
+    }
+  }
+}
+
+template <typename TI, typename TO>
+static int launch_igemm(const ConvArgs& a, cudaStream_t st) {
+  const stfb_conv_params& p = a.p;
+  const long long mtiles = (a.M + BM - 1) / BM;
+  if (mtiles > 2147483647LL) { set_error("conv2d: too many output pixels"); return STFB_EINVAL; }
+  // wide tile only when it still fills the machine
+  const bool wide = p.Cout >= 128 && mtiles * ((p.Cout + 127) / 128) >= 2LL * num_sms();
+  if (wide) {
+    dim3 grid((unsigned)mtiles, (unsigned)((p.Cout + 127) / 128));
+    igemm_simt_kernel<TI, TO, 8><<<grid, NTHREADS, 0, st>>>(a);
+  } else {
+    dim3 grid((unsigned)mtiles, (unsigned)((p.Cout + 63) / 64));
+    igemm_simt_kernel<TI, TO, 4><<<grid, NTHREADS, 0, st>>>(a);
+  }
+  return post_launch("conv2d(simt)");
+}
+
+int conv2d_simt(const stfb_conv_params* p, cudaStream_t st) {
+  ConvArgs a;
+  a.p = *p;
+  a.M = (long long)p->N * p->Ho * p->Wo;
+  a.Cin = p->C1 + p->C2;
+  a.Ktot = p->kh * p->kw * a.Cin;
+  const int esz = p->x_dtype == STFB_BF16 ? 2 : 4;
+  auto aligned = [](const void* q, int b) { return (reinterpret_cast<uintptr_t>(q) % b) == 0; };
+  a.fastA = (a.Cin % 16 == 0) && (p->C1 % 16 == 0) && (p->C2 % 8 == 0) && aligned(p->x, 16) &&
+            (p->x2 == nullptr || aligned(p->x2, 16));
+  a.vecB = (p->ldw % 4 == 0) && aligned(p->w, 4 * esz);
+  const int ysz = p->y_dtype == STFB_BF16 ? 2 : 4;
+  a.vecY = (p->Cout % 4 == 0) && aligned(p->y, 4 * ysz) && (p->residual == nullptr || aligned(p->residual, 4 * ysz));
+  if (a.M == 0) return STFB_OK;
+  if (p->x_dtype == STFB_F32 && p->y_dtype == STFB_F32) return launch_igemm<float, float>(a, st);
+  if (p->x_dtype == STFB_BF16 && p->y_dtype == STFB_BF16) return launch_igemm<__nv_bfloat16, __nv_bfloat16>(a, st);
+  if (p->x_dtype == STFB_BF16 && p->y_dtype == STFB_F32) return launch_igemm<__nv_bfloat16, float>(a, st);
+  set_error("conv2d: unsupported dtype pair (%d,%d)", p->x_dtype, p->y_dtype);
+  return STFB_EINVAL;
+}
+
+// =================================================================================================
+// weight gradient: dW[cp][cg_off+cg][ky][kx] += sum_pix P[pix,cp] * G[gather(pix,ky,kx), cg]
+// GEMM view: rows = kg = (ky,kx,cg) (BM=128), cols = cp (BN=64), reduction over pixels (BK=16), split over
+// gridDim.z with fp32 atomics into the reference-layout gradient.
+// =================================================================================================
+struct WgradArgs {
+  const void* P;
+  const void* G;
+  float* dW;
+  int N, Hp, Wp, Cp, Hg, Wg, Cg, cg_off, cg_total, kh, kw, stride, pad;
+  long long npix;        // N*Hp*Wp
+  long long chunk;       // pixels per z-slice (multiple of BK)
+  int Kg;                // kh*kw*Cg
+  int fastA;             // Cg % 8 == 0 and aligned
+  int vecB;              // Cp % 4 == 0 and aligned
+};
+
+template <typename T>
+__global__ void __launch_bounds__(NTHREADS) wgrad_simt_kernel(const WgradArgs a) {
+  constexpr int BN = 64, TN = 4;
+  __shared__ __align__(16) float As[2][BK][BM];
+  __shared__ __align__(16) float Bs[2][BK][BN];
+  const int tid = threadIdx.x;
+  const int kg0 = blockIdx.x * BM, cp0 = blockIdx.y * BN;
+  const long long pbeg = (long long)blockIdx.z * a.chunk;
+  const long long pend = min(a.npix, pbeg + a.chunk);
+  if (pbeg >= pend) return;
+  const int tn = tid % 16, tm = tid / 16;
+  const T* __restrict__ Pp = reinterpret_cast<const T*>(a.P);
+  const T* __restrict__ Gp = reinterpret_cast<const T*>(a.G);
+
+  const int pl = tid / 16;            // pixel lane within the slice (both loaders)
+  const int akg = kg0 + (tid % 16) * 8;
+  const int bcp = cp0 + (tid % 16) * 4;
+  // fast path: the 8 kg of this thread share a tap
+  int f_ky = 0, f_kx = 0, f_cg = 0;
+  const bool a_in = akg < a.Kg;
+  if (a.fastA && a_in) {
+    const int tap = akg / a.Cg;
+    f_cg = akg - tap * a.Cg;
+    f_ky = tap / a.kw;
+    f_kx = tap - f_ky * a.kw;
+  }
+  float areg[8], breg[4];
+  const int hw = a.Hp * a.Wp;
+
+  auto load_tiles = [&](long long p0) {
+    const long long pix = p0 + pl;
+    const bool pok = pix < pend;
+    int n = 0, py = 0, px = 0;
+    if (pok) {
+      n = (int)(pix / hw);
+      const int rem = (int)(pix - (long long)n * hw);
+      py = rem / a.Wp;
+      px = rem - py * a.Wp;
+    }
+    if (a.fastA) {
+      bool ok = pok && a_in;
+      int iy = 0, ix = 0;
+      if (ok) {
+        iy = py * a.stride - a.pad + f_ky;
+        ix = px * a.stride - a.pad + f_kx;
+        ok = iy >= 0 && iy < a.Hg && ix >= 0 && ix < a.Wg;
+      }
+      if (ok) {
+        f8 v = ld8(Gp + (((long long)n * a.Hg + iy) * a.Wg + ix) * a.Cg + f_cg);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) areg[j] = v.v[j];
+      } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) areg[j] = 0.f;
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        float v = 0.f;
+        const int kg = akg + j;
+        if (pok && kg < a.Kg) {
+          const int tap = kg / a.Cg, cg = kg - tap * a.Cg;
+          const int ky = tap / a.kw, kx = tap - ky * a.kw;
+          const int iy = py * a.stride - a.pad + ky, ix = px * a.stride - a.pad + kx;
+          if (iy >= 0 && iy < a.Hg && ix >= 0 && ix < a.Wg)
+            v = ld1(Gp + (((long long)n * a.Hg + iy) * a.Wg + ix) * a.Cg + cg);
+        }
+        areg[j] = v;
+      }
+    }
+    if (pok) {
+      const T* row = Pp + pix * a.Cp + bcp;
+      if (a.vecB && bcp + 4 <= a.Cp) {
+        f4 v = ld4(row);
+        breg[0] = v.v[0]; breg[1] = v.v[1]; breg[2] = v.v[2]; breg[3] = v.v[3];
+      } else {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) breg[j] = (bcp + j < a.Cp) ? ld1(row + j) : 0.f;
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) breg[j] = 0.f;
+    }
+  };
+  auto store_tiles = [&](int buf) {
+    *reinterpret_cast<float4*>(&As[buf][pl][(tid % 16) * 8]) = make_float4(areg[0], areg[1], areg[2], areg[3]);
+    *reinterpret_cast<float4*>(&As[buf][pl][(tid % 16) * 8 + 4]) = make_float4(areg[4], areg[5], areg[6], areg[7]);
+    *reinterpret_cast<float4*>(&Bs[buf][pl][(tid % 16) * 4]) = make_float4(breg[0], breg[1], breg[2], breg[3]);
+  };
+
+  float acc[8][TN];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < TN; ++j) acc[i][j] = 0.f;
+
+  const int nk = (int)((pend - pbeg + BK - 1) / BK);
+  load_tiles(pbeg);
+  store_tiles(0);
+  __syncthreads();
+  for (int kt = 0; kt < nk; ++kt) {
+    const int buf = kt & 1;
+    if (kt + 1 < nk) load_tiles(pbeg + (long long)(kt + 1) * BK);
+#pragma unroll
+    for (int kk = 0; kk < BK; ++kk) {
+      const float4 a0 = *reinterpret_cast<const float4*>(&As[buf][kk][tm * 8]);
+      const float4 a1 = *reinterpret_cast<const float4*>(&As[buf][kk][tm * 8 + 4]);
+      const float4 b0 = *reinterpret_cast<const float4*>(&Bs[buf][kk][tn * 4]);
+      const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+      const float bv[4] = {b0.x, b0.y, b0.z, b0.w};
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < TN; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+    }
+    if (kt + 1 < nk) store_tiles(buf ^ 1);
+    __syncthreads();
+  }
+
+  const int khw = a.kh * a.kw;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int kg = kg0 + tm * 8 + i;
+    if (kg >= a.Kg) continue;
+    const int tap = kg / a.Cg, cg = kg - tap * a.Cg;
+#pragma unroll
+    for (int j = 0; j < TN; ++j) {
+      const int cp = cp0 + tn * 4 + j;
+      if (cp < a.Cp) atomicAdd(a.dW + ((long long)cp * a.cg_total + a.cg_off + cg) * khw + tap, acc[i][j]);
+    }
+  }
+}
+
+int conv2d_wgrad_simt(const WgradArgs& a0, int dtype, cudaStream_t st) {
+  WgradArgs a = a0;
+  a.npix = (long long)a.N * a.Hp * a.Wp;
+  a.Kg = a.kh * a.kw * a.Cg;
+  if (a.npix == 0) return STFB_OK;
+  const int esz = dtype == STFB_BF16 ? 2 : 4;
+  auto aligned = [](const void* q, int b) { return (reinterpret_cast<uintptr_t>(q) % b) == 0; };
+  a.fastA = (a.Cg % 8 == 0) && aligned(a.G, 16);
+  a.vecB = (a.Cp % 4 == 0) && aligned(a.P, 4 * esz);
+  const int gx = (a.Kg + BM - 1) / BM, gy = (a.Cp + 63) / 64;
+  // split the pixel reduction until the grid covers ~4 waves, keeping >= 8 slices of work per CTA
+  long long want = (4LL * num_sms() + (long long)gx * gy - 1) / ((long long)gx * gy);
+  long long maxsplit = (a.npix + 8 * BK - 1) / (8 * BK);
+  long long splits = want < 1 ? 1 : want;
+  if (splits > maxsplit) splits = maxsplit;
+  if (splits > 65535) splits = 65535;
+  if (splits < 1) splits = 1;
+  long long chunk = (a.npix + splits - 1) / splits;
+  chunk = (chunk + BK - 1) / BK * BK;
+  splits = (a.npix + chunk - 1) / chunk;
+  a.chunk = chunk;
+  dim3 grid(gx, gy, (unsigned)splits);
+  if (dtype == STFB_F32) wgrad_simt_kernel<float><<<grid, NTHREADS, 0, st>>>(a);
+  else wgrad_simt_kernel<__nv_bfloat16><<<grid, NTHREADS, 0, st>>>(a);
+  return post_launch("conv2d_wgrad(simt)");
+}
+
+// =================================================================================================
+// weight packing
+// =================================================================================================
+template <typename T>
+__global__ void pack_weight_kernel(const float* __restrict__ w, T* __restrict__ wp, int D0, int D1, int khw,
+                                   int k_is_dim1) {
+  const long long total = (long long)D0 * D1 * khw;
+  const int Kc = k_is_dim1 ? D1 : D0, Nc = k_is_dim1 ? D0 : D1;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    // destination index i = (tap*Kc + k)*Nc + n   (coalesced writes)
+    const int n = (int)(i % Nc);
+    const long long r = i / Nc;
+    const int k = (int)(r % Kc);
+    const int tap = (int)(r / Kc);
+    const int d0 = k_is_dim1 ? n : k, d1 = k_is_dim1 ? k : n;
+    st1(wp + i, w[((long long)d0 * D1 + d1) * khw + tap]);
+  }
+}
+
+}  // namespace stfb
+
+using namespace stfb;
+
+namespace stfb { int conv2d_tcgen05(const stfb_conv_params* p, cudaStream_t st); int conv2d_tcgen05_supported(const stfb_conv_params* p); }
+
+static int validate_conv(const stfb_conv_params* p) {
+  STFB_REQUIRE(p != nullptr, "conv2d: null params");
+  STFB_REQUIRE(p->x && p->w && p->y, "conv2d: null x/w/y");
+  STFB_REQUIRE(p->N >= 0 && p->H > 0 && p->W > 0 && p->C1 > 0 && p->C2 >= 0 && p->Ho > 0 && p->Wo > 0 && p->Cout > 0,
+               "conv2d: bad dims N=%d H=%d W=%d C1=%d C2=%d Ho=%d Wo=%d Cout=%d", p->N, p->H, p->W, p->C1, p->C2, p->Ho,
+               p->Wo, p->Cout);
+  STFB_REQUIRE(p->C2 == 0 || p->x2 != nullptr, "conv2d: C2 > 0 needs x2");
+  STFB_REQUIRE(p->kh > 0 && p->kw > 0 && p->stride > 0 && p->pad >= 0, "conv2d: bad kernel geometry");
+  STFB_REQUIRE(p->ldw >= p->Cout, "conv2d: ldw (%d) < Cout (%d)", p->ldw, p->Cout);
+  STFB_REQUIRE(p->mode == STFB_CONV_FWD || p->mode == STFB_CONV_TRANSPOSED, "conv2d: bad mode %d", p->mode);
+  STFB_REQUIRE((p->scale == nullptr) == (p->shift == nullptr), "conv2d: scale and shift come together");
+  if (p->mode == STFB_CONV_FWD) {
+    STFB_REQUIRE(p->Ho == (p->H + 2 * p->pad - p->kh) / p->stride + 1 && p->Wo == (p->W + 2 * p->pad - p->kw) / p->stride + 1,
+                 "conv2d: output size %dx%d does not match floor((H+2p-k)/s)+1", p->Ho, p->Wo);
+  } else {
+    const int lo_h = (p->H - 1) * p->stride - 2 * p->pad + p->kh, lo_w = (p->W - 1) * p->stride - 2 * p->pad + p->kw;
+    STFB_REQUIRE(p->Ho >= lo_h && p->Ho < lo_h + p->stride && p->Wo >= lo_w && p->Wo < lo_w + p->stride,
+                 "conv2d(transposed): output size %dx%d outside [(H-1)s-2p+k, +stride)", p->Ho, p->Wo);
+  }
+  return STFB_OK;
+}
+
+extern "C" int stfb_conv2d_tcgen05_supported(const stfb_conv_params* p) {
+  if (validate_conv(p) != STFB_OK) return 0;
+  return stfb::conv2d_tcgen05_supported(p);
+}
+
+extern "C" int stfb_conv2d(const stfb_conv_params* p, void* stream) {
+  int st = validate_conv(p);
+  if (st != STFB_OK) return st;
+  STFB_DEVICE_OR_RETURN();
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  if (p->impl == STFB_IMPL_TCGEN05) {
+    if (!stfb::conv2d_tcgen05_supported(p)) {
+      set_error("conv2d: shape not supported by the tcgen05 family");
+      return STFB_ENOTSUP;
+    }
+    return stfb::conv2d_tcgen05(p, s);
+  }
+  if (p->impl == STFB_IMPL_AUTO && stfb::conv2d_tcgen05_supported(p)) return stfb::conv2d_tcgen05(p, s);
+  return conv2d_simt(p, s);
+}
+
+extern "C" int stfb_conv2d_wgrad(const void* P, const void* G, float* dW, int N, int Hp, int Wp, int Cp, int Hg, int Wg,
+                                 int Cg, int cg_off, int cg_total, int kh, int kw, int stride, int pad, int dtype,
+                                 void* stream) {
+  STFB_REQUIRE(P && G && dW, "conv2d_wgrad: null pointer");
+  STFB_REQUIRE(N >= 0 && Hp > 0 && Wp > 0 && Cp > 0 && Hg > 0 && Wg > 0 && Cg > 0 && kh > 0 && kw > 0 && stride > 0 && pad >= 0,
+               "conv2d_wgrad: bad dims");
+  STFB_REQUIRE(cg_off >= 0 && cg_off + Cg <= cg_total, "conv2d_wgrad: channel window [%d,%d) outside %d", cg_off, cg_off + Cg, cg_total);
+  STFB_REQUIRE(dtype == STFB_F32 || dtype == STFB_BF16, "conv2d_wgrad: bad dtype");
+  STFB_DEVICE_OR_RETURN();
+  WgradArgs a{};
+  a.P = P; a.G = G; a.dW = dW; a.N = N; a.Hp = Hp; a.Wp = Wp; a.Cp = Cp; a.Hg = Hg; a.Wg = Wg; a.Cg = Cg;
+  a.cg_off = cg_off; a.cg_total = cg_total; a.kh = kh; a.kw = kw; a.stride = stride; a.pad = pad;
+  return conv2d_wgrad_simt(a, dtype, reinterpret_cast<cudaStream_t>(stream));
+}
+
+extern "C" int stfb_pack_weight(const float* w, void* wp, int D0, int D1, int kh, int kw, int k_is_dim1, int dtype,
+                                void* stream) {
+  STFB_REQUIRE(w && wp && D0 > 0 && D1 > 0 && kh > 0 && kw > 0, "pack_weight: bad arguments");
+  STFB_REQUIRE(dtype == STFB_F32 || dtype == STFB_BF16, "pack_weight: bad dtype");
+  STFB_DEVICE_OR_RETURN();
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  const long long total = (long long)D0 * D1 * kh * kw;
+  int blocks = ceil_div(total, 256);
+  if (blocks > 8 * num_sms()) blocks = 8 * num_sms();
+  if (dtype == STFB_F32) pack_weight_kernel<float><<<blocks, 256, 0, s>>>(w, reinterpret_cast<float*>(wp), D0, D1, kh * kw, k_is_dim1);
+  else pack_weight_kernel<__nv_bfloat16><<<blocks, 256, 0, s>>>(w, reinterpret_cast<__nv_bfloat16*>(wp), D0, D1, kh * kw, k_is_dim1);
+  return post_launch("pack_weight");
+}

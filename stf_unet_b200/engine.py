@@ -1,0 +1,294 @@
+"""Execution engine of the hot path: a forward executor that records a backward tape.
+
+The reference leaves graph building to torch autograd, one node per library operator.  Here the whole model
+forward is ONE autograd node (see ``ModelFunction``); inside it every operator is a libstfb200 kernel launch and
+the backward pass is this module's own tape walked in reverse.  That keeps gradient accumulation fused into
+kernel epilogues (dgrad + residual add), puts the weight gradients straight into one flat fp32 buffer that the
+data-parallel all-reduce consumes, and makes the step capturable in a CUDA graph (no host syncs anywhere).
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Optional
+
+import torch
+
+from . import ops
+
+BN_EPS = 1e-5
+BN_MOMENTUM = 0.1
+
+
+class Var:
+    """An NHWC activation plus (during backward) its gradient."""
+    __slots__ = ("data", "grad", "needs_grad", "grad_dtype")
+
+    def __init__(self, data, needs_grad=True, grad_dtype=None):
+        self.data = data
+        self.grad = None
+        self.needs_grad = needs_grad
+        self.grad_dtype = grad_dtype or data.dtype
+
+    def accumulate(self, g):
+        if not self.needs_grad:
+            return
+        if g.dtype != self.grad_dtype:
+            g = ops.cast(g, self.grad_dtype)
+        if self.grad is None:
+            self.grad = g
+        else:
+            ops.add_(self.grad, g)
+
+
+class Executor:
+    """Runs layers on NHWC activations; when ``record`` is set every layer pushes its backward closure."""
+
+    def __init__(self, params: Dict[str, torch.Tensor], dtype: torch.dtype, train: bool, record: bool,
+                 grads: Optional[Dict[str, torch.Tensor]] = None):
+        self.params = params
+        self.dtype = dtype
+        self.train = train
+        self.record = record
+        self.grads = grads if grads is not None else {}
+        self.tape: List = []
+        self._packed = {}
+
+    # ---------------------------------------------------------------------------------------------
+    def packed(self, name, k_is_dim1):
+        key = (name, bool(k_is_dim1))
+        wp = self._packed.get(key)
+        if wp is None:
+            wp = ops.pack_weight(self.params[name], k_is_dim1, self.dtype)
+            self._packed[key] = wp
+        return wp
+
+    def wants_grad(self, name):
+        return name in self.grads
+
+    # ---------------------------------------------------------------------------------------------
+    def conv(self, x: Var, wname: str, *, k: int, stride: int = 1, pad: int = 0, transposed: bool = False,
+             out_pad: int = 0, bname: Optional[str] = None, x2: Optional[Var] = None, scale=None, shift=None,
+             residual=None, relu: bool = False, y_dtype=None) -> Var:
+        """Conv2d / ConvTranspose2d (+bias)(+folded BN)(+residual)(+ReLU).  The epilogue extras other than the
+        bias are inference-only (no backward through them)."""
+        w = self.params[wname]
+        Cout = w.shape[1] if transposed else w.shape[0]
+        N, H, W, C1 = x.data.shape
+        C2 = 0 if x2 is None else x2.data.shape[3]
+        assert not (transposed and x2 is not None)
+        mode = ops.CONV_TRANSPOSED if transposed else ops.CONV_FWD
+        out_hw = ops.conv_out_hw(H, W, k, stride, pad, transposed, out_pad)
+        wp = self.packed(wname, k_is_dim1=not transposed)
+        bias = self.params[bname] if bname else None
+        y = ops.conv2d(x.data, wp, Cout, k, stride, pad, mode=mode, out_hw=out_hw, x2=None if x2 is None else x2.data,
+                       bias=bias, scale=scale, shift=shift, residual=residual, relu=relu, y_dtype=y_dtype)
+        out = Var(y, grad_dtype=self.dtype)
+        if not self.record:
+            return out
+        assert scale is None and residual is None and not relu, "fused epilogue is inference-only"
+
+        def bwd():
+            dy = out.grad
+            out.grad = None
+            if dy is None:
+                return
+            rows = dy.shape[0] * dy.shape[1] * dy.shape[2]
+            if bname and self.wants_grad(bname):
+                ops.colsum(dy, self.grads[bname], rows, Cout)
+            if self.wants_grad(wname):
+                if not transposed:
+                    ops.conv2d_wgrad(dy, x.data, self.grads[wname], k, stride, pad, 0, C1 + C2)
+                    if x2 is not None:
+                        ops.conv2d_wgrad(dy, x2.data, self.grads[wname], k, stride, pad, C1, C1 + C2)
+                else:
+                    ops.conv2d_wgrad(x.data, dy, self.grads[wname], k, stride, pad, 0, Cout)
+            srcs = [(x, 0, C1)] + ([(x2, C1, C2)] if x2 is not None else [])
+            for src, off, csrc in srcs:
+                if not src.needs_grad:
+                    continue
+                wpd = self.packed(wname, k_is_dim1=transposed)
+                g = ops.conv2d(dy, wpd, csrc, k, stride, pad, mode=ops.CONV_FWD if transposed else ops.CONV_TRANSPOSED,
+                               out_hw=(H, W), residual=src.grad, out=src.grad, y_dtype=src.grad_dtype, ldw=C1 + C2,
+                               w_offset=off)
+                src.grad = g
+
+        self.tape.append(bwd)
+        return out
+
+    # ---------------------------------------------------------------------------------------------
+    def bn(self, x: Var, prefix: str, G: int, relu: bool, residual: Optional[Var] = None) -> Var:
+        """Train-mode BatchNorm2d over G row groups (+residual)(+ReLU)."""
+        N, H, W, C = x.data.shape
+        assert N % G == 0
+        R = (N // G) * H * W
+        P = self.params
+        sums = ops.bn_stats(x.data, G, R, C)
+        st = ops.bn_finalize_train(sums, P[prefix + ".weight"], P[prefix + ".bias"], P[prefix + ".running_mean"],
+                                   P[prefix + ".running_var"], P[prefix + ".num_batches_tracked"], G, R, C, BN_EPS,
+                                   BN_MOMENTUM)
+        y = ops.bn_apply(x.data, st[0], st[1], G, R, C, relu, None if residual is None else residual.data)
+        out = Var(y, grad_dtype=self.dtype)
+        if not self.record:
+            return out
+        mean, invstd = st[2], st[3]
+
+        def bwd():
+            dy = out.grad
+            out.grad = None
+            if dy is None:
+                return
+            gname, bname = prefix + ".weight", prefix + ".bias"
+            dgamma = self.grads.get(gname)
+            dbeta = self.grads.get(bname)
+            want_dres = residual is not None and residual.needs_grad
+            dx, dres = ops.bn_bwd(dy, y, x.data, mean, invstd, P[gname], dgamma, dbeta, G, R, C, relu, want_dres,
+                                  dres_acc=residual.grad if want_dres else None)
+            x.grad = dx
+            if want_dres:
+                residual.grad = dres
+
+        self.tape.append(bwd)
+        return out
+
+    def conv_bn(self, x: Var, wname: str, bnprefix: str, *, k: int, stride: int = 1, pad: int = 0, relu: bool = True,
+                residual: Optional[Var] = None, bname: Optional[str] = None, x2: Optional[Var] = None, G: int = 1) -> Var:
+        """conv -> BatchNorm -> (+residual) -> ReLU.  Eval: one fused launch with the BN folded into the epilogue."""
+        if self.train:
+            raw = self.conv(x, wname, k=k, stride=stride, pad=pad, bname=bname, x2=x2)
+            return self.bn(raw, bnprefix, G, relu, residual)
+        P = self.params
+        fold = ops.bn_fold_eval(P[bnprefix + ".weight"], P[bnprefix + ".bias"], P[bnprefix + ".running_mean"],
+                                P[bnprefix + ".running_var"], BN_EPS)
+        assert not self.record, "eval-mode BatchNorm has no backward in this engine"
+        return self.conv(x, wname, k=k, stride=stride, pad=pad, bname=bname, x2=x2, scale=fold[0], shift=fold[1],
+                         residual=None if residual is None else residual.data, relu=relu)
+
+    # ---------------------------------------------------------------------------------------------
+    def maxpool(self, x: Var, k: int, stride: int, pad: int) -> Var:
+        y = ops.maxpool_fwd(x.data, k, stride, pad)
+        out = Var(y, grad_dtype=self.dtype)
+        if self.record:
+            def bwd():
+                dy = out.grad
+                out.grad = None
+                if dy is not None and x.needs_grad:
+                    x.accumulate(ops.maxpool_bwd(x.data, dy, k, stride, pad))
+            self.tape.append(bwd)
+        return out
+
+    def resize(self, x: Var, Ho: int, Wo: int) -> Var:
+        """Bilinear, align_corners=True."""
+        N, H, W, C = x.data.shape
+        y = ops.bilinear_fwd(x.data, Ho, Wo)
+        out = Var(y, grad_dtype=self.dtype)
+        if self.record:
+            def bwd():
+                dy = out.grad
+                out.grad = None
+                if dy is not None and x.needs_grad:
+                    x.accumulate(ops.bilinear_bwd(dy, H, W))
+            self.tape.append(bwd)
+        return out
+
+    # ---------------------------------------------------------------------------------------------
+    def lstm_last(self, seq: Var, prefix: str, T: int) -> Var:
+        """Per-pixel nn.LSTM(C, C) over T time-major slabs of `seq` [T*B, h, w, C]; returns h_T [B, h, w, C]."""
+        TB, h, w, C = seq.data.shape
+        assert TB % T == 0
+        B = TB // T
+        R = B * h * w
+        P = self.params
+        dev = seq.data.device
+        wih, whh = prefix + ".weight_ih_l0", prefix + ".weight_hh_l0"
+        bih, bhh = prefix + ".bias_ih_l0", prefix + ".bias_hh_l0"
+        # hoisted input GEMM for all T: gates_x = X W_ih^T + b_ih + b_hh  (fp32 pre-activations)
+        gates = ops.conv2d(seq.data, self.packed(wih, True), 4 * C, 1, 1, 0, bias=P[bih], bias2=P[bhh],
+                           y_dtype=torch.float32)
+        gates = gates.view(T, B, h, w, 4 * C)
+        keep = self.record
+        acts = torch.empty((T, R, 4 * C), dtype=self.dtype, device=dev) if keep else None
+        cs = torch.empty((T if keep else 2, R, C), dtype=torch.float32, device=dev)
+        hs = torch.empty((T if keep else 2, B, h, w, C), dtype=self.dtype, device=dev)
+        whh_p = self.packed(whh, True)
+        for t in range(T):
+            cur = t if keep else t % 2
+            prev = (t - 1) if keep else (t - 1) % 2
+            if t > 0:  # gates_t += h_{t-1} W_hh^T   (in place through the residual epilogue)
+                ops.conv2d(hs[prev], whh_p, 4 * C, 1, 1, 0, residual=gates[t], out=gates[t], y_dtype=torch.float32)
+            ops.lstm_cell_fwd(gates[t], cs[prev] if t > 0 else None, acts[t] if keep else None, cs[cur], hs[cur], R, C)
+        last = (T - 1) if keep else (T - 1) % 2
+        out = Var(hs[last], grad_dtype=torch.float32)
+        if not self.record:
+            return out
+
+        def bwd():
+            dh = out.grad
+            out.grad = None
+            if dh is None:
+                return
+            dG = torch.empty((T, B, h, w, 4 * C), dtype=self.dtype, device=dev)
+            dc = torch.zeros((R, C), dtype=torch.float32, device=dev)
+            whh_d = self.packed(whh, False)
+            for t in range(T - 1, -1, -1):
+                ops.lstm_cell_bwd(dh, dc, acts[t], cs[t - 1] if t > 0 else None, cs[t], dG[t], R, C)
+                if t > 0:
+                    dh = ops.conv2d(dG[t], whh_d, C, 1, 1, 0, y_dtype=torch.float32)
+            dG_all = dG.view(T * B, h, w, 4 * C)
+            if self.wants_grad(wih):
+                ops.conv2d_wgrad(dG_all, seq.data, self.grads[wih], 1, 1, 0)
+            if self.wants_grad(whh) and T > 1:
+                ops.conv2d_wgrad(dG[1:].reshape((T - 1) * B, h, w, 4 * C), hs[:T - 1].reshape((T - 1) * B, h, w, C),
+                                 self.grads[whh], 1, 1, 0)
+            for bn_ in (bih, bhh):
+                if self.wants_grad(bn_):
+                    ops.colsum(dG_all, self.grads[bn_], T * R, 4 * C)
+            if seq.needs_grad:
+                seq.grad = ops.conv2d(dG_all, self.packed(wih, False), C, 1, 1, 0, residual=seq.grad, out=seq.grad,
+                                      y_dtype=seq.grad_dtype)
+
+        self.tape.append(bwd)
+        return out
+
+    # ---------------------------------------------------------------------------------------------
+    def backward(self, out: Var, dout):
+        out.grad = dout
+        for fn in reversed(self.tape):
+            fn()
+        self.tape = []
+        self._packed = {}
+
+
+def flat_grads(named_params):
+    """One flat fp32 buffer with a view per trainable parameter (what the DP all-reduce walks)."""
+    named = [(n, p) for n, p in named_params if p.requires_grad]
+    if not named:
+        return None, {}
+    total = sum(p.numel() for _, p in named)
+    flat = torch.zeros(total, dtype=torch.float32, device=named[0][1].device)
+    views, off = {}, 0
+    for n, p in named:
+        views[n] = flat[off:off + p.numel()].view(p.shape)
+        off += p.numel()
+    return flat, views
+
+
+class ModelFunction(torch.autograd.Function):
+    """The whole model forward as one autograd node; backward = the executor's tape."""
+
+    @staticmethod
+    def forward(ctx, module, x, *params):
+        ex, out_var, logits = module._run(x, record=True)
+        ctx.ex, ctx.out_var, ctx.module = ex, out_var, module
+        ctx.names = module._trainable_names
+        return logits
+
+    @staticmethod
+    def backward(ctx, dlogits):
+        ex, module = ctx.ex, ctx.module
+        d = ops.nchw_to_nhwc(dlogits.contiguous().float(), ex.dtype)
+        ex.backward(ctx.out_var, d)
+        grads = tuple(ex.grads[n] for n in ctx.names)
+        hook = getattr(module, "_grad_ready_hook", None)
+        if hook is not None:
+            hook(module._last_flat_grad)
+        ctx.ex = ctx.out_var = None
+        return (None, None) + grads

@@ -1,0 +1,121 @@
+"""Parameter containers + the shared nn.Module base of the B200 models.
+
+The classes only *hold* parameters under the reference's ``state_dict`` names; no torch
+operator is ever called on them -- the forward pass is ``engine.Executor`` launching libstfb200 kernels.
+"""
+from __future__ import annotations
+
+import math
+import warnings
+
+import torch
+import torch.nn as nn
+
+from . import engine, ops
+
+
+class ConvParams(nn.Module):
+    """weight [Cout, Cin, k, k] (+ bias) -- nn.Conv2d's parameters and default init."""
+
+    def __init__(self, cin, cout, k, bias, transposed=False, resnet_init=False):
+        super().__init__()
+        shape = (cin, cout, k, k) if transposed else (cout, cin, k, k)
+        self.weight = nn.Parameter(torch.empty(shape))
+        if resnet_init:   # torchvision resnet: kaiming_normal_(mode="fan_out", nonlinearity="relu")
+            nn.init.kaiming_normal_(self.weight, mode="fan_out", nonlinearity="relu")
+        else:             # nn.Conv2d / nn.ConvTranspose2d default
+            nn.init.kaiming_uniform_(self.weight, a=math.sqrt(5))
+        if bias:
+            fan_in = shape[1] * k * k
+            bound = 1.0 / math.sqrt(fan_in) if fan_in > 0 else 0.0
+            self.bias = nn.Parameter(torch.empty(cout).uniform_(-bound, bound))
+        else:
+            self.register_parameter("bias", None)
+
+
+class BNParams(nn.Module):
+    """nn.BatchNorm2d's parameters and buffers."""
+
+    def __init__(self, c):
+        super().__init__()
+        self.weight = nn.Parameter(torch.ones(c))
+        self.bias = nn.Parameter(torch.zeros(c))
+        self.register_buffer("running_mean", torch.zeros(c))
+        self.register_buffer("running_var", torch.ones(c))
+        self.register_buffer("num_batches_tracked", torch.tensor(0, dtype=torch.long))
+
+
+class LSTMParams(nn.Module):
+    """nn.LSTM(C, C, batch_first=True) single-layer parameters, gate order i,f,g,o."""
+
+    def __init__(self, c):
+        super().__init__()
+        k = 1.0 / math.sqrt(c)
+        self.weight_ih_l0 = nn.Parameter(torch.empty(4 * c, c).uniform_(-k, k))
+        self.weight_hh_l0 = nn.Parameter(torch.empty(4 * c, c).uniform_(-k, k))
+        self.bias_ih_l0 = nn.Parameter(torch.empty(4 * c).uniform_(-k, k))
+        self.bias_hh_l0 = nn.Parameter(torch.empty(4 * c).uniform_(-k, k))
+
+
+def seq(**children):
+    """ModuleDict whose keys are the reference's nn.Sequential indices (gaps where ReLU sat)."""
+    return nn.ModuleDict(children)
+
+
+class B200Module(nn.Module):
+    """Shared forward plumbing: precision selection, tape recording, the single autograd node."""
+
+    #: None = follow torch autocast (fp32 unless autocast is on); or force torch.float32 / torch.bfloat16
+    compute_dtype = None
+    _warned_fp16 = False
+
+    def _select_dtype(self):
+        if self.compute_dtype is not None:
+            return self.compute_dtype
+        if torch.is_autocast_enabled("cuda"):
+            dt = torch.get_autocast_dtype("cuda")
+            if dt == torch.float16 and not B200Module._warned_fp16:
+                warnings.warn("stf_unet_b200: fp16 autocast requested; the B200 kernels run bf16 (same tensor-core "
+                              "rate, no loss scaling needed). Call torch.set_autocast_dtype('cuda', torch.bfloat16) "
+                              "to silence this.")
+                B200Module._warned_fp16 = True
+            return torch.bfloat16
+        return torch.float32
+
+    def _state(self):
+        params = {n: p.data for n, p in self.named_parameters()}
+        params.update({n: b for n, b in self.named_buffers()})
+        return params
+
+    def _make_executor(self, record):
+        named = list(self.named_parameters())
+        for n, p in named:
+            if not p.is_cuda or p.dtype != torch.float32 or not p.is_contiguous():
+                raise RuntimeError(f"parameter {n} must be a contiguous fp32 CUDA tensor (stf_unet_b200 has no CPU "
+                                   "fallback; call model.to('cuda'))")
+        grads = {}
+        if record:
+            flat, grads = engine.flat_grads(named)
+            self._last_flat_grad = flat
+            self._trainable_names = [n for n, p in named if p.requires_grad]
+        return engine.Executor(self._state(), self._select_dtype(), self.training, record, grads)
+
+    def _forward_impl(self, ex, x):
+        raise NotImplementedError
+
+    def _run(self, x, record):
+        ex = self._make_executor(record)
+        head = self._forward_impl(ex, x)
+        logits = ops.nhwc_to_nchw(head.data)
+        return ex, head, logits
+
+    def _call(self, x):
+        if not x.is_cuda:
+            raise RuntimeError("stf_unet_b200 models run on CUDA (sm_100a) only; there is no CPU fallback")
+        x = x.contiguous().float()
+        trainable = [p for p in self.parameters() if p.requires_grad]
+        if torch.is_grad_enabled() and self.training and trainable:
+            logits = engine.ModelFunction.apply(self, x, *trainable)
+        else:
+            _, _, logits = self._run(x, record=False)
+        return {"out": logits}

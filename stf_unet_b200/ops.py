@@ -1,0 +1,239 @@
+"""Thin tensor-level wrappers over the C ABI (include/stfb200.h).
+
+torch is used for device memory (``torch.empty``) and the current stream only; all arithmetic happens in
+libstfb200.so.  Feature maps are contiguous NHWC tensors ``[N, H, W, C]`` in fp32 or bf16.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+
+from . import _lib
+from ._lib import BF16, CONV_FWD, CONV_TRANSPOSED, F32, IMPL_AUTO, IMPL_SIMT, IMPL_TCGEN05, ConvParams, check
+
+__all__ = ["dt_code", "conv2d", "conv2d_wgrad", "pack_weight", "bn_stats", "bn_finalize_train", "bn_fold_eval",
+           "bn_apply", "bn_bwd", "colsum", "maxpool_fwd", "maxpool_bwd", "bilinear_fwd", "bilinear_bwd",
+           "lstm_cell_fwd", "lstm_cell_bwd", "pack_series", "nhwc_to_nchw", "nchw_to_nhwc", "add_", "cast",
+           "ce_dice_fwd", "ce_dice_bwd", "CONV_FWD", "CONV_TRANSPOSED", "IMPL_AUTO", "IMPL_SIMT", "IMPL_TCGEN05"]
+
+_DT = {torch.float32: F32, torch.bfloat16: BF16}
+
+
+def dt_code(dtype):
+    try:
+        return _DT[dtype]
+    except KeyError:
+        raise TypeError(f"stf_unet_b200 supports fp32 and bf16 activations, got {dtype}") from None
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _p(t):
+    return None if t is None else t.data_ptr()
+
+
+def _need_cuda(*ts):
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError("stf_unet_b200 kernels need CUDA tensors (there is no CPU fallback)")
+
+
+def conv_out_hw(H, W, k, stride, pad, transposed=False, out_pad=0):
+    if transposed:
+        return (H - 1) * stride - 2 * pad + k + out_pad, (W - 1) * stride - 2 * pad + k + out_pad
+    return (H + 2 * pad - k) // stride + 1, (W + 2 * pad - k) // stride + 1
+
+
+def conv2d(x, wp, Cout, k, stride, pad, *, mode=CONV_FWD, out_hw=None, x2=None, bias=None, bias2=None, scale=None,
+           shift=None, residual=None, relu=False, y_dtype=None, ldw=None, out=None, w_offset=0, impl=IMPL_AUTO):
+    """Implicit-GEMM convolution with fused epilogue; see stfb_conv2d in include/stfb200.h."""
+    _need_cuda(x, wp)
+    N, H, W, C1 = x.shape
+    C2 = 0 if x2 is None else x2.shape[3]
+    kh, kw = (k, k) if isinstance(k, int) else k
+    if out_hw is None:
+        out_hw = conv_out_hw(H, W, kh, stride, pad, transposed=(mode == CONV_TRANSPOSED))
+    Ho, Wo = out_hw
+    y_dtype = y_dtype or x.dtype
+    y = out if out is not None else torch.empty((N, Ho, Wo, Cout), dtype=y_dtype, device=x.device)
+    esz = x.element_size()
+    p = ConvParams(x=_p(x), x2=_p(x2), w=wp.data_ptr() + w_offset * esz, y=_p(y), bias=_p(bias), bias2=_p(bias2),
+                   scale=_p(scale), shift=_p(shift), residual=_p(residual), N=N, H=H, W=W, C1=C1, C2=C2, Ho=Ho, Wo=Wo,
+                   Cout=Cout, kh=kh, kw=kw, stride=stride, pad=pad, ldw=ldw if ldw is not None else Cout, mode=mode,
+                   relu=int(bool(relu)), x_dtype=dt_code(x.dtype), y_dtype=dt_code(y.dtype), impl=impl)
+    check(_lib.load().stfb_conv2d(C.byref(p), _stream()), "conv2d")
+    return y
+
+
+def conv2d_wgrad(P, G, dW, k, stride, pad, cg_off=0, cg_total=None):
+    """dW[cp][cg_off+cg][ky][kx] += sum_pix P[pix,cp] * G[gather(pix),cg]; dW fp32, reference layout."""
+    _need_cuda(P, G, dW)
+    N, Hp, Wp, Cp = P.shape
+    _, Hg, Wg, Cg = G.shape
+    kh, kw = (k, k) if isinstance(k, int) else k
+    check(_lib.load().stfb_conv2d_wgrad(_p(P), _p(G), _p(dW), N, Hp, Wp, Cp, Hg, Wg, Cg, cg_off,
+                                        cg_total if cg_total is not None else Cg, kh, kw, stride, pad, dt_code(P.dtype),
+                                        _stream()), "conv2d_wgrad")
+
+
+def pack_weight(w, k_is_dim1, dtype):
+    """[D0, D1, kh, kw] (or [D0, D1]) fp32 parameter -> [(ky,kx,k), n] GEMM operand in `dtype`."""
+    _need_cuda(w)
+    if w.dim() == 2:
+        D0, D1, kh, kw = w.shape[0], w.shape[1], 1, 1
+    else:
+        D0, D1, kh, kw = w.shape
+    Kc, Nc = (D1, D0) if k_is_dim1 else (D0, D1)
+    wp = torch.empty((kh * kw * Kc, Nc), dtype=dtype, device=w.device)
+    check(_lib.load().stfb_pack_weight(_p(w), _p(wp), D0, D1, kh, kw, int(k_is_dim1), dt_code(dtype), _stream()), "pack_weight")
+    return wp
+
+
+def bn_stats(x, G, R, C):
+    sums = torch.empty((2, G, C), dtype=torch.float64, device=x.device)
+    check(_lib.load().stfb_bn_stats(_p(x), _p(sums), G, R, C, dt_code(x.dtype), _stream()), "bn_stats")
+    return sums
+
+
+def bn_finalize_train(sums, gamma, beta, running_mean, running_var, nbt, G, R, C, eps=1e-5, momentum=0.1):
+    out = torch.empty((4, G, C), dtype=torch.float32, device=sums.device)  # scale, shift, mean, invstd
+    check(_lib.load().stfb_bn_finalize_train(_p(sums), _p(gamma), _p(beta), _p(running_mean), _p(running_var), _p(nbt),
+                                             _p(out[0]), _p(out[1]), _p(out[2]), _p(out[3]), G, R, C, eps, momentum,
+                                             _stream()), "bn_finalize_train")
+    return out
+
+
+def bn_fold_eval(gamma, beta, running_mean, running_var, eps=1e-5):
+    C_ = gamma.numel()
+    out = torch.empty((2, C_), dtype=torch.float32, device=gamma.device)
+    check(_lib.load().stfb_bn_fold_eval(_p(gamma), _p(beta), _p(running_mean), _p(running_var), _p(out[0]), _p(out[1]), C_,
+                                        eps, _stream()), "bn_fold_eval")
+    return out
+
+
+def bn_apply(x, scale, shift, G, R, C, relu, residual=None, out=None):
+    y = out if out is not None else torch.empty_like(x)
+    check(_lib.load().stfb_bn_apply(_p(x), _p(scale), _p(shift), _p(residual), _p(y), G, R, C, int(bool(relu)),
+                                    dt_code(x.dtype), _stream()), "bn_apply")
+    return y
+
+
+def bn_bwd(dy, y, x, mean, invstd, gamma, dgamma, dbeta, G, R, C, relu, want_dres, dres_acc=None):
+    """Full BatchNorm(+ReLU)(+residual) backward: returns (dx, dres or None); dgamma/dbeta accumulated.
+    dres_acc: existing gradient of the residual input, accumulated into in place."""
+    lib = _lib.load()
+    s = _stream()
+    red = torch.empty((2, G, C), dtype=torch.float64, device=x.device)
+    check(lib.stfb_bn_bwd_reduce(_p(dy), _p(y) if relu else None, _p(x), _p(mean), _p(invstd), _p(red), G, R, C,
+                                 int(bool(relu)), dt_code(x.dtype), s), "bn_bwd_reduce")
+    coef = torch.empty((G, C, 3), dtype=torch.float32, device=x.device)
+    check(lib.stfb_bn_bwd_finalize(_p(red), _p(gamma), _p(invstd), _p(dgamma), _p(dbeta), _p(coef), G, R, C, s),
+          "bn_bwd_finalize")
+    dx = torch.empty_like(x)
+    dres = dres_acc if dres_acc is not None else (torch.empty_like(x) if want_dres else None)
+    check(lib.stfb_bn_bwd_apply(_p(dy), _p(y) if relu else None, _p(x), _p(mean), _p(invstd), _p(coef), _p(dx), _p(dres),
+                                int(dres_acc is not None), G, R, C, int(bool(relu)), dt_code(x.dtype), s), "bn_bwd_apply")
+    return dx, dres
+
+
+def colsum(x, out, R, C):
+    check(_lib.load().stfb_colsum(_p(x), _p(out), R, C, dt_code(x.dtype), _stream()), "colsum")
+
+
+def maxpool_fwd(x, k, stride, pad):
+    N, H, W, C_ = x.shape
+    Ho, Wo = (H + 2 * pad - k) // stride + 1, (W + 2 * pad - k) // stride + 1
+    y = torch.empty((N, Ho, Wo, C_), dtype=x.dtype, device=x.device)
+    check(_lib.load().stfb_maxpool_fwd(_p(x), _p(y), N, H, W, C_, Ho, Wo, k, stride, pad, dt_code(x.dtype), _stream()),
+          "maxpool_fwd")
+    return y
+
+
+def maxpool_bwd(x, dy, k, stride, pad):
+    N, H, W, C_ = x.shape
+    _, Ho, Wo, _ = dy.shape
+    dx = torch.empty_like(x)
+    check(_lib.load().stfb_maxpool_bwd(_p(x), _p(dy), _p(dx), N, H, W, C_, Ho, Wo, k, stride, pad, dt_code(x.dtype),
+                                       _stream()), "maxpool_bwd")
+    return dx
+
+
+def bilinear_fwd(x, Ho, Wo):
+    N, H, W, C_ = x.shape
+    y = torch.empty((N, Ho, Wo, C_), dtype=x.dtype, device=x.device)
+    check(_lib.load().stfb_bilinear_fwd(_p(x), _p(y), N, H, W, C_, Ho, Wo, dt_code(x.dtype), _stream()), "bilinear_fwd")
+    return y
+
+
+def bilinear_bwd(dy, H, W):
+    N, Ho, Wo, C_ = dy.shape
+    dx = torch.zeros((N, H, W, C_), dtype=torch.float32, device=dy.device)
+    check(_lib.load().stfb_bilinear_bwd(_p(dy), _p(dx), N, H, W, C_, Ho, Wo, dt_code(dy.dtype), _stream()), "bilinear_bwd")
+    return dx
+
+
+def lstm_cell_fwd(gates, c_prev, acts, c_out, h_out, R, C_):
+    check(_lib.load().stfb_lstm_cell_fwd(_p(gates), _p(c_prev), _p(acts), _p(c_out), _p(h_out), R, C_, dt_code(h_out.dtype),
+                                         _stream()), "lstm_cell_fwd")
+
+
+def lstm_cell_bwd(dh, dc, acts, c_prev, c_cur, dgates, R, C_):
+    check(_lib.load().stfb_lstm_cell_bwd(_p(dh), _p(dc), _p(acts), _p(c_prev), _p(c_cur), _p(dgates), R, C_,
+                                         dt_code(dgates.dtype), _stream()), "lstm_cell_bwd")
+
+
+def pack_series(x, dtype):
+    """[B, T, C, H, W] fp32 -> [T*B, H, W, C] `dtype`, time-major image order."""
+    _need_cuda(x)
+    B, T, C_, H, W = x.shape
+    y = torch.empty((T * B, H, W, C_), dtype=dtype, device=x.device)
+    check(_lib.load().stfb_pack_series(_p(x), _p(y), B, T, C_, H, W, dt_code(dtype), _stream()), "pack_series")
+    return y
+
+
+def nhwc_to_nchw(y):
+    N, H, W, C_ = y.shape
+    out = torch.empty((N, C_, H, W), dtype=torch.float32, device=y.device)
+    check(_lib.load().stfb_nhwc_to_nchw(_p(y), _p(out), N, H, W, C_, dt_code(y.dtype), _stream()), "nhwc_to_nchw")
+    return out
+
+
+def nchw_to_nhwc(g, dtype):
+    _need_cuda(g)
+    N, C_, H, W = g.shape
+    out = torch.empty((N, H, W, C_), dtype=dtype, device=g.device)
+    check(_lib.load().stfb_nchw_to_nhwc(_p(g), _p(out), N, H, W, C_, dt_code(dtype), _stream()), "nchw_to_nhwc")
+    return out
+
+
+def add_(dst, src):
+    assert dst.dtype == src.dtype and dst.numel() == src.numel()
+    check(_lib.load().stfb_add_inplace(_p(dst), _p(src), dst.numel(), dt_code(dst.dtype), _stream()), "add_inplace")
+    return dst
+
+
+def cast(src, dtype):
+    dst = torch.empty(src.shape, dtype=dtype, device=src.device)
+    check(_lib.load().stfb_cast(_p(src), dt_code(src.dtype), _p(dst), dt_code(dtype), src.numel(), _stream()), "cast")
+    return dst
+
+
+def ce_dice_fwd(logits, target, eps=1e-6):
+    """logits NCHW fp32, target int64 -> (loss_out[3] = {total, ce, dice}, stats)."""
+    _need_cuda(logits, target)
+    B, C_, H, W = logits.shape
+    stats = torch.empty((B * C_ * 3 + 1,), dtype=torch.float64, device=logits.device)
+    out = torch.empty((3,), dtype=torch.float32, device=logits.device)
+    check(_lib.load().stfb_ce_dice_fwd(_p(logits), _p(target), _p(stats), _p(out), B, C_, H * W, eps, _stream()), "ce_dice_fwd")
+    return out, stats
+
+
+def ce_dice_bwd(logits, target, stats, dloss, eps=1e-6):
+    B, C_, H, W = logits.shape
+    dl = torch.empty_like(logits)
+    check(_lib.load().stfb_ce_dice_bwd(_p(logits), _p(target), _p(stats), _p(dloss), _p(dl), B, C_, H * W, eps, _stream()),
+          "ce_dice_bwd")
+    return dl

@@ -1,0 +1,86 @@
+"""CPU-side checks: the C-ABI library loads and exports every symbol include/stfb200.h declares, argument
+validation works without a device, the module tree reproduces the reference state_dict contract, and the
+product path fails loudly (no CPU fallback)."""
+import ctypes
+import os
+import re
+
+import pytest
+import torch
+
+import stf_unet_b200 as S
+from oracle import weights as W
+from stf_unet_b200 import _lib
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def header_symbols():
+    src = open(os.path.join(ROOT, "include", "stfb200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(stfb_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol():
+    lib = _lib.load()
+    syms = header_symbols()
+    assert len(syms) >= 25
+    for s in syms:
+        assert hasattr(lib, s), f"{s} declared in include/stfb200.h but not exported"
+    # and the ctypes table binds exactly the declared set
+    assert sorted(_lib.EXPORTS) == syms
+    assert lib.stfb_version() >= 100
+
+
+def test_argument_validation_needs_no_device():
+    lib = _lib.load()
+    p = _lib.ConvParams()
+    assert lib.stfb_conv2d(ctypes.byref(p), None) == -1
+    assert b"null" in lib.stfb_last_error()
+    assert lib.stfb_maxpool_fwd(None, None, 1, 4, 4, 4, 2, 2, 2, 2, 0, 0, None) == -1
+    assert lib.stfb_ce_dice_fwd(None, None, None, None, 1, 2, 4, 1e-6, None) == -1
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-device error path")
+def test_no_device_is_an_error_not_a_fallback():
+    lib = _lib.load()
+    buf = (ctypes.c_float * 64)()
+    addr = ctypes.addressof(buf)
+    st = lib.stfb_cast(addr, 0, addr, 0, 16, None)
+    assert st == -3 and b"no CPU fallback" in lib.stfb_last_error()
+    m = S.UNet(1, 2, 8)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        m(torch.zeros(1, 1, 32, 32))
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        S.criterion({"out": torch.zeros(1, 2, 4, 4)}, torch.zeros(1, 4, 4, dtype=torch.long))
+
+
+@pytest.mark.parametrize("kw", [dict(), dict(use_pk_maps=True), dict(in_channels=2, num_classes=3)])
+def test_stf_state_dict_contract(kw):
+    m = S.STFLSTMUNet(**kw)
+    spec = W.stf_param_spec(kw.get("in_channels", 1), kw.get("num_classes", 2), kw.get("use_pk_maps", False))
+    assert [(k, tuple(v.shape)) for k, v in m.state_dict().items()] == [(n, tuple(s)) for n, s, _ in spec]
+    assert all(v.dtype == (torch.int64 if k.endswith("num_batches_tracked") else torch.float32) for k, v in m.state_dict().items())
+    assert not hasattr(m, "input_format")          # resolves to "time_sequence" (train_and_eval.py:10)
+    sd = W.make_state_dict(spec)
+    m.load_state_dict(sd)                           # strict
+
+
+def test_unet_state_dict_contract():
+    m = S.UNet(in_channels=8, num_classes=2, base_c=64)
+    spec = W.unet_param_spec(8, 2, 64)
+    assert [(k, tuple(v.shape)) for k, v in m.state_dict().items()] == [(n, tuple(s)) for n, s, _ in spec]
+    assert S.UNet.input_format == "flat_channels"
+    assert sum(p.numel() for p in m.parameters()) == 31046466
+
+
+def test_param_counts_match_reference():
+    assert sum(p.numel() for p in S.STFLSTMUNet().parameters()) == 27379746
+    assert sum(p.numel() for p in S.UNet(1, 2, 64).parameters()) == 31042434
+
+
+def test_criterion_rejects_unsupported_configuration():
+    with pytest.raises(NotImplementedError):
+        S.criterion({"out": torch.zeros(1, 2, 4, 4)}, torch.zeros(1, 4, 4, dtype=torch.long), ignore_index=255)
+    with pytest.raises(ValueError, match="size mismatch"):
+        S.ce_dice(torch.zeros(1, 2, 4, 4), torch.zeros(1, 8, 8, dtype=torch.long))

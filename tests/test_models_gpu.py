@@ -1,0 +1,220 @@
+"""GPU parity of the B200 models against the oracle and the committed golden fixtures.
+
+Bars (BASELINE.json north_star): fp32 logits rel-err <= 1e-4; bf16 <= 2e-2; identical argmax on >= 99.9 % of
+pixels.  Gradients: fp32 rel-L2 <= 1e-3 per parameter (fp32 atomics reorder sums), bf16 checked on the loss
+and on aggregate gradient direction."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+import stf_unet_b200 as S  # noqa: E402
+from oracle import stf_oracle as O  # noqa: E402
+from oracle import weights as W  # noqa: E402
+
+DEV = "cuda"
+
+
+def rel(a, b):
+    a, b = a.double().flatten().cpu(), b.double().flatten().cpu()
+    return ((a - b).norm() / b.norm().clamp_min(1e-30)).item()
+
+
+def argmax_agree(a, b):
+    return (a.argmax(1).cpu() == b.argmax(1).cpu()).float().mean().item()
+
+
+def load_model(model, sd):
+    model.load_state_dict(sd)
+    return model.to(DEV)
+
+
+def test_stf_eval_fp32_vs_golden_and_oracle(golden_dir):
+    g = np.load(os.path.join(golden_dir, "stf_eval_b2_t3_64.npz"))
+    x, t = W.synthetic_dce_batch(2, 3, 64, 64, seed=11)
+    sd = W.make_state_dict(W.stf_param_spec(1, 2), seed=0)
+    m = load_model(S.STFLSTMUNet(1, 2, 3), sd).eval()
+    with torch.no_grad():
+        y = m(x.to(DEV))["out"]
+    assert y.shape == (2, 2, 32, 32) and y.dtype == torch.float32
+    ref = torch.from_numpy(g["logits"])
+    assert rel(y, ref) < 1e-4
+    assert argmax_agree(y, ref) >= 0.999
+    loss = S.criterion({"out": y}, t.to(DEV))
+    assert abs(loss.item() - float(g["loss"])) < 1e-4
+
+
+def test_stf_eval_ragged_size_uses_bilinear(golden_dir):
+    g = np.load(os.path.join(golden_dir, "stf_eval_b1_t2_80.npz"))
+    x, _ = W.synthetic_dce_batch(1, 2, 80, 80, seed=12)
+    sd = W.make_state_dict(W.stf_param_spec(1, 2), seed=0)
+    m = load_model(S.STFLSTMUNet(1, 2, 2), sd).eval()
+    with torch.no_grad():
+        y = m(x.to(DEV))["out"]
+    assert y.shape == (1, 2, 40, 40)
+    assert rel(y, torch.from_numpy(g["logits"])) < 1e-4
+
+
+def test_stf_eval_bf16_autocast():
+    x, _ = W.synthetic_dce_batch(2, 4, 128, 128, seed=31)
+    sd = W.make_state_dict(W.stf_param_spec(1, 2), seed=0)
+    with torch.no_grad():
+        ref = O.stf_forward({k: v.to(DEV) for k, v in sd.items()}, x.to(DEV), train=False)
+    m = load_model(S.STFLSTMUNet(1, 2, 4), sd).eval()
+    with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16):
+        y = m(x.to(DEV))["out"]
+    assert y.dtype == torch.float32
+    r, a = rel(y, ref), argmax_agree(y, ref)
+    print(f"stf eval bf16: rel={r:.3e} argmax={a:.5f}")
+    assert r < 2e-2 and a >= 0.999
+
+
+def _train_step(model, x, t):
+    model.train()
+    out = model(x)["out"]
+    loss = S.criterion({"out": out}, t)
+    loss.backward()
+    return out.detach(), loss.detach()
+
+
+def test_stf_train_fp32_vs_golden(golden_dir):
+    g = np.load(os.path.join(golden_dir, "stf_train_b2_t3_64.npz"))
+    x, t = W.synthetic_dce_batch(2, 3, 64, 64, seed=11)
+    sd = W.make_state_dict(W.stf_param_spec(1, 2), seed=0)
+    m = load_model(S.STFLSTMUNet(1, 2, 3), sd)
+    out, loss = _train_step(m, x.to(DEV), t.to(DEV))
+    assert rel(out, torch.from_numpy(g["logits"])) < 1e-4
+    assert abs(loss.item() - float(g["loss"])) < 1e-4
+    grads = {n: p.grad for n, p in m.named_parameters()}
+    worst = 0.0
+    for name, norm in zip(g["grad_names"], g["grad_norms"]):
+        mine = grads[str(name)].double().norm().item()
+        err = abs(mine - norm) / (norm + 1e-6)
+        worst = max(worst, err)
+        assert err < 2e-3, (str(name), mine, norm)
+    for k in g.files:
+        if k.startswith("grad::"):
+            ref = torch.from_numpy(g[k])
+            err = (grads[k[6:]].cpu().double() - ref.double()).norm().item()
+            assert err < 1e-3 * ref.double().norm().item() + 1e-6, k
+        if k.startswith("buf::"):
+            mine = m.state_dict()[k[5:]].cpu()
+            if g[k].dtype.kind == "i":
+                assert int(mine) == int(g[k]), k
+            else:
+                assert rel(mine, torch.from_numpy(g[k])) < 1e-4, k
+    print("worst grad-norm rel err", worst)
+
+
+def test_stf_train_bf16_vs_oracle():
+    B, T, HW = 2, 4, 128
+    x, t = W.synthetic_dce_batch(B, T, HW, HW, seed=33)
+    sd = W.make_state_dict(W.stf_param_spec(1, 2), seed=0)
+    sd_dev = {k: v.to(DEV) for k, v in sd.items()}
+    ref_logits, ref_loss, ref_grads, _ = O.loss_and_grads(sd_dev, x.to(DEV), t.to(DEV), model="stf", train=True)
+    m = load_model(S.STFLSTMUNet(1, 2, T), sd)
+    m.train()
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        out = m(x.to(DEV))["out"]
+        loss = S.criterion({"out": out}, t.to(DEV))
+    loss.backward()
+    r, a = rel(out, ref_logits), argmax_agree(out, ref_logits)
+    print(f"stf train bf16: rel={r:.3e} argmax={a:.5f} loss {loss.item():.5f} vs {ref_loss.item():.5f}")
+    assert r < 2e-2 and a >= 0.995
+    assert abs(loss.item() - ref_loss.item()) < 2e-2 * abs(ref_loss.item())
+    # aggregate gradient direction
+    num = den1 = den2 = 0.0
+    for n, p in m.named_parameters():
+        gr = ref_grads[n].double().flatten()
+        gm = p.grad.double().flatten()
+        num += (gr * gm).sum().item()
+        den1 += (gr * gr).sum().item()
+        den2 += (gm * gm).sum().item()
+    cos = num / (den1 ** 0.5 * den2 ** 0.5)
+    print("bf16 grad cosine", cos)
+    assert cos > 0.98
+
+
+@pytest.mark.parametrize("name,cin,c,hw,seed", [("unet_train_in1_c16_32", 1, 16, 32, 21), ("unet_train_in8_c8_48", 8, 8, 48, 22)])
+def test_unet_train_fp32_vs_golden(golden_dir, name, cin, c, hw, seed):
+    g = np.load(os.path.join(golden_dir, name + ".npz"))
+    x, t = W.synthetic_dce_batch(2, cin, hw, hw, seed=seed, half_res_target=False)
+    sd = W.make_state_dict(W.unet_param_spec(cin, 2, c), seed=0)
+    m = load_model(S.UNet(cin, 2, c), sd)
+    out, loss = _train_step(m, x.view(2, cin, hw, hw).to(DEV), t.to(DEV))
+    assert rel(out, torch.from_numpy(g["logits"])) < 1e-4
+    assert abs(loss.item() - float(g["loss"])) < 1e-4
+    grads = {n: p.grad for n, p in m.named_parameters()}
+    for nm, norm in zip(g["grad_names"], g["grad_norms"]):
+        mine = grads[str(nm)].double().norm().item()
+        assert abs(mine - norm) < 2e-3 * norm + 2e-6, (str(nm), mine, norm)
+    for k in g.files:
+        if k.startswith("grad::"):
+            ref = torch.from_numpy(g[k])
+            err = (grads[k[6:]].cpu().double() - ref.double()).norm().item()
+            assert err < 1e-3 * ref.double().norm().item() + 2e-6, k
+        if k.startswith("buf::"):
+            mine = m.state_dict()[k[5:]].cpu()
+            if g[k].dtype.kind == "i":
+                assert int(mine) == int(g[k]), k
+            else:
+                assert rel(mine, torch.from_numpy(g[k])) < 1e-4, k
+
+
+def test_unet_eval_fp32_vs_golden(golden_dir):
+    g = np.load(os.path.join(golden_dir, "unet_eval_in1_c16_32.npz"))
+    x, t = W.synthetic_dce_batch(2, 1, 32, 32, seed=21, half_res_target=False)
+    sd = W.make_state_dict(W.unet_param_spec(1, 2, 16), seed=0)
+    m = load_model(S.UNet(1, 2, 16), sd).eval()
+    with torch.no_grad():
+        y = m(x[:, :, 0].to(DEV))["out"]
+    assert rel(y, torch.from_numpy(g["logits"])) < 1e-4
+
+
+def test_unet_config1_fp32_vs_oracle():
+    """BASELINE.json configs[0]: UNet(in=1, classes=2, base_c=64), B=4, 256x256, fp32 fwd + CE/Dice + bwd."""
+    x, t = W.synthetic_dce_batch(4, 1, 256, 256, seed=41, half_res_target=False)
+    sd = W.make_state_dict(W.unet_param_spec(1, 2, 64), seed=0)
+    sd_dev = {k: v.to(DEV) for k, v in sd.items()}
+    xin = x[:, :, 0].to(DEV)
+    ref_logits, ref_loss, ref_grads, _ = O.loss_and_grads(sd_dev, xin, t.to(DEV), model="unet", train=True)
+    m = load_model(S.UNet(1, 2, 64), sd)
+    out, loss = _train_step(m, xin, t.to(DEV))
+    r, a = rel(out, ref_logits), argmax_agree(out, ref_logits)
+    print(f"unet config1 fp32: rel={r:.3e} argmax={a:.5f}")
+    assert r < 1e-4 and a >= 0.999
+    assert abs(loss.item() - ref_loss.item()) < 1e-4 * abs(ref_loss.item()) + 1e-5
+    for n, p in m.named_parameters():
+        gr = ref_grads[n]
+        err = (p.grad.double() - gr.double()).norm().item()
+        assert err < 2e-3 * gr.double().norm().item() + 1e-5, n
+
+
+def test_training_loop_reduces_loss_bf16():
+    """A few AdamW steps through the public API in bf16: loss must fall (the reference's own smoke criterion)."""
+    torch.manual_seed(0)
+    x, t = W.synthetic_dce_batch(4, 4, 64, 64, seed=51)
+    m = S.STFLSTMUNet(1, 2, 4).to(DEV)
+    opt = torch.optim.AdamW(m.parameters(), lr=1e-3, weight_decay=1e-4, fused=True)
+    x, t = x.to(DEV), t.to(DEV)
+    losses = []
+    for _ in range(12):
+        m.train()
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            loss = S.criterion(m(x), t)
+        opt.zero_grad()
+        loss.backward()
+        opt.step()
+        losses.append(loss.item())
+    print("losses", [round(v, 4) for v in losses])
+    assert losses[-1] < 0.8 * losses[0]
+    assert int(m.bn1.num_batches_tracked) == 12 * 4
+
+
+def test_cpu_input_raises():
+    m = S.UNet(1, 2, 8).to(DEV)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        m(torch.zeros(1, 1, 32, 32))

@@ -1,0 +1,327 @@
+"""GPU parity of every libstfb200 operator against a plain fp32 torch reference of the same op
+(TF32 disabled).  Tolerances: fp32 path rel-L2 <= 2e-5 (north_star bar for logits is 1e-4); bf16 path
+rel-L2 <= 1e-2 against the fp32 reference evaluated on bf16-rounded inputs."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+from stf_unet_b200 import ops  # noqa: E402
+
+DEV = "cuda"
+
+
+@pytest.fixture(autouse=True, scope="module")
+def _no_tf32():
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    yield
+
+
+def rel(a, b):
+    a, b = a.double().flatten(), b.double().flatten()
+    return ((a - b).norm() / b.norm().clamp_min(1e-30)).item()
+
+
+def nhwc(x, dtype):
+    return x.permute(0, 2, 3, 1).contiguous().to(dtype)
+
+
+def nchw(y):
+    return y.float().permute(0, 3, 1, 2).contiguous()
+
+
+def tol(dtype):
+    return 2e-5 if dtype == torch.float32 else 1e-2
+
+
+def rnd(*shape, seed=0, scale=1.0):
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    return (torch.randn(*shape, generator=g) * scale).to(DEV)
+
+
+def q(x, dtype):
+    """round through the storage dtype so the fp32 reference sees what the kernel sees"""
+    return x.to(dtype).float()
+
+
+CONV_CASES = [
+    # N, H, W, C1, C2, Cout, k, stride, pad
+    (2, 16, 16, 64, 0, 64, 3, 1, 1),
+    (2, 9, 11, 64, 0, 128, 3, 2, 1),      # ragged, stride 2
+    (1, 8, 8, 128, 0, 256, 1, 2, 0),      # 1x1 downsample
+    (3, 20, 20, 1, 0, 64, 7, 2, 3),       # stem (slow A path)
+    (2, 12, 12, 32, 32, 32, 1, 1, 0),     # dual source fusion
+    (2, 8, 8, 64, 64, 64, 3, 1, 1),       # UNet concat conv
+    (2, 10, 10, 32, 0, 2, 1, 1, 0),       # head, Cout=2 (scalar epilogue)
+    (1, 6, 6, 8, 0, 16, 3, 1, 1),         # Cin % 16 != 0
+    (2, 4, 4, 512, 0, 512, 3, 1, 1),      # deep K, wide tile candidate
+    (4, 32, 32, 128, 0, 128, 3, 1, 1),
+]
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("case", CONV_CASES)
+def test_conv_fwd_epilogue(case, dtype):
+    N, H, W, C1, C2, Cout, k, s, p = case
+    x = q(rnd(N, C1 + C2, H, W, seed=1), dtype)
+    w = q(rnd(Cout, C1 + C2, k, k, seed=2, scale=(1.0 / (k * k * (C1 + C2)) ** 0.5)), dtype)
+    bias, scale, shift = rnd(Cout, seed=3), rnd(Cout, seed=4).abs() + 0.5, rnd(Cout, seed=5)
+    ref = F.conv2d(x, w, bias, s, p)
+    res = q(rnd(*ref.shape, seed=6), dtype)
+    ref = F.relu(ref * scale.view(1, -1, 1, 1) + shift.view(1, -1, 1, 1) + res)
+    wp = ops.pack_weight(w.contiguous(), True, dtype)
+    x1 = nhwc(x[:, :C1], dtype)
+    x2 = nhwc(x[:, C1:], dtype) if C2 else None
+    y = ops.conv2d(x1, wp, Cout, k, s, p, x2=x2, bias=bias, scale=scale, shift=shift, residual=nhwc(res, dtype), relu=True)
+    assert rel(nchw(y), ref) < tol(dtype)
+    # plain (no epilogue), fp32 output from bf16 inputs
+    y2 = ops.conv2d(x1, wp, Cout, k, s, p, x2=x2, y_dtype=torch.float32)
+    assert y2.dtype == torch.float32
+    assert rel(nchw(y2), F.conv2d(x, w, None, s, p)) < (2e-5 if dtype == torch.float32 else 2e-3)
+
+
+CONVT_CASES = [
+    # N, H, W, Cin, Cout, k, stride, pad, out_pad
+    (2, 8, 8, 64, 32, 3, 2, 1, 1),
+    (1, 5, 7, 128, 64, 3, 2, 1, 1),
+    (2, 6, 6, 32, 16, 2, 2, 0, 0),
+]
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("case", CONVT_CASES)
+def test_conv_transposed_fwd(case, dtype):
+    N, H, W, Cin, Cout, k, s, p, op = case
+    x = q(rnd(N, Cin, H, W, seed=1), dtype)
+    w = q(rnd(Cin, Cout, k, k, seed=2, scale=0.1), dtype)
+    b = rnd(Cout, seed=3)
+    ref = F.conv_transpose2d(x, w, b, stride=s, padding=p, output_padding=op)
+    wp = ops.pack_weight(w.contiguous(), False, dtype)
+    y = ops.conv2d(nhwc(x, dtype), wp, Cout, k, s, p, mode=ops.CONV_TRANSPOSED, out_hw=ref.shape[2:], bias=b)
+    assert rel(nchw(y), ref) < tol(dtype)
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("case", CONV_CASES)
+def test_conv_dgrad_wgrad(case, dtype):
+    N, H, W, C1, C2, Cout, k, s, p = case
+    Cin = C1 + C2
+    x = q(rnd(N, Cin, H, W, seed=1), dtype).requires_grad_(True)
+    w = q(rnd(Cout, Cin, k, k, seed=2, scale=0.1), dtype).requires_grad_(True)
+    y = F.conv2d(x, w, None, s, p)
+    dy = q(rnd(*y.shape, seed=7), dtype)
+    y.backward(dy)
+    # dgrad = transposed-gather conv over dy with the [ (tap,co) ][ ci ] packing
+    wpd = ops.pack_weight(w.detach().contiguous(), False, dtype)
+    dyn = nhwc(dy, dtype)
+    dx1 = ops.conv2d(dyn, wpd, C1, k, s, p, mode=ops.CONV_TRANSPOSED, out_hw=(H, W), ldw=Cin, w_offset=0)
+    assert rel(nchw(dx1), x.grad[:, :C1]) < tol(dtype)
+    if C2:
+        dx2 = ops.conv2d(dyn, wpd, C2, k, s, p, mode=ops.CONV_TRANSPOSED, out_hw=(H, W), ldw=Cin, w_offset=C1)
+        assert rel(nchw(dx2), x.grad[:, C1:]) < tol(dtype)
+    dW = torch.zeros_like(w)
+    xd = x.detach()
+    ops.conv2d_wgrad(dyn, nhwc(xd[:, :C1], dtype), dW, k, s, p, 0, Cin)
+    if C2:
+        ops.conv2d_wgrad(dyn, nhwc(xd[:, C1:], dtype), dW, k, s, p, C1, Cin)
+    assert rel(dW, w.grad) < tol(dtype)
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("case", CONVT_CASES)
+def test_conv_transposed_bwd(case, dtype):
+    N, H, W, Cin, Cout, k, s, p, op = case
+    x = q(rnd(N, Cin, H, W, seed=1), dtype).requires_grad_(True)
+    w = q(rnd(Cin, Cout, k, k, seed=2, scale=0.1), dtype).requires_grad_(True)
+    y = F.conv_transpose2d(x, w, None, stride=s, padding=p, output_padding=op)
+    dy = q(rnd(*y.shape, seed=7), dtype)
+    y.backward(dy)
+    dyn = nhwc(dy, dtype)
+    wpd = ops.pack_weight(w.detach().contiguous(), True, dtype)
+    dx = ops.conv2d(dyn, wpd, Cin, k, s, p, mode=ops.CONV_FWD, out_hw=(H, W))
+    assert rel(nchw(dx), x.grad) < tol(dtype)
+    dW = torch.zeros_like(w)
+    ops.conv2d_wgrad(nhwc(x.detach(), dtype), dyn, dW, k, s, p, 0, Cout)
+    assert rel(dW, w.grad) < tol(dtype)
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("G,B,H,W,C,relu,use_res", [(3, 2, 8, 8, 64, True, True), (1, 4, 5, 7, 32, True, False),
+                                                    (2, 1, 6, 6, 128, False, False), (1, 2, 4, 4, 2, False, False),
+                                                    (4, 2, 16, 16, 512, True, True)])
+def test_batchnorm_train_fwd_bwd(G, B, H, W, C, relu, use_res, dtype):
+    N = G * B
+    x = q(rnd(N, C, H, W, seed=1) * 2 + 0.5, dtype).requires_grad_(True)
+    res = q(rnd(N, C, H, W, seed=2), dtype).requires_grad_(True)
+    gamma = (rnd(C, seed=3).abs() + 0.5).requires_grad_(True)
+    beta = rnd(C, seed=4).requires_grad_(True)
+    rm0, rv0 = rnd(C, seed=5), rnd(C, seed=6).abs() + 0.5
+    rm, rv = rm0.clone(), rv0.clone()
+    outs = []
+    for g in range(G):   # reference semantics: one BN call per group, sequential running-stat updates
+        o = F.batch_norm(x[g * B:(g + 1) * B], rm, rv, gamma, beta, True, 0.1, 1e-5)
+        outs.append(o)
+    ref = torch.cat(outs, 0)
+    if use_res:
+        ref = ref + res
+    if relu:
+        ref = F.relu(ref)
+    dy = q(rnd(*ref.shape, seed=7), dtype)
+    ref.backward(dy)
+
+    R = B * H * W
+    xn = nhwc(x.detach(), dtype)
+    rm_k, rv_k = rm0.clone(), rv0.clone()
+    nbt = torch.zeros((), dtype=torch.int64, device=DEV)
+    sums = ops.bn_stats(xn, G, R, C)
+    st = ops.bn_finalize_train(sums, gamma.detach(), beta.detach(), rm_k, rv_k, nbt, G, R, C)
+    resn = nhwc(res.detach(), dtype) if use_res else None
+    y = ops.bn_apply(xn, st[0], st[1], G, R, C, relu, resn)
+    assert rel(nchw(y), ref) < tol(dtype)
+    assert int(nbt) == G
+    assert rel(rm_k, rm) < 1e-5 and rel(rv_k, rv) < (1e-5 if dtype == torch.float32 else 1e-5)
+    dgamma, dbeta = torch.zeros(C, device=DEV), torch.zeros(C, device=DEV)
+    dx, dres = ops.bn_bwd(nhwc(dy, dtype), y, xn, st[2], st[3], gamma.detach(), dgamma, dbeta, G, R, C, relu, use_res)
+    t = tol(dtype) * (1 if dtype == torch.float32 else 3)
+    assert rel(nchw(dx), x.grad) < t
+    assert rel(dgamma, gamma.grad) < t and rel(dbeta, beta.grad) < t
+    if use_res:
+        assert rel(nchw(dres), res.grad) < t
+        # accumulate form
+        acc = nhwc(torch.ones_like(res), dtype)
+        _, dres2 = ops.bn_bwd(nhwc(dy, dtype), y, xn, st[2], st[3], gamma.detach(), None, None, G, R, C, relu, True, dres_acc=acc)
+        assert rel(nchw(dres2), res.grad + 1) < t
+
+
+def test_bn_fold_eval_matches_batch_norm():
+    C = 48
+    gamma, beta, rm, rv = rnd(C, seed=1), rnd(C, seed=2), rnd(C, seed=3), rnd(C, seed=4).abs() + 0.1
+    x = rnd(2, C, 5, 5, seed=5)
+    f = ops.bn_fold_eval(gamma, beta, rm, rv)
+    ref = F.batch_norm(x, rm, rv, gamma, beta, False, 0.1, 1e-5)
+    assert rel(x * f[0].view(1, -1, 1, 1) + f[1].view(1, -1, 1, 1), ref) < 1e-6
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("k,s,p,H,W,C", [(3, 2, 1, 16, 16, 64), (3, 2, 1, 9, 13, 64), (2, 2, 0, 8, 8, 32), (2, 2, 0, 7, 9, 6)])
+def test_maxpool(k, s, p, H, W, C, dtype):
+    x = q(rnd(2, C, H, W, seed=1), dtype).requires_grad_(True)
+    ref = F.max_pool2d(x, k, s, p)
+    dy = q(rnd(*ref.shape, seed=2), dtype)
+    ref.backward(dy)
+    xn = nhwc(x.detach(), dtype)
+    y = ops.maxpool_fwd(xn, k, s, p)
+    assert torch.equal(nchw(y), ref.detach())
+    dx = ops.maxpool_bwd(xn, nhwc(dy, dtype), k, s, p)
+    assert rel(nchw(dx), x.grad) < (1e-6 if dtype == torch.float32 else 1e-2)
+
+
+def test_maxpool_ties_route_to_first_max():
+    x = torch.zeros(1, 4, 6, 6, device=DEV).requires_grad_(True)   # all equal: every window ties
+    ref = F.max_pool2d(x, 3, 2, 1)
+    dy = rnd(*ref.shape, seed=3)
+    ref.backward(dy)
+    dx = ops.maxpool_bwd(nhwc(x.detach(), torch.float32), nhwc(dy, torch.float32), 3, 2, 1)
+    assert rel(nchw(dx), x.grad) < 1e-6
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_bilinear_align_corners(dtype):
+    x = q(rnd(2, 16, 6, 6, seed=1), dtype).requires_grad_(True)
+    ref = F.interpolate(x, size=(5, 9), mode="bilinear", align_corners=True)
+    dy = q(rnd(*ref.shape, seed=2), dtype)
+    ref.backward(dy)
+    y = ops.bilinear_fwd(nhwc(x.detach(), dtype), 5, 9)
+    assert rel(nchw(y), ref) < (1e-5 if dtype == torch.float32 else 1e-2)
+    dx = ops.bilinear_bwd(nhwc(dy, dtype), 6, 6)
+    assert rel(nchw(dx), x.grad) < 1e-5
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_lstm_cell(dtype):
+    R, C = 300, 64
+    gates = rnd(R, 4 * C, seed=1).requires_grad_(True)
+    c_prev = rnd(R, C, seed=2).requires_grad_(True)
+    i, f, g, o = gates.split(C, 1)
+    c = torch.sigmoid(f) * c_prev + torch.sigmoid(i) * torch.tanh(g)
+    h = torch.sigmoid(o) * torch.tanh(c)
+    dh, dc = rnd(R, C, seed=3), rnd(R, C, seed=4)
+    (h * dh).sum().backward(retain_graph=True)
+    g_h, cp_h = gates.grad.clone(), c_prev.grad.clone()
+    gates.grad = None
+    c_prev.grad = None
+    (h * dh + c * dc).sum().backward()
+    acts = torch.empty(R, 4 * C, dtype=dtype, device=DEV)
+    c_out = torch.empty(R, C, device=DEV)
+    h_out = torch.empty(R, C, dtype=dtype, device=DEV)
+    ops.lstm_cell_fwd(gates.detach(), c_prev.detach(), acts, c_out, h_out, R, C)
+    assert rel(c_out, c) < 1e-5 and rel(h_out, h) < (1e-5 if dtype == torch.float32 else 5e-3)
+    dgates = torch.empty(R, 4 * C, dtype=dtype, device=DEV)
+    dc_io = dc.clone()
+    ops.lstm_cell_bwd(dh, dc_io, acts, c_prev.detach(), c_out, dgates, R, C)
+    t = 1e-4 if dtype == torch.float32 else 2e-2
+    assert rel(dgates, gates.grad) < t and rel(dc_io, c_prev.grad) < t
+    # t = 0 form (no previous state)
+    ops.lstm_cell_fwd(gates.detach(), None, None, c_out, h_out, R, C)
+    c0 = torch.sigmoid(i) * torch.tanh(g)
+    assert rel(c_out, c0) < 1e-5
+    assert g_h is not None and cp_h is not None
+
+
+def test_layout_adapters():
+    x = rnd(3, 5, 2, 6, 7, seed=1)    # B,T,C,H,W
+    y = ops.pack_series(x, torch.float32)
+    ref = x.permute(1, 0, 3, 4, 2).reshape(15, 6, 7, 2)
+    assert torch.equal(y, ref)
+    yb = ops.pack_series(x, torch.bfloat16)
+    assert torch.equal(yb, ref.to(torch.bfloat16))
+    z = rnd(2, 9, 4, 3, seed=2)       # NHWC
+    assert torch.equal(ops.nhwc_to_nchw(z), z.permute(0, 3, 1, 2).contiguous())
+    g = rnd(2, 3, 9, 4, seed=3)       # NCHW
+    assert torch.equal(ops.nchw_to_nhwc(g, torch.float32), g.permute(0, 2, 3, 1).contiguous())
+    a, b = rnd(1000, seed=4), rnd(1000, seed=5)
+    assert torch.equal(ops.add_(a.clone(), b), a + b)
+    assert torch.equal(ops.cast(a, torch.bfloat16), a.to(torch.bfloat16))
+    cs = torch.zeros(12, device=DEV)
+    m = rnd(1000, 12, seed=6)
+    ops.colsum(m, cs, 1000, 12)
+    assert rel(cs, m.sum(0)) < 1e-5
+
+
+@pytest.mark.parametrize("B,C,H,W", [(3, 2, 24, 40), (2, 4, 17, 5), (16, 2, 128, 128)])
+def test_ce_dice_loss(B, C, H, W):
+    from oracle import stf_oracle as O
+    logits = (rnd(B, C, H, W, seed=1) * 3).requires_grad_(True)
+    target = (torch.rand(B, H, W, generator=torch.Generator().manual_seed(2)) * C).long().clamp_(0, C - 1).to(DEV)
+    ref = O.criterion(logits, target)
+    ref.backward()
+    out, stats = ops.ce_dice_fwd(logits.detach(), target)
+    assert abs(out[0].item() - ref.item()) < 2e-6 * max(1.0, abs(ref.item()))
+    up = torch.tensor([0.5], device=DEV)
+    dl = ops.ce_dice_bwd(logits.detach(), target, stats, up)
+    assert rel(dl, 0.5 * logits.grad) < 2e-5
+
+
+def test_ce_dice_golden(golden_dir):
+    import numpy as np
+    import os
+    g = np.load(os.path.join(golden_dir, "criterion_3x2x24x40.npz"))
+    logits = torch.from_numpy(g["logits"]).to(DEV)
+    target = torch.from_numpy(g["target"]).to(DEV)
+    out, stats = ops.ce_dice_fwd(logits, target)
+    assert abs(out[0].item() - float(g["loss"])) < 2e-6
+    dl = ops.ce_dice_bwd(logits, target, stats, None)
+    assert rel(dl.cpu(), torch.from_numpy(g["grad"])) < 2e-5
+
+
+def test_errors_are_raised_not_swallowed():
+    x = torch.zeros(1, 4, 4, 8, device=DEV)
+    wp = torch.zeros(8, 8, device=DEV)
+    with pytest.raises(RuntimeError, match="output size"):
+        ops.conv2d(x, wp, 8, 1, 1, 0, out_hw=(9, 9))
+    with pytest.raises(RuntimeError, match="CUDA tensors"):
+        ops.conv2d(x.cpu(), wp, 8, 1, 1, 0)
+    with pytest.raises(RuntimeError, match="tcgen05"):
+        ops.conv2d(x, wp, 8, 1, 1, 0, impl=ops.IMPL_TCGEN05)   # fp32 is never a tensor-core shape
