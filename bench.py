@@ -1,0 +1,274 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the STF-Unet hot path on B200.
+
+Metric (BASELINE.json): train slices/s of STF-LSTM-UNet, bf16, T=8 DCE phases x 1x256x256, batch 16 per GPU
+(configs[2] sharded 16/GPU: weak scaling).  One "step" = forward + CE/Dice loss + backward (+ gradient all-reduce
+for N>1) + fused AdamW over one synthetic batch.
+
+    python bench.py --gpus 1 --steps 10 --warmup 3          # own arm (libstfb200 kernels)
+    python bench.py --impl reference ...                     # reference arm: the oracle port on the host CPU cores
+    python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...
+
+Prints ONE JSON line (rank 0).  `value` = device-resident inputs; `e2e` = same step fed from pinned host buffers
+with the H2D copies and a D2H read of the loss inside the timed region.
+"""
+import argparse
+import json
+import os
+import statistics
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+T_PHASES, HW, BATCH_PER_GPU = 8, 256, 16
+TRAIN_GFLOP_PER_SLICE = 259.35        # BASELINE.md section 3 (fwd + dgrad + wgrad, conv + LSTM GEMMs)
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        d = json.load(open(path))
+        return {"hbm_gbs": d["hbm_gbs"], "tflops": d.get("bf16_tflops_sustained", d["bf16_tflops"]), "src": "measured"}
+    return {"hbm_gbs": 6650.0, "tflops": 1400.0, "src": "fallback"}
+
+
+class ClockSampler:
+    """Samples SM clock / throttle reasons of one GPU during the timed region (pynvml, 100 ms period)."""
+
+    def __init__(self, index):
+        self.index, self.samples, self.reasons, self.max_mhz = index, [], set(), None
+        self._stop = threading.Event()
+        self._thr = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def _loop(self):
+        nv = self.nv
+        names = {}
+        for k in dir(nv):
+            if k.startswith("nvmlClocksThrottleReason") and isinstance(getattr(nv, k), int):
+                names[getattr(nv, k)] = k[len("nvmlClocksThrottleReason"):]
+        while not self._stop.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, nm in names.items():
+                    if bit and (mask & bit) == bit and nm not in ("None", "All"):
+                        self.reasons.add(nm)
+            except Exception:
+                pass
+            self._stop.wait(0.1)
+
+    def __enter__(self):
+        if self.nv is not None:
+            self._thr = threading.Thread(target=self._loop, daemon=True)
+            self._thr.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        if self._thr is not None:
+            self._thr.join()
+
+    def summary(self):
+        rs = sorted(r for r in self.reasons if r not in ("GpuIdle", "ApplicationsClocksSetting"))
+        return {"sm_mhz": statistics.median(self.samples) if self.samples else None, "sm_max_mhz": self.max_mhz,
+                "reasons": rs}
+
+
+def make_batch(rank, batch=BATCH_PER_GPU, T=T_PHASES, hw=HW):
+    from oracle import weights as W
+    return W.synthetic_dce_batch(batch, T, hw, hw, seed=1234 + rank, half_res_target=True)
+
+
+# ------------------------------------------------------------------------------------------------
+# reference arm / cpu baseline: the oracle (CPU restatement of the reference) on the host cores
+# ------------------------------------------------------------------------------------------------
+def cpu_train_step_time(batch, iters, warmup, threads=None):
+    from oracle import stf_oracle as O
+    from oracle import weights as W
+    threads = threads or os.cpu_count()
+    torch.set_num_threads(threads)
+    sd = W.make_state_dict(W.stf_param_spec(1, 2), seed=0)
+    x, t = make_batch(0, batch=batch)
+    times = []
+    for i in range(warmup + iters):
+        t0 = time.perf_counter()
+        O.loss_and_grads(sd, x, t, model="stf", train=True)
+        dt = time.perf_counter() - t0
+        if i >= warmup:
+            times.append(dt)
+    return times, threads
+
+
+def run_reference(args, rank):
+    if rank != 0:
+        return
+    batch = 2
+    times, threads = cpu_train_step_time(batch, args.steps, args.warmup)
+    ms = 1000.0 * sum(times) / len(times)
+    val = batch / (ms / 1000.0)
+    sample = f"fwd+CE/Dice+bwd of B={batch} slices (T={T_PHASES}, {HW}x{HW}) per step, fp32, oracle port of the reference"
+    line = {"impl": "reference", "metric": "train slices/s STF-LSTM-UNet", "value": round(val, 4), "unit": "slices/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms, 2),
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": workload_config(args.gpus),
+            "cpu_baseline": {"value": round(val, 4), "unit": "slices/s", "cores": threads, "kind": "port", "sample": sample},
+            "e2e": {"value": round(val, 4), "unit": "slices/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(n):
+    return {"workload": f"STF-LSTM-UNet train fwd+CE/Dice+bwd+AdamW, T={T_PHASES} x 1x{HW}x{HW}, batch {BATCH_PER_GPU}/GPU "
+                        f"(BASELINE.json configs[2] = global batch 128 on 8 GPUs)",
+            "global_batch": BATCH_PER_GPU * n, "T": T_PHASES, "hw": HW, "parallelism": f"dp{n}",
+            "l2": "per-step working set (activations ~4 GB) far exceeds the 126 MB L2; no flush needed"}
+
+
+# ------------------------------------------------------------------------------------------------
+# own arm
+# ------------------------------------------------------------------------------------------------
+def run_own(args, rank, world, local_rank):
+    import torch.distributed as dist
+    import stf_unet_b200 as S
+    from stf_unet_b200 import _lib, ops, parallel
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    torch.manual_seed(0)
+    model = S.STFLSTMUNet(1, 2, T_PHASES).to(dev)
+    net = parallel.DataParallel(model) if world > 1 else model
+    opt = torch.optim.AdamW(model.parameters(), lr=1e-3, weight_decay=1e-4, fused=True)
+    x_host, t_host = make_batch(rank)
+    x_pin, t_pin = x_host.pin_memory(), t_host.pin_memory()
+    x_dev, t_dev = x_pin.to(dev), t_pin.to(dev)
+
+    def step(x, t):
+        model.train()
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            out = net(x)
+            loss = S.criterion(out, t)
+        opt.zero_grad(set_to_none=True)
+        loss.backward()
+        opt.step()
+        return loss
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return ms.item()
+
+    for _ in range(max(args.warmup, 3)):
+        step(x_dev, t_dev)
+    n0 = _lib.launch_count()
+    with ClockSampler(local_rank) as clk:
+        total_ms = timed(lambda: step(x_dev, t_dev), args.steps)
+    launches = _lib.launch_count() - n0
+    ms_per_step = total_ms / args.steps
+    value = BATCH_PER_GPU * world / (ms_per_step / 1000.0)
+
+    # ---- end to end: pinned host -> device each step, loss read back each step ----
+    def e2e_step():
+        x = x_pin.to(dev, non_blocking=True)
+        t = t_pin.to(dev, non_blocking=True)
+        return step(x, t).item()
+
+    e2e_step()
+    e2e_ms = timed(e2e_step, args.steps) / args.steps
+    e2e_val = BATCH_PER_GPU * world / (e2e_ms / 1000.0)
+
+    # ---- roofline of the dominant kernel family: per-launch CUDA events over one extra step ----
+    roof = None
+    if rank == 0:
+        prof = ops.KernelProfiler()
+        ops.set_profiler(prof)
+        step(x_dev, t_dev)
+        torch.cuda.synchronize()
+        ops.set_profiler(None)
+        fam = prof.summary()
+        pk = peaks()
+        if fam:
+            top = max(fam.items(), key=lambda kv: kv[1]["ms"])
+            name, d = top
+            ach = d["flops"] / (d["ms"] / 1e3) / 1e12
+            roof = {"bound": "tensor", "kernel": name, "achieved": round(ach, 2), "peak": pk["tflops"], "unit": "TFLOP/s",
+                    "frac": round(ach / pk["tflops"], 4), "traffic": None, "peak_source": pk["src"],
+                    "launches": d["n"], "avg_launch_us": round(1e3 * d["ms"] / d["n"], 2),
+                    "share_of_step": round(d["ms"] / sum(v["ms"] for v in fam.values()), 3),
+                    "families": {k: {"ms": round(v["ms"], 3), "n": v["n"],
+                                     "tflops": round(v["flops"] / (v["ms"] / 1e3) / 1e12, 2) if v["ms"] > 0 else None}
+                                 for k, v in fam.items()}}
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        times, threads = cpu_train_step_time(2, 3, 1)
+        v = 2 / (sum(times) / len(times))
+        cpu = {"value": round(v, 4), "unit": "slices/s", "cores": threads, "kind": "port",
+               "sample": f"3 train steps of B=2 slices (T={T_PHASES}, {HW}x{HW}) fp32 on the oracle port, 1 warm-up"}
+
+    if rank == 0:
+        pk = peaks()
+        model_tflops = value * TRAIN_GFLOP_PER_SLICE / 1e3
+        line = {"metric": "train slices/s STF-LSTM-UNet", "value": round(value, 2), "unit": "slices/s", "n_gpus": world,
+                "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": round(ms_per_step, 3),
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+                "config": workload_config(world), "clocks": clk.summary(),
+                "e2e": {"value": round(e2e_val, 2), "unit": "slices/s", "h2d_bytes_per_step": int(x_pin.numel() * 4 + t_pin.numel() * 8) * world,
+                        "d2h_bytes_per_step": 4 * world, "ms_per_step": round(e2e_ms, 3)},
+                "gpu_launches": int(launches),
+                "model_tflops": round(model_tflops, 2), "model_frac_of_bf16_peak": round(model_tflops / world / pk["tflops"], 4),
+                "roofline": roof, "cpu_baseline": cpu}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="own", choices=["own", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (the product path has no CPU fallback; use --impl reference for the CPU arm)")
+    run_own(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

@@ -286,9 +286,18 @@ class ModelFunction(torch.autograd.Function):
         ex, module = ctx.ex, ctx.module
         d = ops.nchw_to_nhwc(dlogits.contiguous().float(), ex.dtype)
         ex.backward(ctx.out_var, d)
-        grads = tuple(ex.grads[n] for n in ctx.names)
+        # Gradients live in ONE flat fp32 buffer (module._last_flat_grad); each parameter's .grad is a view of it,
+        # assigned directly so that autograd does not clone 110 MB per step and the data-parallel all-reduce can
+        # run on the flat buffer.  A second backward before zero_grad() accumulates, as autograd would.
+        params = dict(module.named_parameters())
+        for n in ctx.names:
+            p = params[n]
+            if p.grad is None:
+                p.grad = ex.grads[n]
+            else:
+                ops.add_(p.grad, ex.grads[n]) if p.grad.is_contiguous() else p.grad.add_(ex.grads[n])
         hook = getattr(module, "_grad_ready_hook", None)
         if hook is not None:
             hook(module._last_flat_grad)
         ctx.ex = ctx.out_var = None
-        return (None, None) + grads
+        return (None, None) + (None,) * len(ctx.names)

@@ -20,6 +20,43 @@ __all__ = ["dt_code", "conv2d", "conv2d_wgrad", "pack_weight", "bn_stats", "bn_f
 _DT = {torch.float32: F32, torch.bfloat16: BF16}
 
 
+class KernelProfiler:
+    """Per-launch CUDA-event timing of the GEMM-shaped kernels (bench.py roofline leg).  Events are recorded on
+    torch's current stream, which is the stream every libstfb200 launch uses."""
+
+    def __init__(self):
+        self.records = []
+
+    def begin(self):
+        e0 = torch.cuda.Event(enable_timing=True)
+        e0.record()
+        return e0
+
+    def end(self, e0, family, flops, nbytes=0):
+        e1 = torch.cuda.Event(enable_timing=True)
+        e1.record()
+        self.records.append((family, float(flops), float(nbytes), e0, e1))
+
+    def summary(self):
+        torch.cuda.synchronize()
+        fam = {}
+        for family, flops, nbytes, e0, e1 in self.records:
+            d = fam.setdefault(family, {"ms": 0.0, "flops": 0.0, "bytes": 0.0, "n": 0})
+            d["ms"] += e0.elapsed_time(e1)
+            d["flops"] += flops
+            d["bytes"] += nbytes
+            d["n"] += 1
+        return fam
+
+
+_prof = None
+
+
+def set_profiler(p):
+    global _prof
+    _prof = p
+
+
 def dt_code(dtype):
     try:
         return _DT[dtype]
@@ -64,7 +101,18 @@ def conv2d(x, wp, Cout, k, stride, pad, *, mode=CONV_FWD, out_hw=None, x2=None, 
                    scale=_p(scale), shift=_p(shift), residual=_p(residual), N=N, H=H, W=W, C1=C1, C2=C2, Ho=Ho, Wo=Wo,
                    Cout=Cout, kh=kh, kw=kw, stride=stride, pad=pad, ldw=ldw if ldw is not None else Cout, mode=mode,
                    relu=int(bool(relu)), x_dtype=dt_code(x.dtype), y_dtype=dt_code(y.dtype), impl=impl)
-    check(_lib.load().stfb_conv2d(C.byref(p), _stream()), "conv2d")
+    if _prof is None:
+        check(_lib.load().stfb_conv2d(C.byref(p), _stream()), "conv2d")
+        return y
+    lib = _lib.load()
+    tc = impl != IMPL_SIMT and lib.stfb_conv2d_tcgen05_supported(C.byref(p)) == 1
+    # algorithmic FLOPs: transposed gathers count the taps that exist, not the zeros
+    pix = N * Ho * Wo if mode == CONV_FWD else N * H * W
+    flops = 2.0 * pix * Cout * (C1 + C2) * kh * kw
+    nbytes = (x.numel() + (0 if x2 is None else x2.numel())) * esz + y.numel() * y.element_size() + wp.numel() * esz
+    e0 = _prof.begin()
+    check(lib.stfb_conv2d(C.byref(p), _stream()), "conv2d")
+    _prof.end(e0, "conv_tcgen05" if tc else "conv_simt_" + ("bf16" if esz == 2 else "f32"), flops, nbytes)
     return y
 
 
@@ -74,9 +122,13 @@ def conv2d_wgrad(P, G, dW, k, stride, pad, cg_off=0, cg_total=None):
     N, Hp, Wp, Cp = P.shape
     _, Hg, Wg, Cg = G.shape
     kh, kw = (k, k) if isinstance(k, int) else k
+    e0 = _prof.begin() if _prof is not None else None
     check(_lib.load().stfb_conv2d_wgrad(_p(P), _p(G), _p(dW), N, Hp, Wp, Cp, Hg, Wg, Cg, cg_off,
                                         cg_total if cg_total is not None else Cg, kh, kw, stride, pad, dt_code(P.dtype),
                                         _stream()), "conv2d_wgrad")
+    if e0 is not None:
+        _prof.end(e0, "wgrad_simt_" + ("bf16" if P.element_size() == 2 else "f32"), 2.0 * N * Hp * Wp * Cp * Cg * kh * kw,
+                  (P.numel() + G.numel()) * P.element_size())
 
 
 def pack_weight(w, k_is_dim1, dtype):
