@@ -41,7 +41,7 @@ extern "C" {
 #define STFB_CONV_TRANSPOSED 1 /* iy = (oy + pad - ky)/stride when divisible      (ConvTranspose2d forward, Conv2d dgrad) */
 
 /* conv kernel families (stfb_conv_params.impl) */
-#define STFB_IMPL_AUTO 0
+#define STFB_IMPL_AUTO 0       /* == SIMT (the families take different weight packings; ask _supported first) */
 #define STFB_IMPL_SIMT 1       /* fp32-FFMA implicit GEMM (fp32-accurate mode and odd shapes) */
 #define STFB_IMPL_TCGEN05 2    /* bf16 tcgen05/TMEM implicit GEMM fed by TMA                  */
 
@@ -63,7 +63,7 @@ unsigned long long stfb_launch_count(void);
 typedef struct stfb_conv_params {
   const void* x;        /* [N, H, W, C1]  x_dtype                                  */
   const void* x2;       /* [N, H, W, C2]  or NULL                                  */
-  const void* w;        /* packed weights [kh*kw*(C1+C2), ldw] in x_dtype (see stfb_pack_weight) */
+  const void* w;        /* SIMT: packed [kh*kw*(C1+C2)][ldw]; TCGEN05: packed [Cout][ldw] (stfb_pack_weight_ex n_major=1) */
   void* y;              /* [N, Ho, Wo, Cout] y_dtype                               */
   const float* bias;    /* [Cout] or NULL                                          */
   const float* bias2;   /* [Cout] or NULL                                          */
@@ -73,7 +73,7 @@ typedef struct stfb_conv_params {
   int N, H, W, C1, C2;
   int Ho, Wo, Cout;
   int kh, kw, stride, pad;
-  int ldw;              /* row stride (elements) of w; >= Cout                     */
+  int ldw;              /* row stride (elements) of w: >= Cout (SIMT) / >= kh*kw*(C1+C2) (TCGEN05) */
   int mode;             /* STFB_CONV_FWD / STFB_CONV_TRANSPOSED                    */
   int relu;
   int x_dtype, y_dtype; /* (f32,f32) (bf16,bf16) (bf16,f32)                        */
@@ -97,6 +97,11 @@ int stfb_conv2d_wgrad(const void* P, const void* G, float* dW, int N, int Hp, in
  *   k_is_dim1 = 1: k = D1 index, n = D0 index (Conv2d forward, ConvTranspose2d dgrad, LSTM x @ W^T)
  *   k_is_dim1 = 0: k = D0 index, n = D1 index (Conv2d dgrad, ConvTranspose2d forward, LSTM dgates @ W) */
 int stfb_pack_weight(const float* w, void* wp, int D0, int D1, int kh, int kw, int k_is_dim1, int dtype, void* stream);
+/* Extended form.  n_major = 1 writes [n][(ky,kx,k)] (each output channel's K contiguous: the K-major B operand of the
+ * tcgen05 family, row stride ldw = kh*kw*K).  flip = 1 mirrors the taps (ky,kx) -> (kh-1-ky, kw-1-kx), which turns the
+ * dgrad of a stride-1 "same" convolution into a forward convolution over dy. */
+int stfb_pack_weight_ex(const float* w, void* wp, int D0, int D1, int kh, int kw, int k_is_dim1, int n_major, int flip,
+                        int dtype, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * BatchNorm2d (eps, momentum as nn.BatchNorm2d defaults 1e-5 / 0.1; torchvision BasicBlock bn1/bn2,

@@ -29,6 +29,7 @@ _SIGS = {
     "stfb_conv2d_tcgen05_supported": [C.POINTER(ConvParams)],
     "stfb_conv2d_wgrad": [_vp, _vp, _vp] + [_i] * 14 + [_vp],
     "stfb_pack_weight": [_vp, _vp, _i, _i, _i, _i, _i, _i, _vp],
+    "stfb_pack_weight_ex": [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp],
     "stfb_bn_stats": [_vp, _vp, _i, _ll, _i, _i, _vp],
     "stfb_bn_finalize_train": [_vp] * 10 + [_i, _ll, _i, _f, _f, _vp],
     "stfb_bn_fold_eval": [_vp] * 6 + [_i, _f, _vp],

@@ -1,9 +1,409 @@
-// tcgen05 / TMEM implicit-GEMM convolution family (placeholder until the kernel lands).
+// tcgen05 / TMEM implicit-GEMM convolution family (bf16 in, fp32 accumulate in tensor memory).
+//
+//   D[128 pixels x BN channels] (TMEM) += A[128 x 64] (smem, TMA) * B[BN x 64]^T (smem, TMA)   per k-block
+//
+// * GEMM rows are a TN x TH x TW patch of output pixels (TN*TH*TW = 128).  For filter tap (r, s) the A tile is
+//   the SAME patch of the NHWC input shifted by (r - pad, s - pad): one 4-D tiled TMA load with box
+//   {64 ch, TW, TH, TN}; out-of-image coordinates (the conv padding, ragged edges) are zero-filled by TMA.
+//   The box lands in shared memory as 128 rows x 128 B with the 128-byte swizzle, which is exactly the K-major
+//   SWIZZLE_128B operand layout tcgen05.mma consumes -- no im2col buffer, no register staging.
+// * B is the weight matrix packed [Cout][(ky,kx,ci)] (K-major), box {64, BN}.
+// * Warp roles: warp 0 = TMA producer, warp 1 = TMEM allocator + single-thread MMA issuer, warps 2..5 = epilogue
+//   (tcgen05.ld -> bias / folded BN / residual / ReLU -> bf16|fp32 NHWC stores).  smem ring of STAGES k-blocks
+//   synchronised with mbarriers (TMA complete_tx -> MMA, tcgen05.commit -> producer / epilogue).
+// * Concat inputs (decoder fusion, UNet skip) are two tensor maps walking one K loop: no materialised torch.cat.
+//
+// Used for: stride-1 "same" Conv2d forward, its dgrad (flipped weights), the LSTM gate GEMMs (1x1).
 #include "common.cuh"
+#include <cuda.h>
+
 namespace stfb {
-int conv2d_tcgen05_supported(const stfb_conv_params*) { return 0; }
-int conv2d_tcgen05(const stfb_conv_params*, cudaStream_t) {
-  set_error("conv2d: tcgen05 family not built");
+
+// ------------------------------------------------------------------------------------------------
+// PTX wrappers
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// Bounded wait: a broken pipeline traps (the launch fails loudly) instead of hanging the GPU.
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t spins = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    if (++spins > (1u << 24)) __trap();
+  }
+}
+
+__device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* tm, uint64_t* bar, int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(tm)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* tm, uint64_t* bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(tm)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void prefetch_tensormap(const CUtensorMap* tm) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(tm)) : "memory");
+}
+
+__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tmem_relinquish() { asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld_x32(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor layout):
+// [0,14) addr>>4 | [16,30) LBO>>4 (unused for swizzled K-major) | [32,46) SBO>>4 = 1024 B between 8-row groups |
+// [46,48) version = 1 | [61,64) layout = 2 (SWIZZLE_128B)
+__device__ __forceinline__ uint64_t make_kmajor_sw128_desc(uint32_t saddr) {
+  return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
+}
+// instruction descriptor (cute::UMMA::InstrDescriptor): D=f32, A=B=bf16, both K-major, N>>3 @17, M>>4 @24
+__host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+// ------------------------------------------------------------------------------------------------
+struct TcArgs {
+  void* y;
+  const void* residual;
+  const float* bias;
+  const float* bias2;
+  const float* scale;
+  const float* shift;
+  int N, H, W, Cout;
+  int C1, C2;
+  int kh, kw, pad;
+  int TW, TH, TN;      // pixel patch of one tile, TN*TH*TW == 128
+  int tiles_w, tiles_h;
+  int relu;
+};
+
+constexpr int TC_BM = 128;
+constexpr int TC_BK = 64;                    // 64 bf16 = 128 B = one swizzle row
+constexpr int TC_A_BYTES = TC_BM * TC_BK * 2;  // 16 KB
+constexpr int TC_THREADS = 192;
+
+template <int BN, int STAGES>
+constexpr int tc_smem_bytes() {
+  return STAGES * (TC_A_BYTES + BN * TC_BK * 2) + 3 * BN * 4 + 256 + 1024;
+}
+
+template <int BN, int STAGES, typename TO>
+__global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(const __grid_constant__ CUtensorMap tmA,
+                                                              const __grid_constant__ CUtensorMap tmA2,
+                                                              const __grid_constant__ CUtensorMap tmB, const TcArgs a) {
+  constexpr int B_BYTES = BN * TC_BK * 2;
+  constexpr int STAGE_BYTES = TC_A_BYTES + B_BYTES;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  float* s_par = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES);              // [3][BN]: bias, scale, shift
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(s_par + 3 * BN);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* accum_bar = empty_bar + STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum_bar + 1);
+
+  const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+  const int n0 = blockIdx.y * BN;
+  int mt = blockIdx.x;
+  const int wb = mt % a.tiles_w; mt /= a.tiles_w;
+  const int hb = mt % a.tiles_h;
+  const int nb = mt / a.tiles_h;
+  const int Cin = a.C1 + a.C2;
+  const int cpt = Cin / TC_BK;                 // k-blocks per filter tap
+  const int num_kb = a.kh * a.kw * cpt;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    mbar_init(accum_bar, 1);
+    fence_barrier_init();
+    prefetch_tensormap(&tmA);
+    prefetch_tensormap(&tmB);
+    if (a.C2 > 0) prefetch_tensormap(&tmA2);
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, BN);
+    tmem_relinquish();
+  }
+  // per-column epilogue parameters
+  for (int i = threadIdx.x; i < BN; i += TC_THREADS) {
+    const int c = n0 + i;
+    float b = 0.f;
+    if (a.bias) b += a.bias[c];
+    if (a.bias2) b += a.bias2[c];
+    s_par[i] = b;
+    s_par[BN + i] = a.scale ? a.scale[c] : 1.f;
+    s_par[2 * BN + i] = a.shift ? a.shift[c] : 0.f;
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_acc = *tmem_slot;
+
+  if (warp == 0) {
+    // ================= TMA producer =================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int kb = 0; kb < num_kb; ++kb) {
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        const int tap = kb / cpt, chunk = kb - tap * cpt;
+        const int r = tap / a.kw, s = tap - r * a.kw;
+        const int c = chunk * TC_BK;
+        uint8_t* sa = smem + stage * STAGE_BYTES;
+        uint8_t* sb = sa + TC_A_BYTES;
+        mbar_arrive_expect_tx(&full_bar[stage], STAGE_BYTES);
+        const int w0 = wb * a.TW - a.pad + s, h0 = hb * a.TH - a.pad + r, i0 = nb * a.TN;
+        if (c < a.C1) tma_load_4d(sa, &tmA, &full_bar[stage], c, w0, h0, i0);
+        else tma_load_4d(sa, &tmA2, &full_bar[stage], c - a.C1, w0, h0, i0);
+        tma_load_2d(sb, &tmB, &full_bar[stage], tap * Cin + c, n0);
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    // ================= MMA issuer =================
+    constexpr uint32_t idesc = make_idesc_bf16(TC_BM, BN);
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int kb = 0; kb < num_kb; ++kb) {
+      mbar_wait(&full_bar[stage], phase);
+      tc_fence_after();
+      if (lane == 0) {
+        const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
+        const uint64_t adesc = make_kmajor_sw128_desc(sa);
+        const uint64_t bdesc = make_kmajor_sw128_desc(sa + TC_A_BYTES);
+#pragma unroll
+        for (int k = 0; k < TC_BK / 16; ++k) {
+          // advance 16 bf16 = 32 B along K inside the swizzle row: +2 in the (addr >> 4) field
+          umma_bf16(tmem_acc, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kb | k) != 0);
+        }
+        umma_commit(&empty_bar[stage]);                 // frees the smem slot when these MMAs have read it
+        if (kb == num_kb - 1) umma_commit(accum_bar);   // accumulator complete
+      }
+      __syncwarp();
+      if (++stage == STAGES) { stage = 0; phase ^= 1; }
+    }
+  } else {
+    // ================= epilogue (warps 2..5; TMEM lane quadrant = warp % 4) =================
+    const int q = warp & 3;
+    const int m = q * 32 + lane;                       // accumulator row = TMEM lane = pixel in the patch
+    const int tw = m % a.TW, th = (m / a.TW) % a.TH, tn = m / (a.TW * a.TH);
+    const int ow = wb * a.TW + tw, oh = hb * a.TH + th, on = nb * a.TN + tn;
+    const bool valid = ow < a.W && oh < a.H && on < a.N;
+    const long long row = (((long long)on * a.H + oh) * a.W + ow) * a.Cout + n0;
+    TO* __restrict__ yp = reinterpret_cast<TO*>(a.y) + row;
+    const TO* rp = a.residual ? reinterpret_cast<const TO*>(a.residual) + row : nullptr;
+    mbar_wait(accum_bar, 0);
+    tc_fence_after();
+    const uint32_t taddr = tmem_acc + ((uint32_t)(q * 32) << 16);
+#pragma unroll 1
+    for (int c0 = 0; c0 < BN; c0 += 32) {
+      uint32_t r[32];
+      tmem_ld_x32(taddr + c0, r);
+      tmem_ld_wait();
+      if (valid) {
+        float v[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          v[j] = fmaf(__uint_as_float(r[j]) + s_par[c0 + j], s_par[BN + c0 + j], s_par[2 * BN + c0 + j]);
+        if (rp) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 8) {
+            f8 t = ld8(rp + c0 + j);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) v[j + e] += t.v[e];
+          }
+        }
+        if (a.relu) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+        }
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) st4(yp + c0 + j, f4{{v[j], v[j + 1], v[j + 2], v[j + 3]}});
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_acc, BN);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+    else
+      cudaGetLastError();
+  }
+  return fn;
+}
+
+static int pow2_floor(int v) { int p = 1; while (p * 2 <= v) p *= 2; return p; }
+
+static void pick_patch(int N, int H, int W, int& TW, int& TH, int& TN) {
+  TW = pow2_floor(W); if (TW > 16) TW = 16;
+  TH = pow2_floor(H); if (TH > TC_BM / TW) TH = TC_BM / TW;
+  TN = TC_BM / (TW * TH);
+}
+
+static int pick_bn(int Cout) {
+  if (Cout % 256 == 0) return 256;
+  if (Cout % 128 == 0) return 128;
+  if (Cout % 64 == 0) return 64;
+  if (Cout % 32 == 0) return 32;
+  return 0;
+}
+
+int conv2d_tcgen05_supported(const stfb_conv_params* p) {
+  if (p->x_dtype != STFB_BF16) return 0;
+  if (p->mode != STFB_CONV_FWD || p->stride != 1) return 0;
+  if (p->kh != p->kw || 2 * p->pad != p->kh - 1 || p->Ho != p->H || p->Wo != p->W) return 0;
+  if (p->C1 % 64 != 0 || p->C2 % 64 != 0) return 0;
+  if (pick_bn(p->Cout) == 0) return 0;
+  auto al = [](const void* q, int b) { return q == nullptr || (reinterpret_cast<uintptr_t>(q) % b) == 0; };
+  if (!al(p->x, 16) || !al(p->x2, 16) || !al(p->y, 16) || !al(p->residual, 16)) return 0;
+  if ((long long)p->N * p->H * p->W > 2000000000LL) return 0;
+  return 1;
+}
+
+static bool encode_act(EncodeTiledFn enc, CUtensorMap* tm, const void* base, int N, int H, int W, int C, int TW, int TH, int TN) {
+  cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
+  cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
+  cuuint32_t box[4] = {(cuuint32_t)TC_BK, (cuuint32_t)TW, (cuuint32_t)TH, (cuuint32_t)TN};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  return enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr,
+             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+template <int BN, int STAGES, typename TO>
+static int launch_tc(const CUtensorMap& tA, const CUtensorMap& tA2, const CUtensorMap& tB, const TcArgs& a, dim3 grid,
+                     cudaStream_t st) {
+  constexpr int smem = tc_smem_bytes<BN, STAGES>();
+  static bool configured = false;
+  if (!configured) {
+    if (cudaFuncSetAttribute(conv_tc_kernel<BN, STAGES, TO>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) {
+      set_error("conv2d(tcgen05): cannot reserve %d bytes of shared memory: %s", smem, cudaGetErrorString(cudaGetLastError()));
+      return STFB_ECUDA;
+    }
+    configured = true;
+  }
+  conv_tc_kernel<BN, STAGES, TO><<<grid, TC_THREADS, smem, st>>>(tA, tA2, tB, a);
+  return post_launch("conv2d(tcgen05)");
+}
+
+int conv2d_tcgen05(const stfb_conv_params* p, cudaStream_t st) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) { set_error("conv2d(tcgen05): cuTensorMapEncodeTiled not available from the driver"); return STFB_ECUDA; }
+  if ((long long)p->N * p->H * p->W == 0) return STFB_OK;
+  if (reinterpret_cast<uintptr_t>(p->w) % 16 != 0) { set_error("conv2d(tcgen05): weights must be 16-byte aligned"); return STFB_EINVAL; }
+  TcArgs a{};
+  a.y = p->y; a.residual = p->residual; a.bias = p->bias; a.bias2 = p->bias2; a.scale = p->scale; a.shift = p->shift;
+  a.N = p->N; a.H = p->H; a.W = p->W; a.Cout = p->Cout; a.C1 = p->C1; a.C2 = p->C2; a.kh = p->kh; a.kw = p->kw; a.pad = p->pad;
+  a.relu = p->relu;
+  pick_patch(p->N, p->H, p->W, a.TW, a.TH, a.TN);
+  a.tiles_w = (p->W + a.TW - 1) / a.TW;
+  a.tiles_h = (p->H + a.TH - 1) / a.TH;
+  const int tiles_n = (p->N + a.TN - 1) / a.TN;
+  const int BN = pick_bn(p->Cout);
+  const int Ktot = p->kh * p->kw * (p->C1 + p->C2);
+
+  CUtensorMap tA, tA2, tB;
+  if (!encode_act(enc, &tA, p->x, p->N, p->H, p->W, p->C1, a.TW, a.TH, a.TN)) {
+    set_error("conv2d(tcgen05): cuTensorMapEncodeTiled failed for x"); return STFB_ECUDA;
+  }
+  tA2 = tA;
+  if (p->C2 > 0 && !encode_act(enc, &tA2, p->x2, p->N, p->H, p->W, p->C2, a.TW, a.TH, a.TN)) {
+    set_error("conv2d(tcgen05): cuTensorMapEncodeTiled failed for x2"); return STFB_ECUDA;
+  }
+  {
+    cuuint64_t dims[2] = {(cuuint64_t)Ktot, (cuuint64_t)p->Cout};
+    cuuint64_t strides[1] = {(cuuint64_t)p->ldw * 2};
+    cuuint32_t box[2] = {(cuuint32_t)TC_BK, (cuuint32_t)BN};
+    cuuint32_t estr[2] = {1, 1};
+    if (enc(&tB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(p->w), dims, strides, box, estr,
+            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS) {
+      set_error("conv2d(tcgen05): cuTensorMapEncodeTiled failed for the weights"); return STFB_ECUDA;
+    }
+  }
+  dim3 grid((unsigned)(tiles_n * a.tiles_h * a.tiles_w), (unsigned)(p->Cout / BN));
+  const bool f32out = p->y_dtype == STFB_F32;
+#define TC_LAUNCH(BN_, ST_)                                                                                   \
+  return f32out ? launch_tc<BN_, ST_, float>(tA, tA2, tB, a, grid, st) : launch_tc<BN_, ST_, __nv_bfloat16>(tA, tA2, tB, a, grid, st)
+  switch (BN) {
+    case 256: TC_LAUNCH(256, 4);
+    case 128: TC_LAUNCH(128, 3);
+    case 64: TC_LAUNCH(64, 4);
+    case 32: TC_LAUNCH(32, 4);
+  }
+#undef TC_LAUNCH
+  set_error("conv2d(tcgen05): no tile for Cout=%d", p->Cout);
   return STFB_ENOTSUP;
 }
+
 }  // namespace stfb

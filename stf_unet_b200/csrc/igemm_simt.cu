@@ -434,17 +434,25 @@ int conv2d_wgrad_simt(const WgradArgs& a0, int dtype, cudaStream_t st) {
 // =================================================================================================
 template <typename T>
 __global__ void pack_weight_kernel(const float* __restrict__ w, T* __restrict__ wp, int D0, int D1, int khw,
-                                   int k_is_dim1) {
+                                   int k_is_dim1, int n_major, int flip) {
   const long long total = (long long)D0 * D1 * khw;
   const int Kc = k_is_dim1 ? D1 : D0, Nc = k_is_dim1 ? D0 : D1;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    // destination index i = (tap*Kc + k)*Nc + n   (coalesced writes)
-    const int n = (int)(i % Nc);
-    const long long r = i / Nc;
-    const int k = (int)(r % Kc);
-    const int tap = (int)(r / Kc);
+    int n, k, tap;
+    if (!n_major) {   // destination index i = (tap*Kc + k)*Nc + n
+      n = (int)(i % Nc);
+      const long long r = i / Nc;
+      k = (int)(r % Kc);
+      tap = (int)(r / Kc);
+    } else {          // destination index i = (n*khw + tap)*Kc + k     ([N][(tap,k)], K-major rows for tcgen05)
+      k = (int)(i % Kc);
+      const long long r = i / Kc;
+      tap = (int)(r % khw);
+      n = (int)(r / khw);
+    }
     const int d0 = k_is_dim1 ? n : k, d1 = k_is_dim1 ? k : n;
-    st1(wp + i, w[((long long)d0 * D1 + d1) * khw + tap]);
+    const int stap = flip ? (khw - 1 - tap) : tap;   // spatial flip (ky,kx) -> (kh-1-ky, kw-1-kx)
+    st1(wp + i, w[((long long)d0 * D1 + d1) * khw + stap]);
   }
 }
 
@@ -462,7 +470,11 @@ static int validate_conv(const stfb_conv_params* p) {
                p->Wo, p->Cout);
   STFB_REQUIRE(p->C2 == 0 || p->x2 != nullptr, "conv2d: C2 > 0 needs x2");
   STFB_REQUIRE(p->kh > 0 && p->kw > 0 && p->stride > 0 && p->pad >= 0, "conv2d: bad kernel geometry");
-  STFB_REQUIRE(p->ldw >= p->Cout, "conv2d: ldw (%d) < Cout (%d)", p->ldw, p->Cout);
+  if (p->impl == STFB_IMPL_TCGEN05)
+    STFB_REQUIRE(p->ldw >= p->kh * p->kw * (p->C1 + p->C2) && p->ldw % 8 == 0,
+                 "conv2d(tcgen05): weights are [Cout][ldw] K-major, ldw (%d) must be >= kh*kw*Cin and a multiple of 8", p->ldw);
+  else
+    STFB_REQUIRE(p->ldw >= p->Cout, "conv2d: ldw (%d) < Cout (%d)", p->ldw, p->Cout);
   STFB_REQUIRE(p->mode == STFB_CONV_FWD || p->mode == STFB_CONV_TRANSPOSED, "conv2d: bad mode %d", p->mode);
   STFB_REQUIRE((p->scale == nullptr) == (p->shift == nullptr), "conv2d: scale and shift come together");
   if (p->mode == STFB_CONV_FWD) {
@@ -477,8 +489,8 @@ static int validate_conv(const stfb_conv_params* p) {
 }
 
 extern "C" int stfb_conv2d_tcgen05_supported(const stfb_conv_params* p) {
-  if (validate_conv(p) != STFB_OK) return 0;
-  return stfb::conv2d_tcgen05_supported(p);
+  if (p == nullptr) return 0;
+  return stfb::conv2d_tcgen05_supported(p);   // pure shape / dtype / alignment check; w and ldw are not inspected
 }
 
 extern "C" int stfb_conv2d(const stfb_conv_params* p, void* stream) {
@@ -493,8 +505,7 @@ extern "C" int stfb_conv2d(const stfb_conv_params* p, void* stream) {
     }
     return stfb::conv2d_tcgen05(p, s);
   }
-  if (p->impl == STFB_IMPL_AUTO && stfb::conv2d_tcgen05_supported(p)) return stfb::conv2d_tcgen05(p, s);
-  return conv2d_simt(p, s);
+  return conv2d_simt(p, s);   // STFB_IMPL_AUTO == SIMT: the two families take different weight packings
 }
 
 extern "C" int stfb_conv2d_wgrad(const void* P, const void* G, float* dW, int N, int Hp, int Wp, int Cp, int Hg, int Wg,
@@ -512,8 +523,8 @@ extern "C" int stfb_conv2d_wgrad(const void* P, const void* G, float* dW, int N,
   return conv2d_wgrad_simt(a, dtype, reinterpret_cast<cudaStream_t>(stream));
 }
 
-extern "C" int stfb_pack_weight(const float* w, void* wp, int D0, int D1, int kh, int kw, int k_is_dim1, int dtype,
-                                void* stream) {
+extern "C" int stfb_pack_weight_ex(const float* w, void* wp, int D0, int D1, int kh, int kw, int k_is_dim1, int n_major,
+                                   int flip, int dtype, void* stream) {
   STFB_REQUIRE(w && wp && D0 > 0 && D1 > 0 && kh > 0 && kw > 0, "pack_weight: bad arguments");
   STFB_REQUIRE(dtype == STFB_F32 || dtype == STFB_BF16, "pack_weight: bad dtype");
   STFB_DEVICE_OR_RETURN();
@@ -521,7 +532,14 @@ extern "C" int stfb_pack_weight(const float* w, void* wp, int D0, int D1, int kh
   const long long total = (long long)D0 * D1 * kh * kw;
   int blocks = ceil_div(total, 256);
   if (blocks > 8 * num_sms()) blocks = 8 * num_sms();
-  if (dtype == STFB_F32) pack_weight_kernel<float><<<blocks, 256, 0, s>>>(w, reinterpret_cast<float*>(wp), D0, D1, kh * kw, k_is_dim1);
-  else pack_weight_kernel<__nv_bfloat16><<<blocks, 256, 0, s>>>(w, reinterpret_cast<__nv_bfloat16*>(wp), D0, D1, kh * kw, k_is_dim1);
+  if (dtype == STFB_F32)
+    pack_weight_kernel<float><<<blocks, 256, 0, s>>>(w, reinterpret_cast<float*>(wp), D0, D1, kh * kw, k_is_dim1, n_major, flip);
+  else
+    pack_weight_kernel<__nv_bfloat16><<<blocks, 256, 0, s>>>(w, reinterpret_cast<__nv_bfloat16*>(wp), D0, D1, kh * kw, k_is_dim1, n_major, flip);
   return post_launch("pack_weight");
+}
+
+extern "C" int stfb_pack_weight(const float* w, void* wp, int D0, int D1, int kh, int kw, int k_is_dim1, int dtype,
+                                void* stream) {
+  return stfb_pack_weight_ex(w, wp, D0, D1, kh, kw, k_is_dim1, 0, 0, dtype, stream);
 }

@@ -14,7 +14,7 @@ from ._lib import BF16, CONV_FWD, CONV_TRANSPOSED, F32, IMPL_AUTO, IMPL_SIMT, IM
 
 __all__ = ["dt_code", "conv2d", "conv2d_wgrad", "pack_weight", "bn_stats", "bn_finalize_train", "bn_fold_eval",
            "bn_apply", "bn_bwd", "colsum", "maxpool_fwd", "maxpool_bwd", "bilinear_fwd", "bilinear_bwd",
-           "lstm_cell_fwd", "lstm_cell_bwd", "pack_series", "nhwc_to_nchw", "nchw_to_nhwc", "add_", "cast",
+           "tcgen05_ok", "lstm_cell_fwd", "lstm_cell_bwd", "pack_series", "nhwc_to_nchw", "nchw_to_nhwc", "add_", "cast",
            "ce_dice_fwd", "ce_dice_bwd", "CONV_FWD", "CONV_TRANSPOSED", "IMPL_AUTO", "IMPL_SIMT", "IMPL_TCGEN05"]
 
 _DT = {torch.float32: F32, torch.bfloat16: BF16}
@@ -97,6 +97,8 @@ def conv2d(x, wp, Cout, k, stride, pad, *, mode=CONV_FWD, out_hw=None, x2=None, 
     y_dtype = y_dtype or x.dtype
     y = out if out is not None else torch.empty((N, Ho, Wo, Cout), dtype=y_dtype, device=x.device)
     esz = x.element_size()
+    if impl == IMPL_TCGEN05 and ldw is None:
+        ldw = wp.shape[1]
     p = ConvParams(x=_p(x), x2=_p(x2), w=wp.data_ptr() + w_offset * esz, y=_p(y), bias=_p(bias), bias2=_p(bias2),
                    scale=_p(scale), shift=_p(shift), residual=_p(residual), N=N, H=H, W=W, C1=C1, C2=C2, Ho=Ho, Wo=Wo,
                    Cout=Cout, kh=kh, kw=kw, stride=stride, pad=pad, ldw=ldw if ldw is not None else Cout, mode=mode,
@@ -105,7 +107,7 @@ def conv2d(x, wp, Cout, k, stride, pad, *, mode=CONV_FWD, out_hw=None, x2=None, 
         check(_lib.load().stfb_conv2d(C.byref(p), _stream()), "conv2d")
         return y
     lib = _lib.load()
-    tc = impl != IMPL_SIMT and lib.stfb_conv2d_tcgen05_supported(C.byref(p)) == 1
+    tc = impl == IMPL_TCGEN05
     # algorithmic FLOPs: transposed gathers count the taps that exist, not the zeros
     pix = N * Ho * Wo if mode == CONV_FWD else N * H * W
     flops = 2.0 * pix * Cout * (C1 + C2) * kh * kw
@@ -131,17 +133,30 @@ def conv2d_wgrad(P, G, dW, k, stride, pad, cg_off=0, cg_total=None):
                   (P.numel() + G.numel()) * P.element_size())
 
 
-def pack_weight(w, k_is_dim1, dtype):
-    """[D0, D1, kh, kw] (or [D0, D1]) fp32 parameter -> [(ky,kx,k), n] GEMM operand in `dtype`."""
+def pack_weight(w, k_is_dim1, dtype, n_major=False, flip=False):
+    """[D0, D1, kh, kw] (or [D0, D1]) fp32 parameter -> GEMM operand in `dtype`:
+    [(ky,kx,k), n] (SIMT family) or, with n_major, [n, (ky,kx,k)] (tcgen05 family)."""
     _need_cuda(w)
     if w.dim() == 2:
         D0, D1, kh, kw = w.shape[0], w.shape[1], 1, 1
     else:
         D0, D1, kh, kw = w.shape
     Kc, Nc = (D1, D0) if k_is_dim1 else (D0, D1)
-    wp = torch.empty((kh * kw * Kc, Nc), dtype=dtype, device=w.device)
-    check(_lib.load().stfb_pack_weight(_p(w), _p(wp), D0, D1, kh, kw, int(k_is_dim1), dt_code(dtype), _stream()), "pack_weight")
+    shape = (Nc, kh * kw * Kc) if n_major else (kh * kw * Kc, Nc)
+    wp = torch.empty(shape, dtype=dtype, device=w.device)
+    check(_lib.load().stfb_pack_weight_ex(_p(w), _p(wp), D0, D1, kh, kw, int(k_is_dim1), int(n_major), int(flip),
+                                          dt_code(dtype), _stream()), "pack_weight")
     return wp
+
+
+def tcgen05_ok(x, Cout, k, stride, pad, mode=CONV_FWD, x2=None, out_hw=None, y_dtype=None):
+    """Shape/dtype check: can the tcgen05 family run this convolution?"""
+    N, H, W, C1 = x.shape
+    C2 = 0 if x2 is None else x2.shape[3]
+    Ho, Wo = out_hw if out_hw is not None else conv_out_hw(H, W, k, stride, pad, transposed=(mode == CONV_TRANSPOSED))
+    p = ConvParams(x=_p(x), x2=_p(x2), N=N, H=H, W=W, C1=C1, C2=C2, Ho=Ho, Wo=Wo, Cout=Cout, kh=k, kw=k, stride=stride,
+                   pad=pad, mode=mode, x_dtype=dt_code(x.dtype), y_dtype=dt_code(y_dtype or x.dtype))
+    return _lib.load().stfb_conv2d_tcgen05_supported(C.byref(p)) == 1
 
 
 def bn_stats(x, G, R, C):

@@ -325,3 +325,65 @@ def test_errors_are_raised_not_swallowed():
         ops.conv2d(x.cpu(), wp, 8, 1, 1, 0)
     with pytest.raises(RuntimeError, match="tcgen05"):
         ops.conv2d(x, wp, 8, 1, 1, 0, impl=ops.IMPL_TCGEN05)   # fp32 is never a tensor-core shape
+
+
+# ------------------------------------------------------------------------------------------------
+# tcgen05 / TMEM family
+# ------------------------------------------------------------------------------------------------
+TC_CASES = [
+    # N, H, W, C1, C2, Cout, k
+    (2, 16, 16, 64, 0, 64, 3),       # one 16x8 patch per tile, BN=64
+    (3, 8, 8, 128, 0, 256, 3),       # two images per tile, ragged N (3 = 2 + 1), BN=256
+    (1, 25, 25, 64, 0, 128, 3),      # ragged H/W (100/4), BN=128
+    (2, 4, 4, 512, 0, 512, 3),       # TN=8 patch > N, deep K (72 k-blocks), two N tiles
+    (2, 32, 32, 64, 64, 64, 1),      # dual-source 1x1 fusion
+    (2, 16, 16, 128, 128, 128, 3),   # dual-source 3x3 (UNet decoder)
+    (4, 16, 16, 64, 0, 256, 1),      # LSTM gate GEMM shape (1x1, N = 4C)
+    (1, 64, 64, 64, 0, 32, 3),       # BN=32
+    (16, 32, 32, 128, 0, 128, 3),    # many tiles: exercises co-resident CTAs
+]
+
+
+@pytest.mark.parametrize("case", TC_CASES)
+def test_conv_tcgen05_matches_reference(case):
+    N, H, W, C1, C2, Cout, k = case
+    dtype = torch.bfloat16
+    pad = (k - 1) // 2
+    x = q(rnd(N, C1 + C2, H, W, seed=1), dtype)
+    w = q(rnd(Cout, C1 + C2, k, k, seed=2, scale=(1.0 / (k * k * (C1 + C2)) ** 0.5)), dtype)
+    x1 = nhwc(x[:, :C1], dtype)
+    x2 = nhwc(x[:, C1:], dtype) if C2 else None
+    assert ops.tcgen05_ok(x1, Cout, k, 1, pad, x2=x2)
+    wp = ops.pack_weight(w.contiguous(), True, dtype, n_major=True)
+    assert wp.shape == (Cout, k * k * (C1 + C2))
+    ref = F.conv2d(x, w, None, 1, pad)
+    y = ops.conv2d(x1, wp, Cout, k, 1, pad, x2=x2, y_dtype=torch.float32, impl=ops.IMPL_TCGEN05)
+    torch.cuda.synchronize()
+    assert rel(nchw(y), ref) < 2e-3
+    # fused epilogue, bf16 out
+    bias, scale, shift = rnd(Cout, seed=3), rnd(Cout, seed=4).abs() + 0.5, rnd(Cout, seed=5)
+    res = q(rnd(*ref.shape, seed=6), dtype)
+    ref2 = F.relu((ref + bias.view(1, -1, 1, 1)) * scale.view(1, -1, 1, 1) + shift.view(1, -1, 1, 1) + res)
+    y2 = ops.conv2d(x1, wp, Cout, k, 1, pad, x2=x2, bias=bias, scale=scale, shift=shift, residual=nhwc(res, dtype),
+                    relu=True, impl=ops.IMPL_TCGEN05)
+    assert y2.dtype == dtype
+    assert rel(nchw(y2), ref2) < 1e-2
+    # agrees with the SIMT family on identical inputs
+    wps = ops.pack_weight(w.contiguous(), True, dtype)
+    y3 = ops.conv2d(x1, wps, Cout, k, 1, pad, x2=x2, y_dtype=torch.float32, impl=ops.IMPL_SIMT)
+    assert rel(y, y3) < 1e-5
+
+
+def test_conv_tcgen05_dgrad_via_flipped_weights():
+    N, H, W, Cin, Cout, k = 2, 16, 16, 128, 64, 3
+    dtype = torch.bfloat16
+    x = q(rnd(N, Cin, H, W, seed=1), dtype).requires_grad_(True)
+    w = q(rnd(Cout, Cin, k, k, seed=2, scale=0.05), dtype)
+    y = F.conv2d(x, w, None, 1, 1)
+    dy = q(rnd(*y.shape, seed=3), dtype)
+    y.backward(dy)
+    # dgrad as a forward conv over dy: B[n = ci][(ky', kx', co)] = W[co][ci][k-1-ky'][k-1-kx']
+    wpd = ops.pack_weight(w.contiguous(), False, dtype, n_major=True, flip=True)
+    assert wpd.shape == (Cin, k * k * Cout)
+    dx = ops.conv2d(nhwc(dy, dtype), wpd, Cin, k, 1, 1, y_dtype=torch.float32, impl=ops.IMPL_TCGEN05)
+    assert rel(nchw(dx), x.grad) < 2e-3
