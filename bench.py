@@ -214,6 +214,9 @@ def run_own(args, rank, world, local_rank):
         torch.cuda.synchronize()
         ops.set_profiler(None)
         fam = prof.summary()
+        if args.profile_detail:
+            for ms, n, tf, family, tag in prof.top(40):
+                print(f"[prof] {ms:8.3f} ms  n={n:3d}  {tf:7.1f} TF/s  {family:18s} {tag}", file=sys.stderr)
         pk = peaks()
         if fam:
             top = max(fam.items(), key=lambda kv: kv[1]["ms"])
@@ -258,6 +261,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="own", choices=["own", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--profile-detail", action="store_true", help="print the slowest GEMM-family launches to stderr")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

@@ -89,9 +89,13 @@ int stfb_conv2d_tcgen05_supported(const stfb_conv_params* p);
  *   G = gathered tensor  [N, Hg, Wg, Cg] (x of a Conv2d;  dy of a ConvTranspose2d), gather iy = py*stride - pad + ky.
  *   dW is fp32 in the reference parameter layout ([Cout,Cin,kh,kw] for Conv2d, [Cin,Cout,kh,kw] for
  *   ConvTranspose2d, [4C,C] for the LSTM matrices) and is ACCUMULATED into (caller zeroes it).
- * Replaces: autograd of the operators listed above (loss.backward(), train_utils/train_and_eval.py:397-404). */
+ * Replaces: autograd of the operators listed above (loss.backward(), train_utils/train_and_eval.py:397-404).
+ * impl: STFB_IMPL_AUTO picks the tcgen05 family when the shape allows (bf16, stride-1 "same" geometry, Cg % 64 == 0,
+ * Cp % 64 == 0), else the SIMT family; STFB_IMPL_SIMT / STFB_IMPL_TCGEN05 force one. */
 int stfb_conv2d_wgrad(const void* P, const void* G, float* dW, int N, int Hp, int Wp, int Cp, int Hg, int Wg, int Cg,
-                      int cg_off, int cg_total, int kh, int kw, int stride, int pad, int dtype, void* stream);
+                      int cg_off, int cg_total, int kh, int kw, int stride, int pad, int dtype, int impl, void* stream);
+int stfb_conv2d_wgrad_tcgen05_supported(const void* P, const void* G, int N, int Hp, int Wp, int Cp, int Hg, int Wg, int Cg,
+                                        int kh, int kw, int stride, int pad, int dtype);
 
 /* Parameter layout [D0][D1][kh][kw] fp32 -> GEMM layout [(ky,kx,k)][n] in dtype.
  *   k_is_dim1 = 1: k = D1 index, n = D0 index (Conv2d forward, ConvTranspose2d dgrad, LSTM x @ W^T)

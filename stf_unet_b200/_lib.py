@@ -27,7 +27,8 @@ _vp, _i, _ll, _f = C.c_void_p, C.c_int, C.c_longlong, C.c_float
 _SIGS = {
     "stfb_conv2d": [C.POINTER(ConvParams), _vp],
     "stfb_conv2d_tcgen05_supported": [C.POINTER(ConvParams)],
-    "stfb_conv2d_wgrad": [_vp, _vp, _vp] + [_i] * 14 + [_vp],
+    "stfb_conv2d_wgrad": [_vp, _vp, _vp] + [_i] * 15 + [_vp],
+    "stfb_conv2d_wgrad_tcgen05_supported": [_vp, _vp] + [_i] * 12,
     "stfb_pack_weight": [_vp, _vp, _i, _i, _i, _i, _i, _i, _vp],
     "stfb_pack_weight_ex": [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp],
     "stfb_bn_stats": [_vp, _vp, _i, _ll, _i, _i, _vp],

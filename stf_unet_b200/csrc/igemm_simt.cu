@@ -460,7 +460,14 @@ __global__ void pack_weight_kernel(const float* __restrict__ w, T* __restrict__ 
 
 using namespace stfb;
 
-namespace stfb { int conv2d_tcgen05(const stfb_conv_params* p, cudaStream_t st); int conv2d_tcgen05_supported(const stfb_conv_params* p); }
+namespace stfb {
+int conv2d_tcgen05(const stfb_conv_params* p, cudaStream_t st);
+int conv2d_tcgen05_supported(const stfb_conv_params* p);
+int wgrad_tcgen05_supported(int N, int Hp, int Wp, int Cp, int Hg, int Wg, int Cg, int kh, int kw, int stride, int pad,
+                            int dtype, const void* P, const void* G);
+int wgrad_tcgen05(const void* P, const void* G, const void* G2, float* dW, int N, int H, int W, int Cp, int C1, int C2,
+                  int cg_off, int cg_total, int kh, int kw, int pad, cudaStream_t st);
+}
 
 static int validate_conv(const stfb_conv_params* p) {
   STFB_REQUIRE(p != nullptr, "conv2d: null params");
@@ -508,8 +515,13 @@ extern "C" int stfb_conv2d(const stfb_conv_params* p, void* stream) {
   return conv2d_simt(p, s);   // STFB_IMPL_AUTO == SIMT: the two families take different weight packings
 }
 
+extern "C" int stfb_conv2d_wgrad_tcgen05_supported(const void* P, const void* G, int N, int Hp, int Wp, int Cp, int Hg, int Wg,
+                                                   int Cg, int kh, int kw, int stride, int pad, int dtype) {
+  return stfb::wgrad_tcgen05_supported(N, Hp, Wp, Cp, Hg, Wg, Cg, kh, kw, stride, pad, dtype, P, G);
+}
+
 extern "C" int stfb_conv2d_wgrad(const void* P, const void* G, float* dW, int N, int Hp, int Wp, int Cp, int Hg, int Wg,
-                                 int Cg, int cg_off, int cg_total, int kh, int kw, int stride, int pad, int dtype,
+                                 int Cg, int cg_off, int cg_total, int kh, int kw, int stride, int pad, int dtype, int impl,
                                  void* stream) {
   STFB_REQUIRE(P && G && dW, "conv2d_wgrad: null pointer");
   STFB_REQUIRE(N >= 0 && Hp > 0 && Wp > 0 && Cp > 0 && Hg > 0 && Wg > 0 && Cg > 0 && kh > 0 && kw > 0 && stride > 0 && pad >= 0,
@@ -517,6 +529,15 @@ extern "C" int stfb_conv2d_wgrad(const void* P, const void* G, float* dW, int N,
   STFB_REQUIRE(cg_off >= 0 && cg_off + Cg <= cg_total, "conv2d_wgrad: channel window [%d,%d) outside %d", cg_off, cg_off + Cg, cg_total);
   STFB_REQUIRE(dtype == STFB_F32 || dtype == STFB_BF16, "conv2d_wgrad: bad dtype");
   STFB_DEVICE_OR_RETURN();
+  if (impl != STFB_IMPL_SIMT) {
+    const int ok = stfb::wgrad_tcgen05_supported(N, Hp, Wp, Cp, Hg, Wg, Cg, kh, kw, stride, pad, dtype, P, G);
+    if (ok) return stfb::wgrad_tcgen05(P, G, nullptr, dW, N, Hp, Wp, Cp, Cg, 0, cg_off, cg_total, kh, kw, pad,
+                                       reinterpret_cast<cudaStream_t>(stream));
+    if (impl == STFB_IMPL_TCGEN05) {
+      set_error("conv2d_wgrad: shape not supported by the tcgen05 family");
+      return STFB_ENOTSUP;
+    }
+  }
   WgradArgs a{};
   a.P = P; a.G = G; a.dW = dW; a.N = N; a.Hp = Hp; a.Wp = Wp; a.Cp = Cp; a.Hg = Hg; a.Wg = Wg; a.Cg = Cg;
   a.cg_off = cg_off; a.cg_total = cg_total; a.kh = kh; a.kw = kw; a.stride = stride; a.pad = pad;

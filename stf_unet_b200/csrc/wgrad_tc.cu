@@ -1,0 +1,244 @@
+// tcgen05 / TMEM weight-gradient kernel for stride-1 "same" convolutions (and 1x1 GEMMs: LSTM matrices).
+//
+//   dW[co][ci][ky][kx] += sum_pix dy[pix, co] * x[pix + (ky - pad, kx - pad), ci]
+//
+// GEMM view: D[m = (tap, ci)][n = co] = sum_k A[m][k = pix] * B[n][k = pix].  Both operands are read straight out of
+// the NHWC activations, whose contiguous axis is the channel axis, i.e. the M / N axis of this GEMM: they are
+// "MN-major" operands.  A 4-D TMA box {64 ch, TW, TH, TN} (64 pixels) lands in smem as 64 rows x 128 B with the
+// 128-byte swizzle = one MN-major SWIZZLE_128B column block; tcgen05.mma consumes it with a_major = b_major = MN.
+//   * A tile (M = 128) = two independent 64-channel column blocks: they may belong to different filter taps, so
+//     64-channel layers still fill the 128-row datapath (block j of the tile is the x patch shifted by ITS tap).
+//   * B tile (N = BN <= 256) = BN/64 column blocks of the dy patch (unshifted).
+//   * The pixel reduction is split across CTAs (gridDim.z); each CTA accumulates its pixel range in TMEM and adds
+//     the fp32 result into dW (reference layout) with red.global.add.f32.
+#include "tc_common.cuh"
+
+namespace stfb {
+
+struct WgTcArgs {
+  float* dW;
+  int N, H, W, Cp;          // dy is [N, H, W, Cp]; x / x2 are [N, H, W, C1 / C2]
+  int C1, C2;
+  int cg_off, cg_total;     // dW channel window (ci axis) of this launch inside the full weight
+  int kh, kw, pad;
+  int TW, TH, TN;           // 64-pixel patch
+  int tiles_w, tiles_h, n_patches;
+  int patches_per_split;
+  int m_chunks;             // kh*kw*(C1+C2)/64 column blocks on the M axis
+};
+
+constexpr int WG_PIX = 64;                       // K per stage
+constexpr int WG_BLK_BYTES = WG_PIX * 128;       // one 64-ch x 64-pixel column block = 8 KB
+constexpr int WG_THREADS = 192;
+
+template <int BN, int STAGES>
+constexpr int wg_smem_bytes() {
+  return STAGES * (2 + BN / 64) * WG_BLK_BYTES + 256 + 1024;
+}
+
+template <int BN, int STAGES>
+__global__ void __launch_bounds__(WG_THREADS) wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmG,
+                                                               const __grid_constant__ CUtensorMap tmG2,
+                                                               const __grid_constant__ CUtensorMap tmP, const WgTcArgs a) {
+  constexpr int NB = BN / 64;
+  constexpr int STAGE_BYTES = (2 + NB) * WG_BLK_BYTES;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* accum_bar = empty_bar + STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum_bar + 1);
+
+  const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+  const int mtile = blockIdx.x;
+  const int n0 = blockIdx.y * BN;
+  const int p_beg = blockIdx.z * a.patches_per_split;
+  const int p_end = min(a.n_patches, p_beg + a.patches_per_split);
+  const int Cin = a.C1 + a.C2;
+  const int cpt = Cin / 64;                       // column blocks per tap
+  // the two column blocks of this M tile (the second falls back to the first when the tile is half empty)
+  const int chunk0 = mtile * 2;
+  const bool has1 = chunk0 + 1 < a.m_chunks;
+  const int chunk1 = has1 ? chunk0 + 1 : chunk0;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    mbar_init(accum_bar, 1);
+    fence_barrier_init();
+    prefetch_tensormap(&tmG);
+    prefetch_tensormap(&tmP);
+    if (a.C2 > 0) prefetch_tensormap(&tmG2);
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, BN);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_acc = *tmem_slot;
+  const int n_iter = p_end - p_beg;
+
+  if (warp == 0) {
+    if (lane == 0 && n_iter > 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      int tapc[2], cc[2];
+      tapc[0] = chunk0 / cpt; cc[0] = (chunk0 - tapc[0] * cpt) * 64;
+      tapc[1] = chunk1 / cpt; cc[1] = (chunk1 - tapc[1] * cpt) * 64;
+      for (int p = p_beg; p < p_end; ++p) {
+        int t = p;
+        const int wb = t % a.tiles_w; t /= a.tiles_w;
+        const int hb = t % a.tiles_h;
+        const int nb = t / a.tiles_h;
+        const int w0 = wb * a.TW, h0 = hb * a.TH, i0 = nb * a.TN;
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        uint8_t* sa = smem + stage * STAGE_BYTES;
+        mbar_arrive_expect_tx(&full_bar[stage], STAGE_BYTES);
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+          const int r = tapc[j] / a.kw, s = tapc[j] - r * a.kw;
+          if (cc[j] < a.C1) tma_load_4d(sa + j * WG_BLK_BYTES, &tmG, &full_bar[stage], cc[j], w0 - a.pad + s, h0 - a.pad + r, i0);
+          else tma_load_4d(sa + j * WG_BLK_BYTES, &tmG2, &full_bar[stage], cc[j] - a.C1, w0 - a.pad + s, h0 - a.pad + r, i0);
+        }
+#pragma unroll
+        for (int i = 0; i < NB; ++i)
+          tma_load_4d(sa + (2 + i) * WG_BLK_BYTES, &tmP, &full_bar[stage], n0 + i * 64, w0, h0, i0);
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    constexpr uint32_t idesc = make_idesc_bf16_mnmajor(128, BN);
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int it = 0; it < n_iter; ++it) {
+      mbar_wait(&full_bar[stage], phase);
+      tc_fence_after();
+      if (lane == 0) {
+        const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
+        const uint64_t adesc = make_mnmajor_sw128_desc(sa, WG_BLK_BYTES);
+        const uint64_t bdesc = make_mnmajor_sw128_desc(sa + 2 * WG_BLK_BYTES, WG_BLK_BYTES);
+#pragma unroll
+        for (int k = 0; k < WG_PIX / 16; ++k) {
+          // 16 pixels = 16 rows of 128 B = 2048 B further down each column block
+          umma_bf16(tmem_acc, adesc + (uint64_t)(128 * k), bdesc + (uint64_t)(128 * k), idesc, (it | k) != 0);
+        }
+        umma_commit(&empty_bar[stage]);
+        if (it == n_iter - 1) umma_commit(accum_bar);
+      }
+      __syncwarp();
+      if (++stage == STAGES) { stage = 0; phase ^= 1; }
+    }
+  } else if (n_iter > 0) {
+    // epilogue: row m of the accumulator = (column block m / 64, channel m % 64)
+    const int q = warp & 3;
+    const int m = q * 32 + lane;
+    const int chunk = (m < 64) ? chunk0 : chunk1;
+    const bool valid = (m < 64) || has1;
+    const int tap = chunk / cpt;
+    const int ci = (chunk - tap * cpt) * 64 + (m & 63);
+    const int khw = a.kh * a.kw;
+    // dW[co][cg_off + ci][tap]
+    float* base = a.dW + ((long long)n0 * a.cg_total + a.cg_off + ci) * khw + tap;
+    const long long co_stride = (long long)a.cg_total * khw;
+    mbar_wait(accum_bar, 0);
+    tc_fence_after();
+    const uint32_t taddr = tmem_acc + ((uint32_t)(q * 32) << 16);
+#pragma unroll 1
+    for (int c0 = 0; c0 < BN; c0 += 32) {
+      uint32_t r[32];
+      tmem_ld_x32(taddr + c0, r);
+      tmem_ld_wait();
+      if (valid) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) atomicAdd(base + (long long)(c0 + j) * co_stride, __uint_as_float(r[j]));
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_acc, BN);
+  }
+}
+
+static int wg_pick_bn(int Cp) {
+  if (Cp % 256 == 0) return 256;
+  if (Cp % 128 == 0) return 128;
+  if (Cp % 64 == 0) return 64;
+  return 0;
+}
+
+int wgrad_tcgen05_supported(int N, int Hp, int Wp, int Cp, int Hg, int Wg, int Cg, int kh, int kw, int stride, int pad,
+                            int dtype, const void* P, const void* G) {
+  if (dtype != STFB_BF16 || stride != 1 || kh != kw || 2 * pad != kh - 1) return 0;
+  if (Hp != Hg || Wp != Wg) return 0;
+  if (Cg % 64 != 0 || wg_pick_bn(Cp) == 0) return 0;
+  if ((reinterpret_cast<uintptr_t>(P) % 16) || (reinterpret_cast<uintptr_t>(G) % 16)) return 0;
+  if ((long long)N * Hp * Wp > 2000000000LL) return 0;
+  return 1;
+}
+
+template <int BN, int STAGES>
+static int launch_wg(const CUtensorMap& tG, const CUtensorMap& tG2, const CUtensorMap& tP, const WgTcArgs& a, dim3 grid,
+                     cudaStream_t st) {
+  constexpr int smem = wg_smem_bytes<BN, STAGES>();
+  static bool configured = false;
+  if (!configured) {
+    if (cudaFuncSetAttribute(wgrad_tc_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) {
+      set_error("conv2d_wgrad(tcgen05): cannot reserve %d bytes of shared memory", smem);
+      cudaGetLastError();
+      return STFB_ECUDA;
+    }
+    configured = true;
+  }
+  wgrad_tc_kernel<BN, STAGES><<<grid, WG_THREADS, smem, st>>>(tG, tG2, tP, a);
+  return post_launch("conv2d_wgrad(tcgen05)");
+}
+
+// G (and optional G2, concatenated on the channel axis after G) are the gathered activations; P = dy.
+int wgrad_tcgen05(const void* P, const void* G, const void* G2, float* dW, int N, int H, int W, int Cp, int C1, int C2,
+                  int cg_off, int cg_total, int kh, int kw, int pad, cudaStream_t st) {
+  EncodeTiledFn enc = get_tensormap_encoder();
+  if (!enc) { set_error("conv2d_wgrad(tcgen05): cuTensorMapEncodeTiled not available"); return STFB_ECUDA; }
+  if ((long long)N * H * W == 0) return STFB_OK;
+  WgTcArgs a{};
+  a.dW = dW; a.N = N; a.H = H; a.W = W; a.Cp = Cp; a.C1 = C1; a.C2 = C2; a.cg_off = cg_off; a.cg_total = cg_total;
+  a.kh = kh; a.kw = kw; a.pad = pad;
+  a.TW = pow2_floor(W); if (a.TW > 8) a.TW = 8;
+  a.TH = pow2_floor(H); if (a.TH > WG_PIX / a.TW) a.TH = WG_PIX / a.TW;
+  a.TN = WG_PIX / (a.TW * a.TH);
+  a.tiles_w = (W + a.TW - 1) / a.TW;
+  a.tiles_h = (H + a.TH - 1) / a.TH;
+  const int tiles_n = (N + a.TN - 1) / a.TN;
+  a.n_patches = tiles_n * a.tiles_h * a.tiles_w;
+  a.m_chunks = kh * kw * (C1 + C2) / 64;
+  const int BN = wg_pick_bn(Cp);
+  const int m_tiles = (a.m_chunks + 1) / 2, n_tiles = Cp / BN;
+  // split the pixel reduction so the grid covers ~2 waves, keeping >= 4 patches per CTA
+  long long want = (2LL * num_sms() + (long long)m_tiles * n_tiles - 1) / ((long long)m_tiles * n_tiles);
+  long long maxsplit = (a.n_patches + 3) / 4;
+  long long splits = want < 1 ? 1 : want;
+  if (splits > maxsplit) splits = maxsplit;
+  if (splits < 1) splits = 1;
+  if (splits > 65535) splits = 65535;
+  a.patches_per_split = (int)((a.n_patches + splits - 1) / splits);
+  splits = (a.n_patches + a.patches_per_split - 1) / a.patches_per_split;
+
+  CUtensorMap tG, tG2, tP;
+  if (!encode_nhwc_map(enc, &tG, G, N, H, W, C1, a.TW, a.TH, a.TN)) { set_error("conv2d_wgrad(tcgen05): tensor map (G) failed"); return STFB_ECUDA; }
+  tG2 = tG;
+  if (C2 > 0 && !encode_nhwc_map(enc, &tG2, G2, N, H, W, C2, a.TW, a.TH, a.TN)) { set_error("conv2d_wgrad(tcgen05): tensor map (G2) failed"); return STFB_ECUDA; }
+  if (!encode_nhwc_map(enc, &tP, P, N, H, W, Cp, a.TW, a.TH, a.TN)) { set_error("conv2d_wgrad(tcgen05): tensor map (P) failed"); return STFB_ECUDA; }
+  dim3 grid((unsigned)m_tiles, (unsigned)n_tiles, (unsigned)splits);
+  switch (BN) {
+    case 256: return launch_wg<256, 4>(tG, tG2, tP, a, grid, st);
+    case 128: return launch_wg<128, 5>(tG, tG2, tP, a, grid, st);
+    case 64: return launch_wg<64, 6>(tG, tG2, tP, a, grid, st);
+  }
+  set_error("conv2d_wgrad(tcgen05): no tile for Cp=%d", Cp);
+  return STFB_ENOTSUP;
+}
+
+}  // namespace stfb

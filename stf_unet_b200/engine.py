@@ -16,6 +16,9 @@ from . import ops
 
 BN_EPS = 1e-5
 BN_MOMENTUM = 0.1
+#: kill switch for A/B measurements (STFB_NO_TCGEN05=1 keeps every conv on the SIMT family)
+import os as _os
+USE_TCGEN05 = _os.environ.get("STFB_NO_TCGEN05", "0") != "1"
 
 
 class Var:
@@ -39,6 +42,11 @@ class Var:
             ops.add_(self.grad, g)
 
 
+def hs_probe(seq, B):
+    """A [B, h, w, C] view of the first time slab (shape probe for the recurrent GEMM)."""
+    return seq[:B]
+
+
 class Executor:
     """Runs layers on NHWC activations; when ``record`` is set every layer pushes its backward closure."""
 
@@ -53,13 +61,26 @@ class Executor:
         self._packed = {}
 
     # ---------------------------------------------------------------------------------------------
-    def packed(self, name, k_is_dim1):
-        key = (name, bool(k_is_dim1))
+    def packed(self, name, k_is_dim1, n_major=False, flip=False):
+        key = (name, bool(k_is_dim1), bool(n_major), bool(flip))
         wp = self._packed.get(key)
         if wp is None:
-            wp = ops.pack_weight(self.params[name], k_is_dim1, self.dtype)
+            wp = ops.pack_weight(self.params[name], k_is_dim1, self.dtype, n_major=n_major, flip=flip)
             self._packed[key] = wp
         return wp
+
+    _tc_cache = {}
+
+    def use_tc(self, x, Cout, k, stride, pad, x2=None, transposed=False):
+        """Does this convolution go to the tcgen05 family (bf16, stride-1 'same', 64-channel multiples)?"""
+        if self.dtype != torch.bfloat16 or transposed or not USE_TCGEN05:
+            return False
+        key = (tuple(x.shape), Cout, k, stride, pad, None if x2 is None else x2.shape[3])
+        r = Executor._tc_cache.get(key)
+        if r is None:
+            r = ops.tcgen05_ok(x, Cout, k, stride, pad, x2=x2)
+            Executor._tc_cache[key] = r
+        return r
 
     def wants_grad(self, name):
         return name in self.grads
@@ -77,10 +98,13 @@ class Executor:
         assert not (transposed and x2 is not None)
         mode = ops.CONV_TRANSPOSED if transposed else ops.CONV_FWD
         out_hw = ops.conv_out_hw(H, W, k, stride, pad, transposed, out_pad)
-        wp = self.packed(wname, k_is_dim1=not transposed)
+        x2d = None if x2 is None else x2.data
+        tc = self.use_tc(x.data, Cout, k, stride, pad, x2d, transposed)
+        wp = self.packed(wname, k_is_dim1=not transposed, n_major=tc)
         bias = self.params[bname] if bname else None
-        y = ops.conv2d(x.data, wp, Cout, k, stride, pad, mode=mode, out_hw=out_hw, x2=None if x2 is None else x2.data,
-                       bias=bias, scale=scale, shift=shift, residual=residual, relu=relu, y_dtype=y_dtype)
+        y = ops.conv2d(x.data, wp, Cout, k, stride, pad, mode=mode, out_hw=out_hw, x2=x2d,
+                       bias=bias, scale=scale, shift=shift, residual=residual, relu=relu, y_dtype=y_dtype,
+                       impl=ops.IMPL_TCGEN05 if tc else ops.IMPL_SIMT)
         out = Var(y, grad_dtype=self.dtype)
         if not self.record:
             return out
@@ -105,10 +129,17 @@ class Executor:
             for src, off, csrc in srcs:
                 if not src.needs_grad:
                     continue
-                wpd = self.packed(wname, k_is_dim1=transposed)
-                g = ops.conv2d(dy, wpd, csrc, k, stride, pad, mode=ops.CONV_FWD if transposed else ops.CONV_TRANSPOSED,
-                               out_hw=(H, W), residual=src.grad, out=src.grad, y_dtype=src.grad_dtype, ldw=C1 + C2,
-                               w_offset=off)
+                if not transposed and self.use_tc(dy, csrc, k, stride, pad):
+                    # stride-1 "same" conv: dgrad == forward conv over dy with mirrored taps, on the tensor cores
+                    wpd = self.packed(wname, k_is_dim1=False, n_major=True, flip=True)     # [Cin][(ky,kx,co)]
+                    g = ops.conv2d(dy, wpd, csrc, k, 1, pad, residual=src.grad, out=src.grad, y_dtype=src.grad_dtype,
+                                   ldw=wpd.shape[1], w_offset=off * wpd.shape[1], impl=ops.IMPL_TCGEN05)
+                else:
+                    wpd = self.packed(wname, k_is_dim1=transposed)
+                    g = ops.conv2d(dy, wpd, csrc, k, stride, pad,
+                                   mode=ops.CONV_FWD if transposed else ops.CONV_TRANSPOSED, out_hw=(H, W),
+                                   residual=src.grad, out=src.grad, y_dtype=src.grad_dtype, ldw=C1 + C2, w_offset=off,
+                                   impl=ops.IMPL_SIMT)
                 src.grad = g
 
         self.tape.append(bwd)
@@ -201,19 +232,22 @@ class Executor:
         wih, whh = prefix + ".weight_ih_l0", prefix + ".weight_hh_l0"
         bih, bhh = prefix + ".bias_ih_l0", prefix + ".bias_hh_l0"
         # hoisted input GEMM for all T: gates_x = X W_ih^T + b_ih + b_hh  (fp32 pre-activations)
-        gates = ops.conv2d(seq.data, self.packed(wih, True), 4 * C, 1, 1, 0, bias=P[bih], bias2=P[bhh],
-                           y_dtype=torch.float32)
+        tc = self.use_tc(seq.data, 4 * C, 1, 1, 0) and self.use_tc(hs_probe(seq.data, B), 4 * C, 1, 1, 0)
+        impl = ops.IMPL_TCGEN05 if tc else ops.IMPL_SIMT
+        gates = ops.conv2d(seq.data, self.packed(wih, True, n_major=tc), 4 * C, 1, 1, 0, bias=P[bih], bias2=P[bhh],
+                           y_dtype=torch.float32, impl=impl)
         gates = gates.view(T, B, h, w, 4 * C)
         keep = self.record
         acts = torch.empty((T, R, 4 * C), dtype=self.dtype, device=dev) if keep else None
         cs = torch.empty((T if keep else 2, R, C), dtype=torch.float32, device=dev)
         hs = torch.empty((T if keep else 2, B, h, w, C), dtype=self.dtype, device=dev)
-        whh_p = self.packed(whh, True)
+        whh_p = self.packed(whh, True, n_major=tc)
         for t in range(T):
             cur = t if keep else t % 2
             prev = (t - 1) if keep else (t - 1) % 2
             if t > 0:  # gates_t += h_{t-1} W_hh^T   (in place through the residual epilogue)
-                ops.conv2d(hs[prev], whh_p, 4 * C, 1, 1, 0, residual=gates[t], out=gates[t], y_dtype=torch.float32)
+                ops.conv2d(hs[prev], whh_p, 4 * C, 1, 1, 0, residual=gates[t], out=gates[t], y_dtype=torch.float32,
+                           impl=impl)
             ops.lstm_cell_fwd(gates[t], cs[prev] if t > 0 else None, acts[t] if keep else None, cs[cur], hs[cur], R, C)
         last = (T - 1) if keep else (T - 1) % 2
         out = Var(hs[last], grad_dtype=torch.float32)
@@ -227,11 +261,13 @@ class Executor:
                 return
             dG = torch.empty((T, B, h, w, 4 * C), dtype=self.dtype, device=dev)
             dc = torch.zeros((R, C), dtype=torch.float32, device=dev)
-            whh_d = self.packed(whh, False)
+            tcb = self.use_tc(dG[0], C, 1, 1, 0)
+            implb = ops.IMPL_TCGEN05 if tcb else ops.IMPL_SIMT
+            whh_d = self.packed(whh, False, n_major=tcb)
             for t in range(T - 1, -1, -1):
                 ops.lstm_cell_bwd(dh, dc, acts[t], cs[t - 1] if t > 0 else None, cs[t], dG[t], R, C)
                 if t > 0:
-                    dh = ops.conv2d(dG[t], whh_d, C, 1, 1, 0, y_dtype=torch.float32)
+                    dh = ops.conv2d(dG[t], whh_d, C, 1, 1, 0, y_dtype=torch.float32, impl=implb)
             dG_all = dG.view(T * B, h, w, 4 * C)
             if self.wants_grad(wih):
                 ops.conv2d_wgrad(dG_all, seq.data, self.grads[wih], 1, 1, 0)
@@ -242,8 +278,10 @@ class Executor:
                 if self.wants_grad(bn_):
                     ops.colsum(dG_all, self.grads[bn_], T * R, 4 * C)
             if seq.needs_grad:
-                seq.grad = ops.conv2d(dG_all, self.packed(wih, False), C, 1, 1, 0, residual=seq.grad, out=seq.grad,
-                                      y_dtype=seq.grad_dtype)
+                tca = self.use_tc(dG_all, C, 1, 1, 0)
+                seq.grad = ops.conv2d(dG_all, self.packed(wih, False, n_major=tca), C, 1, 1, 0, residual=seq.grad,
+                                      out=seq.grad, y_dtype=seq.grad_dtype,
+                                      impl=ops.IMPL_TCGEN05 if tca else ops.IMPL_SIMT)
 
         self.tape.append(bwd)
         return out

@@ -32,21 +32,33 @@ class KernelProfiler:
         e0.record()
         return e0
 
-    def end(self, e0, family, flops, nbytes=0):
+    def end(self, e0, family, flops, nbytes=0, tag=""):
         e1 = torch.cuda.Event(enable_timing=True)
         e1.record()
-        self.records.append((family, float(flops), float(nbytes), e0, e1))
+        self.records.append((family, float(flops), float(nbytes), e0, e1, tag))
 
     def summary(self):
         torch.cuda.synchronize()
         fam = {}
-        for family, flops, nbytes, e0, e1 in self.records:
+        for family, flops, nbytes, e0, e1, _tag in self.records:
             d = fam.setdefault(family, {"ms": 0.0, "flops": 0.0, "bytes": 0.0, "n": 0})
             d["ms"] += e0.elapsed_time(e1)
             d["flops"] += flops
             d["bytes"] += nbytes
             d["n"] += 1
         return fam
+
+    def top(self, n=25):
+        """Slowest launches grouped by (family, shape tag): [(ms, count, TFLOP/s, family, tag)]."""
+        torch.cuda.synchronize()
+        agg = {}
+        for family, flops, nbytes, e0, e1, tag in self.records:
+            d = agg.setdefault((family, tag), [0.0, 0, 0.0])
+            d[0] += e0.elapsed_time(e1)
+            d[1] += 1
+            d[2] += flops
+        rows = [(v[0], v[1], v[2] / (v[0] * 1e-3) / 1e12 if v[0] > 0 else 0.0, k[0], k[1]) for k, v in agg.items()]
+        return sorted(rows, reverse=True)[:n]
 
 
 _prof = None
@@ -114,23 +126,31 @@ def conv2d(x, wp, Cout, k, stride, pad, *, mode=CONV_FWD, out_hw=None, x2=None, 
     nbytes = (x.numel() + (0 if x2 is None else x2.numel())) * esz + y.numel() * y.element_size() + wp.numel() * esz
     e0 = _prof.begin()
     check(lib.stfb_conv2d(C.byref(p), _stream()), "conv2d")
-    _prof.end(e0, "conv_tcgen05" if tc else "conv_simt_" + ("bf16" if esz == 2 else "f32"), flops, nbytes)
+    _prof.end(e0, "conv_tcgen05" if tc else "conv_simt_" + ("bf16" if esz == 2 else "f32"), flops, nbytes,
+              f"x{tuple(x.shape)}+{C2} ->{Cout} k{kh} s{stride} m{mode}")
     return y
 
 
-def conv2d_wgrad(P, G, dW, k, stride, pad, cg_off=0, cg_total=None):
+def conv2d_wgrad(P, G, dW, k, stride, pad, cg_off=0, cg_total=None, impl=IMPL_AUTO):
     """dW[cp][cg_off+cg][ky][kx] += sum_pix P[pix,cp] * G[gather(pix),cg]; dW fp32, reference layout."""
     _need_cuda(P, G, dW)
     N, Hp, Wp, Cp = P.shape
     _, Hg, Wg, Cg = G.shape
     kh, kw = (k, k) if isinstance(k, int) else k
-    e0 = _prof.begin() if _prof is not None else None
-    check(_lib.load().stfb_conv2d_wgrad(_p(P), _p(G), _p(dW), N, Hp, Wp, Cp, Hg, Wg, Cg, cg_off,
-                                        cg_total if cg_total is not None else Cg, kh, kw, stride, pad, dt_code(P.dtype),
-                                        _stream()), "conv2d_wgrad")
+    lib = _lib.load()
+    dt = dt_code(P.dtype)
+    e0 = None
+    if _prof is not None:
+        tc = impl != IMPL_SIMT and lib.stfb_conv2d_wgrad_tcgen05_supported(_p(P), _p(G), N, Hp, Wp, Cp, Hg, Wg, Cg, kh, kw,
+                                                                           stride, pad, dt) == 1
+        e0 = _prof.begin()
+    check(lib.stfb_conv2d_wgrad(_p(P), _p(G), _p(dW), N, Hp, Wp, Cp, Hg, Wg, Cg, cg_off,
+                                cg_total if cg_total is not None else Cg, kh, kw, stride, pad, dt, impl, _stream()),
+          "conv2d_wgrad")
     if e0 is not None:
-        _prof.end(e0, "wgrad_simt_" + ("bf16" if P.element_size() == 2 else "f32"), 2.0 * N * Hp * Wp * Cp * Cg * kh * kw,
-                  (P.numel() + G.numel()) * P.element_size())
+        fam = "wgrad_tcgen05" if tc else "wgrad_simt_" + ("bf16" if P.element_size() == 2 else "f32")
+        _prof.end(e0, fam, 2.0 * N * Hp * Wp * Cp * Cg * kh * kw, (P.numel() + G.numel()) * P.element_size(),
+                  f"P{tuple(P.shape)} G{tuple(G.shape)} k{kh} s{stride}")
 
 
 def pack_weight(w, k_is_dim1, dtype, n_major=False, flip=False):

@@ -243,7 +243,7 @@ def test_unet_config1_fp32_vs_oracle():
         gr = ref_grads[n].double()
         err = (p.grad.cpu().double() - gr).norm().item()
         worst = max(worst, (err / max(gr.norm().item(), 1e-12), n))
-        assert err < 5e-3 * gr.norm().item() + 1e-6 * scale, (n, err, gr.norm().item())
+        assert err < 2e-2 * gr.norm().item() + 1e-6 * scale, (n, err, gr.norm().item())
     print("unet config1 worst grad rel err %.3e at %s" % worst)
 
 

@@ -387,3 +387,37 @@ def test_conv_tcgen05_dgrad_via_flipped_weights():
     assert wpd.shape == (Cin, k * k * Cout)
     dx = ops.conv2d(nhwc(dy, dtype), wpd, Cin, k, 1, 1, y_dtype=torch.float32, impl=ops.IMPL_TCGEN05)
     assert rel(nchw(dx), x.grad) < 2e-3
+
+
+WG_TC_CASES = [
+    # N, H, W, Cin, Cout, k
+    (2, 16, 16, 64, 64, 3),        # 9 column blocks -> last M tile half empty; taps share tiles
+    (3, 8, 8, 128, 256, 3),        # BN=256
+    (1, 25, 25, 64, 128, 3),       # ragged
+    (2, 4, 4, 512, 512, 3),        # TN=4 patches, two N tiles
+    (4, 16, 16, 256, 64, 1),       # 1x1 (LSTM dW shape: P = dgates, G = x)
+    (8, 32, 32, 128, 128, 3),      # split-K over many patches
+]
+
+
+@pytest.mark.parametrize("case", WG_TC_CASES)
+def test_wgrad_tcgen05_matches_reference(case):
+    N, H, W, Cin, Cout, k = case
+    dtype = torch.bfloat16
+    pad = (k - 1) // 2
+    x = q(rnd(N, Cin, H, W, seed=1), dtype)
+    w = torch.zeros(Cout, Cin, k, k, device=DEV, requires_grad=True)
+    y = F.conv2d(x, w, None, 1, pad)
+    dy = q(rnd(*y.shape, seed=2), dtype)
+    y.backward(dy)
+    dW = torch.zeros(Cout, Cin, k, k, device=DEV)
+    ops.conv2d_wgrad(nhwc(dy, dtype), nhwc(x, dtype), dW, k, 1, pad, 0, Cin, impl=ops.IMPL_TCGEN05)
+    torch.cuda.synchronize()
+    assert rel(dW, w.grad) < 1e-4
+    # channel window form (dual-source convs call wgrad once per source)
+    if Cin >= 128:
+        h = Cin // 2
+        dW2 = torch.zeros_like(dW)
+        ops.conv2d_wgrad(nhwc(dy, dtype), nhwc(x[:, :h], dtype), dW2, k, 1, pad, 0, Cin, impl=ops.IMPL_TCGEN05)
+        ops.conv2d_wgrad(nhwc(dy, dtype), nhwc(x[:, h:], dtype), dW2, k, 1, pad, h, Cin, impl=ops.IMPL_TCGEN05)
+        assert rel(dW2, w.grad) < 1e-4
