@@ -13,7 +13,13 @@
 //   synchronised with mbarriers (TMA complete_tx -> MMA, tcgen05.commit -> producer / epilogue).
 // * Concat inputs (decoder fusion, UNet skip) are two tensor maps walking one K loop: no materialised torch.cat.
 //
-// Used for: stride-1 "same" Conv2d forward, its dgrad (flipped weights), the LSTM gate GEMMs (1x1).
+// * Geometry is table driven (TcArgs): a launch is 1..4 "phases" (gridDim.z), each with its own list of filter taps
+//   (A-load offset + weight K block).  That one mechanism covers
+//     - stride-1 "same" convolutions and 1x1 GEMMs (1 phase, kh*kw taps),
+//     - stride-2 forward convolutions (A map built with TMA elementStrides = 2: the box walks every other pixel),
+//     - transposed gathers = ConvTranspose2d forward and Conv2d dgrad at stride 1 or 2: the s*s output parities are
+//       separate phases with 1/2/2/4 dense taps each (no multiplication by inserted zeros), outputs scattered at
+//       stride s.
 #include "tc_common.cuh"
 
 namespace stfb {
@@ -26,12 +32,17 @@ struct TcArgs {
   const float* bias2;
   const float* scale;
   const float* shift;
-  int N, H, W, Cout;
+  int N;
+  int Hout, Wout, Cout;  // output tensor
   int C1, C2;
-  int kh, kw, pad;
-  int TW, TH, TN;      // pixel patch of one tile, TN*TH*TW == 128
+  int a_scale;           // A-map coordinate = logical pixel * a_scale + tap offset (2 for stride-2 forward)
+  int o_scale;           // output pixel = logical pixel * o_scale + phase offset   (2 for stride-2 transposed)
+  int nphase_w;          // phase z -> (z / nphase_w, z % nphase_w) output parity
+  int TW, TH, TN;        // logical pixel patch of one tile, TN*TH*TW == 128
   int tiles_w, tiles_h;
   int relu;
+  int ntaps[4];
+  signed char dh[4][9], dw[4][9], ktap[4][9];
 };
 
 constexpr int TC_BM = 128;
@@ -66,7 +77,9 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(const __grid_consta
   const int nb = mt / a.tiles_h;
   const int Cin = a.C1 + a.C2;
   const int cpt = Cin / TC_BK;                 // k-blocks per filter tap
-  const int num_kb = a.kh * a.kw * cpt;
+  const int ph = blockIdx.z;
+  const int ph_h = ph / a.nphase_w, ph_w = ph - ph_h * a.nphase_w;
+  const int num_kb = a.ntaps[ph] * cpt;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
@@ -102,16 +115,15 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(const __grid_consta
       uint32_t phase = 0;
       for (int kb = 0; kb < num_kb; ++kb) {
         mbar_wait(&empty_bar[stage], phase ^ 1);
-        const int tap = kb / cpt, chunk = kb - tap * cpt;
-        const int r = tap / a.kw, s = tap - r * a.kw;
+        const int t = kb / cpt, chunk = kb - t * cpt;
         const int c = chunk * TC_BK;
         uint8_t* sa = smem + stage * STAGE_BYTES;
         uint8_t* sb = sa + TC_A_BYTES;
         mbar_arrive_expect_tx(&full_bar[stage], STAGE_BYTES);
-        const int w0 = wb * a.TW - a.pad + s, h0 = hb * a.TH - a.pad + r, i0 = nb * a.TN;
+        const int w0 = wb * a.TW * a.a_scale + a.dw[ph][t], h0 = hb * a.TH * a.a_scale + a.dh[ph][t], i0 = nb * a.TN;
         if (c < a.C1) tma_load_4d(sa, &tmA, &full_bar[stage], c, w0, h0, i0);
         else tma_load_4d(sa, &tmA2, &full_bar[stage], c - a.C1, w0, h0, i0);
-        tma_load_2d(sb, &tmB, &full_bar[stage], tap * Cin + c, n0);
+        tma_load_2d(sb, &tmB, &full_bar[stage], (int)a.ktap[ph][t] * Cin + c, n0);
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
     }
@@ -143,19 +155,26 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(const __grid_consta
     const int q = warp & 3;
     const int m = q * 32 + lane;                       // accumulator row = TMEM lane = pixel in the patch
     const int tw = m % a.TW, th = (m / a.TW) % a.TH, tn = m / (a.TW * a.TH);
-    const int ow = wb * a.TW + tw, oh = hb * a.TH + th, on = nb * a.TN + tn;
-    const bool valid = ow < a.W && oh < a.H && on < a.N;
-    const long long row = (((long long)on * a.H + oh) * a.W + ow) * a.Cout + n0;
+    const int ow = (wb * a.TW + tw) * a.o_scale + ph_w, oh = (hb * a.TH + th) * a.o_scale + ph_h, on = nb * a.TN + tn;
+    const bool valid = ow < a.Wout && oh < a.Hout && on < a.N;
+    const long long row = (((long long)on * a.Hout + oh) * a.Wout + ow) * a.Cout + n0;
     TO* __restrict__ yp = reinterpret_cast<TO*>(a.y) + row;
     const TO* rp = a.residual ? reinterpret_cast<const TO*>(a.residual) + row : nullptr;
-    mbar_wait(accum_bar, 0);
-    tc_fence_after();
+    if (num_kb > 0) {
+      mbar_wait(accum_bar, 0);
+      tc_fence_after();
+    }
     const uint32_t taddr = tmem_acc + ((uint32_t)(q * 32) << 16);
 #pragma unroll 1
     for (int c0 = 0; c0 < BN; c0 += 32) {
       uint32_t r[32];
-      tmem_ld_x32(taddr + c0, r);
-      tmem_ld_wait();
+      if (num_kb > 0) {
+        tmem_ld_x32(taddr + c0, r);
+        tmem_ld_wait();
+      } else {   // a parity no tap reaches (1x1 stride-2 dgrad): the accumulator is identically zero
+#pragma unroll
+        for (int j = 0; j < 32; ++j) r[j] = 0u;
+      }
       if (valid) {
         float v[32];
 #pragma unroll
@@ -206,7 +225,7 @@ EncodeTiledFn get_tensormap_encoder() {
 
 int pow2_floor(int v) { int p = 1; while (p * 2 <= v) p *= 2; return p; }
 
-static void pick_patch(int N, int H, int W, int& TW, int& TH, int& TN) {
+static void pick_patch(int H, int W, int& TW, int& TH, int& TN) {
   TW = pow2_floor(W); if (TW > 16) TW = 16;
   TH = pow2_floor(H); if (TH > TC_BM / TW) TH = TC_BM / TW;
   TN = TC_BM / (TW * TH);
@@ -220,26 +239,41 @@ static int pick_bn(int Cout) {
   return 0;
 }
 
+static bool g_tc_strided_fwd = true;   // TMA elementStrides path (stride-2 forward)
+
 int conv2d_tcgen05_supported(const stfb_conv_params* p) {
   if (p->x_dtype != STFB_BF16) return 0;
-  if (p->mode != STFB_CONV_FWD || p->stride != 1) return 0;
-  if (p->kh != p->kw || 2 * p->pad != p->kh - 1 || p->Ho != p->H || p->Wo != p->W) return 0;
+  if (p->kh != p->kw || p->kh > 3) return 0;
+  if (p->stride != 1 && p->stride != 2) return 0;
+  if (p->mode == STFB_CONV_FWD) {
+    if (p->stride == 1 && (2 * p->pad != p->kh - 1 || p->Ho != p->H || p->Wo != p->W)) return 0;
+    if (p->stride == 2 && !g_tc_strided_fwd) return 0;
+    if (p->Ho != (p->H + 2 * p->pad - p->kh) / p->stride + 1 || p->Wo != (p->W + 2 * p->pad - p->kw) / p->stride + 1) return 0;
+  } else if (p->mode != STFB_CONV_TRANSPOSED) {
+    return 0;
+  }
   if (p->C1 % 64 != 0 || p->C2 % 64 != 0) return 0;
   if (pick_bn(p->Cout) == 0) return 0;
   auto al = [](const void* q, int b) { return q == nullptr || (reinterpret_cast<uintptr_t>(q) % b) == 0; };
   if (!al(p->x, 16) || !al(p->x2, 16) || !al(p->y, 16) || !al(p->residual, 16)) return 0;
-  if ((long long)p->N * p->H * p->W > 2000000000LL) return 0;
+  if ((long long)p->N * p->Ho * p->Wo > 2000000000LL || (long long)p->N * p->H * p->W > 2000000000LL) return 0;
   return 1;
 }
 
-bool encode_nhwc_map(EncodeTiledFn enc, CUtensorMap* tm, const void* base, int N, int H, int W, int C, int TW, int TH, int TN) {
+// 4-D NHWC bf16 activation map, box {64 ch, TW, TH, TN} pixels visited with traversal stride `estride` in W and H
+bool encode_nhwc_map_strided(EncodeTiledFn enc, CUtensorMap* tm, const void* base, int N, int H, int W, int C, int TW, int TH,
+                             int TN, int estride) {
   cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
   cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
-  cuuint32_t box[4] = {(cuuint32_t)TC_BK, (cuuint32_t)TW, (cuuint32_t)TH, (cuuint32_t)TN};
-  cuuint32_t estr[4] = {1, 1, 1, 1};
+  cuuint32_t box[4] = {(cuuint32_t)TC_BK, (cuuint32_t)(TW * estride), (cuuint32_t)(TH * estride), (cuuint32_t)TN};
+  cuuint32_t estr[4] = {1, (cuuint32_t)estride, (cuuint32_t)estride, 1};
   return enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr,
              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+bool encode_nhwc_map(EncodeTiledFn enc, CUtensorMap* tm, const void* base, int N, int H, int W, int C, int TW, int TH, int TN) {
+  return encode_nhwc_map_strided(enc, tm, base, N, H, W, C, TW, TH, TN, 1);
 }
 
 template <int BN, int STAGES, typename TO>
@@ -261,25 +295,58 @@ static int launch_tc(const CUtensorMap& tA, const CUtensorMap& tA2, const CUtens
 int conv2d_tcgen05(const stfb_conv_params* p, cudaStream_t st) {
   EncodeTiledFn enc = get_tensormap_encoder();
   if (!enc) { set_error("conv2d(tcgen05): cuTensorMapEncodeTiled not available from the driver"); return STFB_ECUDA; }
-  if ((long long)p->N * p->H * p->W == 0) return STFB_OK;
+  if ((long long)p->N * p->Ho * p->Wo == 0) return STFB_OK;
   if (reinterpret_cast<uintptr_t>(p->w) % 16 != 0) { set_error("conv2d(tcgen05): weights must be 16-byte aligned"); return STFB_EINVAL; }
   TcArgs a{};
   a.y = p->y; a.residual = p->residual; a.bias = p->bias; a.bias2 = p->bias2; a.scale = p->scale; a.shift = p->shift;
-  a.N = p->N; a.H = p->H; a.W = p->W; a.Cout = p->Cout; a.C1 = p->C1; a.C2 = p->C2; a.kh = p->kh; a.kw = p->kw; a.pad = p->pad;
-  a.relu = p->relu;
-  pick_patch(p->N, p->H, p->W, a.TW, a.TH, a.TN);
-  a.tiles_w = (p->W + a.TW - 1) / a.TW;
-  a.tiles_h = (p->H + a.TH - 1) / a.TH;
+  a.N = p->N; a.Hout = p->Ho; a.Wout = p->Wo; a.Cout = p->Cout; a.C1 = p->C1; a.C2 = p->C2; a.relu = p->relu;
+  const int s = p->stride, k = p->kh;
+  int Hl, Wl;   // logical pixel grid the tiles cover
+  if (p->mode == STFB_CONV_FWD) {
+    a.a_scale = s; a.o_scale = 1; a.nphase_w = 1;
+    Hl = p->Ho; Wl = p->Wo;
+    a.ntaps[0] = k * k;
+    for (int r = 0; r < k; ++r)
+      for (int c = 0; c < k; ++c) {
+        a.dh[0][r * k + c] = (signed char)(r - p->pad);
+        a.dw[0][r * k + c] = (signed char)(c - p->pad);
+        a.ktap[0][r * k + c] = (signed char)(r * k + c);
+      }
+  } else {
+    // output pixel o = j*s + ph gathers input (o + pad - ky)/s = j + (ph + pad - ky)/s for the ky that divide
+    a.a_scale = 1; a.o_scale = s; a.nphase_w = s;
+    Hl = (p->Ho + s - 1) / s; Wl = (p->Wo + s - 1) / s;
+    for (int phh = 0; phh < s; ++phh)
+      for (int phw = 0; phw < s; ++phw) {
+        const int z = phh * s + phw;
+        int n = 0;
+        for (int r = 0; r < k; ++r) {
+          if ((phh + p->pad - r) % s != 0) continue;
+          for (int c = 0; c < k; ++c) {
+            if ((phw + p->pad - c) % s != 0) continue;
+            a.dh[z][n] = (signed char)((phh + p->pad - r) / s);
+            a.dw[z][n] = (signed char)((phw + p->pad - c) / s);
+            a.ktap[z][n] = (signed char)(r * k + c);
+            ++n;
+          }
+        }
+        a.ntaps[z] = n;
+      }
+  }
+  pick_patch(Hl, Wl, a.TW, a.TH, a.TN);
+  a.tiles_w = (Wl + a.TW - 1) / a.TW;
+  a.tiles_h = (Hl + a.TH - 1) / a.TH;
   const int tiles_n = (p->N + a.TN - 1) / a.TN;
   const int BN = pick_bn(p->Cout);
-  const int Ktot = p->kh * p->kw * (p->C1 + p->C2);
+  const int Ktot = k * k * (p->C1 + p->C2);
+  if (p->ldw < Ktot) { set_error("conv2d(tcgen05): ldw %d < kh*kw*Cin %d", p->ldw, Ktot); return STFB_EINVAL; }
 
   CUtensorMap tA, tA2, tB;
-  if (!encode_nhwc_map(enc, &tA, p->x, p->N, p->H, p->W, p->C1, a.TW, a.TH, a.TN)) {
+  if (!encode_nhwc_map_strided(enc, &tA, p->x, p->N, p->H, p->W, p->C1, a.TW, a.TH, a.TN, a.a_scale)) {
     set_error("conv2d(tcgen05): cuTensorMapEncodeTiled failed for x"); return STFB_ECUDA;
   }
   tA2 = tA;
-  if (p->C2 > 0 && !encode_nhwc_map(enc, &tA2, p->x2, p->N, p->H, p->W, p->C2, a.TW, a.TH, a.TN)) {
+  if (p->C2 > 0 && !encode_nhwc_map_strided(enc, &tA2, p->x2, p->N, p->H, p->W, p->C2, a.TW, a.TH, a.TN, a.a_scale)) {
     set_error("conv2d(tcgen05): cuTensorMapEncodeTiled failed for x2"); return STFB_ECUDA;
   }
   {
@@ -293,7 +360,7 @@ int conv2d_tcgen05(const stfb_conv_params* p, cudaStream_t st) {
       set_error("conv2d(tcgen05): cuTensorMapEncodeTiled failed for the weights"); return STFB_ECUDA;
     }
   }
-  dim3 grid((unsigned)(tiles_n * a.tiles_h * a.tiles_w), (unsigned)(p->Cout / BN));
+  dim3 grid((unsigned)(tiles_n * a.tiles_h * a.tiles_w), (unsigned)(p->Cout / BN), (unsigned)(a.nphase_w * a.nphase_w));
   const bool f32out = p->y_dtype == STFB_F32;
 #define TC_LAUNCH(BN_, ST_)                                                                                   \
   return f32out ? launch_tc<BN_, ST_, float>(tA, tA2, tB, a, grid, st) : launch_tc<BN_, ST_, __nv_bfloat16>(tA, tA2, tB, a, grid, st)

@@ -465,8 +465,8 @@ int conv2d_tcgen05(const stfb_conv_params* p, cudaStream_t st);
 int conv2d_tcgen05_supported(const stfb_conv_params* p);
 int wgrad_tcgen05_supported(int N, int Hp, int Wp, int Cp, int Hg, int Wg, int Cg, int kh, int kw, int stride, int pad,
                             int dtype, const void* P, const void* G);
-int wgrad_tcgen05(const void* P, const void* G, const void* G2, float* dW, int N, int H, int W, int Cp, int C1, int C2,
-                  int cg_off, int cg_total, int kh, int kw, int pad, cudaStream_t st);
+int wgrad_tcgen05(const void* P, const void* G, const void* G2, float* dW, int N, int H, int W, int Cp, int Hg, int Wg,
+                  int C1, int C2, int cg_off, int cg_total, int kh, int kw, int stride, int pad, cudaStream_t st);
 }
 
 static int validate_conv(const stfb_conv_params* p) {
@@ -531,7 +531,7 @@ extern "C" int stfb_conv2d_wgrad(const void* P, const void* G, float* dW, int N,
   STFB_DEVICE_OR_RETURN();
   if (impl != STFB_IMPL_SIMT) {
     const int ok = stfb::wgrad_tcgen05_supported(N, Hp, Wp, Cp, Hg, Wg, Cg, kh, kw, stride, pad, dtype, P, G);
-    if (ok) return stfb::wgrad_tcgen05(P, G, nullptr, dW, N, Hp, Wp, Cp, Cg, 0, cg_off, cg_total, kh, kw, pad,
+    if (ok) return stfb::wgrad_tcgen05(P, G, nullptr, dW, N, Hp, Wp, Cp, Hg, Wg, Cg, 0, cg_off, cg_total, kh, kw, stride, pad,
                                        reinterpret_cast<cudaStream_t>(stream));
     if (impl == STFB_IMPL_TCGEN05) {
       set_error("conv2d_wgrad: shape not supported by the tcgen05 family");

@@ -17,10 +17,11 @@ namespace stfb {
 
 struct WgTcArgs {
   float* dW;
-  int N, H, W, Cp;          // dy is [N, H, W, Cp]; x / x2 are [N, H, W, C1 / C2]
+  int N, H, W, Cp;          // P (dy) is [N, H, W, Cp]; G / G2 are [N, Hg, Wg, C1 / C2] with H = (Hg + 2 pad - k)/stride + 1
   int C1, C2;
   int cg_off, cg_total;     // dW channel window (ci axis) of this launch inside the full weight
   int kh, kw, pad;
+  int g_scale;              // conv stride: G-map coordinate = patch pixel * g_scale - pad + tap (TMA elementStrides)
   int TW, TH, TN;           // 64-pixel patch
   int tiles_w, tiles_h, n_patches;
   int patches_per_split;
@@ -98,8 +99,9 @@ __global__ void __launch_bounds__(WG_THREADS) wgrad_tc_kernel(const __grid_const
 #pragma unroll
         for (int j = 0; j < 2; ++j) {
           const int r = tapc[j] / a.kw, s = tapc[j] - r * a.kw;
-          if (cc[j] < a.C1) tma_load_4d(sa + j * WG_BLK_BYTES, &tmG, &full_bar[stage], cc[j], w0 - a.pad + s, h0 - a.pad + r, i0);
-          else tma_load_4d(sa + j * WG_BLK_BYTES, &tmG2, &full_bar[stage], cc[j] - a.C1, w0 - a.pad + s, h0 - a.pad + r, i0);
+          const int gw = w0 * a.g_scale - a.pad + s, gh = h0 * a.g_scale - a.pad + r;
+          if (cc[j] < a.C1) tma_load_4d(sa + j * WG_BLK_BYTES, &tmG, &full_bar[stage], cc[j], gw, gh, i0);
+          else tma_load_4d(sa + j * WG_BLK_BYTES, &tmG2, &full_bar[stage], cc[j] - a.C1, gw, gh, i0);
         }
 #pragma unroll
         for (int i = 0; i < NB; ++i)
@@ -163,6 +165,9 @@ __global__ void __launch_bounds__(WG_THREADS) wgrad_tc_kernel(const __grid_const
   }
 }
 
+static bool g_wg_strided = true;   // TMA elementStrides path (stride-2 convolutions / transposed convolutions)
+static bool wgrad_strided_ok() { return g_wg_strided; }
+
 static int wg_pick_bn(int Cp) {
   if (Cp % 256 == 0) return 256;
   if (Cp % 128 == 0) return 128;
@@ -172,8 +177,14 @@ static int wg_pick_bn(int Cp) {
 
 int wgrad_tcgen05_supported(int N, int Hp, int Wp, int Cp, int Hg, int Wg, int Cg, int kh, int kw, int stride, int pad,
                             int dtype, const void* P, const void* G) {
-  if (dtype != STFB_BF16 || stride != 1 || kh != kw || 2 * pad != kh - 1) return 0;
-  if (Hp != Hg || Wp != Wg) return 0;
+  if (dtype != STFB_BF16 || kh != kw || kh > 3) return 0;
+  if (stride == 1) {
+    if (2 * pad != kh - 1 || Hp != Hg || Wp != Wg) return 0;
+  } else if (stride == 2) {
+    if (!wgrad_strided_ok() || Hp != (Hg + 2 * pad - kh) / 2 + 1 || Wp != (Wg + 2 * pad - kw) / 2 + 1) return 0;
+  } else {
+    return 0;
+  }
   if (Cg % 64 != 0 || wg_pick_bn(Cp) == 0) return 0;
   if ((reinterpret_cast<uintptr_t>(P) % 16) || (reinterpret_cast<uintptr_t>(G) % 16)) return 0;
   if ((long long)N * Hp * Wp > 2000000000LL) return 0;
@@ -198,14 +209,14 @@ static int launch_wg(const CUtensorMap& tG, const CUtensorMap& tG2, const CUtens
 }
 
 // G (and optional G2, concatenated on the channel axis after G) are the gathered activations; P = dy.
-int wgrad_tcgen05(const void* P, const void* G, const void* G2, float* dW, int N, int H, int W, int Cp, int C1, int C2,
-                  int cg_off, int cg_total, int kh, int kw, int pad, cudaStream_t st) {
+int wgrad_tcgen05(const void* P, const void* G, const void* G2, float* dW, int N, int H, int W, int Cp, int Hg, int Wg,
+                  int C1, int C2, int cg_off, int cg_total, int kh, int kw, int stride, int pad, cudaStream_t st) {
   EncodeTiledFn enc = get_tensormap_encoder();
   if (!enc) { set_error("conv2d_wgrad(tcgen05): cuTensorMapEncodeTiled not available"); return STFB_ECUDA; }
   if ((long long)N * H * W == 0) return STFB_OK;
   WgTcArgs a{};
   a.dW = dW; a.N = N; a.H = H; a.W = W; a.Cp = Cp; a.C1 = C1; a.C2 = C2; a.cg_off = cg_off; a.cg_total = cg_total;
-  a.kh = kh; a.kw = kw; a.pad = pad;
+  a.kh = kh; a.kw = kw; a.pad = pad; a.g_scale = stride;
   a.TW = pow2_floor(W); if (a.TW > 8) a.TW = 8;
   a.TH = pow2_floor(H); if (a.TH > WG_PIX / a.TW) a.TH = WG_PIX / a.TW;
   a.TN = WG_PIX / (a.TW * a.TH);
@@ -227,9 +238,9 @@ int wgrad_tcgen05(const void* P, const void* G, const void* G2, float* dW, int N
   splits = (a.n_patches + a.patches_per_split - 1) / a.patches_per_split;
 
   CUtensorMap tG, tG2, tP;
-  if (!encode_nhwc_map(enc, &tG, G, N, H, W, C1, a.TW, a.TH, a.TN)) { set_error("conv2d_wgrad(tcgen05): tensor map (G) failed"); return STFB_ECUDA; }
+  if (!encode_nhwc_map_strided(enc, &tG, G, N, Hg, Wg, C1, a.TW, a.TH, a.TN, stride)) { set_error("conv2d_wgrad(tcgen05): tensor map (G) failed"); return STFB_ECUDA; }
   tG2 = tG;
-  if (C2 > 0 && !encode_nhwc_map(enc, &tG2, G2, N, H, W, C2, a.TW, a.TH, a.TN)) { set_error("conv2d_wgrad(tcgen05): tensor map (G2) failed"); return STFB_ECUDA; }
+  if (C2 > 0 && !encode_nhwc_map_strided(enc, &tG2, G2, N, Hg, Wg, C2, a.TW, a.TH, a.TN, stride)) { set_error("conv2d_wgrad(tcgen05): tensor map (G2) failed"); return STFB_ECUDA; }
   if (!encode_nhwc_map(enc, &tP, P, N, H, W, Cp, a.TW, a.TH, a.TN)) { set_error("conv2d_wgrad(tcgen05): tensor map (P) failed"); return STFB_ECUDA; }
   dim3 grid((unsigned)m_tiles, (unsigned)n_tiles, (unsigned)splits);
   switch (BN) {

@@ -71,14 +71,14 @@ class Executor:
 
     _tc_cache = {}
 
-    def use_tc(self, x, Cout, k, stride, pad, x2=None, transposed=False):
-        """Does this convolution go to the tcgen05 family (bf16, stride-1 'same', 64-channel multiples)?"""
-        if self.dtype != torch.bfloat16 or transposed or not USE_TCGEN05:
+    def use_tc(self, x, Cout, k, stride, pad, x2=None, mode=ops.CONV_FWD, out_hw=None):
+        """Does this convolution go to the tcgen05 family (bf16, 64-channel multiples, stride 1/2, k <= 3)?"""
+        if self.dtype != torch.bfloat16 or not USE_TCGEN05:
             return False
-        key = (tuple(x.shape), Cout, k, stride, pad, None if x2 is None else x2.shape[3])
+        key = (tuple(x.shape), Cout, k, stride, pad, None if x2 is None else x2.shape[3], mode, out_hw)
         r = Executor._tc_cache.get(key)
         if r is None:
-            r = ops.tcgen05_ok(x, Cout, k, stride, pad, x2=x2)
+            r = ops.tcgen05_ok(x, Cout, k, stride, pad, mode=mode, x2=x2, out_hw=out_hw)
             Executor._tc_cache[key] = r
         return r
 
@@ -99,7 +99,7 @@ class Executor:
         mode = ops.CONV_TRANSPOSED if transposed else ops.CONV_FWD
         out_hw = ops.conv_out_hw(H, W, k, stride, pad, transposed, out_pad)
         x2d = None if x2 is None else x2.data
-        tc = self.use_tc(x.data, Cout, k, stride, pad, x2d, transposed)
+        tc = self.use_tc(x.data, Cout, k, stride, pad, x2d, mode, out_hw)
         wp = self.packed(wname, k_is_dim1=not transposed, n_major=tc)
         bias = self.params[bname] if bname else None
         y = ops.conv2d(x.data, wp, Cout, k, stride, pad, mode=mode, out_hw=out_hw, x2=x2d,
@@ -129,17 +129,14 @@ class Executor:
             for src, off, csrc in srcs:
                 if not src.needs_grad:
                     continue
-                if not transposed and self.use_tc(dy, csrc, k, stride, pad):
-                    # stride-1 "same" conv: dgrad == forward conv over dy with mirrored taps, on the tensor cores
-                    wpd = self.packed(wname, k_is_dim1=False, n_major=True, flip=True)     # [Cin][(ky,kx,co)]
-                    g = ops.conv2d(dy, wpd, csrc, k, 1, pad, residual=src.grad, out=src.grad, y_dtype=src.grad_dtype,
-                                   ldw=wpd.shape[1], w_offset=off * wpd.shape[1], impl=ops.IMPL_TCGEN05)
-                else:
-                    wpd = self.packed(wname, k_is_dim1=transposed)
-                    g = ops.conv2d(dy, wpd, csrc, k, stride, pad,
-                                   mode=ops.CONV_FWD if transposed else ops.CONV_TRANSPOSED, out_hw=(H, W),
-                                   residual=src.grad, out=src.grad, y_dtype=src.grad_dtype, ldw=C1 + C2, w_offset=off,
-                                   impl=ops.IMPL_SIMT)
+                mode_d = ops.CONV_FWD if transposed else ops.CONV_TRANSPOSED
+                tcd = self.use_tc(dy, csrc, k, stride, pad, None, mode_d, (H, W))
+                wpd = self.packed(wname, k_is_dim1=transposed, n_major=tcd)
+                # tcgen05 packing is [n = source channel][K]: a source window is a row offset; SIMT: a column offset
+                g = ops.conv2d(dy, wpd, csrc, k, stride, pad, mode=mode_d, out_hw=(H, W), residual=src.grad,
+                               out=src.grad, y_dtype=src.grad_dtype, ldw=wpd.shape[1] if tcd else C1 + C2,
+                               w_offset=off * wpd.shape[1] if tcd else off,
+                               impl=ops.IMPL_TCGEN05 if tcd else ops.IMPL_SIMT)
                 src.grad = g
 
         self.tape.append(bwd)

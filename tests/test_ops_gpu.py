@@ -421,3 +421,84 @@ def test_wgrad_tcgen05_matches_reference(case):
         ops.conv2d_wgrad(nhwc(dy, dtype), nhwc(x[:, :h], dtype), dW2, k, 1, pad, 0, Cin, impl=ops.IMPL_TCGEN05)
         ops.conv2d_wgrad(nhwc(dy, dtype), nhwc(x[:, h:], dtype), dW2, k, 1, pad, h, Cin, impl=ops.IMPL_TCGEN05)
         assert rel(dW2, w.grad) < 1e-4
+
+
+TC_S2_FWD = [(2, 16, 16, 64, 128, 3, 1), (3, 9, 11, 64, 64, 3, 1), (2, 32, 32, 128, 256, 1, 0), (16, 64, 64, 64, 128, 3, 1)]
+
+
+@pytest.mark.parametrize("case", TC_S2_FWD)
+def test_conv_tcgen05_stride2_forward(case):
+    N, H, W, Cin, Cout, k, pad = case
+    dtype = torch.bfloat16
+    x = q(rnd(N, Cin, H, W, seed=1), dtype)
+    w = q(rnd(Cout, Cin, k, k, seed=2, scale=(1.0 / (k * k * Cin) ** 0.5)), dtype)
+    ref = F.conv2d(x, w, None, 2, pad)
+    xn = nhwc(x, dtype)
+    assert ops.tcgen05_ok(xn, Cout, k, 2, pad)
+    wp = ops.pack_weight(w.contiguous(), True, dtype, n_major=True)
+    y = ops.conv2d(xn, wp, Cout, k, 2, pad, y_dtype=torch.float32, impl=ops.IMPL_TCGEN05)
+    torch.cuda.synchronize()
+    assert y.shape[1:3] == ref.shape[2:]
+    assert rel(nchw(y), ref) < 2e-3
+
+
+TC_TRANSPOSED = [
+    # N, Hin, Win, Cin(gemm K), Cout(gemm N), k, stride, pad, out_pad
+    (2, 8, 8, 128, 64, 3, 2, 1, 1),      # ConvTranspose2d 3x3/2 (decoder up) == 3x3/2 conv dgrad to an even size
+    (1, 13, 13, 64, 64, 3, 2, 1, 0),     # dgrad of a 3x3/2 conv over a 25x25 input (odd size: ragged phases)
+    (2, 8, 8, 256, 128, 2, 2, 0, 0),     # UNet ConvTranspose2d 2x2/2
+    (2, 8, 8, 128, 64, 1, 2, 0, 1),      # dgrad of the 1x1/2 downsample conv: three of four phases are pure zeros
+    (2, 16, 16, 64, 128, 3, 1, 1, 0),    # stride-1 dgrad without flipping the weights
+    (16, 16, 16, 256, 128, 3, 2, 1, 1),
+]
+
+
+@pytest.mark.parametrize("case", TC_TRANSPOSED)
+def test_conv_tcgen05_transposed_phases(case):
+    N, H, W, Cin, Cout, k, s, pad, op = case
+    dtype = torch.bfloat16
+    x = q(rnd(N, Cin, H, W, seed=1), dtype)
+    w = q(rnd(Cin, Cout, k, k, seed=2, scale=0.05), dtype)       # ConvTranspose2d layout [in, out, k, k]
+    bias = rnd(Cout, seed=3)
+    ref = F.conv_transpose2d(x, w, bias, stride=s, padding=pad, output_padding=op)
+    res = q(rnd(*ref.shape, seed=4), dtype)
+    xn = nhwc(x, dtype)
+    out_hw = tuple(ref.shape[2:])
+    assert ops.tcgen05_ok(xn, Cout, k, s, pad, mode=ops.CONV_TRANSPOSED, out_hw=out_hw)
+    wp = ops.pack_weight(w.contiguous(), False, dtype, n_major=True)    # [co][(tap, ci)]
+    y = ops.conv2d(xn, wp, Cout, k, s, pad, mode=ops.CONV_TRANSPOSED, out_hw=out_hw, bias=bias, residual=nhwc(res, dtype).float(),
+                   y_dtype=torch.float32, impl=ops.IMPL_TCGEN05)
+    torch.cuda.synchronize()
+    assert rel(nchw(y), ref + res) < 2e-3
+
+
+WG_S2 = [(2, 16, 16, 64, 128, 3, 1), (3, 9, 11, 64, 64, 3, 1), (2, 32, 32, 128, 256, 1, 0), (8, 64, 64, 64, 128, 3, 1)]
+
+
+@pytest.mark.parametrize("case", WG_S2)
+def test_wgrad_tcgen05_stride2(case):
+    N, H, W, Cin, Cout, k, pad = case
+    dtype = torch.bfloat16
+    x = q(rnd(N, Cin, H, W, seed=1), dtype)
+    w = torch.zeros(Cout, Cin, k, k, device=DEV, requires_grad=True)
+    y = F.conv2d(x, w, None, 2, pad)
+    dy = q(rnd(*y.shape, seed=2), dtype)
+    y.backward(dy)
+    dW = torch.zeros_like(w)
+    ops.conv2d_wgrad(nhwc(dy, dtype), nhwc(x, dtype), dW, k, 2, pad, 0, Cin, impl=ops.IMPL_TCGEN05)
+    torch.cuda.synchronize()
+    assert rel(dW, w.grad) < 1e-4
+
+
+def test_wgrad_tcgen05_conv_transpose():
+    N, H, W, Cin, Cout, k = 2, 8, 8, 128, 64, 3
+    dtype = torch.bfloat16
+    x = q(rnd(N, Cin, H, W, seed=1), dtype)
+    w = torch.zeros(Cin, Cout, k, k, device=DEV, requires_grad=True)
+    y = F.conv_transpose2d(x, w, None, stride=2, padding=1, output_padding=1)
+    dy = q(rnd(*y.shape, seed=2), dtype)
+    y.backward(dy)
+    dW = torch.zeros_like(w)
+    ops.conv2d_wgrad(nhwc(x, dtype), nhwc(dy, dtype), dW, k, 2, 1, 0, Cout, impl=ops.IMPL_TCGEN05)
+    torch.cuda.synchronize()
+    assert rel(dW, w.grad) < 1e-4
