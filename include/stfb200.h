@@ -105,7 +105,15 @@ int stfb_pack_weight(const float* w, void* wp, int D0, int D1, int kh, int kw, i
  * tcgen05 family, row stride ldw = kh*kw*K).  flip = 1 mirrors the taps (ky,kx) -> (kh-1-ky, kw-1-kx), which turns the
  * dgrad of a stride-1 "same" convolution into a forward convolution over dy. */
 int stfb_pack_weight_ex(const float* w, void* wp, int D0, int D1, int kh, int kw, int k_is_dim1, int n_major, int flip,
-                        int dtype, void* stream);
+                        int ld /* n_major row stride, 0 = dense; the caller zero-fills any padding */, int dtype, void* stream);
+
+/* Small-channel convolutions (7x7/2 stem with Cin = 1, src/stf_lstm_unet.py:105,177; UNet enc1.0, src/unet.py:20) on
+ * the tensor cores: out[N,Ho,Wo,Kpad] (bf16) = im2col of x with K order (ky,kx,ci), zero-padded to Kpad (multiple of 64),
+ * after which the conv is a 1x1 GEMM over `out` and its weight gradient a 1x1 wgrad. */
+int stfb_im2col_small(const void* x, void* out, int N, int H, int W, int Cin, int Ho, int Wo, int k, int stride, int pad,
+                      int Kpad, void* stream);
+/* dW[co][ci][ky][kx] += src[co][(ky,kx,ci)] (src rows ld_src wide): folds the im2col weight gradient back. */
+int stfb_unpad_wgrad(float* dW, const float* src, int Cout, int Cin, int kh, int kw, int ld_src, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * BatchNorm2d (eps, momentum as nn.BatchNorm2d defaults 1e-5 / 0.1; torchvision BasicBlock bn1/bn2,
@@ -149,6 +157,13 @@ int stfb_maxpool_fwd(const void* x, void* y, int N, int H, int W, int C, int Ho,
                      int dtype, void* stream);
 int stfb_maxpool_bwd(const void* x, const void* dy, void* dx, int N, int H, int W, int C, int Ho, int Wo, int k,
                      int stride, int pad, int dtype, void* stream);
+
+/* Training variants: forward also stores, per output element, the window position ky*k+kx of its first maximum (uint8);
+ * backward gathers through that index instead of re-scanning the input windows. */
+int stfb_maxpool_fwd_idx(const void* x, void* y, unsigned char* idx, int N, int H, int W, int C, int Ho, int Wo, int k,
+                         int stride, int pad, int dtype, void* stream);
+int stfb_maxpool_bwd_idx(const unsigned char* idx, const void* dy, void* dx, int N, int H, int W, int C, int Ho, int Wo, int k,
+                         int stride, int pad, int dtype, void* stream);
 
 /* Bilinear resize, align_corners=True (F.interpolate at src/stf_lstm_unet.py:57,191-194), NHWC. */
 int stfb_bilinear_fwd(const void* x, void* y, int N, int H, int W, int C, int Ho, int Wo, int dtype, void* stream);

@@ -30,7 +30,9 @@ _SIGS = {
     "stfb_conv2d_wgrad": [_vp, _vp, _vp] + [_i] * 15 + [_vp],
     "stfb_conv2d_wgrad_tcgen05_supported": [_vp, _vp] + [_i] * 12,
     "stfb_pack_weight": [_vp, _vp, _i, _i, _i, _i, _i, _i, _vp],
-    "stfb_pack_weight_ex": [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp],
+    "stfb_pack_weight_ex": [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp],
+    "stfb_im2col_small": [_vp, _vp] + [_i] * 10 + [_vp],
+    "stfb_unpad_wgrad": [_vp, _vp, _i, _i, _i, _i, _i, _vp],
     "stfb_bn_stats": [_vp, _vp, _i, _ll, _i, _i, _vp],
     "stfb_bn_finalize_train": [_vp] * 10 + [_i, _ll, _i, _f, _f, _vp],
     "stfb_bn_fold_eval": [_vp] * 6 + [_i, _f, _vp],
@@ -41,6 +43,8 @@ _SIGS = {
     "stfb_colsum": [_vp, _vp, _ll, _i, _i, _vp],
     "stfb_maxpool_fwd": [_vp, _vp] + [_i] * 10 + [_vp],
     "stfb_maxpool_bwd": [_vp, _vp, _vp] + [_i] * 10 + [_vp],
+    "stfb_maxpool_fwd_idx": [_vp, _vp, _vp] + [_i] * 10 + [_vp],
+    "stfb_maxpool_bwd_idx": [_vp, _vp, _vp] + [_i] * 10 + [_vp],
     "stfb_bilinear_fwd": [_vp, _vp] + [_i] * 7 + [_vp],
     "stfb_bilinear_bwd": [_vp, _vp] + [_i] * 7 + [_vp],
     "stfb_lstm_cell_fwd": [_vp] * 5 + [_ll, _i, _i, _vp],

@@ -404,6 +404,104 @@ __global__ void maxpool_bwd_kernel(const T* __restrict__ x, const T* __restrict_
   }
 }
 
+// ---- indexed variants: forward stores the window position of the first maximum (uint8), backward gathers by index.
+template <typename T, int VEC>
+__global__ void maxpool_fwd_idx_kernel(const T* __restrict__ x, T* __restrict__ y, unsigned char* __restrict__ idx, int N, int H,
+                                       int W, int C, int Ho, int Wo, int k, int stride, int pad, long long total_vec) {
+  const int CVn = C / VEC;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total_vec; i += (long long)gridDim.x * blockDim.x) {
+    const int cv = (int)(i % CVn);
+    long long r = i / CVn;
+    const int ox = (int)(r % Wo); r /= Wo;
+    const int oy = (int)(r % Ho);
+    const int n = (int)(r / Ho);
+    float best[VEC];
+    int arg[VEC];
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) { best[j] = -INFINITY; arg[j] = -1; }
+    for (int ky = 0; ky < k; ++ky) {
+      const int iy = oy * stride - pad + ky;
+      if (iy < 0 || iy >= H) continue;
+      for (int kx = 0; kx < k; ++kx) {
+        const int ix = ox * stride - pad + kx;
+        if (ix < 0 || ix >= W) continue;
+        const long long off = (((long long)n * H + iy) * W + ix) * C + cv * VEC;
+        float v[VEC];
+        if (VEC == 8) {
+          f8 t = ld8(x + off);
+#pragma unroll
+          for (int j = 0; j < VEC; ++j) v[j] = t.v[j];
+        } else {
+          v[0] = ld1(x + off);
+        }
+#pragma unroll
+        for (int j = 0; j < VEC; ++j)
+          if (v[j] > best[j] || arg[j] < 0) { best[j] = v[j]; arg[j] = ky * k + kx; }
+      }
+    }
+    const long long oo = (((long long)n * Ho + oy) * Wo + ox) * C + cv * VEC;
+    if (VEC == 8) {
+      st4(y + oo, f4{{best[0], best[1], best[2], best[3]}});
+      st4(y + oo + 4, f4{{best[4 % VEC], best[5 % VEC], best[6 % VEC], best[7 % VEC]}});
+      uint2 pk;
+      pk.x = (unsigned)arg[0] | ((unsigned)arg[1 % VEC] << 8) | ((unsigned)arg[2 % VEC] << 16) | ((unsigned)arg[3 % VEC] << 24);
+      pk.y = (unsigned)arg[4 % VEC] | ((unsigned)arg[5 % VEC] << 8) | ((unsigned)arg[6 % VEC] << 16) | ((unsigned)arg[7 % VEC] << 24);
+      *reinterpret_cast<uint2*>(idx + oo) = pk;
+    } else {
+      st1(y + oo, best[0]);
+      idx[oo] = (unsigned char)arg[0];
+    }
+  }
+}
+
+template <typename T, int VEC>
+__global__ void maxpool_bwd_idx_kernel(const unsigned char* __restrict__ idx, const T* __restrict__ dy, T* __restrict__ dx, int N,
+                                       int H, int W, int C, int Ho, int Wo, int k, int stride, int pad, long long total_vec) {
+  const int CVn = C / VEC;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total_vec; i += (long long)gridDim.x * blockDim.x) {
+    const int cv = (int)(i % CVn);
+    long long r = i / CVn;
+    const int ix = (int)(r % W); r /= W;
+    const int iy = (int)(r % H);
+    const int n = (int)(r / H);
+    float acc[VEC];
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) acc[j] = 0.f;
+    int oy_lo = iy + pad - k + 1; oy_lo = oy_lo <= 0 ? 0 : (oy_lo + stride - 1) / stride;
+    int oy_hi = (iy + pad) / stride; if (oy_hi > Ho - 1) oy_hi = Ho - 1;
+    int ox_lo = ix + pad - k + 1; ox_lo = ox_lo <= 0 ? 0 : (ox_lo + stride - 1) / stride;
+    int ox_hi = (ix + pad) / stride; if (ox_hi > Wo - 1) ox_hi = Wo - 1;
+    for (int oy = oy_lo; oy <= oy_hi; ++oy) {
+      for (int ox = ox_lo; ox <= ox_hi; ++ox) {
+        const int pos = (iy - (oy * stride - pad)) * k + (ix - (ox * stride - pad));
+        const long long oo = (((long long)n * Ho + oy) * Wo + ox) * C + cv * VEC;
+        if (VEC == 8) {
+          const uint2 pk = *reinterpret_cast<const uint2*>(idx + oo);
+          const unsigned w[2] = {pk.x, pk.y};
+          bool any = false;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) any |= (int)((w[j >> 2] >> (8 * (j & 3))) & 0xFF) == pos;
+          if (any) {
+            f8 g = ld8(dy + oo);
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              if ((int)((w[j >> 2] >> (8 * (j & 3))) & 0xFF) == pos) acc[j % VEC] += g.v[j];
+          }
+        } else {
+          if ((int)idx[oo] == pos) acc[0] += ld1(dy + oo);
+        }
+      }
+    }
+    const long long io = (((long long)n * H + iy) * W + ix) * C + cv * VEC;
+    if (VEC == 8) {
+      st4(dx + io, f4{{acc[0], acc[1 % VEC], acc[2 % VEC], acc[3 % VEC]}});
+      st4(dx + io + 4, f4{{acc[4 % VEC], acc[5 % VEC], acc[6 % VEC], acc[7 % VEC]}});
+    } else {
+      st1(dx + io, acc[0]);
+    }
+  }
+}
+
 // =================================================================================================
 // bilinear, align_corners=True
 // =================================================================================================
@@ -561,6 +659,52 @@ __global__ void nchw_to_nhwc_kernel(const float* __restrict__ g, T* __restrict__
   }
 }
 
+// im2col for small-channel convolutions (7x7 stem with Cin=1, UNet first conv): out[m][(ky,kx,ci)] zero-padded to Kpad,
+// so the convolution becomes a K = Kpad GEMM the tcgen05 family can take.  One thread = 8 consecutive k (16 B store).
+__global__ void im2col_small_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ out, int N, int H, int W,
+                                    int Cin, int Ho, int Wo, int k, int stride, int pad, int Kpad, long long total) {
+  const int chunks = Kpad / 8;
+  const int Ktot = k * k * Cin;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int ch = (int)(i % chunks);
+    long long r = i / chunks;
+    const int ox = (int)(r % Wo); r /= Wo;
+    const int oy = (int)(r % Ho);
+    const int n = (int)(r / Ho);
+    unsigned short v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int kk = ch * 8 + j;
+      unsigned short bits = 0;
+      if (kk < Ktot) {
+        const int tap = kk / Cin, ci = kk - tap * Cin;
+        const int ky = tap / k, kx = tap - ky * k;
+        const int iy = oy * stride - pad + ky, ix = ox * stride - pad + kx;
+        if (iy >= 0 && iy < H && ix >= 0 && ix < W)
+          bits = __bfloat16_as_ushort(x[(((long long)n * H + iy) * W + ix) * Cin + ci]);
+      }
+      v[j] = bits;
+    }
+    uint4 pk;
+    pk.x = v[0] | ((unsigned)v[1] << 16); pk.y = v[2] | ((unsigned)v[3] << 16);
+    pk.z = v[4] | ((unsigned)v[5] << 16); pk.w = v[6] | ((unsigned)v[7] << 16);
+    *reinterpret_cast<uint4*>(out + i * 8) = pk;
+  }
+}
+
+// dW[r][ci][tap] += src[r][tap*Cin + ci]: folds the K-padded, (tap, ci)-ordered im2col weight gradient back into the
+// parameter layout [Cout][Cin][kh][kw]
+__global__ void unpad_wgrad_kernel(float* __restrict__ dst, const float* __restrict__ src, int rows, int Cin, int khw, int ld_src) {
+  const long long total = (long long)rows * Cin * khw;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int tap = (int)(i % khw);
+    long long r = i / khw;
+    const int ci = (int)(r % Cin);
+    r /= Cin;
+    dst[i] += src[r * ld_src + (long long)tap * Cin + ci];
+  }
+}
+
 template <typename T>
 __global__ void add_inplace_kernel(T* __restrict__ d, const T* __restrict__ s, long long n) {
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
@@ -698,6 +842,38 @@ extern "C" int stfb_maxpool_fwd(const void* x, void* y, int N, int H, int W, int
   return post_launch("maxpool_fwd");
 }
 
+extern "C" int stfb_maxpool_fwd_idx(const void* x, void* y, unsigned char* idx, int N, int H, int W, int C, int Ho, int Wo, int k,
+                                    int stride, int pad, int dtype, void* stream) {
+  STFB_REQUIRE(x && y && idx && N >= 0 && H > 0 && W > 0 && C > 0 && k > 0 && k <= 15 && stride > 0 && pad >= 0 && 2 * pad <= k && DT_OK(dtype),
+               "maxpool_fwd_idx: bad arguments");
+  STFB_REQUIRE(Ho == (H + 2 * pad - k) / stride + 1 && Wo == (W + 2 * pad - k) / stride + 1, "maxpool_fwd_idx: bad output size");
+  STFB_DEVICE_OR_RETURN();
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  const bool v = (C % 8 == 0) && aligned_to(x, 16) && aligned_to(y, 16) && aligned_to(idx, 8);
+  const long long tv = (long long)N * Ho * Wo * (C / (v ? 8 : 1));
+  if (tv == 0) return STFB_OK;
+  DISPATCH_T(dtype, {
+    if (v) maxpool_fwd_idx_kernel<T, 8><<<grid_for(tv), 256, 0, s>>>((const T*)x, (T*)y, idx, N, H, W, C, Ho, Wo, k, stride, pad, tv);
+    else maxpool_fwd_idx_kernel<T, 1><<<grid_for(tv), 256, 0, s>>>((const T*)x, (T*)y, idx, N, H, W, C, Ho, Wo, k, stride, pad, tv);
+  });
+  return post_launch("maxpool_fwd_idx");
+}
+
+extern "C" int stfb_maxpool_bwd_idx(const unsigned char* idx, const void* dy, void* dx, int N, int H, int W, int C, int Ho, int Wo,
+                                    int k, int stride, int pad, int dtype, void* stream) {
+  STFB_REQUIRE(idx && dy && dx && N >= 0 && H > 0 && W > 0 && C > 0 && k > 0 && stride > 0 && pad >= 0 && DT_OK(dtype), "maxpool_bwd_idx: bad arguments");
+  STFB_DEVICE_OR_RETURN();
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  const bool v = (C % 8 == 0) && aligned_to(dy, 16) && aligned_to(dx, 16) && aligned_to(idx, 8);
+  const long long tv = (long long)N * H * W * (C / (v ? 8 : 1));
+  if (tv == 0) return STFB_OK;
+  DISPATCH_T(dtype, {
+    if (v) maxpool_bwd_idx_kernel<T, 8><<<grid_for(tv), 256, 0, s>>>(idx, (const T*)dy, (T*)dx, N, H, W, C, Ho, Wo, k, stride, pad, tv);
+    else maxpool_bwd_idx_kernel<T, 1><<<grid_for(tv), 256, 0, s>>>(idx, (const T*)dy, (T*)dx, N, H, W, C, Ho, Wo, k, stride, pad, tv);
+  });
+  return post_launch("maxpool_bwd_idx");
+}
+
 extern "C" int stfb_maxpool_bwd(const void* x, const void* dy, void* dx, int N, int H, int W, int C, int Ho, int Wo, int k,
                                 int stride, int pad, int dtype, void* stream) {
   STFB_REQUIRE(x && dy && dx && N >= 0 && H > 0 && W > 0 && C > 0 && k > 0 && stride > 0 && pad >= 0 && DT_OK(dtype), "maxpool_bwd: bad arguments");
@@ -807,4 +983,26 @@ extern "C" int stfb_add_inplace(void* dst, const void* src, long long n, int dty
   if (n == 0) return STFB_OK;
   DISPATCH_T(dtype, { add_inplace_kernel<T><<<grid_for(n), 256, 0, s>>>((T*)dst, (const T*)src, n); });
   return post_launch("add_inplace");
+}
+
+extern "C" int stfb_im2col_small(const void* x, void* out, int N, int H, int W, int Cin, int Ho, int Wo, int k, int stride, int pad,
+                                 int Kpad, void* stream) {
+  STFB_REQUIRE(x && out && N >= 0 && H > 0 && W > 0 && Cin > 0 && k > 0 && stride > 0 && pad >= 0, "im2col_small: bad arguments");
+  STFB_REQUIRE(Kpad % 8 == 0 && Kpad >= k * k * Cin, "im2col_small: Kpad must be a multiple of 8 covering k*k*Cin");
+  STFB_REQUIRE(Ho == (H + 2 * pad - k) / stride + 1 && Wo == (W + 2 * pad - k) / stride + 1, "im2col_small: bad output size");
+  STFB_REQUIRE(aligned_to(out, 16), "im2col_small: out must be 16-byte aligned");
+  STFB_DEVICE_OR_RETURN();
+  const long long total = (long long)N * Ho * Wo * (Kpad / 8);
+  if (total == 0) return STFB_OK;
+  im2col_small_kernel<<<grid_for(total), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      (const __nv_bfloat16*)x, (__nv_bfloat16*)out, N, H, W, Cin, Ho, Wo, k, stride, pad, Kpad, total);
+  return post_launch("im2col_small");
+}
+
+extern "C" int stfb_unpad_wgrad(float* dW, const float* src, int Cout, int Cin, int kh, int kw, int ld_src, void* stream) {
+  STFB_REQUIRE(dW && src && Cout > 0 && Cin > 0 && kh > 0 && kw > 0 && ld_src >= Cin * kh * kw, "unpad_wgrad: bad arguments");
+  STFB_DEVICE_OR_RETURN();
+  const long long total = (long long)Cout * Cin * kh * kw;
+  unpad_wgrad_kernel<<<grid_for(total), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(dW, src, Cout, Cin, kh * kw, ld_src);
+  return post_launch("unpad_wgrad");
 }

@@ -434,7 +434,7 @@ int conv2d_wgrad_simt(const WgradArgs& a0, int dtype, cudaStream_t st) {
 // =================================================================================================
 template <typename T>
 __global__ void pack_weight_kernel(const float* __restrict__ w, T* __restrict__ wp, int D0, int D1, int khw,
-                                   int k_is_dim1, int n_major, int flip) {
+                                   int k_is_dim1, int n_major, int flip, int ld) {
   const long long total = (long long)D0 * D1 * khw;
   const int Kc = k_is_dim1 ? D1 : D0, Nc = k_is_dim1 ? D0 : D1;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -452,7 +452,9 @@ __global__ void pack_weight_kernel(const float* __restrict__ w, T* __restrict__ 
     }
     const int d0 = k_is_dim1 ? n : k, d1 = k_is_dim1 ? k : n;
     const int stap = flip ? (khw - 1 - tap) : tap;   // spatial flip (ky,kx) -> (kh-1-ky, kw-1-kx)
-    st1(wp + i, w[((long long)d0 * D1 + d1) * khw + stap]);
+    // n_major rows may be padded to `ld` elements (K padded to the 64-wide k-block; the caller zero-fills the pad)
+    const long long di = n_major ? (long long)n * ld + (long long)tap * Kc + k : i;
+    st1(wp + di, w[((long long)d0 * D1 + d1) * khw + stap]);
   }
 }
 
@@ -545,8 +547,13 @@ extern "C" int stfb_conv2d_wgrad(const void* P, const void* G, float* dW, int N,
 }
 
 extern "C" int stfb_pack_weight_ex(const float* w, void* wp, int D0, int D1, int kh, int kw, int k_is_dim1, int n_major,
-                                   int flip, int dtype, void* stream) {
+                                   int flip, int ld, int dtype, void* stream) {
   STFB_REQUIRE(w && wp && D0 > 0 && D1 > 0 && kh > 0 && kw > 0, "pack_weight: bad arguments");
+  {
+    const int Kc_ = k_is_dim1 ? D1 : D0;
+    if (ld <= 0) ld = kh * kw * Kc_;
+    STFB_REQUIRE(!n_major || ld >= kh * kw * Kc_, "pack_weight: ld (%d) smaller than the packed row (%d)", ld, kh * kw * Kc_);
+  }
   STFB_REQUIRE(dtype == STFB_F32 || dtype == STFB_BF16, "pack_weight: bad dtype");
   STFB_DEVICE_OR_RETURN();
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
@@ -554,13 +561,13 @@ extern "C" int stfb_pack_weight_ex(const float* w, void* wp, int D0, int D1, int
   int blocks = ceil_div(total, 256);
   if (blocks > 8 * num_sms()) blocks = 8 * num_sms();
   if (dtype == STFB_F32)
-    pack_weight_kernel<float><<<blocks, 256, 0, s>>>(w, reinterpret_cast<float*>(wp), D0, D1, kh * kw, k_is_dim1, n_major, flip);
+    pack_weight_kernel<float><<<blocks, 256, 0, s>>>(w, reinterpret_cast<float*>(wp), D0, D1, kh * kw, k_is_dim1, n_major, flip, ld);
   else
-    pack_weight_kernel<__nv_bfloat16><<<blocks, 256, 0, s>>>(w, reinterpret_cast<__nv_bfloat16*>(wp), D0, D1, kh * kw, k_is_dim1, n_major, flip);
+    pack_weight_kernel<__nv_bfloat16><<<blocks, 256, 0, s>>>(w, reinterpret_cast<__nv_bfloat16*>(wp), D0, D1, kh * kw, k_is_dim1, n_major, flip, ld);
   return post_launch("pack_weight");
 }
 
 extern "C" int stfb_pack_weight(const float* w, void* wp, int D0, int D1, int kh, int kw, int k_is_dim1, int dtype,
                                 void* stream) {
-  return stfb_pack_weight_ex(w, wp, D0, D1, kh, kw, k_is_dim1, 0, 0, dtype, stream);
+  return stfb_pack_weight_ex(w, wp, D0, D1, kh, kw, k_is_dim1, 0, 0, 0, dtype, stream);
 }

@@ -96,6 +96,9 @@ class Executor:
         N, H, W, C1 = x.data.shape
         C2 = 0 if x2 is None else x2.data.shape[3]
         assert not (transposed and x2 is not None)
+        if (self.dtype == torch.bfloat16 and USE_TCGEN05 and not transposed and x2 is None and C1 % 64 != 0
+                and C1 * k * k <= 512 and Cout % 32 == 0 and not x.needs_grad and residual is None):
+            return self._conv_small_cin(x, wname, k, stride, pad, bname, scale, shift, relu, y_dtype)
         mode = ops.CONV_TRANSPOSED if transposed else ops.CONV_FWD
         out_hw = ops.conv_out_hw(H, W, k, stride, pad, transposed, out_pad)
         x2d = None if x2 is None else x2.data
@@ -138,6 +141,41 @@ class Executor:
                                w_offset=off * wpd.shape[1] if tcd else off,
                                impl=ops.IMPL_TCGEN05 if tcd else ops.IMPL_SIMT)
                 src.grad = g
+
+        self.tape.append(bwd)
+        return out
+
+    def _conv_small_cin(self, x, wname, k, stride, pad, bname, scale, shift, relu, y_dtype):
+        """Few-input-channel conv (7x7 stem, UNet enc1.0) as im2col (K padded to 64) + 1x1 tcgen05 GEMM; its weight
+        gradient is the 1x1 tcgen05 wgrad over the same im2col buffer.  The input never needs a gradient."""
+        w = self.params[wname]
+        Cout, Cin = w.shape[0], w.shape[1]
+        kpad = (Cin * k * k + 63) // 64 * 64
+        col = ops.im2col_small(x.data, k, stride, pad, kpad)
+        key = (wname, "im2col", kpad)
+        wp = self._packed.get(key)
+        if wp is None:
+            wp = ops.pack_weight(w, True, self.dtype, n_major=True, kpad=kpad)
+            self._packed[key] = wp
+        bias = self.params[bname] if bname else None
+        y = ops.conv2d(col, wp, Cout, 1, 1, 0, bias=bias, scale=scale, shift=shift, relu=relu, y_dtype=y_dtype,
+                       impl=ops.IMPL_TCGEN05)
+        out = Var(y, grad_dtype=self.dtype)
+        if not self.record:
+            return out
+        assert scale is None and not relu, "fused epilogue is inference-only"
+
+        def bwd():
+            dy = out.grad
+            out.grad = None
+            if dy is None:
+                return
+            if bname and self.wants_grad(bname):
+                ops.colsum(dy, self.grads[bname], dy.shape[0] * dy.shape[1] * dy.shape[2], Cout)
+            if self.wants_grad(wname):
+                scratch = torch.zeros((Cout, kpad), dtype=torch.float32, device=dy.device)
+                ops.conv2d_wgrad(dy, col, scratch, 1, 1, 0, 0, kpad)
+                ops.unpad_wgrad(self.grads[wname], scratch)
 
         self.tape.append(bwd)
         return out
@@ -192,15 +230,18 @@ class Executor:
 
     # ---------------------------------------------------------------------------------------------
     def maxpool(self, x: Var, k: int, stride: int, pad: int) -> Var:
-        y = ops.maxpool_fwd(x.data, k, stride, pad)
+        if not self.record:
+            return Var(ops.maxpool_fwd(x.data, k, stride, pad), grad_dtype=self.dtype)
+        y, idx = ops.maxpool_fwd_idx(x.data, k, stride, pad)
         out = Var(y, grad_dtype=self.dtype)
-        if self.record:
-            def bwd():
-                dy = out.grad
-                out.grad = None
-                if dy is not None and x.needs_grad:
-                    x.accumulate(ops.maxpool_bwd(x.data, dy, k, stride, pad))
-            self.tape.append(bwd)
+        in_shape = tuple(x.data.shape)
+
+        def bwd():
+            dy = out.grad
+            out.grad = None
+            if dy is not None and x.needs_grad:
+                x.accumulate(ops.maxpool_bwd_idx(idx, dy, in_shape, k, stride, pad))
+        self.tape.append(bwd)
         return out
 
     def resize(self, x: Var, Ho: int, Wo: int) -> Var:

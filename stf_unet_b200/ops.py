@@ -13,8 +13,8 @@ from . import _lib
 from ._lib import BF16, CONV_FWD, CONV_TRANSPOSED, F32, IMPL_AUTO, IMPL_SIMT, IMPL_TCGEN05, ConvParams, check
 
 __all__ = ["dt_code", "conv2d", "conv2d_wgrad", "pack_weight", "bn_stats", "bn_finalize_train", "bn_fold_eval",
-           "bn_apply", "bn_bwd", "colsum", "maxpool_fwd", "maxpool_bwd", "bilinear_fwd", "bilinear_bwd",
-           "tcgen05_ok", "lstm_cell_fwd", "lstm_cell_bwd", "pack_series", "nhwc_to_nchw", "nchw_to_nhwc", "add_", "cast",
+           "bn_apply", "bn_bwd", "colsum", "maxpool_fwd", "maxpool_bwd", "maxpool_fwd_idx", "maxpool_bwd_idx", "bilinear_fwd", "bilinear_bwd",
+           "tcgen05_ok", "im2col_small", "unpad_wgrad", "lstm_cell_fwd", "lstm_cell_bwd", "pack_series", "nhwc_to_nchw", "nchw_to_nhwc", "add_", "cast",
            "ce_dice_fwd", "ce_dice_bwd", "CONV_FWD", "CONV_TRANSPOSED", "IMPL_AUTO", "IMPL_SIMT", "IMPL_TCGEN05"]
 
 _DT = {torch.float32: F32, torch.bfloat16: BF16}
@@ -153,20 +153,39 @@ def conv2d_wgrad(P, G, dW, k, stride, pad, cg_off=0, cg_total=None, impl=IMPL_AU
                   f"P{tuple(P.shape)} G{tuple(G.shape)} k{kh} s{stride}")
 
 
-def pack_weight(w, k_is_dim1, dtype, n_major=False, flip=False):
+def pack_weight(w, k_is_dim1, dtype, n_major=False, flip=False, kpad=None):
     """[D0, D1, kh, kw] (or [D0, D1]) fp32 parameter -> GEMM operand in `dtype`:
-    [(ky,kx,k), n] (SIMT family) or, with n_major, [n, (ky,kx,k)] (tcgen05 family)."""
+    [(ky,kx,k), n] (SIMT family) or, with n_major, [n, (ky,kx,k)] (tcgen05 family; kpad zero-pads each row)."""
     _need_cuda(w)
     if w.dim() == 2:
         D0, D1, kh, kw = w.shape[0], w.shape[1], 1, 1
     else:
         D0, D1, kh, kw = w.shape
     Kc, Nc = (D1, D0) if k_is_dim1 else (D0, D1)
-    shape = (Nc, kh * kw * Kc) if n_major else (kh * kw * Kc, Nc)
-    wp = torch.empty(shape, dtype=dtype, device=w.device)
-    check(_lib.load().stfb_pack_weight_ex(_p(w), _p(wp), D0, D1, kh, kw, int(k_is_dim1), int(n_major), int(flip),
+    ld = 0
+    if n_major:
+        ld = kpad if kpad else kh * kw * Kc
+        wp = (torch.zeros if kpad else torch.empty)((Nc, ld), dtype=dtype, device=w.device)
+    else:
+        wp = torch.empty((kh * kw * Kc, Nc), dtype=dtype, device=w.device)
+    check(_lib.load().stfb_pack_weight_ex(_p(w), _p(wp), D0, D1, kh, kw, int(k_is_dim1), int(n_major), int(flip), ld,
                                           dt_code(dtype), _stream()), "pack_weight")
     return wp
+
+
+def im2col_small(x, k, stride, pad, kpad):
+    """bf16 [N,H,W,Cin] -> [N,Ho,Wo,kpad]: K order (ky,kx,ci), zero padded (small-channel convs on the tensor cores)."""
+    N, H, W, Cin = x.shape
+    Ho, Wo = conv_out_hw(H, W, k, stride, pad)
+    out = torch.empty((N, Ho, Wo, kpad), dtype=torch.bfloat16, device=x.device)
+    check(_lib.load().stfb_im2col_small(_p(x), _p(out), N, H, W, Cin, Ho, Wo, k, stride, pad, kpad, _stream()), "im2col_small")
+    return out
+
+
+def unpad_wgrad(dW, src):
+    """dW [Cout,Cin,kh,kw] += src [Cout, kpad] whose columns are ordered (ky,kx,ci)."""
+    Cout, Cin, kh, kw = dW.shape
+    check(_lib.load().stfb_unpad_wgrad(_p(dW), _p(src), Cout, Cin, kh, kw, src.shape[1], _stream()), "unpad_wgrad")
 
 
 def tcgen05_ok(x, Cout, k, stride, pad, mode=CONV_FWD, x2=None, out_hw=None, y_dtype=None):
@@ -237,6 +256,26 @@ def maxpool_fwd(x, k, stride, pad):
     check(_lib.load().stfb_maxpool_fwd(_p(x), _p(y), N, H, W, C_, Ho, Wo, k, stride, pad, dt_code(x.dtype), _stream()),
           "maxpool_fwd")
     return y
+
+
+def maxpool_fwd_idx(x, k, stride, pad):
+    """Forward that also returns the uint8 first-max window position per output element (training)."""
+    N, H, W, C_ = x.shape
+    Ho, Wo = (H + 2 * pad - k) // stride + 1, (W + 2 * pad - k) // stride + 1
+    y = torch.empty((N, Ho, Wo, C_), dtype=x.dtype, device=x.device)
+    idx = torch.empty((N, Ho, Wo, C_), dtype=torch.uint8, device=x.device)
+    check(_lib.load().stfb_maxpool_fwd_idx(_p(x), _p(y), _p(idx), N, H, W, C_, Ho, Wo, k, stride, pad, dt_code(x.dtype),
+                                           _stream()), "maxpool_fwd_idx")
+    return y, idx
+
+
+def maxpool_bwd_idx(idx, dy, in_shape, k, stride, pad):
+    N, H, W, C_ = in_shape
+    _, Ho, Wo, _ = dy.shape
+    dx = torch.empty(in_shape, dtype=dy.dtype, device=dy.device)
+    check(_lib.load().stfb_maxpool_bwd_idx(_p(idx), _p(dy), _p(dx), N, H, W, C_, Ho, Wo, k, stride, pad, dt_code(dy.dtype),
+                                           _stream()), "maxpool_bwd_idx")
+    return dx
 
 
 def maxpool_bwd(x, dy, k, stride, pad):

@@ -216,15 +216,25 @@ def test_maxpool(k, s, p, H, W, C, dtype):
     assert torch.equal(nchw(y), ref.detach())
     dx = ops.maxpool_bwd(xn, nhwc(dy, dtype), k, s, p)
     assert rel(nchw(dx), x.grad) < (1e-6 if dtype == torch.float32 else 1e-2)
+    # indexed (training) variants
+    y2, idx = ops.maxpool_fwd_idx(xn, k, s, p)
+    assert torch.equal(y2, y) and idx.dtype == torch.uint8 and int(idx.max()) < k * k
+    dx2 = ops.maxpool_bwd_idx(idx, nhwc(dy, dtype), tuple(xn.shape), k, s, p)
+    assert torch.equal(dx2, dx)
 
 
-def test_maxpool_ties_route_to_first_max():
-    x = torch.zeros(1, 4, 6, 6, device=DEV).requires_grad_(True)   # all equal: every window ties
+@pytest.mark.parametrize("C", [4, 16])
+def test_maxpool_ties_route_to_first_max(C):
+    x = torch.zeros(1, C, 6, 6, device=DEV).requires_grad_(True)   # all equal: every window ties
     ref = F.max_pool2d(x, 3, 2, 1)
     dy = rnd(*ref.shape, seed=3)
     ref.backward(dy)
-    dx = ops.maxpool_bwd(nhwc(x.detach(), torch.float32), nhwc(dy, torch.float32), 3, 2, 1)
+    xn = nhwc(x.detach(), torch.float32)
+    dx = ops.maxpool_bwd(xn, nhwc(dy, torch.float32), 3, 2, 1)
     assert rel(nchw(dx), x.grad) < 1e-6
+    _, idx = ops.maxpool_fwd_idx(xn, 3, 2, 1)
+    dx2 = ops.maxpool_bwd_idx(idx, nhwc(dy, torch.float32), tuple(xn.shape), 3, 2, 1)
+    assert rel(nchw(dx2), x.grad) < 1e-6
 
 
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
@@ -501,4 +511,25 @@ def test_wgrad_tcgen05_conv_transpose():
     dW = torch.zeros_like(w)
     ops.conv2d_wgrad(nhwc(x, dtype), nhwc(dy, dtype), dW, k, 2, 1, 0, Cout, impl=ops.IMPL_TCGEN05)
     torch.cuda.synchronize()
+    assert rel(dW, w.grad) < 1e-4
+
+
+@pytest.mark.parametrize("N,H,W,Cin,Cout,k,stride,pad", [(3, 20, 20, 1, 64, 7, 2, 3), (2, 16, 16, 8, 64, 3, 1, 1), (2, 33, 31, 1, 32, 3, 1, 1)])
+def test_small_cin_conv_via_im2col(N, H, W, Cin, Cout, k, stride, pad):
+    """7x7 stem / UNet first conv: im2col (K padded to 64) + 1x1 tcgen05 GEMM, and the wgrad through the same buffer."""
+    dtype = torch.bfloat16
+    x = q(rnd(N, Cin, H, W, seed=1), dtype)
+    w = q(rnd(Cout, Cin, k, k, seed=2, scale=0.2), dtype).requires_grad_(True)
+    y = F.conv2d(x, w, None, stride, pad)
+    dy = q(rnd(*y.shape, seed=3), dtype)
+    y.backward(dy)
+    kpad = (Cin * k * k + 63) // 64 * 64
+    col = ops.im2col_small(nhwc(x, dtype), k, stride, pad, kpad)
+    wp = ops.pack_weight(w.detach().contiguous(), True, dtype, n_major=True, kpad=kpad)
+    out = ops.conv2d(col, wp, Cout, 1, 1, 0, y_dtype=torch.float32, impl=ops.IMPL_TCGEN05)
+    assert rel(nchw(out), y.detach()) < 2e-3
+    scratch = torch.zeros(Cout, kpad, device=DEV)
+    ops.conv2d_wgrad(nhwc(dy, dtype), col, scratch, 1, 1, 0, 0, kpad)
+    dW = torch.zeros(Cout, Cin, k, k, device=DEV)
+    ops.unpad_wgrad(dW, scratch)
     assert rel(dW, w.grad) < 1e-4
