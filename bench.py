@@ -217,7 +217,13 @@ def run_own(args, rank, world, local_rank):
         if args.profile_detail:
             for ms, n, tf, family, tag in prof.top(40):
                 print(f"[prof] {ms:8.3f} ms  n={n:3d}  {tf:7.1f} TF/s  {family:18s} {tag}", file=sys.stderr)
+            for k, v in sorted(fam.items(), key=lambda kv: -kv[1]["ms"]):
+                print(f"[family] {k:18s} {v['ms']:8.3f} ms  n={v['n']:4d}  {v['flops'] / (v['ms'] * 1e-3) / 1e12 if v['ms'] else 0:7.1f} TF/s  "
+                      f"{v['bytes'] / (v['ms'] * 1e-3) / 1e9 if v['ms'] else 0:8.1f} GB/s", file=sys.stderr)
         pk = peaks()
+        gemm = {k: v for k, v in fam.items() if v["flops"] > 0}
+        membound = {k: v for k, v in fam.items() if v["flops"] == 0}
+        fam = gemm
         if fam:
             top = max(fam.items(), key=lambda kv: kv[1]["ms"])
             name, d = top
@@ -228,7 +234,11 @@ def run_own(args, rank, world, local_rank):
                     "share_of_step": round(d["ms"] / sum(v["ms"] for v in fam.values()), 3),
                     "families": {k: {"ms": round(v["ms"], 3), "n": v["n"],
                                      "tflops": round(v["flops"] / (v["ms"] / 1e3) / 1e12, 2) if v["ms"] > 0 else None}
-                                 for k, v in fam.items()}}
+                                 for k, v in fam.items()},
+                    "hbm_families": {k: {"ms": round(v["ms"], 3), "n": v["n"],
+                                         "gbs": round(v["bytes"] / (v["ms"] / 1e3) / 1e9, 1) if v["ms"] > 0 else None,
+                                         "frac_of_hbm_peak": round(v["bytes"] / (v["ms"] / 1e3) / 1e9 / pk["hbm_gbs"], 3) if v["ms"] > 0 else None}
+                                     for k, v in membound.items()}}
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:

@@ -33,6 +33,40 @@ struct ColRedArgs {
   int tpr;             // threads per row (power of two <= 256)
 };
 
+// VEC-wide (1 / 4 / 8 elements; 8 = 16-byte bf16 accesses) loads and stores with conversion to float
+template <int VEC, typename T>
+__device__ __forceinline__ void ldv(const T* p, float* v) {
+  if constexpr (VEC == 8) {
+    f8 t = ld8(p);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = t.v[j];
+  } else if constexpr (VEC == 4) {
+    f4 t = ld4(p);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) v[j] = t.v[j];
+  } else {
+    v[0] = ld1(p);
+  }
+}
+__device__ __forceinline__ void st8(float* p, const float* v) {
+  *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+  *reinterpret_cast<float4*>(p + 4) = make_float4(v[4], v[5], v[6], v[7]);
+}
+__device__ __forceinline__ void st8(__nv_bfloat16* p, const float* v) {
+  __nv_bfloat162 a = __floats2bfloat162_rn(v[0], v[1]), b = __floats2bfloat162_rn(v[2], v[3]);
+  __nv_bfloat162 c = __floats2bfloat162_rn(v[4], v[5]), d = __floats2bfloat162_rn(v[6], v[7]);
+  uint4 t;
+  t.x = *reinterpret_cast<uint32_t*>(&a); t.y = *reinterpret_cast<uint32_t*>(&b);
+  t.z = *reinterpret_cast<uint32_t*>(&c); t.w = *reinterpret_cast<uint32_t*>(&d);
+  *reinterpret_cast<uint4*>(p) = t;
+}
+template <int VEC, typename T>
+__device__ __forceinline__ void stv(T* p, const float* v) {
+  if constexpr (VEC == 8) st8(p, v);
+  else if constexpr (VEC == 4) st4(p, f4{{v[0], v[1], v[2], v[3]}});
+  else st1(p, v[0]);
+}
+
 template <typename T, int VEC, int MODE>
 __global__ void __launch_bounds__(256) colreduce_kernel(const ColRedArgs A) {
   __shared__ float red[256 * VEC * 2];
@@ -63,41 +97,52 @@ __global__ void __launch_bounds__(256) colreduce_kernel(const ColRedArgs A) {
           is[j] = A.invstd[g * A.C + c + j];
         }
       }
-      for (long long r = r0 + rl; r < r1; r += lanes) {
-        const long long off = ((long long)g * A.R + r) * A.C + c;
-        float va[VEC], vb[VEC], vc[VEC];
-        if (VEC == 4) {
-          f4 t = ld4(pa + off);
+      const long long gbase = (long long)g * A.R;
+      // U rows per trip: U (x3 in MODE 1) independent 16-byte loads in flight per thread
+      constexpr int U = (MODE == 1) ? 2 : 4;
+      long long r = r0 + rl;
+      for (; r + (long long)(U - 1) * lanes < r1; r += (long long)U * lanes) {
+        float va[U][VEC], vb[U][VEC], vc[U][VEC];
 #pragma unroll
-          for (int j = 0; j < VEC; ++j) va[j] = t.v[j];
+        for (int u = 0; u < U; ++u) {
+          const long long off = (gbase + r + (long long)u * lanes) * A.C + c;
+          ldv<VEC>(pa + off, va[u]);
           if (MODE == 1) {
-            f4 u = ld4(pc + off);
-#pragma unroll
-            for (int j = 0; j < VEC; ++j) vc[j] = u.v[j];
-            if (A.relu) {
-              f4 w = ld4(pb + off);
-#pragma unroll
-              for (int j = 0; j < VEC; ++j) vb[j] = w.v[j];
-            }
-          }
-        } else {
-          va[0] = ld1(pa + off);
-          if (MODE == 1) {
-            vc[0] = ld1(pc + off);
-            if (A.relu) vb[0] = ld1(pb + off);
+            ldv<VEC>(pc + off, vc[u]);
+            if (A.relu) ldv<VEC>(pb + off, vb[u]);
           }
         }
 #pragma unroll
+        for (int u = 0; u < U; ++u)
+#pragma unroll
+          for (int j = 0; j < VEC; ++j) {
+            if (MODE == 1) {
+              const float dz = (A.relu && !(vb[u][j] > 0.f)) ? 0.f : va[u][j];
+              s[j] += dz;
+              q[j] = fmaf(dz, (vc[u][j] - mu[j]) * is[j], q[j]);
+            } else {
+              s[j] += va[u][j];
+              if (MODE == 0) q[j] = fmaf(va[u][j], va[u][j], q[j]);
+            }
+          }
+      }
+      for (; r < r1; r += lanes) {
+        const long long off = (gbase + r) * A.C + c;
+        float va[VEC], vb[VEC], vc[VEC];
+        ldv<VEC>(pa + off, va);
+        if (MODE == 1) {
+          ldv<VEC>(pc + off, vc);
+          if (A.relu) ldv<VEC>(pb + off, vb);
+        }
+#pragma unroll
         for (int j = 0; j < VEC; ++j) {
-          if (MODE == 0) {
-            s[j] += va[j];
-            q[j] = fmaf(va[j], va[j], q[j]);
-          } else if (MODE == 1) {
+          if (MODE == 1) {
             const float dz = (A.relu && !(vb[j] > 0.f)) ? 0.f : va[j];
             s[j] += dz;
             q[j] = fmaf(dz, (vc[j] - mu[j]) * is[j], q[j]);
           } else {
             s[j] += va[j];
+            if (MODE == 0) q[j] = fmaf(va[j], va[j], q[j]);
           }
         }
       }
@@ -108,15 +153,16 @@ __global__ void __launch_bounds__(256) colreduce_kernel(const ColRedArgs A) {
       red[(tid * VEC + j) * 2 + 1] = q[j];
     }
     __syncthreads();
-    if (rl == 0 && active) {
-#pragma unroll
-      for (int j = 0; j < VEC; ++j) {
+    // column sums over the row lanes: thread t < tpr*VEC owns column (t / VEC, t % VEC)
+    for (int t = tid; t < tpr * VEC; t += 256) {
+      const int ccl = t / VEC, j = t - ccl * VEC;
+      if (cv0 + ccl < CVn) {
         double ds = 0.0, dq = 0.0;
         for (int l = 0; l < lanes; ++l) {
-          ds += (double)red[((l * tpr + cl) * VEC + j) * 2];
-          dq += (double)red[((l * tpr + cl) * VEC + j) * 2 + 1];
+          ds += (double)red[((l * tpr + ccl) * VEC + j) * 2];
+          dq += (double)red[((l * tpr + ccl) * VEC + j) * 2 + 1];
         }
-        const int c = cv * VEC + j;
+        const int c = (cv0 + ccl) * VEC + j;
         if (MODE == 2) {
           atomicAdd(A.outf + c, (float)ds);
         } else {
@@ -129,27 +175,29 @@ __global__ void __launch_bounds__(256) colreduce_kernel(const ColRedArgs A) {
   }
 }
 
+template <typename T, int MODE>
+static void launch_colreduce_t(const ColRedArgs& A, int VEC, dim3 grid, cudaStream_t st) {
+  if (VEC == 8) colreduce_kernel<T, 8, MODE><<<grid, 256, 0, st>>>(A);
+  else if (VEC == 4) colreduce_kernel<T, 4, MODE><<<grid, 256, 0, st>>>(A);
+  else colreduce_kernel<T, 1, MODE><<<grid, 256, 0, st>>>(A);
+}
+
 template <int MODE>
-static int launch_colreduce(ColRedArgs A, int dtype, bool vec_ok, cudaStream_t st, const char* what) {
+static int launch_colreduce(ColRedArgs A, int dtype, int VEC, cudaStream_t st, const char* what) {
   if (A.R == 0 || A.G == 0) return STFB_OK;
-  const int VEC = vec_ok ? 4 : 1;
   const int CVn = A.C / VEC;
   int tpr = 1;
   while (tpr * 2 <= CVn && tpr * 2 <= 256) tpr *= 2;
   A.tpr = tpr;
   const int lanes = 256 / tpr;
-  long long rpb = (long long)lanes * 32;
-  const long long maxblocks = 16LL * num_sms();
-  while (((A.R + rpb - 1) / rpb) * A.G > maxblocks && rpb < (long long)lanes * 128) rpb *= 2;
+  // >= 64 rows per thread when the tensor is large, while still covering the machine ~4x
+  long long rpb = (long long)lanes * 16;
+  const long long target_blocks = 6LL * num_sms();
+  while (rpb < (long long)lanes * 128 && ((A.R + 2 * rpb - 1) / (2 * rpb)) * A.G >= target_blocks) rpb *= 2;
   A.rows_per_block = rpb;
   dim3 grid((unsigned)((A.R + rpb - 1) / rpb), (unsigned)A.G);
-  if (dtype == STFB_F32) {
-    if (vec_ok) colreduce_kernel<float, 4, MODE><<<grid, 256, 0, st>>>(A);
-    else colreduce_kernel<float, 1, MODE><<<grid, 256, 0, st>>>(A);
-  } else {
-    if (vec_ok) colreduce_kernel<__nv_bfloat16, 4, MODE><<<grid, 256, 0, st>>>(A);
-    else colreduce_kernel<__nv_bfloat16, 1, MODE><<<grid, 256, 0, st>>>(A);
-  }
+  if (dtype == STFB_F32) launch_colreduce_t<float, MODE>(A, VEC, grid, st);
+  else launch_colreduce_t<__nv_bfloat16, MODE>(A, VEC, grid, st);
   return post_launch(what);
 }
 
@@ -202,28 +250,23 @@ __global__ void bn_apply_kernel(const T* __restrict__ x, const float* __restrict
     const int c = (int)(i - row * CVn) * VEC;
     const int g = (int)(row / R);
     const long long off = row * C + c;
-    if (VEC == 4) {
-      f4 v = ld4(x + off);
-      const float4 sc = *reinterpret_cast<const float4*>(scale + g * C + c);
-      const float4 sh = *reinterpret_cast<const float4*>(shift + g * C + c);
-      v.v[0] = fmaf(v.v[0], sc.x, sh.x); v.v[1] = fmaf(v.v[1], sc.y, sh.y);
-      v.v[2] = fmaf(v.v[2], sc.z, sh.z); v.v[3] = fmaf(v.v[3], sc.w, sh.w);
-      if (res) {
-        f4 r = ld4(res + off);
+    float v[VEC], sc[VEC], sh[VEC];
+    ldv<VEC>(x + off, v);
+    ldv<VEC>(scale + g * C + c, sc);
+    ldv<VEC>(shift + g * C + c, sh);
 #pragma unroll
-        for (int j = 0; j < 4; ++j) v.v[j] += r.v[j];
-      }
-      if (relu) {
+    for (int j = 0; j < VEC; ++j) v[j] = fmaf(v[j], sc[j], sh[j]);
+    if (res) {
+      float r[VEC];
+      ldv<VEC>(res + off, r);
 #pragma unroll
-        for (int j = 0; j < 4; ++j) v.v[j] = fmaxf(v.v[j], 0.f);
-      }
-      st4(y + off, v);
-    } else {
-      float v = fmaf(ld1(x + off), scale[g * C + c], shift[g * C + c]);
-      if (res) v += ld1(res + off);
-      if (relu) v = fmaxf(v, 0.f);
-      st1(y + off, v);
+      for (int j = 0; j < VEC; ++j) v[j] += r[j];
     }
+    if (relu) {
+#pragma unroll
+      for (int j = 0; j < VEC; ++j) v[j] = fmaxf(v[j], 0.f);
+    }
+    stv<VEC>(y + off, v);
   }
 }
 
@@ -258,22 +301,10 @@ __global__ void bn_bwd_apply_kernel(const T* __restrict__ dy, const T* __restric
     const int c = (int)(i - row * CVn) * VEC;
     const int g = (int)(row / R);
     const long long off = row * C + c;
-    float d[VEC], xv[VEC], yv[VEC];
-    if (VEC == 4) {
-      f4 a = ld4(dy + off), b = ld4(x + off);
-#pragma unroll
-      for (int j = 0; j < 4; ++j) { d[j] = a.v[j]; xv[j] = b.v[j]; }
-      if (relu) {
-        f4 m = ld4(y + off);
-#pragma unroll
-        for (int j = 0; j < 4; ++j) yv[j] = m.v[j];
-      }
-    } else {
-      d[0] = ld1(dy + off);
-      xv[0] = ld1(x + off);
-      if (relu) yv[0] = ld1(y + off);
-    }
-    float o[VEC];
+    float d[VEC], xv[VEC], yv[VEC], o[VEC];
+    ldv<VEC>(dy + off, d);
+    ldv<VEC>(x + off, xv);
+    if (relu) ldv<VEC>(y + off, yv);
 #pragma unroll
     for (int j = 0; j < VEC; ++j) {
       const int gc = g * C + c + j;
@@ -283,19 +314,15 @@ __global__ void bn_bwd_apply_kernel(const T* __restrict__ dy, const T* __restric
       const float* k = coef + (long long)gc * 3;
       o[j] = k[0] * (dz - k[1] - xh * k[2]);
     }
-    if (VEC == 4) {
-      st4(dx + off, f4{{o[0], o[1], o[2], o[3]}});
-      if (dres) {
-        if (accum_dres) {
-          f4 old = ld4(dres + off);
+    stv<VEC>(dx + off, o);
+    if (dres) {
+      if (accum_dres) {
+        float old[VEC];
+        ldv<VEC>(dres + off, old);
 #pragma unroll
-          for (int j = 0; j < 4; ++j) d[j] += old.v[j];
-        }
-        st4(dres + off, f4{{d[0], d[1], d[2], d[3]}});
+        for (int j = 0; j < VEC; ++j) d[j] += old[j];
       }
-    } else {
-      st1(dx + off, o[0]);
-      if (dres) st1(dres + off, accum_dres ? d[0] + ld1(dres + off) : d[0]);
+      stv<VEC>(dres + off, d);
     }
   }
 }
@@ -728,6 +755,20 @@ using namespace stfb;
     else { using T = __nv_bfloat16; __VA_ARGS__; }               \
   } while (0)
 
+// widest vector the channel count / alignment allows: 8 (bf16, 16 B) > 4 > 1
+static int pick_vec(int C, int dtype, std::initializer_list<const void*> ptrs) {
+  auto ok = [&](int v) {
+    if (C % v != 0) return false;
+    const int b = v * (dtype == STFB_BF16 ? 2 : 4);
+    for (const void* p : ptrs)
+      if (p && !aligned_to(p, b > 16 ? 16 : b)) return false;
+    return true;
+  };
+  if (dtype == STFB_BF16 && ok(8)) return 8;
+  if (ok(4)) return 4;
+  return 1;
+}
+
 static bool vec4_ok(int C, int dtype, std::initializer_list<const void*> ptrs) {
   if (C % 4 != 0) return false;
   const int b = dtype == STFB_BF16 ? 8 : 16;
@@ -743,7 +784,7 @@ extern "C" int stfb_bn_stats(const void* x, double* sums, int G, long long R, in
   cudaMemsetAsync(sums, 0, sizeof(double) * 2 * G * C, s);
   ColRedArgs A{};
   A.a = x; A.out = sums; A.G = G; A.R = R; A.C = C;
-  return launch_colreduce<0>(A, dtype, vec4_ok(C, dtype, {x}), s, "bn_stats");
+  return launch_colreduce<0>(A, dtype, pick_vec(C, dtype, {x}), s, "bn_stats");
 }
 
 extern "C" int stfb_bn_finalize_train(const double* sums, const float* gamma, const float* beta, float* running_mean,
@@ -771,10 +812,12 @@ extern "C" int stfb_bn_apply(const void* x, const float* scale, const float* shi
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   const long long rows = (long long)G * R;
   if (rows == 0) return STFB_OK;
-  const bool v = vec4_ok(C, dtype, {x, residual, y}) && aligned_to(scale, 16) && aligned_to(shift, 16);
-  const long long tv = rows * (C / (v ? 4 : 1));
+  int v = pick_vec(C, dtype, {x, residual, y});
+  if (v > 1 && !(aligned_to(scale, 16) && aligned_to(shift, 16))) v = 1;
+  const long long tv = rows * (C / v);
   DISPATCH_T(dtype, {
-    if (v) bn_apply_kernel<T, 4><<<grid_for(tv), 256, 0, s>>>((const T*)x, scale, shift, (const T*)residual, (T*)y, R, C, tv, relu);
+    if (v == 8) bn_apply_kernel<T, 8><<<grid_for(tv), 256, 0, s>>>((const T*)x, scale, shift, (const T*)residual, (T*)y, R, C, tv, relu);
+    else if (v == 4) bn_apply_kernel<T, 4><<<grid_for(tv), 256, 0, s>>>((const T*)x, scale, shift, (const T*)residual, (T*)y, R, C, tv, relu);
     else bn_apply_kernel<T, 1><<<grid_for(tv), 256, 0, s>>>((const T*)x, scale, shift, (const T*)residual, (T*)y, R, C, tv, relu);
   });
   return post_launch("bn_apply");
@@ -789,7 +832,7 @@ extern "C" int stfb_bn_bwd_reduce(const void* dy, const void* y, const void* x, 
   cudaMemsetAsync(red, 0, sizeof(double) * 2 * G * C, s);
   ColRedArgs A{};
   A.a = dy; A.b = y; A.c = x; A.mean = mean; A.invstd = invstd; A.out = red; A.G = G; A.R = R; A.C = C; A.relu = relu;
-  return launch_colreduce<1>(A, dtype, vec4_ok(C, dtype, {dy, y, x}), s, "bn_bwd_reduce");
+  return launch_colreduce<1>(A, dtype, pick_vec(C, dtype, {dy, y, x}), s, "bn_bwd_reduce");
 }
 
 extern "C" int stfb_bn_bwd_finalize(const double* red, const float* gamma, const float* invstd, float* dgamma, float* dbeta,
@@ -809,10 +852,11 @@ extern "C" int stfb_bn_bwd_apply(const void* dy, const void* y, const void* x, c
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   const long long rows = (long long)G * R;
   if (rows == 0) return STFB_OK;
-  const bool v = vec4_ok(C, dtype, {dy, y, x, dx, dres});
-  const long long tv = rows * (C / (v ? 4 : 1));
+  const int v = pick_vec(C, dtype, {dy, y, x, dx, dres});
+  const long long tv = rows * (C / v);
   DISPATCH_T(dtype, {
-    if (v) bn_bwd_apply_kernel<T, 4><<<grid_for(tv), 256, 0, s>>>((const T*)dy, (const T*)y, (const T*)x, mean, invstd, coef, (T*)dx, (T*)dres, R, C, tv, relu, accum_dres);
+    if (v == 8) bn_bwd_apply_kernel<T, 8><<<grid_for(tv), 256, 0, s>>>((const T*)dy, (const T*)y, (const T*)x, mean, invstd, coef, (T*)dx, (T*)dres, R, C, tv, relu, accum_dres);
+    else if (v == 4) bn_bwd_apply_kernel<T, 4><<<grid_for(tv), 256, 0, s>>>((const T*)dy, (const T*)y, (const T*)x, mean, invstd, coef, (T*)dx, (T*)dres, R, C, tv, relu, accum_dres);
     else bn_bwd_apply_kernel<T, 1><<<grid_for(tv), 256, 0, s>>>((const T*)dy, (const T*)y, (const T*)x, mean, invstd, coef, (T*)dx, (T*)dres, R, C, tv, relu, accum_dres);
   });
   return post_launch("bn_bwd_apply");
@@ -823,7 +867,7 @@ extern "C" int stfb_colsum(const void* x, float* out, long long R, int C, int dt
   STFB_DEVICE_OR_RETURN();
   ColRedArgs A{};
   A.a = x; A.outf = out; A.G = 1; A.R = R; A.C = C;
-  return launch_colreduce<2>(A, dtype, vec4_ok(C, dtype, {x}), reinterpret_cast<cudaStream_t>(stream), "colsum");
+  return launch_colreduce<2>(A, dtype, pick_vec(C, dtype, {x}), reinterpret_cast<cudaStream_t>(stream), "colsum");
 }
 
 extern "C" int stfb_maxpool_fwd(const void* x, void* y, int N, int H, int W, int C, int Ho, int Wo, int k, int stride, int pad,

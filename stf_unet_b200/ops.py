@@ -64,6 +64,28 @@ class KernelProfiler:
 _prof = None
 
 
+class _timed:
+    """with _timed(family, bytes): ...  -- records a CUDA-event pair when a profiler is installed (no-op otherwise)."""
+    __slots__ = ("fam", "nbytes", "tag", "e0")
+
+    def __init__(self, fam, nbytes, tag=""):
+        self.fam, self.nbytes, self.tag, self.e0 = fam, nbytes, tag, None
+
+    def __enter__(self):
+        if _prof is not None:
+            self.e0 = _prof.begin()
+        return self
+
+    def __exit__(self, *a):
+        if self.e0 is not None:
+            _prof.end(self.e0, self.fam, 0.0, self.nbytes, self.tag)
+        return False
+
+
+def _nb(*ts):
+    return sum(t.numel() * t.element_size() for t in ts if t is not None)
+
+
 def set_profiler(p):
     global _prof
     _prof = p
@@ -168,8 +190,9 @@ def pack_weight(w, k_is_dim1, dtype, n_major=False, flip=False, kpad=None):
         wp = (torch.zeros if kpad else torch.empty)((Nc, ld), dtype=dtype, device=w.device)
     else:
         wp = torch.empty((kh * kw * Kc, Nc), dtype=dtype, device=w.device)
-    check(_lib.load().stfb_pack_weight_ex(_p(w), _p(wp), D0, D1, kh, kw, int(k_is_dim1), int(n_major), int(flip), ld,
-                                          dt_code(dtype), _stream()), "pack_weight")
+    with _timed("pack_weight", _nb(w, wp)):
+        check(_lib.load().stfb_pack_weight_ex(_p(w), _p(wp), D0, D1, kh, kw, int(k_is_dim1), int(n_major), int(flip), ld,
+                                              dt_code(dtype), _stream()), "pack_weight")
     return wp
 
 
@@ -178,7 +201,9 @@ def im2col_small(x, k, stride, pad, kpad):
     N, H, W, Cin = x.shape
     Ho, Wo = conv_out_hw(H, W, k, stride, pad)
     out = torch.empty((N, Ho, Wo, kpad), dtype=torch.bfloat16, device=x.device)
-    check(_lib.load().stfb_im2col_small(_p(x), _p(out), N, H, W, Cin, Ho, Wo, k, stride, pad, kpad, _stream()), "im2col_small")
+    with _timed("im2col_small", _nb(x, out)):
+        check(_lib.load().stfb_im2col_small(_p(x), _p(out), N, H, W, Cin, Ho, Wo, k, stride, pad, kpad, _stream()),
+              "im2col_small")
     return out
 
 
@@ -200,7 +225,8 @@ def tcgen05_ok(x, Cout, k, stride, pad, mode=CONV_FWD, x2=None, out_hw=None, y_d
 
 def bn_stats(x, G, R, C):
     sums = torch.empty((2, G, C), dtype=torch.float64, device=x.device)
-    check(_lib.load().stfb_bn_stats(_p(x), _p(sums), G, R, C, dt_code(x.dtype), _stream()), "bn_stats")
+    with _timed("bn_stats", _nb(x), f"C{C}"):
+        check(_lib.load().stfb_bn_stats(_p(x), _p(sums), G, R, C, dt_code(x.dtype), _stream()), "bn_stats")
     return sums
 
 
@@ -222,8 +248,9 @@ def bn_fold_eval(gamma, beta, running_mean, running_var, eps=1e-5):
 
 def bn_apply(x, scale, shift, G, R, C, relu, residual=None, out=None):
     y = out if out is not None else torch.empty_like(x)
-    check(_lib.load().stfb_bn_apply(_p(x), _p(scale), _p(shift), _p(residual), _p(y), G, R, C, int(bool(relu)),
-                                    dt_code(x.dtype), _stream()), "bn_apply")
+    with _timed("bn_apply", _nb(x, residual, y), f"C{C}"):
+        check(_lib.load().stfb_bn_apply(_p(x), _p(scale), _p(shift), _p(residual), _p(y), G, R, C, int(bool(relu)),
+                                        dt_code(x.dtype), _stream()), "bn_apply")
     return y
 
 
@@ -233,20 +260,24 @@ def bn_bwd(dy, y, x, mean, invstd, gamma, dgamma, dbeta, G, R, C, relu, want_dre
     lib = _lib.load()
     s = _stream()
     red = torch.empty((2, G, C), dtype=torch.float64, device=x.device)
-    check(lib.stfb_bn_bwd_reduce(_p(dy), _p(y) if relu else None, _p(x), _p(mean), _p(invstd), _p(red), G, R, C,
-                                 int(bool(relu)), dt_code(x.dtype), s), "bn_bwd_reduce")
+    with _timed("bn_bwd_reduce", _nb(dy, x, y if relu else None), f"C{C}"):
+        check(lib.stfb_bn_bwd_reduce(_p(dy), _p(y) if relu else None, _p(x), _p(mean), _p(invstd), _p(red), G, R, C,
+                                     int(bool(relu)), dt_code(x.dtype), s), "bn_bwd_reduce")
     coef = torch.empty((G, C, 3), dtype=torch.float32, device=x.device)
     check(lib.stfb_bn_bwd_finalize(_p(red), _p(gamma), _p(invstd), _p(dgamma), _p(dbeta), _p(coef), G, R, C, s),
           "bn_bwd_finalize")
     dx = torch.empty_like(x)
     dres = dres_acc if dres_acc is not None else (torch.empty_like(x) if want_dres else None)
-    check(lib.stfb_bn_bwd_apply(_p(dy), _p(y) if relu else None, _p(x), _p(mean), _p(invstd), _p(coef), _p(dx), _p(dres),
-                                int(dres_acc is not None), G, R, C, int(bool(relu)), dt_code(x.dtype), s), "bn_bwd_apply")
+    with _timed("bn_bwd_apply", _nb(dy, x, y if relu else None, dx, dres, dres_acc), f"C{C}"):
+        check(lib.stfb_bn_bwd_apply(_p(dy), _p(y) if relu else None, _p(x), _p(mean), _p(invstd), _p(coef), _p(dx),
+                                    _p(dres), int(dres_acc is not None), G, R, C, int(bool(relu)), dt_code(x.dtype), s),
+              "bn_bwd_apply")
     return dx, dres
 
 
 def colsum(x, out, R, C):
-    check(_lib.load().stfb_colsum(_p(x), _p(out), R, C, dt_code(x.dtype), _stream()), "colsum")
+    with _timed("colsum", R * C * x.element_size(), f"C{C}"):
+        check(_lib.load().stfb_colsum(_p(x), _p(out), R, C, dt_code(x.dtype), _stream()), "colsum")
 
 
 def maxpool_fwd(x, k, stride, pad):
@@ -264,8 +295,9 @@ def maxpool_fwd_idx(x, k, stride, pad):
     Ho, Wo = (H + 2 * pad - k) // stride + 1, (W + 2 * pad - k) // stride + 1
     y = torch.empty((N, Ho, Wo, C_), dtype=x.dtype, device=x.device)
     idx = torch.empty((N, Ho, Wo, C_), dtype=torch.uint8, device=x.device)
-    check(_lib.load().stfb_maxpool_fwd_idx(_p(x), _p(y), _p(idx), N, H, W, C_, Ho, Wo, k, stride, pad, dt_code(x.dtype),
-                                           _stream()), "maxpool_fwd_idx")
+    with _timed("maxpool_fwd", _nb(x, y, idx)):
+        check(_lib.load().stfb_maxpool_fwd_idx(_p(x), _p(y), _p(idx), N, H, W, C_, Ho, Wo, k, stride, pad,
+                                               dt_code(x.dtype), _stream()), "maxpool_fwd_idx")
     return y, idx
 
 
@@ -273,8 +305,9 @@ def maxpool_bwd_idx(idx, dy, in_shape, k, stride, pad):
     N, H, W, C_ = in_shape
     _, Ho, Wo, _ = dy.shape
     dx = torch.empty(in_shape, dtype=dy.dtype, device=dy.device)
-    check(_lib.load().stfb_maxpool_bwd_idx(_p(idx), _p(dy), _p(dx), N, H, W, C_, Ho, Wo, k, stride, pad, dt_code(dy.dtype),
-                                           _stream()), "maxpool_bwd_idx")
+    with _timed("maxpool_bwd", _nb(idx, dy, dx)):
+        check(_lib.load().stfb_maxpool_bwd_idx(_p(idx), _p(dy), _p(dx), N, H, W, C_, Ho, Wo, k, stride, pad,
+                                               dt_code(dy.dtype), _stream()), "maxpool_bwd_idx")
     return dx
 
 
@@ -302,11 +335,21 @@ def bilinear_bwd(dy, H, W):
 
 
 def lstm_cell_fwd(gates, c_prev, acts, c_out, h_out, R, C_):
+    with _timed("lstm_cell_fwd", R * C_ * (16 + (4 if c_prev is not None else 0) + 4 + h_out.element_size() * (5 if acts is not None else 1))):
+        _lstm_cell_fwd(gates, c_prev, acts, c_out, h_out, R, C_)
+
+
+def _lstm_cell_fwd(gates, c_prev, acts, c_out, h_out, R, C_):
     check(_lib.load().stfb_lstm_cell_fwd(_p(gates), _p(c_prev), _p(acts), _p(c_out), _p(h_out), R, C_, dt_code(h_out.dtype),
                                          _stream()), "lstm_cell_fwd")
 
 
 def lstm_cell_bwd(dh, dc, acts, c_prev, c_cur, dgates, R, C_):
+    with _timed("lstm_cell_bwd", R * C_ * (4 + 8 + 4 + (4 if c_prev is not None else 0) + 8 * dgates.element_size())):
+        _lstm_cell_bwd(dh, dc, acts, c_prev, c_cur, dgates, R, C_)
+
+
+def _lstm_cell_bwd(dh, dc, acts, c_prev, c_cur, dgates, R, C_):
     check(_lib.load().stfb_lstm_cell_bwd(_p(dh), _p(dc), _p(acts), _p(c_prev), _p(c_cur), _p(dgates), R, C_,
                                          dt_code(dgates.dtype), _stream()), "lstm_cell_bwd")
 
