@@ -149,7 +149,8 @@ def run_own(args, rank, world, local_rank):
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+        import datetime
+        dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=180))
     torch.manual_seed(0)
     model = S.STFLSTMUNet(1, 2, T_PHASES).to(dev)
     net = parallel.DataParallel(model) if world > 1 else model
@@ -207,12 +208,13 @@ def run_own(args, rank, world, local_rank):
 
     # ---- roofline of the dominant kernel family: per-launch CUDA events over one extra step ----
     roof = None
+    # every rank runs the extra step (it contains the gradient all-reduce); only rank 0 records events
+    prof = ops.KernelProfiler() if rank == 0 else None
+    ops.set_profiler(prof)
+    step(x_dev, t_dev)
+    torch.cuda.synchronize()
+    ops.set_profiler(None)
     if rank == 0:
-        prof = ops.KernelProfiler()
-        ops.set_profiler(prof)
-        step(x_dev, t_dev)
-        torch.cuda.synchronize()
-        ops.set_profiler(None)
         fam = prof.summary()
         if args.profile_detail:
             for ms, n, tf, family, tag in prof.top(40):
@@ -231,7 +233,7 @@ def run_own(args, rank, world, local_rank):
             roof = {"bound": "tensor", "kernel": name, "achieved": round(ach, 2), "peak": pk["tflops"], "unit": "TFLOP/s",
                     "frac": round(ach / pk["tflops"], 4), "traffic": None, "peak_source": pk["src"],
                     "launches": d["n"], "avg_launch_us": round(1e3 * d["ms"] / d["n"], 2),
-                    "share_of_step": round(d["ms"] / sum(v["ms"] for v in fam.values()), 3),
+                    "share_of_step": round(d["ms"] / ms_per_step, 3),
                     "families": {k: {"ms": round(v["ms"], 3), "n": v["n"],
                                      "tflops": round(v["flops"] / (v["ms"] / 1e3) / 1e12, 2) if v["ms"] > 0 else None}
                                  for k, v in fam.items()},
