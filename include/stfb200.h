@@ -107,6 +107,16 @@ int stfb_pack_weight(const float* w, void* wp, int D0, int D1, int kh, int kw, i
 int stfb_pack_weight_ex(const float* w, void* wp, int D0, int D1, int kh, int kw, int k_is_dim1, int n_major, int flip,
                         int ld /* n_major row stride, 0 = dense; the caller zero-fills any padding */, int dtype, void* stream);
 
+/* Batched form: one launch packs every weight of a step.  `jobs_dev` is a DEVICE array (uploaded once per model);
+ * job j covers flat element range [start_j, start_{j+1}) of `total`; fields as in stfb_pack_weight_ex. */
+typedef struct stfb_pack_job {
+  const float* src;
+  void* dst;
+  long long start;
+  int D0, D1, khw, k_is_dim1, n_major, flip, ld, pad_;
+} stfb_pack_job;
+int stfb_pack_weights_batched(const stfb_pack_job* jobs_dev, int njobs, long long total, int dtype, void* stream);
+
 /* Small-channel convolutions (7x7/2 stem with Cin = 1, src/stf_lstm_unet.py:105,177; UNet enc1.0, src/unet.py:20) on
  * the tensor cores: out[N,Ho,Wo,Kpad] (bf16) = im2col of x with K order (ky,kx,ci), zero-padded to Kpad (multiple of 64),
  * after which the conv is a 1x1 GEMM over `out` and its weight gradient a 1x1 wgrad. */

@@ -39,7 +39,8 @@ struct TcArgs {
   int o_scale;           // output pixel = logical pixel * o_scale + phase offset   (2 for stride-2 transposed)
   int nphase_w;          // phase z -> (z / nphase_w, z % nphase_w) output parity
   int TW, TH, TN;        // logical pixel patch of one tile, TN*TH*TW == 128
-  int tiles_w, tiles_h;
+  int tiles_w, tiles_h, tiles_n;
+  int num_tiles;         // phases * tiles_n * tiles_h * tiles_w * (Cout / BN)
   int relu;
   int ntaps[4];
   signed char dh[4][9], dw[4][9], ktap[4][9];
@@ -52,156 +53,204 @@ constexpr int TC_THREADS = 192;
 
 template <int BN, int STAGES>
 constexpr int tc_smem_bytes() {
-  return STAGES * (TC_A_BYTES + BN * TC_BK * 2) + 3 * BN * 4 + 256 + 1024;
+  return STAGES * (TC_A_BYTES + BN * TC_BK * 2) + 256 + 1024;
 }
 
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+struct TileCoord {
+  int ph, ph_h, ph_w, wb, hb, nb, n0, num_kb;
+};
+
+template <int BN>
+__device__ __forceinline__ TileCoord decode_tile(const TcArgs& a, int tile, int n_tiles, int cpt) {
+  // order: N tile fastest (CTAs that run concurrently share the A patch in L2), then pixel tile, then phase
+  TileCoord t;
+  const int nt = tile % n_tiles;
+  int r = tile / n_tiles;
+  t.wb = r % a.tiles_w; r /= a.tiles_w;
+  t.hb = r % a.tiles_h; r /= a.tiles_h;
+  t.nb = r % a.tiles_n;
+  t.ph = r / a.tiles_n;
+  t.ph_h = t.ph / a.nphase_w;
+  t.ph_w = t.ph - t.ph_h * a.nphase_w;
+  t.n0 = nt * BN;
+  t.num_kb = a.ntaps[t.ph] * cpt;
+  return t;
+}
+
+// Persistent: one CTA per SM walks tiles `blockIdx.x, +gridDim.x, ...`.  The TMA ring keeps streaming across tile
+// boundaries and the accumulator is double-buffered in TMEM (2 x BN columns), so the epilogue of tile i overlaps the
+// main loop of tile i+1 and the per-tile prologue (barrier init, TMEM alloc, first TMA round trip) is paid once.
 template <int BN, int STAGES, typename TO>
-__global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(const __grid_constant__ CUtensorMap tmA,
-                                                              const __grid_constant__ CUtensorMap tmA2,
-                                                              const __grid_constant__ CUtensorMap tmB, const TcArgs a) {
+__global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_constant__ CUtensorMap tmA,
+                                                                 const __grid_constant__ CUtensorMap tmA2,
+                                                                 const __grid_constant__ CUtensorMap tmB, const TcArgs a) {
   constexpr int B_BYTES = BN * TC_BK * 2;
   constexpr int STAGE_BYTES = TC_A_BYTES + B_BYTES;
+  constexpr int TMEM_COLS = (2 * BN < 32) ? 32 : 2 * BN;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  float* s_par = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES);              // [3][BN]: bias, scale, shift
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(s_par + 3 * BN);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
   uint64_t* empty_bar = full_bar + STAGES;
-  uint64_t* accum_bar = empty_bar + STAGES;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum_bar + 1);
+  uint64_t* tfull_bar = empty_bar + STAGES;     // [2] accumulator ready  (MMA -> epilogue)
+  uint64_t* tempty_bar = tfull_bar + 2;         // [2] accumulator drained (epilogue -> MMA)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
 
   const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
-  const int n0 = blockIdx.y * BN;
-  int mt = blockIdx.x;
-  const int wb = mt % a.tiles_w; mt /= a.tiles_w;
-  const int hb = mt % a.tiles_h;
-  const int nb = mt / a.tiles_h;
   const int Cin = a.C1 + a.C2;
   const int cpt = Cin / TC_BK;                 // k-blocks per filter tap
-  const int ph = blockIdx.z;
-  const int ph_h = ph / a.nphase_w, ph_w = ph - ph_h * a.nphase_w;
-  const int num_kb = a.ntaps[ph] * cpt;
+  const int n_tiles = a.Cout / BN;
+  const int num_tiles = a.num_tiles;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-    mbar_init(accum_bar, 1);
+    for (int s = 0; s < 2; ++s) { mbar_init(&tfull_bar[s], 1); mbar_init(&tempty_bar[s], 4); }
     fence_barrier_init();
     prefetch_tensormap(&tmA);
     prefetch_tensormap(&tmB);
     if (a.C2 > 0) prefetch_tensormap(&tmA2);
   }
   if (warp == 1) {
-    tmem_alloc(tmem_slot, BN);
+    tmem_alloc(tmem_slot, TMEM_COLS);
     tmem_relinquish();
-  }
-  // per-column epilogue parameters
-  for (int i = threadIdx.x; i < BN; i += TC_THREADS) {
-    const int c = n0 + i;
-    float b = 0.f;
-    if (a.bias) b += a.bias[c];
-    if (a.bias2) b += a.bias2[c];
-    s_par[i] = b;
-    s_par[BN + i] = a.scale ? a.scale[c] : 1.f;
-    s_par[2 * BN + i] = a.shift ? a.shift[c] : 0.f;
   }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_acc = *tmem_slot;
+  const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
     // ================= TMA producer =================
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int kb = 0; kb < num_kb; ++kb) {
-        mbar_wait(&empty_bar[stage], phase ^ 1);
-        const int t = kb / cpt, chunk = kb - t * cpt;
-        const int c = chunk * TC_BK;
-        uint8_t* sa = smem + stage * STAGE_BYTES;
-        uint8_t* sb = sa + TC_A_BYTES;
-        mbar_arrive_expect_tx(&full_bar[stage], STAGE_BYTES);
-        const int w0 = wb * a.TW * a.a_scale + a.dw[ph][t], h0 = hb * a.TH * a.a_scale + a.dh[ph][t], i0 = nb * a.TN;
-        if (c < a.C1) tma_load_4d(sa, &tmA, &full_bar[stage], c, w0, h0, i0);
-        else tma_load_4d(sa, &tmA2, &full_bar[stage], c - a.C1, w0, h0, i0);
-        tma_load_2d(sb, &tmB, &full_bar[stage], (int)a.ktap[ph][t] * Cin + c, n0);
-        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const TileCoord t = decode_tile<BN>(a, tile, n_tiles, cpt);
+        const int wbase = t.wb * a.TW * a.a_scale, hbase = t.hb * a.TH * a.a_scale, i0 = t.nb * a.TN;
+        for (int kb = 0; kb < t.num_kb; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          const int tp = kb / cpt, chunk = kb - tp * cpt;
+          const int c = chunk * TC_BK;
+          uint8_t* sa = smem + stage * STAGE_BYTES;
+          uint8_t* sb = sa + TC_A_BYTES;
+          mbar_arrive_expect_tx(&full_bar[stage], STAGE_BYTES);
+          const int w0 = wbase + a.dw[t.ph][tp], h0 = hbase + a.dh[t.ph][tp];
+          if (c < a.C1) tma_load_4d(sa, &tmA, &full_bar[stage], c, w0, h0, i0);
+          else tma_load_4d(sa, &tmA2, &full_bar[stage], c - a.C1, w0, h0, i0);
+          tma_load_2d(sb, &tmB, &full_bar[stage], (int)a.ktap[t.ph][tp] * Cin + c, t.n0);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
       }
     }
   } else if (warp == 1) {
     // ================= MMA issuer =================
     constexpr uint32_t idesc = make_idesc_bf16(TC_BM, BN);
-    int stage = 0;
-    uint32_t phase = 0;
-    for (int kb = 0; kb < num_kb; ++kb) {
-      mbar_wait(&full_bar[stage], phase);
+    int stage = 0, acc = 0;
+    uint32_t phase = 0, acc_phase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const TileCoord t = decode_tile<BN>(a, tile, n_tiles, cpt);
+      mbar_wait(&tempty_bar[acc], acc_phase ^ 1);       // epilogue has drained this accumulator buffer
       tc_fence_after();
-      if (lane == 0) {
-        const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
-        const uint64_t adesc = make_kmajor_sw128_desc(sa);
-        const uint64_t bdesc = make_kmajor_sw128_desc(sa + TC_A_BYTES);
+      const uint32_t tmem_acc = tmem_base + (uint32_t)(acc * BN);
+      for (int kb = 0; kb < t.num_kb; ++kb) {
+        mbar_wait(&full_bar[stage], phase);
+        tc_fence_after();
+        if (lane == 0) {
+          const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
+          const uint64_t adesc = make_kmajor_sw128_desc(sa);
+          const uint64_t bdesc = make_kmajor_sw128_desc(sa + TC_A_BYTES);
 #pragma unroll
-        for (int k = 0; k < TC_BK / 16; ++k) {
-          // advance 16 bf16 = 32 B along K inside the swizzle row: +2 in the (addr >> 4) field
-          umma_bf16(tmem_acc, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kb | k) != 0);
+          for (int k = 0; k < TC_BK / 16; ++k) {
+            // advance 16 bf16 = 32 B along K inside the swizzle row: +2 in the (addr >> 4) field
+            umma_bf16(tmem_acc, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kb | k) != 0);
+          }
+          umma_commit(&empty_bar[stage]);                    // frees the smem slot when these MMAs have read it
+          if (kb == t.num_kb - 1) umma_commit(&tfull_bar[acc]);   // accumulator complete
         }
-        umma_commit(&empty_bar[stage]);                 // frees the smem slot when these MMAs have read it
-        if (kb == num_kb - 1) umma_commit(accum_bar);   // accumulator complete
+        __syncwarp();
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
+      if (t.num_kb == 0 && lane == 0) mbar_arrive(&tfull_bar[acc]);   // a parity no tap reaches: nothing to wait for
       __syncwarp();
-      if (++stage == STAGES) { stage = 0; phase ^= 1; }
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
   } else {
     // ================= epilogue (warps 2..5; TMEM lane quadrant = warp % 4) =================
     const int q = warp & 3;
     const int m = q * 32 + lane;                       // accumulator row = TMEM lane = pixel in the patch
     const int tw = m % a.TW, th = (m / a.TW) % a.TH, tn = m / (a.TW * a.TH);
-    const int ow = (wb * a.TW + tw) * a.o_scale + ph_w, oh = (hb * a.TH + th) * a.o_scale + ph_h, on = nb * a.TN + tn;
-    const bool valid = ow < a.Wout && oh < a.Hout && on < a.N;
-    const long long row = (((long long)on * a.Hout + oh) * a.Wout + ow) * a.Cout + n0;
-    TO* __restrict__ yp = reinterpret_cast<TO*>(a.y) + row;
-    const TO* rp = a.residual ? reinterpret_cast<const TO*>(a.residual) + row : nullptr;
-    if (num_kb > 0) {
-      mbar_wait(accum_bar, 0);
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const TileCoord t = decode_tile<BN>(a, tile, n_tiles, cpt);
+      const int ow = (t.wb * a.TW + tw) * a.o_scale + t.ph_w, oh = (t.hb * a.TH + th) * a.o_scale + t.ph_h;
+      const int on = t.nb * a.TN + tn;
+      const bool valid = ow < a.Wout && oh < a.Hout && on < a.N;
+      const long long row = (((long long)on * a.Hout + oh) * a.Wout + ow) * a.Cout + t.n0;
+      TO* __restrict__ yp = reinterpret_cast<TO*>(a.y) + row;
+      const TO* rp = a.residual ? reinterpret_cast<const TO*>(a.residual) + row : nullptr;
+      mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
-    }
-    const uint32_t taddr = tmem_acc + ((uint32_t)(q * 32) << 16);
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN);
 #pragma unroll 1
-    for (int c0 = 0; c0 < BN; c0 += 32) {
-      uint32_t r[32];
-      if (num_kb > 0) {
-        tmem_ld_x32(taddr + c0, r);
-        tmem_ld_wait();
-      } else {   // a parity no tap reaches (1x1 stride-2 dgrad): the accumulator is identically zero
+      for (int c0 = 0; c0 < BN; c0 += 32) {
+        uint32_t r[32];
+        if (t.num_kb > 0) {
+          tmem_ld_x32(taddr + c0, r);
+          tmem_ld_wait();
+        } else {
 #pragma unroll
-        for (int j = 0; j < 32; ++j) r[j] = 0u;
-      }
-      if (valid) {
-        float v[32];
+          for (int j = 0; j < 32; ++j) r[j] = 0u;
+        }
+        if (c0 + 32 >= BN) {           // last chunk is in registers: hand the accumulator buffer back to the MMA warp
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+        }
+        if (valid) {
+          float v[32];
+          const int cg = t.n0 + c0;
 #pragma unroll
-        for (int j = 0; j < 32; ++j)
-          v[j] = fmaf(__uint_as_float(r[j]) + s_par[c0 + j], s_par[BN + c0 + j], s_par[2 * BN + c0 + j]);
-        if (rp) {
+          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+          if (a.bias) {
 #pragma unroll
-          for (int j = 0; j < 32; j += 8) {
-            f8 t = ld8(rp + c0 + j);
-#pragma unroll
-            for (int e = 0; e < 8; ++e) v[j + e] += t.v[e];
+            for (int j = 0; j < 32; ++j) v[j] += __ldg(a.bias + cg + j);
           }
-        }
-        if (a.relu) {
+          if (a.bias2) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
-        }
+            for (int j = 0; j < 32; ++j) v[j] += __ldg(a.bias2 + cg + j);
+          }
+          if (a.scale) {
 #pragma unroll
-        for (int j = 0; j < 32; j += 4) st4(yp + c0 + j, f4{{v[j], v[j + 1], v[j + 2], v[j + 3]}});
+            for (int j = 0; j < 32; ++j) v[j] = fmaf(v[j], __ldg(a.scale + cg + j), __ldg(a.shift + cg + j));
+          }
+          if (rp) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 8) {
+              f8 tt = ld8(rp + c0 + j);
+#pragma unroll
+              for (int e = 0; e < 8; ++e) v[j + e] += tt.v[e];
+            }
+          }
+          if (a.relu) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+          }
+#pragma unroll
+          for (int j = 0; j < 32; j += 8) st8(yp + c0 + j, v + j);
+        }
       }
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
   }
   tc_fence_before();
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_acc, BN);
+    tmem_dealloc(tmem_base, TMEM_COLS);
   }
 }
 
@@ -360,15 +409,17 @@ int conv2d_tcgen05(const stfb_conv_params* p, cudaStream_t st) {
       set_error("conv2d(tcgen05): cuTensorMapEncodeTiled failed for the weights"); return STFB_ECUDA;
     }
   }
-  dim3 grid((unsigned)(tiles_n * a.tiles_h * a.tiles_w), (unsigned)(p->Cout / BN), (unsigned)(a.nphase_w * a.nphase_w));
+  a.tiles_n = tiles_n;
+  a.num_tiles = a.nphase_w * a.nphase_w * tiles_n * a.tiles_h * a.tiles_w * (p->Cout / BN);
+  dim3 grid((unsigned)(a.num_tiles < num_sms() ? a.num_tiles : num_sms()));
   const bool f32out = p->y_dtype == STFB_F32;
 #define TC_LAUNCH(BN_, ST_)                                                                                   \
   return f32out ? launch_tc<BN_, ST_, float>(tA, tA2, tB, a, grid, st) : launch_tc<BN_, ST_, __nv_bfloat16>(tA, tA2, tB, a, grid, st)
   switch (BN) {
-    case 256: TC_LAUNCH(256, 4);
-    case 128: TC_LAUNCH(128, 3);
-    case 64: TC_LAUNCH(64, 4);
-    case 32: TC_LAUNCH(32, 4);
+    case 256: TC_LAUNCH(256, 4);   // 4 x 48 KB
+    case 128: TC_LAUNCH(128, 6);   // 6 x 32 KB
+    case 64: TC_LAUNCH(64, 8);     // 8 x 24 KB
+    case 32: TC_LAUNCH(32, 8);     // 8 x 20 KB
   }
 #undef TC_LAUNCH
   set_error("conv2d(tcgen05): no tile for Cout=%d", p->Cout);

@@ -48,18 +48,6 @@ __device__ __forceinline__ void ldv(const T* p, float* v) {
     v[0] = ld1(p);
   }
 }
-__device__ __forceinline__ void st8(float* p, const float* v) {
-  *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
-  *reinterpret_cast<float4*>(p + 4) = make_float4(v[4], v[5], v[6], v[7]);
-}
-__device__ __forceinline__ void st8(__nv_bfloat16* p, const float* v) {
-  __nv_bfloat162 a = __floats2bfloat162_rn(v[0], v[1]), b = __floats2bfloat162_rn(v[2], v[3]);
-  __nv_bfloat162 c = __floats2bfloat162_rn(v[4], v[5]), d = __floats2bfloat162_rn(v[6], v[7]);
-  uint4 t;
-  t.x = *reinterpret_cast<uint32_t*>(&a); t.y = *reinterpret_cast<uint32_t*>(&b);
-  t.z = *reinterpret_cast<uint32_t*>(&c); t.w = *reinterpret_cast<uint32_t*>(&d);
-  *reinterpret_cast<uint4*>(p) = t;
-}
 template <int VEC, typename T>
 __device__ __forceinline__ void stv(T* p, const float* v) {
   if constexpr (VEC == 8) st8(p, v);

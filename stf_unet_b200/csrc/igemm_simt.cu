@@ -458,9 +458,52 @@ __global__ void pack_weight_kernel(const float* __restrict__ w, T* __restrict__ 
   }
 }
 
+// all weight packs of a step in ONE launch: job table in device memory, binary search on the element offset
+template <typename T>
+__global__ void pack_weights_batched_kernel(const stfb_pack_job* __restrict__ jobs, int njobs, long long total) {
+  for (long long gi = (long long)blockIdx.x * blockDim.x + threadIdx.x; gi < total; gi += (long long)gridDim.x * blockDim.x) {
+    int lo = 0, hi = njobs - 1;
+    while (lo < hi) {
+      const int mid = (lo + hi + 1) >> 1;
+      if (jobs[mid].start <= gi) lo = mid; else hi = mid - 1;
+    }
+    const stfb_pack_job jb = jobs[lo];
+    const long long i = gi - jb.start;
+    const int Kc = jb.k_is_dim1 ? jb.D1 : jb.D0, Nc = jb.k_is_dim1 ? jb.D0 : jb.D1;
+    int n, k, tap;
+    if (!jb.n_major) {
+      n = (int)(i % Nc);
+      const long long r = i / Nc;
+      k = (int)(r % Kc);
+      tap = (int)(r / Kc);
+    } else {
+      k = (int)(i % Kc);
+      const long long r = i / Kc;
+      tap = (int)(r % jb.khw);
+      n = (int)(r / jb.khw);
+    }
+    const int d0 = jb.k_is_dim1 ? n : k, d1 = jb.k_is_dim1 ? k : n;
+    const int stap = jb.flip ? (jb.khw - 1 - tap) : tap;
+    const long long di = jb.n_major ? (long long)n * jb.ld + (long long)tap * Kc + k : i;
+    st1(reinterpret_cast<T*>(jb.dst) + di, jb.src[((long long)d0 * jb.D1 + d1) * jb.khw + stap]);
+  }
+}
+
 }  // namespace stfb
 
 using namespace stfb;
+
+extern "C" int stfb_pack_weights_batched(const stfb_pack_job* jobs_dev, int njobs, long long total, int dtype, void* stream) {
+  STFB_REQUIRE(jobs_dev && njobs > 0 && total > 0, "pack_weights_batched: bad arguments");
+  STFB_REQUIRE(dtype == STFB_F32 || dtype == STFB_BF16, "pack_weights_batched: bad dtype");
+  STFB_DEVICE_OR_RETURN();
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  int blocks = ceil_div(total, 256);
+  if (blocks > 16 * num_sms()) blocks = 16 * num_sms();
+  if (dtype == STFB_F32) pack_weights_batched_kernel<float><<<blocks, 256, 0, s>>>(jobs_dev, njobs, total);
+  else pack_weights_batched_kernel<__nv_bfloat16><<<blocks, 256, 0, s>>>(jobs_dev, njobs, total);
+  return post_launch("pack_weights_batched");
+}
 
 namespace stfb {
 int conv2d_tcgen05(const stfb_conv_params* p, cudaStream_t st);

@@ -59,14 +59,16 @@ class Executor:
         self.grads = grads if grads is not None else {}
         self.tape: List = []
         self._packed = {}
+        self._new_pack_keys = []      # packs this forward needed that the module's PackPlan did not hold
 
     # ---------------------------------------------------------------------------------------------
-    def packed(self, name, k_is_dim1, n_major=False, flip=False):
-        key = (name, bool(k_is_dim1), bool(n_major), bool(flip))
+    def packed(self, name, k_is_dim1, n_major=False, flip=False, kpad=None):
+        key = (name, bool(k_is_dim1), bool(n_major), bool(flip), kpad)
         wp = self._packed.get(key)
         if wp is None:
-            wp = ops.pack_weight(self.params[name], k_is_dim1, self.dtype, n_major=n_major, flip=flip)
+            wp = ops.pack_weight(self.params[name], k_is_dim1, self.dtype, n_major=n_major, flip=flip, kpad=kpad)
             self._packed[key] = wp
+            self._new_pack_keys.append(key)
         return wp
 
     _tc_cache = {}
@@ -152,11 +154,7 @@ class Executor:
         Cout, Cin = w.shape[0], w.shape[1]
         kpad = (Cin * k * k + 63) // 64 * 64
         col = ops.im2col_small(x.data, k, stride, pad, kpad)
-        key = (wname, "im2col", kpad)
-        wp = self._packed.get(key)
-        if wp is None:
-            wp = ops.pack_weight(w, True, self.dtype, n_major=True, kpad=kpad)
-            self._packed[key] = wp
+        wp = self.packed(wname, True, n_major=True, kpad=kpad)
         bias = self.params[bname] if bname else None
         y = ops.conv2d(col, wp, Cout, 1, 1, 0, bias=bias, scale=scale, shift=shift, relu=relu, y_dtype=y_dtype,
                        impl=ops.IMPL_TCGEN05)
@@ -375,5 +373,6 @@ class ModelFunction(torch.autograd.Function):
         hook = getattr(module, "_grad_ready_hook", None)
         if hook is not None:
             hook(module._last_flat_grad)
+        module._learn_pack_plan(ex)
         ctx.ex = ctx.out_var = None
         return (None, None) + (None,) * len(ctx.names)

@@ -98,16 +98,37 @@ class B200Module(nn.Module):
             flat, grads = engine.flat_grads(named)
             self._last_flat_grad = flat
             self._trainable_names = [n for n, p in named if p.requires_grad]
-        return engine.Executor(self._state(), self._select_dtype(), self.training, record, grads)
+        ex = engine.Executor(self._state(), self._select_dtype(), self.training, record, grads)
+        # one batched launch re-packs every weight this mode needs (plan learned on the first forward of the mode)
+        plans = self.__dict__.setdefault("_pack_plans", {})
+        plan = plans.get((ex.dtype, self.training, record))
+        if plan is not None and plan.valid_for(ex.params, ex.dtype):
+            ex._packed = plan.run()
+        else:
+            plans.pop((ex.dtype, self.training, record), None)
+        return ex
 
     def _forward_impl(self, ex, x):
         raise NotImplementedError
 
     def _run(self, x, record):
         ex = self._make_executor(record)
+        ex._mode_key = (ex.dtype, self.training, record)
+        ex._owner = self
         head = self._forward_impl(ex, x)
         logits = ops.nhwc_to_nchw(head.data)
+        if not record:
+            self._learn_pack_plan(ex)
         return ex, head, logits
+
+    def _learn_pack_plan(self, ex):
+        """After a forward (and backward, when recording) that had to pack weights one by one: build the batched plan."""
+        if ex._new_pack_keys:
+            plans = self.__dict__.setdefault("_pack_plans", {})
+            old = plans.get(ex._mode_key)
+            keys = (old.keys if old is not None else []) + ex._new_pack_keys
+            plans[ex._mode_key] = ops.PackPlan(ex.params, keys, ex.dtype)
+            ex._new_pack_keys = []
 
     def _call(self, x):
         if not x.is_cuda:

@@ -196,6 +196,59 @@ def pack_weight(w, k_is_dim1, dtype, n_major=False, flip=False, kpad=None):
     return wp
 
 
+def packed_shape(w, k_is_dim1, n_major, kpad=None):
+    if w.dim() == 2:
+        D0, D1, kh, kw = w.shape[0], w.shape[1], 1, 1
+    else:
+        D0, D1, kh, kw = w.shape
+    Kc, Nc = (D1, D0) if k_is_dim1 else (D0, D1)
+    if n_major:
+        return (Nc, kpad if kpad else kh * kw * Kc)
+    return (kh * kw * Kc, Nc)
+
+
+class PackPlan:
+    """Every weight pack of one forward(+backward) as a single launch.  The job table lives in device memory and is
+    rebuilt only when a parameter's storage moves."""
+
+    def __init__(self, params, keys, dtype):
+        import numpy as np
+        self.keys = list(keys)
+        self.dtype = dtype
+        dev = next(iter(params.values())).device
+        self.buffers = {}
+        job_t = np.dtype([("src", "<u8"), ("dst", "<u8"), ("start", "<i8"), ("D0", "<i4"), ("D1", "<i4"), ("khw", "<i4"),
+                          ("k_is_dim1", "<i4"), ("n_major", "<i4"), ("flip", "<i4"), ("ld", "<i4"), ("pad_", "<i4")])
+        jobs = np.zeros(len(self.keys), dtype=job_t)
+        start = 0
+        for j, key in enumerate(self.keys):
+            name, k_is_dim1, n_major, flip, kpad = key
+            w = params[name]
+            shape = packed_shape(w, k_is_dim1, n_major, kpad)
+            buf = (torch.zeros if kpad else torch.empty)(shape, dtype=dtype, device=dev)
+            self.buffers[key] = buf
+            D0, D1 = w.shape[0], w.shape[1]
+            khw = 1 if w.dim() == 2 else w.shape[2] * w.shape[3]
+            jobs[j] = (w.data_ptr(), buf.data_ptr(), start, D0, D1, khw, int(k_is_dim1), int(n_major), int(flip),
+                       shape[1] if n_major else 0, 0)
+            start += w.numel()
+        self.total = start
+        self.table = torch.from_numpy(jobs.view(np.uint8)).to(dev)
+        self.signature = tuple(params[k[0]].data_ptr() for k in self.keys)
+
+    def valid_for(self, params, dtype):
+        try:
+            return dtype == self.dtype and self.signature == tuple(params[k[0]].data_ptr() for k in self.keys)
+        except KeyError:
+            return False
+
+    def run(self):
+        with _timed("pack_weight", 0):
+            check(_lib.load().stfb_pack_weights_batched(_p(self.table), len(self.keys), self.total, dt_code(self.dtype),
+                                                        _stream()), "pack_weights_batched")
+        return dict(self.buffers)
+
+
 def im2col_small(x, k, stride, pad, kpad):
     """bf16 [N,H,W,Cin] -> [N,Ho,Wo,kpad]: K order (ky,kx,ci), zero padded (small-channel convs on the tensor cores)."""
     N, H, W, Cin = x.shape

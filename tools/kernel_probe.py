@@ -1,0 +1,73 @@
+"""Launch a few representative GEMM-family kernels in isolation (for ncu captures and quick CUDA-event timing).
+
+    python tools/kernel_probe.py [conv|wgrad|bn] [--iters N]
+"""
+import argparse
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from stf_unet_b200 import ops  # noqa: E402
+
+DEV = "cuda"
+CONV_SHAPES = [  # N, H, W, Cin, Cout, k  (encoder shapes at B=16, T=8, 256x256)
+    (128, 64, 64, 64, 64, 3), (128, 32, 32, 128, 128, 3), (128, 16, 16, 256, 256, 3), (128, 8, 8, 512, 512, 3),
+    (16, 64, 64, 64, 256, 1), (128, 64, 64, 64, 256, 1)]
+
+
+def timeit(fn, iters):
+    fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / iters
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("what", nargs="?", default="conv")
+    ap.add_argument("--iters", type=int, default=20)
+    a = ap.parse_args()
+    bf = torch.bfloat16
+    if a.what in ("conv", "all"):
+        for (N, H, W, Cin, Cout, k) in CONV_SHAPES:
+            x = torch.randn(N, H, W, Cin, device=DEV).to(bf)
+            w = (torch.randn(Cout, Cin, k, k, device=DEV) * 0.05)
+            wp = ops.pack_weight(w, True, bf, n_major=True)
+            y = torch.empty(N, H, W, Cout, device=DEV, dtype=bf)
+            ms = timeit(lambda: ops.conv2d(x, wp, Cout, k, 1, (k - 1) // 2, out=y, impl=ops.IMPL_TCGEN05), a.iters)
+            fl = 2.0 * N * H * W * Cin * Cout * k * k
+            print(f"conv   N{N} {H}x{W} {Cin}->{Cout} k{k}: {ms * 1e3:8.1f} us  {fl / ms / 1e9:8.1f} TFLOP/s")
+    if a.what in ("wgrad", "all"):
+        for (N, H, W, Cin, Cout, k) in CONV_SHAPES[:4]:
+            x = torch.randn(N, H, W, Cin, device=DEV).to(bf)
+            dy = torch.randn(N, H, W, Cout, device=DEV).to(bf)
+            dW = torch.zeros(Cout, Cin, k, k, device=DEV)
+            ms = timeit(lambda: ops.conv2d_wgrad(dy, x, dW, k, 1, (k - 1) // 2, 0, Cin, impl=ops.IMPL_TCGEN05), a.iters)
+            fl = 2.0 * N * H * W * Cin * Cout * k * k
+            print(f"wgrad  N{N} {H}x{W} {Cin}->{Cout} k{k}: {ms * 1e3:8.1f} us  {fl / ms / 1e9:8.1f} TFLOP/s")
+    if a.what in ("bn", "all"):
+        for (N, H, W, C) in [(128, 128, 128, 64), (128, 64, 64, 64), (128, 32, 32, 128), (128, 16, 16, 256), (128, 8, 8, 512)]:
+            G, R = 8, (N // 8) * H * W
+            x = torch.randn(N, H, W, C, device=DEV).to(bf)
+            dy = torch.randn_like(x)
+            gamma, beta = torch.ones(C, device=DEV), torch.zeros(C, device=DEV)
+            S = x.numel() * 2
+            ms = timeit(lambda: ops.bn_stats(x, G, R, C), a.iters)
+            st = ops.bn_finalize_train(ops.bn_stats(x, G, R, C), gamma, beta, None, None, None, G, R, C)
+            y = torch.empty_like(x)
+            ms2 = timeit(lambda: ops.bn_apply(x, st[0], st[1], G, R, C, True, x, out=y), a.iters)
+            dg, db = torch.zeros(C, device=DEV), torch.zeros(C, device=DEV)
+            ms3 = timeit(lambda: ops.bn_bwd(dy, y, x, st[2], st[3], gamma, dg, db, G, R, C, True, True), a.iters)
+            print(f"bn     N{N} {H}x{W} C{C}: stats {ms * 1e3:7.1f} us ({S / ms / 1e6:7.1f} GB/s)  apply+res {ms2 * 1e3:7.1f} us "
+                  f"({4 * S / ms2 / 1e6:7.1f} GB/s)  bwd(reduce+fin+apply) {ms3 * 1e3:7.1f} us ({8 * S / ms3 / 1e6:7.1f} GB/s)")
+
+
+if __name__ == "__main__":
+    main()
