@@ -134,7 +134,7 @@ def run_reference(args, rank):
 def workload_config(n):
     return {"workload": f"STF-LSTM-UNet train fwd+CE/Dice+bwd+AdamW, T={T_PHASES} x 1x{HW}x{HW}, batch {BATCH_PER_GPU}/GPU "
                         f"(BASELINE.json configs[2] = global batch 128 on 8 GPUs)",
-            "global_batch": BATCH_PER_GPU * n, "T": T_PHASES, "hw": HW, "parallelism": f"dp{n}",
+            "global_batch": BATCH_PER_GPU * n, "T": T_PHASES, "hw": HW, "parallelism": f"dp{n}", "launch": "CUDA graph (fwd+loss+bwd) + eager all-reduce/AdamW",
             "l2": "per-step working set (activations ~4 GB) far exceeds the 126 MB L2; no flush needed"}
 
 
@@ -159,13 +159,27 @@ def run_own(args, rank, world, local_rank):
     x_pin, t_pin = x_host.pin_memory(), t_host.pin_memory()
     x_dev, t_dev = x_pin.to(dev), t_pin.to(dev)
 
-    def step(x, t):
+    def eager_step(x, t):
         model.train()
         with torch.autocast("cuda", dtype=torch.bfloat16):
             out = net(x)
             loss = S.criterion(out, t)
         opt.zero_grad(set_to_none=True)
         loss.backward()
+        opt.step()
+        return loss
+
+    graphed = None
+    if not args.no_graph:
+        from stf_unet_b200.graph import GraphedStep
+        graphed = GraphedStep(net.module if world > 1 else model, S.criterion, x_dev, t_dev)
+        if world > 1:
+            graphed._hook = net._on_grads
+
+    def step(x, t):
+        if graphed is None:
+            return eager_step(x, t)
+        loss = graphed(x, t)          # fwd + CE/Dice + bwd: one CUDA-graph launch (+ gradient all-reduce for N > 1)
         opt.step()
         return loss
 
@@ -193,6 +207,8 @@ def run_own(args, rank, world, local_rank):
     with ClockSampler(local_rank) as clk:
         total_ms = timed(lambda: step(x_dev, t_dev), args.steps)
     launches = _lib.launch_count() - n0
+    if graphed is not None:
+        launches += graphed.launches_per_replay * args.steps     # replays do not pass through the host-side counter
     ms_per_step = total_ms / args.steps
     value = BATCH_PER_GPU * world / (ms_per_step / 1000.0)
 
@@ -211,7 +227,7 @@ def run_own(args, rank, world, local_rank):
     # every rank runs the extra step (it contains the gradient all-reduce); only rank 0 records events
     prof = ops.KernelProfiler() if rank == 0 else None
     ops.set_profiler(prof)
-    step(x_dev, t_dev)
+    eager_step(x_dev, t_dev)        # per-launch events need the eager path
     torch.cuda.synchronize()
     ops.set_profiler(None)
     if rank == 0:
@@ -273,6 +289,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="own", choices=["own", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="enqueue every kernel from Python instead of replaying a CUDA graph")
     ap.add_argument("--profile-detail", action="store_true", help="print the slowest GEMM-family launches to stderr")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))

@@ -131,11 +131,14 @@ int stfb_unpad_wgrad(float* dW, const float* src, int Cout, int Cin, int kh, int
  * the STF encoder runs with G = T groups because the reference calls each BN once per time step
  * (src/stf_lstm_unet.py:168-186) -- statistics are per group, running stats get G sequential updates.
  * ---------------------------------------------------------------------------------------------- */
-/* sums[g][c] = sum x, sums[G*C + g*C + c] = sum x^2 (fp64, zeroed inside) */
-int stfb_bn_stats(const void* x, double* sums, int G, long long R, int C, int dtype, void* stream);
-/* train: batch stats -> scale/shift/mean/invstd [G][C]; running_mean/var updated G times in place,
- * num_batches_tracked += G.   */
-int stfb_bn_finalize_train(const double* sums, const float* gamma, const float* beta, float* running_mean,
+/* Statistics are reduced in two steps without atomics: every CTA of the reduction writes its partial sums
+ * partial[blk][0][g][c] = sum x, partial[blk][1][g][c] = sum x^2 (fp32), and the finalize kernel adds the nblk slots in
+ * fp64.  nblk = stfb_bn_partial_blocks(G, R) (host-only, deterministic); the caller allocates nblk*2*G*C floats. */
+int stfb_bn_partial_blocks(int G, long long R);
+int stfb_bn_stats(const void* x, float* partial, int nblk, int G, long long R, int C, int dtype, void* stream);
+/* train: batch stats -> scale/shift/mean/invstd [G][C]; running_mean/var updated G times in place (sequentially, one
+ * update per group = per reference BN call), num_batches_tracked += G. */
+int stfb_bn_finalize_train(const float* partial, int nblk, const float* gamma, const float* beta, float* running_mean,
                            float* running_var, long long* num_batches_tracked, float* scale, float* shift,
                            float* mean, float* invstd, int G, long long R, int C, float eps, float momentum,
                            void* stream);
@@ -145,12 +148,12 @@ int stfb_bn_fold_eval(const float* gamma, const float* beta, const float* runnin
 /* y = relu?( x*scale[g][c] + shift[g][c] + residual ) */
 int stfb_bn_apply(const void* x, const float* scale, const float* shift, const void* residual, void* y, int G,
                   long long R, int C, int relu, int dtype, void* stream);
-/* backward, step 1: dz = dy * (y > 0 if relu); red[g][c] = sum dz, red[G*C + g*C + c] = sum dz*xhat (fp64, zeroed inside) */
+/* backward, step 1: dz = dy * (y > 0 if relu); partial[blk][0][g][c] = sum dz, partial[blk][1][g][c] = sum dz*xhat */
 int stfb_bn_bwd_reduce(const void* dy, const void* y, const void* x, const float* mean, const float* invstd,
-                       double* red, int G, long long R, int C, int relu, int dtype, void* stream);
-/* backward, step 2: dgamma[c] += sum_g red2, dbeta[c] += sum_g red1; coef[g][c][3] = {gamma*invstd, red1/R, red2/R} */
-int stfb_bn_bwd_finalize(const double* red, const float* gamma, const float* invstd, float* dgamma, float* dbeta,
-                         float* coef, int G, long long R, int C, void* stream);
+                       float* partial, int nblk, int G, long long R, int C, int relu, int dtype, void* stream);
+/* backward, step 2: dgamma[c] += sum_g sum2, dbeta[c] += sum_g sum1; coef[g][c][3] = {gamma*invstd, sum1/R, sum2/R} */
+int stfb_bn_bwd_finalize(const float* partial, int nblk, const float* gamma, const float* invstd, float* dgamma,
+                         float* dbeta, float* coef, int G, long long R, int C, void* stream);
 /* backward, step 3: dx = coef0 * (dz - coef1 - xhat*coef2); if dres != NULL: dres = dz (+ dres when accum_dres:
  * the residual input of a block already carries the gradient of its other consumers) */
 int stfb_bn_bwd_apply(const void* dy, const void* y, const void* x, const float* mean, const float* invstd,

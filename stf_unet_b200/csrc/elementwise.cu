@@ -23,7 +23,7 @@ struct ColRedArgs {
   const void* c;       //                  MODE 1: x (pre-BN)
   const float* mean;   // [G][C]  (MODE 1)
   const float* invstd; // [G][C]  (MODE 1)
-  double* out;         // [2][G][C]  (MODE 0/1)
+  float* partial;      // [nblk][2][G][C]  (MODE 0/1): per-CTA partial sums, combined in fp64 by the finalize kernels
   float* outf;         // [C]        (MODE 2)
   int G;
   long long R;
@@ -153,9 +153,10 @@ __global__ void __launch_bounds__(256) colreduce_kernel(const ColRedArgs A) {
         const int c = (cv0 + ccl) * VEC + j;
         if (MODE == 2) {
           atomicAdd(A.outf + c, (float)ds);
-        } else {
-          atomicAdd(A.out + (long long)g * A.C + c, ds);
-          atomicAdd(A.out + (long long)(A.G + g) * A.C + c, dq);
+        } else {   // no atomics, no memset: one slot per (CTA, group, channel)
+          float* pp = A.partial + ((long long)blockIdx.x * 2 * A.G + g) * A.C + c;
+          pp[0] = (float)ds;
+          pp[(long long)A.G * A.C] = (float)dq;
         }
       }
     }
@@ -170,53 +171,96 @@ static void launch_colreduce_t(const ColRedArgs& A, int VEC, dim3 grid, cudaStre
   else colreduce_kernel<T, 1, MODE><<<grid, 256, 0, st>>>(A);
 }
 
+// number of CTAs along the row axis (= number of partial-sum slots per (group, channel)); host-only, deterministic
+static int colreduce_blocks(int G, long long R) {
+  long long want = (2LL * num_sms() + G - 1) / G;     // ~2 waves in total
+  long long cap = (R + 31) / 32;                      // at least 32 rows per CTA
+  long long n = want < cap ? want : cap;
+  if (n > 64) n = 64;
+  if (n < 1) n = 1;
+  return (int)n;
+}
+
 template <int MODE>
-static int launch_colreduce(ColRedArgs A, int dtype, int VEC, cudaStream_t st, const char* what) {
+static int launch_colreduce(ColRedArgs A, int dtype, int VEC, cudaStream_t st, const char* what, int nblk = 0) {
   if (A.R == 0 || A.G == 0) return STFB_OK;
   const int CVn = A.C / VEC;
   int tpr = 1;
   while (tpr * 2 <= CVn && tpr * 2 <= 256) tpr *= 2;
   A.tpr = tpr;
-  const int lanes = 256 / tpr;
-  // >= 64 rows per thread when the tensor is large, while still covering the machine ~4x
-  long long rpb = (long long)lanes * 16;
-  const long long target_blocks = 6LL * num_sms();
-  while (rpb < (long long)lanes * 128 && ((A.R + 2 * rpb - 1) / (2 * rpb)) * A.G >= target_blocks) rpb *= 2;
-  A.rows_per_block = rpb;
-  dim3 grid((unsigned)((A.R + rpb - 1) / rpb), (unsigned)A.G);
+  if (MODE == 2) {
+    long long n = (A.R + 255) / 256;
+    const long long cap = 4LL * num_sms();
+    nblk = (int)(n < 1 ? 1 : (n > cap ? cap : n));
+  } else if (nblk <= 0) {
+    nblk = colreduce_blocks(A.G, A.R);
+  }
+  A.rows_per_block = (A.R + nblk - 1) / nblk;
+  dim3 grid((unsigned)nblk, (unsigned)A.G);
   if (dtype == STFB_F32) launch_colreduce_t<float, MODE>(A, VEC, grid, st);
   else launch_colreduce_t<__nv_bfloat16, MODE>(A, VEC, grid, st);
   return post_launch(what);
 }
 
+// fp64 sum over the nblk partial slots of 8 consecutive groups for channel c; lanes stride over the slots
+__device__ __forceinline__ void sum_partials8(const float* __restrict__ partial, int nblk, int G, int C, int g0, int c, int lane,
+                                              double* s, double* q) {
+#pragma unroll
+  for (int j = 0; j < 8; ++j) s[j] = q[j] = 0.0;
+  for (int b = lane; b < nblk; b += 32) {
+    const float* pp = partial + ((long long)b * 2 * G) * C + c;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      if (g0 + j < G) {
+        s[j] += (double)pp[(long long)(g0 + j) * C];
+        q[j] += (double)pp[(long long)(G + g0 + j) * C];
+      }
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { s[j] = warp_sum(s[j]); q[j] = warp_sum(q[j]); }
+}
+
 // =================================================================================================
 // BatchNorm finalize / fold / apply / backward apply
 // =================================================================================================
-__global__ void bn_finalize_train_kernel(const double* __restrict__ sums, const float* __restrict__ gamma,
+// one warp per channel: lanes sum the per-CTA partials (fp64), lane 0 walks the groups in order (the reference updates
+// the running stats once per time step, sequentially)
+__global__ void bn_finalize_train_kernel(const float* __restrict__ partial, int nblk, const float* __restrict__ gamma,
                                          const float* __restrict__ beta, float* running_mean, float* running_var,
                                          long long* nbt, float* scale, float* shift, float* mean, float* invstd, int G,
                                          long long R, int C, float eps, float momentum) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c == 0 && nbt) *nbt += G;
+  const int lane = threadIdx.x % 32;
+  const int c = blockIdx.x * (blockDim.x / 32) + threadIdx.x / 32;
+  if (blockIdx.x == 0 && threadIdx.x == 0 && nbt) *nbt += G;
   if (c >= C) return;
   float rm = running_mean ? running_mean[c] : 0.f, rv = running_var ? running_var[c] : 1.f;
   const double n = (double)R;
-  for (int g = 0; g < G; ++g) {
-    const double m = sums[(long long)g * C + c] / n;
-    double var = sums[(long long)(G + g) * C + c] / n - m * m;
-    if (var < 0.0) var = 0.0;
-    const float is = (float)(1.0 / sqrt(var + (double)eps));
-    const float sc = gamma[c] * is;
-    scale[g * C + c] = sc;
-    shift[g * C + c] = beta[c] - (float)m * sc;
-    mean[g * C + c] = (float)m;
-    invstd[g * C + c] = is;
-    const double unbiased = R > 1 ? var * n / (n - 1.0) : var;
-    rm = (1.f - momentum) * rm + momentum * (float)m;
-    rv = (1.f - momentum) * rv + momentum * (float)unbiased;
+  for (int g0 = 0; g0 < G; g0 += 8) {
+    double s[8], q[8];
+    sum_partials8(partial, nblk, G, C, g0, c, lane, s, q);
+    if (lane == 0) {
+      for (int j = 0; j < 8 && g0 + j < G; ++j) {
+        const int g = g0 + j;
+        const double m = s[j] / n;
+        double var = q[j] / n - m * m;
+        if (var < 0.0) var = 0.0;
+        const float is = (float)(1.0 / sqrt(var + (double)eps));
+        const float sc = gamma[c] * is;
+        scale[g * C + c] = sc;
+        shift[g * C + c] = beta[c] - (float)m * sc;
+        mean[g * C + c] = (float)m;
+        invstd[g * C + c] = is;
+        const double unbiased = R > 1 ? var * n / (n - 1.0) : var;
+        rm = (1.f - momentum) * rm + momentum * (float)m;
+        rv = (1.f - momentum) * rv + momentum * (float)unbiased;
+      }
+    }
   }
-  if (running_mean) running_mean[c] = rm;
-  if (running_var) running_var[c] = rv;
+  if (lane == 0) {
+    if (running_mean) running_mean[c] = rm;
+    if (running_var) running_var[c] = rv;
+  }
 }
 
 __global__ void bn_fold_eval_kernel(const float* __restrict__ gamma, const float* __restrict__ beta,
@@ -258,24 +302,33 @@ __global__ void bn_apply_kernel(const T* __restrict__ x, const float* __restrict
   }
 }
 
-__global__ void bn_bwd_finalize_kernel(const double* __restrict__ red, const float* __restrict__ gamma,
+__global__ void bn_bwd_finalize_kernel(const float* __restrict__ partial, int nblk, const float* __restrict__ gamma,
                                        const float* __restrict__ invstd, float* dgamma, float* dbeta, float* coef, int G,
                                        long long R, int C) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  const int lane = threadIdx.x % 32;
+  const int c = blockIdx.x * (blockDim.x / 32) + threadIdx.x / 32;
   if (c >= C) return;
   double dg = 0.0, db = 0.0;
   const double n = (double)R;
-  for (int g = 0; g < G; ++g) {
-    const double s1 = red[(long long)g * C + c], s2 = red[(long long)(G + g) * C + c];
-    db += s1;
-    dg += s2;
-    float* k = coef + ((long long)g * C + c) * 3;
-    k[0] = gamma[c] * invstd[g * C + c];
-    k[1] = (float)(s1 / n);
-    k[2] = (float)(s2 / n);
+  for (int g0 = 0; g0 < G; g0 += 8) {
+    double s[8], q[8];
+    sum_partials8(partial, nblk, G, C, g0, c, lane, s, q);
+    if (lane == 0) {
+      for (int j = 0; j < 8 && g0 + j < G; ++j) {
+        const int g = g0 + j;
+        db += s[j];
+        dg += q[j];
+        float* k = coef + ((long long)g * C + c) * 3;
+        k[0] = gamma[c] * invstd[g * C + c];
+        k[1] = (float)(s[j] / n);
+        k[2] = (float)(q[j] / n);
+      }
+    }
   }
-  if (dgamma) dgamma[c] += (float)dg;
-  if (dbeta) dbeta[c] += (float)db;
+  if (lane == 0) {
+    if (dgamma) dgamma[c] += (float)dg;
+    if (dbeta) dbeta[c] += (float)db;
+  }
 }
 
 template <typename T, int VEC>
@@ -765,23 +818,29 @@ static bool vec4_ok(int C, int dtype, std::initializer_list<const void*> ptrs) {
   return true;
 }
 
-extern "C" int stfb_bn_stats(const void* x, double* sums, int G, long long R, int C, int dtype, void* stream) {
-  STFB_REQUIRE(x && sums && G > 0 && R >= 0 && C > 0 && DT_OK(dtype), "bn_stats: bad arguments");
-  STFB_DEVICE_OR_RETURN();
-  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
-  cudaMemsetAsync(sums, 0, sizeof(double) * 2 * G * C, s);
-  ColRedArgs A{};
-  A.a = x; A.out = sums; A.G = G; A.R = R; A.C = C;
-  return launch_colreduce<0>(A, dtype, pick_vec(C, dtype, {x}), s, "bn_stats");
+extern "C" int stfb_bn_partial_blocks(int G, long long R) {
+  if (G <= 0 || R <= 0) return 1;
+  return colreduce_blocks(G, R);
 }
 
-extern "C" int stfb_bn_finalize_train(const double* sums, const float* gamma, const float* beta, float* running_mean,
+extern "C" int stfb_bn_stats(const void* x, float* partial, int nblk, int G, long long R, int C, int dtype, void* stream) {
+  STFB_REQUIRE(x && partial && G > 0 && R >= 0 && C > 0 && DT_OK(dtype), "bn_stats: bad arguments");
+  STFB_DEVICE_OR_RETURN();
+  STFB_REQUIRE(nblk == colreduce_blocks(G, R), "bn_stats: nblk must come from stfb_bn_partial_blocks");
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  ColRedArgs A{};
+  A.a = x; A.partial = partial; A.G = G; A.R = R; A.C = C;
+  return launch_colreduce<0>(A, dtype, pick_vec(C, dtype, {x}), s, "bn_stats", nblk);
+}
+
+extern "C" int stfb_bn_finalize_train(const float* partial, int nblk, const float* gamma, const float* beta, float* running_mean,
                                       float* running_var, long long* nbt, float* scale, float* shift, float* mean,
                                       float* invstd, int G, long long R, int C, float eps, float momentum, void* stream) {
-  STFB_REQUIRE(sums && gamma && beta && scale && shift && mean && invstd && G > 0 && R > 0 && C > 0, "bn_finalize_train: bad arguments");
+  STFB_REQUIRE(partial && nblk > 0 && gamma && beta && scale && shift && mean && invstd && G > 0 && R > 0 && C > 0,
+               "bn_finalize_train: bad arguments");
   STFB_DEVICE_OR_RETURN();
-  bn_finalize_train_kernel<<<ceil_div(C, 128), 128, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
-      sums, gamma, beta, running_mean, running_var, nbt, scale, shift, mean, invstd, G, R, C, eps, momentum);
+  bn_finalize_train_kernel<<<ceil_div(C, 8), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      partial, nblk, gamma, beta, running_mean, running_var, nbt, scale, shift, mean, invstd, G, R, C, eps, momentum);
   return post_launch("bn_finalize_train");
 }
 
@@ -812,22 +871,23 @@ extern "C" int stfb_bn_apply(const void* x, const float* scale, const float* shi
 }
 
 extern "C" int stfb_bn_bwd_reduce(const void* dy, const void* y, const void* x, const float* mean, const float* invstd,
-                                  double* red, int G, long long R, int C, int relu, int dtype, void* stream) {
-  STFB_REQUIRE(dy && x && mean && invstd && red && G > 0 && R >= 0 && C > 0 && DT_OK(dtype), "bn_bwd_reduce: bad arguments");
+                                  float* partial, int nblk, int G, long long R, int C, int relu, int dtype, void* stream) {
+  STFB_REQUIRE(dy && x && mean && invstd && partial && G > 0 && R >= 0 && C > 0 && DT_OK(dtype), "bn_bwd_reduce: bad arguments");
   STFB_REQUIRE(!relu || y, "bn_bwd_reduce: relu needs y");
   STFB_DEVICE_OR_RETURN();
+  STFB_REQUIRE(nblk == colreduce_blocks(G, R), "bn_bwd_reduce: nblk must come from stfb_bn_partial_blocks");
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
-  cudaMemsetAsync(red, 0, sizeof(double) * 2 * G * C, s);
   ColRedArgs A{};
-  A.a = dy; A.b = y; A.c = x; A.mean = mean; A.invstd = invstd; A.out = red; A.G = G; A.R = R; A.C = C; A.relu = relu;
-  return launch_colreduce<1>(A, dtype, pick_vec(C, dtype, {dy, y, x}), s, "bn_bwd_reduce");
+  A.a = dy; A.b = y; A.c = x; A.mean = mean; A.invstd = invstd; A.partial = partial; A.G = G; A.R = R; A.C = C; A.relu = relu;
+  return launch_colreduce<1>(A, dtype, pick_vec(C, dtype, {dy, y, x}), s, "bn_bwd_reduce", nblk);
 }
 
-extern "C" int stfb_bn_bwd_finalize(const double* red, const float* gamma, const float* invstd, float* dgamma, float* dbeta,
-                                    float* coef, int G, long long R, int C, void* stream) {
-  STFB_REQUIRE(red && gamma && invstd && coef && G > 0 && R > 0 && C > 0, "bn_bwd_finalize: bad arguments");
+extern "C" int stfb_bn_bwd_finalize(const float* partial, int nblk, const float* gamma, const float* invstd, float* dgamma,
+                                    float* dbeta, float* coef, int G, long long R, int C, void* stream) {
+  STFB_REQUIRE(partial && nblk > 0 && gamma && invstd && coef && G > 0 && R > 0 && C > 0, "bn_bwd_finalize: bad arguments");
   STFB_DEVICE_OR_RETURN();
-  bn_bwd_finalize_kernel<<<ceil_div(C, 128), 128, 0, reinterpret_cast<cudaStream_t>(stream)>>>(red, gamma, invstd, dgamma, dbeta, coef, G, R, C);
+  bn_bwd_finalize_kernel<<<ceil_div(C, 8), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(partial, nblk, gamma, invstd, dgamma,
+                                                                                             dbeta, coef, G, R, C);
   return post_launch("bn_bwd_finalize");
 }
 

@@ -310,9 +310,13 @@ class Executor:
             if self.wants_grad(whh) and T > 1:
                 ops.conv2d_wgrad(dG[1:].reshape((T - 1) * B, h, w, 4 * C), hs[:T - 1].reshape((T - 1) * B, h, w, C),
                                  self.grads[whh], 1, 1, 0)
-            for bn_ in (bih, bhh):
-                if self.wants_grad(bn_):
-                    ops.colsum(dG_all, self.grads[bn_], T * R, 4 * C)
+            # d b_ih == d b_hh == column sums of dG: reduce once, add the (tiny) result into the second bias
+            if self.wants_grad(bih):
+                ops.colsum(dG_all, self.grads[bih], T * R, 4 * C)
+                if self.wants_grad(bhh):
+                    ops.add_(self.grads[bhh], self.grads[bih])
+            elif self.wants_grad(bhh):
+                ops.colsum(dG_all, self.grads[bhh], T * R, 4 * C)
             if seq.needs_grad:
                 tca = self.use_tc(dG_all, C, 1, 1, 0)
                 seq.grad = ops.conv2d(dG_all, self.packed(wih, False, n_major=tca), C, 1, 1, 0, residual=seq.grad,

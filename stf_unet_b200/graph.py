@@ -1,0 +1,58 @@
+"""CUDA-graph capture of the hot path: forward + criterion + backward as ONE graph launch.
+
+A training step of STF-LSTM-UNet is ~590 kernel launches; enqueueing them from Python costs ~14 ms of host time per
+step, which is more than the GPU needs once the kernels are fast.  Every libstfb200 launch is capture-safe (no host
+syncs, no allocation, tensor maps are by-value kernel parameters), so the whole step is captured once and replayed.
+The optimizer and the data-parallel all-reduce stay outside the graph (a handful of launches) so the same object
+serves 1..8 GPUs.
+"""
+from __future__ import annotations
+
+import torch
+
+
+class GraphedStep:
+    """loss = step(x, target): copies the batch into static buffers, replays fwd + loss + bwd; gradients land in the
+    parameters' persistent ``.grad`` views (one flat buffer), ready for all-reduce / optimizer.step()."""
+
+    def __init__(self, model, criterion, example_x, example_target, autocast_dtype=torch.bfloat16, warmup=3):
+        self.model = model
+        self.x = example_x.clone()
+        self.t = example_target.clone()
+        self._hook = model.__dict__.pop("_grad_ready_hook", None)   # collectives stay outside the graph
+
+        def fwd_bwd():
+            with torch.autocast("cuda", dtype=autocast_dtype, enabled=autocast_dtype is not None):
+                loss = criterion(model(self.x), self.t)
+            loss.backward()
+            return loss
+
+        model.train()
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(warmup):                      # learns the pack plan, configures kernels, warms the allocator
+                for p in model.parameters():
+                    p.grad = None
+                fwd_bwd()
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        for p in model.parameters():
+            p.grad = None
+        from . import _lib
+        self.graph = torch.cuda.CUDAGraph()
+        n0 = _lib.launch_count()
+        with torch.cuda.graph(self.graph):
+            self.loss = fwd_bwd()
+        self.launches_per_replay = _lib.launch_count() - n0      # libstfb200 kernels inside the captured graph
+        self.flat_grad = model._last_flat_grad
+        if self._hook is not None:
+            model._grad_ready_hook = self._hook
+
+    def __call__(self, x, target):
+        self.x.copy_(x, non_blocking=True)
+        self.t.copy_(target, non_blocking=True)
+        self.graph.replay()
+        if self._hook is not None:
+            self._hook(self.flat_grad)
+        return self.loss

@@ -277,17 +277,20 @@ def tcgen05_ok(x, Cout, k, stride, pad, mode=CONV_FWD, x2=None, out_hw=None, y_d
 
 
 def bn_stats(x, G, R, C):
-    sums = torch.empty((2, G, C), dtype=torch.float64, device=x.device)
+    """-> per-CTA partial sums [nblk, 2, G, C] fp32 (combined in fp64 by bn_finalize_train)."""
+    lib = _lib.load()
+    nblk = lib.stfb_bn_partial_blocks(G, R)
+    partial = torch.empty((nblk, 2, G, C), dtype=torch.float32, device=x.device)
     with _timed("bn_stats", _nb(x), f"C{C}"):
-        check(_lib.load().stfb_bn_stats(_p(x), _p(sums), G, R, C, dt_code(x.dtype), _stream()), "bn_stats")
-    return sums
+        check(lib.stfb_bn_stats(_p(x), _p(partial), nblk, G, R, C, dt_code(x.dtype), _stream()), "bn_stats")
+    return partial
 
 
-def bn_finalize_train(sums, gamma, beta, running_mean, running_var, nbt, G, R, C, eps=1e-5, momentum=0.1):
-    out = torch.empty((4, G, C), dtype=torch.float32, device=sums.device)  # scale, shift, mean, invstd
-    check(_lib.load().stfb_bn_finalize_train(_p(sums), _p(gamma), _p(beta), _p(running_mean), _p(running_var), _p(nbt),
-                                             _p(out[0]), _p(out[1]), _p(out[2]), _p(out[3]), G, R, C, eps, momentum,
-                                             _stream()), "bn_finalize_train")
+def bn_finalize_train(partial, gamma, beta, running_mean, running_var, nbt, G, R, C, eps=1e-5, momentum=0.1):
+    out = torch.empty((4, G, C), dtype=torch.float32, device=partial.device)  # scale, shift, mean, invstd
+    check(_lib.load().stfb_bn_finalize_train(_p(partial), partial.shape[0], _p(gamma), _p(beta), _p(running_mean),
+                                             _p(running_var), _p(nbt), _p(out[0]), _p(out[1]), _p(out[2]), _p(out[3]), G, R,
+                                             C, eps, momentum, _stream()), "bn_finalize_train")
     return out
 
 
@@ -312,12 +315,13 @@ def bn_bwd(dy, y, x, mean, invstd, gamma, dgamma, dbeta, G, R, C, relu, want_dre
     dres_acc: existing gradient of the residual input, accumulated into in place."""
     lib = _lib.load()
     s = _stream()
-    red = torch.empty((2, G, C), dtype=torch.float64, device=x.device)
+    nblk = lib.stfb_bn_partial_blocks(G, R)
+    red = torch.empty((nblk, 2, G, C), dtype=torch.float32, device=x.device)
     with _timed("bn_bwd_reduce", _nb(dy, x, y if relu else None), f"C{C}"):
-        check(lib.stfb_bn_bwd_reduce(_p(dy), _p(y) if relu else None, _p(x), _p(mean), _p(invstd), _p(red), G, R, C,
+        check(lib.stfb_bn_bwd_reduce(_p(dy), _p(y) if relu else None, _p(x), _p(mean), _p(invstd), _p(red), nblk, G, R, C,
                                      int(bool(relu)), dt_code(x.dtype), s), "bn_bwd_reduce")
     coef = torch.empty((G, C, 3), dtype=torch.float32, device=x.device)
-    check(lib.stfb_bn_bwd_finalize(_p(red), _p(gamma), _p(invstd), _p(dgamma), _p(dbeta), _p(coef), G, R, C, s),
+    check(lib.stfb_bn_bwd_finalize(_p(red), nblk, _p(gamma), _p(invstd), _p(dgamma), _p(dbeta), _p(coef), G, R, C, s),
           "bn_bwd_finalize")
     dx = torch.empty_like(x)
     dres = dres_acc if dres_acc is not None else (torch.empty_like(x) if want_dres else None)
