@@ -47,13 +47,21 @@ struct TcArgs {
 };
 
 constexpr int TC_BM = 128;
-constexpr int TC_BK = 64;                    // 64 bf16 = 128 B = one swizzle row
-constexpr int TC_A_BYTES = TC_BM * TC_BK * 2;  // 16 KB
 constexpr int TC_THREADS = 192;
+// BK = channels per k-block = one swizzle row: 64 bf16 (128 B, SWIZZLE_128B) or 32 bf16 (64 B, SWIZZLE_64B) for the
+// 32-channel layers at the end of the decoder.
 
-template <int BN, int STAGES>
+template <int BN, int STAGES, int BK>
 constexpr int tc_smem_bytes() {
-  return STAGES * (TC_A_BYTES + BN * TC_BK * 2) + 256 + 1024;
+  return STAGES * (TC_BM * BK * 2 + BN * BK * 2) + 256 + 1024;
+}
+
+// K-major descriptor for a [rows][BK] bf16 tile whose rows are BK*2 bytes with the matching swizzle
+template <int BK>
+__device__ __forceinline__ uint64_t make_kmajor_desc(uint32_t saddr) {
+  if constexpr (BK == 64) return make_kmajor_sw128_desc(saddr);
+  // SWIZZLE_64B: layout code 4, 8-row groups are 8 * 64 B = 512 B apart
+  return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)(512 >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)4 << 61);
 }
 
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
@@ -84,10 +92,12 @@ __device__ __forceinline__ TileCoord decode_tile(const TcArgs& a, int tile, int 
 // Persistent: one CTA per SM walks tiles `blockIdx.x, +gridDim.x, ...`.  The TMA ring keeps streaming across tile
 // boundaries and the accumulator is double-buffered in TMEM (2 x BN columns), so the epilogue of tile i overlaps the
 // main loop of tile i+1 and the per-tile prologue (barrier init, TMEM alloc, first TMA round trip) is paid once.
-template <int BN, int STAGES, typename TO>
+template <int BN, int STAGES, typename TO, int BK>
 __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_constant__ CUtensorMap tmA,
                                                                  const __grid_constant__ CUtensorMap tmA2,
                                                                  const __grid_constant__ CUtensorMap tmB, const TcArgs a) {
+  constexpr int TC_BK = BK;
+  constexpr int TC_A_BYTES = TC_BM * BK * 2;
   constexpr int B_BYTES = BN * TC_BK * 2;
   constexpr int STAGE_BYTES = TC_A_BYTES + B_BYTES;
   constexpr int TMEM_COLS = (2 * BN < 32) ? 32 : 2 * BN;
@@ -160,8 +170,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
         tc_fence_after();
         if (lane == 0) {
           const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
-          const uint64_t adesc = make_kmajor_sw128_desc(sa);
-          const uint64_t bdesc = make_kmajor_sw128_desc(sa + TC_A_BYTES);
+          const uint64_t adesc = make_kmajor_desc<BK>(sa);
+          const uint64_t bdesc = make_kmajor_desc<BK>(sa + TC_A_BYTES);
 #pragma unroll
           for (int k = 0; k < TC_BK / 16; ++k) {
             // advance 16 bf16 = 32 B along K inside the swizzle row: +2 in the (addr >> 4) field
@@ -301,7 +311,7 @@ int conv2d_tcgen05_supported(const stfb_conv_params* p) {
   } else if (p->mode != STFB_CONV_TRANSPOSED) {
     return 0;
   }
-  if (p->C1 % 64 != 0 || p->C2 % 64 != 0) return 0;
+  if (p->C1 % 32 != 0 || p->C2 % 32 != 0) return 0;
   if (pick_bn(p->Cout) == 0) return 0;
   auto al = [](const void* q, int b) { return q == nullptr || (reinterpret_cast<uintptr_t>(q) % b) == 0; };
   if (!al(p->x, 16) || !al(p->x2, 16) || !al(p->y, 16) || !al(p->residual, 16)) return 0;
@@ -311,33 +321,33 @@ int conv2d_tcgen05_supported(const stfb_conv_params* p) {
 
 // 4-D NHWC bf16 activation map, box {64 ch, TW, TH, TN} pixels visited with traversal stride `estride` in W and H
 bool encode_nhwc_map_strided(EncodeTiledFn enc, CUtensorMap* tm, const void* base, int N, int H, int W, int C, int TW, int TH,
-                             int TN, int estride) {
+                             int TN, int estride, int cblock) {
   cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
   cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
-  cuuint32_t box[4] = {(cuuint32_t)TC_BK, (cuuint32_t)(TW * estride), (cuuint32_t)(TH * estride), (cuuint32_t)TN};
+  cuuint32_t box[4] = {(cuuint32_t)cblock, (cuuint32_t)(TW * estride), (cuuint32_t)(TH * estride), (cuuint32_t)TN};
   cuuint32_t estr[4] = {1, (cuuint32_t)estride, (cuuint32_t)estride, 1};
   return enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr,
-             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+             CU_TENSOR_MAP_INTERLEAVE_NONE, cblock == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+             CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
 bool encode_nhwc_map(EncodeTiledFn enc, CUtensorMap* tm, const void* base, int N, int H, int W, int C, int TW, int TH, int TN) {
-  return encode_nhwc_map_strided(enc, tm, base, N, H, W, C, TW, TH, TN, 1);
+  return encode_nhwc_map_strided(enc, tm, base, N, H, W, C, TW, TH, TN, 1, 64);
 }
 
-template <int BN, int STAGES, typename TO>
+template <int BN, int STAGES, typename TO, int BK>
 static int launch_tc(const CUtensorMap& tA, const CUtensorMap& tA2, const CUtensorMap& tB, const TcArgs& a, dim3 grid,
                      cudaStream_t st) {
-  constexpr int smem = tc_smem_bytes<BN, STAGES>();
+  constexpr int smem = tc_smem_bytes<BN, STAGES, BK>();
   static bool configured = false;
   if (!configured) {
-    if (cudaFuncSetAttribute(conv_tc_kernel<BN, STAGES, TO>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) {
+    if (cudaFuncSetAttribute(conv_tc_kernel<BN, STAGES, TO, BK>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) {
       set_error("conv2d(tcgen05): cannot reserve %d bytes of shared memory: %s", smem, cudaGetErrorString(cudaGetLastError()));
       return STFB_ECUDA;
     }
     configured = true;
   }
-  conv_tc_kernel<BN, STAGES, TO><<<grid, TC_THREADS, smem, st>>>(tA, tA2, tB, a);
+  conv_tc_kernel<BN, STAGES, TO, BK><<<grid, TC_THREADS, smem, st>>>(tA, tA2, tB, a);
   return post_launch("conv2d(tcgen05)");
 }
 
@@ -391,20 +401,22 @@ int conv2d_tcgen05(const stfb_conv_params* p, cudaStream_t st) {
   if (p->ldw < Ktot) { set_error("conv2d(tcgen05): ldw %d < kh*kw*Cin %d", p->ldw, Ktot); return STFB_EINVAL; }
 
   CUtensorMap tA, tA2, tB;
-  if (!encode_nhwc_map_strided(enc, &tA, p->x, p->N, p->H, p->W, p->C1, a.TW, a.TH, a.TN, a.a_scale)) {
+  const int BK = (p->C1 % 64 == 0 && p->C2 % 64 == 0) ? 64 : 32;
+  if (!encode_nhwc_map_strided(enc, &tA, p->x, p->N, p->H, p->W, p->C1, a.TW, a.TH, a.TN, a.a_scale, BK)) {
     set_error("conv2d(tcgen05): cuTensorMapEncodeTiled failed for x"); return STFB_ECUDA;
   }
   tA2 = tA;
-  if (p->C2 > 0 && !encode_nhwc_map_strided(enc, &tA2, p->x2, p->N, p->H, p->W, p->C2, a.TW, a.TH, a.TN, a.a_scale)) {
+  if (p->C2 > 0 && !encode_nhwc_map_strided(enc, &tA2, p->x2, p->N, p->H, p->W, p->C2, a.TW, a.TH, a.TN, a.a_scale, BK)) {
     set_error("conv2d(tcgen05): cuTensorMapEncodeTiled failed for x2"); return STFB_ECUDA;
   }
   {
     cuuint64_t dims[2] = {(cuuint64_t)Ktot, (cuuint64_t)p->Cout};
     cuuint64_t strides[1] = {(cuuint64_t)p->ldw * 2};
-    cuuint32_t box[2] = {(cuuint32_t)TC_BK, (cuuint32_t)BN};
+    cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)BN};
     cuuint32_t estr[2] = {1, 1};
     if (enc(&tB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(p->w), dims, strides, box, estr,
-            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+            CU_TENSOR_MAP_INTERLEAVE_NONE, BK == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+            CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS) {
       set_error("conv2d(tcgen05): cuTensorMapEncodeTiled failed for the weights"); return STFB_ECUDA;
     }
@@ -413,13 +425,23 @@ int conv2d_tcgen05(const stfb_conv_params* p, cudaStream_t st) {
   a.num_tiles = a.nphase_w * a.nphase_w * tiles_n * a.tiles_h * a.tiles_w * (p->Cout / BN);
   dim3 grid((unsigned)(a.num_tiles < num_sms() ? a.num_tiles : num_sms()));
   const bool f32out = p->y_dtype == STFB_F32;
-#define TC_LAUNCH(BN_, ST_)                                                                                   \
-  return f32out ? launch_tc<BN_, ST_, float>(tA, tA2, tB, a, grid, st) : launch_tc<BN_, ST_, __nv_bfloat16>(tA, tA2, tB, a, grid, st)
-  switch (BN) {
-    case 256: TC_LAUNCH(256, 4);   // 4 x 48 KB
-    case 128: TC_LAUNCH(128, 6);   // 6 x 32 KB
-    case 64: TC_LAUNCH(64, 8);     // 8 x 24 KB
-    case 32: TC_LAUNCH(32, 8);     // 8 x 20 KB
+#define TC_LAUNCH(BN_, ST_, BK_)                                                                              \
+  return f32out ? launch_tc<BN_, ST_, float, BK_>(tA, tA2, tB, a, grid, st)                                 \
+                : launch_tc<BN_, ST_, __nv_bfloat16, BK_>(tA, tA2, tB, a, grid, st)
+  if (BK == 64) {
+    switch (BN) {
+      case 256: TC_LAUNCH(256, 4, 64);   // 4 x 48 KB
+      case 128: TC_LAUNCH(128, 6, 64);   // 6 x 32 KB
+      case 64: TC_LAUNCH(64, 8, 64);     // 8 x 24 KB
+      case 32: TC_LAUNCH(32, 8, 64);     // 8 x 20 KB
+    }
+  } else {
+    switch (BN) {                        // 32-channel inputs (decoder tail): small, memory-bound problems
+      case 256: TC_LAUNCH(256, 6, 32);
+      case 128: TC_LAUNCH(128, 8, 32);
+      case 64: TC_LAUNCH(64, 8, 32);
+      case 32: TC_LAUNCH(32, 8, 32);
+    }
   }
 #undef TC_LAUNCH
   set_error("conv2d(tcgen05): no tile for Cout=%d", p->Cout);

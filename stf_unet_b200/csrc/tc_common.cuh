@@ -117,7 +117,7 @@ EncodeTiledFn get_tensormap_encoder();
 // 4-D NHWC bf16 activation map with box {64 channels, TW, TH, TN}, 128-byte swizzle, zero OOB fill
 bool encode_nhwc_map(EncodeTiledFn enc, CUtensorMap* tm, const void* base, int N, int H, int W, int C, int TW, int TH, int TN);
 bool encode_nhwc_map_strided(EncodeTiledFn enc, CUtensorMap* tm, const void* base, int N, int H, int W, int C, int TW, int TH,
-                             int TN, int estride);
+                             int TN, int estride, int cblock /* 64 -> SWIZZLE_128B, 32 -> SWIZZLE_64B */);
 int pow2_floor(int v);
 
 }  // namespace stfb

@@ -238,9 +238,9 @@ int wgrad_tcgen05(const void* P, const void* G, const void* G2, float* dW, int N
   splits = (a.n_patches + a.patches_per_split - 1) / a.patches_per_split;
 
   CUtensorMap tG, tG2, tP;
-  if (!encode_nhwc_map_strided(enc, &tG, G, N, Hg, Wg, C1, a.TW, a.TH, a.TN, stride)) { set_error("conv2d_wgrad(tcgen05): tensor map (G) failed"); return STFB_ECUDA; }
+  if (!encode_nhwc_map_strided(enc, &tG, G, N, Hg, Wg, C1, a.TW, a.TH, a.TN, stride, 64)) { set_error("conv2d_wgrad(tcgen05): tensor map (G) failed"); return STFB_ECUDA; }
   tG2 = tG;
-  if (C2 > 0 && !encode_nhwc_map_strided(enc, &tG2, G2, N, Hg, Wg, C2, a.TW, a.TH, a.TN, stride)) { set_error("conv2d_wgrad(tcgen05): tensor map (G2) failed"); return STFB_ECUDA; }
+  if (C2 > 0 && !encode_nhwc_map_strided(enc, &tG2, G2, N, Hg, Wg, C2, a.TW, a.TH, a.TN, stride, 64)) { set_error("conv2d_wgrad(tcgen05): tensor map (G2) failed"); return STFB_ECUDA; }
   if (!encode_nhwc_map(enc, &tP, P, N, H, W, Cp, a.TW, a.TH, a.TN)) { set_error("conv2d_wgrad(tcgen05): tensor map (P) failed"); return STFB_ECUDA; }
   dim3 grid((unsigned)m_tiles, (unsigned)n_tiles, (unsigned)splits);
   switch (BN) {

@@ -98,7 +98,7 @@ class Executor:
         N, H, W, C1 = x.data.shape
         C2 = 0 if x2 is None else x2.data.shape[3]
         assert not (transposed and x2 is not None)
-        if (self.dtype == torch.bfloat16 and USE_TCGEN05 and not transposed and x2 is None and C1 % 64 != 0
+        if (self.dtype == torch.bfloat16 and USE_TCGEN05 and not transposed and x2 is None and C1 % 32 != 0
                 and C1 * k * k <= 512 and Cout % 32 == 0 and not x.needs_grad and residual is None):
             return self._conv_small_cin(x, wname, k, stride, pad, bname, scale, shift, relu, y_dtype)
         mode = ops.CONV_TRANSPOSED if transposed else ops.CONV_FWD

@@ -350,7 +350,11 @@ TC_CASES = [
     (2, 16, 16, 128, 128, 128, 3),   # dual-source 3x3 (UNet decoder)
     (4, 16, 16, 64, 0, 256, 1),      # LSTM gate GEMM shape (1x1, N = 4C)
     (1, 64, 64, 64, 0, 32, 3),       # BN=32
-    (16, 32, 32, 128, 0, 128, 3),    # many tiles: exercises co-resident CTAs
+    (16, 32, 32, 128, 0, 128, 3),    # many tiles: every persistent CTA walks several
+    (2, 32, 32, 32, 0, 32, 3),       # 32-channel layer (final_res): 64-byte swizzle path
+    (2, 16, 16, 32, 0, 64, 1),       # 32 -> 64, 1x1
+    (2, 16, 16, 64, 32, 64, 3),      # mixed 64 + 32 channel concat
+    (3, 20, 24, 96, 0, 160, 3),      # channel counts that are multiples of 32 but not 64; Cout = 5 x 32
 ]
 
 
@@ -460,6 +464,8 @@ TC_TRANSPOSED = [
     (2, 8, 8, 128, 64, 1, 2, 0, 1),      # dgrad of the 1x1/2 downsample conv: three of four phases are pure zeros
     (2, 16, 16, 64, 128, 3, 1, 1, 0),    # stride-1 dgrad without flipping the weights
     (16, 16, 16, 256, 128, 3, 2, 1, 1),
+    (2, 16, 16, 64, 32, 3, 2, 1, 1),     # upconv1: 64 -> 32 channels
+    (2, 16, 16, 32, 64, 3, 2, 1, 0),     # its dgrad direction: K = 32 channels
 ]
 
 
