@@ -24,10 +24,11 @@ class ConvParams(C.Structure):
 
 
 _vp, _i, _ll, _f = C.c_void_p, C.c_int, C.c_longlong, C.c_float
+_SIZE_T_FUNCS = {"stfb_conv2d_wgrad_workspace_bytes": [_vp, _vp] + [_i] * 13}
 _SIGS = {
     "stfb_conv2d": [C.POINTER(ConvParams), _vp],
     "stfb_conv2d_tcgen05_supported": [C.POINTER(ConvParams)],
-    "stfb_conv2d_wgrad": [_vp, _vp, _vp] + [_i] * 15 + [_vp],
+    "stfb_conv2d_wgrad": [_vp, _vp, _vp] + [_i] * 15 + [_vp, C.c_size_t, _vp],
     "stfb_conv2d_wgrad_tcgen05_supported": [_vp, _vp] + [_i] * 12,
     "stfb_pack_weight": [_vp, _vp, _i, _i, _i, _i, _i, _i, _vp],
     "stfb_pack_weight_ex": [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp],
@@ -59,7 +60,7 @@ _SIGS = {
     "stfb_ce_dice_fwd": [_vp] * 4 + [_i, _i, _i, _f, _vp],
     "stfb_ce_dice_bwd": [_vp] * 5 + [_i, _i, _i, _f, _vp],
 }
-EXPORTS = sorted(list(_SIGS) + ["stfb_version", "stfb_last_error", "stfb_launch_count"])
+EXPORTS = sorted(list(_SIGS) + list(_SIZE_T_FUNCS) + ["stfb_version", "stfb_last_error", "stfb_launch_count"])
 
 _lib = None
 
@@ -77,6 +78,10 @@ def load():
         fn = getattr(lib, name)
         fn.argtypes = sig
         fn.restype = C.c_int
+    for name, sig in _SIZE_T_FUNCS.items():
+        fn = getattr(lib, name)
+        fn.argtypes = sig
+        fn.restype = C.c_size_t
     lib.stfb_version.restype = C.c_int
     lib.stfb_last_error.restype = C.c_char_p
     lib.stfb_launch_count.restype = C.c_ulonglong

@@ -21,6 +21,7 @@
 //       separate phases with 1/2/2/4 dense taps each (no multiplication by inserted zeros), outputs scattered at
 //       stride s.
 #include "tc_common.cuh"
+#include <stdlib.h>
 
 namespace stfb {
 
@@ -42,6 +43,7 @@ struct TcArgs {
   int tiles_w, tiles_h, tiles_n;
   int num_tiles;         // phases * tiles_n * tiles_h * tiles_w * (Cout / BN)
   int relu;
+  int debug;             // STFB_TC_DEBUG: 1 = no MMAs (TMA pipeline only), 2 = no TMA (MMA issue only); timing experiments
   int ntaps[4];
   signed char dh[4][9], dw[4][9], ktap[4][9];
 };
@@ -146,6 +148,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
           const int c = chunk * TC_BK;
           uint8_t* sa = smem + stage * STAGE_BYTES;
           uint8_t* sb = sa + TC_A_BYTES;
+          if (a.debug == 2) {
+            mbar_arrive(&full_bar[stage]);
+            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+            continue;
+          }
           mbar_arrive_expect_tx(&full_bar[stage], STAGE_BYTES);
           const int w0 = wbase + a.dw[t.ph][tp], h0 = hbase + a.dh[t.ph][tp];
           if (c < a.C1) tma_load_4d(sa, &tmA, &full_bar[stage], c, w0, h0, i0);
@@ -172,10 +179,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
           const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
           const uint64_t adesc = make_kmajor_desc<BK>(sa);
           const uint64_t bdesc = make_kmajor_desc<BK>(sa + TC_A_BYTES);
+          if (a.debug != 1) {
 #pragma unroll
-          for (int k = 0; k < TC_BK / 16; ++k) {
-            // advance 16 bf16 = 32 B along K inside the swizzle row: +2 in the (addr >> 4) field
-            umma_bf16(tmem_acc, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kb | k) != 0);
+            for (int k = 0; k < TC_BK / 16; ++k) {
+              // advance 16 bf16 = 32 B along K inside the swizzle row: +2 in the (addr >> 4) field
+              umma_bf16(tmem_acc, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kb | k) != 0);
+            }
           }
           umma_commit(&empty_bar[stage]);                    // frees the smem slot when these MMAs have read it
           if (kb == t.num_kb - 1) umma_commit(&tfull_bar[acc]);   // accumulator complete
@@ -358,6 +367,11 @@ int conv2d_tcgen05(const stfb_conv_params* p, cudaStream_t st) {
   if (reinterpret_cast<uintptr_t>(p->w) % 16 != 0) { set_error("conv2d(tcgen05): weights must be 16-byte aligned"); return STFB_EINVAL; }
   TcArgs a{};
   a.y = p->y; a.residual = p->residual; a.bias = p->bias; a.bias2 = p->bias2; a.scale = p->scale; a.shift = p->shift;
+  {
+    static int dbg = -1;
+    if (dbg < 0) { const char* e = getenv("STFB_TC_DEBUG"); dbg = e ? atoi(e) : 0; }
+    a.debug = dbg;
+  }
   a.N = p->N; a.Hout = p->Ho; a.Wout = p->Wo; a.Cout = p->Cout; a.C1 = p->C1; a.C2 = p->C2; a.relu = p->relu;
   const int s = p->stride, k = p->kh;
   int Hl, Wl;   // logical pixel grid the tiles cover

@@ -511,7 +511,9 @@ int conv2d_tcgen05_supported(const stfb_conv_params* p);
 int wgrad_tcgen05_supported(int N, int Hp, int Wp, int Cp, int Hg, int Wg, int Cg, int kh, int kw, int stride, int pad,
                             int dtype, const void* P, const void* G);
 int wgrad_tcgen05(const void* P, const void* G, const void* G2, float* dW, int N, int H, int W, int Cp, int Hg, int Wg,
-                  int C1, int C2, int cg_off, int cg_total, int kh, int kw, int stride, int pad, cudaStream_t st);
+                  int C1, int C2, int cg_off, int cg_total, int kh, int kw, int stride, int pad, float* ws, size_t ws_bytes,
+                  cudaStream_t st);
+size_t wgrad_tcgen05_workspace_bytes(int N, int H, int W, int Cp, int Cg, int kh, int kw);
 }
 
 static int validate_conv(const stfb_conv_params* p) {
@@ -565,9 +567,16 @@ extern "C" int stfb_conv2d_wgrad_tcgen05_supported(const void* P, const void* G,
   return stfb::wgrad_tcgen05_supported(N, Hp, Wp, Cp, Hg, Wg, Cg, kh, kw, stride, pad, dtype, P, G);
 }
 
+extern "C" size_t stfb_conv2d_wgrad_workspace_bytes(const void* P, const void* G, int N, int Hp, int Wp, int Cp, int Hg, int Wg,
+                                                    int Cg, int kh, int kw, int stride, int pad, int dtype, int impl) {
+  if (impl == STFB_IMPL_SIMT) return 0;
+  if (!stfb::wgrad_tcgen05_supported(N, Hp, Wp, Cp, Hg, Wg, Cg, kh, kw, stride, pad, dtype, P, G)) return 0;
+  return stfb::wgrad_tcgen05_workspace_bytes(N, Hp, Wp, Cp, Cg, kh, kw);
+}
+
 extern "C" int stfb_conv2d_wgrad(const void* P, const void* G, float* dW, int N, int Hp, int Wp, int Cp, int Hg, int Wg,
                                  int Cg, int cg_off, int cg_total, int kh, int kw, int stride, int pad, int dtype, int impl,
-                                 void* stream) {
+                                 void* workspace, size_t ws_bytes, void* stream) {
   STFB_REQUIRE(P && G && dW, "conv2d_wgrad: null pointer");
   STFB_REQUIRE(N >= 0 && Hp > 0 && Wp > 0 && Cp > 0 && Hg > 0 && Wg > 0 && Cg > 0 && kh > 0 && kw > 0 && stride > 0 && pad >= 0,
                "conv2d_wgrad: bad dims");
@@ -577,7 +586,7 @@ extern "C" int stfb_conv2d_wgrad(const void* P, const void* G, float* dW, int N,
   if (impl != STFB_IMPL_SIMT) {
     const int ok = stfb::wgrad_tcgen05_supported(N, Hp, Wp, Cp, Hg, Wg, Cg, kh, kw, stride, pad, dtype, P, G);
     if (ok) return stfb::wgrad_tcgen05(P, G, nullptr, dW, N, Hp, Wp, Cp, Hg, Wg, Cg, 0, cg_off, cg_total, kh, kw, stride, pad,
-                                       reinterpret_cast<cudaStream_t>(stream));
+                                       reinterpret_cast<float*>(workspace), ws_bytes, reinterpret_cast<cudaStream_t>(stream));
     if (impl == STFB_IMPL_TCGEN05) {
       set_error("conv2d_wgrad: shape not supported by the tcgen05 family");
       return STFB_ENOTSUP;

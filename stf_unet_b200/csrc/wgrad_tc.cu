@@ -9,14 +9,19 @@
 //   * A tile (M = 128) = two independent 64-channel column blocks: they may belong to different filter taps, so
 //     64-channel layers still fill the 128-row datapath (block j of the tile is the x patch shifted by ITS tap).
 //   * B tile (N = BN <= 256) = BN/64 column blocks of the dy patch (unshifted).
-//   * The pixel reduction is split across CTAs (gridDim.z); each CTA accumulates its pixel range in TMEM and adds
-//     the fp32 result into dW (reference layout) with red.global.add.f32.
+//   * The pixel reduction is split across CTAs (gridDim.z); each CTA accumulates its pixel range in TMEM and writes its
+//     fp32 tile to a workspace slice [split][(tap,ci)][co] with coalesced 128-byte row stores; a second small kernel sums
+//     the slices in a fixed order and adds the result into dW in the reference layout.  No atomics: the first version
+//     used red.global.add.f32 straight into [co][ci][ky][kx] and was bound by the L2 atomic units (10 M scattered
+//     sector updates per launch, tensor pipe 12-20 % busy -- profiles/r01_ncu_wgrad_atomics.txt); it is also
+//     bitwise deterministic now.
 #include "tc_common.cuh"
+#include <stdlib.h>
 
 namespace stfb {
 
 struct WgTcArgs {
-  float* dW;
+  float* ws;                // [splits][Kg][Cp] fp32 partial tiles
   int N, H, W, Cp;          // P (dy) is [N, H, W, Cp]; G / G2 are [N, Hg, Wg, C1 / C2] with H = (Hg + 2 pad - k)/stride + 1
   int C1, C2;
   int cg_off, cg_total;     // dW channel window (ci axis) of this launch inside the full weight
@@ -26,6 +31,7 @@ struct WgTcArgs {
   int tiles_w, tiles_h, n_patches;
   int patches_per_split;
   int m_chunks;             // kh*kw*(C1+C2)/64 column blocks on the M axis
+  int debug;                // STFB_WG_DEBUG: 1 = no MMAs (TMA pipeline only), 2 = no TMA (MMA issue only); timing experiments
 };
 
 constexpr int WG_PIX = 64;                       // K per stage
@@ -95,6 +101,11 @@ __global__ void __launch_bounds__(WG_THREADS) wgrad_tc_kernel(const __grid_const
         const int w0 = wb * a.TW, h0 = hb * a.TH, i0 = nb * a.TN;
         mbar_wait(&empty_bar[stage], phase ^ 1);
         uint8_t* sa = smem + stage * STAGE_BYTES;
+        if (a.debug == 2) {
+          asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&full_bar[stage])) : "memory");
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          continue;
+        }
         mbar_arrive_expect_tx(&full_bar[stage], STAGE_BYTES);
 #pragma unroll
         for (int j = 0; j < 2; ++j) {
@@ -120,10 +131,12 @@ __global__ void __launch_bounds__(WG_THREADS) wgrad_tc_kernel(const __grid_const
         const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
         const uint64_t adesc = make_mnmajor_sw128_desc(sa, WG_BLK_BYTES);
         const uint64_t bdesc = make_mnmajor_sw128_desc(sa + 2 * WG_BLK_BYTES, WG_BLK_BYTES);
+        if (a.debug != 1) {
 #pragma unroll
-        for (int k = 0; k < WG_PIX / 16; ++k) {
-          // 16 pixels = 16 rows of 128 B = 2048 B further down each column block
-          umma_bf16(tmem_acc, adesc + (uint64_t)(128 * k), bdesc + (uint64_t)(128 * k), idesc, (it | k) != 0);
+          for (int k = 0; k < WG_PIX / 16; ++k) {
+            // 16 pixels = 16 rows of 128 B = 2048 B further down each column block
+            umma_bf16(tmem_acc, adesc + (uint64_t)(128 * k), bdesc + (uint64_t)(128 * k), idesc, (it | k) != 0);
+          }
         }
         umma_commit(&empty_bar[stage]);
         if (it == n_iter - 1) umma_commit(accum_bar);
@@ -132,17 +145,12 @@ __global__ void __launch_bounds__(WG_THREADS) wgrad_tc_kernel(const __grid_const
       if (++stage == STAGES) { stage = 0; phase ^= 1; }
     }
   } else if (n_iter > 0) {
-    // epilogue: row m of the accumulator = (column block m / 64, channel m % 64)
+    // epilogue: row m of the accumulator = (column block m / 64, channel m % 64) = row kg of the [Kg][Cp] slice
     const int q = warp & 3;
     const int m = q * 32 + lane;
-    const int chunk = (m < 64) ? chunk0 : chunk1;
     const bool valid = (m < 64) || has1;
-    const int tap = chunk / cpt;
-    const int ci = (chunk - tap * cpt) * 64 + (m & 63);
-    const int khw = a.kh * a.kw;
-    // dW[co][cg_off + ci][tap]
-    float* base = a.dW + ((long long)n0 * a.cg_total + a.cg_off + ci) * khw + tap;
-    const long long co_stride = (long long)a.cg_total * khw;
+    const long long kg = (long long)chunk0 * 64 + m;
+    float* rowp = a.ws + ((long long)blockIdx.z * a.m_chunks * 64 + kg) * a.Cp + n0;
     mbar_wait(accum_bar, 0);
     tc_fence_after();
     const uint32_t taddr = tmem_acc + ((uint32_t)(q * 32) << 16);
@@ -153,7 +161,9 @@ __global__ void __launch_bounds__(WG_THREADS) wgrad_tc_kernel(const __grid_const
       tmem_ld_wait();
       if (valid) {
 #pragma unroll
-        for (int j = 0; j < 32; ++j) atomicAdd(base + (long long)(c0 + j) * co_stride, __uint_as_float(r[j]));
+        for (int j = 0; j < 32; j += 4)
+          *reinterpret_cast<float4*>(rowp + c0 + j) = make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]),
+                                                                   __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
       }
     }
   }
@@ -162,6 +172,20 @@ __global__ void __launch_bounds__(WG_THREADS) wgrad_tc_kernel(const __grid_const
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc(tmem_acc, BN);
+  }
+}
+
+// dW[co][cg_off + ci][tap] += sum_s ws[s][(tap, ci)][co]   (fixed summation order)
+__global__ void wgrad_reduce_kernel(const float* __restrict__ ws, float* __restrict__ dW, int splits, int Kg, int Cp, int Cg,
+                                    int khw, int cg_off, int cg_total) {
+  const long long total = (long long)Kg * Cp;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int co = (int)(i % Cp);
+    const int kg = (int)(i / Cp);
+    float acc = 0.f;
+    for (int s = 0; s < splits; ++s) acc += ws[(long long)s * total + i];
+    const int tap = kg / Cg, ci = kg - tap * Cg;
+    dW[((long long)co * cg_total + cg_off + ci) * khw + tap] += acc;
   }
 }
 
@@ -209,33 +233,61 @@ static int launch_wg(const CUtensorMap& tG, const CUtensorMap& tG2, const CUtens
 }
 
 // G (and optional G2, concatenated on the channel axis after G) are the gathered activations; P = dy.
-int wgrad_tcgen05(const void* P, const void* G, const void* G2, float* dW, int N, int H, int W, int Cp, int Hg, int Wg,
-                  int C1, int C2, int cg_off, int cg_total, int kh, int kw, int stride, int pad, cudaStream_t st) {
-  EncodeTiledFn enc = get_tensormap_encoder();
-  if (!enc) { set_error("conv2d_wgrad(tcgen05): cuTensorMapEncodeTiled not available"); return STFB_ECUDA; }
-  if ((long long)N * H * W == 0) return STFB_OK;
-  WgTcArgs a{};
-  a.dW = dW; a.N = N; a.H = H; a.W = W; a.Cp = Cp; a.C1 = C1; a.C2 = C2; a.cg_off = cg_off; a.cg_total = cg_total;
-  a.kh = kh; a.kw = kw; a.pad = pad; a.g_scale = stride;
-  a.TW = pow2_floor(W); if (a.TW > 8) a.TW = 8;
-  a.TH = pow2_floor(H); if (a.TH > WG_PIX / a.TW) a.TH = WG_PIX / a.TW;
-  a.TN = WG_PIX / (a.TW * a.TH);
-  a.tiles_w = (W + a.TW - 1) / a.TW;
-  a.tiles_h = (H + a.TH - 1) / a.TH;
-  const int tiles_n = (N + a.TN - 1) / a.TN;
-  a.n_patches = tiles_n * a.tiles_h * a.tiles_w;
-  a.m_chunks = kh * kw * (C1 + C2) / 64;
-  const int BN = wg_pick_bn(Cp);
-  const int m_tiles = (a.m_chunks + 1) / 2, n_tiles = Cp / BN;
+struct WgPlan { int TW, TH, TN, tiles_w, tiles_h, n_patches, m_chunks, BN, m_tiles, n_tiles, pps, splits; };
+
+static WgPlan wg_plan(int N, int H, int W, int Cp, int Ctot, int kh, int kw) {
+  WgPlan p{};
+  p.TW = pow2_floor(W); if (p.TW > 8) p.TW = 8;
+  p.TH = pow2_floor(H); if (p.TH > WG_PIX / p.TW) p.TH = WG_PIX / p.TW;
+  p.TN = WG_PIX / (p.TW * p.TH);
+  p.tiles_w = (W + p.TW - 1) / p.TW;
+  p.tiles_h = (H + p.TH - 1) / p.TH;
+  p.n_patches = ((N + p.TN - 1) / p.TN) * p.tiles_h * p.tiles_w;
+  p.m_chunks = kh * kw * Ctot / 64;
+  p.BN = wg_pick_bn(Cp);
+  p.m_tiles = (p.m_chunks + 1) / 2;
+  p.n_tiles = Cp / p.BN;
   // split the pixel reduction so the grid covers ~2 waves, keeping >= 4 patches per CTA
-  long long want = (2LL * num_sms() + (long long)m_tiles * n_tiles - 1) / ((long long)m_tiles * n_tiles);
-  long long maxsplit = (a.n_patches + 3) / 4;
+  long long want = (2LL * num_sms() + (long long)p.m_tiles * p.n_tiles - 1) / ((long long)p.m_tiles * p.n_tiles);
+  long long maxsplit = (p.n_patches + 3) / 4;
   long long splits = want < 1 ? 1 : want;
   if (splits > maxsplit) splits = maxsplit;
   if (splits < 1) splits = 1;
   if (splits > 65535) splits = 65535;
-  a.patches_per_split = (int)((a.n_patches + splits - 1) / splits);
-  splits = (a.n_patches + a.patches_per_split - 1) / a.patches_per_split;
+  p.pps = (int)((p.n_patches + splits - 1) / splits);
+  p.splits = (p.n_patches + p.pps - 1) / p.pps;
+  return p;
+}
+
+size_t wgrad_tcgen05_workspace_bytes(int N, int H, int W, int Cp, int Cg, int kh, int kw) {
+  const WgPlan p = wg_plan(N, H, W, Cp, Cg, kh, kw);
+  return (size_t)p.splits * p.m_chunks * 64 * Cp * sizeof(float);
+}
+
+int wgrad_tcgen05(const void* P, const void* G, const void* G2, float* dW, int N, int H, int W, int Cp, int Hg, int Wg,
+                  int C1, int C2, int cg_off, int cg_total, int kh, int kw, int stride, int pad, float* ws, size_t ws_bytes,
+                  cudaStream_t st) {
+  EncodeTiledFn enc = get_tensormap_encoder();
+  if (!enc) { set_error("conv2d_wgrad(tcgen05): cuTensorMapEncodeTiled not available"); return STFB_ECUDA; }
+  if ((long long)N * H * W == 0) return STFB_OK;
+  const WgPlan pl = wg_plan(N, H, W, Cp, C1 + C2, kh, kw);
+  const size_t need = (size_t)pl.splits * pl.m_chunks * 64 * Cp * sizeof(float);
+  if (ws == nullptr || ws_bytes < need || (reinterpret_cast<uintptr_t>(ws) % 16) != 0) {
+    set_error("conv2d_wgrad(tcgen05): workspace of %zu bytes (16-byte aligned) required, got %zu", need, ws_bytes);
+    return STFB_EINVAL;
+  }
+  WgTcArgs a{};
+  a.ws = ws; a.N = N; a.H = H; a.W = W; a.Cp = Cp; a.C1 = C1; a.C2 = C2; a.cg_off = cg_off; a.cg_total = cg_total;
+  a.kh = kh; a.kw = kw; a.pad = pad; a.g_scale = stride;
+  {
+    static int dbg = -1;
+    if (dbg < 0) { const char* e = getenv("STFB_WG_DEBUG"); dbg = e ? atoi(e) : 0; }
+    a.debug = dbg;
+  }
+  a.TW = pl.TW; a.TH = pl.TH; a.TN = pl.TN; a.tiles_w = pl.tiles_w; a.tiles_h = pl.tiles_h; a.n_patches = pl.n_patches;
+  a.m_chunks = pl.m_chunks; a.patches_per_split = pl.pps;
+  const int BN = pl.BN, m_tiles = pl.m_tiles, n_tiles = pl.n_tiles;
+  const long long splits = pl.splits;
 
   CUtensorMap tG, tG2, tP;
   if (!encode_nhwc_map_strided(enc, &tG, G, N, Hg, Wg, C1, a.TW, a.TH, a.TN, stride, 64)) { set_error("conv2d_wgrad(tcgen05): tensor map (G) failed"); return STFB_ECUDA; }
@@ -243,13 +295,20 @@ int wgrad_tcgen05(const void* P, const void* G, const void* G2, float* dW, int N
   if (C2 > 0 && !encode_nhwc_map_strided(enc, &tG2, G2, N, Hg, Wg, C2, a.TW, a.TH, a.TN, stride, 64)) { set_error("conv2d_wgrad(tcgen05): tensor map (G2) failed"); return STFB_ECUDA; }
   if (!encode_nhwc_map(enc, &tP, P, N, H, W, Cp, a.TW, a.TH, a.TN)) { set_error("conv2d_wgrad(tcgen05): tensor map (P) failed"); return STFB_ECUDA; }
   dim3 grid((unsigned)m_tiles, (unsigned)n_tiles, (unsigned)splits);
+  int rc = STFB_ENOTSUP;
   switch (BN) {
-    case 256: return launch_wg<256, 4>(tG, tG2, tP, a, grid, st);
-    case 128: return launch_wg<128, 5>(tG, tG2, tP, a, grid, st);
-    case 64: return launch_wg<64, 6>(tG, tG2, tP, a, grid, st);
+    case 256: rc = launch_wg<256, 4>(tG, tG2, tP, a, grid, st); break;
+    case 128: rc = launch_wg<128, 5>(tG, tG2, tP, a, grid, st); break;
+    case 64: rc = launch_wg<64, 6>(tG, tG2, tP, a, grid, st); break;
+    default: set_error("conv2d_wgrad(tcgen05): no tile for Cp=%d", Cp); return STFB_ENOTSUP;
   }
-  set_error("conv2d_wgrad(tcgen05): no tile for Cp=%d", Cp);
-  return STFB_ENOTSUP;
+  if (rc != STFB_OK) return rc;
+  const int Kg = pl.m_chunks * 64;
+  const long long total = (long long)Kg * Cp;
+  int blocks = (int)((total + 255) / 256);
+  if (blocks > 8 * num_sms()) blocks = 8 * num_sms();
+  wgrad_reduce_kernel<<<blocks, 256, 0, st>>>(ws, dW, (int)splits, Kg, Cp, C1 + C2, kh * kw, cg_off, cg_total);
+  return post_launch("conv2d_wgrad(reduce)");
 }
 
 }  // namespace stfb

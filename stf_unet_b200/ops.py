@@ -166,9 +166,11 @@ def conv2d_wgrad(P, G, dW, k, stride, pad, cg_off=0, cg_total=None, impl=IMPL_AU
         tc = impl != IMPL_SIMT and lib.stfb_conv2d_wgrad_tcgen05_supported(_p(P), _p(G), N, Hp, Wp, Cp, Hg, Wg, Cg, kh, kw,
                                                                            stride, pad, dt) == 1
         e0 = _prof.begin()
+    ws_bytes = lib.stfb_conv2d_wgrad_workspace_bytes(_p(P), _p(G), N, Hp, Wp, Cp, Hg, Wg, Cg, kh, kw, stride, pad, dt, impl)
+    ws = torch.empty((ws_bytes // 4,), dtype=torch.float32, device=P.device) if ws_bytes else None
     check(lib.stfb_conv2d_wgrad(_p(P), _p(G), _p(dW), N, Hp, Wp, Cp, Hg, Wg, Cg, cg_off,
-                                cg_total if cg_total is not None else Cg, kh, kw, stride, pad, dt, impl, _stream()),
-          "conv2d_wgrad")
+                                cg_total if cg_total is not None else Cg, kh, kw, stride, pad, dt, impl, _p(ws), ws_bytes,
+                                _stream()), "conv2d_wgrad")
     if e0 is not None:
         fam = "wgrad_tcgen05" if tc else "wgrad_simt_" + ("bf16" if P.element_size() == 2 else "f32")
         _prof.end(e0, fam, 2.0 * N * Hp * Wp * Cp * Cg * kh * kw, (P.numel() + G.numel()) * P.element_size(),
