@@ -92,8 +92,8 @@ int stfb_conv2d_tcgen05_supported(const stfb_conv_params* p);
  * Replaces: autograd of the operators listed above (loss.backward(), train_utils/train_and_eval.py:397-404).
  * impl: STFB_IMPL_AUTO picks the tcgen05 family when the shape allows (bf16, stride-1 "same" geometry, Cg % 64 == 0,
  * Cp % 64 == 0), else the SIMT family; STFB_IMPL_SIMT / STFB_IMPL_TCGEN05 force one.
- * The tcgen05 family needs a caller-provided fp32 workspace (split-K partial tiles, reduced in a fixed order: the result
- * is bitwise deterministic); stfb_conv2d_wgrad_workspace_bytes returns its size (0 when the SIMT family will run). */
+ * The tcgen05 family needs a caller-provided fp32 workspace (the [(ky,kx,ci)][co] accumulation buffer the split-K CTAs
+ * reduce into); stfb_conv2d_wgrad_workspace_bytes returns its size (0 when the SIMT family will run). */
 size_t stfb_conv2d_wgrad_workspace_bytes(const void* P, const void* G, int N, int Hp, int Wp, int Cp, int Hg, int Wg, int Cg,
                                          int kh, int kw, int stride, int pad, int dtype, int impl);
 int stfb_conv2d_wgrad(const void* P, const void* G, float* dW, int N, int Hp, int Wp, int Cp, int Hg, int Wg, int Cg,

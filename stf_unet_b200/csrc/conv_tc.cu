@@ -229,7 +229,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
           __syncwarp();
           if (lane == 0) mbar_arrive(&tempty_bar[acc]);
         }
-        if (valid) {
+        if (valid && a.debug != 3) {
           float v[32];
           const int cg = t.n0 + c0;
 #pragma unroll

@@ -9,12 +9,11 @@
 //   * A tile (M = 128) = two independent 64-channel column blocks: they may belong to different filter taps, so
 //     64-channel layers still fill the 128-row datapath (block j of the tile is the x patch shifted by ITS tap).
 //   * B tile (N = BN <= 256) = BN/64 column blocks of the dy patch (unshifted).
-//   * The pixel reduction is split across CTAs (gridDim.z); each CTA accumulates its pixel range in TMEM and writes its
-//     fp32 tile to a workspace slice [split][(tap,ci)][co] with coalesced 128-byte row stores; a second small kernel sums
-//     the slices in a fixed order and adds the result into dW in the reference layout.  No atomics: the first version
-//     used red.global.add.f32 straight into [co][ci][ky][kx] and was bound by the L2 atomic units (10 M scattered
-//     sector updates per launch, tensor pipe 12-20 % busy -- profiles/r01_ncu_wgrad_atomics.txt); it is also
-//     bitwise deterministic now.
+//   * The pixel reduction is split across CTAs (gridDim.z, one wave); each CTA accumulates its pixel range in TMEM and
+//     adds its fp32 tile into an L2-resident accumulation buffer [(tap,ci)][co] with 16-byte vector reductions
+//     (red.global.add.v4.f32: a 128-byte row per thread); a small second kernel transposes that buffer into dW in the
+//     reference layout.  (v1 issued scalar red.add straight into [co][ci][ky][kx]: 10 M scattered sector updates per
+//     launch -- profiles/r01_ncu_wgrad_atomics.txt; v2 wrote per-split partial tiles: 38 MB out + 38 MB back per launch.)
 #include "tc_common.cuh"
 #include <stdlib.h>
 
@@ -38,17 +37,22 @@ constexpr int WG_PIX = 64;                       // K per stage
 constexpr int WG_BLK_BYTES = WG_PIX * 128;       // one 64-ch x 64-pixel column block = 8 KB
 constexpr int WG_THREADS = 192;
 
-template <int BN, int STAGES>
+// NA accumulators (M = 128 each = two 64-channel column blocks of the gathered operand) share ONE dy tile per stage:
+// the kernel is bound by the L2 -> shared-memory fill rate (~12 TB/s chip-wide, profiles/), so every byte of dy that is
+// fetched should feed as many (tap, ci) rows as TMEM can hold (NA * BN <= 512 columns).
+template <int BN, int NA, int STAGES>
 constexpr int wg_smem_bytes() {
-  return STAGES * (2 + BN / 64) * WG_BLK_BYTES + 256 + 1024;
+  return STAGES * (2 * NA + BN / 64) * WG_BLK_BYTES + 256 + 1024;
 }
 
-template <int BN, int STAGES>
-__global__ void __launch_bounds__(WG_THREADS) wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmG,
-                                                               const __grid_constant__ CUtensorMap tmG2,
-                                                               const __grid_constant__ CUtensorMap tmP, const WgTcArgs a) {
+template <int BN, int NA, int STAGES>
+__global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmG,
+                                                                  const __grid_constant__ CUtensorMap tmG2,
+                                                                  const __grid_constant__ CUtensorMap tmP, const WgTcArgs a) {
   constexpr int NB = BN / 64;
-  constexpr int STAGE_BYTES = (2 + NB) * WG_BLK_BYTES;
+  constexpr int STAGE_BYTES = (2 * NA + NB) * WG_BLK_BYTES;
+  constexpr int TMEM_COLS = (NA * BN <= 32) ? 32 : (NA * BN <= 64) ? 64 : (NA * BN <= 128) ? 128 : (NA * BN <= 256) ? 256 : 512;
+  static_assert(NA * BN <= 512, "accumulators exceed tensor memory");
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
@@ -57,16 +61,16 @@ __global__ void __launch_bounds__(WG_THREADS) wgrad_tc_kernel(const __grid_const
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum_bar + 1);
 
   const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
-  const int mtile = blockIdx.x;
   const int n0 = blockIdx.y * BN;
   const int p_beg = blockIdx.z * a.patches_per_split;
   const int p_end = min(a.n_patches, p_beg + a.patches_per_split);
   const int Cin = a.C1 + a.C2;
   const int cpt = Cin / 64;                       // column blocks per tap
-  // the two column blocks of this M tile (the second falls back to the first when the tile is half empty)
-  const int chunk0 = mtile * 2;
-  const bool has1 = chunk0 + 1 < a.m_chunks;
-  const int chunk1 = has1 ? chunk0 + 1 : chunk0;
+  // this CTA owns column blocks [chunk_lo, chunk_hi) of the (tap, ci) axis: up to 2*NA of them
+  const int chunk_lo = blockIdx.x * 2 * NA;
+  const int chunk_hi = min(a.m_chunks, chunk_lo + 2 * NA);
+  const int nchunks = chunk_hi - chunk_lo;
+  const int nacc = (nchunks + 1) / 2;             // accumulators in use
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
@@ -77,22 +81,23 @@ __global__ void __launch_bounds__(WG_THREADS) wgrad_tc_kernel(const __grid_const
     if (a.C2 > 0) prefetch_tensormap(&tmG2);
   }
   if (warp == 1) {
-    tmem_alloc(tmem_slot, BN);
+    tmem_alloc(tmem_slot, TMEM_COLS);
     tmem_relinquish();
   }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_acc = *tmem_slot;
+  const uint32_t tmem_base = *tmem_slot;
   const int n_iter = p_end - p_beg;
 
   if (warp == 0) {
     if (lane == 0 && n_iter > 0) {
       int stage = 0;
       uint32_t phase = 0;
-      int tapc[2], cc[2];
-      tapc[0] = chunk0 / cpt; cc[0] = (chunk0 - tapc[0] * cpt) * 64;
-      tapc[1] = chunk1 / cpt; cc[1] = (chunk1 - tapc[1] * cpt) * 64;
+      // an odd block count leaves the upper half of the last accumulator unused: it re-reads the previous block
+      // (its rows are never written out), so every stage moves the same number of bytes
+      const int nload = 2 * nacc;
+      const uint32_t bytes = (uint32_t)(nload + NB) * WG_BLK_BYTES;
       for (int p = p_beg; p < p_end; ++p) {
         int t = p;
         const int wb = t % a.tiles_w; t /= a.tiles_w;
@@ -106,17 +111,18 @@ __global__ void __launch_bounds__(WG_THREADS) wgrad_tc_kernel(const __grid_const
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
           continue;
         }
-        mbar_arrive_expect_tx(&full_bar[stage], STAGE_BYTES);
-#pragma unroll
-        for (int j = 0; j < 2; ++j) {
-          const int r = tapc[j] / a.kw, s = tapc[j] - r * a.kw;
-          const int gw = w0 * a.g_scale - a.pad + s, gh = h0 * a.g_scale - a.pad + r;
-          if (cc[j] < a.C1) tma_load_4d(sa + j * WG_BLK_BYTES, &tmG, &full_bar[stage], cc[j], gw, gh, i0);
-          else tma_load_4d(sa + j * WG_BLK_BYTES, &tmG2, &full_bar[stage], cc[j] - a.C1, gw, gh, i0);
+        mbar_arrive_expect_tx(&full_bar[stage], bytes);
+        for (int j = 0; j < nload; ++j) {
+          const int chunk = min(chunk_lo + j, chunk_hi - 1);
+          const int tap = chunk / cpt, cc = (chunk - tap * cpt) * 64;
+          const int r = tap / a.kw, sx = tap - r * a.kw;
+          const int gw = w0 * a.g_scale - a.pad + sx, gh = h0 * a.g_scale - a.pad + r;
+          if (cc < a.C1) tma_load_4d(sa + j * WG_BLK_BYTES, &tmG, &full_bar[stage], cc, gw, gh, i0);
+          else tma_load_4d(sa + j * WG_BLK_BYTES, &tmG2, &full_bar[stage], cc - a.C1, gw, gh, i0);
         }
 #pragma unroll
         for (int i = 0; i < NB; ++i)
-          tma_load_4d(sa + (2 + i) * WG_BLK_BYTES, &tmP, &full_bar[stage], n0 + i * 64, w0, h0, i0);
+          tma_load_4d(sa + (2 * NA + i) * WG_BLK_BYTES, &tmP, &full_bar[stage], n0 + i * 64, w0, h0, i0);
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
     }
@@ -129,13 +135,16 @@ __global__ void __launch_bounds__(WG_THREADS) wgrad_tc_kernel(const __grid_const
       tc_fence_after();
       if (lane == 0) {
         const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
-        const uint64_t adesc = make_mnmajor_sw128_desc(sa, WG_BLK_BYTES);
-        const uint64_t bdesc = make_mnmajor_sw128_desc(sa + 2 * WG_BLK_BYTES, WG_BLK_BYTES);
+        const uint64_t bdesc = make_mnmajor_sw128_desc(sa + 2 * NA * WG_BLK_BYTES, WG_BLK_BYTES);
         if (a.debug != 1) {
 #pragma unroll
           for (int k = 0; k < WG_PIX / 16; ++k) {
             // 16 pixels = 16 rows of 128 B = 2048 B further down each column block
-            umma_bf16(tmem_acc, adesc + (uint64_t)(128 * k), bdesc + (uint64_t)(128 * k), idesc, (it | k) != 0);
+            for (int j = 0; j < nacc; ++j) {
+              const uint64_t adesc = make_mnmajor_sw128_desc(sa + (uint32_t)(2 * j) * WG_BLK_BYTES, WG_BLK_BYTES);
+              umma_bf16(tmem_base + (uint32_t)(j * BN), adesc + (uint64_t)(128 * k), bdesc + (uint64_t)(128 * k), idesc,
+                        (it | k) != 0);
+            }
           }
         }
         umma_commit(&empty_bar[stage]);
@@ -145,25 +154,29 @@ __global__ void __launch_bounds__(WG_THREADS) wgrad_tc_kernel(const __grid_const
       if (++stage == STAGES) { stage = 0; phase ^= 1; }
     }
   } else if (n_iter > 0) {
-    // epilogue: row m of the accumulator = (column block m / 64, channel m % 64) = row kg of the [Kg][Cp] slice
+    // epilogue: accumulator j, row m = (column block chunk_lo + 2j + m/64, channel m % 64) = row kg of the [Kg][Cp] slice
     const int q = warp & 3;
     const int m = q * 32 + lane;
-    const bool valid = (m < 64) || has1;
-    const long long kg = (long long)chunk0 * 64 + m;
-    float* rowp = a.ws + ((long long)blockIdx.z * a.m_chunks * 64 + kg) * a.Cp + n0;
     mbar_wait(accum_bar, 0);
     tc_fence_after();
-    const uint32_t taddr = tmem_acc + ((uint32_t)(q * 32) << 16);
+    for (int j = 0; j < nacc; ++j) {
+      const int chunk = chunk_lo + 2 * j + (m >> 6);
+      const bool valid = chunk < chunk_hi;
+      const long long kg = (long long)chunk * 64 + (m & 63);
+      float* rowp = a.ws + kg * a.Cp + n0;
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(j * BN);
 #pragma unroll 1
-    for (int c0 = 0; c0 < BN; c0 += 32) {
-      uint32_t r[32];
-      tmem_ld_x32(taddr + c0, r);
-      tmem_ld_wait();
-      if (valid) {
+      for (int c0 = 0; c0 < BN; c0 += 32) {
+        uint32_t r[32];
+        tmem_ld_x32(taddr + c0, r);
+        tmem_ld_wait();
+        if (valid && a.debug != 3) {
 #pragma unroll
-        for (int j = 0; j < 32; j += 4)
-          *reinterpret_cast<float4*>(rowp + c0 + j) = make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]),
-                                                                   __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
+          for (int e = 0; e < 32; e += 4)
+            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(rowp + c0 + e), "f"(__uint_as_float(r[e])),
+                         "f"(__uint_as_float(r[e + 1])), "f"(__uint_as_float(r[e + 2])), "f"(__uint_as_float(r[e + 3]))
+                         : "memory");
+        }
       }
     }
   }
@@ -171,21 +184,33 @@ __global__ void __launch_bounds__(WG_THREADS) wgrad_tc_kernel(const __grid_const
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_acc, BN);
+    tmem_dealloc(tmem_base, TMEM_COLS);
   }
 }
 
-// dW[co][cg_off + ci][tap] += sum_s ws[s][(tap, ci)][co]   (fixed summation order)
-__global__ void wgrad_reduce_kernel(const float* __restrict__ ws, float* __restrict__ dW, int splits, int Kg, int Cp, int Cg,
-                                    int khw, int cg_off, int cg_total) {
-  const long long total = (long long)Kg * Cp;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const int co = (int)(i % Cp);
-    const int kg = (int)(i / Cp);
-    float acc = 0.f;
-    for (int s = 0; s < splits; ++s) acc += ws[(long long)s * total + i];
-    const int tap = kg / Cg, ci = kg - tap * Cg;
-    dW[((long long)co * cg_total + cg_off + ci) * khw + tap] += acc;
+// dW[co][cg_off + ci][tap] += acc[(tap, ci)][co]: 32 ci x 32 co tiles transposed through shared memory so that both the
+// reads (along co) and the writes (along (ci, tap), contiguous in the reference layout) are coalesced
+__global__ void __launch_bounds__(256) wgrad_scatter_kernel(const float* __restrict__ acc, float* __restrict__ dW, int Cp, int Cg,
+                                                           int khw, int cg_off, int cg_total) {
+  __shared__ float tile[9][32][33];
+  const int ci0 = blockIdx.x * 32, co0 = blockIdx.y * 32;
+  const int tx = threadIdx.x % 32, ty = threadIdx.x / 32;       // 32 x 8
+  for (int tap = 0; tap < khw; ++tap)
+    for (int r = ty; r < 32; r += 8) {
+      const int ci = ci0 + r, co = co0 + tx;
+      tile[tap][r][tx] = (ci < Cg && co < Cp) ? acc[((long long)tap * Cg + ci) * Cp + co] : 0.f;
+    }
+  __syncthreads();
+  // one co row at a time: 32 ci x khw taps = a contiguous run of 32*khw floats in dW
+  const int run = 32 * khw;
+  for (int r = ty; r < 32; r += 8) {
+    const int co = co0 + r;
+    if (co >= Cp) continue;
+    float* dst = dW + ((long long)co * cg_total + cg_off + ci0) * khw;
+    for (int e = tx; e < run; e += 32) {
+      const int ci = e / khw, tap = e - ci * khw;
+      if (ci0 + ci < Cg) dst[e] += tile[tap][ci][r];
+    }
   }
 }
 
@@ -215,25 +240,26 @@ int wgrad_tcgen05_supported(int N, int Hp, int Wp, int Cp, int Hg, int Wg, int C
   return 1;
 }
 
-template <int BN, int STAGES>
+template <int BN, int NA, int STAGES>
 static int launch_wg(const CUtensorMap& tG, const CUtensorMap& tG2, const CUtensorMap& tP, const WgTcArgs& a, dim3 grid,
                      cudaStream_t st) {
-  constexpr int smem = wg_smem_bytes<BN, STAGES>();
+  constexpr int smem = wg_smem_bytes<BN, NA, STAGES>();
+  static_assert(smem <= 232448, "shared memory budget");
   static bool configured = false;
   if (!configured) {
-    if (cudaFuncSetAttribute(wgrad_tc_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) {
+    if (cudaFuncSetAttribute(wgrad_tc_kernel<BN, NA, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) {
       set_error("conv2d_wgrad(tcgen05): cannot reserve %d bytes of shared memory", smem);
       cudaGetLastError();
       return STFB_ECUDA;
     }
     configured = true;
   }
-  wgrad_tc_kernel<BN, STAGES><<<grid, WG_THREADS, smem, st>>>(tG, tG2, tP, a);
+  wgrad_tc_kernel<BN, NA, STAGES><<<grid, WG_THREADS, smem, st>>>(tG, tG2, tP, a);
   return post_launch("conv2d_wgrad(tcgen05)");
 }
 
 // G (and optional G2, concatenated on the channel axis after G) are the gathered activations; P = dy.
-struct WgPlan { int TW, TH, TN, tiles_w, tiles_h, n_patches, m_chunks, BN, m_tiles, n_tiles, pps, splits; };
+struct WgPlan { int TW, TH, TN, tiles_w, tiles_h, n_patches, m_chunks, BN, NA, m_tiles, n_tiles, pps, splits; };
 
 static WgPlan wg_plan(int N, int H, int W, int Cp, int Ctot, int kh, int kw) {
   WgPlan p{};
@@ -245,12 +271,17 @@ static WgPlan wg_plan(int N, int H, int W, int Cp, int Ctot, int kh, int kw) {
   p.n_patches = ((N + p.TN - 1) / p.TN) * p.tiles_h * p.tiles_w;
   p.m_chunks = kh * kw * Ctot / 64;
   p.BN = wg_pick_bn(Cp);
-  p.m_tiles = (p.m_chunks + 1) / 2;
+  // accumulators per CTA: as many as TMEM holds (BN=256: 2, 128: 3, 64: 5) but no more than the problem has
+  const int na_max = p.BN == 256 ? 2 : (p.BN == 128 ? 3 : 5);
+  const int na_need = (p.m_chunks + 1) / 2;
+  p.NA = na_need >= na_max ? na_max : (na_need >= 2 ? 2 : 1);
+  if (p.BN == 64 && p.NA == 2 && na_need > 2) p.NA = na_max;
+  p.m_tiles = (p.m_chunks + 2 * p.NA - 1) / (2 * p.NA);
   p.n_tiles = Cp / p.BN;
-  // split the pixel reduction so the grid covers ~2 waves, keeping >= 4 patches per CTA
-  long long want = (2LL * num_sms() + (long long)p.m_tiles * p.n_tiles - 1) / ((long long)p.m_tiles * p.n_tiles);
-  long long maxsplit = (p.n_patches + 3) / 4;
-  long long splits = want < 1 ? 1 : want;
+  // ONE wave: m_tiles * n_tiles * splits <= #SMs (a 2.03-wave grid costs a whole third round), >= 2 patches per CTA
+  long long tiles = (long long)p.m_tiles * p.n_tiles;
+  long long splits = num_sms() / tiles;
+  long long maxsplit = (p.n_patches + 1) / 2;
   if (splits > maxsplit) splits = maxsplit;
   if (splits < 1) splits = 1;
   if (splits > 65535) splits = 65535;
@@ -260,8 +291,7 @@ static WgPlan wg_plan(int N, int H, int W, int Cp, int Ctot, int kh, int kw) {
 }
 
 size_t wgrad_tcgen05_workspace_bytes(int N, int H, int W, int Cp, int Cg, int kh, int kw) {
-  const WgPlan p = wg_plan(N, H, W, Cp, Cg, kh, kw);
-  return (size_t)p.splits * p.m_chunks * 64 * Cp * sizeof(float);
+  return (size_t)kh * kw * Cg * Cp * sizeof(float);     // fp32 accumulation buffer [(tap, ci)][co]
 }
 
 int wgrad_tcgen05(const void* P, const void* G, const void* G2, float* dW, int N, int H, int W, int Cp, int Hg, int Wg,
@@ -271,7 +301,7 @@ int wgrad_tcgen05(const void* P, const void* G, const void* G2, float* dW, int N
   if (!enc) { set_error("conv2d_wgrad(tcgen05): cuTensorMapEncodeTiled not available"); return STFB_ECUDA; }
   if ((long long)N * H * W == 0) return STFB_OK;
   const WgPlan pl = wg_plan(N, H, W, Cp, C1 + C2, kh, kw);
-  const size_t need = (size_t)pl.splits * pl.m_chunks * 64 * Cp * sizeof(float);
+  const size_t need = (size_t)pl.m_chunks * 64 * Cp * sizeof(float);
   if (ws == nullptr || ws_bytes < need || (reinterpret_cast<uintptr_t>(ws) % 16) != 0) {
     set_error("conv2d_wgrad(tcgen05): workspace of %zu bytes (16-byte aligned) required, got %zu", need, ws_bytes);
     return STFB_EINVAL;
@@ -295,20 +325,25 @@ int wgrad_tcgen05(const void* P, const void* G, const void* G2, float* dW, int N
   if (C2 > 0 && !encode_nhwc_map_strided(enc, &tG2, G2, N, Hg, Wg, C2, a.TW, a.TH, a.TN, stride, 64)) { set_error("conv2d_wgrad(tcgen05): tensor map (G2) failed"); return STFB_ECUDA; }
   if (!encode_nhwc_map(enc, &tP, P, N, H, W, Cp, a.TW, a.TH, a.TN)) { set_error("conv2d_wgrad(tcgen05): tensor map (P) failed"); return STFB_ECUDA; }
   dim3 grid((unsigned)m_tiles, (unsigned)n_tiles, (unsigned)splits);
+  cudaMemsetAsync(ws, 0, need, st);
   int rc = STFB_ENOTSUP;
-  switch (BN) {
-    case 256: rc = launch_wg<256, 4>(tG, tG2, tP, a, grid, st); break;
-    case 128: rc = launch_wg<128, 5>(tG, tG2, tP, a, grid, st); break;
-    case 64: rc = launch_wg<64, 6>(tG, tG2, tP, a, grid, st); break;
-    default: set_error("conv2d_wgrad(tcgen05): no tile for Cp=%d", Cp); return STFB_ENOTSUP;
+  const int key = BN * 10 + pl.NA;
+  switch (key) {
+    case 2562: rc = launch_wg<256, 2, 3>(tG, tG2, tP, a, grid, st); break;   // stage 64 KB
+    case 2561: rc = launch_wg<256, 1, 4>(tG, tG2, tP, a, grid, st); break;   // stage 48 KB
+    case 1283: rc = launch_wg<128, 3, 3>(tG, tG2, tP, a, grid, st); break;   // stage 64 KB
+    case 1282: rc = launch_wg<128, 2, 4>(tG, tG2, tP, a, grid, st); break;   // stage 48 KB
+    case 1281: rc = launch_wg<128, 1, 6>(tG, tG2, tP, a, grid, st); break;   // stage 32 KB
+    case 645: rc = launch_wg<64, 5, 2>(tG, tG2, tP, a, grid, st); break;     // stage 88 KB
+    case 642: rc = launch_wg<64, 2, 5>(tG, tG2, tP, a, grid, st); break;     // stage 40 KB
+    case 641: rc = launch_wg<64, 1, 8>(tG, tG2, tP, a, grid, st); break;     // stage 24 KB
+    default: set_error("conv2d_wgrad(tcgen05): no kernel for Cp=%d NA=%d", Cp, pl.NA); return STFB_ENOTSUP;
   }
   if (rc != STFB_OK) return rc;
-  const int Kg = pl.m_chunks * 64;
-  const long long total = (long long)Kg * Cp;
-  int blocks = (int)((total + 255) / 256);
-  if (blocks > 8 * num_sms()) blocks = 8 * num_sms();
-  wgrad_reduce_kernel<<<blocks, 256, 0, st>>>(ws, dW, (int)splits, Kg, Cp, C1 + C2, kh * kw, cg_off, cg_total);
-  return post_launch("conv2d_wgrad(reduce)");
+  (void)splits;
+  dim3 sgrid((unsigned)((C1 + C2 + 31) / 32), (unsigned)((Cp + 31) / 32));
+  wgrad_scatter_kernel<<<sgrid, 256, 0, st>>>(ws, dW, Cp, C1 + C2, kh * kw, cg_off, cg_total);
+  return post_launch("conv2d_wgrad(scatter)");
 }
 
 }  // namespace stfb

@@ -33,7 +33,10 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("what", nargs="?", default="conv")
     ap.add_argument("--iters", type=int, default=20)
+    ap.add_argument("--nmul", type=int, default=1, help="multiply the batch of every shape (scaling experiments)")
     a = ap.parse_args()
+    global CONV_SHAPES
+    CONV_SHAPES = [(n * a.nmul, h, w, ci, co, k) for (n, h, w, ci, co, k) in CONV_SHAPES]
     bf = torch.bfloat16
     if a.what in ("conv", "all"):
         for (N, H, W, Cin, Cout, k) in CONV_SHAPES:
