@@ -207,6 +207,12 @@ int stfb_lstm_cell_bwd(const float* dh, float* dc, const void* acts, const float
  * ---------------------------------------------------------------------------------------------- */
 /* x [B, T, C, H, W] fp32  ->  y [T*B, H, W, C] dtype  (time-major image order n = t*B + b) */
 int stfb_pack_series(const float* x, void* y, int B, int T, int C, int H, int W, int dtype, void* stream);
+/* PK-map branch (src/stf_lstm_unet.py:146-156, :172-174): x [B,T,Cx,H,W] fp32 + maps [B,Cm,H,W] fp32 ->
+ * y [T*B, H, W, Cx+Cm] dtype (the torch.cat([x_t, pk_maps], 1) of every time step, time-major) */
+int stfb_pack_series_maps(const float* x, const float* maps, void* y, int B, int T, int Cx, int Cm, int H, int W, int dtype,
+                          void* stream);
+/* dst = `times` back-to-back copies of src (bytes each): a per-sample map repeated for every time step */
+int stfb_repeat(const void* src, void* dst, size_t bytes, int times, void* stream);
 /* y NHWC dtype [N,H,W,C] -> out NCHW fp32 [N,C,H,W] */
 int stfb_nhwc_to_nchw(const void* y, float* out, int N, int H, int W, int C, int dtype, void* stream);
 /* g NCHW fp32 -> NHWC dtype */

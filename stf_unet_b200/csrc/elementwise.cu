@@ -703,6 +703,24 @@ __global__ void pack_series_kernel(const float* __restrict__ x, T* __restrict__ 
   }
 }
 
+// time series + static per-sample maps -> one NHWC tensor: y[t*B+b][h][w][c] = c < Cx ? x[b][t][c][h][w] : m[b][c-Cx][h][w]
+template <typename T>
+__global__ void pack_series_maps_kernel(const float* __restrict__ x, const float* __restrict__ m, T* __restrict__ y, int B, int Tn,
+                                        int Cx, int Cm, int H, int W, long long total) {
+  const int C = Cx + Cm;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C);
+    long long r = i / C;
+    const int xx = (int)(r % W); r /= W;
+    const int yy = (int)(r % H); r /= H;
+    const int b = (int)(r % B);
+    const int t = (int)(r / B);
+    const float v = c < Cx ? x[((((long long)b * Tn + t) * Cx + c) * H + yy) * W + xx]
+                           : m[(((long long)b * Cm + (c - Cx)) * H + yy) * W + xx];
+    st1(y + i, v);
+  }
+}
+
 template <typename T>
 __global__ void nhwc_to_nchw_kernel(const T* __restrict__ y, float* __restrict__ out, int N, int HW, int C, long long total) {
   // destination order (n, c, p): coalesced writes
@@ -1097,4 +1115,28 @@ extern "C" int stfb_unpad_wgrad(float* dW, const float* src, int Cout, int Cin, 
   const long long total = (long long)Cout * Cin * kh * kw;
   unpad_wgrad_kernel<<<grid_for(total), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(dW, src, Cout, Cin, kh * kw, ld_src);
   return post_launch("unpad_wgrad");
+}
+
+extern "C" int stfb_pack_series_maps(const float* x, const float* maps, void* y, int B, int T_, int Cx, int Cm, int H, int W,
+                                     int dtype, void* stream) {
+  STFB_REQUIRE(x && maps && y && B >= 0 && T_ > 0 && Cx > 0 && Cm > 0 && H > 0 && W > 0 && DT_OK(dtype), "pack_series_maps: bad arguments");
+  STFB_DEVICE_OR_RETURN();
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  const long long total = (long long)B * T_ * (Cx + Cm) * H * W;
+  if (total == 0) return STFB_OK;
+  DISPATCH_T(dtype, { pack_series_maps_kernel<T><<<grid_for(total), 256, 0, s>>>(x, maps, (T*)y, B, T_, Cx, Cm, H, W, total); });
+  return post_launch("pack_series_maps");
+}
+
+extern "C" int stfb_repeat(const void* src, void* dst, size_t bytes, int times, void* stream) {
+  STFB_REQUIRE(src && dst && times >= 0, "repeat: bad arguments");
+  STFB_DEVICE_OR_RETURN();
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  for (int t = 0; t < times; ++t) {
+    if (cudaMemcpyAsync(static_cast<char*>(dst) + (size_t)t * bytes, src, bytes, cudaMemcpyDeviceToDevice, s) != cudaSuccess) {
+      set_error("repeat: cudaMemcpyAsync failed: %s", cudaGetErrorString(cudaGetLastError()));
+      return STFB_ECUDA;
+    }
+  }
+  return STFB_OK;
 }

@@ -14,7 +14,7 @@ from ._lib import BF16, CONV_FWD, CONV_TRANSPOSED, F32, IMPL_AUTO, IMPL_SIMT, IM
 
 __all__ = ["dt_code", "conv2d", "conv2d_wgrad", "pack_weight", "bn_stats", "bn_finalize_train", "bn_fold_eval",
            "bn_apply", "bn_bwd", "colsum", "maxpool_fwd", "maxpool_bwd", "maxpool_fwd_idx", "maxpool_bwd_idx", "bilinear_fwd", "bilinear_bwd",
-           "tcgen05_ok", "im2col_small", "unpad_wgrad", "lstm_cell_fwd", "lstm_cell_bwd", "pack_series", "nhwc_to_nchw", "nchw_to_nhwc", "add_", "cast",
+           "tcgen05_ok", "im2col_small", "unpad_wgrad", "lstm_cell_fwd", "lstm_cell_bwd", "pack_series", "pack_series_maps", "repeat_batch", "nhwc_to_nchw", "nchw_to_nhwc", "add_", "cast",
            "ce_dice_fwd", "ce_dice_bwd", "CONV_FWD", "CONV_TRANSPOSED", "IMPL_AUTO", "IMPL_SIMT", "IMPL_TCGEN05"]
 
 _DT = {torch.float32: F32, torch.bfloat16: BF16}
@@ -420,6 +420,24 @@ def pack_series(x, dtype):
     y = torch.empty((T * B, H, W, C_), dtype=dtype, device=x.device)
     check(_lib.load().stfb_pack_series(_p(x), _p(y), B, T, C_, H, W, dt_code(dtype), _stream()), "pack_series")
     return y
+
+
+def pack_series_maps(x, maps, dtype):
+    """x [B,T,Cx,H,W] + maps [B,Cm,H,W] (fp32) -> [T*B, H, W, Cx+Cm] `dtype`, time-major."""
+    _need_cuda(x, maps)
+    B, T, Cx, H, W = x.shape
+    Cm = maps.shape[1]
+    y = torch.empty((T * B, H, W, Cx + Cm), dtype=dtype, device=x.device)
+    check(_lib.load().stfb_pack_series_maps(_p(x), _p(maps), _p(y), B, T, Cx, Cm, H, W, dt_code(dtype), _stream()),
+          "pack_series_maps")
+    return y
+
+
+def repeat_batch(src, times):
+    """[B, ...] -> [times*B, ...]: `times` back-to-back copies (per-sample maps repeated for every time step)."""
+    dst = torch.empty((times * src.shape[0],) + tuple(src.shape[1:]), dtype=src.dtype, device=src.device)
+    check(_lib.load().stfb_repeat(_p(src), _p(dst), src.numel() * src.element_size(), times, _stream()), "repeat")
+    return dst
 
 
 def nhwc_to_nchw(y):

@@ -98,13 +98,13 @@ class STFLSTMUNet(B200Module):
             T = total - self.pk_channels
             if T < 1 or C != 1:
                 raise ValueError("use_pk_maps needs T + pk_channels steps of single-channel images")
-            pk = engine.Var(ops.nchw_to_nhwc(x[:, T:, 0].contiguous(), ex.dtype), needs_grad=False)   # [B,H,W,pk]
-            x = x[:, :T].contiguous()
+            maps = x[:, T:, 0].contiguous()                                   # [B, pk, H, W] (reference :149-153)
+            series = x[:, :T].contiguous()
+            pk = ops.nchw_to_nhwc(maps, ex.dtype)                             # [B, H, W, pk], resized per scale below
+            xin = engine.Var(ops.pack_series_maps(series, maps, ex.dtype), needs_grad=False)   # cat([x_t, pk]) for all t
         else:
             T = total
-        xin = engine.Var(ops.pack_series(x, ex.dtype), needs_grad=False)          # [T*B, H, W, C] time-major
-        if pk is not None:
-            xin = self._concat_pk(ex, xin, pk, T)
+            xin = engine.Var(ops.pack_series(x, ex.dtype), needs_grad=False)  # [T*B, H, W, C] time-major
         s = ex.conv_bn(xin, "conv1.weight", "bn1", k=7, stride=2, pad=3, relu=True, G=T)
         e = ex.maxpool(s, 3, 2, 1)
         feats = []
@@ -129,9 +129,10 @@ class STFLSTMUNet(B200Module):
         d = self._residual_block(ex, d, "final_res")
         return ex.conv(d, "final.weight", k=1, bname="final.bias", y_dtype=__import__("torch").float32)
 
-    # -- PK-map branch (use_pk_maps=True; reference :146-156, :172-174, :189-200) --------------------
-    def _concat_pk(self, ex, xin, pk, T):
-        raise NotImplementedError("use_pk_maps=True is not built yet (SURVEY.md section 8(f) rank 2)")
-
+    # -- PK-map branch (use_pk_maps=True; reference :189-200) -----------------------------------------
     def _pk_fuse(self, ex, f, pk, k, T):
-        raise NotImplementedError("use_pk_maps=True is not built yet (SURVEY.md section 8(f) rank 2)")
+        """e_k = pk_fusion_k(cat([e_k, bilinear(pk_maps -> e_k size, align_corners=True)])) for every time step."""
+        h, w = f.data.shape[1], f.data.shape[2]
+        pk_k = ops.bilinear_fwd(pk, h, w)                                      # [B, h, w, pk]
+        pk_t = engine.Var(ops.repeat_batch(pk_k, T), needs_grad=False)         # same maps at every time step
+        return ex.conv(f, f"pk_fusion{k}.weight", k=1, bname=f"pk_fusion{k}.bias", x2=pk_t)

@@ -272,3 +272,98 @@ def test_cpu_input_raises():
     m = S.UNet(1, 2, 8).to(DEV)
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         m(torch.zeros(1, 1, 32, 32))
+
+
+def test_stf_pk_maps_eval_fp32_vs_golden(golden_dir):
+    """use_pk_maps=True (reference :146-156, :172-174, :189-200): 4-channel stem + bilinear PK maps fused at 4 scales."""
+    g = np.load(os.path.join(golden_dir, "stf_pk_eval_b1_t2_64.npz"))
+    x, _ = W.synthetic_dce_batch(1, 5, 64, 64, seed=13)
+    sd = W.make_state_dict(W.stf_param_spec(1, 2, use_pk_maps=True), seed=0)
+    m = load_model(S.STFLSTMUNet(1, 2, 2, use_pk_maps=True), sd).eval()
+    with torch.no_grad():
+        y = m(x.to(DEV))["out"]
+    assert y.shape == (1, 2, 32, 32)
+    assert rel(y, torch.from_numpy(g["logits"])) < 1e-4
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_stf_pk_maps_train_vs_oracle(dtype):
+    B, T = 2, 3
+    x, t = W.synthetic_dce_batch(B, T + 3, 64, 64, seed=61)
+    sd = W.make_state_dict(W.stf_param_spec(1, 2, use_pk_maps=True), seed=0)
+    if dtype == torch.bfloat16:      # bf16 bars need BatchNorm statistics that match the data: a few fp32 steps first
+        m0 = load_model(S.STFLSTMUNet(1, 2, T, use_pk_maps=True), sd)
+        opt = torch.optim.AdamW(m0.parameters(), lr=1e-3)
+        for _ in range(8):
+            loss = S.criterion(m0(x.to(DEV)), t.to(DEV))
+            opt.zero_grad()
+            loss.backward()
+            opt.step()
+        sd = {k: v.detach().cpu().clone() for k, v in m0.state_dict().items()}
+    sd_dev = {k: v.to(DEV) for k, v in sd.items()}
+    ref_logits, ref_loss, ref_grads, _ = O.loss_and_grads(sd_dev, x.to(DEV), t.to(DEV), model="stf", train=True,
+                                                          use_pk_maps=True)
+    m = load_model(S.STFLSTMUNet(1, 2, T, use_pk_maps=True), sd)
+    m.train()
+    with torch.autocast("cuda", dtype=torch.bfloat16, enabled=dtype == torch.bfloat16):
+        out = m(x.to(DEV))["out"]
+        loss = S.criterion({"out": out}, t.to(DEV))
+    loss.backward()
+    r = rel(out, ref_logits)
+    print(f"stf pk-maps train {dtype}: rel={r:.3e} loss {loss.item():.5f} vs {ref_loss.item():.5f}")
+    assert r < (1e-4 if dtype == torch.float32 else 2e-2)
+    # bf16 gradients of the deepest layer (conv1, after 34 layers of bf16 backward) carry the most rounding noise
+    for name, tol16 in (("pk_fusion1.weight", 1.5e-1), ("pk_fusion4.bias", 1.5e-1), ("conv1.weight", 3e-1)):
+        gm, gr = dict(m.named_parameters())[name].grad, ref_grads[name]
+        assert rel(gm, gr) < (2e-2 if dtype == torch.float32 else tol16), name
+
+
+def test_graphed_step_matches_eager():
+    """CUDA-graph replay of fwd + loss + bwd gives the eager step's loss and gradients, step after step."""
+    from stf_unet_b200.graph import GraphedStep
+    torch.manual_seed(0)
+    x, t = W.synthetic_dce_batch(2, 3, 64, 64, seed=71)
+    x2, t2 = W.synthetic_dce_batch(2, 3, 64, 64, seed=72)
+    sd = W.make_state_dict(W.stf_param_spec(1, 2), seed=0)
+    a = load_model(S.STFLSTMUNet(1, 2, 3), sd)
+    b = load_model(S.STFLSTMUNet(1, 2, 3), sd)
+    gs = GraphedStep(a, S.criterion, x.to(DEV), t.to(DEV), warmup=2)
+    b.load_state_dict(a.state_dict())          # warm-up + capture advanced a's BatchNorm buffers
+    for xb, tb in ((x, t), (x2, t2)):
+        la = gs(xb.to(DEV), tb.to(DEV))
+        b.train()
+        for p in b.parameters():
+            p.grad = None
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            lb = S.criterion(b(xb.to(DEV)), tb.to(DEV))
+        lb.backward()
+        assert abs(la.item() - lb.item()) < 1e-5 * max(1.0, abs(lb.item()))
+        for (n, pa), (_, pb) in zip(a.named_parameters(), b.named_parameters()):
+            assert rel(pa.grad, pb.grad) < 1e-3, n
+    assert int(a.bn1.num_batches_tracked) == int(b.bn1.num_batches_tracked)
+    assert gs.launches_per_replay > 100
+
+
+def test_unet_bf16_train_vs_oracle():
+    x, t = W.synthetic_dce_batch(4, 8, 64, 64, seed=81, half_res_target=False)
+    xin = x.view(4, 8, 64, 64).to(DEV)
+    torch.manual_seed(1)
+    m0 = S.UNet(8, 2, 32).to(DEV)
+    opt = torch.optim.AdamW(m0.parameters(), lr=1e-3)
+    for _ in range(30):
+        loss = S.criterion(m0(xin), t.to(DEV))
+        opt.zero_grad()
+        loss.backward()
+        opt.step()
+    sd_dev = {k: v.detach().clone() for k, v in m0.state_dict().items()}
+    ref_logits, ref_loss, ref_grads, _ = O.loss_and_grads(sd_dev, xin, t.to(DEV), model="unet", train=True)
+    m = S.UNet(8, 2, 32).to(DEV)
+    m.load_state_dict(sd_dev)
+    m.train()
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        out = m(xin)["out"]
+        loss = S.criterion({"out": out}, t.to(DEV))
+    loss.backward()
+    r, a = rel(out, ref_logits), argmax_agree(out, ref_logits)
+    print(f"unet bf16 train: rel={r:.3e} argmax={a:.5f}")
+    assert r < 2e-2 and a >= 0.995
