@@ -110,7 +110,10 @@ int stfb_pack_weight(const float* w, void* wp, int D0, int D1, int kh, int kw, i
  * tcgen05 family, row stride ldw = kh*kw*K).  flip = 1 mirrors the taps (ky,kx) -> (kh-1-ky, kw-1-kx), which turns the
  * dgrad of a stride-1 "same" convolution into a forward convolution over dy. */
 int stfb_pack_weight_ex(const float* w, void* wp, int D0, int D1, int kh, int kw, int k_is_dim1, int n_major, int flip,
-                        int ld /* n_major row stride, 0 = dense; the caller zero-fills any padding */, int dtype, void* stream);
+                        int ld /* n_major row stride, 0 = dense; the caller zero-fills any padding */,
+                        int gate_c /* > 0: LSTM [4C][C] matrix, rows re-ordered so that each 256-row block holds gates
+                                      i,f,g,o of the same 64 hidden units (for stfb_lstm_step_fused) */,
+                        int dtype, void* stream);
 
 /* Batched form: one launch packs every weight of a step.  `jobs_dev` is a DEVICE array (uploaded once per model);
  * job j covers flat element range [start_j, start_{j+1}) of `total`; fields as in stfb_pack_weight_ex. */
@@ -193,6 +196,12 @@ int stfb_bilinear_bwd(const void* dy, float* dx, int N, int H, int W, int C, int
  * src/stf_lstm_unet.py:124-127, :216-242).  gates = pre-activations [R][4C] fp32 in PyTorch order i,f,g,o
  * (already containing W_ih x + b_ih + W_hh h + b_hh, produced by stfb_conv2d as 1x1 GEMMs).
  * ---------------------------------------------------------------------------------------------- */
+/* One recurrent step with the cell fused into the tcgen05 GEMM epilogue ("gates never leave the SM"): the accumulator
+ * h_prev W_hh^T stays in TMEM, the epilogue adds gates_x (fp32 [rows][4C], i,f,g,o: W_ih x_t + b_ih + b_hh), applies the
+ * gate non-linearities and writes c_out (fp32), h_out (bf16) and, for training, the post-activation gates (bf16).
+ * bf16 only; C % 64 == 0; w_hh_il = stfb_pack_weight_ex(W_hh, n_major = 1, gate_c = C); h_out must not alias h_prev. */
+int stfb_lstm_step_fused(const void* h_prev, const void* w_hh_il, const float* gates_x, const float* c_prev, float* c_out,
+                         void* h_out, void* acts, int N, int H, int W, int C, void* stream);
 /* c_prev may be NULL (t = 0, zero state).  acts (dtype, [R][4C]) may be NULL in eval mode.
  * c_out fp32 [R][C]; h_out dtype [R][C]. */
 int stfb_lstm_cell_fwd(const float* gates, const float* c_prev, void* acts, float* c_out, void* h_out, long long R,

@@ -31,7 +31,8 @@ _SIGS = {
     "stfb_conv2d_wgrad": [_vp, _vp, _vp] + [_i] * 15 + [_vp, C.c_size_t, _vp],
     "stfb_conv2d_wgrad_tcgen05_supported": [_vp, _vp] + [_i] * 12,
     "stfb_pack_weight": [_vp, _vp, _i, _i, _i, _i, _i, _i, _vp],
-    "stfb_pack_weight_ex": [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp],
+    "stfb_pack_weight_ex": [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp],
+    "stfb_lstm_step_fused": [_vp] * 7 + [_i, _i, _i, _i, _vp],
     "stfb_pack_weights_batched": [_vp, _i, _ll, _i, _vp],
     "stfb_im2col_small": [_vp, _vp] + [_i] * 10 + [_vp],
     "stfb_unpad_wgrad": [_vp, _vp, _i, _i, _i, _i, _i, _vp],

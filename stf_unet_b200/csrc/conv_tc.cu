@@ -43,6 +43,12 @@ struct TcArgs {
   int tiles_w, tiles_h, tiles_n;
   int num_tiles;         // phases * tiles_n * tiles_h * tiles_w * (Cout / BN)
   int relu;
+  // fused LSTM cell epilogue (EPI == 1): accumulator = h_{t-1} W_hh^T with gate-interleaved columns
+  const float* gates_x;  // [rows][4*Chid] fp32, PyTorch order i,f,g,o: W_ih x_t + b_ih + b_hh
+  const float* c_prev;   // [rows][Chid] fp32
+  float* c_out;          // [rows][Chid] fp32
+  void* acts;            // [rows][4*Chid] bf16 post-activation gates (NULL in eval)
+  int Chid;
   int debug;             // STFB_TC_DEBUG: 1 = no MMAs (TMA pipeline only), 2 = no TMA (MMA issue only); timing experiments
   int ntaps[4];
   signed char dh[4][9], dw[4][9], ktap[4][9];
@@ -94,7 +100,23 @@ __device__ __forceinline__ TileCoord decode_tile(const TcArgs& a, int tile, int 
 // Persistent: one CTA per SM walks tiles `blockIdx.x, +gridDim.x, ...`.  The TMA ring keeps streaming across tile
 // boundaries and the accumulator is double-buffered in TMEM (2 x BN columns), so the epilogue of tile i overlaps the
 // main loop of tile i+1 and the per-tile prologue (barrier init, TMEM alloc, first TMA round trip) is paid once.
-template <int BN, int STAGES, typename TO, int BK>
+__device__ __forceinline__ void tmem_ld_x16(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ float fast_sigmoid(float x) { return __fdividef(1.f, 1.f + __expf(-x)); }
+__device__ __forceinline__ float fast_tanh(float x) {
+  float y;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+template <int BN, int STAGES, typename TO, int BK, int EPI>
 __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_constant__ CUtensorMap tmA,
                                                                  const __grid_constant__ CUtensorMap tmA2,
                                                                  const __grid_constant__ CUtensorMap tmB, const TcArgs a) {
@@ -214,6 +236,66 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN);
+      if constexpr (EPI == 1) {
+        // ===== fused LSTM cell: this 256-column tile = gates i,f,g,o (64 columns each) of hidden units [n0/4, n0/4 + 64)
+        static_assert(EPI != 1 || BN == 256, "LSTM epilogue needs the 4 x 64 gate-interleaved tile");
+        const int C = a.Chid;
+        const int u_base = t.n0 / 4;
+        const long long prow = ((long long)on * a.Hout + oh) * a.Wout + ow;       // pixel row
+        const float* gx = a.gates_x + prow * 4 * C;
+        const float* cp = a.c_prev ? a.c_prev + prow * C : nullptr;
+        float* co = a.c_out + prow * C;
+        __nv_bfloat16* ho = reinterpret_cast<__nv_bfloat16*>(a.y) + prow * C;
+        __nv_bfloat16* ac = a.acts ? reinterpret_cast<__nv_bfloat16*>(a.acts) + prow * 4 * C : nullptr;
+#pragma unroll 1
+        for (int u0 = 0; u0 < 64; u0 += 16) {
+          uint32_t ri[16], rf[16], rg[16], ro[16];
+          tmem_ld_x16(taddr + u0, ri);
+          tmem_ld_x16(taddr + 64 + u0, rf);
+          tmem_ld_x16(taddr + 128 + u0, rg);
+          tmem_ld_x16(taddr + 192 + u0, ro);
+          tmem_ld_wait();
+          if (u0 + 16 >= 64) {
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+          }
+          if (valid) {
+            const int u = u_base + u0;
+            float hv[16], cv[16], ai[16], af[16], ag[16], ao[16];
+#pragma unroll
+            for (int e = 0; e < 16; e += 4) {
+              const float4 xi = *reinterpret_cast<const float4*>(gx + u + e);
+              const float4 xf = *reinterpret_cast<const float4*>(gx + C + u + e);
+              const float4 xg = *reinterpret_cast<const float4*>(gx + 2 * C + u + e);
+              const float4 xo = *reinterpret_cast<const float4*>(gx + 3 * C + u + e);
+              float4 cc = make_float4(0.f, 0.f, 0.f, 0.f);
+              if (cp) cc = *reinterpret_cast<const float4*>(cp + u + e);
+              const float pi[4] = {xi.x, xi.y, xi.z, xi.w}, pf[4] = {xf.x, xf.y, xf.z, xf.w};
+              const float pg[4] = {xg.x, xg.y, xg.z, xg.w}, po[4] = {xo.x, xo.y, xo.z, xo.w};
+              const float pc[4] = {cc.x, cc.y, cc.z, cc.w};
+#pragma unroll
+              for (int z = 0; z < 4; ++z) {
+                ai[e + z] = fast_sigmoid(__uint_as_float(ri[e + z]) + pi[z]);
+                af[e + z] = fast_sigmoid(__uint_as_float(rf[e + z]) + pf[z]);
+                ag[e + z] = fast_tanh(__uint_as_float(rg[e + z]) + pg[z]);
+                ao[e + z] = fast_sigmoid(__uint_as_float(ro[e + z]) + po[z]);
+                cv[e + z] = af[e + z] * pc[z] + ai[e + z] * ag[e + z];
+                hv[e + z] = ao[e + z] * fast_tanh(cv[e + z]);
+              }
+              *reinterpret_cast<float4*>(co + u + e) = make_float4(cv[e], cv[e + 1], cv[e + 2], cv[e + 3]);
+            }
+            st8(ho + u, hv);
+            st8(ho + u + 8, hv + 8);
+            if (ac) {
+              st8(ac + u, ai); st8(ac + u + 8, ai + 8);
+              st8(ac + C + u, af); st8(ac + C + u + 8, af + 8);
+              st8(ac + 2 * C + u, ag); st8(ac + 2 * C + u + 8, ag + 8);
+              st8(ac + 3 * C + u, ao); st8(ac + 3 * C + u + 8, ao + 8);
+            }
+          }
+        }
+      } else {
 #pragma unroll 1
       for (int c0 = 0; c0 < BN; c0 += 32) {
         uint32_t r[32];
@@ -261,6 +343,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
 #pragma unroll
           for (int j = 0; j < 32; j += 8) st8(yp + c0 + j, v + j);
         }
+      }
       }
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
@@ -344,19 +427,19 @@ bool encode_nhwc_map(EncodeTiledFn enc, CUtensorMap* tm, const void* base, int N
   return encode_nhwc_map_strided(enc, tm, base, N, H, W, C, TW, TH, TN, 1, 64);
 }
 
-template <int BN, int STAGES, typename TO, int BK>
+template <int BN, int STAGES, typename TO, int BK, int EPI = 0>
 static int launch_tc(const CUtensorMap& tA, const CUtensorMap& tA2, const CUtensorMap& tB, const TcArgs& a, dim3 grid,
                      cudaStream_t st) {
   constexpr int smem = tc_smem_bytes<BN, STAGES, BK>();
   static bool configured = false;
   if (!configured) {
-    if (cudaFuncSetAttribute(conv_tc_kernel<BN, STAGES, TO, BK>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) {
+    if (cudaFuncSetAttribute(conv_tc_kernel<BN, STAGES, TO, BK, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) {
       set_error("conv2d(tcgen05): cannot reserve %d bytes of shared memory: %s", smem, cudaGetErrorString(cudaGetLastError()));
       return STFB_ECUDA;
     }
     configured = true;
   }
-  conv_tc_kernel<BN, STAGES, TO, BK><<<grid, TC_THREADS, smem, st>>>(tA, tA2, tB, a);
+  conv_tc_kernel<BN, STAGES, TO, BK, EPI><<<grid, TC_THREADS, smem, st>>>(tA, tA2, tB, a);
   return post_launch("conv2d(tcgen05)");
 }
 
@@ -460,6 +543,43 @@ int conv2d_tcgen05(const stfb_conv_params* p, cudaStream_t st) {
 #undef TC_LAUNCH
   set_error("conv2d(tcgen05): no tile for Cout=%d", p->Cout);
   return STFB_ENOTSUP;
+}
+
+// One recurrent LSTM step on the tensor cores with the cell update fused into the epilogue:
+//   gates = h_prev W_hh^T (TMEM) + gates_x ; c = sig(f) c_prev + sig(i) tanh(g) ; h = sig(o) tanh(c)
+// w_hh_il: W_hh packed [4C][C] K-major with gate-interleaved rows (stfb_pack_weight_ex gate_c = C).
+int lstm_step_tcgen05(const void* h_prev, const void* w_hh_il, const float* gates_x, const float* c_prev, float* c_out,
+                      void* h_out, void* acts, int N, int H, int W, int C, cudaStream_t st) {
+  EncodeTiledFn enc = get_tensormap_encoder();
+  if (!enc) { set_error("lstm_step(tcgen05): cuTensorMapEncodeTiled not available"); return STFB_ECUDA; }
+  if ((long long)N * H * W == 0) return STFB_OK;
+  TcArgs a{};
+  a.y = h_out; a.gates_x = gates_x; a.c_prev = c_prev; a.c_out = c_out; a.acts = acts; a.Chid = C;
+  a.N = N; a.Hout = H; a.Wout = W; a.Cout = 4 * C; a.C1 = C; a.C2 = 0;
+  a.a_scale = 1; a.o_scale = 1; a.nphase_w = 1;
+  a.ntaps[0] = 1; a.dh[0][0] = 0; a.dw[0][0] = 0; a.ktap[0][0] = 0;
+  pick_patch(H, W, a.TW, a.TH, a.TN);
+  a.tiles_w = (W + a.TW - 1) / a.TW;
+  a.tiles_h = (H + a.TH - 1) / a.TH;
+  a.tiles_n = (N + a.TN - 1) / a.TN;
+  a.num_tiles = a.tiles_n * a.tiles_h * a.tiles_w * (4 * C / 256);
+  CUtensorMap tA, tB;
+  if (!encode_nhwc_map_strided(enc, &tA, h_prev, N, H, W, C, a.TW, a.TH, a.TN, 1, 64)) {
+    set_error("lstm_step(tcgen05): tensor map (h) failed"); return STFB_ECUDA;
+  }
+  {
+    cuuint64_t dims[2] = {(cuuint64_t)C, (cuuint64_t)(4 * C)};
+    cuuint64_t strides[1] = {(cuuint64_t)C * 2};
+    cuuint32_t box[2] = {64, 256};
+    cuuint32_t estr[2] = {1, 1};
+    if (enc(&tB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(w_hh_il), dims, strides, box, estr,
+            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS) {
+      set_error("lstm_step(tcgen05): tensor map (W_hh) failed"); return STFB_ECUDA;
+    }
+  }
+  dim3 grid((unsigned)(a.num_tiles < num_sms() ? a.num_tiles : num_sms()));
+  return launch_tc<256, 4, __nv_bfloat16, 64, 1>(tA, tA, tB, a, grid, st);
 }
 
 }  // namespace stfb

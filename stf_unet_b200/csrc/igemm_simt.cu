@@ -434,7 +434,7 @@ int conv2d_wgrad_simt(const WgradArgs& a0, int dtype, cudaStream_t st) {
 // =================================================================================================
 template <typename T>
 __global__ void pack_weight_kernel(const float* __restrict__ w, T* __restrict__ wp, int D0, int D1, int khw,
-                                   int k_is_dim1, int n_major, int flip, int ld) {
+                                   int k_is_dim1, int n_major, int flip, int ld, int gate_c) {
   const long long total = (long long)D0 * D1 * khw;
   const int Kc = k_is_dim1 ? D1 : D0, Nc = k_is_dim1 ? D0 : D1;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -452,8 +452,12 @@ __global__ void pack_weight_kernel(const float* __restrict__ w, T* __restrict__ 
     }
     const int d0 = k_is_dim1 ? n : k, d1 = k_is_dim1 ? k : n;
     const int stap = flip ? (khw - 1 - tap) : tap;   // spatial flip (ky,kx) -> (kh-1-ky, kw-1-kx)
-    // n_major rows may be padded to `ld` elements (K padded to the 64-wide k-block; the caller zero-fills the pad)
-    const long long di = n_major ? (long long)n * ld + (long long)tap * Kc + k : i;
+    // n_major rows may be padded to `ld` elements (K padded to the 64-wide k-block; the caller zero-fills the pad).
+    // gate_c > 0: LSTM gate interleave -- source row gate*C + u lands at (u/64)*256 + gate*64 + u%64, so one 256-column
+    // GEMM tile holds i,f,g,o of the same 64 hidden units.
+    int nd = n;
+    if (gate_c > 0) { const int gate = n / gate_c, u = n - gate * gate_c; nd = (u / 64) * 256 + gate * 64 + (u % 64); }
+    const long long di = n_major ? (long long)nd * ld + (long long)tap * Kc + k : i;
     st1(wp + di, w[((long long)d0 * D1 + d1) * khw + stap]);
   }
 }
@@ -484,7 +488,9 @@ __global__ void pack_weights_batched_kernel(const stfb_pack_job* __restrict__ jo
     }
     const int d0 = jb.k_is_dim1 ? n : k, d1 = jb.k_is_dim1 ? k : n;
     const int stap = jb.flip ? (jb.khw - 1 - tap) : tap;
-    const long long di = jb.n_major ? (long long)n * jb.ld + (long long)tap * Kc + k : i;
+    int nd = n;
+    if (jb.pad_ > 0) { const int gate = n / jb.pad_, u = n - gate * jb.pad_; nd = (u / 64) * 256 + gate * 64 + (u % 64); }
+    const long long di = jb.n_major ? (long long)nd * jb.ld + (long long)tap * Kc + k : i;
     st1(reinterpret_cast<T*>(jb.dst) + di, jb.src[((long long)d0 * jb.D1 + d1) * jb.khw + stap]);
   }
 }
@@ -514,6 +520,8 @@ int wgrad_tcgen05(const void* P, const void* G, const void* G2, float* dW, int N
                   int C1, int C2, int cg_off, int cg_total, int kh, int kw, int stride, int pad, float* ws, size_t ws_bytes,
                   cudaStream_t st);
 size_t wgrad_tcgen05_workspace_bytes(int N, int H, int W, int Cp, int Cg, int kh, int kw);
+int lstm_step_tcgen05(const void* h_prev, const void* w_hh_il, const float* gates_x, const float* c_prev, float* c_out,
+                      void* h_out, void* acts, int N, int H, int W, int C, cudaStream_t st);
 }
 
 static int validate_conv(const stfb_conv_params* p) {
@@ -599,12 +607,14 @@ extern "C" int stfb_conv2d_wgrad(const void* P, const void* G, float* dW, int N,
 }
 
 extern "C" int stfb_pack_weight_ex(const float* w, void* wp, int D0, int D1, int kh, int kw, int k_is_dim1, int n_major,
-                                   int flip, int ld, int dtype, void* stream) {
+                                   int flip, int ld, int gate_c, int dtype, void* stream) {
   STFB_REQUIRE(w && wp && D0 > 0 && D1 > 0 && kh > 0 && kw > 0, "pack_weight: bad arguments");
   {
     const int Kc_ = k_is_dim1 ? D1 : D0;
     if (ld <= 0) ld = kh * kw * Kc_;
     STFB_REQUIRE(!n_major || ld >= kh * kw * Kc_, "pack_weight: ld (%d) smaller than the packed row (%d)", ld, kh * kw * Kc_);
+    STFB_REQUIRE(gate_c == 0 || (n_major && k_is_dim1 && gate_c % 64 == 0 && D0 == 4 * gate_c),
+                 "pack_weight: gate interleave needs an n_major [4C][C] LSTM matrix with C %% 64 == 0");
   }
   STFB_REQUIRE(dtype == STFB_F32 || dtype == STFB_BF16, "pack_weight: bad dtype");
   STFB_DEVICE_OR_RETURN();
@@ -613,13 +623,26 @@ extern "C" int stfb_pack_weight_ex(const float* w, void* wp, int D0, int D1, int
   int blocks = ceil_div(total, 256);
   if (blocks > 8 * num_sms()) blocks = 8 * num_sms();
   if (dtype == STFB_F32)
-    pack_weight_kernel<float><<<blocks, 256, 0, s>>>(w, reinterpret_cast<float*>(wp), D0, D1, kh * kw, k_is_dim1, n_major, flip, ld);
+    pack_weight_kernel<float><<<blocks, 256, 0, s>>>(w, reinterpret_cast<float*>(wp), D0, D1, kh * kw, k_is_dim1, n_major, flip, ld, gate_c);
   else
-    pack_weight_kernel<__nv_bfloat16><<<blocks, 256, 0, s>>>(w, reinterpret_cast<__nv_bfloat16*>(wp), D0, D1, kh * kw, k_is_dim1, n_major, flip, ld);
+    pack_weight_kernel<__nv_bfloat16><<<blocks, 256, 0, s>>>(w, reinterpret_cast<__nv_bfloat16*>(wp), D0, D1, kh * kw, k_is_dim1, n_major, flip, ld, gate_c);
   return post_launch("pack_weight");
 }
 
 extern "C" int stfb_pack_weight(const float* w, void* wp, int D0, int D1, int kh, int kw, int k_is_dim1, int dtype,
                                 void* stream) {
-  return stfb_pack_weight_ex(w, wp, D0, D1, kh, kw, k_is_dim1, 0, 0, 0, dtype, stream);
+  return stfb_pack_weight_ex(w, wp, D0, D1, kh, kw, k_is_dim1, 0, 0, 0, 0, dtype, stream);
+}
+
+extern "C" int stfb_lstm_step_fused(const void* h_prev, const void* w_hh_il, const float* gates_x, const float* c_prev,
+                                    float* c_out, void* h_out, void* acts, int N, int H, int W, int C, void* stream) {
+  STFB_REQUIRE(h_prev && w_hh_il && gates_x && c_out && h_out && N >= 0 && H > 0 && W > 0, "lstm_step_fused: bad arguments");
+  STFB_REQUIRE(C > 0 && C % 64 == 0, "lstm_step_fused: hidden size must be a multiple of 64 (got %d)", C);
+  STFB_REQUIRE(h_prev != h_out, "lstm_step_fused: h_out must not alias h_prev (other tiles still read it)");
+  auto al = [](const void* q) { return q == nullptr || (reinterpret_cast<uintptr_t>(q) % 16) == 0; };
+  STFB_REQUIRE(al(h_prev) && al(w_hh_il) && al(gates_x) && al(c_prev) && al(c_out) && al(h_out) && al(acts),
+               "lstm_step_fused: pointers must be 16-byte aligned");
+  STFB_DEVICE_OR_RETURN();
+  return stfb::lstm_step_tcgen05(h_prev, w_hh_il, gates_x, c_prev, c_out, h_out, acts, N, H, W, C,
+                                 reinterpret_cast<cudaStream_t>(stream));
 }

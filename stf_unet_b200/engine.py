@@ -19,6 +19,7 @@ BN_MOMENTUM = 0.1
 #: kill switch for A/B measurements (STFB_NO_TCGEN05=1 keeps every conv on the SIMT family)
 import os as _os
 USE_TCGEN05 = _os.environ.get("STFB_NO_TCGEN05", "0") != "1"
+USE_FUSED_LSTM = _os.environ.get("STFB_NO_FUSED_LSTM", "0") != "1"
 
 
 class Var:
@@ -62,11 +63,12 @@ class Executor:
         self._new_pack_keys = []      # packs this forward needed that the module's PackPlan did not hold
 
     # ---------------------------------------------------------------------------------------------
-    def packed(self, name, k_is_dim1, n_major=False, flip=False, kpad=None):
-        key = (name, bool(k_is_dim1), bool(n_major), bool(flip), kpad)
+    def packed(self, name, k_is_dim1, n_major=False, flip=False, kpad=None, gate_c=0):
+        key = (name, bool(k_is_dim1), bool(n_major), bool(flip), kpad, int(gate_c))
         wp = self._packed.get(key)
         if wp is None:
-            wp = ops.pack_weight(self.params[name], k_is_dim1, self.dtype, n_major=n_major, flip=flip, kpad=kpad)
+            wp = ops.pack_weight(self.params[name], k_is_dim1, self.dtype, n_major=n_major, flip=flip, kpad=kpad,
+                                 gate_c=gate_c)
             self._packed[key] = wp
             self._new_pack_keys.append(key)
         return wp
@@ -277,10 +279,16 @@ class Executor:
         acts = torch.empty((T, R, 4 * C), dtype=self.dtype, device=dev) if keep else None
         cs = torch.empty((T if keep else 2, R, C), dtype=torch.float32, device=dev)
         hs = torch.empty((T if keep else 2, B, h, w, C), dtype=self.dtype, device=dev)
-        whh_p = self.packed(whh, True, n_major=tc)
+        fused = tc and C % 64 == 0 and USE_FUSED_LSTM
+        whh_p = self.packed(whh, True, n_major=tc, gate_c=C if fused else 0)
         for t in range(T):
             cur = t if keep else t % 2
             prev = (t - 1) if keep else (t - 1) % 2
+            if t > 0 and fused:
+                # recurrent GEMM + cell update in one kernel: the gate pre-activations never leave the SM
+                ops.lstm_step_fused(hs[prev], whh_p, gates[t], cs[prev], cs[cur], hs[cur],
+                                    acts[t].view(B, h, w, 4 * C) if keep else None)
+                continue
             if t > 0:  # gates_t += h_{t-1} W_hh^T   (in place through the residual epilogue)
                 ops.conv2d(hs[prev], whh_p, 4 * C, 1, 1, 0, residual=gates[t], out=gates[t], y_dtype=torch.float32,
                            impl=impl)

@@ -14,7 +14,7 @@ from ._lib import BF16, CONV_FWD, CONV_TRANSPOSED, F32, IMPL_AUTO, IMPL_SIMT, IM
 
 __all__ = ["dt_code", "conv2d", "conv2d_wgrad", "pack_weight", "bn_stats", "bn_finalize_train", "bn_fold_eval",
            "bn_apply", "bn_bwd", "colsum", "maxpool_fwd", "maxpool_bwd", "maxpool_fwd_idx", "maxpool_bwd_idx", "bilinear_fwd", "bilinear_bwd",
-           "tcgen05_ok", "im2col_small", "unpad_wgrad", "lstm_cell_fwd", "lstm_cell_bwd", "pack_series", "pack_series_maps", "repeat_batch", "nhwc_to_nchw", "nchw_to_nhwc", "add_", "cast",
+           "tcgen05_ok", "im2col_small", "unpad_wgrad", "lstm_step_fused", "lstm_cell_fwd", "lstm_cell_bwd", "pack_series", "pack_series_maps", "repeat_batch", "nhwc_to_nchw", "nchw_to_nhwc", "add_", "cast",
            "ce_dice_fwd", "ce_dice_bwd", "CONV_FWD", "CONV_TRANSPOSED", "IMPL_AUTO", "IMPL_SIMT", "IMPL_TCGEN05"]
 
 _DT = {torch.float32: F32, torch.bfloat16: BF16}
@@ -177,7 +177,7 @@ def conv2d_wgrad(P, G, dW, k, stride, pad, cg_off=0, cg_total=None, impl=IMPL_AU
                   f"P{tuple(P.shape)} G{tuple(G.shape)} k{kh} s{stride}")
 
 
-def pack_weight(w, k_is_dim1, dtype, n_major=False, flip=False, kpad=None):
+def pack_weight(w, k_is_dim1, dtype, n_major=False, flip=False, kpad=None, gate_c=0):
     """[D0, D1, kh, kw] (or [D0, D1]) fp32 parameter -> GEMM operand in `dtype`:
     [(ky,kx,k), n] (SIMT family) or, with n_major, [n, (ky,kx,k)] (tcgen05 family; kpad zero-pads each row)."""
     _need_cuda(w)
@@ -194,7 +194,7 @@ def pack_weight(w, k_is_dim1, dtype, n_major=False, flip=False, kpad=None):
         wp = torch.empty((kh * kw * Kc, Nc), dtype=dtype, device=w.device)
     with _timed("pack_weight", _nb(w, wp)):
         check(_lib.load().stfb_pack_weight_ex(_p(w), _p(wp), D0, D1, kh, kw, int(k_is_dim1), int(n_major), int(flip), ld,
-                                              dt_code(dtype), _stream()), "pack_weight")
+                                              int(gate_c), dt_code(dtype), _stream()), "pack_weight")
     return wp
 
 
@@ -224,7 +224,8 @@ class PackPlan:
         jobs = np.zeros(len(self.keys), dtype=job_t)
         start = 0
         for j, key in enumerate(self.keys):
-            name, k_is_dim1, n_major, flip, kpad = key
+            name, k_is_dim1, n_major, flip, kpad = key[:5]
+            gate_c = key[5] if len(key) > 5 else 0
             w = params[name]
             shape = packed_shape(w, k_is_dim1, n_major, kpad)
             buf = (torch.zeros if kpad else torch.empty)(shape, dtype=dtype, device=dev)
@@ -232,7 +233,7 @@ class PackPlan:
             D0, D1 = w.shape[0], w.shape[1]
             khw = 1 if w.dim() == 2 else w.shape[2] * w.shape[3]
             jobs[j] = (w.data_ptr(), buf.data_ptr(), start, D0, D1, khw, int(k_is_dim1), int(n_major), int(flip),
-                       shape[1] if n_major else 0, 0)
+                       shape[1] if n_major else 0, int(gate_c))
             start += w.numel()
         self.total = start
         self.table = torch.from_numpy(jobs.view(np.uint8)).to(dev)
@@ -391,6 +392,18 @@ def bilinear_bwd(dy, H, W):
     dx = torch.zeros((N, H, W, C_), dtype=torch.float32, device=dy.device)
     check(_lib.load().stfb_bilinear_bwd(_p(dy), _p(dx), N, H, W, C_, Ho, Wo, dt_code(dy.dtype), _stream()), "bilinear_bwd")
     return dx
+
+
+def lstm_step_fused(h_prev, w_hh_il, gates_x, c_prev, c_out, h_out, acts):
+    """One recurrent LSTM step: tcgen05 GEMM h_prev @ W_hh^T with the cell update fused into the epilogue."""
+    N, H, W, C_ = h_prev.shape
+    e0 = _prof.begin() if _prof is not None else None
+    check(_lib.load().stfb_lstm_step_fused(_p(h_prev), _p(w_hh_il), _p(gates_x), _p(c_prev), _p(c_out), _p(h_out), _p(acts),
+                                           N, H, W, C_, _stream()), "lstm_step_fused")
+    if e0 is not None:
+        rows = N * H * W
+        _prof.end(e0, "conv_tcgen05", 2.0 * rows * C_ * 4 * C_, rows * C_ * (2 + 16 + 8 + 2 + (8 if acts is not None else 0)),
+                  f"lstm_step_fused rows{rows} C{C_}")
 
 
 def lstm_cell_fwd(gates, c_prev, acts, c_out, h_out, R, C_):

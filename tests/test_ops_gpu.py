@@ -539,3 +539,31 @@ def test_small_cin_conv_via_im2col(N, H, W, Cin, Cout, k, stride, pad):
     dW = torch.zeros(Cout, Cin, k, k, device=DEV)
     ops.unpad_wgrad(dW, scratch)
     assert rel(dW, w.grad) < 1e-4
+
+
+@pytest.mark.parametrize("B,h,w,C", [(2, 16, 16, 64), (3, 8, 8, 128), (1, 10, 12, 256), (2, 4, 4, 512)])
+def test_lstm_step_fused_matches_reference(B, h, w, C):
+    """Recurrent GEMM + cell update in one tcgen05 kernel (gate-interleaved W_hh) vs the gate-by-gate reference."""
+    bf = torch.bfloat16
+    R = B * h * w
+    hp = q(rnd(R, C, seed=1) * 0.5, bf)
+    whh = q(rnd(4 * C, C, seed=2, scale=1.0 / C ** 0.5), bf)
+    gx = rnd(R, 4 * C, seed=3)
+    cp = rnd(R, C, seed=4)
+    gates = hp @ whh.t() + gx
+    i, f, g, o = gates.split(C, 1)
+    c_ref = torch.sigmoid(f) * cp + torch.sigmoid(i) * torch.tanh(g)
+    h_ref = torch.sigmoid(o) * torch.tanh(c_ref)
+    wp = ops.pack_weight(whh.contiguous(), True, bf, n_major=True, gate_c=C)
+    c_out = torch.empty(R, C, device=DEV)
+    h_out = torch.empty(B, h, w, C, device=DEV, dtype=bf)
+    acts = torch.empty(B, h, w, 4 * C, device=DEV, dtype=bf)
+    ops.lstm_step_fused(hp.to(bf).view(B, h, w, C), wp, gx, cp, c_out, h_out, acts)
+    torch.cuda.synchronize()
+    assert rel(c_out, c_ref) < 3e-3
+    assert rel(h_out.view(R, C), h_ref) < 6e-3
+    a_ref = torch.cat([torch.sigmoid(i), torch.sigmoid(f), torch.tanh(g), torch.sigmoid(o)], 1)
+    assert rel(acts.view(R, 4 * C), a_ref) < 6e-3
+    # eval form: no saved activations
+    ops.lstm_step_fused(hp.to(bf).view(B, h, w, C), wp, gx, cp, c_out, h_out, None)
+    assert rel(c_out, c_ref) < 3e-3
