@@ -93,9 +93,20 @@ int stfb_conv2d_tcgen05_supported(const stfb_conv_params* p);
  * impl: STFB_IMPL_AUTO picks the tcgen05 family when the shape allows (bf16, stride-1 "same" geometry, Cg % 64 == 0,
  * Cp % 64 == 0), else the SIMT family; STFB_IMPL_SIMT / STFB_IMPL_TCGEN05 force one.
  * The tcgen05 family needs a caller-provided fp32 workspace (the [(ky,kx,ci)][co] accumulation buffer the split-K CTAs
- * reduce into); stfb_conv2d_wgrad_workspace_bytes returns its size (0 when the SIMT family will run). */
+ * reduce into); stfb_conv2d_wgrad_workspace_bytes returns its size (0 when the SIMT family will run).
+ * Deferred mode (dW == NULL, tcgen05 only): the launch only accumulates into `workspace`, laid out
+ * [(ky,kx, ci over cg_total)][Cp] and zeroed by the caller; one stfb_wgrad_scatter_batched at the end of the backward pass
+ * folds every such buffer into the flat gradient (instead of a memset + transpose launch per weight). */
 size_t stfb_conv2d_wgrad_workspace_bytes(const void* P, const void* G, int N, int Hp, int Wp, int Cp, int Hg, int Wg, int Cg,
-                                         int kh, int kw, int stride, int pad, int dtype, int impl);
+                                         int cg_total, int kh, int kw, int stride, int pad, int dtype, int impl);
+typedef struct stfb_scatter_job {
+  long long start;   /* first tile (32 ci x 32 co, all taps) of this job in [0, total_tiles); khw <= 9 */
+  long long off;     /* element offset of the weight in BOTH flat buffers (gradient and accumulation) */
+  int Cp, Cg, khw, pad_;
+} stfb_scatter_job;
+/* grad_flat[off + (co*Cg + ci)*khw + tap] += acc_flat[off + (tap*Cg + ci)*Cp + co] for every job (device job table) */
+int stfb_wgrad_scatter_batched(const stfb_scatter_job* jobs_dev, int njobs, long long total_tiles, const float* acc_flat,
+                               float* grad_flat, void* stream);
 int stfb_conv2d_wgrad(const void* P, const void* G, float* dW, int N, int Hp, int Wp, int Cp, int Hg, int Wg, int Cg,
                       int cg_off, int cg_total, int kh, int kw, int stride, int pad, int dtype, int impl,
                       void* workspace, size_t ws_bytes, void* stream);

@@ -202,23 +202,25 @@ static int launch_colreduce(ColRedArgs A, int dtype, int VEC, cudaStream_t st, c
   return post_launch(what);
 }
 
-// fp64 sum over the nblk partial slots of 8 consecutive groups for channel c; lanes stride over the slots
+// sum over the nblk partial slots of 8 consecutive groups for channel c; lanes stride over the slots (each lane adds at
+// most two fp32 partials, the 32 lane sums are combined in fp64: B200 fp64 is slow, so it is kept to 5 shuffle steps)
 __device__ __forceinline__ void sum_partials8(const float* __restrict__ partial, int nblk, int G, int C, int g0, int c, int lane,
                                               double* s, double* q) {
+  float fs[8], fq[8];
 #pragma unroll
-  for (int j = 0; j < 8; ++j) s[j] = q[j] = 0.0;
+  for (int j = 0; j < 8; ++j) fs[j] = fq[j] = 0.f;
   for (int b = lane; b < nblk; b += 32) {
     const float* pp = partial + ((long long)b * 2 * G) * C + c;
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       if (g0 + j < G) {
-        s[j] += (double)pp[(long long)(g0 + j) * C];
-        q[j] += (double)pp[(long long)(G + g0 + j) * C];
+        fs[j] += pp[(long long)(g0 + j) * C];
+        fq[j] += pp[(long long)(G + g0 + j) * C];
       }
     }
   }
 #pragma unroll
-  for (int j = 0; j < 8; ++j) { s[j] = warp_sum(s[j]); q[j] = warp_sum(q[j]); }
+  for (int j = 0; j < 8; ++j) { s[j] = warp_sum((double)fs[j]); q[j] = warp_sum((double)fq[j]); }
 }
 
 // =================================================================================================
@@ -245,7 +247,7 @@ __global__ void bn_finalize_train_kernel(const float* __restrict__ partial, int 
         const double m = s[j] / n;
         double var = q[j] / n - m * m;
         if (var < 0.0) var = 0.0;
-        const float is = (float)(1.0 / sqrt(var + (double)eps));
+        const float is = rsqrtf((float)var + eps);
         const float sc = gamma[c] * is;
         scale[g * C + c] = sc;
         shift[g * C + c] = beta[c] - (float)m * sc;

@@ -519,7 +519,9 @@ int wgrad_tcgen05_supported(int N, int Hp, int Wp, int Cp, int Hg, int Wg, int C
 int wgrad_tcgen05(const void* P, const void* G, const void* G2, float* dW, int N, int H, int W, int Cp, int Hg, int Wg,
                   int C1, int C2, int cg_off, int cg_total, int kh, int kw, int stride, int pad, float* ws, size_t ws_bytes,
                   cudaStream_t st);
-size_t wgrad_tcgen05_workspace_bytes(int N, int H, int W, int Cp, int Cg, int kh, int kw);
+size_t wgrad_tcgen05_workspace_bytes(int N, int H, int W, int Cp, int cg_total, int kh, int kw);
+int wgrad_scatter_batched(const stfb_scatter_job* jobs_dev, int njobs, long long total, const float* acc, float* grad,
+                          cudaStream_t st);
 int lstm_step_tcgen05(const void* h_prev, const void* w_hh_il, const float* gates_x, const float* c_prev, float* c_out,
                       void* h_out, void* acts, int N, int H, int W, int C, cudaStream_t st);
 }
@@ -576,16 +578,24 @@ extern "C" int stfb_conv2d_wgrad_tcgen05_supported(const void* P, const void* G,
 }
 
 extern "C" size_t stfb_conv2d_wgrad_workspace_bytes(const void* P, const void* G, int N, int Hp, int Wp, int Cp, int Hg, int Wg,
-                                                    int Cg, int kh, int kw, int stride, int pad, int dtype, int impl) {
+                                                    int Cg, int cg_total, int kh, int kw, int stride, int pad, int dtype,
+                                                    int impl) {
   if (impl == STFB_IMPL_SIMT) return 0;
   if (!stfb::wgrad_tcgen05_supported(N, Hp, Wp, Cp, Hg, Wg, Cg, kh, kw, stride, pad, dtype, P, G)) return 0;
-  return stfb::wgrad_tcgen05_workspace_bytes(N, Hp, Wp, Cp, Cg, kh, kw);
+  return stfb::wgrad_tcgen05_workspace_bytes(N, Hp, Wp, Cp, cg_total, kh, kw);
+}
+
+extern "C" int stfb_wgrad_scatter_batched(const stfb_scatter_job* jobs_dev, int njobs, long long total, const float* acc_flat,
+                                          float* grad_flat, void* stream) {
+  STFB_REQUIRE(jobs_dev && njobs > 0 && total > 0 && acc_flat && grad_flat, "wgrad_scatter_batched: bad arguments");
+  STFB_DEVICE_OR_RETURN();
+  return stfb::wgrad_scatter_batched(jobs_dev, njobs, total, acc_flat, grad_flat, reinterpret_cast<cudaStream_t>(stream));
 }
 
 extern "C" int stfb_conv2d_wgrad(const void* P, const void* G, float* dW, int N, int Hp, int Wp, int Cp, int Hg, int Wg,
                                  int Cg, int cg_off, int cg_total, int kh, int kw, int stride, int pad, int dtype, int impl,
                                  void* workspace, size_t ws_bytes, void* stream) {
-  STFB_REQUIRE(P && G && dW, "conv2d_wgrad: null pointer");
+  STFB_REQUIRE(P && G && (dW || workspace), "conv2d_wgrad: null pointer");
   STFB_REQUIRE(N >= 0 && Hp > 0 && Wp > 0 && Cp > 0 && Hg > 0 && Wg > 0 && Cg > 0 && kh > 0 && kw > 0 && stride > 0 && pad >= 0,
                "conv2d_wgrad: bad dims");
   STFB_REQUIRE(cg_off >= 0 && cg_off + Cg <= cg_total, "conv2d_wgrad: channel window [%d,%d) outside %d", cg_off, cg_off + Cg, cg_total);
@@ -600,6 +610,7 @@ extern "C" int stfb_conv2d_wgrad(const void* P, const void* G, float* dW, int N,
       return STFB_ENOTSUP;
     }
   }
+  STFB_REQUIRE(dW != nullptr, "conv2d_wgrad: deferred mode (dW = NULL) needs the tcgen05 family");
   WgradArgs a{};
   a.P = P; a.G = G; a.dW = dW; a.N = N; a.Hp = Hp; a.Wp = Wp; a.Cp = Cp; a.Hg = Hg; a.Wg = Wg; a.Cg = Cg;
   a.cg_off = cg_off; a.cg_total = cg_total; a.kh = kh; a.kw = kw; a.stride = stride; a.pad = pad;

@@ -162,7 +162,9 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_kernel(const __grid_co
     for (int j = 0; j < nacc; ++j) {
       const int chunk = chunk_lo + 2 * j + (m >> 6);
       const bool valid = chunk < chunk_hi;
-      const long long kg = (long long)chunk * 64 + (m & 63);
+      // accumulation buffer is [(tap, ci over the FULL weight)][co]: this launch owns the ci window [cg_off, cg_off + Cin)
+      const int tapq = chunk / cpt;
+      const long long kg = (long long)tapq * a.cg_total + a.cg_off + (chunk - tapq * cpt) * 64 + (m & 63);
       float* rowp = a.ws + kg * a.Cp + n0;
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(j * BN);
 #pragma unroll 1
@@ -193,6 +195,8 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_kernel(const __grid_co
 __global__ void __launch_bounds__(256) wgrad_scatter_kernel(const float* __restrict__ acc, float* __restrict__ dW, int Cp, int Cg,
                                                            int khw, int cg_off, int cg_total) {
   __shared__ float tile[9][32][33];
+  Cg = cg_total;   // the accumulation buffer spans the full ci axis
+  (void)cg_off;
   const int ci0 = blockIdx.x * 32, co0 = blockIdx.y * 32;
   const int tx = threadIdx.x % 32, ty = threadIdx.x / 32;       // 32 x 8
   for (int tap = 0; tap < khw; ++tap)
@@ -206,7 +210,7 @@ __global__ void __launch_bounds__(256) wgrad_scatter_kernel(const float* __restr
   for (int r = ty; r < 32; r += 8) {
     const int co = co0 + r;
     if (co >= Cp) continue;
-    float* dst = dW + ((long long)co * cg_total + cg_off + ci0) * khw;
+    float* dst = dW + ((long long)co * cg_total + ci0) * khw;
     for (int e = tx; e < run; e += 32) {
       const int ci = e / khw, tap = e - ci * khw;
       if (ci0 + ci < Cg) dst[e] += tile[tap][ci][r];
@@ -290,8 +294,56 @@ static WgPlan wg_plan(int N, int H, int W, int Cp, int Ctot, int kh, int kw) {
   return p;
 }
 
-size_t wgrad_tcgen05_workspace_bytes(int N, int H, int W, int Cp, int Cg, int kh, int kw) {
-  return (size_t)kh * kw * Cg * Cp * sizeof(float);     // fp32 accumulation buffer [(tap, ci)][co]
+size_t wgrad_tcgen05_workspace_bytes(int N, int H, int W, int Cp, int cg_total, int kh, int kw) {
+  return (size_t)kh * kw * cg_total * Cp * sizeof(float);     // fp32 accumulation buffer [(tap, ci)][co] of the full weight
+}
+
+// all deferred weight-gradient transposes of a backward pass in one launch:
+//   grad_flat[off + (co*Cg + ci)*khw + tap] += acc_flat[off + (tap*Cg + ci)*Cp + co]
+// one CTA = one 32 (ci) x 32 (co) tile of one weight, all taps, transposed through shared memory (coalesced both ways)
+__global__ void __launch_bounds__(256) wgrad_scatter_batched_kernel(const stfb_scatter_job* __restrict__ jobs, int njobs,
+                                                                   const float* __restrict__ acc, float* __restrict__ grad) {
+  __shared__ float tile[9][32][33];
+  __shared__ stfb_scatter_job jb;
+  if (threadIdx.x == 0) {
+    int lo = 0, hi = njobs - 1;
+    const long long b = blockIdx.x;
+    while (lo < hi) {
+      const int mid = (lo + hi + 1) >> 1;
+      if (jobs[mid].start <= b) lo = mid; else hi = mid - 1;
+    }
+    jb = jobs[lo];
+  }
+  __syncthreads();
+  const int Cp = jb.Cp, Cg = jb.Cg, khw = jb.khw;
+  const int local = (int)(blockIdx.x - jb.start);
+  const int tiles_ci = (Cg + 31) / 32;
+  const int ci0 = (local % tiles_ci) * 32, co0 = (local / tiles_ci) * 32;
+  const float* a = acc + jb.off;
+  float* g = grad + jb.off;
+  const int tx = threadIdx.x % 32, ty = threadIdx.x / 32;
+  for (int tap = 0; tap < khw; ++tap)
+    for (int r = ty; r < 32; r += 8) {
+      const int ci = ci0 + r, co = co0 + tx;
+      tile[tap][r][tx] = (ci < Cg && co < Cp) ? a[((long long)tap * Cg + ci) * Cp + co] : 0.f;
+    }
+  __syncthreads();
+  const int run = 32 * khw;
+  for (int r = ty; r < 32; r += 8) {
+    const int co = co0 + r;
+    if (co >= Cp) continue;
+    float* dst = g + ((long long)co * Cg + ci0) * khw;
+    for (int e = tx; e < run; e += 32) {
+      const int ci = e / khw, tap = e - ci * khw;
+      if (ci0 + ci < Cg) dst[e] += tile[tap][ci][r];
+    }
+  }
+}
+
+int wgrad_scatter_batched(const stfb_scatter_job* jobs_dev, int njobs, long long total_tiles, const float* acc, float* grad,
+                          cudaStream_t st) {
+  wgrad_scatter_batched_kernel<<<(unsigned)total_tiles, 256, 0, st>>>(jobs_dev, njobs, acc, grad);
+  return post_launch("wgrad_scatter_batched");
 }
 
 int wgrad_tcgen05(const void* P, const void* G, const void* G2, float* dW, int N, int H, int W, int Cp, int Hg, int Wg,
@@ -301,7 +353,7 @@ int wgrad_tcgen05(const void* P, const void* G, const void* G2, float* dW, int N
   if (!enc) { set_error("conv2d_wgrad(tcgen05): cuTensorMapEncodeTiled not available"); return STFB_ECUDA; }
   if ((long long)N * H * W == 0) return STFB_OK;
   const WgPlan pl = wg_plan(N, H, W, Cp, C1 + C2, kh, kw);
-  const size_t need = (size_t)pl.m_chunks * 64 * Cp * sizeof(float);
+  const size_t need = (size_t)kh * kw * cg_total * Cp * sizeof(float);
   if (ws == nullptr || ws_bytes < need || (reinterpret_cast<uintptr_t>(ws) % 16) != 0) {
     set_error("conv2d_wgrad(tcgen05): workspace of %zu bytes (16-byte aligned) required, got %zu", need, ws_bytes);
     return STFB_EINVAL;
@@ -325,7 +377,7 @@ int wgrad_tcgen05(const void* P, const void* G, const void* G2, float* dW, int N
   if (C2 > 0 && !encode_nhwc_map_strided(enc, &tG2, G2, N, Hg, Wg, C2, a.TW, a.TH, a.TN, stride, 64)) { set_error("conv2d_wgrad(tcgen05): tensor map (G2) failed"); return STFB_ECUDA; }
   if (!encode_nhwc_map(enc, &tP, P, N, H, W, Cp, a.TW, a.TH, a.TN)) { set_error("conv2d_wgrad(tcgen05): tensor map (P) failed"); return STFB_ECUDA; }
   dim3 grid((unsigned)m_tiles, (unsigned)n_tiles, (unsigned)splits);
-  cudaMemsetAsync(ws, 0, need, st);
+  if (dW != nullptr) cudaMemsetAsync(ws, 0, need, st);   // immediate mode owns the buffer; deferred mode: the caller zeroed it
   int rc = STFB_ENOTSUP;
   const int key = BN * 10 + pl.NA;
   switch (key) {
@@ -341,7 +393,8 @@ int wgrad_tcgen05(const void* P, const void* G, const void* G2, float* dW, int N
   }
   if (rc != STFB_OK) return rc;
   (void)splits;
-  dim3 sgrid((unsigned)((C1 + C2 + 31) / 32), (unsigned)((Cp + 31) / 32));
+  if (dW == nullptr) return STFB_OK;                    // deferred: stfb_wgrad_scatter_batched folds the buffer into dW later
+  dim3 sgrid((unsigned)((cg_total + 31) / 32), (unsigned)((Cp + 31) / 32));
   wgrad_scatter_kernel<<<sgrid, 256, 0, st>>>(ws, dW, Cp, C1 + C2, kh * kw, cg_off, cg_total);
   return post_launch("conv2d_wgrad(scatter)");
 }

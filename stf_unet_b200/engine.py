@@ -61,6 +61,11 @@ class Executor:
         self.tape: List = []
         self._packed = {}
         self._new_pack_keys = []      # packs this forward needed that the module's PackPlan did not hold
+        # deferred tcgen05 weight gradients: side buffer with the flat gradient's layout + who used it
+        self.acc_flat = None
+        self.acc: Dict[str, torch.Tensor] = {}
+        self.grad_offsets: Dict[str, int] = {}
+        self._deferred = {}           # name -> (flat offset, Cp, Cg_total, khw)
 
     # ---------------------------------------------------------------------------------------------
     def packed(self, name, k_is_dim1, n_major=False, flip=False, kpad=None, gate_c=0):
@@ -88,6 +93,15 @@ class Executor:
 
     def wants_grad(self, name):
         return name in self.grads
+
+    def wgrad(self, wname, P, G, k, stride, pad, cg_off=0, cg_total=None):
+        """Weight gradient of `wname`; tcgen05 launches accumulate in the side buffer and are folded in once, at the
+        end of the backward pass (Executor.backward)."""
+        acc = self.acc.get(wname)
+        if ops.conv2d_wgrad(P, G, self.grads[wname], k, stride, pad, cg_off, cg_total, acc=acc):
+            w = self.params[wname]
+            khw = 1 if w.dim() == 2 else w.shape[2] * w.shape[3]
+            self._deferred[wname] = (self.grad_offsets[wname], w.shape[0], w.shape[1], khw)
 
     # ---------------------------------------------------------------------------------------------
     def conv(self, x: Var, wname: str, *, k: int, stride: int = 1, pad: int = 0, transposed: bool = False,
@@ -127,11 +141,11 @@ class Executor:
                 ops.colsum(dy, self.grads[bname], rows, Cout)
             if self.wants_grad(wname):
                 if not transposed:
-                    ops.conv2d_wgrad(dy, x.data, self.grads[wname], k, stride, pad, 0, C1 + C2)
+                    self.wgrad(wname, dy, x.data, k, stride, pad, 0, C1 + C2)
                     if x2 is not None:
-                        ops.conv2d_wgrad(dy, x2.data, self.grads[wname], k, stride, pad, C1, C1 + C2)
+                        self.wgrad(wname, dy, x2.data, k, stride, pad, C1, C1 + C2)
                 else:
-                    ops.conv2d_wgrad(x.data, dy, self.grads[wname], k, stride, pad, 0, Cout)
+                    self.wgrad(wname, x.data, dy, k, stride, pad, 0, Cout)
             srcs = [(x, 0, C1)] + ([(x2, C1, C2)] if x2 is not None else [])
             for src, off, csrc in srcs:
                 if not src.needs_grad:
@@ -314,10 +328,9 @@ class Executor:
                     dh = ops.conv2d(dG[t], whh_d, C, 1, 1, 0, y_dtype=torch.float32, impl=implb)
             dG_all = dG.view(T * B, h, w, 4 * C)
             if self.wants_grad(wih):
-                ops.conv2d_wgrad(dG_all, seq.data, self.grads[wih], 1, 1, 0)
+                self.wgrad(wih, dG_all, seq.data, 1, 1, 0)
             if self.wants_grad(whh) and T > 1:
-                ops.conv2d_wgrad(dG[1:].reshape((T - 1) * B, h, w, 4 * C), hs[:T - 1].reshape((T - 1) * B, h, w, C),
-                                 self.grads[whh], 1, 1, 0)
+                self.wgrad(whh, dG[1:].reshape((T - 1) * B, h, w, 4 * C), hs[:T - 1].reshape((T - 1) * B, h, w, C), 1, 1, 0)
             # d b_ih == d b_hh == column sums of dG: reduce once, add the (tiny) result into the second bias
             if self.wants_grad(bih):
                 ops.colsum(dG_all, self.grads[bih], T * R, 4 * C)
@@ -335,26 +348,35 @@ class Executor:
         return out
 
     # ---------------------------------------------------------------------------------------------
-    def backward(self, out: Var, dout):
+    def backward(self, out: Var, dout, flat_grad=None, owner=None):
         out.grad = dout
         for fn in reversed(self.tape):
             fn()
+        if self._deferred and flat_grad is not None:
+            entries = sorted(self._deferred.values())
+            plan = getattr(owner, "_scatter_plan", None) if owner is not None else None
+            if plan is None or plan.key != tuple(entries):
+                plan = ops.ScatterPlan(entries, flat_grad.device)
+                if owner is not None:
+                    owner._scatter_plan = plan
+            plan.run(self.acc_flat, flat_grad)
         self.tape = []
         self._packed = {}
 
 
-def flat_grads(named_params):
+def flat_grads(named_params, with_offsets=False):
     """One flat fp32 buffer with a view per trainable parameter (what the DP all-reduce walks)."""
     named = [(n, p) for n, p in named_params if p.requires_grad]
     if not named:
-        return None, {}
+        return (None, {}, {}) if with_offsets else (None, {})
     total = sum(p.numel() for _, p in named)
     flat = torch.zeros(total, dtype=torch.float32, device=named[0][1].device)
-    views, off = {}, 0
+    views, offsets, off = {}, {}, 0
     for n, p in named:
         views[n] = flat[off:off + p.numel()].view(p.shape)
+        offsets[n] = off
         off += p.numel()
-    return flat, views
+    return (flat, views, offsets) if with_offsets else (flat, views)
 
 
 class ModelFunction(torch.autograd.Function):
@@ -371,7 +393,7 @@ class ModelFunction(torch.autograd.Function):
     def backward(ctx, dlogits):
         ex, module = ctx.ex, ctx.module
         d = ops.nchw_to_nhwc(dlogits.contiguous().float(), ex.dtype)
-        ex.backward(ctx.out_var, d)
+        ex.backward(ctx.out_var, d, flat_grad=module._last_flat_grad, owner=module)
         # Gradients live in ONE flat fp32 buffer (module._last_flat_grad); each parameter's .grad is a view of it,
         # assigned directly so that autograd does not clone 110 MB per step and the data-parallel all-reduce can
         # run on the flat buffer.  A second backward before zero_grad() accumulates, as autograd would.

