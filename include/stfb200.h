@@ -127,7 +127,8 @@ int stfb_pack_weight_ex(const float* w, void* wp, int D0, int D1, int kh, int kw
                         int dtype, void* stream);
 
 /* Batched form: one launch packs every weight of a step.  `jobs_dev` is a DEVICE array (uploaded once per model);
- * job j covers flat element range [start_j, start_{j+1}) of `total`; fields as in stfb_pack_weight_ex. */
+ * job j covers work items [start_j, start_{j+1}) of `total`, one work item = one (d0, d1) position with all its kh*kw
+ * taps (so a job has D0*D1 items); fields as in stfb_pack_weight_ex. */
 typedef struct stfb_pack_job {
   const float* src;
   void* dst;

@@ -275,32 +275,59 @@ __global__ void bn_fold_eval_kernel(const float* __restrict__ gamma, const float
   shift[c] = beta[c] - rm[c] * sc;
 }
 
+// Row-tiled elementwise kernels: thread (rl, cl) of a CTA owns channels [cl*VEC, cl*VEC + VEC) of every (256/tpr)-th row
+// of its row range inside ONE group (blockIdx.y), so the per-(group, channel) coefficients sit in registers and the
+// loop body is U independent 16-byte loads per tensor followed by the stores.
 template <typename T, int VEC>
-__global__ void bn_apply_kernel(const T* __restrict__ x, const float* __restrict__ scale, const float* __restrict__ shift,
-                                const T* res, T* y, long long R, int C, long long total_vec, int relu) {
+__global__ void __launch_bounds__(256, 4) bn_apply_kernel(const T* __restrict__ x, const float* __restrict__ scale,
+                                                       const float* __restrict__ shift, const T* res, T* y, long long R, int C,
+                                                       long long rows_per_block, int tpr, int relu) {
+  constexpr int U = 2;
+  const int lanes = 256 / tpr;
+  const int cl = threadIdx.x % tpr, rl = threadIdx.x / tpr;
+  const int g = blockIdx.y;
   const int CVn = C / VEC;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total_vec; i += (long long)gridDim.x * blockDim.x) {
-    const long long row = i / CVn;
-    const int c = (int)(i - row * CVn) * VEC;
-    const int g = (int)(row / R);
-    const long long off = row * C + c;
-    float v[VEC], sc[VEC], sh[VEC];
-    ldv<VEC>(x + off, v);
-    ldv<VEC>(scale + g * C + c, sc);
-    ldv<VEC>(shift + g * C + c, sh);
+  const long long r0 = (long long)blockIdx.x * rows_per_block;
+  const long long r1 = min(R, r0 + rows_per_block);
+  const long long gbase = (long long)g * R;
+  for (int cv = cl; cv < CVn; cv += tpr) {
+    const int c = cv * VEC;
+    float sc[VEC], sh[VEC];
 #pragma unroll
-    for (int j = 0; j < VEC; ++j) v[j] = fmaf(v[j], sc[j], sh[j]);
-    if (res) {
-      float r[VEC];
-      ldv<VEC>(res + off, r);
+    for (int j = 0; j < VEC; ++j) { sc[j] = scale[g * C + c + j]; sh[j] = shift[g * C + c + j]; }
+    long long r = r0 + rl;
+    for (; r + (long long)(U - 1) * lanes < r1; r += (long long)U * lanes) {
+      float v[U][VEC], rr[U][VEC];
 #pragma unroll
-      for (int j = 0; j < VEC; ++j) v[j] += r[j];
+      for (int u = 0; u < U; ++u) {
+        const long long off = (gbase + r + (long long)u * lanes) * C + c;
+        ldv<VEC>(x + off, v[u]);
+        if (res) ldv<VEC>(res + off, rr[u]);
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+#pragma unroll
+        for (int j = 0; j < VEC; ++j) {
+          float t = fmaf(v[u][j], sc[j], sh[j]);
+          if (res) t += rr[u][j];
+          v[u][j] = relu ? fmaxf(t, 0.f) : t;
+        }
+        stv<VEC>(y + (gbase + r + (long long)u * lanes) * C + c, v[u]);
+      }
     }
-    if (relu) {
+    for (; r < r1; r += lanes) {
+      const long long off = (gbase + r) * C + c;
+      float v[VEC], rr[VEC];
+      ldv<VEC>(x + off, v);
+      if (res) ldv<VEC>(res + off, rr);
 #pragma unroll
-      for (int j = 0; j < VEC; ++j) v[j] = fmaxf(v[j], 0.f);
+      for (int j = 0; j < VEC; ++j) {
+        float t = fmaf(v[j], sc[j], sh[j]);
+        if (res) t += rr[j];
+        v[j] = relu ? fmaxf(t, 0.f) : t;
+      }
+      stv<VEC>(y + off, v);
     }
-    stv<VEC>(y + off, v);
   }
 }
 
@@ -333,39 +360,69 @@ __global__ void bn_bwd_finalize_kernel(const float* __restrict__ partial, int nb
   }
 }
 
+// dx = k0 * (dz - k1 - xhat * k2) with xhat = (x - mean) * invstd, folded per channel into dx = k0*dz + cb*x + cc
+// (three coefficient registers per channel instead of five: the kernel has to fit 4 CTAs of 256 threads per SM).
 template <typename T, int VEC>
-__global__ void bn_bwd_apply_kernel(const T* __restrict__ dy, const T* __restrict__ y, const T* __restrict__ x,
-                                    const float* __restrict__ mean, const float* __restrict__ invstd,
-                                    const float* __restrict__ coef, T* dx, T* dres, long long R, int C,
-                                    long long total_vec, int relu, int accum_dres) {
+__global__ void __launch_bounds__(256, 4) bn_bwd_apply_kernel(const T* __restrict__ dy, const T* __restrict__ y,
+                                                              const T* __restrict__ x, const float* __restrict__ mean,
+                                                              const float* __restrict__ invstd, const float* __restrict__ coef,
+                                                              T* dx, T* dres, long long R, int C, long long rows_per_block, int tpr,
+                                                              int relu, int accum_dres) {
+  constexpr int U = 1;
+  const int lanes = 256 / tpr;
+  const int cl = threadIdx.x % tpr, rl = threadIdx.x / tpr;
+  const int g = blockIdx.y;
   const int CVn = C / VEC;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total_vec; i += (long long)gridDim.x * blockDim.x) {
-    const long long row = i / CVn;
-    const int c = (int)(i - row * CVn) * VEC;
-    const int g = (int)(row / R);
-    const long long off = row * C + c;
-    float d[VEC], xv[VEC], yv[VEC], o[VEC];
-    ldv<VEC>(dy + off, d);
-    ldv<VEC>(x + off, xv);
-    if (relu) ldv<VEC>(y + off, yv);
+  const long long r0 = (long long)blockIdx.x * rows_per_block;
+  const long long r1 = min(R, r0 + rows_per_block);
+  const long long gbase = (long long)g * R;
+  for (int cv = cl; cv < CVn; cv += tpr) {
+    const int c = cv * VEC;
+    float k0[VEC], cb[VEC], cc[VEC];
 #pragma unroll
     for (int j = 0; j < VEC; ++j) {
       const int gc = g * C + c + j;
-      const float dz = (relu && !(yv[j] > 0.f)) ? 0.f : d[j];
-      d[j] = dz;
-      const float xh = (xv[j] - mean[gc]) * invstd[gc];
-      const float* k = coef + (long long)gc * 3;
-      o[j] = k[0] * (dz - k[1] - xh * k[2]);
+      const float mu = mean[gc], is = invstd[gc];
+      const float a0 = coef[(long long)gc * 3], a1 = coef[(long long)gc * 3 + 1], a2 = coef[(long long)gc * 3 + 2];
+      k0[j] = a0;
+      cb[j] = -a0 * a2 * is;
+      cc[j] = a0 * (mu * is * a2 - a1);
     }
-    stv<VEC>(dx + off, o);
-    if (dres) {
-      if (accum_dres) {
-        float old[VEC];
-        ldv<VEC>(dres + off, old);
+    for (long long r = r0 + rl; r < r1; r += (long long)U * lanes) {
+      float d[U][VEC], xv[U][VEC], yv[U][VEC];
 #pragma unroll
-        for (int j = 0; j < VEC; ++j) d[j] += old[j];
+      for (int u = 0; u < U; ++u) {
+        const long long rr = r + (long long)u * lanes;
+        if (rr < r1) {
+          const long long off = (gbase + rr) * C + c;
+          ldv<VEC>(dy + off, d[u]);
+          ldv<VEC>(x + off, xv[u]);
+          if (relu) ldv<VEC>(y + off, yv[u]);
+        }
       }
-      stv<VEC>(dres + off, d);
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const long long rr = r + (long long)u * lanes;
+        if (rr < r1) {
+          const long long off = (gbase + rr) * C + c;
+#pragma unroll
+          for (int j = 0; j < VEC; ++j) {
+            const float dz = (relu && !(yv[u][j] > 0.f)) ? 0.f : d[u][j];
+            d[u][j] = dz;
+            xv[u][j] = fmaf(k0[j], dz, fmaf(cb[j], xv[u][j], cc[j]));
+          }
+          stv<VEC>(dx + off, xv[u]);
+          if (dres) {
+            if (accum_dres) {
+              float old[VEC];
+              ldv<VEC>(dres + off, old);
+#pragma unroll
+              for (int j = 0; j < VEC; ++j) d[u][j] += old[j];
+            }
+            stv<VEC>(dres + off, d[u]);
+          }
+        }
+      }
     }
   }
 }
@@ -475,9 +532,13 @@ __global__ void maxpool_bwd_kernel(const T* __restrict__ x, const T* __restrict_
 }
 
 // ---- indexed variants: forward stores the window position of the first maximum (uint8), backward gathers by index.
-template <typename T, int VEC>
-__global__ void maxpool_fwd_idx_kernel(const T* __restrict__ x, T* __restrict__ y, unsigned char* __restrict__ idx, int N, int H,
-                                       int W, int C, int Ho, int Wo, int k, int stride, int pad, long long total_vec) {
+// KC > 0: compile-time window size -- the KC*KC loads of a window are issued back to back (predicated, not branched
+// around), so one thread keeps KC*KC 16-byte loads in flight instead of a dependent chain.
+template <typename T, int VEC, int KC>
+__global__ void __launch_bounds__(256) maxpool_fwd_idx_kernel(const T* __restrict__ x, T* __restrict__ y,
+                                                              unsigned char* __restrict__ idx, int N, int H, int W, int C, int Ho,
+                                                              int Wo, int k_, int stride, int pad, long long total_vec) {
+  const int k = KC > 0 ? KC : k_;
   const int CVn = C / VEC;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total_vec; i += (long long)gridDim.x * blockDim.x) {
     const int cv = (int)(i % CVn);
@@ -489,44 +550,57 @@ __global__ void maxpool_fwd_idx_kernel(const T* __restrict__ x, T* __restrict__ 
     int arg[VEC];
 #pragma unroll
     for (int j = 0; j < VEC; ++j) { best[j] = -INFINITY; arg[j] = -1; }
-    for (int ky = 0; ky < k; ++ky) {
-      const int iy = oy * stride - pad + ky;
-      if (iy < 0 || iy >= H) continue;
-      for (int kx = 0; kx < k; ++kx) {
-        const int ix = ox * stride - pad + kx;
-        if (ix < 0 || ix >= W) continue;
-        const long long off = (((long long)n * H + iy) * W + ix) * C + cv * VEC;
-        float v[VEC];
-        if (VEC == 8) {
-          f8 t = ld8(x + off);
+    const T* __restrict__ xb = x + (long long)n * H * W * C + cv * VEC;
+    if constexpr (KC > 0) {
+      float v[KC * KC][VEC];
+      bool ok[KC * KC];
 #pragma unroll
-          for (int j = 0; j < VEC; ++j) v[j] = t.v[j];
-        } else {
-          v[0] = ld1(x + off);
-        }
+      for (int t = 0; t < KC * KC; ++t) {
+        const int iy = oy * stride - pad + t / KC, ix = ox * stride - pad + t % KC;
+        ok[t] = iy >= 0 && iy < H && ix >= 0 && ix < W;
+        const long long off = ok[t] ? ((long long)iy * W + ix) * C : 0;
+        ldv<VEC>(xb + off, v[t]);
+      }
+#pragma unroll
+      for (int t = 0; t < KC * KC; ++t)
 #pragma unroll
         for (int j = 0; j < VEC; ++j)
-          if (v[j] > best[j] || arg[j] < 0) { best[j] = v[j]; arg[j] = ky * k + kx; }
+          if (ok[t] && (v[t][j] > best[j] || arg[j] < 0)) { best[j] = v[t][j]; arg[j] = t; }
+    } else {
+      for (int ky = 0; ky < k; ++ky) {
+        const int iy = oy * stride - pad + ky;
+        if (iy < 0 || iy >= H) continue;
+        for (int kx = 0; kx < k; ++kx) {
+          const int ix = ox * stride - pad + kx;
+          if (ix < 0 || ix >= W) continue;
+          float v[VEC];
+          ldv<VEC>(xb + ((long long)iy * W + ix) * C, v);
+#pragma unroll
+          for (int j = 0; j < VEC; ++j)
+            if (v[j] > best[j] || arg[j] < 0) { best[j] = v[j]; arg[j] = ky * k + kx; }
+        }
       }
     }
     const long long oo = (((long long)n * Ho + oy) * Wo + ox) * C + cv * VEC;
-    if (VEC == 8) {
-      st4(y + oo, f4{{best[0], best[1], best[2], best[3]}});
-      st4(y + oo + 4, f4{{best[4 % VEC], best[5 % VEC], best[6 % VEC], best[7 % VEC]}});
+    stv<VEC>(y + oo, best);
+    if constexpr (VEC == 8) {
       uint2 pk;
-      pk.x = (unsigned)arg[0] | ((unsigned)arg[1 % VEC] << 8) | ((unsigned)arg[2 % VEC] << 16) | ((unsigned)arg[3 % VEC] << 24);
-      pk.y = (unsigned)arg[4 % VEC] | ((unsigned)arg[5 % VEC] << 8) | ((unsigned)arg[6 % VEC] << 16) | ((unsigned)arg[7 % VEC] << 24);
+      pk.x = (unsigned)arg[0] | ((unsigned)arg[1] << 8) | ((unsigned)arg[2] << 16) | ((unsigned)arg[3] << 24);
+      pk.y = (unsigned)arg[4] | ((unsigned)arg[5] << 8) | ((unsigned)arg[6] << 16) | ((unsigned)arg[7] << 24);
       *reinterpret_cast<uint2*>(idx + oo) = pk;
     } else {
-      st1(y + oo, best[0]);
-      idx[oo] = (unsigned char)arg[0];
+#pragma unroll
+      for (int j = 0; j < VEC; ++j) idx[oo + j] = (unsigned char)arg[j];
     }
   }
 }
 
-template <typename T, int VEC>
-__global__ void maxpool_bwd_idx_kernel(const unsigned char* __restrict__ idx, const T* __restrict__ dy, T* __restrict__ dx, int N,
-                                       int H, int W, int C, int Ho, int Wo, int k, int stride, int pad, long long total_vec) {
+// gather form: input element (iy, ix) belongs to at most WMAX x WMAX windows (WMAX = ceil(k / stride)); their index words
+// and dy vectors are all loaded up front (the branchy form waited on idx before it asked for dy: a dependent chain).
+template <typename T, int VEC, int WMAX>
+__global__ void __launch_bounds__(256) maxpool_bwd_idx_kernel(const unsigned char* __restrict__ idx, const T* __restrict__ dy,
+                                                              T* __restrict__ dx, int N, int H, int W, int C, int Ho, int Wo, int k,
+                                                              int stride, int pad, long long total_vec) {
   const int CVn = C / VEC;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total_vec; i += (long long)gridDim.x * blockDim.x) {
     const int cv = (int)(i % CVn);
@@ -541,34 +615,32 @@ __global__ void maxpool_bwd_idx_kernel(const unsigned char* __restrict__ idx, co
     int oy_hi = (iy + pad) / stride; if (oy_hi > Ho - 1) oy_hi = Ho - 1;
     int ox_lo = ix + pad - k + 1; ox_lo = ox_lo <= 0 ? 0 : (ox_lo + stride - 1) / stride;
     int ox_hi = (ix + pad) / stride; if (ox_hi > Wo - 1) ox_hi = Wo - 1;
-    for (int oy = oy_lo; oy <= oy_hi; ++oy) {
-      for (int ox = ox_lo; ox <= ox_hi; ++ox) {
-        const int pos = (iy - (oy * stride - pad)) * k + (ix - (ox * stride - pad));
-        const long long oo = (((long long)n * Ho + oy) * Wo + ox) * C + cv * VEC;
-        if (VEC == 8) {
-          const uint2 pk = *reinterpret_cast<const uint2*>(idx + oo);
-          const unsigned w[2] = {pk.x, pk.y};
-          bool any = false;
+    float g[WMAX * WMAX][VEC];
+    unsigned char a[WMAX * WMAX][VEC];
+    int pos[WMAX * WMAX];
 #pragma unroll
-          for (int j = 0; j < 8; ++j) any |= (int)((w[j >> 2] >> (8 * (j & 3))) & 0xFF) == pos;
-          if (any) {
-            f8 g = ld8(dy + oo);
+    for (int t = 0; t < WMAX * WMAX; ++t) {
+      const int oy = oy_lo + t / WMAX, ox = ox_lo + t % WMAX;
+      const bool ok = oy <= oy_hi && ox <= ox_hi;
+      pos[t] = ok ? (iy - (oy * stride - pad)) * k + (ix - (ox * stride - pad)) : -1;
+      const long long oo = ok ? (((long long)n * Ho + oy) * Wo + ox) * C + cv * VEC : (long long)cv * VEC;
+      if constexpr (VEC == 8) {
+        const uint2 pk = *reinterpret_cast<const uint2*>(idx + oo);
 #pragma unroll
-            for (int j = 0; j < 8; ++j)
-              if ((int)((w[j >> 2] >> (8 * (j & 3))) & 0xFF) == pos) acc[j % VEC] += g.v[j];
-          }
-        } else {
-          if ((int)idx[oo] == pos) acc[0] += ld1(dy + oo);
-        }
+        for (int j = 0; j < 4; ++j) { a[t][j] = (unsigned char)(pk.x >> (8 * j)); a[t][4 + j] = (unsigned char)(pk.y >> (8 * j)); }
+      } else {
+#pragma unroll
+        for (int j = 0; j < VEC; ++j) a[t][j] = idx[oo + j];
       }
+      ldv<VEC>(dy + oo, g[t]);
     }
+#pragma unroll
+    for (int t = 0; t < WMAX * WMAX; ++t)
+#pragma unroll
+      for (int j = 0; j < VEC; ++j)
+        if ((int)a[t][j] == pos[t]) acc[j] += g[t][j];
     const long long io = (((long long)n * H + iy) * W + ix) * C + cv * VEC;
-    if (VEC == 8) {
-      st4(dx + io, f4{{acc[0], acc[1 % VEC], acc[2 % VEC], acc[3 % VEC]}});
-      st4(dx + io + 4, f4{{acc[4 % VEC], acc[5 % VEC], acc[6 % VEC], acc[7 % VEC]}});
-    } else {
-      st1(dx + io, acc[0]);
-    }
+    stv<VEC>(dx + io, acc);
   }
 }
 
@@ -749,29 +821,34 @@ __global__ void nchw_to_nhwc_kernel(const float* __restrict__ g, T* __restrict__
 
 // im2col for small-channel convolutions (7x7 stem with Cin=1, UNet first conv): out[m][(ky,kx,ci)] zero-padded to Kpad,
 // so the convolution becomes a K = Kpad GEMM the tcgen05 family can take.  One thread = 8 consecutive k (16 B store).
-__global__ void im2col_small_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ out, int N, int H, int W,
-                                    int Cin, int Ho, int Wo, int k, int stride, int pad, int Kpad, long long total) {
+// KC / CINC > 0: compile-time filter size / channel count (the divisions become multiplies; the runtime form spent its
+// time in integer div/mod: 0.51 ms for the 7x7 stem at 128 x 256^2 against 0.05 ms of HBM time).
+template <int KC, int CINC>
+__global__ void __launch_bounds__(256) im2col_small_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ out,
+                                                           int N, int H, int W, int Cin_, int Ho, int Wo, int k_, int stride,
+                                                           int pad, int Kpad, long long total) {
+  const int k = KC > 0 ? KC : k_;
+  const int Cin = CINC > 0 ? CINC : Cin_;
   const int chunks = Kpad / 8;
   const int Ktot = k * k * Cin;
+  const unsigned short* __restrict__ xs = reinterpret_cast<const unsigned short*>(x);
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const int ch = (int)(i % chunks);
     long long r = i / chunks;
     const int ox = (int)(r % Wo); r /= Wo;
     const int oy = (int)(r % Ho);
     const int n = (int)(r / Ho);
+    const int iy0 = oy * stride - pad, ix0 = ox * stride - pad;
+    const unsigned short* __restrict__ xn = xs + (long long)n * H * W * Cin;
     unsigned short v[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       const int kk = ch * 8 + j;
-      unsigned short bits = 0;
-      if (kk < Ktot) {
-        const int tap = kk / Cin, ci = kk - tap * Cin;
-        const int ky = tap / k, kx = tap - ky * k;
-        const int iy = oy * stride - pad + ky, ix = ox * stride - pad + kx;
-        if (iy >= 0 && iy < H && ix >= 0 && ix < W)
-          bits = __bfloat16_as_ushort(x[(((long long)n * H + iy) * W + ix) * Cin + ci]);
-      }
-      v[j] = bits;
+      const int tap = kk / Cin, ci = kk - tap * Cin;
+      const int ky = tap / k, kx = tap - ky * k;
+      const int iy = iy0 + ky, ix = ix0 + kx;
+      const bool ok = kk < Ktot && iy >= 0 && iy < H && ix >= 0 && ix < W;
+      v[j] = ok ? __ldg(xn + ((long long)iy * W + ix) * Cin + ci) : (unsigned short)0;
     }
     uint4 pk;
     pk.x = v[0] | ((unsigned)v[1] << 16); pk.y = v[2] | ((unsigned)v[3] << 16);
@@ -838,6 +915,26 @@ static bool vec4_ok(int C, int dtype, std::initializer_list<const void*> ptrs) {
   return true;
 }
 
+// launch geometry of the row-tiled kernels: tpr threads span a row's vectors, ~8 CTAs per SM, >= 8 row passes per CTA
+struct RowTile { int tpr; long long rows_per_block; dim3 grid; };
+static RowTile row_tile(int G, long long R, int C, int vec, int unroll) {
+  RowTile t;
+  const int CVn = C / vec;
+  int tpr = 1;
+  while (tpr * 2 <= CVn && tpr * 2 <= 256) tpr *= 2;
+  t.tpr = tpr;
+  const long long lanes = 256 / tpr;
+  long long want = (8LL * num_sms() + G - 1) / G;
+  long long cap = (R + lanes * unroll * 2 - 1) / (lanes * unroll * 2);
+  long long nblk = want < cap ? want : cap;
+  if (nblk < 1) nblk = 1;
+  if (nblk > 65535) nblk = 65535;
+  t.rows_per_block = (R + nblk - 1) / nblk;
+  nblk = (R + t.rows_per_block - 1) / t.rows_per_block;
+  t.grid = dim3((unsigned)nblk, (unsigned)G);
+  return t;
+}
+
 extern "C" int stfb_bn_partial_blocks(int G, long long R) {
   if (G <= 0 || R <= 0) return 1;
   return colreduce_blocks(G, R);
@@ -879,13 +976,12 @@ extern "C" int stfb_bn_apply(const void* x, const float* scale, const float* shi
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   const long long rows = (long long)G * R;
   if (rows == 0) return STFB_OK;
-  int v = pick_vec(C, dtype, {x, residual, y});
-  if (v > 1 && !(aligned_to(scale, 16) && aligned_to(shift, 16))) v = 1;
-  const long long tv = rows * (C / v);
+  const int v = pick_vec(C, dtype, {x, residual, y});
+  const RowTile rt = row_tile(G, R, C, v, 2);
   DISPATCH_T(dtype, {
-    if (v == 8) bn_apply_kernel<T, 8><<<grid_for(tv), 256, 0, s>>>((const T*)x, scale, shift, (const T*)residual, (T*)y, R, C, tv, relu);
-    else if (v == 4) bn_apply_kernel<T, 4><<<grid_for(tv), 256, 0, s>>>((const T*)x, scale, shift, (const T*)residual, (T*)y, R, C, tv, relu);
-    else bn_apply_kernel<T, 1><<<grid_for(tv), 256, 0, s>>>((const T*)x, scale, shift, (const T*)residual, (T*)y, R, C, tv, relu);
+    if (v == 8) bn_apply_kernel<T, 8><<<rt.grid, 256, 0, s>>>((const T*)x, scale, shift, (const T*)residual, (T*)y, R, C, rt.rows_per_block, rt.tpr, relu);
+    else if (v == 4) bn_apply_kernel<T, 4><<<rt.grid, 256, 0, s>>>((const T*)x, scale, shift, (const T*)residual, (T*)y, R, C, rt.rows_per_block, rt.tpr, relu);
+    else bn_apply_kernel<T, 1><<<rt.grid, 256, 0, s>>>((const T*)x, scale, shift, (const T*)residual, (T*)y, R, C, rt.rows_per_block, rt.tpr, relu);
   });
   return post_launch("bn_apply");
 }
@@ -921,11 +1017,11 @@ extern "C" int stfb_bn_bwd_apply(const void* dy, const void* y, const void* x, c
   const long long rows = (long long)G * R;
   if (rows == 0) return STFB_OK;
   const int v = pick_vec(C, dtype, {dy, y, x, dx, dres});
-  const long long tv = rows * (C / v);
+  const RowTile rt = row_tile(G, R, C, v, 1);
   DISPATCH_T(dtype, {
-    if (v == 8) bn_bwd_apply_kernel<T, 8><<<grid_for(tv), 256, 0, s>>>((const T*)dy, (const T*)y, (const T*)x, mean, invstd, coef, (T*)dx, (T*)dres, R, C, tv, relu, accum_dres);
-    else if (v == 4) bn_bwd_apply_kernel<T, 4><<<grid_for(tv), 256, 0, s>>>((const T*)dy, (const T*)y, (const T*)x, mean, invstd, coef, (T*)dx, (T*)dres, R, C, tv, relu, accum_dres);
-    else bn_bwd_apply_kernel<T, 1><<<grid_for(tv), 256, 0, s>>>((const T*)dy, (const T*)y, (const T*)x, mean, invstd, coef, (T*)dx, (T*)dres, R, C, tv, relu, accum_dres);
+    if (v == 8) bn_bwd_apply_kernel<T, 8><<<rt.grid, 256, 0, s>>>((const T*)dy, (const T*)y, (const T*)x, mean, invstd, coef, (T*)dx, (T*)dres, R, C, rt.rows_per_block, rt.tpr, relu, accum_dres);
+    else if (v == 4) bn_bwd_apply_kernel<T, 4><<<rt.grid, 256, 0, s>>>((const T*)dy, (const T*)y, (const T*)x, mean, invstd, coef, (T*)dx, (T*)dres, R, C, rt.rows_per_block, rt.tpr, relu, accum_dres);
+    else bn_bwd_apply_kernel<T, 1><<<rt.grid, 256, 0, s>>>((const T*)dy, (const T*)y, (const T*)x, mean, invstd, coef, (T*)dx, (T*)dres, R, C, rt.rows_per_block, rt.tpr, relu, accum_dres);
   });
   return post_launch("bn_bwd_apply");
 }
@@ -964,10 +1060,13 @@ extern "C" int stfb_maxpool_fwd_idx(const void* x, void* y, unsigned char* idx, 
   const bool v = (C % 8 == 0) && aligned_to(x, 16) && aligned_to(y, 16) && aligned_to(idx, 8);
   const long long tv = (long long)N * Ho * Wo * (C / (v ? 8 : 1));
   if (tv == 0) return STFB_OK;
+  const int grid = grid_for(tv);
+#define MP_FWD(V, KC) maxpool_fwd_idx_kernel<T, V, KC><<<grid, 256, 0, s>>>((const T*)x, (T*)y, idx, N, H, W, C, Ho, Wo, k, stride, pad, tv)
   DISPATCH_T(dtype, {
-    if (v) maxpool_fwd_idx_kernel<T, 8><<<grid_for(tv), 256, 0, s>>>((const T*)x, (T*)y, idx, N, H, W, C, Ho, Wo, k, stride, pad, tv);
-    else maxpool_fwd_idx_kernel<T, 1><<<grid_for(tv), 256, 0, s>>>((const T*)x, (T*)y, idx, N, H, W, C, Ho, Wo, k, stride, pad, tv);
+    if (v) { if (k == 3) MP_FWD(8, 3); else if (k == 2) MP_FWD(8, 2); else MP_FWD(8, 0); }
+    else { if (k == 3) MP_FWD(1, 3); else if (k == 2) MP_FWD(1, 2); else MP_FWD(1, 0); }
   });
+#undef MP_FWD
   return post_launch("maxpool_fwd_idx");
 }
 
@@ -979,10 +1078,15 @@ extern "C" int stfb_maxpool_bwd_idx(const unsigned char* idx, const void* dy, vo
   const bool v = (C % 8 == 0) && aligned_to(dy, 16) && aligned_to(dx, 16) && aligned_to(idx, 8);
   const long long tv = (long long)N * H * W * (C / (v ? 8 : 1));
   if (tv == 0) return STFB_OK;
+  const int wmax = (k + stride - 1) / stride;        // windows that can contain one input element, per axis
+  STFB_REQUIRE(wmax <= 3, "maxpool_bwd_idx: k (%d) > 3 * stride (%d) is not supported", k, stride);
+  const int grid = grid_for(tv);
+#define MP_BWD(V, WM) maxpool_bwd_idx_kernel<T, V, WM><<<grid, 256, 0, s>>>(idx, (const T*)dy, (T*)dx, N, H, W, C, Ho, Wo, k, stride, pad, tv)
   DISPATCH_T(dtype, {
-    if (v) maxpool_bwd_idx_kernel<T, 8><<<grid_for(tv), 256, 0, s>>>(idx, (const T*)dy, (T*)dx, N, H, W, C, Ho, Wo, k, stride, pad, tv);
-    else maxpool_bwd_idx_kernel<T, 1><<<grid_for(tv), 256, 0, s>>>(idx, (const T*)dy, (T*)dx, N, H, W, C, Ho, Wo, k, stride, pad, tv);
+    if (v) { if (wmax == 1) MP_BWD(8, 1); else if (wmax == 2) MP_BWD(8, 2); else MP_BWD(8, 3); }
+    else { if (wmax == 1) MP_BWD(1, 1); else if (wmax == 2) MP_BWD(1, 2); else MP_BWD(1, 3); }
   });
+#undef MP_BWD
   return post_launch("maxpool_bwd_idx");
 }
 
@@ -1106,8 +1210,17 @@ extern "C" int stfb_im2col_small(const void* x, void* out, int N, int H, int W, 
   STFB_DEVICE_OR_RETURN();
   const long long total = (long long)N * Ho * Wo * (Kpad / 8);
   if (total == 0) return STFB_OK;
-  im2col_small_kernel<<<grid_for(total), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
-      (const __nv_bfloat16*)x, (__nv_bfloat16*)out, N, H, W, Cin, Ho, Wo, k, stride, pad, Kpad, total);
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  const int grid = grid_for(total);
+#define IM2COL_LAUNCH(KC, CC)                                                                                         \
+  im2col_small_kernel<KC, CC><<<grid, 256, 0, s>>>((const __nv_bfloat16*)x, (__nv_bfloat16*)out, N, H, W, Cin, Ho, Wo, k, \
+                                                   stride, pad, Kpad, total)
+  if (k == 7 && Cin == 1) IM2COL_LAUNCH(7, 1);          // STF stem (src/stf_lstm_unet.py:105)
+  else if (k == 7 && Cin == 4) IM2COL_LAUNCH(7, 4);     // STF stem with PK maps
+  else if (k == 3 && Cin == 1) IM2COL_LAUNCH(3, 1);     // UNet enc1.0 with one input channel
+  else if (k == 3 && Cin == 8) IM2COL_LAUNCH(3, 8);     // UNet enc1.0 with the 8 DCE phases as channels
+  else IM2COL_LAUNCH(0, 0);
+#undef IM2COL_LAUNCH
   return post_launch("im2col_small");
 }
 

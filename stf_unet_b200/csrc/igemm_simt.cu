@@ -462,36 +462,33 @@ __global__ void pack_weight_kernel(const float* __restrict__ w, T* __restrict__ 
   }
 }
 
-// all weight packs of a step in ONE launch: job table in device memory, binary search on the element offset
+// all weight packs of a step in ONE launch: job table in device memory, binary search on the work-item offset.
+// One work item = one (d0, d1) position of a weight = its khw filter taps: the taps are contiguous in the source
+// ([D0][D1][kh][kw]), so a warp reads a contiguous run and writes khw coalesced rows of the packed operand.
 template <typename T>
 __global__ void pack_weights_batched_kernel(const stfb_pack_job* __restrict__ jobs, int njobs, long long total) {
   for (long long gi = (long long)blockIdx.x * blockDim.x + threadIdx.x; gi < total; gi += (long long)gridDim.x * blockDim.x) {
     int lo = 0, hi = njobs - 1;
     while (lo < hi) {
       const int mid = (lo + hi + 1) >> 1;
-      if (jobs[mid].start <= gi) lo = mid; else hi = mid - 1;
+      if (__ldg(&jobs[mid].start) <= gi) lo = mid; else hi = mid - 1;
     }
     const stfb_pack_job jb = jobs[lo];
     const long long i = gi - jb.start;
     const int Kc = jb.k_is_dim1 ? jb.D1 : jb.D0, Nc = jb.k_is_dim1 ? jb.D0 : jb.D1;
-    int n, k, tap;
-    if (!jb.n_major) {
-      n = (int)(i % Nc);
-      const long long r = i / Nc;
-      k = (int)(r % Kc);
-      tap = (int)(r / Kc);
-    } else {
-      k = (int)(i % Kc);
-      const long long r = i / Kc;
-      tap = (int)(r % jb.khw);
-      n = (int)(r / jb.khw);
-    }
+    int n, k;
+    if (!jb.n_major) { n = (int)(i % Nc); k = (int)(i / Nc); }      // destination (tap, k, n): n fastest
+    else { k = (int)(i % Kc); n = (int)(i / Kc); }                  // destination (n, tap, k): k fastest
     const int d0 = jb.k_is_dim1 ? n : k, d1 = jb.k_is_dim1 ? k : n;
-    const int stap = jb.flip ? (jb.khw - 1 - tap) : tap;
     int nd = n;
     if (jb.pad_ > 0) { const int gate = n / jb.pad_, u = n - gate * jb.pad_; nd = (u / 64) * 256 + gate * 64 + (u % 64); }
-    const long long di = jb.n_major ? (long long)nd * jb.ld + (long long)tap * Kc + k : i;
-    st1(reinterpret_cast<T*>(jb.dst) + di, jb.src[((long long)d0 * jb.D1 + d1) * jb.khw + stap]);
+    const float* sp = jb.src + ((long long)d0 * jb.D1 + d1) * jb.khw;
+    T* dp = reinterpret_cast<T*>(jb.dst);
+    for (int tap = 0; tap < jb.khw; ++tap) {
+      const int stap = jb.flip ? (jb.khw - 1 - tap) : tap;
+      const long long di = jb.n_major ? (long long)nd * jb.ld + (long long)tap * Kc + k : ((long long)tap * Kc + k) * Nc + n;
+      st1(dp + di, sp[stap]);
+    }
   }
 }
 

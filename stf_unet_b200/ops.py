@@ -270,7 +270,7 @@ class PackPlan:
             khw = 1 if w.dim() == 2 else w.shape[2] * w.shape[3]
             jobs[j] = (w.data_ptr(), buf.data_ptr(), start, D0, D1, khw, int(k_is_dim1), int(n_major), int(flip),
                        shape[1] if n_major else 0, int(gate_c))
-            start += w.numel()
+            start += D0 * D1                      # one work item per (d0, d1) position, all taps
         self.total = start
         self.table = torch.from_numpy(jobs.view(np.uint8)).to(dev)
         self.signature = tuple(params[k[0]].data_ptr() for k in self.keys)
