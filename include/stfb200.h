@@ -122,8 +122,8 @@ int stfb_pack_weight(const float* w, void* wp, int D0, int D1, int kh, int kw, i
  * dgrad of a stride-1 "same" convolution into a forward convolution over dy. */
 int stfb_pack_weight_ex(const float* w, void* wp, int D0, int D1, int kh, int kw, int k_is_dim1, int n_major, int flip,
                         int ld /* n_major row stride, 0 = dense; the caller zero-fills any padding */,
-                        int gate_c /* > 0: LSTM [4C][C] matrix, rows re-ordered so that each 256-row block holds gates
-                                      i,f,g,o of the same 64 hidden units (for stfb_lstm_step_fused) */,
+                        int gate_c /* > 0: LSTM [4C][C] matrix, row gate*C + u goes to (u/16)*64 + gate*16 + u%16: each 256-row
+                                      block holds gates i,f,g,o of the same 64 hidden units (for stfb_lstm_step_fused) */,
                         int dtype, void* stream);
 
 /* Batched form: one launch packs every weight of a step.  `jobs_dev` is a DEVICE array (uploaded once per model);
@@ -208,12 +208,15 @@ int stfb_bilinear_bwd(const void* dy, float* dx, int N, int H, int W, int C, int
  * src/stf_lstm_unet.py:124-127, :216-242).  gates = pre-activations [R][4C] fp32 in PyTorch order i,f,g,o
  * (already containing W_ih x + b_ih + W_hh h + b_hh, produced by stfb_conv2d as 1x1 GEMMs).
  * ---------------------------------------------------------------------------------------------- */
-/* One recurrent step with the cell fused into the tcgen05 GEMM epilogue ("gates never leave the SM"): the accumulator
- * h_prev W_hh^T stays in TMEM, the epilogue adds gates_x (fp32 [rows][4C], i,f,g,o: W_ih x_t + b_ih + b_hh), applies the
- * gate non-linearities and writes c_out (fp32), h_out (bf16) and, for training, the post-activation gates (bf16).
- * bf16 only; C % 64 == 0; w_hh_il = stfb_pack_weight_ex(W_hh, n_major = 1, gate_c = C); h_out must not alias h_prev. */
-int stfb_lstm_step_fused(const void* h_prev, const void* w_hh_il, const float* gates_x, const float* c_prev, float* c_out,
-                         void* h_out, void* acts, int N, int H, int W, int C, void* stream);
+/* One LSTM step as ONE tcgen05 kernel: implicit GEMM over the K-concatenation [x_t, h_{t-1}] against [W_ih | W_hh]
+ * producing all four gates in TMEM, with bias add, gate non-linearities and the cell update fused in the epilogue (the
+ * gate pre-activations never leave the SM).  Writes c_out (fp32 [rows][C]), h_out (bf16 [rows][C]) and, for training,
+ * the post-activation gates acts (bf16 [rows][4C]) in ACCUMULATOR COLUMN ORDER: (gate, unit u) at (u/16)*64 + gate*16 +
+ * u%16 (pass acts_il = 1 to stfb_lstm_cell_bwd).  h_prev = NULL at t = 0 (zero state: only W_ih is walked, c_prev ignored).
+ * bf16 only; C % 64 == 0; w_xh_il = [4C][2C]: stfb_pack_weight_ex(W_ih, n_major = 1, ld = 2C, gate_c = C) into columns
+ * [0, C) and the same for W_hh into columns [C, 2C); h_out must not alias x_t or h_prev; all pointers 16-byte aligned. */
+int stfb_lstm_step_fused(const void* x_t, const void* h_prev, const void* w_xh_il, const float* b_ih, const float* b_hh,
+                         const float* c_prev, float* c_out, void* h_out, void* acts, int N, int H, int W, int C, void* stream);
 /* c_prev may be NULL (t = 0, zero state).  acts (dtype, [R][4C]) may be NULL in eval mode.
  * c_out fp32 [R][C]; h_out dtype [R][C]. */
 int stfb_lstm_cell_fwd(const float* gates, const float* c_prev, void* acts, float* c_out, void* h_out, long long R,
@@ -221,7 +224,8 @@ int stfb_lstm_cell_fwd(const float* gates, const float* c_prev, void* acts, floa
 /* dh fp32 [R][C]; dc fp32 [R][C] in/out (dc_t in, dc_{t-1} out; pass zeros at t = T-1);
  * dgates dtype [R][4C] out. c_prev may be NULL (t = 0). */
 int stfb_lstm_cell_bwd(const float* dh, float* dc, const void* acts, const float* c_prev, const float* c_cur,
-                       void* dgates, long long R, int C, int dtype, void* stream);
+                       void* dgates, long long R, int C, int acts_il /* acts in stfb_lstm_step_fused order */, int dtype,
+                       void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Layout adapters at the API boundary (reference tensors are NCHW fp32).

@@ -32,7 +32,7 @@ _SIGS = {
     "stfb_conv2d_wgrad_tcgen05_supported": [_vp, _vp] + [_i] * 12,
     "stfb_pack_weight": [_vp, _vp, _i, _i, _i, _i, _i, _i, _vp],
     "stfb_pack_weight_ex": [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp],
-    "stfb_lstm_step_fused": [_vp] * 7 + [_i, _i, _i, _i, _vp],
+    "stfb_lstm_step_fused": [_vp] * 9 + [_i, _i, _i, _i, _vp],
     "stfb_wgrad_scatter_batched": [_vp, _i, _ll, _vp, _vp, _vp],
     "stfb_pack_weights_batched": [_vp, _i, _ll, _i, _vp],
     "stfb_im2col_small": [_vp, _vp] + [_i] * 10 + [_vp],
@@ -53,7 +53,7 @@ _SIGS = {
     "stfb_bilinear_fwd": [_vp, _vp] + [_i] * 7 + [_vp],
     "stfb_bilinear_bwd": [_vp, _vp] + [_i] * 7 + [_vp],
     "stfb_lstm_cell_fwd": [_vp] * 5 + [_ll, _i, _i, _vp],
-    "stfb_lstm_cell_bwd": [_vp] * 6 + [_ll, _i, _i, _vp],
+    "stfb_lstm_cell_bwd": [_vp] * 6 + [_ll, _i, _i, _i, _vp],
     "stfb_pack_series": [_vp, _vp] + [_i] * 6 + [_vp],
     "stfb_pack_series_maps": [_vp, _vp, _vp] + [_i] * 7 + [_vp],
     "stfb_repeat": [_vp, _vp, C.c_size_t, _i, _vp],

@@ -43,11 +43,11 @@ struct TcArgs {
   int tiles_w, tiles_h, tiles_n;
   int num_tiles;         // phases * tiles_n * tiles_h * tiles_w * (Cout / BN)
   int relu;
-  // fused LSTM cell epilogue (EPI == 1): accumulator = h_{t-1} W_hh^T with gate-interleaved columns
-  const float* gates_x;  // [rows][4*Chid] fp32, PyTorch order i,f,g,o: W_ih x_t + b_ih + b_hh
-  const float* c_prev;   // [rows][Chid] fp32
+  // fused LSTM cell epilogue (EPI == 1): accumulator = [x_t, h_{t-1}] [W_ih | W_hh]^T with chunk-interleaved columns
+  // (column j of a 256-wide tile: 16-unit chunk j / 64, gate (j % 64) / 16, unit u_base + 16 * chunk + j % 16)
+  const float* c_prev;   // [rows][Chid] fp32 or NULL (t = 0)
   float* c_out;          // [rows][Chid] fp32
-  void* acts;            // [rows][4*Chid] bf16 post-activation gates (NULL in eval)
+  void* acts;            // [rows][4*Chid] bf16 post-activation gates in accumulator column order (NULL in eval)
   int Chid;
   int debug;             // STFB_TC_DEBUG: 1 = no MMAs (TMA pipeline only), 2 = no TMA (MMA issue only); timing experiments
   int ntaps[4];
@@ -59,9 +59,17 @@ constexpr int TC_THREADS = 192;
 // BK = channels per k-block = one swizzle row: 64 bf16 (128 B, SWIZZLE_128B) or 32 bf16 (64 B, SWIZZLE_64B) for the
 // 32-channel layers at the end of the decoder.
 
-template <int BN, int STAGES, int BK>
+// Epilogue staging: every epilogue warp owns TC_STG_SEGS segments of 32 rows x 128 B in shared memory.  Accumulator rows
+// live one per thread (TMEM lane = pixel), but a pixel's channels are contiguous in memory: results are written to the
+// segment row by row (16-byte chunks XOR-swizzled by row, conflict free) and then moved to global memory with 8 lanes per
+// 128-byte row segment, so a warp store instruction touches 4 full lines instead of 32 partial ones (and likewise for
+// the residual / previous-cell-state loads).
+constexpr int TC_SEG_BYTES = 32 * 128;
+template <int EPI>
+__host__ __device__ constexpr int tc_stg_segs() { return EPI == 1 ? 3 : 1; }
+template <int BN, int STAGES, int BK, int EPI = 0>
 constexpr int tc_smem_bytes() {
-  return STAGES * (TC_BM * BK * 2 + BN * BK * 2) + 256 + 1024;
+  return STAGES * (TC_BM * BK * 2 + BN * BK * 2) + 4 * tc_stg_segs<EPI>() * TC_SEG_BYTES + 256 + 1024;
 }
 
 // K-major descriptor for a [rows][BK] bf16 tile whose rows are BK*2 bytes with the matching swizzle
@@ -114,6 +122,67 @@ __device__ __forceinline__ float fast_tanh(float x) {
   float y;
   asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
+}
+
+// ---- epilogue staging helpers ---------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t stg_off(int row, int chunk) { return (uint32_t)(row * 128 + ((chunk ^ (row & 7)) << 4)); }
+// explicit shared-space accesses: the staging pointer comes from an integer round-up of the dynamic smem base, which
+// hides the address space from the compiler (generic ST.E / LD.E to shared memory are several times slower than STS / LDS)
+__device__ __forceinline__ void sts128(uint32_t addr, const uint4& v) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ uint4 lds128(uint32_t addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
+  return v;
+}
+__device__ __forceinline__ void sts128f(uint32_t addr, float a, float b, float c, float d) {
+  sts128(addr, make_uint4(__float_as_uint(a), __float_as_uint(b), __float_as_uint(c), __float_as_uint(d)));
+}
+__device__ __forceinline__ float4 lds128f(uint32_t addr) {
+  const uint4 v = lds128(addr);
+  return make_float4(__uint_as_float(v.x), __uint_as_float(v.y), __uint_as_float(v.z), __uint_as_float(v.w));
+}
+__device__ __forceinline__ uint4 pack8_bf16(const float* v) {
+  __nv_bfloat162 a = __floats2bfloat162_rn(v[0], v[1]), b = __floats2bfloat162_rn(v[2], v[3]);
+  __nv_bfloat162 c = __floats2bfloat162_rn(v[4], v[5]), d = __floats2bfloat162_rn(v[6], v[7]);
+  uint4 t;
+  t.x = *reinterpret_cast<uint32_t*>(&a); t.y = *reinterpret_cast<uint32_t*>(&b);
+  t.z = *reinterpret_cast<uint32_t*>(&c); t.w = *reinterpret_cast<uint32_t*>(&d);
+  return t;
+}
+__device__ __forceinline__ void unpack8_bf16(const uint4& t, float* f) {
+  const uint32_t w[4] = {t.x, t.y, t.z, t.w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float2 p = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w[i]));
+    f[2 * i] = p.x;
+    f[2 * i + 1] = p.y;
+  }
+}
+__device__ __forceinline__ float4 ldg_add4(const float* p, const float* q) {
+  const float4 x = __ldg(reinterpret_cast<const float4*>(p)), y = __ldg(reinterpret_cast<const float4*>(q));
+  return make_float4(x.x + y.x, x.y + y.y, x.z + y.z, x.w + y.w);
+}
+// global -> staging segment: row r of the segment is the 128 bytes at base + cpix[r] * pitch (8 lanes x 16 B per row)
+__device__ __forceinline__ void seg_load(uint32_t seg, const uint8_t* base, const int* cpix, unsigned cmask, long long pitch, int lane) {
+  const int crow = lane >> 3, cch = lane & 7;
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+    if ((cmask >> i) & 1u)
+      sts128(seg + stg_off(i * 4 + crow, cch), *reinterpret_cast<const uint4*>(base + (long long)cpix[i] * pitch + cch * 16));
+  __syncwarp();
+}
+// staging segment -> global; the leading barrier orders the row-per-thread writes before the cooperative reads, the
+// trailing one lets the segment be rewritten
+__device__ __forceinline__ void seg_store(uint32_t seg, uint8_t* base, const int* cpix, unsigned cmask, long long pitch, int lane) {
+  const int crow = lane >> 3, cch = lane & 7;
+  __syncwarp();
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+    if ((cmask >> i) & 1u)
+      *reinterpret_cast<uint4*>(base + (long long)cpix[i] * pitch + cch * 16) = lds128(seg + stg_off(i * 4 + crow, cch));
+  __syncwarp();
 }
 
 template <int BN, int STAGES, typename TO, int BK, int EPI>
@@ -220,9 +289,18 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
     }
   } else {
     // ================= epilogue (warps 2..5; TMEM lane quadrant = warp % 4) =================
+    constexpr int STG_SEGS = tc_stg_segs<EPI>();
     const int q = warp & 3;
+    const uint32_t stg = smem_u32(smem) + STAGES * STAGE_BYTES + q * (STG_SEGS * TC_SEG_BYTES);
     const int m = q * 32 + lane;                       // accumulator row = TMEM lane = pixel in the patch
     const int tw = m % a.TW, th = (m / a.TW) % a.TH, tn = m / (a.TW * a.TH);
+    // cooperative mapping of the staged moves: instruction i handles rows i*4 + lane/8, 16-byte chunk lane%8
+    int cpk[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int mm = q * 32 + i * 4 + (lane >> 3);
+      cpk[i] = (mm % a.TW) | (((mm / a.TW) % a.TH) << 8) | ((mm / (a.TW * a.TH)) << 16);
+    }
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
@@ -230,120 +308,224 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
       const int ow = (t.wb * a.TW + tw) * a.o_scale + t.ph_w, oh = (t.hb * a.TH + th) * a.o_scale + t.ph_h;
       const int on = t.nb * a.TN + tn;
       const bool valid = ow < a.Wout && oh < a.Hout && on < a.N;
-      const long long row = (((long long)on * a.Hout + oh) * a.Wout + ow) * a.Cout + t.n0;
-      TO* __restrict__ yp = reinterpret_cast<TO*>(a.y) + row;
-      const TO* rp = a.residual ? reinterpret_cast<const TO*>(a.residual) + row : nullptr;
+      // pixel index of the rows this lane moves cooperatively (N*Ho*Wo < 2^31 is checked on the host)
+      int cpix[8];
+      unsigned cmask = 0;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int cw = (t.wb * a.TW + (cpk[i] & 0xFF)) * a.o_scale + t.ph_w;
+        const int chh = (t.hb * a.TH + ((cpk[i] >> 8) & 0xFF)) * a.o_scale + t.ph_h;
+        const int cn = t.nb * a.TN + (cpk[i] >> 16);
+        const bool ok = cw < a.Wout && chh < a.Hout && cn < a.N;
+        cpix[i] = ok ? (cn * a.Hout + chh) * a.Wout + cw : 0;
+        cmask |= (ok ? 1u : 0u) << i;
+      }
+      if (a.debug == 3) cmask = 0;
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN);
       if constexpr (EPI == 1) {
-        // ===== fused LSTM cell: this 256-column tile = gates i,f,g,o (64 columns each) of hidden units [n0/4, n0/4 + 64)
-        static_assert(EPI != 1 || BN == 256, "LSTM epilogue needs the 4 x 64 gate-interleaved tile");
+        // ===== fused LSTM cell.  Tile = 64 hidden units [u_base, u_base + 64); TMEM column 64*k + 16*gate + e holds
+        // gate (i,f,g,o) of unit u_base + 16*k + e.  c (fp32) is staged 32 units at a time, h (bf16) once per tile, the
+        // saved activations (bf16, stored in accumulator column order) once per 16-unit chunk.
+        static_assert(EPI != 1 || BN == 256, "LSTM epilogue needs the 256-column gate tile");
         const int C = a.Chid;
         const int u_base = t.n0 / 4;
-        const long long prow = ((long long)on * a.Hout + oh) * a.Wout + ow;       // pixel row
-        const float* gx = a.gates_x + prow * 4 * C;
-        const float* cp = a.c_prev ? a.c_prev + prow * C : nullptr;
-        float* co = a.c_out + prow * C;
-        __nv_bfloat16* ho = reinterpret_cast<__nv_bfloat16*>(a.y) + prow * C;
-        __nv_bfloat16* ac = a.acts ? reinterpret_cast<__nv_bfloat16*>(a.acts) + prow * 4 * C : nullptr;
+        const uint32_t seg_c = stg, seg_h = stg + TC_SEG_BYTES, seg_a = stg + 2 * TC_SEG_BYTES;
+        const long long pitch_c = (long long)C * 4, pitch_h = (long long)C * 2, pitch_a = (long long)C * 8;
+        const uint8_t* cprev_base = a.c_prev ? reinterpret_cast<const uint8_t*>(a.c_prev) + (long long)u_base * 4 : nullptr;
+        uint8_t* cout_base = reinterpret_cast<uint8_t*>(a.c_out) + (long long)u_base * 4;
+        uint8_t* h_base = reinterpret_cast<uint8_t*>(a.y) + (long long)u_base * 2;
+        uint8_t* acts_base = a.acts ? reinterpret_cast<uint8_t*>(a.acts) + (long long)t.n0 * 2 : nullptr;
 #pragma unroll 1
-        for (int u0 = 0; u0 < 64; u0 += 16) {
-          uint32_t ri[16], rf[16], rg[16], ro[16];
-          tmem_ld_x16(taddr + u0, ri);
-          tmem_ld_x16(taddr + 64 + u0, rf);
-          tmem_ld_x16(taddr + 128 + u0, rg);
-          tmem_ld_x16(taddr + 192 + u0, ro);
-          tmem_ld_wait();
-          if (u0 + 16 >= 64) {
+        for (int pair = 0; pair < 2; ++pair) {
+          if (cprev_base) seg_load(seg_c, cprev_base + pair * 128, cpix, cmask, pitch_c, lane);
+#pragma unroll 1
+          for (int kk = 0; kk < 2; ++kk) {
+            const int k = pair * 2 + kk;
+            uint32_t ri[16], rf[16], rg[16], ro[16];
+            if (t.num_kb > 0) {
+              tmem_ld_x16(taddr + k * 64, ri);
+              tmem_ld_x16(taddr + k * 64 + 16, rf);
+              tmem_ld_x16(taddr + k * 64 + 32, rg);
+              tmem_ld_x16(taddr + k * 64 + 48, ro);
+              tmem_ld_wait();
+            }
+            if (k == 3) {
+              tc_fence_before();
+              __syncwarp();
+              if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+            }
+            const int u = u_base + k * 16;
+            float hv[16], cv[16], ai[16], af[16], ag[16], ao[16];
+#pragma unroll
+            for (int e = 0; e < 16; e += 4) {
+              float4 cc = make_float4(0.f, 0.f, 0.f, 0.f);
+              if (cprev_base) cc = lds128f(seg_c + stg_off(lane, kk * 4 + (e >> 2)));
+              const float pc[4] = {cc.x, cc.y, cc.z, cc.w};
+              const int uu = u + e;
+              const float4 bi4 = ldg_add4(a.bias + uu, a.bias2 + uu), bf4 = ldg_add4(a.bias + C + uu, a.bias2 + C + uu);
+              const float4 bg4 = ldg_add4(a.bias + 2 * C + uu, a.bias2 + 2 * C + uu), bo4 = ldg_add4(a.bias + 3 * C + uu, a.bias2 + 3 * C + uu);
+              const float pbi[4] = {bi4.x, bi4.y, bi4.z, bi4.w}, pbf[4] = {bf4.x, bf4.y, bf4.z, bf4.w};
+              const float pbg[4] = {bg4.x, bg4.y, bg4.z, bg4.w}, pbo[4] = {bo4.x, bo4.y, bo4.z, bo4.w};
+#pragma unroll
+              for (int z = 0; z < 4; ++z) {
+                const float bi = pbi[z], bf = pbf[z], bg = pbg[z], bo = pbo[z];
+                ai[e + z] = fast_sigmoid(__uint_as_float(ri[e + z]) + bi);
+                af[e + z] = fast_sigmoid(__uint_as_float(rf[e + z]) + bf);
+                ag[e + z] = fast_tanh(__uint_as_float(rg[e + z]) + bg);
+                ao[e + z] = fast_sigmoid(__uint_as_float(ro[e + z]) + bo);
+                cv[e + z] = af[e + z] * pc[z] + ai[e + z] * ag[e + z];
+                hv[e + z] = ao[e + z] * fast_tanh(cv[e + z]);
+              }
+              sts128f(seg_c + stg_off(lane, kk * 4 + (e >> 2)), cv[e], cv[e + 1], cv[e + 2], cv[e + 3]);
+            }
+            sts128(seg_h + stg_off(lane, k * 2), pack8_bf16(hv));
+            sts128(seg_h + stg_off(lane, k * 2 + 1), pack8_bf16(hv + 8));
+            if (acts_base) {
+              sts128(seg_a + stg_off(lane, 0), pack8_bf16(ai));
+              sts128(seg_a + stg_off(lane, 1), pack8_bf16(ai + 8));
+              sts128(seg_a + stg_off(lane, 2), pack8_bf16(af));
+              sts128(seg_a + stg_off(lane, 3), pack8_bf16(af + 8));
+              sts128(seg_a + stg_off(lane, 4), pack8_bf16(ag));
+              sts128(seg_a + stg_off(lane, 5), pack8_bf16(ag + 8));
+              sts128(seg_a + stg_off(lane, 6), pack8_bf16(ao));
+              sts128(seg_a + stg_off(lane, 7), pack8_bf16(ao + 8));
+              seg_store(seg_a, acts_base + k * 128, cpix, cmask, pitch_a, lane);
+            }
+          }
+          seg_store(seg_c, cout_base + pair * 128, cpix, cmask, pitch_c, lane);
+        }
+        seg_store(seg_h, h_base, cpix, cmask, pitch_h, lane);
+      } else if constexpr (BN * (int)sizeof(TO) >= 128) {
+        // ===== staged epilogue: one 128-byte row segment (64 bf16 / 32 fp32 channels) at a time
+        constexpr int ESZ = (int)sizeof(TO);
+        constexpr int SEGC = 128 / ESZ;
+        constexpr int NSEG = BN / SEGC;
+        const long long pitch = (long long)a.Cout * ESZ;
+        uint8_t* ybase = reinterpret_cast<uint8_t*>(a.y) + (long long)t.n0 * ESZ;
+        const uint8_t* rbase = a.residual ? reinterpret_cast<const uint8_t*>(a.residual) + (long long)t.n0 * ESZ : nullptr;
+#pragma unroll 1
+        for (int seg = 0; seg < NSEG; ++seg) {
+          if (rbase) seg_load(stg, rbase + seg * 128, cpix, cmask, pitch, lane);
+#pragma unroll
+          for (int h = 0; h < SEGC / 32; ++h) {
+            const int c0 = seg * SEGC + h * 32;
+            uint32_t r[32];
+            if (t.num_kb > 0) {
+              tmem_ld_x32(taddr + c0, r);
+              tmem_ld_wait();
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) r[j] = 0u;
+            }
+            if (c0 + 32 >= BN) {         // last chunk is in registers: hand the accumulator buffer back to the MMA warp
+              tc_fence_before();
+              __syncwarp();
+              if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+            }
+            float v[32];
+            const int cg = t.n0 + c0;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+            if (a.bias) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) v[j] += __ldg(a.bias + cg + j);
+            }
+            if (a.bias2) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) v[j] += __ldg(a.bias2 + cg + j);
+            }
+            if (a.scale) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) v[j] = fmaf(v[j], __ldg(a.scale + cg + j), __ldg(a.shift + cg + j));
+            }
+            if (rbase) {
+              if constexpr (ESZ == 2) {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                  const uint4 rv = lds128(stg + stg_off(lane, h * 4 + k));
+                  float f[8];
+                  unpack8_bf16(rv, f);
+#pragma unroll
+                  for (int e = 0; e < 8; ++e) v[k * 8 + e] += f[e];
+                }
+              } else {
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                  const float4 rv = lds128f(stg + stg_off(lane, k));
+                  v[k * 4] += rv.x; v[k * 4 + 1] += rv.y; v[k * 4 + 2] += rv.z; v[k * 4 + 3] += rv.w;
+                }
+              }
+            }
+            if (a.relu) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+            }
+            if constexpr (ESZ == 2) {
+#pragma unroll
+              for (int k = 0; k < 4; ++k) sts128(stg + stg_off(lane, h * 4 + k), pack8_bf16(v + k * 8));
+            } else {
+#pragma unroll
+              for (int k = 0; k < 8; ++k)
+                sts128f(stg + stg_off(lane, k), v[k * 4], v[k * 4 + 1], v[k * 4 + 2], v[k * 4 + 3]);
+            }
+          }
+          seg_store(stg, ybase + seg * 128, cpix, cmask, pitch, lane);
+        }
+      } else {
+        // ===== direct epilogue (rows narrower than 128 B: the 32-channel decoder tail)
+        const long long row = (((long long)on * a.Hout + oh) * a.Wout + ow) * a.Cout + t.n0;
+        TO* __restrict__ yp = reinterpret_cast<TO*>(a.y) + row;
+        const TO* rp = a.residual ? reinterpret_cast<const TO*>(a.residual) + row : nullptr;
+#pragma unroll 1
+        for (int c0 = 0; c0 < BN; c0 += 32) {
+          uint32_t r[32];
+          if (t.num_kb > 0) {
+            tmem_ld_x32(taddr + c0, r);
+            tmem_ld_wait();
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) r[j] = 0u;
+          }
+          if (c0 + 32 >= BN) {
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&tempty_bar[acc]);
           }
-          if (valid) {
-            const int u = u_base + u0;
-            float hv[16], cv[16], ai[16], af[16], ag[16], ao[16];
+          if (valid && a.debug != 3) {
+            float v[32];
+            const int cg = t.n0 + c0;
 #pragma unroll
-            for (int e = 0; e < 16; e += 4) {
-              const float4 xi = *reinterpret_cast<const float4*>(gx + u + e);
-              const float4 xf = *reinterpret_cast<const float4*>(gx + C + u + e);
-              const float4 xg = *reinterpret_cast<const float4*>(gx + 2 * C + u + e);
-              const float4 xo = *reinterpret_cast<const float4*>(gx + 3 * C + u + e);
-              float4 cc = make_float4(0.f, 0.f, 0.f, 0.f);
-              if (cp) cc = *reinterpret_cast<const float4*>(cp + u + e);
-              const float pi[4] = {xi.x, xi.y, xi.z, xi.w}, pf[4] = {xf.x, xf.y, xf.z, xf.w};
-              const float pg[4] = {xg.x, xg.y, xg.z, xg.w}, po[4] = {xo.x, xo.y, xo.z, xo.w};
-              const float pc[4] = {cc.x, cc.y, cc.z, cc.w};
+            for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+            if (a.bias) {
 #pragma unroll
-              for (int z = 0; z < 4; ++z) {
-                ai[e + z] = fast_sigmoid(__uint_as_float(ri[e + z]) + pi[z]);
-                af[e + z] = fast_sigmoid(__uint_as_float(rf[e + z]) + pf[z]);
-                ag[e + z] = fast_tanh(__uint_as_float(rg[e + z]) + pg[z]);
-                ao[e + z] = fast_sigmoid(__uint_as_float(ro[e + z]) + po[z]);
-                cv[e + z] = af[e + z] * pc[z] + ai[e + z] * ag[e + z];
-                hv[e + z] = ao[e + z] * fast_tanh(cv[e + z]);
+              for (int j = 0; j < 32; ++j) v[j] += __ldg(a.bias + cg + j);
+            }
+            if (a.bias2) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) v[j] += __ldg(a.bias2 + cg + j);
+            }
+            if (a.scale) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) v[j] = fmaf(v[j], __ldg(a.scale + cg + j), __ldg(a.shift + cg + j));
+            }
+            if (rp) {
+#pragma unroll
+              for (int j = 0; j < 32; j += 8) {
+                f8 tt = ld8(rp + c0 + j);
+#pragma unroll
+                for (int e = 0; e < 8; ++e) v[j + e] += tt.v[e];
               }
-              *reinterpret_cast<float4*>(co + u + e) = make_float4(cv[e], cv[e + 1], cv[e + 2], cv[e + 3]);
             }
-            st8(ho + u, hv);
-            st8(ho + u + 8, hv + 8);
-            if (ac) {
-              st8(ac + u, ai); st8(ac + u + 8, ai + 8);
-              st8(ac + C + u, af); st8(ac + C + u + 8, af + 8);
-              st8(ac + 2 * C + u, ag); st8(ac + 2 * C + u + 8, ag + 8);
-              st8(ac + 3 * C + u, ao); st8(ac + 3 * C + u + 8, ao + 8);
+            if (a.relu) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
             }
+#pragma unroll
+            for (int j = 0; j < 32; j += 8) st8(yp + c0 + j, v + j);
           }
         }
-      } else {
-#pragma unroll 1
-      for (int c0 = 0; c0 < BN; c0 += 32) {
-        uint32_t r[32];
-        if (t.num_kb > 0) {
-          tmem_ld_x32(taddr + c0, r);
-          tmem_ld_wait();
-        } else {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) r[j] = 0u;
-        }
-        if (c0 + 32 >= BN) {           // last chunk is in registers: hand the accumulator buffer back to the MMA warp
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&tempty_bar[acc]);
-        }
-        if (valid && a.debug != 3) {
-          float v[32];
-          const int cg = t.n0 + c0;
-#pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-          if (a.bias) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] += __ldg(a.bias + cg + j);
-          }
-          if (a.bias2) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] += __ldg(a.bias2 + cg + j);
-          }
-          if (a.scale) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = fmaf(v[j], __ldg(a.scale + cg + j), __ldg(a.shift + cg + j));
-          }
-          if (rp) {
-#pragma unroll
-            for (int j = 0; j < 32; j += 8) {
-              f8 tt = ld8(rp + c0 + j);
-#pragma unroll
-              for (int e = 0; e < 8; ++e) v[j + e] += tt.v[e];
-            }
-          }
-          if (a.relu) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
-          }
-#pragma unroll
-          for (int j = 0; j < 32; j += 8) st8(yp + c0 + j, v + j);
-        }
-      }
       }
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
@@ -430,7 +612,8 @@ bool encode_nhwc_map(EncodeTiledFn enc, CUtensorMap* tm, const void* base, int N
 template <int BN, int STAGES, typename TO, int BK, int EPI = 0>
 static int launch_tc(const CUtensorMap& tA, const CUtensorMap& tA2, const CUtensorMap& tB, const TcArgs& a, dim3 grid,
                      cudaStream_t st) {
-  constexpr int smem = tc_smem_bytes<BN, STAGES, BK>();
+  constexpr int smem = tc_smem_bytes<BN, STAGES, BK, EPI>();
+  static_assert(smem <= 232448, "shared memory budget");
   static bool configured = false;
   if (!configured) {
     if (cudaFuncSetAttribute(conv_tc_kernel<BN, STAGES, TO, BK, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) {
@@ -545,17 +728,18 @@ int conv2d_tcgen05(const stfb_conv_params* p, cudaStream_t st) {
   return STFB_ENOTSUP;
 }
 
-// One recurrent LSTM step on the tensor cores with the cell update fused into the epilogue:
-//   gates = h_prev W_hh^T (TMEM) + gates_x ; c = sig(f) c_prev + sig(i) tanh(g) ; h = sig(o) tanh(c)
-// w_hh_il: W_hh packed [4C][C] K-major with gate-interleaved rows (stfb_pack_weight_ex gate_c = C).
-int lstm_step_tcgen05(const void* h_prev, const void* w_hh_il, const float* gates_x, const float* c_prev, float* c_out,
-                      void* h_out, void* acts, int N, int H, int W, int C, cudaStream_t st) {
+// One LSTM step on the tensor cores, input and recurrent GEMM in ONE K loop with the cell update in the epilogue:
+//   gates = [x_t, h_{t-1}] [W_ih | W_hh]^T (TMEM) + b_ih + b_hh ; c = sig(f) c_prev + sig(i) tanh(g) ; h = sig(o) tanh(c)
+// w_xh_il: [4C][2C] K-major, rows chunk-interleaved (stfb_pack_weight_ex gate_c = C), columns [0,C) = W_ih, [C,2C) = W_hh.
+// h_prev == NULL (t = 0): only the W_ih half of K is walked and c_prev is taken as zero.
+int lstm_step_tcgen05(const void* x_t, const void* h_prev, const void* w_xh_il, const float* b_ih, const float* b_hh,
+                      const float* c_prev, float* c_out, void* h_out, void* acts, int N, int H, int W, int C, cudaStream_t st) {
   EncodeTiledFn enc = get_tensormap_encoder();
   if (!enc) { set_error("lstm_step(tcgen05): cuTensorMapEncodeTiled not available"); return STFB_ECUDA; }
   if ((long long)N * H * W == 0) return STFB_OK;
   TcArgs a{};
-  a.y = h_out; a.gates_x = gates_x; a.c_prev = c_prev; a.c_out = c_out; a.acts = acts; a.Chid = C;
-  a.N = N; a.Hout = H; a.Wout = W; a.Cout = 4 * C; a.C1 = C; a.C2 = 0;
+  a.y = h_out; a.bias = b_ih; a.bias2 = b_hh; a.c_prev = h_prev ? c_prev : nullptr; a.c_out = c_out; a.acts = acts; a.Chid = C;
+  a.N = N; a.Hout = H; a.Wout = W; a.Cout = 4 * C; a.C1 = C; a.C2 = h_prev ? C : 0;
   a.a_scale = 1; a.o_scale = 1; a.nphase_w = 1;
   a.ntaps[0] = 1; a.dh[0][0] = 0; a.dw[0][0] = 0; a.ktap[0][0] = 0;
   pick_patch(H, W, a.TW, a.TH, a.TN);
@@ -563,23 +747,27 @@ int lstm_step_tcgen05(const void* h_prev, const void* w_hh_il, const float* gate
   a.tiles_h = (H + a.TH - 1) / a.TH;
   a.tiles_n = (N + a.TN - 1) / a.TN;
   a.num_tiles = a.tiles_n * a.tiles_h * a.tiles_w * (4 * C / 256);
-  CUtensorMap tA, tB;
-  if (!encode_nhwc_map_strided(enc, &tA, h_prev, N, H, W, C, a.TW, a.TH, a.TN, 1, 64)) {
+  CUtensorMap tA, tA2, tB;
+  if (!encode_nhwc_map_strided(enc, &tA, x_t, N, H, W, C, a.TW, a.TH, a.TN, 1, 64)) {
+    set_error("lstm_step(tcgen05): tensor map (x) failed"); return STFB_ECUDA;
+  }
+  tA2 = tA;
+  if (h_prev && !encode_nhwc_map_strided(enc, &tA2, h_prev, N, H, W, C, a.TW, a.TH, a.TN, 1, 64)) {
     set_error("lstm_step(tcgen05): tensor map (h) failed"); return STFB_ECUDA;
   }
   {
-    cuuint64_t dims[2] = {(cuuint64_t)C, (cuuint64_t)(4 * C)};
-    cuuint64_t strides[1] = {(cuuint64_t)C * 2};
+    cuuint64_t dims[2] = {(cuuint64_t)(a.C1 + a.C2), (cuuint64_t)(4 * C)};
+    cuuint64_t strides[1] = {(cuuint64_t)(2 * C) * 2};
     cuuint32_t box[2] = {64, 256};
     cuuint32_t estr[2] = {1, 1};
-    if (enc(&tB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(w_hh_il), dims, strides, box, estr,
+    if (enc(&tB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(w_xh_il), dims, strides, box, estr,
             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS) {
-      set_error("lstm_step(tcgen05): tensor map (W_hh) failed"); return STFB_ECUDA;
+      set_error("lstm_step(tcgen05): tensor map (W) failed"); return STFB_ECUDA;
     }
   }
   dim3 grid((unsigned)(a.num_tiles < num_sms() ? a.num_tiles : num_sms()));
-  return launch_tc<256, 4, __nv_bfloat16, 64, 1>(tA, tA, tB, a, grid, st);
+  return launch_tc<256, 3, __nv_bfloat16, 64, 1>(tA, tA2, tB, a, grid, st);
 }
 
 }  // namespace stfb

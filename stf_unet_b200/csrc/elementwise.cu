@@ -729,16 +729,19 @@ __global__ void lstm_cell_fwd_kernel(const float* __restrict__ gates, const floa
   }
 }
 
+// acts_il: the saved activations are in the fused step's accumulator column order, (row, gate, u) at
+// row*4C + (u/16)*64 + gate*16 + u%16 (stfb_lstm_step_fused), instead of gate-major [row][gate*C + u].
 template <typename T>
 __global__ void lstm_cell_bwd_kernel(const float* __restrict__ dh, float* dc, const T* __restrict__ acts,
                                      const float* __restrict__ c_prev, const float* __restrict__ c_cur, T* dgates, long long R,
-                                     int C, long long total_vec) {
+                                     int C, long long total_vec, int acts_il) {
   const int CVn = C / 4;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total_vec; i += (long long)gridDim.x * blockDim.x) {
     const long long row = i / CVn;
     const int c = (int)(i - row * CVn) * 4;
-    const T* ap = acts + row * 4 * C + c;
-    const f4 ai = ld4(ap), af = ld4(ap + C), ag = ld4(ap + 2 * C), ao = ld4(ap + 3 * C);
+    const T* ap = acts + row * 4 * C + (acts_il ? (c >> 4) * 64 + (c & 15) : c);
+    const int gs = acts_il ? 16 : C;
+    const f4 ai = ld4(ap), af = ld4(ap + gs), ag = ld4(ap + 2 * gs), ao = ld4(ap + 3 * gs);
     const f4 vdh = ld4(dh + row * C + c), vdc = ld4(dc + row * C + c), cc = ld4(c_cur + row * C + c);
     f4 cp{{0.f, 0.f, 0.f, 0.f}};
     if (c_prev) cp = ld4(c_prev + row * C + c);
@@ -1139,13 +1142,14 @@ extern "C" int stfb_lstm_cell_fwd(const float* gates, const float* c_prev, void*
 }
 
 extern "C" int stfb_lstm_cell_bwd(const float* dh, float* dc, const void* acts, const float* c_prev, const float* c_cur,
-                                  void* dgates, long long R, int C, int dtype, void* stream) {
+                                  void* dgates, long long R, int C, int acts_il, int dtype, void* stream) {
   STFB_REQUIRE(dh && dc && acts && c_cur && dgates && R >= 0 && C > 0 && C % 4 == 0 && DT_OK(dtype), "lstm_cell_bwd: bad arguments");
+  STFB_REQUIRE(!acts_il || C % 64 == 0, "lstm_cell_bwd: interleaved activations need C %% 64 == 0");
   STFB_DEVICE_OR_RETURN();
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   const long long tv = R * (C / 4);
   if (tv == 0) return STFB_OK;
-  DISPATCH_T(dtype, { lstm_cell_bwd_kernel<T><<<grid_for(tv), 256, 0, s>>>(dh, dc, (const T*)acts, c_prev, c_cur, (T*)dgates, R, C, tv); });
+  DISPATCH_T(dtype, { lstm_cell_bwd_kernel<T><<<grid_for(tv), 256, 0, s>>>(dh, dc, (const T*)acts, c_prev, c_cur, (T*)dgates, R, C, tv, acts_il); });
   return post_launch("lstm_cell_bwd");
 }
 

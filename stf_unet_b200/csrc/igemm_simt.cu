@@ -453,10 +453,10 @@ __global__ void pack_weight_kernel(const float* __restrict__ w, T* __restrict__ 
     const int d0 = k_is_dim1 ? n : k, d1 = k_is_dim1 ? k : n;
     const int stap = flip ? (khw - 1 - tap) : tap;   // spatial flip (ky,kx) -> (kh-1-ky, kw-1-kx)
     // n_major rows may be padded to `ld` elements (K padded to the 64-wide k-block; the caller zero-fills the pad).
-    // gate_c > 0: LSTM gate interleave -- source row gate*C + u lands at (u/64)*256 + gate*64 + u%64, so one 256-column
-    // GEMM tile holds i,f,g,o of the same 64 hidden units.
+    // gate_c > 0: LSTM gate interleave -- source row gate*C + u lands at (u/16)*64 + gate*16 + u%16, so one 256-column
+    // GEMM tile holds i,f,g,o of the same 64 hidden units and every 64 columns the four gates of 16 units.
     int nd = n;
-    if (gate_c > 0) { const int gate = n / gate_c, u = n - gate * gate_c; nd = (u / 64) * 256 + gate * 64 + (u % 64); }
+    if (gate_c > 0) { const int gate = n / gate_c, u = n - gate * gate_c; nd = (u / 64) * 256 + ((u % 64) / 16) * 64 + gate * 16 + (u % 16); }
     const long long di = n_major ? (long long)nd * ld + (long long)tap * Kc + k : i;
     st1(wp + di, w[((long long)d0 * D1 + d1) * khw + stap]);
   }
@@ -481,7 +481,7 @@ __global__ void pack_weights_batched_kernel(const stfb_pack_job* __restrict__ jo
     else { k = (int)(i % Kc); n = (int)(i / Kc); }                  // destination (n, tap, k): k fastest
     const int d0 = jb.k_is_dim1 ? n : k, d1 = jb.k_is_dim1 ? k : n;
     int nd = n;
-    if (jb.pad_ > 0) { const int gate = n / jb.pad_, u = n - gate * jb.pad_; nd = (u / 64) * 256 + gate * 64 + (u % 64); }
+    if (jb.pad_ > 0) { const int gate = n / jb.pad_, u = n - gate * jb.pad_; nd = (u / 64) * 256 + ((u % 64) / 16) * 64 + gate * 16 + (u % 16); }
     const float* sp = jb.src + ((long long)d0 * jb.D1 + d1) * jb.khw;
     T* dp = reinterpret_cast<T*>(jb.dst);
     for (int tap = 0; tap < jb.khw; ++tap) {
@@ -519,8 +519,8 @@ int wgrad_tcgen05(const void* P, const void* G, const void* G2, float* dW, int N
 size_t wgrad_tcgen05_workspace_bytes(int N, int H, int W, int Cp, int cg_total, int kh, int kw);
 int wgrad_scatter_batched(const stfb_scatter_job* jobs_dev, int njobs, long long total, const float* acc, float* grad,
                           cudaStream_t st);
-int lstm_step_tcgen05(const void* h_prev, const void* w_hh_il, const float* gates_x, const float* c_prev, float* c_out,
-                      void* h_out, void* acts, int N, int H, int W, int C, cudaStream_t st);
+int lstm_step_tcgen05(const void* x_t, const void* h_prev, const void* w_xh_il, const float* b_ih, const float* b_hh,
+                      const float* c_prev, float* c_out, void* h_out, void* acts, int N, int H, int W, int C, cudaStream_t st);
 }
 
 static int validate_conv(const stfb_conv_params* p) {
@@ -642,15 +642,18 @@ extern "C" int stfb_pack_weight(const float* w, void* wp, int D0, int D1, int kh
   return stfb_pack_weight_ex(w, wp, D0, D1, kh, kw, k_is_dim1, 0, 0, 0, 0, dtype, stream);
 }
 
-extern "C" int stfb_lstm_step_fused(const void* h_prev, const void* w_hh_il, const float* gates_x, const float* c_prev,
-                                    float* c_out, void* h_out, void* acts, int N, int H, int W, int C, void* stream) {
-  STFB_REQUIRE(h_prev && w_hh_il && gates_x && c_out && h_out && N >= 0 && H > 0 && W > 0, "lstm_step_fused: bad arguments");
+extern "C" int stfb_lstm_step_fused(const void* x_t, const void* h_prev, const void* w_xh_il, const float* b_ih,
+                                    const float* b_hh, const float* c_prev, float* c_out, void* h_out, void* acts, int N, int H,
+                                    int W, int C, void* stream) {
+  STFB_REQUIRE(x_t && w_xh_il && b_ih && b_hh && c_out && h_out && N >= 0 && H > 0 && W > 0, "lstm_step_fused: bad arguments");
   STFB_REQUIRE(C > 0 && C % 64 == 0, "lstm_step_fused: hidden size must be a multiple of 64 (got %d)", C);
-  STFB_REQUIRE(h_prev != h_out, "lstm_step_fused: h_out must not alias h_prev (other tiles still read it)");
+  STFB_REQUIRE(h_prev == nullptr || c_prev != nullptr, "lstm_step_fused: h_prev needs c_prev");
+  STFB_REQUIRE(h_prev != h_out && x_t != h_out, "lstm_step_fused: h_out must not alias an input (other tiles still read it)");
+  STFB_REQUIRE((long long)N * H * W < 2000000000LL, "lstm_step_fused: too many rows");
   auto al = [](const void* q) { return q == nullptr || (reinterpret_cast<uintptr_t>(q) % 16) == 0; };
-  STFB_REQUIRE(al(h_prev) && al(w_hh_il) && al(gates_x) && al(c_prev) && al(c_out) && al(h_out) && al(acts),
+  STFB_REQUIRE(al(x_t) && al(h_prev) && al(w_xh_il) && al(b_ih) && al(b_hh) && al(c_prev) && al(c_out) && al(h_out) && al(acts),
                "lstm_step_fused: pointers must be 16-byte aligned");
   STFB_DEVICE_OR_RETURN();
-  return stfb::lstm_step_tcgen05(h_prev, w_hh_il, gates_x, c_prev, c_out, h_out, acts, N, H, W, C,
+  return stfb::lstm_step_tcgen05(x_t, h_prev, w_xh_il, b_ih, b_hh, c_prev, c_out, h_out, acts, N, H, W, C,
                                  reinterpret_cast<cudaStream_t>(stream));
 }

@@ -78,6 +78,18 @@ class Executor:
             self._new_pack_keys.append(key)
         return wp
 
+    def packed_lstm_xh(self, wih, whh, C):
+        """[W_ih | W_hh] K-concatenated, gate rows chunk-interleaved: the B operand of ops.lstm_step_fused."""
+        cat = "xh:" + wih
+        k1 = (wih, True, True, False, None, int(C), (cat, 0, 2 * C))
+        k2 = (whh, True, True, False, None, int(C), (cat, C, 2 * C))
+        wp = self._packed.get(k1)
+        if wp is None:
+            wp = ops.pack_lstm_xh(self.params[wih], self.params[whh], self.dtype)
+            self._packed[k1] = self._packed[k2] = wp
+            self._new_pack_keys += [k1, k2]
+        return wp
+
     _tc_cache = {}
 
     def use_tc(self, x, Cout, k, stride, pad, x2=None, mode=ops.CONV_FWD, out_hw=None):
@@ -283,30 +295,36 @@ class Executor:
         dev = seq.data.device
         wih, whh = prefix + ".weight_ih_l0", prefix + ".weight_hh_l0"
         bih, bhh = prefix + ".bias_ih_l0", prefix + ".bias_hh_l0"
-        # hoisted input GEMM for all T: gates_x = X W_ih^T + b_ih + b_hh  (fp32 pre-activations)
         tc = self.use_tc(seq.data, 4 * C, 1, 1, 0) and self.use_tc(hs_probe(seq.data, B), 4 * C, 1, 1, 0)
         impl = ops.IMPL_TCGEN05 if tc else ops.IMPL_SIMT
-        gates = ops.conv2d(seq.data, self.packed(wih, True, n_major=tc), 4 * C, 1, 1, 0, bias=P[bih], bias2=P[bhh],
-                           y_dtype=torch.float32, impl=impl)
-        gates = gates.view(T, B, h, w, 4 * C)
         keep = self.record
         acts = torch.empty((T, R, 4 * C), dtype=self.dtype, device=dev) if keep else None
         cs = torch.empty((T if keep else 2, R, C), dtype=torch.float32, device=dev)
         hs = torch.empty((T if keep else 2, B, h, w, C), dtype=self.dtype, device=dev)
         fused = tc and C % 64 == 0 and USE_FUSED_LSTM
-        whh_p = self.packed(whh, True, n_major=tc, gate_c=C if fused else 0)
-        for t in range(T):
-            cur = t if keep else t % 2
-            prev = (t - 1) if keep else (t - 1) % 2
-            if t > 0 and fused:
-                # recurrent GEMM + cell update in one kernel: the gate pre-activations never leave the SM
-                ops.lstm_step_fused(hs[prev], whh_p, gates[t], cs[prev], cs[cur], hs[cur],
-                                    acts[t].view(B, h, w, 4 * C) if keep else None)
-                continue
-            if t > 0:  # gates_t += h_{t-1} W_hh^T   (in place through the residual epilogue)
-                ops.conv2d(hs[prev], whh_p, 4 * C, 1, 1, 0, residual=gates[t], out=gates[t], y_dtype=torch.float32,
-                           impl=impl)
-            ops.lstm_cell_fwd(gates[t], cs[prev] if t > 0 else None, acts[t] if keep else None, cs[cur], hs[cur], R, C)
+        if fused:
+            # one kernel per time step: implicit GEMM over [x_t, h_{t-1}] -> four gates in TMEM -> cell update in the
+            # epilogue; the gate pre-activations never exist in memory
+            wxh = self.packed_lstm_xh(wih, whh, C)
+            xs = seq.data.view(T, B, h, w, C)
+            for t in range(T):
+                cur = t if keep else t % 2
+                prev = (t - 1) if keep else (t - 1) % 2
+                ops.lstm_step_fused(xs[t], hs[prev] if t > 0 else None, wxh, P[bih], P[bhh], cs[prev] if t > 0 else None,
+                                    cs[cur], hs[cur], acts[t].view(B, h, w, 4 * C) if keep else None)
+        else:
+            # hoisted input GEMM for all T: gates_x = X W_ih^T + b_ih + b_hh  (fp32 pre-activations)
+            gates = ops.conv2d(seq.data, self.packed(wih, True, n_major=tc), 4 * C, 1, 1, 0, bias=P[bih], bias2=P[bhh],
+                               y_dtype=torch.float32, impl=impl)
+            gates = gates.view(T, B, h, w, 4 * C)
+            whh_p = self.packed(whh, True, n_major=tc)
+            for t in range(T):
+                cur = t if keep else t % 2
+                prev = (t - 1) if keep else (t - 1) % 2
+                if t > 0:  # gates_t += h_{t-1} W_hh^T   (in place through the residual epilogue)
+                    ops.conv2d(hs[prev], whh_p, 4 * C, 1, 1, 0, residual=gates[t], out=gates[t], y_dtype=torch.float32,
+                               impl=impl)
+                ops.lstm_cell_fwd(gates[t], cs[prev] if t > 0 else None, acts[t] if keep else None, cs[cur], hs[cur], R, C)
         last = (T - 1) if keep else (T - 1) % 2
         out = Var(hs[last], grad_dtype=torch.float32)
         if not self.record:
@@ -323,7 +341,7 @@ class Executor:
             implb = ops.IMPL_TCGEN05 if tcb else ops.IMPL_SIMT
             whh_d = self.packed(whh, False, n_major=tcb)
             for t in range(T - 1, -1, -1):
-                ops.lstm_cell_bwd(dh, dc, acts[t], cs[t - 1] if t > 0 else None, cs[t], dG[t], R, C)
+                ops.lstm_cell_bwd(dh, dc, acts[t], cs[t - 1] if t > 0 else None, cs[t], dG[t], R, C, acts_il=fused)
                 if t > 0:
                     dh = ops.conv2d(dG[t], whh_d, C, 1, 1, 0, y_dtype=torch.float32, impl=implb)
             dG_all = dG.view(T * B, h, w, 4 * C)

@@ -14,7 +14,7 @@ from ._lib import BF16, CONV_FWD, CONV_TRANSPOSED, F32, IMPL_AUTO, IMPL_SIMT, IM
 
 __all__ = ["dt_code", "conv2d", "conv2d_wgrad", "pack_weight", "bn_stats", "bn_finalize_train", "bn_fold_eval",
            "bn_apply", "bn_bwd", "colsum", "maxpool_fwd", "maxpool_bwd", "maxpool_fwd_idx", "maxpool_bwd_idx", "bilinear_fwd", "bilinear_bwd",
-           "tcgen05_ok", "im2col_small", "unpad_wgrad", "lstm_step_fused", "lstm_cell_fwd", "lstm_cell_bwd", "pack_series", "pack_series_maps", "repeat_batch", "nhwc_to_nchw", "nchw_to_nhwc", "add_", "cast",
+           "tcgen05_ok", "im2col_small", "unpad_wgrad", "lstm_step_fused", "pack_lstm_xh", "lstm_cell_fwd", "lstm_cell_bwd", "pack_series", "pack_series_maps", "repeat_batch", "nhwc_to_nchw", "nchw_to_nhwc", "add_", "cast",
            "ce_dice_fwd", "ce_dice_bwd", "CONV_FWD", "CONV_TRANSPOSED", "IMPL_AUTO", "IMPL_SIMT", "IMPL_TCGEN05"]
 
 _DT = {torch.float32: F32, torch.bfloat16: BF16}
@@ -259,17 +259,28 @@ class PackPlan:
                           ("k_is_dim1", "<i4"), ("n_major", "<i4"), ("flip", "<i4"), ("ld", "<i4"), ("pad_", "<i4")])
         jobs = np.zeros(len(self.keys), dtype=job_t)
         start = 0
+        cats = {}
         for j, key in enumerate(self.keys):
             name, k_is_dim1, n_major, flip, kpad = key[:5]
             gate_c = key[5] if len(key) > 5 else 0
+            cat = key[6] if len(key) > 6 else None       # (buffer name, column offset, row stride): K-concatenated operands
             w = params[name]
             shape = packed_shape(w, k_is_dim1, n_major, kpad)
-            buf = (torch.zeros if kpad else torch.empty)(shape, dtype=dtype, device=dev)
+            esz = torch.empty((), dtype=dtype).element_size()
+            if cat is not None:
+                cat_name, col_off, ld = cat
+                buf = cats.get(cat_name)
+                if buf is None:
+                    buf = cats[cat_name] = torch.empty((shape[0], ld), dtype=dtype, device=dev)
+                dst = buf.data_ptr() + col_off * esz
+            else:
+                buf = (torch.zeros if kpad else torch.empty)(shape, dtype=dtype, device=dev)
+                dst, ld = buf.data_ptr(), shape[1]
             self.buffers[key] = buf
             D0, D1 = w.shape[0], w.shape[1]
             khw = 1 if w.dim() == 2 else w.shape[2] * w.shape[3]
-            jobs[j] = (w.data_ptr(), buf.data_ptr(), start, D0, D1, khw, int(k_is_dim1), int(n_major), int(flip),
-                       shape[1] if n_major else 0, int(gate_c))
+            jobs[j] = (w.data_ptr(), dst, start, D0, D1, khw, int(k_is_dim1), int(n_major), int(flip),
+                       ld if n_major else 0, int(gate_c))
             start += D0 * D1                      # one work item per (d0, d1) position, all taps
         self.total = start
         self.table = torch.from_numpy(jobs.view(np.uint8)).to(dev)
@@ -430,16 +441,33 @@ def bilinear_bwd(dy, H, W):
     return dx
 
 
-def lstm_step_fused(h_prev, w_hh_il, gates_x, c_prev, c_out, h_out, acts):
-    """One recurrent LSTM step: tcgen05 GEMM h_prev @ W_hh^T with the cell update fused into the epilogue."""
-    N, H, W, C_ = h_prev.shape
+def lstm_step_fused(x_t, h_prev, w_xh_il, b_ih, b_hh, c_prev, c_out, h_out, acts):
+    """One LSTM step: tcgen05 GEMM over [x_t, h_prev] @ [W_ih | W_hh]^T with bias + cell update fused into the epilogue.
+    h_prev / c_prev None at t = 0.  acts (optional) receives the post-activation gates in accumulator column order."""
+    N, H, W, C_ = x_t.shape
     e0 = _prof.begin() if _prof is not None else None
-    check(_lib.load().stfb_lstm_step_fused(_p(h_prev), _p(w_hh_il), _p(gates_x), _p(c_prev), _p(c_out), _p(h_out), _p(acts),
-                                           N, H, W, C_, _stream()), "lstm_step_fused")
+    check(_lib.load().stfb_lstm_step_fused(_p(x_t), _p(h_prev), _p(w_xh_il), _p(b_ih), _p(b_hh), _p(c_prev), _p(c_out),
+                                           _p(h_out), _p(acts), N, H, W, C_, _stream()), "lstm_step_fused")
     if e0 is not None:
         rows = N * H * W
-        _prof.end(e0, "conv_tcgen05", 2.0 * rows * C_ * 4 * C_, rows * C_ * (2 + 16 + 8 + 2 + (8 if acts is not None else 0)),
-                  f"lstm_step_fused rows{rows} C{C_}")
+        kc = C_ * (2 if h_prev is not None else 1)
+        _prof.end(e0, "conv_tcgen05", 2.0 * rows * kc * 4 * C_,
+                  rows * C_ * (2 + 4 + 2 + (2 + 4 if h_prev is not None else 0) + (8 if acts is not None else 0)),
+                  f"lstm_step_fused rows{rows} C{C_} K{kc}")
+
+
+def pack_lstm_xh(w_ih, w_hh, dtype):
+    """[W_ih | W_hh] as one K-major [4C][2C] operand with chunk-interleaved gate rows (for lstm_step_fused)."""
+    C4, C_ = w_ih.shape
+    wp = torch.empty((C4, 2 * C_), dtype=dtype, device=w_ih.device)
+    lib = _lib.load()
+    esz = wp.element_size()
+    with _timed("pack_weight", _nb(w_ih, w_hh, wp)):
+        check(lib.stfb_pack_weight_ex(_p(w_ih), wp.data_ptr(), C4, C_, 1, 1, 1, 1, 0, 2 * C_, C_, dt_code(dtype), _stream()),
+              "pack_weight")
+        check(lib.stfb_pack_weight_ex(_p(w_hh), wp.data_ptr() + C_ * esz, C4, C_, 1, 1, 1, 1, 0, 2 * C_, C_, dt_code(dtype),
+                                      _stream()), "pack_weight")
+    return wp
 
 
 def lstm_cell_fwd(gates, c_prev, acts, c_out, h_out, R, C_):
@@ -452,13 +480,13 @@ def _lstm_cell_fwd(gates, c_prev, acts, c_out, h_out, R, C_):
                                          _stream()), "lstm_cell_fwd")
 
 
-def lstm_cell_bwd(dh, dc, acts, c_prev, c_cur, dgates, R, C_):
+def lstm_cell_bwd(dh, dc, acts, c_prev, c_cur, dgates, R, C_, acts_il=False):
     with _timed("lstm_cell_bwd", R * C_ * (4 + 8 + 4 + (4 if c_prev is not None else 0) + 8 * dgates.element_size())):
-        _lstm_cell_bwd(dh, dc, acts, c_prev, c_cur, dgates, R, C_)
+        _lstm_cell_bwd(dh, dc, acts, c_prev, c_cur, dgates, R, C_, acts_il)
 
 
-def _lstm_cell_bwd(dh, dc, acts, c_prev, c_cur, dgates, R, C_):
-    check(_lib.load().stfb_lstm_cell_bwd(_p(dh), _p(dc), _p(acts), _p(c_prev), _p(c_cur), _p(dgates), R, C_,
+def _lstm_cell_bwd(dh, dc, acts, c_prev, c_cur, dgates, R, C_, acts_il=False):
+    check(_lib.load().stfb_lstm_cell_bwd(_p(dh), _p(dc), _p(acts), _p(c_prev), _p(c_cur), _p(dgates), R, C_, int(acts_il),
                                          dt_code(dgates.dtype), _stream()), "lstm_cell_bwd")
 
 

@@ -541,29 +541,67 @@ def test_small_cin_conv_via_im2col(N, H, W, Cin, Cout, k, stride, pad):
     assert rel(dW, w.grad) < 1e-4
 
 
+def _acts_il_to_gate_major(acts_il, R, C):
+    """[R, 4C] in accumulator column order ((u/16)*64 + gate*16 + u%16) -> gate-major [R, gate*C + u]."""
+    return acts_il.view(R, C // 16, 4, 16).permute(0, 2, 1, 3).reshape(R, 4 * C)
+
+
 @pytest.mark.parametrize("B,h,w,C", [(2, 16, 16, 64), (3, 8, 8, 128), (1, 10, 12, 256), (2, 4, 4, 512)])
 def test_lstm_step_fused_matches_reference(B, h, w, C):
-    """Recurrent GEMM + cell update in one tcgen05 kernel (gate-interleaved W_hh) vs the gate-by-gate reference."""
+    """[x_t, h_{t-1}] @ [W_ih | W_hh]^T + biases + cell update in one tcgen05 kernel vs the gate-by-gate reference
+    (reference: nn.LSTM at src/stf_lstm_unet.py:124-127, :216-242)."""
     bf = torch.bfloat16
     R = B * h * w
+    xt = q(rnd(R, C, seed=7) * 0.7, bf)
     hp = q(rnd(R, C, seed=1) * 0.5, bf)
+    wih = q(rnd(4 * C, C, seed=5, scale=1.0 / C ** 0.5), bf)
     whh = q(rnd(4 * C, C, seed=2, scale=1.0 / C ** 0.5), bf)
-    gx = rnd(R, 4 * C, seed=3)
+    bih = rnd(4 * C, seed=3) * 0.1
+    bhh = rnd(4 * C, seed=6) * 0.1
     cp = rnd(R, C, seed=4)
-    gates = hp @ whh.t() + gx
-    i, f, g, o = gates.split(C, 1)
-    c_ref = torch.sigmoid(f) * cp + torch.sigmoid(i) * torch.tanh(g)
-    h_ref = torch.sigmoid(o) * torch.tanh(c_ref)
-    wp = ops.pack_weight(whh.contiguous(), True, bf, n_major=True, gate_c=C)
-    c_out = torch.empty(R, C, device=DEV)
-    h_out = torch.empty(B, h, w, C, device=DEV, dtype=bf)
-    acts = torch.empty(B, h, w, 4 * C, device=DEV, dtype=bf)
-    ops.lstm_step_fused(hp.to(bf).view(B, h, w, C), wp, gx, cp, c_out, h_out, acts)
-    torch.cuda.synchronize()
-    assert rel(c_out, c_ref) < 3e-3
-    assert rel(h_out.view(R, C), h_ref) < 6e-3
-    a_ref = torch.cat([torch.sigmoid(i), torch.sigmoid(f), torch.tanh(g), torch.sigmoid(o)], 1)
-    assert rel(acts.view(R, 4 * C), a_ref) < 6e-3
-    # eval form: no saved activations
-    ops.lstm_step_fused(hp.to(bf).view(B, h, w, C), wp, gx, cp, c_out, h_out, None)
-    assert rel(c_out, c_ref) < 3e-3
+    wp = ops.pack_lstm_xh(wih.contiguous(), whh.contiguous(), bf)
+
+    def ref(with_h):
+        gates = xt @ wih.t() + bih + bhh
+        cprev = torch.zeros_like(cp)
+        if with_h:
+            gates = gates + hp @ whh.t()
+            cprev = cp
+        i, f, g, o = gates.split(C, 1)
+        c_ref = torch.sigmoid(f) * cprev + torch.sigmoid(i) * torch.tanh(g)
+        h_ref = torch.sigmoid(o) * torch.tanh(c_ref)
+        a_ref = torch.cat([torch.sigmoid(i), torch.sigmoid(f), torch.tanh(g), torch.sigmoid(o)], 1)
+        return c_ref, h_ref, a_ref
+
+    for with_h in (True, False):
+        c_ref, h_ref, a_ref = ref(with_h)
+        c_out = torch.full((R, C), float("nan"), device=DEV)
+        h_out = torch.empty(B, h, w, C, device=DEV, dtype=bf)
+        acts = torch.empty(B, h, w, 4 * C, device=DEV, dtype=bf)
+        ops.lstm_step_fused(xt.to(bf).view(B, h, w, C), hp.to(bf).view(B, h, w, C) if with_h else None, wp, bih, bhh,
+                            cp if with_h else None, c_out, h_out, acts)
+        torch.cuda.synchronize()
+        assert rel(c_out, c_ref) < 3e-3
+        assert rel(h_out.view(R, C), h_ref) < 6e-3
+        assert rel(_acts_il_to_gate_major(acts.view(R, 4 * C).float(), R, C), a_ref) < 6e-3
+        # eval form: no saved activations
+        c2 = torch.empty_like(c_out)
+        ops.lstm_step_fused(xt.to(bf).view(B, h, w, C), hp.to(bf).view(B, h, w, C) if with_h else None, wp, bih, bhh,
+                            cp if with_h else None, c2, h_out, None)
+        assert rel(c2, c_ref) < 3e-3
+
+
+def test_lstm_cell_bwd_interleaved_acts_matches_gate_major():
+    """lstm_cell_bwd reads the fused step's activation layout (acts_il) and must agree with the gate-major form."""
+    bf = torch.bfloat16
+    R, C = 96, 128
+    a_gm = torch.rand(R, 4 * C, device=DEV).to(bf)
+    a_il = a_gm.view(R, 4, C // 16, 16).permute(0, 2, 1, 3).reshape(R, 4 * C).contiguous()
+    dh, cp, cc = rnd(R, C, seed=1), rnd(R, C, seed=2), rnd(R, C, seed=3)
+    outs = []
+    for acts, il in ((a_gm, False), (a_il, True)):
+        dc = rnd(R, C, seed=4).clone()
+        dg = torch.empty(R, 4 * C, device=DEV, dtype=bf)
+        ops.lstm_cell_bwd(dh, dc, acts, cp, cc, dg, R, C, acts_il=il)
+        outs.append((dg.float(), dc))
+    assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])

@@ -55,6 +55,22 @@ def main():
             ms = timeit(lambda: ops.conv2d_wgrad(dy, x, dW, k, 1, (k - 1) // 2, 0, Cin, impl=ops.IMPL_TCGEN05), a.iters)
             fl = 2.0 * N * H * W * Cin * Cout * k * k
             print(f"wgrad  N{N} {H}x{W} {Cin}->{Cout} k{k}: {ms * 1e3:8.1f} us  {fl / ms / 1e9:8.1f} TFLOP/s")
+    if a.what in ("lstm", "all"):
+        for (B, h, w, C) in [(16, 64, 64, 64), (16, 32, 32, 128), (16, 16, 16, 256), (16, 8, 8, 512)]:
+            R = B * h * w
+            xt = torch.randn(B, h, w, C, device=DEV).to(bf)
+            hp = torch.randn(B, h, w, C, device=DEV).to(bf)
+            wih = torch.randn(4 * C, C, device=DEV) / C ** 0.5
+            whh = torch.randn(4 * C, C, device=DEV) / C ** 0.5
+            bih, bhh = torch.randn(4 * C, device=DEV) * 0.1, torch.randn(4 * C, device=DEV) * 0.1
+            cp = torch.randn(R, C, device=DEV)
+            wp = ops.pack_lstm_xh(wih, whh, bf)
+            c_out = torch.empty(R, C, device=DEV)
+            h_out = torch.empty(B, h, w, C, device=DEV, dtype=bf)
+            acts = torch.empty(B, h, w, 4 * C, device=DEV, dtype=bf)
+            ms = timeit(lambda: ops.lstm_step_fused(xt, hp, wp, bih, bhh, cp, c_out, h_out, acts), a.iters)
+            nbytes = R * C * (2 + 2 + 4 + 4 + 2 + 8)
+            print(f"lstm   rows{R} C{C}: {ms * 1e3:8.1f} us  {2.0 * R * 2 * C * 4 * C / ms / 1e9:8.1f} TFLOP/s  {nbytes / ms / 1e6:8.1f} GB/s")
     if a.what in ("bn", "all"):
         for (N, H, W, C) in [(128, 128, 128, 64), (128, 64, 64, 64), (128, 32, 32, 128), (128, 16, 16, 256), (128, 8, 8, 512)]:
             G, R = 8, (N // 8) * H * W
