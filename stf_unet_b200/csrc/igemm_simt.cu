@@ -517,6 +517,11 @@ int wgrad_tcgen05(const void* P, const void* G, const void* G2, float* dW, int N
                   int C1, int C2, int cg_off, int cg_total, int kh, int kw, int stride, int pad, float* ws, size_t ws_bytes,
                   cudaStream_t st);
 size_t wgrad_tcgen05_workspace_bytes(int N, int H, int W, int Cp, int cg_total, int kh, int kw);
+int wgrad_pairs_supported(int N, int Hp, int Wp, int Cp, int Hg, int Wg, int Cg, int cg_off, int cg_total, int kh, int kw,
+                          int stride, int pad, int dtype, const void* P, const void* G);
+size_t wgrad_pairs_workspace_bytes(int Cp, int Cg);
+int wgrad_pairs(const void* P, const void* G, float* dW, int N, int H, int W, int Cp, int Cg, float* ws, size_t ws_bytes,
+                cudaStream_t st);
 int wgrad_scatter_batched(const stfb_scatter_job* jobs_dev, int njobs, long long total, const float* acc, float* grad,
                           cudaStream_t st);
 int lstm_step_tcgen05(const void* x_t, const void* h_prev, const void* w_xh_il, const float* b_ih, const float* b_hh,
@@ -578,6 +583,8 @@ extern "C" size_t stfb_conv2d_wgrad_workspace_bytes(const void* P, const void* G
                                                     int Cg, int cg_total, int kh, int kw, int stride, int pad, int dtype,
                                                     int impl) {
   if (impl == STFB_IMPL_SIMT) return 0;
+  if (stfb::wgrad_pairs_supported(N, Hp, Wp, Cp, Hg, Wg, Cg, 0, cg_total, kh, kw, stride, pad, dtype, P, G))
+    return stfb::wgrad_pairs_workspace_bytes(Cp, Cg);
   if (!stfb::wgrad_tcgen05_supported(N, Hp, Wp, Cp, Hg, Wg, Cg, kh, kw, stride, pad, dtype, P, G)) return 0;
   return stfb::wgrad_tcgen05_workspace_bytes(N, Hp, Wp, Cp, cg_total, kh, kw);
 }
@@ -602,6 +609,10 @@ extern "C" int stfb_conv2d_wgrad(const void* P, const void* G, float* dW, int N,
     const int ok = stfb::wgrad_tcgen05_supported(N, Hp, Wp, Cp, Hg, Wg, Cg, kh, kw, stride, pad, dtype, P, G);
     if (ok) return stfb::wgrad_tcgen05(P, G, nullptr, dW, N, Hp, Wp, Cp, Hg, Wg, Cg, 0, cg_off, cg_total, kh, kw, stride, pad,
                                        reinterpret_cast<float*>(workspace), ws_bytes, reinterpret_cast<cudaStream_t>(stream));
+    if (dW != nullptr && workspace != nullptr &&
+        stfb::wgrad_pairs_supported(N, Hp, Wp, Cp, Hg, Wg, Cg, cg_off, cg_total, kh, kw, stride, pad, dtype, P, G))
+      return stfb::wgrad_pairs(P, G, dW, N, Hp, Wp, Cp, Cg, reinterpret_cast<float*>(workspace), ws_bytes,
+                               reinterpret_cast<cudaStream_t>(stream));
     if (impl == STFB_IMPL_TCGEN05) {
       set_error("conv2d_wgrad: shape not supported by the tcgen05 family");
       return STFB_ENOTSUP;

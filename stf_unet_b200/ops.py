@@ -174,9 +174,12 @@ def conv2d_wgrad(P, G, dW, k, stride, pad, cg_off=0, cg_total=None, impl=IMPL_AU
         check(lib.stfb_conv2d_wgrad(_p(P), _p(G), None, N, Hp, Wp, Cp, Hg, Wg, Cg, cg_off, cgt, kh, kw, stride, pad, dt, impl,
                                     _p(acc), acc.numel() * 4, _stream()), "conv2d_wgrad")
     else:
+        # non-zero for the tcgen05 family and for the pixel-paired 32-channel path (then `tc` is False but the launch is
+        # still a tcgen05 one)
         ws_bytes = lib.stfb_conv2d_wgrad_workspace_bytes(_p(P), _p(G), N, Hp, Wp, Cp, Hg, Wg, Cg, cgt, kh, kw, stride, pad, dt,
-                                                         impl) if tc else 0
+                                                         impl) if (impl != IMPL_SIMT and cg_off == 0 and cgt == Cg) or tc else 0
         ws = torch.empty((ws_bytes // 4,), dtype=torch.float32, device=P.device) if ws_bytes else None
+        tc = tc or ws_bytes > 0
         check(lib.stfb_conv2d_wgrad(_p(P), _p(G), _p(dW), N, Hp, Wp, Cp, Hg, Wg, Cg, cg_off, cgt, kh, kw, stride, pad, dt,
                                     impl, _p(ws), ws_bytes, _stream()), "conv2d_wgrad")
     if e0 is not None:

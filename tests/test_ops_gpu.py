@@ -506,6 +506,25 @@ def test_wgrad_tcgen05_stride2(case):
     assert rel(dW, w.grad) < 1e-4
 
 
+@pytest.mark.parametrize("case", [(2, 16, 16, 32, 32), (1, 12, 20, 32, 32), (3, 7, 10, 32, 96)])
+def test_wgrad_pixel_pairs_32_channels(case):
+    """32-channel 3x3 layers (final_res, src/stf_lstm_unet.py:136) through the 64-channel tcgen05 wgrad kernel via pixel
+    pairing ([N,H,W,32] viewed as [N,H,W/2,64]) + the fold kernel."""
+    N, H, W, Cin, Cout = case
+    dtype = torch.bfloat16
+    x = q(rnd(N, Cin, H, W, seed=1), dtype)
+    w = torch.zeros(Cout, Cin, 3, 3, device=DEV, requires_grad=True)
+    y = F.conv2d(x, w, None, 1, 1)
+    dy = q(rnd(*y.shape, seed=2), dtype)
+    y.backward(dy)
+    dW = torch.full((Cout, Cin, 3, 3), 0.5, device=DEV)       # accumulates into what is there
+    from stf_unet_b200 import _lib
+    n0 = _lib.launch_count()
+    ops.conv2d_wgrad(nhwc(dy, dtype), nhwc(x, dtype), dW, 3, 1, 1, 0, Cin)
+    torch.cuda.synchronize()
+    assert rel(dW - 0.5, w.grad) < 1e-4
+
+
 def test_wgrad_tcgen05_conv_transpose():
     N, H, W, Cin, Cout, k = 2, 8, 8, 128, 64, 3
     dtype = torch.bfloat16
