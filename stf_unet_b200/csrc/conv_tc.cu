@@ -49,6 +49,7 @@ struct TcArgs {
   float* c_out;          // [rows][Chid] fp32
   void* acts;            // [rows][4*Chid] bf16 post-activation gates in accumulator column order (NULL in eval)
   int Chid;
+  int w_resident;        // halo kernel: the whole weight matrix sits in the B ring (loaded once, never released)
   int debug;             // STFB_TC_DEBUG: 1 = no MMAs (TMA pipeline only), 2 = no TMA (MMA issue only); timing experiments
   int ntaps[4];
   signed char dh[4][9], dw[4][9], ktap[4][9];
@@ -185,6 +186,144 @@ __device__ __forceinline__ void seg_store(uint32_t seg, uint8_t* base, const int
   __syncwarp();
 }
 
+
+// Generic epilogue of one output tile (bias / folded BN / residual / ReLU -> TO), shared by the streaming and the halo
+// kernels.  `taddr` = this warp's TMEM lane quadrant + accumulator buffer, `stg` = its staging segment (shared space).
+template <int BN, typename TO>
+__device__ __forceinline__ void epilogue_tile(const TcArgs& a, const TileCoord& t, uint32_t taddr, uint32_t stg, const int* cpix,
+                                              unsigned cmask, bool valid, int on, int oh, int ow, uint64_t* tempty, int lane) {
+  if constexpr (BN * (int)sizeof(TO) >= 128) {
+    // ===== staged epilogue: one 128-byte row segment (64 bf16 / 32 fp32 channels) at a time
+    constexpr int ESZ = (int)sizeof(TO);
+    constexpr int SEGC = 128 / ESZ;
+    constexpr int NSEG = BN / SEGC;
+    const long long pitch = (long long)a.Cout * ESZ;
+    uint8_t* ybase = reinterpret_cast<uint8_t*>(a.y) + (long long)t.n0 * ESZ;
+    const uint8_t* rbase = a.residual ? reinterpret_cast<const uint8_t*>(a.residual) + (long long)t.n0 * ESZ : nullptr;
+#pragma unroll 1
+    for (int seg = 0; seg < NSEG; ++seg) {
+      if (rbase) seg_load(stg, rbase + seg * 128, cpix, cmask, pitch, lane);
+#pragma unroll
+      for (int h = 0; h < SEGC / 32; ++h) {
+        const int c0 = seg * SEGC + h * 32;
+        uint32_t r[32];
+        if (t.num_kb > 0) {
+          tmem_ld_x32(taddr + c0, r);
+          tmem_ld_wait();
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) r[j] = 0u;
+        }
+        if (c0 + 32 >= BN) {         // last chunk is in registers: hand the accumulator buffer back to the MMA warp
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(tempty);
+        }
+        float v[32];
+        const int cg = t.n0 + c0;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+        if (a.bias) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] += __ldg(a.bias + cg + j);
+        }
+        if (a.bias2) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] += __ldg(a.bias2 + cg + j);
+        }
+        if (a.scale) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = fmaf(v[j], __ldg(a.scale + cg + j), __ldg(a.shift + cg + j));
+        }
+        if (rbase) {
+          if constexpr (ESZ == 2) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const uint4 rv = lds128(stg + stg_off(lane, h * 4 + k));
+              float f[8];
+              unpack8_bf16(rv, f);
+#pragma unroll
+              for (int e = 0; e < 8; ++e) v[k * 8 + e] += f[e];
+            }
+          } else {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+              const float4 rv = lds128f(stg + stg_off(lane, k));
+              v[k * 4] += rv.x; v[k * 4 + 1] += rv.y; v[k * 4 + 2] += rv.z; v[k * 4 + 3] += rv.w;
+            }
+          }
+        }
+        if (a.relu) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+        }
+        if constexpr (ESZ == 2) {
+#pragma unroll
+          for (int k = 0; k < 4; ++k) sts128(stg + stg_off(lane, h * 4 + k), pack8_bf16(v + k * 8));
+        } else {
+#pragma unroll
+          for (int k = 0; k < 8; ++k)
+            sts128f(stg + stg_off(lane, k), v[k * 4], v[k * 4 + 1], v[k * 4 + 2], v[k * 4 + 3]);
+        }
+      }
+      seg_store(stg, ybase + seg * 128, cpix, cmask, pitch, lane);
+    }
+  } else {
+    // ===== direct epilogue (rows narrower than 128 B: the 32-channel decoder tail)
+    const long long row = (((long long)on * a.Hout + oh) * a.Wout + ow) * a.Cout + t.n0;
+    TO* __restrict__ yp = reinterpret_cast<TO*>(a.y) + row;
+    const TO* rp = a.residual ? reinterpret_cast<const TO*>(a.residual) + row : nullptr;
+#pragma unroll 1
+    for (int c0 = 0; c0 < BN; c0 += 32) {
+      uint32_t r[32];
+      if (t.num_kb > 0) {
+        tmem_ld_x32(taddr + c0, r);
+        tmem_ld_wait();
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) r[j] = 0u;
+      }
+      if (c0 + 32 >= BN) {
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(tempty);
+      }
+      if (valid && a.debug != 3) {
+        float v[32];
+        const int cg = t.n0 + c0;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+        if (a.bias) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] += __ldg(a.bias + cg + j);
+        }
+        if (a.bias2) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] += __ldg(a.bias2 + cg + j);
+        }
+        if (a.scale) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = fmaf(v[j], __ldg(a.scale + cg + j), __ldg(a.shift + cg + j));
+        }
+        if (rp) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 8) {
+            f8 tt = ld8(rp + c0 + j);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) v[j + e] += tt.v[e];
+          }
+        }
+        if (a.relu) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+        }
+#pragma unroll
+        for (int j = 0; j < 32; j += 8) st8(yp + c0 + j, v + j);
+      }
+    }
+  }
+}
+
 template <int BN, int STAGES, typename TO, int BK, int EPI>
 __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_constant__ CUtensorMap tmA,
                                                                  const __grid_constant__ CUtensorMap tmA2,
@@ -227,7 +366,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
 
   if (warp == 0) {
     // ================= TMA producer =================
-    if (lane == 0) {
+    if (elect_one()) {
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
@@ -266,7 +405,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
       for (int kb = 0; kb < t.num_kb; ++kb) {
         mbar_wait(&full_bar[stage], phase);
         tc_fence_after();
-        if (lane == 0) {
+        if (elect_one()) {
           const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
           const uint64_t adesc = make_kmajor_desc<BK>(sa);
           const uint64_t bdesc = make_kmajor_desc<BK>(sa + TC_A_BYTES);
@@ -397,136 +536,191 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
           seg_store(seg_c, cout_base + pair * 128, cpix, cmask, pitch_c, lane);
         }
         seg_store(seg_h, h_base, cpix, cmask, pitch_h, lane);
-      } else if constexpr (BN * (int)sizeof(TO) >= 128) {
-        // ===== staged epilogue: one 128-byte row segment (64 bf16 / 32 fp32 channels) at a time
-        constexpr int ESZ = (int)sizeof(TO);
-        constexpr int SEGC = 128 / ESZ;
-        constexpr int NSEG = BN / SEGC;
-        const long long pitch = (long long)a.Cout * ESZ;
-        uint8_t* ybase = reinterpret_cast<uint8_t*>(a.y) + (long long)t.n0 * ESZ;
-        const uint8_t* rbase = a.residual ? reinterpret_cast<const uint8_t*>(a.residual) + (long long)t.n0 * ESZ : nullptr;
-#pragma unroll 1
-        for (int seg = 0; seg < NSEG; ++seg) {
-          if (rbase) seg_load(stg, rbase + seg * 128, cpix, cmask, pitch, lane);
-#pragma unroll
-          for (int h = 0; h < SEGC / 32; ++h) {
-            const int c0 = seg * SEGC + h * 32;
-            uint32_t r[32];
-            if (t.num_kb > 0) {
-              tmem_ld_x32(taddr + c0, r);
-              tmem_ld_wait();
-            } else {
-#pragma unroll
-              for (int j = 0; j < 32; ++j) r[j] = 0u;
-            }
-            if (c0 + 32 >= BN) {         // last chunk is in registers: hand the accumulator buffer back to the MMA warp
-              tc_fence_before();
-              __syncwarp();
-              if (lane == 0) mbar_arrive(&tempty_bar[acc]);
-            }
-            float v[32];
-            const int cg = t.n0 + c0;
-#pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-            if (a.bias) {
-#pragma unroll
-              for (int j = 0; j < 32; ++j) v[j] += __ldg(a.bias + cg + j);
-            }
-            if (a.bias2) {
-#pragma unroll
-              for (int j = 0; j < 32; ++j) v[j] += __ldg(a.bias2 + cg + j);
-            }
-            if (a.scale) {
-#pragma unroll
-              for (int j = 0; j < 32; ++j) v[j] = fmaf(v[j], __ldg(a.scale + cg + j), __ldg(a.shift + cg + j));
-            }
-            if (rbase) {
-              if constexpr (ESZ == 2) {
-#pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                  const uint4 rv = lds128(stg + stg_off(lane, h * 4 + k));
-                  float f[8];
-                  unpack8_bf16(rv, f);
-#pragma unroll
-                  for (int e = 0; e < 8; ++e) v[k * 8 + e] += f[e];
-                }
-              } else {
-#pragma unroll
-                for (int k = 0; k < 8; ++k) {
-                  const float4 rv = lds128f(stg + stg_off(lane, k));
-                  v[k * 4] += rv.x; v[k * 4 + 1] += rv.y; v[k * 4 + 2] += rv.z; v[k * 4 + 3] += rv.w;
-                }
-              }
-            }
-            if (a.relu) {
-#pragma unroll
-              for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
-            }
-            if constexpr (ESZ == 2) {
-#pragma unroll
-              for (int k = 0; k < 4; ++k) sts128(stg + stg_off(lane, h * 4 + k), pack8_bf16(v + k * 8));
-            } else {
-#pragma unroll
-              for (int k = 0; k < 8; ++k)
-                sts128f(stg + stg_off(lane, k), v[k * 4], v[k * 4 + 1], v[k * 4 + 2], v[k * 4 + 3]);
-            }
-          }
-          seg_store(stg, ybase + seg * 128, cpix, cmask, pitch, lane);
-        }
       } else {
-        // ===== direct epilogue (rows narrower than 128 B: the 32-channel decoder tail)
-        const long long row = (((long long)on * a.Hout + oh) * a.Wout + ow) * a.Cout + t.n0;
-        TO* __restrict__ yp = reinterpret_cast<TO*>(a.y) + row;
-        const TO* rp = a.residual ? reinterpret_cast<const TO*>(a.residual) + row : nullptr;
-#pragma unroll 1
-        for (int c0 = 0; c0 < BN; c0 += 32) {
-          uint32_t r[32];
-          if (t.num_kb > 0) {
-            tmem_ld_x32(taddr + c0, r);
-            tmem_ld_wait();
-          } else {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) r[j] = 0u;
-          }
-          if (c0 + 32 >= BN) {
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&tempty_bar[acc]);
-          }
-          if (valid && a.debug != 3) {
-            float v[32];
-            const int cg = t.n0 + c0;
-#pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-            if (a.bias) {
-#pragma unroll
-              for (int j = 0; j < 32; ++j) v[j] += __ldg(a.bias + cg + j);
+        epilogue_tile<BN, TO>(a, t, taddr, stg, cpix, cmask, valid, on, oh, ow, &tempty_bar[acc], lane);
+      }
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, TMEM_COLS);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Halo variant for 3x3 / stride-1 "same" convolutions (forward and dgrad): the streaming kernel above fetches the
+// input patch once per filter tap (9 shifted 16 KB boxes per 64 channels) and is bound by the L2 -> SM fill rate
+// (profiles/: 8.5 TB/s, tensor pipe 18 % on the 64-channel layer).  Here a tile is an 8 x 16 pixel patch of ONE image and
+// the A operand of all nine taps is ONE (8+2) x (16+2) pixel box per 64 channels (23 KB instead of 144 KB): tap (r, s) is
+// the same shared-memory block read through a descriptor that starts (r*10 + s) rows further down, with 1280 B (= one
+// halo row of 10 pixels) between 8-pixel row groups instead of the dense 1024 B.  The 128-byte swizzle is a function of
+// the shared-memory address bits, so TMA's write pattern and the shifted MMA reads agree.
+// Weights stream through their own ring of (tap, 64-channel) blocks; when the whole matrix fits (64 -> 64 channels:
+// 72 KB) it is loaded once per CTA and stays resident.
+constexpr int HALO_TW = 8, HALO_TH = 16;
+constexpr int HALO_PITCH = (HALO_TW + 2) * 128;                      // bytes between patch rows in the halo block
+constexpr int HALO_TX_BYTES = (HALO_TH + 2) * (HALO_TW + 2) * 128;   // 23040 B per TMA box
+constexpr int HALO_BLK_BYTES = 23552;                                // rounded up to the 1 KB swizzle period
+
+template <int BN, int SA, int SB>
+constexpr int halo_smem_bytes() {
+  return SA * HALO_BLK_BYTES + SB * BN * 128 + 4 * TC_SEG_BYTES + 512 + 1024;
+}
+
+__device__ __forceinline__ uint64_t make_halo_a_desc(uint32_t saddr) {
+  return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)(HALO_PITCH >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
+}
+
+template <int BN, int SA, int SB, typename TO>
+__global__ void __launch_bounds__(TC_THREADS, 1) conv_halo_kernel(const __grid_constant__ CUtensorMap tmA,
+                                                                   const __grid_constant__ CUtensorMap tmA2,
+                                                                   const __grid_constant__ CUtensorMap tmB, const TcArgs a) {
+  constexpr int B_BYTES = BN * 128;
+  constexpr int TMEM_COLS = (2 * BN < 32) ? 32 : 2 * BN;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const uint32_t sA = smem_u32(smem);
+  const uint32_t sB = sA + SA * HALO_BLK_BYTES;
+  const uint32_t sStg = sB + SB * B_BYTES;
+  uint64_t* afull = reinterpret_cast<uint64_t*>(smem + SA * HALO_BLK_BYTES + SB * B_BYTES + 4 * TC_SEG_BYTES);
+  uint64_t* aempty = afull + SA;
+  uint64_t* bfull = aempty + SA;
+  uint64_t* bempty = bfull + SB;
+  uint64_t* tfull_bar = bempty + SB;
+  uint64_t* tempty_bar = tfull_bar + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+  const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+  const int Cin = a.C1 + a.C2;
+  const int cpt = Cin / 64;
+  const int n_tiles = a.Cout / BN;
+  const int num_tiles = a.num_tiles;
+  const int ntaps = a.ntaps[0];
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < SA; ++s) { mbar_init(&afull[s], 1); mbar_init(&aempty[s], 1); }
+    for (int s = 0; s < SB; ++s) { mbar_init(&bfull[s], 1); mbar_init(&bempty[s], 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&tfull_bar[s], 1); mbar_init(&tempty_bar[s], 4); }
+    fence_barrier_init();
+    prefetch_tensormap(&tmA);
+    prefetch_tensormap(&tmB);
+    if (a.C2 > 0) prefetch_tensormap(&tmA2);
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ================= TMA producer =================
+    if (elect_one()) {
+      int sa = 0, sb = 0;
+      uint32_t pa = 0, pb = 0;
+      bool first = true;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const TileCoord t = decode_tile<BN>(a, tile, n_tiles, cpt);
+        const int w0 = t.wb * HALO_TW - 1, h0 = t.hb * HALO_TH - 1;
+        for (int c = 0; c < cpt; ++c) {
+          mbar_wait(&aempty[sa], pa ^ 1);
+          mbar_arrive_expect_tx(&afull[sa], HALO_TX_BYTES);
+          const int cc = c * 64;
+          uint8_t* dst = smem + sa * HALO_BLK_BYTES;
+          if (cc < a.C1) tma_load_4d(dst, &tmA, &afull[sa], cc, w0, h0, t.nb);
+          else tma_load_4d(dst, &tmA2, &afull[sa], cc - a.C1, w0, h0, t.nb);
+          if (++sa == SA) { sa = 0; pa ^= 1; }
+          for (int tp = 0; tp < ntaps; ++tp) {
+            if (first || !a.w_resident) {
+              mbar_wait(&bempty[sb], pb ^ 1);
+              mbar_arrive_expect_tx(&bfull[sb], B_BYTES);
+              tma_load_2d(smem + SA * HALO_BLK_BYTES + sb * B_BYTES, &tmB, &bfull[sb], (int)a.ktap[0][tp] * Cin + cc, t.n0);
             }
-            if (a.bias2) {
-#pragma unroll
-              for (int j = 0; j < 32; ++j) v[j] += __ldg(a.bias2 + cg + j);
-            }
-            if (a.scale) {
-#pragma unroll
-              for (int j = 0; j < 32; ++j) v[j] = fmaf(v[j], __ldg(a.scale + cg + j), __ldg(a.shift + cg + j));
-            }
-            if (rp) {
-#pragma unroll
-              for (int j = 0; j < 32; j += 8) {
-                f8 tt = ld8(rp + c0 + j);
-#pragma unroll
-                for (int e = 0; e < 8; ++e) v[j + e] += tt.v[e];
-              }
-            }
-            if (a.relu) {
-#pragma unroll
-              for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
-            }
-#pragma unroll
-            for (int j = 0; j < 32; j += 8) st8(yp + c0 + j, v + j);
+            if (++sb == SB) { sb = 0; pb ^= 1; }
           }
         }
+        first = false;
       }
+    }
+  } else if (warp == 1) {
+    // ================= MMA issuer =================
+    constexpr uint32_t idesc = make_idesc_bf16(TC_BM, BN);
+    int sa = 0, sb = 0, acc = 0;
+    uint32_t pa = 0, pb = 0, acc_phase = 0;
+    bool first = true;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+      tc_fence_after();
+      const uint32_t tmem_acc = tmem_base + (uint32_t)(acc * BN);
+      for (int c = 0; c < cpt; ++c) {
+        mbar_wait(&afull[sa], pa);
+        tc_fence_after();
+        const uint32_t ablk = sA + sa * HALO_BLK_BYTES;
+        for (int tp = 0; tp < ntaps; ++tp) {
+          const bool streamed = first || !a.w_resident;
+          if (streamed) {
+            mbar_wait(&bfull[sb], pb);
+            tc_fence_after();
+          }
+          if (elect_one()) {
+            // tap (dh, dw): the patch shifted by (dh, dw) starts (dh+1) halo rows and (dw+1) pixels into the block
+            const uint32_t aoff = (uint32_t)(((int)a.dh[0][tp] + 1) * HALO_PITCH + ((int)a.dw[0][tp] + 1) * 128);
+            const uint64_t adesc = make_halo_a_desc(ablk + aoff);
+            const uint64_t bdesc = make_kmajor_sw128_desc(sB + sb * B_BYTES);
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              umma_bf16(tmem_acc, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (c | tp | k) != 0);
+            if (streamed && !a.w_resident) umma_commit(&bempty[sb]);
+          }
+          __syncwarp();
+          if (++sb == SB) { sb = 0; pb ^= 1; }
+        }
+        if (elect_one()) {
+          umma_commit(&aempty[sa]);
+          if (c == cpt - 1) umma_commit(&tfull_bar[acc]);
+        }
+        __syncwarp();
+        if (++sa == SA) { sa = 0; pa ^= 1; }
+      }
+      first = false;
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  } else {
+    // ================= epilogue (same as the streaming kernel) =================
+    const int q = warp & 3;
+    const uint32_t stg = sStg + q * TC_SEG_BYTES;
+    const int m = q * 32 + lane;
+    const int tw = m % HALO_TW, th = m / HALO_TW;
+    int cpk[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int mm = q * 32 + i * 4 + (lane >> 3);
+      cpk[i] = (mm % HALO_TW) | ((mm / HALO_TW) << 8);
+    }
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const TileCoord t = decode_tile<BN>(a, tile, n_tiles, cpt);
+      const int ow = t.wb * HALO_TW + tw, oh = t.hb * HALO_TH + th, on = t.nb;
+      const bool valid = ow < a.Wout && oh < a.Hout && on < a.N;
+      int cpix[8];
+      unsigned cmask = 0;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int cw = t.wb * HALO_TW + (cpk[i] & 0xFF), chh = t.hb * HALO_TH + (cpk[i] >> 8);
+        const bool ok = cw < a.Wout && chh < a.Hout && on < a.N;
+        cpix[i] = ok ? (on * a.Hout + chh) * a.Wout + cw : 0;
+        cmask |= (ok ? 1u : 0u) << i;
+      }
+      mbar_wait(&tfull_bar[acc], acc_phase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN);
+      epilogue_tile<BN, TO>(a, t, taddr, stg, cpix, cmask, valid, on, oh, ow, &tempty_bar[acc], lane);
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
   }
@@ -626,6 +820,37 @@ static int launch_tc(const CUtensorMap& tA, const CUtensorMap& tA2, const CUtens
   return post_launch("conv2d(tcgen05)");
 }
 
+
+template <int BN, int SA, int SB, typename TO>
+static int launch_halo(const CUtensorMap& tA, const CUtensorMap& tA2, const CUtensorMap& tB, const TcArgs& a, dim3 grid,
+                       cudaStream_t st) {
+  constexpr int smem = halo_smem_bytes<BN, SA, SB>();
+  static_assert(smem <= 232448, "shared memory budget");
+  static bool configured = false;
+  if (!configured) {
+    if (cudaFuncSetAttribute(conv_halo_kernel<BN, SA, SB, TO>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) {
+      set_error("conv2d(tcgen05 halo): cannot reserve %d bytes of shared memory: %s", smem, cudaGetErrorString(cudaGetLastError()));
+      return STFB_ECUDA;
+    }
+    configured = true;
+  }
+  conv_halo_kernel<BN, SA, SB, TO><<<grid, TC_THREADS, smem, st>>>(tA, tA2, tB, a);
+  return post_launch("conv2d(tcgen05 halo)");
+}
+
+static int g_tc_halo = -1;   // STFB_NO_HALO=1 keeps every 3x3 on the streaming kernel (A/B measurements)
+
+// 3x3 / stride 1 / pad 1 (forward or dgrad), 64-channel multiples, maps at least 12 x 8: the halo kernel
+static bool halo_ok(const stfb_conv_params* p, int BN) {
+  if (g_tc_halo < 0) { const char* e = getenv("STFB_NO_HALO"); g_tc_halo = (e && atoi(e)) ? 0 : 1; }
+  if (!g_tc_halo) return false;
+  if (p->kh != 3 || p->kw != 3 || p->stride != 1 || p->pad != 1) return false;
+  if (p->C1 % 64 != 0 || p->C2 % 64 != 0) return false;
+  if (BN < 64) return false;
+  if (p->Ho != p->H || p->Wo != p->W) return false;
+  return p->Ho >= 12 && p->Wo >= 8;
+}
+
 int conv2d_tcgen05(const stfb_conv_params* p, cudaStream_t st) {
   EncodeTiledFn enc = get_tensormap_encoder();
   if (!enc) { set_error("conv2d(tcgen05): cuTensorMapEncodeTiled not available from the driver"); return STFB_ECUDA; }
@@ -682,11 +907,15 @@ int conv2d_tcgen05(const stfb_conv_params* p, cudaStream_t st) {
 
   CUtensorMap tA, tA2, tB;
   const int BK = (p->C1 % 64 == 0 && p->C2 % 64 == 0) ? 64 : 32;
-  if (!encode_nhwc_map_strided(enc, &tA, p->x, p->N, p->H, p->W, p->C1, a.TW, a.TH, a.TN, a.a_scale, BK)) {
+  const bool halo = halo_ok(p, BN);
+  if (halo) { a.TW = HALO_TW; a.TH = HALO_TH; a.TN = 1; a.tiles_w = (Wl + a.TW - 1) / a.TW; a.tiles_h = (Hl + a.TH - 1) / a.TH; }
+  const int tiles_n_eff = halo ? p->N : tiles_n;
+  const int abox_w = halo ? HALO_TW + 2 : a.TW, abox_h = halo ? HALO_TH + 2 : a.TH;
+  if (!encode_nhwc_map_strided(enc, &tA, p->x, p->N, p->H, p->W, p->C1, abox_w, abox_h, a.TN, a.a_scale, BK)) {
     set_error("conv2d(tcgen05): cuTensorMapEncodeTiled failed for x"); return STFB_ECUDA;
   }
   tA2 = tA;
-  if (p->C2 > 0 && !encode_nhwc_map_strided(enc, &tA2, p->x2, p->N, p->H, p->W, p->C2, a.TW, a.TH, a.TN, a.a_scale, BK)) {
+  if (p->C2 > 0 && !encode_nhwc_map_strided(enc, &tA2, p->x2, p->N, p->H, p->W, p->C2, abox_w, abox_h, a.TN, a.a_scale, BK)) {
     set_error("conv2d(tcgen05): cuTensorMapEncodeTiled failed for x2"); return STFB_ECUDA;
   }
   {
@@ -701,10 +930,24 @@ int conv2d_tcgen05(const stfb_conv_params* p, cudaStream_t st) {
       set_error("conv2d(tcgen05): cuTensorMapEncodeTiled failed for the weights"); return STFB_ECUDA;
     }
   }
-  a.tiles_n = tiles_n;
-  a.num_tiles = a.nphase_w * a.nphase_w * tiles_n * a.tiles_h * a.tiles_w * (p->Cout / BN);
+  a.tiles_n = tiles_n_eff;
+  a.num_tiles = a.nphase_w * a.nphase_w * tiles_n_eff * a.tiles_h * a.tiles_w * (p->Cout / BN);
   dim3 grid((unsigned)(a.num_tiles < num_sms() ? a.num_tiles : num_sms()));
   const bool f32out = p->y_dtype == STFB_F32;
+  if (halo) {
+    const int cpt = (p->C1 + p->C2) / 64;
+#define HALO_LAUNCH(BN_, SA_, SB_)                                                                             \
+    return f32out ? launch_halo<BN_, SA_, SB_, float>(tA, tA2, tB, a, grid, st)                               \
+                  : launch_halo<BN_, SA_, SB_, __nv_bfloat16>(tA, tA2, tB, a, grid, st)
+    switch (BN) {
+      case 256: HALO_LAUNCH(256, 3, 3);
+      case 128: HALO_LAUNCH(128, 4, 6);
+      case 64:
+        a.w_resident = (9 * cpt == 9 && p->Cout == 64) ? 1 : 0;     // the whole 64 x 576 matrix = the 9-slot ring
+        HALO_LAUNCH(64, 4, 9);
+    }
+#undef HALO_LAUNCH
+  }
 #define TC_LAUNCH(BN_, ST_, BK_)                                                                              \
   return f32out ? launch_tc<BN_, ST_, float, BK_>(tA, tA2, tB, a, grid, st)                                 \
                 : launch_tc<BN_, ST_, __nv_bfloat16, BK_>(tA, tA2, tB, a, grid, st)

@@ -53,6 +53,20 @@ __device__ __forceinline__ void prefetch_tensormap(const CUtensorMap* tm) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(tm)) : "memory");
 }
 
+// One lane of a converged warp (elect.sync).  tcgen05.mma / tcgen05.commit / TMA take uniform-register operands: guarded
+// by `lane == 0` ptxas wraps EVERY such instruction in an ELECT / BRA.U.ANY waterfall (the MMA warp then spends ~140
+// cycles per MMA on issue overhead -- profiles/r01_ncu_halo_l1_issue_bound.txt); guarded by elect.sync it knows that
+// exactly one lane runs them.
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
+
 __device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {
   asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols) : "memory");
 }

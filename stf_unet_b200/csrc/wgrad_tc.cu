@@ -97,7 +97,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_kernel(const __grid_co
   const int n_iter = p_end - p_beg;
 
   if (warp == 0) {
-    if (lane == 0 && n_iter > 0) {
+    if (n_iter > 0 && elect_one()) {
       int stage = 0;
       uint32_t phase = 0;
       // an odd block count leaves the upper half of the last accumulator unused: it re-reads the previous block
@@ -139,7 +139,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_kernel(const __grid_co
     for (int it = 0; it < n_iter; ++it) {
       mbar_wait(&full_bar[stage], phase);
       tc_fence_after();
-      if (lane == 0) {
+      if (elect_one()) {
         const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
         const uint64_t bdesc = make_mnmajor_sw128_desc(sa + 2 * NA * WG_BLK_BYTES, WG_BLK_BYTES);
         if (a.debug != 1) {

@@ -355,6 +355,9 @@ TC_CASES = [
     (2, 16, 16, 32, 0, 64, 1),       # 32 -> 64, 1x1
     (2, 16, 16, 64, 32, 64, 3),      # mixed 64 + 32 channel concat
     (3, 20, 24, 96, 0, 160, 3),      # channel counts that are multiples of 32 but not 64; Cout = 5 x 32
+    (2, 16, 16, 256, 0, 256, 3),     # halo kernel, BN=256, 4 channel blocks
+    (40, 32, 32, 64, 0, 64, 3),      # halo kernel with resident weights: 320 tiles, every CTA walks 2-3
+    (5, 13, 9, 128, 0, 64, 3),       # halo kernel, ragged patch (13 x 9 inside 16 x 16), streamed weights at BN=64
 ]
 
 
