@@ -196,6 +196,148 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_kernel(const __grid_co
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Halo variant for 3x3 / stride-1 / pad-1 weight gradients.  The kernel above fetches the gathered operand once per
+// filter tap (nine shifted 8 KB boxes per 64 pixels x 64 channels) and is bound by the L2 -> SM fill rate (ncu: 6-7 TB/s
+// of xbar traffic, tensor pipe 17-41 % active).  Here a CTA owns ONE (64 input channels, 64 output channels) pair and all
+// nine taps of it: per 8 x 8 pixel patch it loads one (8+2) x (8+2) halo box of x (12.5 KB) and the 8 x 8 box of dy
+// (8 KB); tap (r, s) is the same shared-memory block read through an MN-major descriptor that starts (r*10 + s) rows
+// further down with 1280 B between 8-pixel row groups.  An M = 128 accumulator holds two taps (its two 64-channel
+// column blocks are `LBO` = the distance between the two tap offsets apart), so nine taps fill 4.5 accumulators of
+// 64 TMEM columns each.  The pixel reduction is split over gridDim.z as before.
+constexpr int WH_PATCH = 8;
+constexpr int WH_PITCH = (WH_PATCH + 2) * 128;                         // bytes between patch rows inside the halo block
+constexpr int WH_X_TX = (WH_PATCH + 2) * (WH_PATCH + 2) * 128;          // 12800 B per TMA box
+constexpr int WH_X_BYTES = 13312;                                      // rounded up to the 1 KB swizzle period
+constexpr int WH_STAGE_BYTES = WH_X_BYTES + WG_BLK_BYTES;              // + one 64-pixel x 64-channel block of dy
+constexpr int WH_STAGES = 6;
+constexpr int WH_NACC = 5;
+constexpr int wh_smem_bytes() { return WH_STAGES * WH_STAGE_BYTES + 256 + 1024; }
+
+__device__ __forceinline__ uint64_t make_mnmajor_halo_desc(uint32_t saddr, uint32_t lbo_bytes) {
+  return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16) | ((uint64_t)(WH_PITCH >> 4) << 32) |
+         ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
+}
+__host__ __device__ constexpr int wh_tap_off(int tap) { return (tap / 3) * WH_PITCH + (tap % 3) * 128; }
+
+__global__ void __launch_bounds__(WG_THREADS, 1) wgrad_halo_kernel(const __grid_constant__ CUtensorMap tmG,
+                                                                    const __grid_constant__ CUtensorMap tmG2,
+                                                                    const __grid_constant__ CUtensorMap tmP, const WgTcArgs a) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + WH_STAGES * WH_STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + WH_STAGES;
+  uint64_t* accum_bar = empty_bar + WH_STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum_bar + 1);
+
+  const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+  const int cblk = blockIdx.x;                    // 64-channel block of the gathered operand (ci axis of dW)
+  const int n0 = blockIdx.y * 64;                 // output-channel block
+  const int p_beg = blockIdx.z * a.patches_per_split;
+  const int p_end = min(a.n_patches, p_beg + a.patches_per_split);
+  const int n_iter = p_end - p_beg;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < WH_STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    mbar_init(accum_bar, 1);
+    fence_barrier_init();
+    prefetch_tensormap(&tmG);
+    prefetch_tensormap(&tmP);
+    if (a.C2 > 0) prefetch_tensormap(&tmG2);
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (n_iter > 0 && elect_one()) {
+      int stage = 0;
+      uint32_t phase = 0;
+      const int cc = cblk * 64;
+      for (int p = p_beg; p < p_end; ++p) {
+        int t = p;
+        const int wb = t % a.tiles_w; t /= a.tiles_w;
+        const int hb = t % a.tiles_h;
+        const int nb = t / a.tiles_h;
+        const int w0 = wb * WH_PATCH, h0 = hb * WH_PATCH;
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        uint8_t* sx = smem + stage * WH_STAGE_BYTES;
+        mbar_arrive_expect_tx(&full_bar[stage], WH_X_TX + WG_BLK_BYTES);
+        if (cc < a.C1) tma_load_4d(sx, &tmG, &full_bar[stage], cc, w0 - 1, h0 - 1, nb);
+        else tma_load_4d(sx, &tmG2, &full_bar[stage], cc - a.C1, w0 - 1, h0 - 1, nb);
+        tma_load_4d(sx + WH_X_BYTES, &tmP, &full_bar[stage], n0, w0, h0, nb);
+        if (++stage == WH_STAGES) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    constexpr uint32_t idesc = make_idesc_bf16_mnmajor(128, 64);
+    int stage = 0;
+    uint32_t phase = 0;
+    const uint32_t s0 = smem_u32(smem);
+    for (int it = 0; it < n_iter; ++it) {
+      mbar_wait(&full_bar[stage], phase);
+      tc_fence_after();
+      if (elect_one()) {
+        const uint32_t sx = s0 + stage * WH_STAGE_BYTES;
+        const uint64_t bdesc = make_mnmajor_sw128_desc(sx + WH_X_BYTES, WG_BLK_BYTES);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {          // 16 pixels = two patch rows per MMA
+#pragma unroll
+          for (int j = 0; j < WH_NACC; ++j) {
+            // accumulator j: taps 2j (rows 0..63) and 2j+1 (rows 64..127); the last one repeats tap 8 (never written out)
+            constexpr int dummy = 0;
+            const int t0 = 2 * j, t1 = (2 * j + 1 < 9) ? 2 * j + 1 : 2 * j;
+            const uint32_t lbo = (uint32_t)(wh_tap_off(t1) - wh_tap_off(t0)) + dummy;
+            const uint64_t adesc = make_mnmajor_halo_desc(sx + wh_tap_off(t0) + k * 2 * WH_PITCH, lbo);
+            umma_bf16(tmem_base + (uint32_t)(j * 64), adesc, bdesc + (uint64_t)(128 * k), idesc, (it | k) != 0);
+          }
+        }
+        umma_commit(&empty_bar[stage]);
+        if (it == n_iter - 1) umma_commit(accum_bar);
+      }
+      __syncwarp();
+      if (++stage == WH_STAGES) { stage = 0; phase ^= 1; }
+    }
+  } else if (n_iter > 0) {
+    const int q = warp & 3;
+    const int m = q * 32 + lane;
+    mbar_wait(accum_bar, 0);
+    tc_fence_after();
+#pragma unroll 1
+    for (int j = 0; j < WH_NACC; ++j) {
+      const int tap = 2 * j + (m >> 6);
+      const bool valid = tap < 9;
+      const long long kg = (long long)tap * a.cg_total + a.cg_off + cblk * 64 + (m & 63);
+      float* rowp = a.ws + kg * a.Cp + n0;
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(j * 64);
+#pragma unroll 1
+      for (int c0 = 0; c0 < 64; c0 += 32) {
+        uint32_t r[32];
+        tmem_ld_x32(taddr + c0, r);
+        tmem_ld_wait();
+        if (valid && a.debug != 3) {
+#pragma unroll
+          for (int e = 0; e < 32; e += 4)
+            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(rowp + c0 + e), "f"(__uint_as_float(r[e])),
+                         "f"(__uint_as_float(r[e + 1])), "f"(__uint_as_float(r[e + 2])), "f"(__uint_as_float(r[e + 3]))
+                         : "memory");
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
 // dW[co][cg_off + ci][tap] += acc[(tap, ci)][co]: 32 ci x 32 co tiles transposed through shared memory so that both the
 // reads (along co) and the writes (along (ci, tap), contiguous in the reference layout) are coalesced
 __global__ void __launch_bounds__(256) wgrad_scatter_kernel(const float* __restrict__ acc, float* __restrict__ dW, int Cp, int Cg,
@@ -419,6 +561,47 @@ int wgrad_tcgen05(const void* P, const void* G, const void* G2, float* dW, int N
     static int dbg = -1;
     if (dbg < 0) { const char* e = getenv("STFB_WG_DEBUG"); dbg = e ? atoi(e) : 0; }
     a.debug = dbg;
+  }
+  {
+    static int no_halo = -1;
+    if (no_halo < 0) { const char* e = getenv("STFB_NO_HALO"); no_halo = (e && atoi(e)) ? 1 : 0; }
+    if (!no_halo && kh == 3 && kw == 3 && stride == 1 && pad == 1 && H == Hg && W == Wg && H >= 8 && W >= 8 && C1 % 64 == 0 &&
+        C2 % 64 == 0 && Cp % 64 == 0) {
+      a.TW = WH_PATCH; a.TH = WH_PATCH; a.TN = 1;
+      a.tiles_w = (W + WH_PATCH - 1) / WH_PATCH;
+      a.tiles_h = (H + WH_PATCH - 1) / WH_PATCH;
+      a.n_patches = N * a.tiles_h * a.tiles_w;
+      const int pairs = ((C1 + C2) / 64) * (Cp / 64);
+      long long splits = num_sms() / pairs;
+      const long long maxsplit = (a.n_patches + 1) / 2;
+      if (splits > maxsplit) splits = maxsplit;
+      if (splits < 1) splits = 1;
+      if (splits > 65535) splits = 65535;
+      a.patches_per_split = (int)((a.n_patches + splits - 1) / splits);
+      splits = (a.n_patches + a.patches_per_split - 1) / a.patches_per_split;
+      CUtensorMap tG, tG2, tP;
+      if (!encode_nhwc_map(enc, &tG, G, N, Hg, Wg, C1, WH_PATCH + 2, WH_PATCH + 2, 1)) { set_error("conv2d_wgrad(halo): tensor map (G) failed"); return STFB_ECUDA; }
+      tG2 = tG;
+      if (C2 > 0 && !encode_nhwc_map(enc, &tG2, G2, N, Hg, Wg, C2, WH_PATCH + 2, WH_PATCH + 2, 1)) { set_error("conv2d_wgrad(halo): tensor map (G2) failed"); return STFB_ECUDA; }
+      if (!encode_nhwc_map(enc, &tP, P, N, H, W, Cp, WH_PATCH, WH_PATCH, 1)) { set_error("conv2d_wgrad(halo): tensor map (P) failed"); return STFB_ECUDA; }
+      static bool configured = false;
+      if (!configured) {
+        if (cudaFuncSetAttribute(wgrad_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, wh_smem_bytes()) != cudaSuccess) {
+          set_error("conv2d_wgrad(halo): cannot reserve %d bytes of shared memory", wh_smem_bytes());
+          cudaGetLastError();
+          return STFB_ECUDA;
+        }
+        configured = true;
+      }
+      if (dW != nullptr) cudaMemsetAsync(ws, 0, need, st);
+      dim3 hgrid((unsigned)((C1 + C2) / 64), (unsigned)(Cp / 64), (unsigned)splits);
+      wgrad_halo_kernel<<<hgrid, WG_THREADS, wh_smem_bytes(), st>>>(tG, tG2, tP, a);
+      int rc = post_launch("conv2d_wgrad(tcgen05 halo)");
+      if (rc != STFB_OK || dW == nullptr) return rc;
+      dim3 sgrid((unsigned)((cg_total + 31) / 32), (unsigned)((Cp + 31) / 32));
+      wgrad_scatter_kernel<<<sgrid, 256, 0, st>>>(ws, dW, Cp, C1 + C2, kh * kw, cg_off, cg_total);
+      return post_launch("conv2d_wgrad(scatter)");
+    }
   }
   a.TW = pl.TW; a.TH = pl.TH; a.TN = pl.TN; a.tiles_w = pl.tiles_w; a.tiles_h = pl.tiles_h; a.n_patches = pl.n_patches;
   a.m_chunks = pl.m_chunks; a.patches_per_split = pl.pps;
