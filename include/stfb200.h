@@ -99,6 +99,11 @@ int stfb_conv2d_tcgen05_supported(const stfb_conv_params* p);
  * folds every such buffer into the flat gradient (instead of a memset + transpose launch per weight). */
 size_t stfb_conv2d_wgrad_workspace_bytes(const void* P, const void* G, int N, int Hp, int Wp, int Cp, int Hg, int Wg, int Cg,
                                          int cg_total, int kh, int kw, int stride, int pad, int dtype, int impl);
+/* Optional caller-owned scratch for the tcgen05 weight-gradient kernels (per-split partial tiles, summed by a second
+ * kernel, instead of fp32 atomics from every CTA).  Register stfb_wgrad_scratch_bytes() bytes once per process (one process
+ * drives one GPU); NULL unregisters.  The buffer must stay alive, and is used on the stream of each wgrad call. */
+size_t stfb_wgrad_scratch_bytes(void);
+int stfb_set_wgrad_scratch(void* scratch, size_t bytes);
 typedef struct stfb_scatter_job {
   long long start;   /* first tile (32 ci x 32 co, all taps) of this job in [0, total_tiles); khw <= 9 */
   long long off;     /* element offset of the weight in BOTH flat buffers (gradient and accumulation) */

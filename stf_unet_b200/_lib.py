@@ -24,7 +24,7 @@ class ConvParams(C.Structure):
 
 
 _vp, _i, _ll, _f = C.c_void_p, C.c_int, C.c_longlong, C.c_float
-_SIZE_T_FUNCS = {"stfb_conv2d_wgrad_workspace_bytes": [_vp, _vp] + [_i] * 14}
+_SIZE_T_FUNCS = {"stfb_conv2d_wgrad_workspace_bytes": [_vp, _vp] + [_i] * 14, "stfb_wgrad_scratch_bytes": []}
 _SIGS = {
     "stfb_conv2d": [C.POINTER(ConvParams), _vp],
     "stfb_conv2d_tcgen05_supported": [C.POINTER(ConvParams)],
@@ -33,6 +33,7 @@ _SIGS = {
     "stfb_pack_weight": [_vp, _vp, _i, _i, _i, _i, _i, _i, _vp],
     "stfb_pack_weight_ex": [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp],
     "stfb_lstm_step_fused": [_vp] * 9 + [_i, _i, _i, _i, _vp],
+    "stfb_set_wgrad_scratch": [_vp, C.c_size_t],
     "stfb_wgrad_scatter_batched": [_vp, _i, _ll, _vp, _vp, _vp],
     "stfb_pack_weights_batched": [_vp, _i, _ll, _i, _vp],
     "stfb_im2col_small": [_vp, _vp] + [_i] * 10 + [_vp],

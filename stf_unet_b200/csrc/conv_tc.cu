@@ -335,7 +335,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
   constexpr int TMEM_COLS = (2 * BN < 32) ? 32 : 2 * BN;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
+  // layout: [STAGES x (A, B)] [4 epilogue warps x staging segments] [mbarriers, TMEM slot]
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES + 4 * tc_stg_segs<EPI>() * TC_SEG_BYTES);
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tfull_bar = empty_bar + STAGES;     // [2] accumulator ready  (MMA -> epilogue)
   uint64_t* tempty_bar = tfull_bar + 2;         // [2] accumulator drained (epilogue -> MMA)

@@ -520,6 +520,8 @@ size_t wgrad_tcgen05_workspace_bytes(int N, int H, int W, int Cp, int cg_total, 
 int wgrad_pairs_supported(int N, int Hp, int Wp, int Cp, int Hg, int Wg, int Cg, int cg_off, int cg_total, int kh, int kw,
                           int stride, int pad, int dtype, const void* P, const void* G);
 size_t wgrad_pairs_workspace_bytes(int Cp, int Cg);
+void wgrad_set_scratch(void* p, size_t bytes);
+size_t wgrad_scratch_bytes();
 int wgrad_pairs(const void* P, const void* G, float* dW, int N, int H, int W, int Cp, int Cg, float* ws, size_t ws_bytes,
                 cudaStream_t st);
 int wgrad_scatter_batched(const stfb_scatter_job* jobs_dev, int njobs, long long total, const float* acc, float* grad,
@@ -587,6 +589,17 @@ extern "C" size_t stfb_conv2d_wgrad_workspace_bytes(const void* P, const void* G
     return stfb::wgrad_pairs_workspace_bytes(Cp, Cg);
   if (!stfb::wgrad_tcgen05_supported(N, Hp, Wp, Cp, Hg, Wg, Cg, kh, kw, stride, pad, dtype, P, G)) return 0;
   return stfb::wgrad_tcgen05_workspace_bytes(N, Hp, Wp, Cp, cg_total, kh, kw);
+}
+
+extern "C" size_t stfb_wgrad_scratch_bytes() {
+  if (stfb::check_device() != STFB_OK) return 0;
+  return stfb::wgrad_scratch_bytes();
+}
+
+extern "C" int stfb_set_wgrad_scratch(void* scratch, size_t bytes) {
+  STFB_REQUIRE(scratch == nullptr || (reinterpret_cast<uintptr_t>(scratch) % 16) == 0, "set_wgrad_scratch: 16-byte alignment required");
+  stfb::wgrad_set_scratch(scratch, scratch ? bytes : 0);
+  return STFB_OK;
 }
 
 extern "C" int stfb_wgrad_scatter_batched(const stfb_scatter_job* jobs_dev, int njobs, long long total, const float* acc_flat,

@@ -30,6 +30,7 @@ struct WgTcArgs {
   int tiles_w, tiles_h, n_patches;
   int patches_per_split;
   int m_chunks;             // kh*kw*(C1+C2)/64 column blocks on the M axis
+  float* partial;           // halo kernel: per-split partial tiles [split][pair][576][64] fp32 (NULL: red.add into ws)
   int debug;                // STFB_WG_DEBUG: 1 = no MMAs (TMA pipeline only), 2 = no TMA (MMA issue only); timing experiments
 };
 
@@ -314,6 +315,11 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_halo_kernel(const __grid_
       const bool valid = tap < 9;
       const long long kg = (long long)tap * a.cg_total + a.cg_off + cblk * 64 + (m & 63);
       float* rowp = a.ws + kg * a.Cp + n0;
+      // with a scratch buffer every CTA stores its tile as a plain partial (summed by wgrad_halo_reduce_kernel): the
+      // red.add epilogue (41 k fp32 atomics per CTA) took longer than the 55-patch main loop
+      float* prow = a.partial ? a.partial + ((((long long)blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) * 576 +
+                                             tap * 64 + (m & 63)) * 64
+                              : nullptr;
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(j * 64);
 #pragma unroll 1
       for (int c0 = 0; c0 < 64; c0 += 32) {
@@ -321,11 +327,17 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_halo_kernel(const __grid_
         tmem_ld_x32(taddr + c0, r);
         tmem_ld_wait();
         if (valid && a.debug != 3) {
+          if (prow) {
 #pragma unroll
-          for (int e = 0; e < 32; e += 4)
-            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(rowp + c0 + e), "f"(__uint_as_float(r[e])),
-                         "f"(__uint_as_float(r[e + 1])), "f"(__uint_as_float(r[e + 2])), "f"(__uint_as_float(r[e + 3]))
-                         : "memory");
+            for (int e = 0; e < 32; e += 4)
+              *reinterpret_cast<uint4*>(prow + c0 + e) = make_uint4(r[e], r[e + 1], r[e + 2], r[e + 3]);
+          } else {
+#pragma unroll
+            for (int e = 0; e < 32; e += 4)
+              asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(rowp + c0 + e), "f"(__uint_as_float(r[e])),
+                           "f"(__uint_as_float(r[e + 1])), "f"(__uint_as_float(r[e + 2])), "f"(__uint_as_float(r[e + 3]))
+                           : "memory");
+          }
         }
       }
     }
@@ -337,6 +349,42 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_halo_kernel(const __grid_
     tmem_dealloc(tmem_base, 512);
   }
 }
+
+// acc[(tap, cg_off + c*64 + i)][n*64 + j] += sum over splits of partial[split][n][c][tap*64 + i][j]
+// grid (36, pairs): one thread = 4 consecutive output channels of one (tap, ci) row; the partials are L2 resident
+__global__ void __launch_bounds__(256) wgrad_halo_reduce_kernel(const float* __restrict__ partial, float* __restrict__ acc,
+                                                               int splits, int cblocks, int nblocks, int Cp, int cg_off,
+                                                               int cg_total) {
+  const int pair = blockIdx.y;                       // = n * cblocks + c  (blockIdx.y * gridDim.x + blockIdx.x of the main grid)
+  const int c = pair % cblocks, n = pair / cblocks;
+  const int e = blockIdx.x * 256 + threadIdx.x;      // float4 index inside the 576 x 64 tile
+  const int row = e >> 4, j = (e & 15) * 4;
+  const int pairs = cblocks * nblocks;
+  const float4* src = reinterpret_cast<const float4*>(partial + ((long long)pair * 576 + row) * 64 + j);
+  const long long stride4 = (long long)pairs * 576 * 64 / 4;
+  float4 s0 = make_float4(0.f, 0.f, 0.f, 0.f), s1 = s0;
+  int sp = 0;
+  for (; sp + 1 < splits; sp += 2) {
+    const float4 u = src[(long long)sp * stride4], v = src[(long long)(sp + 1) * stride4];
+    s0.x += u.x; s0.y += u.y; s0.z += u.z; s0.w += u.w;
+    s1.x += v.x; s1.y += v.y; s1.z += v.z; s1.w += v.w;
+  }
+  if (sp < splits) {
+    const float4 u = src[(long long)sp * stride4];
+    s0.x += u.x; s0.y += u.y; s0.z += u.z; s0.w += u.w;
+  }
+  const int tap = row >> 6, i = row & 63;
+  float4* dst = reinterpret_cast<float4*>(acc + ((long long)tap * cg_total + cg_off + c * 64 + i) * Cp + n * 64 + j);
+  float4 o = *dst;
+  o.x += s0.x + s1.x; o.y += s0.y + s1.y; o.z += s0.z + s1.z; o.w += s0.w + s1.w;
+  *dst = o;
+}
+
+// caller-owned scratch for the per-split partial tiles (registered once per process: one process drives one GPU)
+static float* g_wg_scratch = nullptr;
+static size_t g_wg_scratch_bytes = 0;
+void wgrad_set_scratch(void* p, size_t bytes) { g_wg_scratch = reinterpret_cast<float*>(p); g_wg_scratch_bytes = bytes; }
+size_t wgrad_scratch_bytes() { return (size_t)num_sms() * 576 * 64 * sizeof(float); }
 
 // dW[co][cg_off + ci][tap] += acc[(tap, ci)][co]: 32 ci x 32 co tiles transposed through shared memory so that both the
 // reads (along co) and the writes (along (ci, tap), contiguous in the reference layout) are coalesced
@@ -595,8 +643,17 @@ int wgrad_tcgen05(const void* P, const void* G, const void* G2, float* dW, int N
       }
       if (dW != nullptr) cudaMemsetAsync(ws, 0, need, st);
       dim3 hgrid((unsigned)((C1 + C2) / 64), (unsigned)(Cp / 64), (unsigned)splits);
+      const size_t part_bytes = (size_t)pairs * splits * 576 * 64 * sizeof(float);
+      const bool use_partials = g_wg_scratch != nullptr && part_bytes <= g_wg_scratch_bytes &&
+                                (reinterpret_cast<uintptr_t>(g_wg_scratch) % 16) == 0 && Cp % 4 == 0;
+      a.partial = use_partials ? g_wg_scratch : nullptr;
       wgrad_halo_kernel<<<hgrid, WG_THREADS, wh_smem_bytes(), st>>>(tG, tG2, tP, a);
       int rc = post_launch("conv2d_wgrad(tcgen05 halo)");
+      if (rc == STFB_OK && use_partials) {
+        dim3 rgrid(576 * 64 / 4 / 256, (unsigned)pairs);
+        wgrad_halo_reduce_kernel<<<rgrid, 256, 0, st>>>(g_wg_scratch, ws, (int)splits, (C1 + C2) / 64, Cp / 64, Cp, cg_off, cg_total);
+        rc = post_launch("conv2d_wgrad(halo reduce)");
+      }
       if (rc != STFB_OK || dW == nullptr) return rc;
       dim3 sgrid((unsigned)((cg_total + 31) / 32), (unsigned)((Cp + 31) / 32));
       wgrad_scatter_kernel<<<sgrid, 256, 0, st>>>(ws, dW, Cp, C1 + C2, kh * kw, cg_off, cg_total);

@@ -153,6 +153,20 @@ def conv2d(x, wp, Cout, k, stride, pad, *, mode=CONV_FWD, out_hw=None, x2=None, 
     return y
 
 
+_wg_scratch = {}
+
+
+def _ensure_wgrad_scratch(device):
+    """Registers (once per device) the scratch buffer the tcgen05 wgrad kernels keep their per-split partial tiles in."""
+    key = (device.type, device.index if device.index is not None else torch.cuda.current_device())
+    if key not in _wg_scratch:
+        lib = _lib.load()
+        n = lib.stfb_wgrad_scratch_bytes()
+        buf = torch.empty((max(n, 16) // 4,), dtype=torch.float32, device=device)
+        check(lib.stfb_set_wgrad_scratch(buf.data_ptr(), buf.numel() * 4), "set_wgrad_scratch")
+        _wg_scratch[key] = buf
+
+
 def conv2d_wgrad(P, G, dW, k, stride, pad, cg_off=0, cg_total=None, impl=IMPL_AUTO, acc=None):
     """dW[cp][cg_off+cg][ky][kx] += sum_pix P[pix,cp] * G[gather(pix),cg]; dW fp32, reference layout.
 
@@ -160,6 +174,7 @@ def conv2d_wgrad(P, G, dW, k, stride, pad, cg_off=0, cg_total=None, impl=IMPL_AU
     tcgen05 family takes the shape, the launch only accumulates into it (returns True) and the caller folds it into dW
     later with ScatterPlan; otherwise dW is updated immediately (returns False)."""
     _need_cuda(P, G)
+    _ensure_wgrad_scratch(P.device)
     N, Hp, Wp, Cp = P.shape
     _, Hg, Wg, Cg = G.shape
     kh, kw = (k, k) if isinstance(k, int) else k

@@ -356,6 +356,10 @@ TC_CASES = [
     (2, 16, 16, 64, 32, 64, 3),      # mixed 64 + 32 channel concat
     (3, 20, 24, 96, 0, 160, 3),      # channel counts that are multiples of 32 but not 64; Cout = 5 x 32
     (2, 16, 16, 256, 0, 256, 3),     # halo kernel, BN=256, 4 channel blocks
+    (40, 32, 32, 64, 0, 128, 1),     # streaming kernel, 320 tiles: every persistent CTA walks 2-3 (staging vs barriers)
+    (24, 8, 8, 256, 0, 512, 3),      # streaming 3x3 on 8x8 maps, 2 N tiles x 12 pixel tiles... and
+    (160, 8, 8, 128, 0, 128, 3),     # ...80 pixel tiles x 1: with the 1x1 above, several tiles per CTA on every path
+    (300, 8, 8, 64, 0, 64, 3),       # 150 tiles of two images at BN=64
     (40, 32, 32, 64, 0, 64, 3),      # halo kernel with resident weights: 320 tiles, every CTA walks 2-3
     (5, 13, 9, 128, 0, 64, 3),       # halo kernel, ragged patch (13 x 9 inside 16 x 16), streamed weights at BN=64
 ]
@@ -568,7 +572,7 @@ def _acts_il_to_gate_major(acts_il, R, C):
     return acts_il.view(R, C // 16, 4, 16).permute(0, 2, 1, 3).reshape(R, 4 * C)
 
 
-@pytest.mark.parametrize("B,h,w,C", [(2, 16, 16, 64), (3, 8, 8, 128), (1, 10, 12, 256), (2, 4, 4, 512)])
+@pytest.mark.parametrize("B,h,w,C", [(2, 16, 16, 64), (3, 8, 8, 128), (1, 10, 12, 256), (2, 4, 4, 512), (12, 64, 64, 64)])
 def test_lstm_step_fused_matches_reference(B, h, w, C):
     """[x_t, h_{t-1}] @ [W_ih | W_hh]^T + biases + cell update in one tcgen05 kernel vs the gate-by-gate reference
     (reference: nn.LSTM at src/stf_lstm_unet.py:124-127, :216-242)."""
