@@ -222,6 +222,39 @@ def run_own(args, rank, world, local_rank):
     e2e_ms = timed(e2e_step, args.steps) / args.steps
     e2e_val = BATCH_PER_GPU * world / (e2e_ms / 1000.0)
 
+    # ---- numerics guard at the full bench size (the CPU oracle is too slow here): the bf16 tensor-core loss of this batch
+    #      against the fp32 FFMA family of the same library on the same weights; a corrupted pipeline shows up here ----
+    loss_check = None
+    if True:                              # every rank: the train-mode backward below holds the gradient all-reduce
+        model.eval()                      # eval mode: no running-stat updates, no tape
+        with torch.no_grad():
+            with torch.autocast("cuda", dtype=torch.bfloat16):
+                l16 = S.criterion(model(x_dev), t_dev).item()
+            l32 = S.criterion(model(x_dev), t_dev).item()
+        model.train()
+        # backward kernels (dgrad / wgrad / BN / LSTM): gradients of one train-mode step, bf16 tensor cores vs fp32 FFMA
+        names = ["conv1.weight", "layer1.0.conv1.weight", "layer2.1.conv2.weight", "layer3.2.conv1.weight",
+                 "layer4.1.conv2.weight", "lstm1.weight_hh_l0", "lstm4.weight_ih_l0", "decoder3.fusion.weight",
+                 "final_res.conv_block.0.weight"]
+        pd = dict(model.named_parameters())
+        grads = {}
+        for tag, dt in (("bf16", torch.bfloat16), ("fp32", None)):
+            for p_ in model.parameters():
+                p_.grad = None
+            with torch.autocast("cuda", dtype=torch.bfloat16, enabled=dt is not None):
+                loss_ = S.criterion(model(x_dev), t_dev)
+            loss_.backward()
+            grads[tag] = {n: pd[n].grad.detach().double().clone() for n in names}
+        gerr = {n: ((grads["bf16"][n] - grads["fp32"][n]).norm() / grads["fp32"][n].norm().clamp_min(1e-30)).item() for n in names}
+        for p_ in model.parameters():
+            p_.grad = None
+        loss_check = {"eval_loss_bf16_tcgen05": round(l16, 6), "eval_loss_fp32_simt": round(l32, 6),
+                      "rel_diff": round(abs(l16 - l32) / max(abs(l32), 1e-12), 6),
+                      "grad_rel_err_bf16_vs_fp32_max": round(max(gerr.values()), 5),
+                      "grad_rel_err_worst": max(gerr, key=gerr.get)}
+        if not (abs(l16 - l32) <= 5e-2 * max(abs(l32), 1e-6)) or not (max(gerr.values()) < 0.3):
+            raise SystemExit(f"bench.py: bf16 and fp32 paths disagree on the bench batch: {loss_check} {gerr}")
+
     # ---- roofline of the dominant kernel family: per-launch CUDA events over one extra step ----
     roof = None
     # every rank runs the extra step (it contains the gradient all-reduce); only rank 0 records events
@@ -276,7 +309,102 @@ def run_own(args, rank, world, local_rank):
                         "d2h_bytes_per_step": 4 * world, "ms_per_step": round(e2e_ms, 3)},
                 "gpu_launches": int(launches),
                 "model_tflops": round(model_tflops, 2), "model_frac_of_bf16_peak": round(model_tflops / world / pk["tflops"], 4),
-                "roofline": roof, "cpu_baseline": cpu}
+                "loss_check": loss_check, "roofline": roof, "cpu_baseline": cpu}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+INFER_GFLOP_PER_SLICE = 86.72          # BASELINE.md / SURVEY.md section 8(d): forward conv + LSTM GEMMs
+
+
+def run_infer(args, rank, world, local_rank):
+    """BASELINE.json configs[1]: STF-LSTM-UNet eval forward, T=8 x 1x256x256, batch 16 bf16 per GPU, followed by the fused
+    argmax-mask kernel (the per-slice product of configs[4]).  Slices are independent: no collective."""
+    import torch.distributed as dist
+    import stf_unet_b200 as S
+    from stf_unet_b200 import _lib
+    from stf_unet_b200.metrics import EvalMetrics
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        import datetime
+        dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=180))
+    torch.manual_seed(0)
+    model = S.STFLSTMUNet(1, 2, T_PHASES).to(dev).eval()
+    x_host, t_host = make_batch(rank)
+    x_pin, t_pin = x_host.pin_memory(), t_host.pin_memory()
+    xs, ts = x_pin.to(dev), t_pin.to(dev)
+    met = EvalMetrics(2, ignore_index=255, device=dev)
+
+    def fwd():
+        with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16):
+            out = model(xs)
+        return met.update(out, ts, want_mask=True)
+
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        for _ in range(3):
+            fwd()
+    torch.cuda.current_stream().wait_stream(side)
+    torch.cuda.synchronize()
+    graph = torch.cuda.CUDAGraph()
+    n0 = _lib.launch_count()
+    with torch.cuda.graph(graph):
+        mask = fwd()
+    per_replay = _lib.launch_count() - n0
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return ms.item()
+
+    for _ in range(max(args.warmup, 3)):
+        graph.replay()
+    with ClockSampler(local_rank) as clk:
+        ms = timed(graph.replay, args.steps) / args.steps
+    value = BATCH_PER_GPU * world / (ms / 1e3)
+    mask_host = torch.empty(mask.shape, dtype=torch.uint8).pin_memory()
+
+    def e2e_step():
+        xs.copy_(x_pin, non_blocking=True)
+        graph.replay()
+        mask_host.copy_(mask, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+
+    e2e_step()
+    e2e_ms = timed(e2e_step, args.steps) / args.steps
+    if rank == 0:
+        pk = peaks()
+        tf = value * INFER_GFLOP_PER_SLICE / 1e3
+        cfg = {"workload": f"STF-LSTM-UNet eval forward + argmax mask, T={T_PHASES} x 1x{HW}x{HW}, batch {BATCH_PER_GPU}/GPU bf16 "
+                           "(BASELINE.json configs[1])", "global_batch": BATCH_PER_GPU * world, "T": T_PHASES, "hw": HW,
+               "parallelism": f"dp{world} (independent slices, no collective)", "launch": "CUDA graph",
+               "l2": "activations of one forward (~1.5 GB) exceed the 126 MB L2; no flush needed"}
+        line = {"metric": "inference slices/s STF-LSTM-UNet", "value": round(value, 2), "unit": "slices/s", "n_gpus": world,
+                "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": round(ms, 3), "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic", "config": cfg,
+                "clocks": clk.summary(),
+                "e2e": {"value": round(BATCH_PER_GPU * world / (e2e_ms / 1e3), 2), "unit": "slices/s",
+                        "h2d_bytes_per_step": int(x_pin.numel() * 4) * world, "d2h_bytes_per_step": int(mask.numel()) * world,
+                        "ms_per_step": round(e2e_ms, 3)},
+                "gpu_launches": int(per_replay * args.steps), "model_tflops": round(tf, 2),
+                "model_frac_of_bf16_peak": round(tf / world / pk["tflops"], 4), "roofline": None, "cpu_baseline": None}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -291,6 +419,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="enqueue every kernel from Python instead of replaying a CUDA graph")
     ap.add_argument("--profile-detail", action="store_true", help="print the slowest GEMM-family launches to stderr")
+    ap.add_argument("--workload", default="train", choices=["train", "infer"],
+                    help="train = BASELINE.json configs[2] sharded 16/GPU (the headline metric); infer = configs[1], eval forward")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -300,6 +430,9 @@ def main():
         return
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device (the product path has no CPU fallback; use --impl reference for the CPU arm)")
+    if args.workload == "infer":
+        run_infer(args, rank, world, local_rank)
+        return
     run_own(args, rank, world, local_rank)
 
 

@@ -233,6 +233,21 @@ int stfb_lstm_cell_bwd(const float* dh, float* dc, const void* acts, const float
                        void* stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * Evaluation metrics on the device (evaluate(), train_utils/train_and_eval.py:322-336; ConfusionMatrix :25-70,
+ * DiceCoefficient :73-132): ONE pass over the logits [B,C,HW] fp32 (NCHW) + target [B,HW] int64 does
+ *   - argmax over classes (first maximum, as torch.argmax) -> mask [B,HW] uint8 (may be NULL),
+ *   - confmat[t*C + pred] += 1 for 0 <= t < C (int64 [C*C], accumulated across calls),
+ *   - the Dice update of this batch: with use_ignore, pixels whose target == ignore_index count as class 0 on both
+ *     sides (the reference's pred*mask / target*mask); dice_c = 2*inter/(|pred==c| + |target==c|), 1 when the union is
+ *     empty; dice_cumulative[c] += dice_c, *dice_updates += 1 (both may be NULL to only collect dice_counts).
+ * dice_counts = int64 [3*C] scratch {inter, pred, target}, zeroed by the caller once, cleared by each call that passes
+ * dice_cumulative.  No host synchronisation.  C <= 8.
+ * ---------------------------------------------------------------------------------------------- */
+int stfb_eval_metrics(const float* logits, const long long* target, unsigned char* mask, long long* confmat,
+                      long long* dice_counts, float* dice_cumulative, long long* dice_updates, int B, int C, int HW,
+                      long long ignore_index, int use_ignore, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
  * Layout adapters at the API boundary (reference tensors are NCHW fp32).
  * ---------------------------------------------------------------------------------------------- */
 /* x [B, T, C, H, W] fp32  ->  y [T*B, H, W, C] dtype  (time-major image order n = t*B + b) */

@@ -212,3 +212,31 @@ def loss_and_grads(sd, x, target, model="stf", train=True, **kw):
     gs = torch.autograd.grad(loss, [params[k] for k in names], allow_unused=True)
     grads = OrderedDict((k, g) for k, g in zip(names, gs))
     return logits.detach(), loss.detach(), grads, bufs
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# evaluation metrics (test infrastructure, like everything in oracle/): restatement of ConfusionMatrix.update
+# (train_utils/train_and_eval.py:30-39) and DiceCoefficient.update (:80-118) for ONE batch, as integer counts
+# ---------------------------------------------------------------------------------------------------------------------
+def eval_metrics_batch(logits, target, num_classes=2, ignore_index=255):
+    """-> (confmat int64 [C,C] with rows = target, dice_per_class float [C]) of one update() call.
+
+    The confusion matrix counts every pixel whose target is a valid class (:36-38); the Dice update first turns
+    ignore_index pixels into class 0 on BOTH sides (`pred * mask`, `target * mask`, :88-91), then per class
+    dice = 2*|pred==c & target==c| / (|pred==c| + |target==c|), 1.0 for an empty union (:103-107)."""
+    pred = torch.argmax(torch.softmax(logits.float(), dim=1), dim=1)
+    a, b = target.flatten(), pred.flatten()
+    k = (a >= 0) & (a < num_classes)
+    inds = num_classes * a[k].to(torch.int64) + b[k]
+    mat = torch.bincount(inds, minlength=num_classes ** 2).reshape(num_classes, num_classes)
+    p, t = pred, target
+    if ignore_index is not None:
+        m = target != ignore_index
+        p, t = pred * m, target * m
+    p, t = p.reshape(-1), t.reshape(-1)
+    dice = []
+    for c in range(num_classes):
+        pc, tc = (p == c).double(), (t == c).double()
+        union = pc.sum() + tc.sum()
+        dice.append((2.0 * (pc * tc).sum() / union).item() if union > 0 else 1.0)
+    return mat, torch.tensor(dice, dtype=torch.float64)

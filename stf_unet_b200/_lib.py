@@ -63,6 +63,7 @@ _SIGS = {
     "stfb_add_inplace": [_vp, _vp, _ll, _i, _vp],
     "stfb_cast": [_vp, _i, _vp, _i, _ll, _vp],
     "stfb_ce_dice_fwd": [_vp] * 4 + [_i, _i, _i, _f, _vp],
+    "stfb_eval_metrics": [_vp] * 7 + [_i, _i, _i, _ll, _i, _vp],
     "stfb_ce_dice_bwd": [_vp] * 5 + [_i, _i, _i, _f, _vp],
 }
 EXPORTS = sorted(list(_SIGS) + list(_SIZE_T_FUNCS) + ["stfb_version", "stfb_last_error", "stfb_launch_count"])

@@ -117,5 +117,33 @@ def main():
     print("criterion:", loss.item())
 
 
+def metrics_case():
+    """evaluate()'s metric classes (train_utils/train_and_eval.py:25-132) on two random batches, one holding 255s."""
+    from train_utils.train_and_eval import ConfusionMatrix, DiceCoefficient
+    g = np.random.Generator(np.random.PCG64(9))
+    conf, dice = ConfusionMatrix(2), DiceCoefficient(num_classes=2, ignore_index=255)
+    out = {}
+    for i in range(2):
+        logits = torch.from_numpy(g.standard_normal((3, 2, 24, 40)).astype(np.float32))
+        logits[0, :, 3, 5:9] = 0.25                       # exact ties: argmax must take the first class
+        tgt = torch.from_numpy((g.uniform(size=(3, 24, 40)) < 0.35).astype(np.int64))
+        if i == 1:
+            tgt[g.uniform(size=(3, 24, 40)) < 0.1] = 255   # ignored pixels
+        conf.update(tgt.flatten(), logits.argmax(1).flatten())
+        dice.update(logits, tgt)
+        out[f"logits{i}"], out[f"target{i}"] = logits.numpy(), tgt.numpy()
+        out[f"mat{i}"] = conf.mat.numpy().copy()
+        out[f"dice_cum{i}"] = dice.cumulative_dice.numpy().copy()
+    out["dice"] = dice.compute().numpy()
+    acc_global, acc, iu = conf.compute()
+    out["acc_global"], out["acc"], out["iu"] = acc_global.numpy(), acc.numpy(), iu.numpy()
+    np.savez_compressed(os.path.join(HERE, "eval_metrics_2x3x2x24x40.npz"), **out)
+    print("metrics:", out["mat1"].tolist(), out["dice"].tolist())
+
+
 if __name__ == "__main__":
-    main()
+    if len(sys.argv) > 1 and sys.argv[1] == "metrics":
+        metrics_case()
+    else:
+        main()
+        metrics_case()

@@ -631,3 +631,36 @@ def test_lstm_cell_bwd_interleaved_acts_matches_gate_major():
         ops.lstm_cell_bwd(dh, dc, acts, cp, cc, dg, R, C, acts_il=il)
         outs.append((dg.float(), dc))
     assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])
+
+
+def test_eval_metrics_kernel_matches_golden_and_oracle(golden_dir):
+    """stfb_eval_metrics (argmax + confusion matrix + Dice counts in one pass) vs the fixture generated from the
+    reference's ConfusionMatrix / DiceCoefficient (train_utils/train_and_eval.py:25-132): integer work, bit-exact."""
+    import os
+    import numpy as np
+    from oracle import stf_oracle as O
+    from stf_unet_b200.metrics import EvalMetrics, argmax_mask
+    g = np.load(os.path.join(golden_dir, "eval_metrics_2x3x2x24x40.npz"))
+    m = EvalMetrics(2, ignore_index=255, device=DEV)
+    for i in range(2):
+        logits, tgt = torch.from_numpy(g[f"logits{i}"]).to(DEV), torch.from_numpy(g[f"target{i}"]).to(DEV)
+        mask = m.update({"out": logits}, tgt, want_mask=True)
+        assert torch.equal(mask.cpu().long(), torch.from_numpy(g[f"logits{i}"]).argmax(1))
+        assert np.array_equal(m.mat.cpu().numpy(), g[f"mat{i}"])
+        assert np.allclose(m.cumulative_dice.cpu().numpy(), g[f"dice_cum{i}"], atol=1e-6)
+    assert np.allclose(m.compute_dice().cpu().numpy(), g["dice"], atol=1e-6)
+    acc_global, acc, iu = m.compute_confusion()
+    assert np.allclose(acc_global.cpu().numpy(), g["acc_global"], atol=1e-6) and np.allclose(iu.cpu().numpy(), g["iu"], atol=1e-6)
+    # larger random case with 4 classes against the oracle, ragged size, no ignore index
+    gen = torch.Generator().manual_seed(3)
+    logits = torch.randn(5, 4, 37, 53, generator=gen)
+    tgt = torch.randint(0, 4, (5, 37, 53), generator=gen)
+    tgt[0, :5] = 7                                       # out-of-range labels are skipped by the confusion matrix
+    m4 = EvalMetrics(4, ignore_index=None, device=DEV)
+    m4.update(logits.to(DEV), tgt.to(DEV))
+    mat_ref, dice_ref = O.eval_metrics_batch(logits, tgt, 4, None)
+    assert torch.equal(m4.mat.cpu(), mat_ref)
+    assert torch.allclose(m4.compute_dice().cpu().double(), dice_ref, atol=1e-6)
+    assert torch.equal(argmax_mask(logits.to(DEV)).cpu().long(), logits.argmax(1))
+    # empty batch
+    m4.update(torch.empty(0, 4, 8, 8, device=DEV), torch.empty(0, 8, 8, dtype=torch.int64, device=DEV))

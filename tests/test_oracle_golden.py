@@ -105,3 +105,17 @@ def test_criterion(golden_dir):
     loss.backward()
     assert abs(loss.item() - float(g["loss"])) < 1e-6
     assert rel(logits.grad.numpy(), g["grad"]) < 1e-5
+
+
+def test_eval_metrics_oracle_matches_reference_classes(golden_dir):
+    """oracle.eval_metrics_batch == ConfusionMatrix / DiceCoefficient of the live reference (fixture from make_golden.py)."""
+    g = load(golden_dir, "eval_metrics_2x3x2x24x40")
+    mat = torch.zeros(2, 2, dtype=torch.int64)
+    cum = torch.zeros(2, dtype=torch.float64)
+    for i in range(2):
+        m, d = O.eval_metrics_batch(torch.from_numpy(g[f"logits{i}"]), torch.from_numpy(g[f"target{i}"]), 2, 255)
+        mat += m
+        cum += d
+        assert np.array_equal(mat.numpy(), g[f"mat{i}"])
+        assert np.allclose(cum.numpy(), g[f"dice_cum{i}"], rtol=0, atol=1e-6)
+    assert np.allclose((cum / 2).numpy(), g["dice"], atol=1e-6)

@@ -52,7 +52,8 @@ def main():
             x = torch.randn(N, H, W, Cin, device=DEV).to(bf)
             dy = torch.randn(N, H, W, Cout, device=DEV).to(bf)
             dW = torch.zeros(Cout, Cin, k, k, device=DEV)
-            ms = timeit(lambda: ops.conv2d_wgrad(dy, x, dW, k, 1, (k - 1) // 2, 0, Cin, impl=ops.IMPL_TCGEN05), a.iters)
+            acc = torch.zeros(Cout * Cin * k * k, device=DEV)      # deferred mode: accumulate only (what the engine does)
+            ms = timeit(lambda: ops.conv2d_wgrad(dy, x, dW, k, 1, (k - 1) // 2, 0, Cin, impl=ops.IMPL_TCGEN05, acc=acc), a.iters)
             fl = 2.0 * N * H * W * Cin * Cout * k * k
             print(f"wgrad  N{N} {H}x{W} {Cin}->{Cout} k{k}: {ms * 1e3:8.1f} us  {fl / ms / 1e9:8.1f} TFLOP/s")
     if a.what in ("lstm", "all"):
