@@ -78,11 +78,20 @@ typedef struct stfb_conv_params {
   int relu;
   int x_dtype, y_dtype; /* (f32,f32) (bf16,bf16) (bf16,f32)                        */
   int impl;             /* STFB_IMPL_*                                             */
+  /* Fused train-mode BatchNorm statistics of the OUTPUT (tcgen05 family, bf16 y, no epilogue extras): the epilogue adds
+   * per-channel sum / sum of squares of the (bf16-rounded) outputs of image group g = n / (N / stat_groups) into
+   * stat_partial[slot][0|1][g][c] (fp32, red.add; slot = CTA % stat_slots), the layout stfb_bn_finalize_train reads with
+   * nblk = stat_slots.  The caller zeroes the buffer.  NULL = off.  Use stfb_conv2d_stats_fusable() first. */
+  float* stat_partial;
+  int stat_slots, stat_groups;
 } stfb_conv_params;
 
 int stfb_conv2d(const stfb_conv_params* p, void* stream);
 /* 1 if the tcgen05 kernel family supports this problem (host-only check, no launch). */
 int stfb_conv2d_tcgen05_supported(const stfb_conv_params* p);
+/* 1 if, in addition, the launch can produce the BatchNorm statistics of its output (every tile lies inside one of the
+ * `groups` image groups, 128-byte output rows). */
+int stfb_conv2d_stats_fusable(const stfb_conv_params* p, int groups);
 
 /* Weight gradient:  dW[cp][cg_off + cg][ky][kx] += sum_pix P[pix, cp] * G[gather(pix,ky,kx), cg]
  *   P = per-pixel tensor [N, Hp, Wp, Cp] (dy of a Conv2d; x of a ConvTranspose2d),

@@ -20,7 +20,8 @@ IMPL_AUTO, IMPL_SIMT, IMPL_TCGEN05 = 0, 1, 2
 class ConvParams(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in ("x", "x2", "w", "y", "bias", "bias2", "scale", "shift", "residual")] + \
                [(n, C.c_int) for n in ("N", "H", "W", "C1", "C2", "Ho", "Wo", "Cout", "kh", "kw", "stride", "pad",
-                                       "ldw", "mode", "relu", "x_dtype", "y_dtype", "impl")]
+                                       "ldw", "mode", "relu", "x_dtype", "y_dtype", "impl")] + \
+               [("stat_partial", C.c_void_p), ("stat_slots", C.c_int), ("stat_groups", C.c_int)]
 
 
 _vp, _i, _ll, _f = C.c_void_p, C.c_int, C.c_longlong, C.c_float
@@ -28,6 +29,7 @@ _SIZE_T_FUNCS = {"stfb_conv2d_wgrad_workspace_bytes": [_vp, _vp] + [_i] * 14, "s
 _SIGS = {
     "stfb_conv2d": [C.POINTER(ConvParams), _vp],
     "stfb_conv2d_tcgen05_supported": [C.POINTER(ConvParams)],
+    "stfb_conv2d_stats_fusable": [C.POINTER(ConvParams), _i],
     "stfb_conv2d_wgrad": [_vp, _vp, _vp] + [_i] * 15 + [_vp, C.c_size_t, _vp],
     "stfb_conv2d_wgrad_tcgen05_supported": [_vp, _vp] + [_i] * 12,
     "stfb_pack_weight": [_vp, _vp, _i, _i, _i, _i, _i, _i, _vp],

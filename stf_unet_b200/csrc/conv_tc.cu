@@ -49,6 +49,8 @@ struct TcArgs {
   float* c_out;          // [rows][Chid] fp32
   void* acts;            // [rows][4*Chid] bf16 post-activation gates in accumulator column order (NULL in eval)
   int Chid;
+  float* stat_partial;   // fused BatchNorm statistics: [stat_slots][2][stat_groups][Cout] fp32 (NULL = off)
+  int stat_slots, stat_groups, stat_imgs;   // stat_imgs = images per group
   int w_resident;        // halo kernel: the whole weight matrix sits in the B ring (loaded once, never released)
   int debug;             // STFB_TC_DEBUG: 1 = no MMAs (TMA pipeline only), 2 = no TMA (MMA issue only); timing experiments
   int ntaps[4];
@@ -264,6 +266,37 @@ __device__ __forceinline__ void epilogue_tile(const TcArgs& a, const TileCoord& 
 #pragma unroll
           for (int k = 0; k < 8; ++k)
             sts128f(stg + stg_off(lane, k), v[k * 4], v[k * 4 + 1], v[k * 4 + 2], v[k * 4 + 3]);
+        }
+      }
+      if constexpr (ESZ == 2) {
+        if (a.stat_partial) {
+          // train-mode BatchNorm statistics of this tile, from the bf16 values that are about to be stored: lane l owns
+          // channels 2l, 2l+1 of the segment and walks the warp's 32 rows in shared memory (conflict free)
+          __syncwarp();
+          const unsigned vmask = __ballot_sync(0xffffffffu, valid);
+          float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
+#pragma unroll 8
+          for (int r = 0; r < 32; ++r) {
+            if ((vmask >> r) & 1u) {
+              uint32_t w;
+              asm volatile("ld.shared.b32 %0, [%1];"
+                           : "=r"(w)
+                           : "r"(stg + (uint32_t)(r * 128 + (((lane >> 2) ^ (r & 7)) << 4) + (lane & 3) * 4)));
+              const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w));
+              s0 += f.x; s1 += f.y;
+              q0 = fmaf(f.x, f.x, q0); q1 = fmaf(f.y, f.y, q1);
+            }
+          }
+          const int g = (t.nb * a.TN) / a.stat_imgs;
+          float* dst = a.stat_partial + ((long long)(blockIdx.x % a.stat_slots) * 2 * a.stat_groups + g) * a.Cout + t.n0 +
+                       seg * SEGC + 2 * lane;
+          const long long qoff = (long long)a.stat_groups * a.Cout;
+          if (vmask) {
+            asm volatile("red.global.add.f32 [%0], %1;" ::"l"(dst), "f"(s0) : "memory");
+            asm volatile("red.global.add.f32 [%0], %1;" ::"l"(dst + 1), "f"(s1) : "memory");
+            asm volatile("red.global.add.f32 [%0], %1;" ::"l"(dst + qoff), "f"(q0) : "memory");
+            asm volatile("red.global.add.f32 [%0], %1;" ::"l"(dst + qoff + 1), "f"(q1) : "memory");
+          }
         }
       }
       seg_store(stg, ybase + seg * 128, cpix, cmask, pitch, lane);
@@ -839,6 +872,23 @@ static int launch_halo(const CUtensorMap& tA, const CUtensorMap& tA2, const CUte
   return post_launch("conv2d(tcgen05 halo)");
 }
 
+static bool halo_ok(const stfb_conv_params* p, int BN);
+
+// can this launch also reduce the BatchNorm statistics of its output? (bf16 rows of >= 128 B through the staged epilogue,
+// plain forward conv without epilogue extras, every 128-pixel tile inside one image group)
+int conv2d_stats_fusable(const stfb_conv_params* p, int groups) {
+  if (!conv2d_tcgen05_supported(p)) return 0;
+  if (p->mode != STFB_CONV_FWD || p->y_dtype != STFB_BF16) return 0;
+  if (p->scale || p->residual || p->relu) return 0;
+  if (groups <= 0 || p->N % groups != 0) return 0;
+  const int BN = pick_bn(p->Cout);
+  if (BN * 2 < 128) return 0;
+  if (halo_ok(p, BN)) return 1;              // one image per tile
+  int TW, TH, TN;
+  pick_patch(p->Ho, p->Wo, TW, TH, TN);
+  return ((p->N / groups) % TN == 0) ? 1 : 0;
+}
+
 static int g_tc_halo = -1;   // STFB_NO_HALO=1 keeps every 3x3 on the streaming kernel (A/B measurements)
 
 // 3x3 / stride 1 / pad 1 (forward or dgrad), 64-channel multiples, maps at least 12 x 8: the halo kernel
@@ -865,6 +915,14 @@ int conv2d_tcgen05(const stfb_conv_params* p, cudaStream_t st) {
     a.debug = dbg;
   }
   a.N = p->N; a.Hout = p->Ho; a.Wout = p->Wo; a.Cout = p->Cout; a.C1 = p->C1; a.C2 = p->C2; a.relu = p->relu;
+  if (p->stat_partial) {
+    if (p->stat_slots <= 0 || !conv2d_stats_fusable(p, p->stat_groups)) {
+      set_error("conv2d(tcgen05): fused BatchNorm statistics not available for this launch (stfb_conv2d_stats_fusable)");
+      return STFB_ENOTSUP;
+    }
+    a.stat_partial = p->stat_partial; a.stat_slots = p->stat_slots; a.stat_groups = p->stat_groups;
+    a.stat_imgs = p->N / p->stat_groups;
+  }
   const int s = p->stride, k = p->kh;
   int Hl, Wl;   // logical pixel grid the tiles cover
   if (p->mode == STFB_CONV_FWD) {

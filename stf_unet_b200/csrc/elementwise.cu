@@ -202,64 +202,71 @@ static int launch_colreduce(ColRedArgs A, int dtype, int VEC, cudaStream_t st, c
   return post_launch(what);
 }
 
-// sum over the nblk partial slots of 8 consecutive groups for channel c; lanes stride over the slots (each lane adds at
-// most two fp32 partials, the 32 lane sums are combined in fp64: B200 fp64 is slow, so it is kept to 5 shuffle steps)
-__device__ __forceinline__ void sum_partials8(const float* __restrict__ partial, int nblk, int G, int C, int g0, int c, int lane,
-                                              double* s, double* q) {
-  float fs[8], fq[8];
-#pragma unroll
-  for (int j = 0; j < 8; ++j) fs[j] = fq[j] = 0.f;
-  for (int b = lane; b < nblk; b += 32) {
-    const float* pp = partial + ((long long)b * 2 * G) * C + c;
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      if (g0 + j < G) {
-        fs[j] += pp[(long long)(g0 + j) * C];
-        fq[j] += pp[(long long)(G + g0 + j) * C];
-      }
-    }
-  }
-#pragma unroll
-  for (int j = 0; j < 8; ++j) { s[j] = warp_sum((double)fs[j]); q[j] = warp_sum((double)fq[j]); }
-}
-
 // =================================================================================================
 // BatchNorm finalize / fold / apply / backward apply
 // =================================================================================================
-// one warp per channel: lanes sum the per-CTA partials (fp64), lane 0 walks the groups in order (the reference updates
-// the running stats once per time step, sequentially)
-__global__ void bn_finalize_train_kernel(const float* __restrict__ partial, int nblk, const float* __restrict__ gamma,
-                                         const float* __restrict__ beta, float* running_mean, float* running_var,
-                                         long long* nbt, float* scale, float* shift, float* mean, float* invstd, int G,
-                                         long long R, int C, float eps, float momentum) {
-  const int lane = threadIdx.x % 32;
-  const int c = blockIdx.x * (blockDim.x / 32) + threadIdx.x / 32;
+// Finalize kernels: one thread per (group, channel) adds the nblk partial slots (coalesced along c, independent loads,
+// fp64 accumulate), the block's G x 32 results meet in shared memory and the 32 threads of group 0 walk the groups in
+// order (the reference updates the running stats once per time step, sequentially).  The first version gave each channel
+// one warp with the slots strided over the lanes: 23 us per launch for a few KB of work (profiles/r01_launches_*).
+constexpr int FIN_CH = 32;       // channels per block
+constexpr int FIN_MAXG = 32;     // groups per block pass (blockDim = FIN_CH * min(G, FIN_MAXG))
+
+__device__ __forceinline__ void sum_slots(const float* __restrict__ partial, int nblk, int G, int C, int g, int c, double& s,
+                                          double& q) {
+  double a0 = 0.0, a1 = 0.0, b0 = 0.0, b1 = 0.0;
+  const long long slot = 2LL * G * C;
+  const float* p = partial + (long long)g * C + c;
+  int b = 0;
+  for (; b + 1 < nblk; b += 2) {
+    const float s0 = p[(long long)b * slot], q0 = p[(long long)b * slot + (long long)G * C];
+    const float s1 = p[(long long)(b + 1) * slot], q1 = p[(long long)(b + 1) * slot + (long long)G * C];
+    a0 += (double)s0; b0 += (double)q0; a1 += (double)s1; b1 += (double)q1;
+  }
+  if (b < nblk) { a0 += (double)p[(long long)b * slot]; b0 += (double)p[(long long)b * slot + (long long)G * C]; }
+  s = a0 + a1;
+  q = b0 + b1;
+}
+
+__global__ void __launch_bounds__(FIN_CH * FIN_MAXG) bn_finalize_train_kernel(
+    const float* __restrict__ partial, int nblk, const float* __restrict__ gamma, const float* __restrict__ beta,
+    float* running_mean, float* running_var, long long* nbt, float* scale, float* shift, float* mean, float* invstd, int G,
+    long long R, int C, float eps, float momentum) {
+  __shared__ float sh_m[FIN_MAXG][FIN_CH], sh_v[FIN_MAXG][FIN_CH];
+  const int cl = threadIdx.x % FIN_CH, gl = threadIdx.x / FIN_CH;
+  const int c = blockIdx.x * FIN_CH + cl;
+  const int gpb = blockDim.x / FIN_CH;
   if (blockIdx.x == 0 && threadIdx.x == 0 && nbt) *nbt += G;
-  if (c >= C) return;
-  float rm = running_mean ? running_mean[c] : 0.f, rv = running_var ? running_var[c] : 1.f;
+  float rm = 0.f, rv = 1.f;
+  if (gl == 0 && c < C) { rm = running_mean ? running_mean[c] : 0.f; rv = running_var ? running_var[c] : 1.f; }
   const double n = (double)R;
-  for (int g0 = 0; g0 < G; g0 += 8) {
-    double s[8], q[8];
-    sum_partials8(partial, nblk, G, C, g0, c, lane, s, q);
-    if (lane == 0) {
-      for (int j = 0; j < 8 && g0 + j < G; ++j) {
-        const int g = g0 + j;
-        const double m = s[j] / n;
-        double var = q[j] / n - m * m;
-        if (var < 0.0) var = 0.0;
-        const float is = rsqrtf((float)var + eps);
-        const float sc = gamma[c] * is;
-        scale[g * C + c] = sc;
-        shift[g * C + c] = beta[c] - (float)m * sc;
-        mean[g * C + c] = (float)m;
-        invstd[g * C + c] = is;
-        const double unbiased = R > 1 ? var * n / (n - 1.0) : var;
-        rm = (1.f - momentum) * rm + momentum * (float)m;
-        rv = (1.f - momentum) * rv + momentum * (float)unbiased;
+  for (int g0 = 0; g0 < G; g0 += gpb) {
+    const int g = g0 + gl;
+    if (g < G && c < C) {
+      double s, q;
+      sum_slots(partial, nblk, G, C, g, c, s, q);
+      const double m = s / n;
+      double var = q / n - m * m;
+      if (var < 0.0) var = 0.0;
+      const float is = rsqrtf((float)var + eps);
+      const float sc = gamma[c] * is;
+      scale[g * C + c] = sc;
+      shift[g * C + c] = beta[c] - (float)m * sc;
+      mean[g * C + c] = (float)m;
+      invstd[g * C + c] = is;
+      sh_m[gl][cl] = (float)m;
+      sh_v[gl][cl] = (float)(R > 1 ? var * n / (n - 1.0) : var);
+    }
+    __syncthreads();
+    if (gl == 0 && c < C) {
+      for (int j = 0; j < gpb && g0 + j < G; ++j) {
+        rm = (1.f - momentum) * rm + momentum * sh_m[j][cl];
+        rv = (1.f - momentum) * rv + momentum * sh_v[j][cl];
       }
     }
+    __syncthreads();
   }
-  if (lane == 0) {
+  if (gl == 0 && c < C) {
     if (running_mean) running_mean[c] = rm;
     if (running_var) running_var[c] = rv;
   }
@@ -331,30 +338,35 @@ __global__ void __launch_bounds__(256, 4) bn_apply_kernel(const T* __restrict__ 
   }
 }
 
-__global__ void bn_bwd_finalize_kernel(const float* __restrict__ partial, int nblk, const float* __restrict__ gamma,
-                                       const float* __restrict__ invstd, float* dgamma, float* dbeta, float* coef, int G,
-                                       long long R, int C) {
-  const int lane = threadIdx.x % 32;
-  const int c = blockIdx.x * (blockDim.x / 32) + threadIdx.x / 32;
-  if (c >= C) return;
+__global__ void __launch_bounds__(FIN_CH * FIN_MAXG) bn_bwd_finalize_kernel(const float* __restrict__ partial, int nblk,
+                                                                            const float* __restrict__ gamma,
+                                                                            const float* __restrict__ invstd, float* dgamma,
+                                                                            float* dbeta, float* coef, int G, long long R, int C) {
+  __shared__ float sh_s[FIN_MAXG][FIN_CH], sh_q[FIN_MAXG][FIN_CH];
+  const int cl = threadIdx.x % FIN_CH, gl = threadIdx.x / FIN_CH;
+  const int c = blockIdx.x * FIN_CH + cl;
+  const int gpb = blockDim.x / FIN_CH;
   double dg = 0.0, db = 0.0;
   const double n = (double)R;
-  for (int g0 = 0; g0 < G; g0 += 8) {
-    double s[8], q[8];
-    sum_partials8(partial, nblk, G, C, g0, c, lane, s, q);
-    if (lane == 0) {
-      for (int j = 0; j < 8 && g0 + j < G; ++j) {
-        const int g = g0 + j;
-        db += s[j];
-        dg += q[j];
-        float* k = coef + ((long long)g * C + c) * 3;
-        k[0] = gamma[c] * invstd[g * C + c];
-        k[1] = (float)(s[j] / n);
-        k[2] = (float)(q[j] / n);
-      }
+  for (int g0 = 0; g0 < G; g0 += gpb) {
+    const int g = g0 + gl;
+    if (g < G && c < C) {
+      double s, q;
+      sum_slots(partial, nblk, G, C, g, c, s, q);
+      float* k = coef + ((long long)g * C + c) * 3;
+      k[0] = gamma[c] * invstd[g * C + c];
+      k[1] = (float)(s / n);
+      k[2] = (float)(q / n);
+      sh_s[gl][cl] = (float)s;
+      sh_q[gl][cl] = (float)q;
     }
+    __syncthreads();
+    if (gl == 0 && c < C) {
+      for (int j = 0; j < gpb && g0 + j < G; ++j) { db += (double)sh_s[j][cl]; dg += (double)sh_q[j][cl]; }
+    }
+    __syncthreads();
   }
-  if (lane == 0) {
+  if (gl == 0 && c < C) {
     if (dgamma) dgamma[c] += (float)dg;
     if (dbeta) dbeta[c] += (float)db;
   }
@@ -531,6 +543,34 @@ __global__ void maxpool_bwd_kernel(const T* __restrict__ x, const T* __restrict_
   }
 }
 
+// Work-item -> (image, y, x, channel vector) with a CTA pass covering a compact 2-D tile of pixels (all channel vectors
+// of tw x th pixels), so that the overlapping pooling windows of neighbouring pixels are served by L1 instead of L2
+// (the linear mapping re-read every window up to 9 times from L2: 338 us for the stem's max-pool backward).
+struct PixTile { int tw, th, tiles_w, tiles_h; };
+__host__ __device__ inline PixTile make_pix_tile(int CVn, int H, int W) {
+  PixTile t;
+  int ppb = 256 / CVn; if (ppb < 1) ppb = 1;
+  t.tw = ppb < 8 ? ppb : 8;
+  t.th = ppb / t.tw; if (t.th < 1) t.th = 1;
+  t.tiles_w = (W + t.tw - 1) / t.tw;
+  t.tiles_h = (H + t.th - 1) / t.th;
+  return t;
+}
+__device__ __forceinline__ bool tile_decode(long long i, int CVn, const PixTile& t, int H, int W, int& n, int& y, int& x, int& cv) {
+  const int per_tile = t.tw * t.th * CVn;
+  const long long tile = i / per_tile;
+  int r = (int)(i - tile * per_tile);
+  cv = r % CVn; r /= CVn;
+  const int lx = r % t.tw, ly = r / t.tw;
+  long long q = tile;
+  const int bx = (int)(q % t.tiles_w); q /= t.tiles_w;
+  const int by = (int)(q % t.tiles_h);
+  n = (int)(q / t.tiles_h);
+  x = bx * t.tw + lx;
+  y = by * t.th + ly;
+  return x < W && y < H;
+}
+
 // ---- indexed variants: forward stores the window position of the first maximum (uint8), backward gathers by index.
 // KC > 0: compile-time window size -- the KC*KC loads of a window are issued back to back (predicated, not branched
 // around), so one thread keeps KC*KC 16-byte loads in flight instead of a dependent chain.
@@ -540,12 +580,10 @@ __global__ void __launch_bounds__(256) maxpool_fwd_idx_kernel(const T* __restric
                                                               int Wo, int k_, int stride, int pad, long long total_vec) {
   const int k = KC > 0 ? KC : k_;
   const int CVn = C / VEC;
+  const PixTile pt = make_pix_tile(CVn, Ho, Wo);
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total_vec; i += (long long)gridDim.x * blockDim.x) {
-    const int cv = (int)(i % CVn);
-    long long r = i / CVn;
-    const int ox = (int)(r % Wo); r /= Wo;
-    const int oy = (int)(r % Ho);
-    const int n = (int)(r / Ho);
+    int n, oy, ox, cv;
+    if (!tile_decode(i, CVn, pt, Ho, Wo, n, oy, ox, cv)) continue;
     float best[VEC];
     int arg[VEC];
 #pragma unroll
@@ -602,12 +640,10 @@ __global__ void __launch_bounds__(256) maxpool_bwd_idx_kernel(const unsigned cha
                                                               T* __restrict__ dx, int N, int H, int W, int C, int Ho, int Wo, int k,
                                                               int stride, int pad, long long total_vec) {
   const int CVn = C / VEC;
+  const PixTile pt = make_pix_tile(CVn, H, W);
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total_vec; i += (long long)gridDim.x * blockDim.x) {
-    const int cv = (int)(i % CVn);
-    long long r = i / CVn;
-    const int ix = (int)(r % W); r /= W;
-    const int iy = (int)(r % H);
-    const int n = (int)(r / H);
+    int n, iy, ix, cv;
+    if (!tile_decode(i, CVn, pt, H, W, n, iy, ix, cv)) continue;
     float acc[VEC];
 #pragma unroll
     for (int j = 0; j < VEC; ++j) acc[j] = 0.f;
@@ -959,7 +995,8 @@ extern "C" int stfb_bn_finalize_train(const float* partial, int nblk, const floa
   STFB_REQUIRE(partial && nblk > 0 && gamma && beta && scale && shift && mean && invstd && G > 0 && R > 0 && C > 0,
                "bn_finalize_train: bad arguments");
   STFB_DEVICE_OR_RETURN();
-  bn_finalize_train_kernel<<<ceil_div(C, 8), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+  const int fin_g = G < FIN_MAXG ? G : FIN_MAXG;
+  bn_finalize_train_kernel<<<ceil_div(C, FIN_CH), FIN_CH * fin_g, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
       partial, nblk, gamma, beta, running_mean, running_var, nbt, scale, shift, mean, invstd, G, R, C, eps, momentum);
   return post_launch("bn_finalize_train");
 }
@@ -1005,7 +1042,8 @@ extern "C" int stfb_bn_bwd_finalize(const float* partial, int nblk, const float*
                                     float* dbeta, float* coef, int G, long long R, int C, void* stream) {
   STFB_REQUIRE(partial && nblk > 0 && gamma && invstd && coef && G > 0 && R > 0 && C > 0, "bn_bwd_finalize: bad arguments");
   STFB_DEVICE_OR_RETURN();
-  bn_bwd_finalize_kernel<<<ceil_div(C, 8), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(partial, nblk, gamma, invstd, dgamma,
+  const int fin_g = G < FIN_MAXG ? G : FIN_MAXG;
+  bn_bwd_finalize_kernel<<<ceil_div(C, FIN_CH), FIN_CH * fin_g, 0, reinterpret_cast<cudaStream_t>(stream)>>>(partial, nblk, gamma, invstd, dgamma,
                                                                                              dbeta, coef, G, R, C);
   return post_launch("bn_bwd_finalize");
 }
@@ -1061,7 +1099,8 @@ extern "C" int stfb_maxpool_fwd_idx(const void* x, void* y, unsigned char* idx, 
   STFB_DEVICE_OR_RETURN();
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   const bool v = (C % 8 == 0) && aligned_to(x, 16) && aligned_to(y, 16) && aligned_to(idx, 8);
-  const long long tv = (long long)N * Ho * Wo * (C / (v ? 8 : 1));
+  const PixTile ptile = make_pix_tile(C / (v ? 8 : 1), Ho, Wo);
+  const long long tv = (long long)N * ptile.tiles_h * ptile.tiles_w * ptile.tw * ptile.th * (C / (v ? 8 : 1));
   if (tv == 0) return STFB_OK;
   const int grid = grid_for(tv);
 #define MP_FWD(V, KC) maxpool_fwd_idx_kernel<T, V, KC><<<grid, 256, 0, s>>>((const T*)x, (T*)y, idx, N, H, W, C, Ho, Wo, k, stride, pad, tv)
@@ -1079,7 +1118,8 @@ extern "C" int stfb_maxpool_bwd_idx(const unsigned char* idx, const void* dy, vo
   STFB_DEVICE_OR_RETURN();
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   const bool v = (C % 8 == 0) && aligned_to(dy, 16) && aligned_to(dx, 16) && aligned_to(idx, 8);
-  const long long tv = (long long)N * H * W * (C / (v ? 8 : 1));
+  const PixTile ptile = make_pix_tile(C / (v ? 8 : 1), H, W);
+  const long long tv = (long long)N * ptile.tiles_h * ptile.tiles_w * ptile.tw * ptile.th * (C / (v ? 8 : 1));
   if (tv == 0) return STFB_OK;
   const int wmax = (k + stride - 1) / stride;        // windows that can contain one input element, per axis
   STFB_REQUIRE(wmax <= 3, "maxpool_bwd_idx: k (%d) > 3 * stride (%d) is not supported", k, stride);

@@ -429,6 +429,67 @@ int conv2d_wgrad_simt(const WgradArgs& a0, int dtype, cudaStream_t st) {
   return post_launch("conv2d_wgrad(simt)");
 }
 
+// 1x1 weight gradient with very few output channels (the 32 -> 2 segmentation head, src/stf_lstm_unet.py:137):
+// dW[cp][cg] += sum_rows P[row][cp] * G[row][cg] is a pure streaming reduction over G (Cp <= 4 accumulators per channel),
+// not a GEMM: the tiled FFMA kernel spent 150 us on it (one 128 x 64 tile, 2 useful columns).
+template <typename T, int CPMAX>
+__global__ void __launch_bounds__(256) wgrad_head_kernel(const T* __restrict__ P, const T* __restrict__ G, float* dW, long long rows,
+                                                         int Cp, int Cg, int cg_off, int cg_total, long long rows_per_block) {
+  __shared__ float red[256 * 8];
+  const int tpr = Cg / 8, lanes = 256 / tpr;
+  const int cl = threadIdx.x % tpr, rl = threadIdx.x / tpr;
+  const long long r0 = (long long)blockIdx.x * rows_per_block, r1 = min(rows, r0 + rows_per_block);
+  float acc[CPMAX][8];
+#pragma unroll
+  for (int p = 0; p < CPMAX; ++p)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[p][j] = 0.f;
+  if (rl < lanes) {
+    for (long long r = r0 + rl; r < r1; r += lanes) {
+      const f8 g = ld8(G + r * Cg + cl * 8);
+      float pv[CPMAX];
+#pragma unroll
+      for (int p = 0; p < CPMAX; ++p) pv[p] = p < Cp ? ld1(P + r * Cp + p) : 0.f;
+#pragma unroll
+      for (int p = 0; p < CPMAX; ++p)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[p][j] = fmaf(pv[p], g.v[j], acc[p][j]);
+    }
+  }
+  for (int p = 0; p < Cp; ++p) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) red[threadIdx.x * 8 + j] = (rl < lanes) ? acc[p][j] : 0.f;
+    __syncthreads();
+    for (int t = threadIdx.x; t < Cg; t += 256) {        // column t = (cl = t / 8, j = t % 8)
+      float s = 0.f;
+      for (int l = 0; l < lanes; ++l) s += red[(l * tpr + t / 8) * 8 + (t & 7)];
+      atomicAdd(dW + (long long)p * cg_total + cg_off + t, s);
+    }
+    __syncthreads();
+  }
+}
+
+static bool wgrad_head_ok(const void* P, const void* G, int Cp, int Cg, int kh, int kw, int stride, int pad, int Hp, int Wp, int Hg,
+                          int Wg) {
+  return kh == 1 && kw == 1 && stride == 1 && pad == 0 && Hp == Hg && Wp == Wg && Cp <= 4 && Cg % 8 == 0 && Cg <= 2048 &&
+         256 % (Cg / 8) == 0 && (reinterpret_cast<uintptr_t>(G) % 16) == 0 && P != nullptr;
+}
+
+static int wgrad_head(const void* P, const void* G, float* dW, long long rows, int Cp, int Cg, int cg_off, int cg_total, int dtype,
+                      cudaStream_t st) {
+  if (rows == 0) return STFB_OK;
+  long long nblk = (rows + 511) / 512;
+  if (nblk > 4LL * num_sms()) nblk = 4LL * num_sms();
+  const long long rpb = (rows + nblk - 1) / nblk;
+  nblk = (rows + rpb - 1) / rpb;
+  if (dtype == STFB_F32)
+    wgrad_head_kernel<float, 4><<<(unsigned)nblk, 256, 0, st>>>((const float*)P, (const float*)G, dW, rows, Cp, Cg, cg_off, cg_total, rpb);
+  else
+    wgrad_head_kernel<__nv_bfloat16, 4><<<(unsigned)nblk, 256, 0, st>>>((const __nv_bfloat16*)P, (const __nv_bfloat16*)G, dW, rows, Cp,
+                                                                      Cg, cg_off, cg_total, rpb);
+  return post_launch("conv2d_wgrad(head)");
+}
+
 // =================================================================================================
 // weight packing
 // =================================================================================================
@@ -511,6 +572,7 @@ extern "C" int stfb_pack_weights_batched(const stfb_pack_job* jobs_dev, int njob
 namespace stfb {
 int conv2d_tcgen05(const stfb_conv_params* p, cudaStream_t st);
 int conv2d_tcgen05_supported(const stfb_conv_params* p);
+int conv2d_stats_fusable(const stfb_conv_params* p, int groups);
 int wgrad_tcgen05_supported(int N, int Hp, int Wp, int Cp, int Hg, int Wg, int Cg, int kh, int kw, int stride, int pad,
                             int dtype, const void* P, const void* G);
 int wgrad_tcgen05(const void* P, const void* G, const void* G2, float* dW, int N, int H, int W, int Cp, int Hg, int Wg,
@@ -561,6 +623,11 @@ extern "C" int stfb_conv2d_tcgen05_supported(const stfb_conv_params* p) {
   return stfb::conv2d_tcgen05_supported(p);   // pure shape / dtype / alignment check; w and ldw are not inspected
 }
 
+extern "C" int stfb_conv2d_stats_fusable(const stfb_conv_params* p, int groups) {
+  if (p == nullptr) return 0;
+  return stfb::conv2d_stats_fusable(p, groups);
+}
+
 extern "C" int stfb_conv2d(const stfb_conv_params* p, void* stream) {
   int st = validate_conv(p);
   if (st != STFB_OK) return st;
@@ -573,6 +640,7 @@ extern "C" int stfb_conv2d(const stfb_conv_params* p, void* stream) {
     }
     return stfb::conv2d_tcgen05(p, s);
   }
+  STFB_REQUIRE(p->stat_partial == nullptr, "conv2d: fused BatchNorm statistics need the tcgen05 family");
   return conv2d_simt(p, s);   // STFB_IMPL_AUTO == SIMT: the two families take different weight packings
 }
 
@@ -632,6 +700,8 @@ extern "C" int stfb_conv2d_wgrad(const void* P, const void* G, float* dW, int N,
     }
   }
   STFB_REQUIRE(dW != nullptr, "conv2d_wgrad: deferred mode (dW = NULL) needs the tcgen05 family");
+  if (wgrad_head_ok(P, G, Cp, Cg, kh, kw, stride, pad, Hp, Wp, Hg, Wg))
+    return wgrad_head(P, G, dW, (long long)N * Hp * Wp, Cp, Cg, cg_off, cg_total, dtype, reinterpret_cast<cudaStream_t>(stream));
   WgradArgs a{};
   a.P = P; a.G = G; a.dW = dW; a.N = N; a.Hp = Hp; a.Wp = Wp; a.Cp = Cp; a.Hg = Hg; a.Wg = Wg; a.Cg = Cg;
   a.cg_off = cg_off; a.cg_total = cg_total; a.kh = kh; a.kw = kw; a.stride = stride; a.pad = pad;

@@ -20,13 +20,15 @@ BN_MOMENTUM = 0.1
 import os as _os
 USE_TCGEN05 = _os.environ.get("STFB_NO_TCGEN05", "0") != "1"
 USE_FUSED_LSTM = _os.environ.get("STFB_NO_FUSED_LSTM", "0") != "1"
+USE_FUSED_BN_STATS = _os.environ.get("STFB_NO_FUSED_BN_STATS", "0") != "1"
 
 
 class Var:
     """An NHWC activation plus (during backward) its gradient."""
-    __slots__ = ("data", "grad", "needs_grad", "grad_dtype")
+    __slots__ = ("data", "grad", "needs_grad", "grad_dtype", "bn_partial")
 
     def __init__(self, data, needs_grad=True, grad_dtype=None):
+        self.bn_partial = None     # fused BatchNorm partial sums produced by the conv that wrote `data`
         self.data = data
         self.grad = None
         self.needs_grad = needs_grad
@@ -103,6 +105,33 @@ class Executor:
             Executor._tc_cache[key] = r
         return r
 
+    _sf_cache = {}
+
+    def stats_fusable(self, x, Cout, k, stride, pad, G, x2=None):
+        if not USE_FUSED_BN_STATS:
+            return False
+        key = (tuple(x.shape), Cout, k, stride, pad, G, None if x2 is None else x2.shape[3])
+        r = Executor._sf_cache.get(key)
+        if r is None:
+            r = ops.conv_stats_fusable(x, Cout, k, stride, pad, G, x2)
+            Executor._sf_cache[key] = r
+        return r
+
+    STAT_ARENA_FLOATS = 1 << 21        # 8 MB of zeroed fp32 per forward: one fill instead of one per BatchNorm layer
+
+    def stat_buffer(self, G, C, device):
+        """Zeroed [STAT_SLOTS, 2, G, C] fp32 for the fused BatchNorm statistics, carved from one arena per forward."""
+        n = ops.STAT_SLOTS * 2 * G * C
+        arena = getattr(self, "_stat_arena", None)
+        if arena is None or self._stat_off + n > arena.numel():
+            if n > self.STAT_ARENA_FLOATS:
+                return torch.zeros((ops.STAT_SLOTS, 2, G, C), dtype=torch.float32, device=device)
+            arena = self._stat_arena = torch.zeros(self.STAT_ARENA_FLOATS, dtype=torch.float32, device=device)
+            self._stat_off = 0
+        buf = arena[self._stat_off:self._stat_off + n].view(ops.STAT_SLOTS, 2, G, C)
+        self._stat_off += (n + 63) // 64 * 64
+        return buf
+
     def wants_grad(self, name):
         return name in self.grads
 
@@ -118,7 +147,7 @@ class Executor:
     # ---------------------------------------------------------------------------------------------
     def conv(self, x: Var, wname: str, *, k: int, stride: int = 1, pad: int = 0, transposed: bool = False,
              out_pad: int = 0, bname: Optional[str] = None, x2: Optional[Var] = None, scale=None, shift=None,
-             residual=None, relu: bool = False, y_dtype=None) -> Var:
+             residual=None, relu: bool = False, y_dtype=None, stats_G: int = 0) -> Var:
         """Conv2d / ConvTranspose2d (+bias)(+folded BN)(+residual)(+ReLU).  The epilogue extras other than the
         bias are inference-only (no backward through them)."""
         w = self.params[wname]
@@ -128,17 +157,22 @@ class Executor:
         assert not (transposed and x2 is not None)
         if (self.dtype == torch.bfloat16 and USE_TCGEN05 and not transposed and x2 is None and C1 % 32 != 0
                 and C1 * k * k <= 512 and Cout % 32 == 0 and not x.needs_grad and residual is None):
-            return self._conv_small_cin(x, wname, k, stride, pad, bname, scale, shift, relu, y_dtype)
+            return self._conv_small_cin(x, wname, k, stride, pad, bname, scale, shift, relu, y_dtype, stats_G)
         mode = ops.CONV_TRANSPOSED if transposed else ops.CONV_FWD
         out_hw = ops.conv_out_hw(H, W, k, stride, pad, transposed, out_pad)
         x2d = None if x2 is None else x2.data
         tc = self.use_tc(x.data, Cout, k, stride, pad, x2d, mode, out_hw)
         wp = self.packed(wname, k_is_dim1=not transposed, n_major=tc)
         bias = self.params[bname] if bname else None
+        partial = None
+        if stats_G and tc and not transposed and y_dtype in (None, torch.bfloat16) and self.stats_fusable(x.data, Cout, k, stride, pad, stats_G, x2d):
+            # train-mode BatchNorm statistics of the output come out of the conv epilogue (no separate pass over y)
+            partial = self.stat_buffer(stats_G, Cout, x.data.device)
         y = ops.conv2d(x.data, wp, Cout, k, stride, pad, mode=mode, out_hw=out_hw, x2=x2d,
                        bias=bias, scale=scale, shift=shift, residual=residual, relu=relu, y_dtype=y_dtype,
-                       impl=ops.IMPL_TCGEN05 if tc else ops.IMPL_SIMT)
+                       impl=ops.IMPL_TCGEN05 if tc else ops.IMPL_SIMT, stat_partial=partial, stat_groups=stats_G if partial is not None else 0)
         out = Var(y, grad_dtype=self.dtype)
+        out.bn_partial = partial
         if not self.record:
             return out
         assert scale is None and residual is None and not relu, "fused epilogue is inference-only"
@@ -175,7 +209,7 @@ class Executor:
         self.tape.append(bwd)
         return out
 
-    def _conv_small_cin(self, x, wname, k, stride, pad, bname, scale, shift, relu, y_dtype):
+    def _conv_small_cin(self, x, wname, k, stride, pad, bname, scale, shift, relu, y_dtype, stats_G=0):
         """Few-input-channel conv (7x7 stem, UNet enc1.0) as im2col (K padded to 64) + 1x1 tcgen05 GEMM; its weight
         gradient is the 1x1 tcgen05 wgrad over the same im2col buffer.  The input never needs a gradient."""
         w = self.params[wname]
@@ -184,9 +218,13 @@ class Executor:
         col = ops.im2col_small(x.data, k, stride, pad, kpad)
         wp = self.packed(wname, True, n_major=True, kpad=kpad)
         bias = self.params[bname] if bname else None
+        partial = None
+        if stats_G and y_dtype in (None, torch.bfloat16) and self.stats_fusable(col, Cout, 1, 1, 0, stats_G):
+            partial = self.stat_buffer(stats_G, Cout, col.device)
         y = ops.conv2d(col, wp, Cout, 1, 1, 0, bias=bias, scale=scale, shift=shift, relu=relu, y_dtype=y_dtype,
-                       impl=ops.IMPL_TCGEN05)
+                       impl=ops.IMPL_TCGEN05, stat_partial=partial, stat_groups=stats_G if partial is not None else 0)
         out = Var(y, grad_dtype=self.dtype)
+        out.bn_partial = partial
         if not self.record:
             return out
         assert scale is None and not relu, "fused epilogue is inference-only"
@@ -213,7 +251,8 @@ class Executor:
         assert N % G == 0
         R = (N // G) * H * W
         P = self.params
-        sums = ops.bn_stats(x.data, G, R, C)
+        sums = x.bn_partial if x.bn_partial is not None else ops.bn_stats(x.data, G, R, C)
+        x.bn_partial = None
         st = ops.bn_finalize_train(sums, P[prefix + ".weight"], P[prefix + ".bias"], P[prefix + ".running_mean"],
                                    P[prefix + ".running_var"], P[prefix + ".num_batches_tracked"], G, R, C, BN_EPS,
                                    BN_MOMENTUM)
@@ -245,7 +284,7 @@ class Executor:
                 residual: Optional[Var] = None, bname: Optional[str] = None, x2: Optional[Var] = None, G: int = 1) -> Var:
         """conv -> BatchNorm -> (+residual) -> ReLU.  Eval: one fused launch with the BN folded into the epilogue."""
         if self.train:
-            raw = self.conv(x, wname, k=k, stride=stride, pad=pad, bname=bname, x2=x2)
+            raw = self.conv(x, wname, k=k, stride=stride, pad=pad, bname=bname, x2=x2, stats_G=G)
             return self.bn(raw, bnprefix, G, relu, residual)
         P = self.params
         fold = ops.bn_fold_eval(P[bnprefix + ".weight"], P[bnprefix + ".bias"], P[bnprefix + ".running_mean"],

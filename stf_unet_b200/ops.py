@@ -14,7 +14,7 @@ from ._lib import BF16, CONV_FWD, CONV_TRANSPOSED, F32, IMPL_AUTO, IMPL_SIMT, IM
 
 __all__ = ["dt_code", "conv2d", "conv2d_wgrad", "pack_weight", "bn_stats", "bn_finalize_train", "bn_fold_eval",
            "bn_apply", "bn_bwd", "colsum", "maxpool_fwd", "maxpool_bwd", "maxpool_fwd_idx", "maxpool_bwd_idx", "bilinear_fwd", "bilinear_bwd",
-           "tcgen05_ok", "im2col_small", "unpad_wgrad", "lstm_step_fused", "pack_lstm_xh", "lstm_cell_fwd", "lstm_cell_bwd", "pack_series", "pack_series_maps", "repeat_batch", "nhwc_to_nchw", "nchw_to_nhwc", "add_", "cast",
+           "tcgen05_ok", "conv_stats_fusable", "STAT_SLOTS", "im2col_small", "unpad_wgrad", "lstm_step_fused", "pack_lstm_xh", "lstm_cell_fwd", "lstm_cell_bwd", "pack_series", "pack_series_maps", "repeat_batch", "nhwc_to_nchw", "nchw_to_nhwc", "add_", "cast",
            "ce_dice_fwd", "ce_dice_bwd", "CONV_FWD", "CONV_TRANSPOSED", "IMPL_AUTO", "IMPL_SIMT", "IMPL_TCGEN05"]
 
 _DT = {torch.float32: F32, torch.bfloat16: BF16}
@@ -118,8 +118,12 @@ def conv_out_hw(H, W, k, stride, pad, transposed=False, out_pad=0):
     return (H + 2 * pad - k) // stride + 1, (W + 2 * pad - k) // stride + 1
 
 
+STAT_SLOTS = 8   # partial-sum slots of the fused BatchNorm statistics (CTA % slots): bounds the red.add contention
+
+
 def conv2d(x, wp, Cout, k, stride, pad, *, mode=CONV_FWD, out_hw=None, x2=None, bias=None, bias2=None, scale=None,
-           shift=None, residual=None, relu=False, y_dtype=None, ldw=None, out=None, w_offset=0, impl=IMPL_AUTO):
+           shift=None, residual=None, relu=False, y_dtype=None, ldw=None, out=None, w_offset=0, impl=IMPL_AUTO,
+           stat_partial=None, stat_groups=0):
     """Implicit-GEMM convolution with fused epilogue; see stfb_conv2d in include/stfb200.h."""
     _need_cuda(x, wp)
     N, H, W, C1 = x.shape
@@ -136,7 +140,9 @@ def conv2d(x, wp, Cout, k, stride, pad, *, mode=CONV_FWD, out_hw=None, x2=None, 
     p = ConvParams(x=_p(x), x2=_p(x2), w=wp.data_ptr() + w_offset * esz, y=_p(y), bias=_p(bias), bias2=_p(bias2),
                    scale=_p(scale), shift=_p(shift), residual=_p(residual), N=N, H=H, W=W, C1=C1, C2=C2, Ho=Ho, Wo=Wo,
                    Cout=Cout, kh=kh, kw=kw, stride=stride, pad=pad, ldw=ldw if ldw is not None else Cout, mode=mode,
-                   relu=int(bool(relu)), x_dtype=dt_code(x.dtype), y_dtype=dt_code(y.dtype), impl=impl)
+                   relu=int(bool(relu)), x_dtype=dt_code(x.dtype), y_dtype=dt_code(y.dtype), impl=impl,
+                   stat_partial=_p(stat_partial), stat_slots=0 if stat_partial is None else stat_partial.shape[0],
+                   stat_groups=stat_groups)
     if _prof is None:
         check(_lib.load().stfb_conv2d(C.byref(p), _stream()), "conv2d")
         return y
@@ -342,6 +348,16 @@ def tcgen05_ok(x, Cout, k, stride, pad, mode=CONV_FWD, x2=None, out_hw=None, y_d
     p = ConvParams(x=_p(x), x2=_p(x2), N=N, H=H, W=W, C1=C1, C2=C2, Ho=Ho, Wo=Wo, Cout=Cout, kh=k, kw=k, stride=stride,
                    pad=pad, mode=mode, x_dtype=dt_code(x.dtype), y_dtype=dt_code(y_dtype or x.dtype))
     return _lib.load().stfb_conv2d_tcgen05_supported(C.byref(p)) == 1
+
+
+def conv_stats_fusable(x, Cout, k, stride, pad, G, x2=None):
+    """Can the tcgen05 conv of this shape also reduce the BatchNorm statistics of its (bf16) output over G image groups?"""
+    N, H, W, C1 = x.shape
+    C2 = 0 if x2 is None else x2.shape[3]
+    Ho, Wo = conv_out_hw(H, W, k, stride, pad)
+    p = ConvParams(x=_p(x), x2=_p(x2), N=N, H=H, W=W, C1=C1, C2=C2, Ho=Ho, Wo=Wo, Cout=Cout, kh=k, kw=k, stride=stride,
+                   pad=pad, mode=CONV_FWD, x_dtype=dt_code(x.dtype), y_dtype=BF16)
+    return _lib.load().stfb_conv2d_stats_fusable(C.byref(p), G) == 1
 
 
 def bn_stats(x, G, R, C):

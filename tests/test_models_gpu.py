@@ -326,9 +326,15 @@ def test_stf_pk_maps_train_vs_oracle(dtype):
         assert cos > 0.95
 
 
-def test_graphed_step_matches_eager():
-    """CUDA-graph replay of fwd + loss + bwd gives the eager step's loss and gradients, step after step."""
+@pytest.mark.parametrize("fused_stats", [False, True])
+def test_graphed_step_matches_eager(fused_stats, monkeypatch):
+    """CUDA-graph replay of fwd + loss + bwd gives the eager step's loss and gradients, step after step.  With the
+    BatchNorm statistics fused into the conv epilogue the per-channel sums are fp32 red.adds whose order differs from
+    run to run, so that variant is compared at bf16 noise level instead of bit level."""
     from stf_unet_b200.graph import GraphedStep
+    from stf_unet_b200 import engine
+    monkeypatch.setattr(engine, "USE_FUSED_BN_STATS", fused_stats)
+    ltol, gtol = (2e-3, 3e-2) if fused_stats else (1e-5, 1e-3)
     torch.manual_seed(0)
     x, t = W.synthetic_dce_batch(2, 3, 64, 64, seed=71)
     x2, t2 = W.synthetic_dce_batch(2, 3, 64, 64, seed=72)
@@ -345,11 +351,43 @@ def test_graphed_step_matches_eager():
         with torch.autocast("cuda", dtype=torch.bfloat16):
             lb = S.criterion(b(xb.to(DEV)), tb.to(DEV))
         lb.backward()
-        assert abs(la.item() - lb.item()) < 1e-5 * max(1.0, abs(lb.item()))
+        assert abs(la.item() - lb.item()) < ltol * max(1.0, abs(lb.item()))
+        if fused_stats:
+            continue      # B=2 puts 8..32 samples behind each deep BatchNorm: atomics-order noise is amplified chaotically there;
+                          # gradients of the fused path are checked at a well-conditioned size in the next test
         for (n, pa), (_, pb) in zip(a.named_parameters(), b.named_parameters()):
-            assert rel(pa.grad, pb.grad) < 1e-3, n
+            assert rel(pa.grad, pb.grad) < gtol, n
     assert int(a.bn1.num_batches_tracked) == int(b.bn1.num_batches_tracked)
     assert gs.launches_per_replay > 100
+
+
+def test_fused_bn_statistics_match_two_pass_training(monkeypatch):
+    """One bf16 training step (warm weights) with the BatchNorm statistics reduced in the conv epilogues vs the same step
+    with the separate statistics pass: same loss, same running statistics, gradients aligned at bf16 noise level (each
+    route is checked against the oracle in test_stf_train_bf16_vs_oracle)."""
+    from stf_unet_b200 import engine
+    B, T, HW = 4, 4, 128
+    x, t = W.synthetic_dce_batch(B, T, HW, HW, seed=91)
+    sd = warm_stf_state()
+    outs = []
+    for fused in (False, True):
+        monkeypatch.setattr(engine, "USE_FUSED_BN_STATS", fused)
+        m = load_model(S.STFLSTMUNet(1, 2, T), sd)
+        m.train()
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            loss = S.criterion(m(x.to(DEV)), t.to(DEV))
+        loss.backward()
+        outs.append((loss.item(), {n: p.grad.double().flatten() for n, p in m.named_parameters()},
+                     m.layer2[1].bn1.running_var.clone(), int(m.bn1.num_batches_tracked)))
+    (l0, g0, rv0, nb0), (l1, g1, rv1, nb1) = outs
+    assert abs(l0 - l1) < 2e-3 * max(1.0, abs(l0))
+    assert nb0 == nb1 and rel(rv1, rv0) < 2e-3
+    num = sum((g0[n] * g1[n]).sum().item() for n in g0)
+    d0 = sum((g0[n] * g0[n]).sum().item() for n in g0)
+    d1 = sum((g1[n] * g1[n]).sum().item() for n in g0)
+    cos = num / (d0 ** 0.5 * d1 ** 0.5)
+    print("fused-vs-two-pass grad cosine", cos, "norm ratio", (d1 / d0) ** 0.5)
+    assert cos > 0.99 and 0.95 < (d1 / d0) ** 0.5 < 1.05
 
 
 def test_unet_bf16_train_vs_oracle():

@@ -664,3 +664,33 @@ def test_eval_metrics_kernel_matches_golden_and_oracle(golden_dir):
     assert torch.equal(argmax_mask(logits.to(DEV)).cpu().long(), logits.argmax(1))
     # empty batch
     m4.update(torch.empty(0, 4, 8, 8, device=DEV), torch.empty(0, 8, 8, dtype=torch.int64, device=DEV))
+
+
+@pytest.mark.parametrize("case", [(16, 32, 32, 64, 64, 3, 1, 8), (8, 16, 16, 128, 256, 3, 1, 4), (32, 8, 8, 128, 128, 3, 1, 8),
+                                  (6, 25, 19, 64, 128, 3, 1, 3), (8, 32, 32, 64, 128, 3, 2, 2), (12, 16, 16, 64, 64, 1, 1, 4),
+                                  (40, 32, 32, 64, 64, 3, 1, 5)])
+def test_conv_fused_bn_statistics(case):
+    """Train-mode BatchNorm statistics (per image group sum / sum of squares of the bf16 outputs) reduced in the conv
+    epilogue == the separate bn_stats pass over the stored output (reference: nn.BatchNorm2d after every conv,
+    src/stf_lstm_unet.py:14,17 ; one call per time step -> per-group statistics, :168-186)."""
+    N, H, W, Cin, Cout, k, stride, G = case
+    dtype = torch.bfloat16
+    pad = (k - 1) // 2
+    x = nhwc(q(rnd(N, Cin, H, W, seed=1), dtype), dtype)
+    w = q(rnd(Cout, Cin, k, k, seed=2, scale=(1.0 / (k * k * Cin)) ** 0.5), dtype)
+    wp = ops.pack_weight(w.contiguous(), True, dtype, n_major=True)
+    assert ops.conv_stats_fusable(x, Cout, k, stride, pad, G)
+    partial = torch.zeros(ops.STAT_SLOTS, 2, G, Cout, device=DEV)
+    y = ops.conv2d(x, wp, Cout, k, stride, pad, impl=ops.IMPL_TCGEN05, stat_partial=partial, stat_groups=G)
+    y_plain = ops.conv2d(x, wp, Cout, k, stride, pad, impl=ops.IMPL_TCGEN05)
+    assert torch.equal(y, y_plain)
+    yf = y.float().view(G, -1, Cout)
+    s_ref, q_ref = yf.sum(1), (yf * yf).sum(1)
+    got = partial.double().sum(0)
+    assert rel(got[0], s_ref) < 1e-5 and rel(got[1], q_ref) < 1e-5
+    # and through the finalize kernel: same scale / shift as the two-pass route
+    R = yf.shape[1]
+    gamma, beta = rnd(Cout, seed=3).abs() + 0.5, rnd(Cout, seed=4)
+    st_f = ops.bn_finalize_train(partial, gamma, beta, None, None, None, G, R, Cout)
+    st_2 = ops.bn_finalize_train(ops.bn_stats(y, G, R, Cout), gamma, beta, None, None, None, G, R, Cout)
+    assert rel(st_f[0], st_2[0]) < 1e-5 and (st_f[1] - st_2[1]).abs().max().item() < 1e-4
