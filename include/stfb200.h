@@ -183,16 +183,19 @@ int stfb_bn_fold_eval(const float* gamma, const float* beta, const float* runnin
 int stfb_bn_apply(const void* x, const float* scale, const float* shift, const void* residual, void* y, int G,
                   long long R, int C, int relu, int dtype, void* stream);
 /* backward, step 1: dz = dy * (y > 0 if relu); partial[blk][0][g][c] = sum dz, partial[blk][1][g][c] = sum dz*xhat */
+/* relu: the ReLU mask is y > 0; with y == NULL it is recomputed as fma(x, scale, shift) > 0 from the forward's scale and
+ * shift (saves the read of y; only valid when no residual was added before the ReLU). */
 int stfb_bn_bwd_reduce(const void* dy, const void* y, const void* x, const float* mean, const float* invstd,
-                       float* partial, int nblk, int G, long long R, int C, int relu, int dtype, void* stream);
+                       const float* scale, const float* shift, float* partial, int nblk, int G, long long R, int C, int relu,
+                       int dtype, void* stream);
 /* backward, step 2: dgamma[c] += sum_g sum2, dbeta[c] += sum_g sum1; coef[g][c][3] = {gamma*invstd, sum1/R, sum2/R} */
 int stfb_bn_bwd_finalize(const float* partial, int nblk, const float* gamma, const float* invstd, float* dgamma,
                          float* dbeta, float* coef, int G, long long R, int C, void* stream);
 /* backward, step 3: dx = coef0 * (dz - coef1 - xhat*coef2); if dres != NULL: dres = dz (+ dres when accum_dres:
  * the residual input of a block already carries the gradient of its other consumers) */
 int stfb_bn_bwd_apply(const void* dy, const void* y, const void* x, const float* mean, const float* invstd,
-                      const float* coef, void* dx, void* dres, int accum_dres, int G, long long R, int C, int relu,
-                      int dtype, void* stream);
+                      const float* coef, const float* shift /* with y == NULL: mask = fma(x, coef0, shift) > 0 */, void* dx,
+                      void* dres, int accum_dres, int G, long long R, int C, int relu, int dtype, void* stream);
 /* out[c] += sum_rows x[row][c]  (bias gradients: Conv2d/ConvTranspose2d bias, LSTM bias_ih/bias_hh) */
 int stfb_colsum(const void* x, float* out, long long R, int C, int dtype, void* stream);
 

@@ -23,6 +23,8 @@ struct ColRedArgs {
   const void* c;       //                  MODE 1: x (pre-BN)
   const float* mean;   // [G][C]  (MODE 1)
   const float* invstd; // [G][C]  (MODE 1)
+  const float* scale;  // [G][C]  (MODE 1, relu without y: the mask is recomputed as fma(x, scale, shift) > 0)
+  const float* shift;  // [G][C]
   float* partial;      // [nblk][2][G][C]  (MODE 0/1): per-CTA partial sums, combined in fp64 by the finalize kernels
   float* outf;         // [C]        (MODE 2)
   int G;
@@ -77,12 +79,15 @@ __global__ void __launch_bounds__(256) colreduce_kernel(const ColRedArgs A) {
     for (int j = 0; j < VEC; ++j) s[j] = q[j] = 0.f;
     if (active) {
       const int c = cv * VEC;
-      float mu[VEC], is[VEC];
+      float mu[VEC], is[VEC], sc[VEC], sh[VEC];
+      const bool mask_from_x = MODE == 1 && A.relu && pb == nullptr;
       if (MODE == 1) {
 #pragma unroll
         for (int j = 0; j < VEC; ++j) {
           mu[j] = A.mean[g * A.C + c + j];
           is[j] = A.invstd[g * A.C + c + j];
+          sc[j] = mask_from_x ? A.scale[g * A.C + c + j] : 0.f;
+          sh[j] = mask_from_x ? A.shift[g * A.C + c + j] : 0.f;
         }
       }
       const long long gbase = (long long)g * A.R;
@@ -97,8 +102,14 @@ __global__ void __launch_bounds__(256) colreduce_kernel(const ColRedArgs A) {
           ldv<VEC>(pa + off, va[u]);
           if (MODE == 1) {
             ldv<VEC>(pc + off, vc[u]);
-            if (A.relu) ldv<VEC>(pb + off, vb[u]);
+            if (A.relu && !mask_from_x) ldv<VEC>(pb + off, vb[u]);
           }
+        }
+        if (mask_from_x) {
+#pragma unroll
+          for (int u = 0; u < U; ++u)
+#pragma unroll
+            for (int j = 0; j < VEC; ++j) vb[u][j] = fmaf(vc[u][j], sc[j], sh[j]);
         }
 #pragma unroll
         for (int u = 0; u < U; ++u)
@@ -120,7 +131,11 @@ __global__ void __launch_bounds__(256) colreduce_kernel(const ColRedArgs A) {
         ldv<VEC>(pa + off, va);
         if (MODE == 1) {
           ldv<VEC>(pc + off, vc);
-          if (A.relu) ldv<VEC>(pb + off, vb);
+          if (A.relu && !mask_from_x) ldv<VEC>(pb + off, vb);
+          if (mask_from_x) {
+#pragma unroll
+            for (int j = 0; j < VEC; ++j) vb[j] = fmaf(vc[j], sc[j], sh[j]);
+          }
         }
 #pragma unroll
         for (int j = 0; j < VEC; ++j) {
@@ -379,7 +394,7 @@ __global__ void __launch_bounds__(256, 4) bn_bwd_apply_kernel(const T* __restric
                                                               const T* __restrict__ x, const float* __restrict__ mean,
                                                               const float* __restrict__ invstd, const float* __restrict__ coef,
                                                               T* dx, T* dres, long long R, int C, long long rows_per_block, int tpr,
-                                                              int relu, int accum_dres) {
+                                                              int relu, int accum_dres, const float* __restrict__ shift) {
   constexpr int U = 1;
   const int lanes = 256 / tpr;
   const int cl = threadIdx.x % tpr, rl = threadIdx.x / tpr;
@@ -390,7 +405,9 @@ __global__ void __launch_bounds__(256, 4) bn_bwd_apply_kernel(const T* __restric
   const long long gbase = (long long)g * R;
   for (int cv = cl; cv < CVn; cv += tpr) {
     const int c = cv * VEC;
-    float k0[VEC], cb[VEC], cc[VEC];
+    // relu without y: the mask is fma(x, scale, shift) > 0 with scale = gamma * invstd = coef[0] (what bn_apply computed)
+    const bool mask_from_x = relu && y == nullptr;
+    float k0[VEC], cb[VEC], cc[VEC], sh[VEC];
 #pragma unroll
     for (int j = 0; j < VEC; ++j) {
       const int gc = g * C + c + j;
@@ -399,6 +416,7 @@ __global__ void __launch_bounds__(256, 4) bn_bwd_apply_kernel(const T* __restric
       k0[j] = a0;
       cb[j] = -a0 * a2 * is;
       cc[j] = a0 * (mu * is * a2 - a1);
+      sh[j] = mask_from_x ? shift[gc] : 0.f;
     }
     for (long long r = r0 + rl; r < r1; r += (long long)U * lanes) {
       float d[U][VEC], xv[U][VEC], yv[U][VEC];
@@ -409,7 +427,11 @@ __global__ void __launch_bounds__(256, 4) bn_bwd_apply_kernel(const T* __restric
           const long long off = (gbase + rr) * C + c;
           ldv<VEC>(dy + off, d[u]);
           ldv<VEC>(x + off, xv[u]);
-          if (relu) ldv<VEC>(y + off, yv[u]);
+          if (relu && !mask_from_x) ldv<VEC>(y + off, yv[u]);
+          if (mask_from_x) {
+#pragma unroll
+            for (int j = 0; j < VEC; ++j) yv[u][j] = fmaf(xv[u][j], k0[j], sh[j]);
+          }
         }
       }
 #pragma unroll
@@ -1027,14 +1049,16 @@ extern "C" int stfb_bn_apply(const void* x, const float* scale, const float* shi
 }
 
 extern "C" int stfb_bn_bwd_reduce(const void* dy, const void* y, const void* x, const float* mean, const float* invstd,
-                                  float* partial, int nblk, int G, long long R, int C, int relu, int dtype, void* stream) {
+                                  const float* scale, const float* shift, float* partial, int nblk, int G, long long R, int C,
+                                  int relu, int dtype, void* stream) {
   STFB_REQUIRE(dy && x && mean && invstd && partial && G > 0 && R >= 0 && C > 0 && DT_OK(dtype), "bn_bwd_reduce: bad arguments");
-  STFB_REQUIRE(!relu || y, "bn_bwd_reduce: relu needs y");
+  STFB_REQUIRE(!relu || y || (scale && shift), "bn_bwd_reduce: relu needs y, or scale and shift to recompute the mask from x");
   STFB_DEVICE_OR_RETURN();
   STFB_REQUIRE(nblk == colreduce_blocks(G, R), "bn_bwd_reduce: nblk must come from stfb_bn_partial_blocks");
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   ColRedArgs A{};
   A.a = dy; A.b = y; A.c = x; A.mean = mean; A.invstd = invstd; A.partial = partial; A.G = G; A.R = R; A.C = C; A.relu = relu;
+  A.scale = scale; A.shift = shift;
   return launch_colreduce<1>(A, dtype, pick_vec(C, dtype, {dy, y, x}), s, "bn_bwd_reduce", nblk);
 }
 
@@ -1049,10 +1073,10 @@ extern "C" int stfb_bn_bwd_finalize(const float* partial, int nblk, const float*
 }
 
 extern "C" int stfb_bn_bwd_apply(const void* dy, const void* y, const void* x, const float* mean, const float* invstd,
-                                 const float* coef, void* dx, void* dres, int accum_dres, int G, long long R, int C, int relu,
-                                 int dtype, void* stream) {
+                                 const float* coef, const float* shift, void* dx, void* dres, int accum_dres, int G, long long R,
+                                 int C, int relu, int dtype, void* stream) {
   STFB_REQUIRE(dy && x && mean && invstd && coef && dx && G > 0 && R >= 0 && C > 0 && DT_OK(dtype), "bn_bwd_apply: bad arguments");
-  STFB_REQUIRE(!relu || y, "bn_bwd_apply: relu needs y");
+  STFB_REQUIRE(!relu || y || shift, "bn_bwd_apply: relu needs y, or shift to recompute the mask from x");
   STFB_DEVICE_OR_RETURN();
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   const long long rows = (long long)G * R;
@@ -1060,9 +1084,9 @@ extern "C" int stfb_bn_bwd_apply(const void* dy, const void* y, const void* x, c
   const int v = pick_vec(C, dtype, {dy, y, x, dx, dres});
   const RowTile rt = row_tile(G, R, C, v, 1);
   DISPATCH_T(dtype, {
-    if (v == 8) bn_bwd_apply_kernel<T, 8><<<rt.grid, 256, 0, s>>>((const T*)dy, (const T*)y, (const T*)x, mean, invstd, coef, (T*)dx, (T*)dres, R, C, rt.rows_per_block, rt.tpr, relu, accum_dres);
-    else if (v == 4) bn_bwd_apply_kernel<T, 4><<<rt.grid, 256, 0, s>>>((const T*)dy, (const T*)y, (const T*)x, mean, invstd, coef, (T*)dx, (T*)dres, R, C, rt.rows_per_block, rt.tpr, relu, accum_dres);
-    else bn_bwd_apply_kernel<T, 1><<<rt.grid, 256, 0, s>>>((const T*)dy, (const T*)y, (const T*)x, mean, invstd, coef, (T*)dx, (T*)dres, R, C, rt.rows_per_block, rt.tpr, relu, accum_dres);
+    if (v == 8) bn_bwd_apply_kernel<T, 8><<<rt.grid, 256, 0, s>>>((const T*)dy, (const T*)y, (const T*)x, mean, invstd, coef, (T*)dx, (T*)dres, R, C, rt.rows_per_block, rt.tpr, relu, accum_dres, shift);
+    else if (v == 4) bn_bwd_apply_kernel<T, 4><<<rt.grid, 256, 0, s>>>((const T*)dy, (const T*)y, (const T*)x, mean, invstd, coef, (T*)dx, (T*)dres, R, C, rt.rows_per_block, rt.tpr, relu, accum_dres, shift);
+    else bn_bwd_apply_kernel<T, 1><<<rt.grid, 256, 0, s>>>((const T*)dy, (const T*)y, (const T*)x, mean, invstd, coef, (T*)dx, (T*)dres, R, C, rt.rows_per_block, rt.tpr, relu, accum_dres, shift);
   });
   return post_launch("bn_bwd_apply");
 }

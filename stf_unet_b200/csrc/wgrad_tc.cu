@@ -351,7 +351,9 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_halo_kernel(const __grid_
 }
 
 // acc[(tap, cg_off + c*64 + i)][n*64 + j] += sum over splits of partial[split][n][c][tap*64 + i][j]
-// grid (36, pairs): one thread = 4 consecutive output channels of one (tap, ci) row; the partials are L2 resident
+// grid (36, pairs, zchunks): one thread = 4 consecutive output channels of one (tap, ci) row over ONE chunk of the splits
+// (a 64 -> 64 layer has a single pair and 148 splits: without the z axis 36 CTAs would walk all of them); the partials
+// are L2 resident, the chunk sums meet in acc through 16-byte red.adds
 __global__ void __launch_bounds__(256) wgrad_halo_reduce_kernel(const float* __restrict__ partial, float* __restrict__ acc,
                                                                int splits, int cblocks, int nblocks, int Cp, int cg_off,
                                                                int cg_total) {
@@ -360,24 +362,36 @@ __global__ void __launch_bounds__(256) wgrad_halo_reduce_kernel(const float* __r
   const int e = blockIdx.x * 256 + threadIdx.x;      // float4 index inside the 576 x 64 tile
   const int row = e >> 4, j = (e & 15) * 4;
   const int pairs = cblocks * nblocks;
+  const int per = (splits + gridDim.z - 1) / gridDim.z;
+  const int sp0 = blockIdx.z * per, sp1 = min(splits, sp0 + per);
+  if (sp0 >= sp1) return;
   const float4* src = reinterpret_cast<const float4*>(partial + ((long long)pair * 576 + row) * 64 + j);
   const long long stride4 = (long long)pairs * 576 * 64 / 4;
-  float4 s0 = make_float4(0.f, 0.f, 0.f, 0.f), s1 = s0;
-  int sp = 0;
-  for (; sp + 1 < splits; sp += 2) {
+  float4 s0 = make_float4(0.f, 0.f, 0.f, 0.f), s1 = s0, s2 = s0, s3 = s0;
+  int sp = sp0;
+  for (; sp + 3 < sp1; sp += 4) {
     const float4 u = src[(long long)sp * stride4], v = src[(long long)(sp + 1) * stride4];
+    const float4 w = src[(long long)(sp + 2) * stride4], z = src[(long long)(sp + 3) * stride4];
     s0.x += u.x; s0.y += u.y; s0.z += u.z; s0.w += u.w;
     s1.x += v.x; s1.y += v.y; s1.z += v.z; s1.w += v.w;
+    s2.x += w.x; s2.y += w.y; s2.z += w.z; s2.w += w.w;
+    s3.x += z.x; s3.y += z.y; s3.z += z.z; s3.w += z.w;
   }
-  if (sp < splits) {
+  for (; sp < sp1; ++sp) {
     const float4 u = src[(long long)sp * stride4];
     s0.x += u.x; s0.y += u.y; s0.z += u.z; s0.w += u.w;
   }
   const int tap = row >> 6, i = row & 63;
-  float4* dst = reinterpret_cast<float4*>(acc + ((long long)tap * cg_total + cg_off + c * 64 + i) * Cp + n * 64 + j);
-  float4 o = *dst;
-  o.x += s0.x + s1.x; o.y += s0.y + s1.y; o.z += s0.z + s1.z; o.w += s0.w + s1.w;
-  *dst = o;
+  float* dst = acc + ((long long)tap * cg_total + cg_off + c * 64 + i) * Cp + n * 64 + j;
+  const float ox = (s0.x + s1.x) + (s2.x + s3.x), oy = (s0.y + s1.y) + (s2.y + s3.y);
+  const float oz = (s0.z + s1.z) + (s2.z + s3.z), ow = (s0.w + s1.w) + (s2.w + s3.w);
+  if (gridDim.z == 1) {
+    float4 o = *reinterpret_cast<float4*>(dst);
+    o.x += ox; o.y += oy; o.z += oz; o.w += ow;
+    *reinterpret_cast<float4*>(dst) = o;
+  } else {
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(ox), "f"(oy), "f"(oz), "f"(ow) : "memory");
+  }
 }
 
 // caller-owned scratch for the per-split partial tiles (registered once per process: one process drives one GPU)
@@ -650,7 +664,12 @@ int wgrad_tcgen05(const void* P, const void* G, const void* G2, float* dW, int N
       wgrad_halo_kernel<<<hgrid, WG_THREADS, wh_smem_bytes(), st>>>(tG, tG2, tP, a);
       int rc = post_launch("conv2d_wgrad(tcgen05 halo)");
       if (rc == STFB_OK && use_partials) {
-        dim3 rgrid(576 * 64 / 4 / 256, (unsigned)pairs);
+        // ~4 CTAs per SM: split the walk over the partials when there are few (ci, co) pairs
+        int zc = (4 * num_sms() + 36 * pairs - 1) / (36 * pairs);
+        if (zc > (int)splits) zc = (int)splits;
+        if (zc > 16) zc = 16;
+        if (zc < 1) zc = 1;
+        dim3 rgrid(576 * 64 / 4 / 256, (unsigned)pairs, (unsigned)zc);
         wgrad_halo_reduce_kernel<<<rgrid, 256, 0, st>>>(g_wg_scratch, ws, (int)splits, (C1 + C2) / 64, Cp / 64, Cp, cg_off, cg_total);
         rc = post_launch("conv2d_wgrad(halo reduce)");
       }

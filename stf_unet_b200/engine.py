@@ -272,7 +272,8 @@ class Executor:
             dbeta = self.grads.get(bname)
             want_dres = residual is not None and residual.needs_grad
             dx, dres = ops.bn_bwd(dy, y, x.data, mean, invstd, P[gname], dgamma, dbeta, G, R, C, relu, want_dres,
-                                  dres_acc=residual.grad if want_dres else None)
+                                  dres_acc=residual.grad if want_dres else None,
+                                  scale=st[0] if residual is None else None, shift=st[1] if residual is None else None)
             x.grad = dx
             if want_dres:
                 residual.grad = dres

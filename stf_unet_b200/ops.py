@@ -394,23 +394,27 @@ def bn_apply(x, scale, shift, G, R, C, relu, residual=None, out=None):
     return y
 
 
-def bn_bwd(dy, y, x, mean, invstd, gamma, dgamma, dbeta, G, R, C, relu, want_dres, dres_acc=None):
+def bn_bwd(dy, y, x, mean, invstd, gamma, dgamma, dbeta, G, R, C, relu, want_dres, dres_acc=None, scale=None, shift=None):
     """Full BatchNorm(+ReLU)(+residual) backward: returns (dx, dres or None); dgamma/dbeta accumulated.
-    dres_acc: existing gradient of the residual input, accumulated into in place."""
+    dres_acc: existing gradient of the residual input, accumulated into in place.
+    scale/shift (the forward's, [G][C]): with relu and no residual the mask is recomputed from x and y is not read."""
     lib = _lib.load()
     s = _stream()
+    from_x = bool(relu) and not want_dres and dres_acc is None and scale is not None and shift is not None
+    ym = None if (from_x or not relu) else y
     nblk = lib.stfb_bn_partial_blocks(G, R)
     red = torch.empty((nblk, 2, G, C), dtype=torch.float32, device=x.device)
-    with _timed("bn_bwd_reduce", _nb(dy, x, y if relu else None), f"C{C}"):
-        check(lib.stfb_bn_bwd_reduce(_p(dy), _p(y) if relu else None, _p(x), _p(mean), _p(invstd), _p(red), nblk, G, R, C,
-                                     int(bool(relu)), dt_code(x.dtype), s), "bn_bwd_reduce")
+    with _timed("bn_bwd_reduce", _nb(dy, x, ym), f"C{C}"):
+        check(lib.stfb_bn_bwd_reduce(_p(dy), _p(ym), _p(x), _p(mean), _p(invstd), _p(scale) if from_x else None,
+                                     _p(shift) if from_x else None, _p(red), nblk, G, R, C, int(bool(relu)), dt_code(x.dtype), s),
+              "bn_bwd_reduce")
     coef = torch.empty((G, C, 3), dtype=torch.float32, device=x.device)
     check(lib.stfb_bn_bwd_finalize(_p(red), nblk, _p(gamma), _p(invstd), _p(dgamma), _p(dbeta), _p(coef), G, R, C, s),
           "bn_bwd_finalize")
     dx = torch.empty_like(x)
     dres = dres_acc if dres_acc is not None else (torch.empty_like(x) if want_dres else None)
-    with _timed("bn_bwd_apply", _nb(dy, x, y if relu else None, dx, dres, dres_acc), f"C{C}"):
-        check(lib.stfb_bn_bwd_apply(_p(dy), _p(y) if relu else None, _p(x), _p(mean), _p(invstd), _p(coef), _p(dx),
+    with _timed("bn_bwd_apply", _nb(dy, x, ym, dx, dres, dres_acc), f"C{C}"):
+        check(lib.stfb_bn_bwd_apply(_p(dy), _p(ym), _p(x), _p(mean), _p(invstd), _p(coef), _p(shift) if from_x else None, _p(dx),
                                     _p(dres), int(dres_acc is not None), G, R, C, int(bool(relu)), dt_code(x.dtype), s),
               "bn_bwd_apply")
     return dx, dres

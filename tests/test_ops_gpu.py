@@ -187,6 +187,12 @@ def test_batchnorm_train_fwd_bwd(G, B, H, W, C, relu, use_res, dtype):
     t = tol(dtype) * (1 if dtype == torch.float32 else 3)
     assert rel(nchw(dx), x.grad) < t
     assert rel(dgamma, gamma.grad) < t and rel(dbeta, beta.grad) < t
+    if relu and not use_res:
+        # mask recomputed from x (fma(x, scale, shift) > 0) instead of read from y: bit-identical to the y route
+        dg2, db2 = torch.zeros(C, device=DEV), torch.zeros(C, device=DEV)
+        dx2, _ = ops.bn_bwd(nhwc(dy, dtype), None, xn, st[2], st[3], gamma.detach(), dg2, db2, G, R, C, relu, False,
+                            scale=st[0], shift=st[1])
+        assert torch.equal(dx2, dx) and torch.equal(dg2, dgamma) and torch.equal(db2, dbeta)
     if use_res:
         assert rel(nchw(dres), res.grad) < t
         # accumulate form
