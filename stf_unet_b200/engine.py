@@ -21,6 +21,7 @@ import os as _os
 USE_TCGEN05 = _os.environ.get("STFB_NO_TCGEN05", "0") != "1"
 USE_FUSED_LSTM = _os.environ.get("STFB_NO_FUSED_LSTM", "0") != "1"
 USE_FUSED_BN_STATS = _os.environ.get("STFB_NO_FUSED_BN_STATS", "0") != "1"
+USE_LSTM_STREAMS = _os.environ.get("STFB_NO_LSTM_STREAMS", "0") != "1"
 
 
 class Var:
@@ -406,6 +407,38 @@ class Executor:
         return out
 
     # ---------------------------------------------------------------------------------------------
+    _side_streams = {}
+
+    def fork_join(self, thunks):
+        """Run independent launch sequences on side streams (forked from / joined to the current stream; capturable).
+        The four per-pixel LSTMs are sequential chains of small launches (rows = 65536 .. 1024): run one after the other
+        the deep levels leave most SMs idle for 16 of the 32 steps."""
+        if not USE_LSTM_STREAMS or len(thunks) < 2:
+            return [th() for th in thunks]
+        cur = torch.cuda.current_stream()
+        key = (cur.device.index, len(thunks))
+        pool = Executor._side_streams.get(key)
+        if pool is None:
+            pool = Executor._side_streams[key] = [torch.cuda.Stream(device=cur.device) for _ in thunks]
+        results = []
+        for st_, th in zip(pool, thunks):
+            st_.wait_stream(cur)
+            with torch.cuda.stream(st_):
+                results.append(th())
+        for st_ in pool:
+            cur.wait_stream(st_)
+        return results
+
+    def lstm_levels(self, seqs, prefixes, T):
+        """lstm_last for every encoder level, concurrently; ONE tape entry runs the four backward chains concurrently."""
+        mark = len(self.tape)
+        outs = self.fork_join([(lambda sq=sq, pf=pf: self.lstm_last(sq, pf, T)) for sq, pf in zip(seqs, prefixes)])
+        if self.record:
+            bwds = self.tape[mark:]
+            del self.tape[mark:]
+            self.tape.append(lambda: self.fork_join(list(reversed(bwds))))
+        return outs
+
     def backward(self, out: Var, dout, flat_grad=None, owner=None):
         out.grad = dout
         for fn in reversed(self.tape):

@@ -121,7 +121,7 @@ class STFLSTMUNet(B200Module):
             feats.append(e)
         if pk is not None:
             feats = [self._pk_fuse(ex, f, pk, k + 1, T) for k, f in enumerate(feats)]
-        enc = [ex.lstm_last(f, f"lstm{k + 1}", T) for k, f in enumerate(feats)]
+        enc = ex.lstm_levels(feats, [f"lstm{k + 1}" for k in range(len(feats))], T)
         d = self._decoder(ex, enc[3], enc[2], "decoder4")
         d = self._decoder(ex, d, enc[1], "decoder3")
         d = self._decoder(ex, d, enc[0], "decoder2")
