@@ -219,7 +219,7 @@ __device__ __forceinline__ void epilogue_tile(const TcArgs& a, const TileCoord& 
         if (c0 + 32 >= BN) {         // last chunk is in registers: hand the accumulator buffer back to the MMA warp
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive(tempty);
+          if (lane == 0 && tempty) mbar_arrive(tempty);
         }
         float v[32];
         const int cg = t.n0 + c0;
@@ -319,7 +319,7 @@ __device__ __forceinline__ void epilogue_tile(const TcArgs& a, const TileCoord& 
       if (c0 + 32 >= BN) {
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(tempty);
+        if (lane == 0 && tempty) mbar_arrive(tempty);
       }
       if (valid && a.debug != 3) {
         float v[32];
@@ -607,13 +607,24 @@ constexpr int halo_smem_bytes() {
 __device__ __forceinline__ uint64_t make_halo_a_desc(uint32_t saddr) {
   return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)(HALO_PITCH >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
 }
+// byte offset of filter tap tp = (dh + 1) * 3 + (dw + 1) inside the halo block (taps are issued in this canonical order;
+// the host permutes the weight k-blocks to match: forward ktap = tp, dgrad ktap = 8 - tp)
+__host__ __device__ constexpr uint32_t halo_tap_off(int tp) { return (uint32_t)((tp / 3) * HALO_PITCH + (tp % 3) * 128); }
 
-template <int BN, int SA, int SB, typename TO>
+// MT = pixel tiles per weight pass: with MT = 2 every weight block that reaches shared memory feeds two 128-pixel
+// accumulators (half the L2 -> SM weight traffic per output, twice the MMAs per barrier round trip).  Tiles 2p and 2p+1
+// of the same output-channel block form a "super tile"; TMEM holds MT * BN columns per buffer, double buffered when
+// 2 * MT * BN <= 512.  SB divides 9, so the weight slot of a tap is a compile-time constant of the unrolled tap loop.
+template <int BN, int MT, int SA, int SB, typename TO>
 __global__ void __launch_bounds__(TC_THREADS, 1) conv_halo_kernel(const __grid_constant__ CUtensorMap tmA,
                                                                    const __grid_constant__ CUtensorMap tmA2,
                                                                    const __grid_constant__ CUtensorMap tmB, const TcArgs a) {
+  static_assert(9 % SB == 0, "the weight ring must divide the nine taps");
+  static_assert(SA % MT == 0, "the A ring holds whole super-tile channel blocks");
   constexpr int B_BYTES = BN * 128;
-  constexpr int TMEM_COLS = (2 * BN < 32) ? 32 : 2 * BN;
+  constexpr int NBUF = (2 * MT * BN <= 512) ? 2 : 1;
+  constexpr int TMEM_COLS = (NBUF * MT * BN < 32) ? 32 : NBUF * MT * BN;
+  constexpr int WRAPS = 9 / SB;                       // ring wraps per channel block
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const uint32_t sA = smem_u32(smem);
@@ -631,8 +642,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_halo_kernel(const __grid_c
   const int Cin = a.C1 + a.C2;
   const int cpt = Cin / 64;
   const int n_tiles = a.Cout / BN;
-  const int num_tiles = a.num_tiles;
-  const int ntaps = a.ntaps[0];
+  const int pix_tiles = a.num_tiles / n_tiles;
+  const int n_super = ((pix_tiles + MT - 1) / MT) * n_tiles;       // super tile = n-tile fastest, then pixel-tile pairs
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < SA; ++s) { mbar_init(&afull[s], 1); mbar_init(&aempty[s], 1); }
@@ -655,27 +666,37 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_halo_kernel(const __grid_c
   if (warp == 0) {
     // ================= TMA producer =================
     if (elect_one()) {
-      int sa = 0, sb = 0;
-      uint32_t pa = 0, pb = 0;
+      int sa = 0;
+      uint32_t pa = 0, nblk = 0;
       bool first = true;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const TileCoord t = decode_tile<BN>(a, tile, n_tiles, cpt);
-        const int w0 = t.wb * HALO_TW - 1, h0 = t.hb * HALO_TH - 1;
-        for (int c = 0; c < cpt; ++c) {
-          mbar_wait(&aempty[sa], pa ^ 1);
-          mbar_arrive_expect_tx(&afull[sa], HALO_TX_BYTES);
+      for (int st = blockIdx.x; st < n_super; st += gridDim.x) {
+        const int nt = st % n_tiles, pp = st / n_tiles;
+        for (int c = 0; c < cpt; ++c, ++nblk) {
           const int cc = c * 64;
-          uint8_t* dst = smem + sa * HALO_BLK_BYTES;
-          if (cc < a.C1) tma_load_4d(dst, &tmA, &afull[sa], cc, w0, h0, t.nb);
-          else tma_load_4d(dst, &tmA2, &afull[sa], cc - a.C1, w0, h0, t.nb);
-          if (++sa == SA) { sa = 0; pa ^= 1; }
-          for (int tp = 0; tp < ntaps; ++tp) {
-            if (first || !a.w_resident) {
-              mbar_wait(&bempty[sb], pb ^ 1);
-              mbar_arrive_expect_tx(&bfull[sb], B_BYTES);
-              tma_load_2d(smem + SA * HALO_BLK_BYTES + sb * B_BYTES, &tmB, &bfull[sb], (int)a.ktap[0][tp] * Cin + cc, t.n0);
+#pragma unroll
+          for (int m = 0; m < MT; ++m) {
+            const int ptile = pp * MT + m;
+            mbar_wait(&aempty[sa], pa ^ 1);
+            if (ptile < pix_tiles) {
+              const TileCoord t = decode_tile<BN>(a, ptile * n_tiles + nt, n_tiles, cpt);
+              mbar_arrive_expect_tx(&afull[sa], HALO_TX_BYTES);
+              uint8_t* dst = smem + sa * HALO_BLK_BYTES;
+              const int w0 = t.wb * HALO_TW - 1, h0 = t.hb * HALO_TH - 1;
+              if (cc < a.C1) tma_load_4d(dst, &tmA, &afull[sa], cc, w0, h0, t.nb);
+              else tma_load_4d(dst, &tmA2, &afull[sa], cc - a.C1, w0, h0, t.nb);
+            } else {
+              mbar_arrive(&afull[sa]);              // odd tail: the second accumulator is computed on stale data, never stored
             }
-            if (++sb == SB) { sb = 0; pb ^= 1; }
+            if (++sa == SA) { sa = 0; pa ^= 1; }
+          }
+          if (first || !a.w_resident) {
+#pragma unroll
+            for (int tp = 0; tp < 9; ++tp) {
+              const int sb = tp % SB;
+              mbar_wait(&bempty[sb], ((nblk * WRAPS + tp / SB) & 1) ^ 1);
+              mbar_arrive_expect_tx(&bfull[sb], B_BYTES);
+              tma_load_2d(smem + SA * HALO_BLK_BYTES + sb * B_BYTES, &tmB, &bfull[sb], (int)a.ktap[0][tp] * Cin + cc, nt * BN);
+            }
           }
         }
         first = false;
@@ -684,52 +705,65 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_halo_kernel(const __grid_c
   } else if (warp == 1) {
     // ================= MMA issuer =================
     constexpr uint32_t idesc = make_idesc_bf16(TC_BM, BN);
-    int sa = 0, sb = 0, acc = 0;
-    uint32_t pa = 0, pb = 0, acc_phase = 0;
+    int sa = 0, acc = 0;
+    uint32_t pa = 0, acc_phase = 0, nblk = 0;
     bool first = true;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+    for (int st = blockIdx.x; st < n_super; st += gridDim.x) {
       mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
       tc_fence_after();
-      const uint32_t tmem_acc = tmem_base + (uint32_t)(acc * BN);
-      for (int c = 0; c < cpt; ++c) {
-        mbar_wait(&afull[sa], pa);
+      const uint32_t tmem_acc = tmem_base + (uint32_t)(acc * MT * BN);
+      for (int c = 0; c < cpt; ++c, ++nblk) {
+        uint32_t ablk[MT];
+#pragma unroll
+        for (int m = 0; m < MT; ++m) {
+          mbar_wait(&afull[sa], pa);
+          ablk[m] = sA + sa * HALO_BLK_BYTES;
+          if (++sa == SA) { sa = 0; pa ^= 1; }
+        }
         tc_fence_after();
-        const uint32_t ablk = sA + sa * HALO_BLK_BYTES;
-        for (int tp = 0; tp < ntaps; ++tp) {
-          const bool streamed = first || !a.w_resident;
-          if (streamed) {
-            mbar_wait(&bfull[sb], pb);
-            tc_fence_after();
-          }
-          if (elect_one()) {
-            // tap (dh, dw): the patch shifted by (dh, dw) starts (dh+1) halo rows and (dw+1) pixels into the block
-            const uint32_t aoff = (uint32_t)(((int)a.dh[0][tp] + 1) * HALO_PITCH + ((int)a.dw[0][tp] + 1) * 128);
-            const uint64_t adesc = make_halo_a_desc(ablk + aoff);
+        const bool streamed = first || !a.w_resident;
+        if (elect_one()) {
+#pragma unroll
+          for (int tp = 0; tp < 9; ++tp) {
+            const int sb = tp % SB;
+            if (streamed) {
+              mbar_wait(&bfull[sb], (nblk * WRAPS + tp / SB) & 1);
+              tc_fence_after();
+            }
             const uint64_t bdesc = make_kmajor_sw128_desc(sB + sb * B_BYTES);
 #pragma unroll
-            for (int k = 0; k < 4; ++k)
-              umma_bf16(tmem_acc, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (c | tp | k) != 0);
-            if (streamed && !a.w_resident) umma_commit(&bempty[sb]);
+            for (int m = 0; m < MT; ++m) {
+              const uint64_t adesc = make_halo_a_desc(ablk[m] + halo_tap_off(tp));
+#pragma unroll
+              for (int k = 0; k < 4; ++k)
+                umma_bf16(tmem_acc + (uint32_t)(m * BN), adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc,
+                          (c | tp | k) != 0);
+            }
+            if (!a.w_resident) umma_commit(&bempty[sb]);
           }
-          __syncwarp();
-          if (++sb == SB) { sb = 0; pb ^= 1; }
-        }
-        if (elect_one()) {
-          umma_commit(&aempty[sa]);
+          // the A blocks of this channel step are free once the MMAs above have read them
+          {
+            int s2 = sa;
+#pragma unroll
+            for (int m = MT - 1; m >= 0; --m) {
+              s2 = (s2 == 0) ? SA - 1 : s2 - 1;
+              umma_commit(&aempty[s2]);
+            }
+          }
           if (c == cpt - 1) umma_commit(&tfull_bar[acc]);
         }
         __syncwarp();
-        if (++sa == SA) { sa = 0; pa ^= 1; }
       }
       first = false;
-      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      if (NBUF == 2) { if (++acc == 2) { acc = 0; acc_phase ^= 1; } }
+      else acc_phase ^= 1;
     }
   } else {
-    // ================= epilogue (same as the streaming kernel) =================
+    // ================= epilogue (same as the streaming kernel), one pixel tile of the super tile after the other ========
     const int q = warp & 3;
     const uint32_t stg = sStg + q * TC_SEG_BYTES;
-    const int m = q * 32 + lane;
-    const int tw = m % HALO_TW, th = m / HALO_TW;
+    const int m_ = q * 32 + lane;
+    const int tw = m_ % HALO_TW, th = m_ / HALO_TW;
     int cpk[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
@@ -738,24 +772,31 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_halo_kernel(const __grid_c
     }
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      const TileCoord t = decode_tile<BN>(a, tile, n_tiles, cpt);
-      const int ow = t.wb * HALO_TW + tw, oh = t.hb * HALO_TH + th, on = t.nb;
-      const bool valid = ow < a.Wout && oh < a.Hout && on < a.N;
-      int cpix[8];
-      unsigned cmask = 0;
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const int cw = t.wb * HALO_TW + (cpk[i] & 0xFF), chh = t.hb * HALO_TH + (cpk[i] >> 8);
-        const bool ok = cw < a.Wout && chh < a.Hout && on < a.N;
-        cpix[i] = ok ? (on * a.Hout + chh) * a.Wout + cw : 0;
-        cmask |= (ok ? 1u : 0u) << i;
-      }
+    for (int st = blockIdx.x; st < n_super; st += gridDim.x) {
+      const int nt = st % n_tiles, pp = st / n_tiles;
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
-      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN);
-      epilogue_tile<BN, TO>(a, t, taddr, stg, cpix, cmask, valid, on, oh, ow, &tempty_bar[acc], lane);
-      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+#pragma unroll 1
+      for (int m = 0; m < MT; ++m) {
+        const int ptile = pp * MT + m;
+        const bool live = ptile < pix_tiles;
+        const TileCoord t = decode_tile<BN>(a, (live ? ptile : pix_tiles - 1) * n_tiles + nt, n_tiles, cpt);
+        const int ow = t.wb * HALO_TW + tw, oh = t.hb * HALO_TH + th, on = t.nb;
+        const bool valid = live && ow < a.Wout && oh < a.Hout && on < a.N;
+        int cpix[8];
+        unsigned cmask = 0;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int cw = t.wb * HALO_TW + (cpk[i] & 0xFF), chh = t.hb * HALO_TH + (cpk[i] >> 8);
+          const bool ok = live && cw < a.Wout && chh < a.Hout && on < a.N;
+          cpix[i] = ok ? (on * a.Hout + chh) * a.Wout + cw : 0;
+          cmask |= (ok ? 1u : 0u) << i;
+        }
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((acc * MT + m) * BN);
+        epilogue_tile<BN, TO>(a, t, taddr, stg, cpix, cmask, valid, on, oh, ow, m == MT - 1 ? &tempty_bar[acc] : nullptr, lane);
+      }
+      if (NBUF == 2) { if (++acc == 2) { acc = 0; acc_phase ^= 1; } }
+      else acc_phase ^= 1;
     }
   }
   tc_fence_before();
@@ -855,20 +896,20 @@ static int launch_tc(const CUtensorMap& tA, const CUtensorMap& tA2, const CUtens
 }
 
 
-template <int BN, int SA, int SB, typename TO>
+template <int BN, int MT, int SA, int SB, typename TO>
 static int launch_halo(const CUtensorMap& tA, const CUtensorMap& tA2, const CUtensorMap& tB, const TcArgs& a, dim3 grid,
                        cudaStream_t st) {
   constexpr int smem = halo_smem_bytes<BN, SA, SB>();
   static_assert(smem <= 232448, "shared memory budget");
   static bool configured = false;
   if (!configured) {
-    if (cudaFuncSetAttribute(conv_halo_kernel<BN, SA, SB, TO>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) {
+    if (cudaFuncSetAttribute(conv_halo_kernel<BN, MT, SA, SB, TO>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) {
       set_error("conv2d(tcgen05 halo): cannot reserve %d bytes of shared memory: %s", smem, cudaGetErrorString(cudaGetLastError()));
       return STFB_ECUDA;
     }
     configured = true;
   }
-  conv_halo_kernel<BN, SA, SB, TO><<<grid, TC_THREADS, smem, st>>>(tA, tA2, tB, a);
+  conv_halo_kernel<BN, MT, SA, SB, TO><<<grid, TC_THREADS, smem, st>>>(tA, tA2, tB, a);
   return post_launch("conv2d(tcgen05 halo)");
 }
 
@@ -995,15 +1036,31 @@ int conv2d_tcgen05(const stfb_conv_params* p, cudaStream_t st) {
   const bool f32out = p->y_dtype == STFB_F32;
   if (halo) {
     const int cpt = (p->C1 + p->C2) / 64;
-#define HALO_LAUNCH(BN_, SA_, SB_)                                                                             \
-    return f32out ? launch_halo<BN_, SA_, SB_, float>(tA, tA2, tB, a, grid, st)                               \
-                  : launch_halo<BN_, SA_, SB_, __nv_bfloat16>(tA, tA2, tB, a, grid, st)
+    // canonical tap order tp = (dh + 1) * 3 + (dw + 1): permute the weight k-block table to match
+    {
+      signed char kt[9];
+      for (int i = 0; i < 9; ++i) kt[(a.dh[0][i] + 1) * 3 + (a.dw[0][i] + 1)] = a.ktap[0][i];
+      for (int tp = 0; tp < 9; ++tp) { a.ktap[0][tp] = kt[tp]; a.dh[0][tp] = (signed char)(tp / 3 - 1); a.dw[0][tp] = (signed char)(tp % 3 - 1); }
+    }
+    const int n_tiles_ = p->Cout / BN, pix_tiles = a.num_tiles / n_tiles_;
+    // MT = 2 halves the weight traffic per pixel but needs enough super tiles to keep the SMs busy
+    // Pairing two pixel tiles per weight pass (MT = 2) halves the weight traffic and wins on L2-warm microbenchmarks
+    // (64->64: 70 -> 52 us, 128->128: 47 -> 41 us) but loses inside the training step (13.45 vs 13.85 ms), where the tiles
+    // stream from DRAM and the longer super-tile epilogue is exposed: off unless STFB_HALO_MT=2.
+    const char* mt_env = getenv("STFB_HALO_MT");       // read per launch: tests switch it
+    const int mt_mode = mt_env ? atoi(mt_env) : 0;
+    const bool mt2 = mt_mode == 2 && ((pix_tiles + 1) / 2) * n_tiles_ >= (num_sms() * 3) / 4;
+    const int n_super = mt2 ? ((pix_tiles + 1) / 2) * n_tiles_ : a.num_tiles;
+    dim3 hgrid((unsigned)(n_super < num_sms() ? n_super : num_sms()));
+#define HALO_LAUNCH(BN_, MT_, SA_, SB_)                                                                        \
+    return f32out ? launch_halo<BN_, MT_, SA_, SB_, float>(tA, tA2, tB, a, hgrid, st)                         \
+                  : launch_halo<BN_, MT_, SA_, SB_, __nv_bfloat16>(tA, tA2, tB, a, hgrid, st)
     switch (BN) {
-      case 256: HALO_LAUNCH(256, 3, 3);
-      case 128: HALO_LAUNCH(128, 4, 6);
+      case 256: if (mt2) { HALO_LAUNCH(256, 2, 4, 3); } else { HALO_LAUNCH(256, 1, 3, 3); }
+      case 128: if (mt2) { HALO_LAUNCH(128, 2, 4, 3); } else { HALO_LAUNCH(128, 1, 4, 3); }
       case 64:
-        a.w_resident = (9 * cpt == 9 && p->Cout == 64) ? 1 : 0;     // the whole 64 x 576 matrix = the 9-slot ring
-        HALO_LAUNCH(64, 4, 9);
+        a.w_resident = (cpt == 1 && p->Cout == 64) ? 1 : 0;         // the whole 64 x 576 matrix = the 9-slot ring
+        if (mt2) { HALO_LAUNCH(64, 2, 4, 9); } else { HALO_LAUNCH(64, 1, 4, 9); }
     }
 #undef HALO_LAUNCH
   }

@@ -362,6 +362,10 @@ TC_CASES = [
     (2, 16, 16, 64, 32, 64, 3),      # mixed 64 + 32 channel concat
     (3, 20, 24, 96, 0, 160, 3),      # channel counts that are multiples of 32 but not 64; Cout = 5 x 32
     (2, 16, 16, 256, 0, 256, 3),     # halo kernel, BN=256, 4 channel blocks
+    (36, 32, 32, 128, 0, 128, 3),    # halo, two pixel tiles per weight pass (MT=2), BN=128, double-buffered TMEM
+    (112, 16, 16, 256, 0, 256, 3),   # halo MT=2 at BN=256: 512 TMEM columns, single buffered
+    (225, 16, 8, 64, 0, 64, 3),      # halo MT=2 with an odd number of pixel tiles (dead second accumulator in the tail)
+    (230, 16, 8, 128, 64, 64, 3),    # halo MT=2, dual source, streamed weights at BN=64
     (40, 32, 32, 64, 0, 128, 1),     # streaming kernel, 320 tiles: every persistent CTA walks 2-3 (staging vs barriers)
     (24, 8, 8, 256, 0, 512, 3),      # streaming 3x3 on 8x8 maps, 2 N tiles x 12 pixel tiles... and
     (160, 8, 8, 128, 0, 128, 3),     # ...80 pixel tiles x 1: with the 1x1 above, several tiles per CTA on every path
@@ -371,9 +375,13 @@ TC_CASES = [
 ]
 
 
+@pytest.mark.parametrize("halo_mt", ["0", "2"])
 @pytest.mark.parametrize("case", TC_CASES)
-def test_conv_tcgen05_matches_reference(case):
+def test_conv_tcgen05_matches_reference(case, halo_mt, monkeypatch):
     N, H, W, C1, C2, Cout, k = case
+    if halo_mt == "2" and not (k == 3 and N * H * W >= 148 * 96):
+        pytest.skip("tile pairing (STFB_HALO_MT=2) only engages on 3x3 layers with >= 111 super tiles")
+    monkeypatch.setenv("STFB_HALO_MT", halo_mt)
     dtype = torch.bfloat16
     pad = (k - 1) // 2
     x = q(rnd(N, C1 + C2, H, W, seed=1), dtype)
