@@ -22,6 +22,7 @@ USE_TCGEN05 = _os.environ.get("STFB_NO_TCGEN05", "0") != "1"
 USE_FUSED_LSTM = _os.environ.get("STFB_NO_FUSED_LSTM", "0") != "1"
 USE_FUSED_BN_STATS = _os.environ.get("STFB_NO_FUSED_BN_STATS", "0") != "1"
 USE_LSTM_STREAMS = _os.environ.get("STFB_NO_LSTM_STREAMS", "0") != "1"
+USE_WGRAD_STREAM = _os.environ.get("STFB_NO_WGRAD_STREAM", "0") != "1"
 
 
 class Var:
@@ -69,6 +70,7 @@ class Executor:
         self.acc: Dict[str, torch.Tensor] = {}
         self.grad_offsets: Dict[str, int] = {}
         self._deferred = {}           # name -> (flat offset, Cp, Cg_total, khw)
+        self._wg_keep = []            # (dy, x) pairs the side-stream wgrad launches still read
 
     # ---------------------------------------------------------------------------------------------
     def packed(self, name, k_is_dim1, n_major=False, flip=False, kpad=None, gate_c=0):
@@ -136,14 +138,42 @@ class Executor:
     def wants_grad(self, name):
         return name in self.grads
 
+    _wg_streams = {}
+
     def wgrad(self, wname, P, G, k, stride, pad, cg_off=0, cg_total=None):
         """Weight gradient of `wname`; tcgen05 launches accumulate in the side buffer and are folded in once, at the
-        end of the backward pass (Executor.backward)."""
+        end of the backward pass (Executor.backward).
+
+        Nothing downstream of a weight gradient is needed before the optimizer, so (bf16 path) every wgrad launch goes to
+        ONE side stream forked from the current one: the tensor-core bound wgrad kernels (192 threads, 130 KB of shared
+        memory per SM) then share the SMs with the memory-bound BatchNorm-backward kernels of the main chain instead of
+        alternating with them.  P and G are kept alive until the join at the end of the backward pass."""
         acc = self.acc.get(wname)
-        if ops.conv2d_wgrad(P, G, self.grads[wname], k, stride, pad, cg_off, cg_total, acc=acc):
+        side = None
+        if USE_WGRAD_STREAM and self.dtype == torch.bfloat16 and P.is_cuda:
+            cur = torch.cuda.current_stream()
+            side = Executor._wg_streams.get(cur.device.index)
+            if side is None:
+                side = Executor._wg_streams[cur.device.index] = torch.cuda.Stream(device=cur.device)
+            side.wait_stream(cur)
+            self._wg_keep.append((P, G))
+        if side is not None:
+            with torch.cuda.stream(side):
+                deferred = ops.conv2d_wgrad(P, G, self.grads[wname], k, stride, pad, cg_off, cg_total, acc=acc)
+        else:
+            deferred = ops.conv2d_wgrad(P, G, self.grads[wname], k, stride, pad, cg_off, cg_total, acc=acc)
+        if deferred:
             w = self.params[wname]
             khw = 1 if w.dim() == 2 else w.shape[2] * w.shape[3]
             self._deferred[wname] = (self.grad_offsets[wname], w.shape[0], w.shape[1], khw)
+
+    def join_wgrad(self):
+        if self._wg_keep:
+            cur = torch.cuda.current_stream()
+            side = Executor._wg_streams.get(cur.device.index)
+            if side is not None:
+                cur.wait_stream(side)
+            self._wg_keep = []
 
     # ---------------------------------------------------------------------------------------------
     def conv(self, x: Var, wname: str, *, k: int, stride: int = 1, pad: int = 0, transposed: bool = False,
@@ -443,6 +473,7 @@ class Executor:
         out.grad = dout
         for fn in reversed(self.tape):
             fn()
+        self.join_wgrad()
         if self._deferred and flat_grad is not None:
             entries = sorted(self._deferred.values())
             plan = getattr(owner, "_scatter_plan", None) if owner is not None else None
