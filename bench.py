@@ -213,11 +213,31 @@ def run_own(args, rank, world, local_rank):
     value = BATCH_PER_GPU * world / (ms_per_step / 1000.0)
 
     # ---- end to end: pinned host -> device each step, loss read back each step ----
-    def e2e_step():
-        x = x_pin.to(dev, non_blocking=True)
-        t = t_pin.to(dev, non_blocking=True)
-        return step(x, t).item()
+    # Every step copies ITS batch from pinned host memory and reads the loss back.  The copy of step i+1 is issued on a copy
+    # stream into the other half of a double buffer while step i computes (what a prefetching loader does); the loss read
+    # synchronises every step.
+    copy_stream = torch.cuda.Stream(device=dev)
+    xbuf = [torch.empty_like(x_dev), torch.empty_like(x_dev)]
+    tbuf = [torch.empty_like(t_dev), torch.empty_like(t_dev)]
+    ready = [torch.cuda.Event(), torch.cuda.Event()]
+    state = {"i": 0}
 
+    def issue_copy(slot):
+        # no wait needed: the previous user of this slot was step i-1, whose loss read already synchronised the host
+        with torch.cuda.stream(copy_stream):
+            xbuf[slot].copy_(x_pin, non_blocking=True)
+            tbuf[slot].copy_(t_pin, non_blocking=True)
+            ready[slot].record(copy_stream)
+
+    def e2e_step():
+        slot = state["i"] & 1
+        issue_copy(slot ^ 1)                                      # next step's batch, overlapped with this step's compute
+        torch.cuda.current_stream().wait_event(ready[slot])
+        loss = step(xbuf[slot], tbuf[slot])
+        state["i"] += 1
+        return loss.item()
+
+    issue_copy(0)
     e2e_step()
     e2e_ms = timed(e2e_step, args.steps) / args.steps
     e2e_val = BATCH_PER_GPU * world / (e2e_ms / 1000.0)

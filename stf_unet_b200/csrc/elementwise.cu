@@ -353,35 +353,58 @@ __global__ void __launch_bounds__(256, 4) bn_apply_kernel(const T* __restrict__ 
   }
 }
 
-__global__ void __launch_bounds__(FIN_CH * FIN_MAXG) bn_bwd_finalize_kernel(const float* __restrict__ partial, int nblk,
-                                                                            const float* __restrict__ gamma,
-                                                                            const float* __restrict__ invstd, float* dgamma,
-                                                                            float* dbeta, float* coef, int G, long long R, int C) {
-  __shared__ float sh_s[FIN_MAXG][FIN_CH], sh_q[FIN_MAXG][FIN_CH];
-  const int cl = threadIdx.x % FIN_CH, gl = threadIdx.x / FIN_CH;
+// backward finalize: up to 64 partial slots per (group, channel) -> FIN_SL threads share the slot walk
+constexpr int FIN_SL = 4;
+constexpr int FIN_BG = 8;        // groups per block pass (blockDim = FIN_CH * FIN_BG * FIN_SL = 1024)
+
+__global__ void __launch_bounds__(FIN_CH * FIN_BG * FIN_SL) bn_bwd_finalize_kernel(const float* __restrict__ partial, int nblk,
+                                                                                  const float* __restrict__ gamma,
+                                                                                  const float* __restrict__ invstd, float* dgamma,
+                                                                                  float* dbeta, float* coef, int G, long long R,
+                                                                                  int C) {
+  __shared__ float sh_s[FIN_SL][FIN_BG][FIN_CH], sh_q[FIN_SL][FIN_BG][FIN_CH];
+  const int cl = threadIdx.x % FIN_CH;
+  const int gl = (threadIdx.x / FIN_CH) % FIN_BG;
+  const int sl = threadIdx.x / (FIN_CH * FIN_BG);
   const int c = blockIdx.x * FIN_CH + cl;
-  const int gpb = blockDim.x / FIN_CH;
   double dg = 0.0, db = 0.0;
   const double n = (double)R;
-  for (int g0 = 0; g0 < G; g0 += gpb) {
+  const long long slot = 2LL * G * C;
+  for (int g0 = 0; g0 < G; g0 += FIN_BG) {
     const int g = g0 + gl;
+    float s = 0.f, q = 0.f;
     if (g < G && c < C) {
-      double s, q;
-      sum_slots(partial, nblk, G, C, g, c, s, q);
+      const float* p = partial + (long long)g * C + c;
+      float s1 = 0.f, q1 = 0.f;
+      int b = sl;
+      for (; b + FIN_SL < nblk; b += 2 * FIN_SL) {
+        s += p[(long long)b * slot]; q += p[(long long)b * slot + (long long)G * C];
+        s1 += p[(long long)(b + FIN_SL) * slot]; q1 += p[(long long)(b + FIN_SL) * slot + (long long)G * C];
+      }
+      if (b < nblk) { s += p[(long long)b * slot]; q += p[(long long)b * slot + (long long)G * C]; }
+      s += s1; q += q1;
+    }
+    sh_s[sl][gl][cl] = s;
+    sh_q[sl][gl][cl] = q;
+    __syncthreads();
+    if (sl == 0 && g < G && c < C) {
+      double ds = 0.0, dq = 0.0;
+#pragma unroll
+      for (int j = 0; j < FIN_SL; ++j) { ds += (double)sh_s[j][gl][cl]; dq += (double)sh_q[j][gl][cl]; }
       float* k = coef + ((long long)g * C + c) * 3;
       k[0] = gamma[c] * invstd[g * C + c];
-      k[1] = (float)(s / n);
-      k[2] = (float)(q / n);
-      sh_s[gl][cl] = (float)s;
-      sh_q[gl][cl] = (float)q;
+      k[1] = (float)(ds / n);
+      k[2] = (float)(dq / n);
+      sh_s[0][gl][cl] = (float)ds;
+      sh_q[0][gl][cl] = (float)dq;
     }
     __syncthreads();
-    if (gl == 0 && c < C) {
-      for (int j = 0; j < gpb && g0 + j < G; ++j) { db += (double)sh_s[j][cl]; dg += (double)sh_q[j][cl]; }
+    if (sl == 0 && gl == 0 && c < C) {
+      for (int j = 0; j < FIN_BG && g0 + j < G; ++j) { db += (double)sh_s[0][j][cl]; dg += (double)sh_q[0][j][cl]; }
     }
     __syncthreads();
   }
-  if (gl == 0 && c < C) {
+  if (sl == 0 && gl == 0 && c < C) {
     if (dgamma) dgamma[c] += (float)dg;
     if (dbeta) dbeta[c] += (float)db;
   }
@@ -673,6 +696,35 @@ __global__ void __launch_bounds__(256) maxpool_bwd_idx_kernel(const unsigned cha
     int oy_hi = (iy + pad) / stride; if (oy_hi > Ho - 1) oy_hi = Ho - 1;
     int ox_lo = ix + pad - k + 1; ox_lo = ox_lo <= 0 ? 0 : (ox_lo + stride - 1) / stride;
     int ox_hi = (ix + pad) / stride; if (ox_hi > Wo - 1) ox_hi = Wo - 1;
+    if constexpr (VEC == 8 && sizeof(T) == 2) {
+      // bf16 fast path: the 8 argmax bytes of a window are compared against this pixel's window position with two SIMD
+      // byte compares, the byte masks widened to halfword masks (PRMT) and ANDed onto the bf16x2 words of dy; the <= 4
+      // masked contributions are added in bf16x2 (the unpack / compare / convert form was instruction bound: 380 us for
+      // the stem's 268 MB map against ~60 us of HBM time)
+      uint32_t accw[4] = {0u, 0u, 0u, 0u};
+#pragma unroll
+      for (int t = 0; t < WMAX * WMAX; ++t) {
+        const int oy = oy_lo + t / WMAX, ox = ox_lo + t % WMAX;
+        const bool ok = oy <= oy_hi && ox <= ox_hi;
+        const int p = ok ? (iy - (oy * stride - pad)) * k + (ix - (ox * stride - pad)) : 255;
+        const long long oo = ok ? (((long long)n * Ho + oy) * Wo + ox) * C + cv * VEC : (long long)cv * VEC;
+        const uint2 pk = *reinterpret_cast<const uint2*>(idx + oo);
+        const uint4 dv = *reinterpret_cast<const uint4*>(dy + oo);
+        const uint32_t p4 = (uint32_t)p * 0x01010101u;
+        const uint32_t e0 = __vcmpeq4(pk.x, p4), e1 = __vcmpeq4(pk.y, p4);
+        const uint32_t m0 = __byte_perm(e0, 0, 0x1100), m1 = __byte_perm(e0, 0, 0x3322);
+        const uint32_t m2 = __byte_perm(e1, 0, 0x1100), m3 = __byte_perm(e1, 0, 0x3322);
+        const uint32_t w[4] = {dv.x & m0, dv.y & m1, dv.z & m2, dv.w & m3};
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          __nv_bfloat162 s2 = __hadd2(*reinterpret_cast<const __nv_bfloat162*>(&accw[q]), *reinterpret_cast<const __nv_bfloat162*>(&w[q]));
+          accw[q] = *reinterpret_cast<const uint32_t*>(&s2);
+        }
+      }
+      const long long io = (((long long)n * H + iy) * W + ix) * C + cv * VEC;
+      *reinterpret_cast<uint4*>(dx + io) = make_uint4(accw[0], accw[1], accw[2], accw[3]);
+      continue;
+    }
     float g[WMAX * WMAX][VEC];
     unsigned char a[WMAX * WMAX][VEC];
     int pos[WMAX * WMAX];
@@ -1066,9 +1118,8 @@ extern "C" int stfb_bn_bwd_finalize(const float* partial, int nblk, const float*
                                     float* dbeta, float* coef, int G, long long R, int C, void* stream) {
   STFB_REQUIRE(partial && nblk > 0 && gamma && invstd && coef && G > 0 && R > 0 && C > 0, "bn_bwd_finalize: bad arguments");
   STFB_DEVICE_OR_RETURN();
-  const int fin_g = G < FIN_MAXG ? G : FIN_MAXG;
-  bn_bwd_finalize_kernel<<<ceil_div(C, FIN_CH), FIN_CH * fin_g, 0, reinterpret_cast<cudaStream_t>(stream)>>>(partial, nblk, gamma, invstd, dgamma,
-                                                                                             dbeta, coef, G, R, C);
+  bn_bwd_finalize_kernel<<<ceil_div(C, FIN_CH), FIN_CH * FIN_BG * FIN_SL, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      partial, nblk, gamma, invstd, dgamma, dbeta, coef, G, R, C);
   return post_launch("bn_bwd_finalize");
 }
 

@@ -226,7 +226,11 @@ def test_maxpool(k, s, p, H, W, C, dtype):
     y2, idx = ops.maxpool_fwd_idx(xn, k, s, p)
     assert torch.equal(y2, y) and idx.dtype == torch.uint8 and int(idx.max()) < k * k
     dx2 = ops.maxpool_bwd_idx(idx, nhwc(dy, dtype), tuple(xn.shape), k, s, p)
-    assert torch.equal(dx2, dx)
+    if dtype == torch.float32:
+        assert torch.equal(dx2, dx)
+    else:   # the bf16 fast path adds the (<= 4) window contributions of a pixel in bf16x2 instead of fp32
+        assert rel(nchw(dx2), x.grad) < 1e-2 and rel(dx2, dx) < 1e-2
+        assert torch.equal(dx2 == 0, dx == 0)
 
 
 @pytest.mark.parametrize("C", [4, 16])
