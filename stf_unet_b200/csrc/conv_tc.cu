@@ -69,7 +69,7 @@ constexpr int TC_THREADS = 192;
 // the residual / previous-cell-state loads).
 constexpr int TC_SEG_BYTES = 32 * 128;
 template <int EPI>
-__host__ __device__ constexpr int tc_stg_segs() { return EPI == 1 ? 3 : 1; }
+__host__ __device__ constexpr int tc_stg_segs() { return EPI == 1 ? 5 : 1; }   // LSTM: c x2, h, acts, (bias in the 5th)
 template <int BN, int STAGES, int BK, int EPI = 0>
 constexpr int tc_smem_bytes() {
   return STAGES * (TC_BM * BK * 2 + BN * BK * 2) + 4 * tc_stg_segs<EPI>() * TC_SEG_BYTES + 256 + 1024;
@@ -121,6 +121,12 @@ __device__ __forceinline__ void tmem_ld_x16(uint32_t taddr, uint32_t* r) {
       : "memory");
 }
 __device__ __forceinline__ float fast_sigmoid(float x) { return __fdividef(1.f, 1.f + __expf(-x)); }
+// sigmoid(x) = 0.5 tanh(0.5 x) + 0.5: one MUFU instead of EX2 + RCP (tanh.approx: 2^-11 relative, below bf16 resolution)
+__device__ __forceinline__ float tanh_sigmoid(float x) {
+  float y;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(0.5f * x));
+  return fmaf(0.5f, y, 0.5f);
+}
 __device__ __forceinline__ float fast_tanh(float x) {
   float y;
   asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
@@ -494,9 +500,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
         cmask |= (ok ? 1u : 0u) << i;
       }
       if (a.debug == 3) cmask = 0;
-      mbar_wait(&tfull_bar[acc], acc_phase);
-      tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN);
+      if constexpr (EPI != 1) {
+        mbar_wait(&tfull_bar[acc], acc_phase);
+        tc_fence_after();
+      }
       if constexpr (EPI == 1) {
         // ===== fused LSTM cell.  Tile = 64 hidden units [u_base, u_base + 64); TMEM column 64*k + 16*gate + e holds
         // gate (i,f,g,o) of unit u_base + 16*k + e.  c (fp32) is staged 32 units at a time, h (bf16) once per tile, the
@@ -504,15 +512,31 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
         static_assert(EPI != 1 || BN == 256, "LSTM epilogue needs the 256-column gate tile");
         const int C = a.Chid;
         const int u_base = t.n0 / 4;
-        const uint32_t seg_c = stg, seg_h = stg + TC_SEG_BYTES, seg_a = stg + 2 * TC_SEG_BYTES;
+        const uint32_t seg_c0 = stg, seg_h = stg + 2 * TC_SEG_BYTES, seg_a = stg + 3 * TC_SEG_BYTES;
+        const uint32_t bias_s = stg + 4 * TC_SEG_BYTES;                  // 256 floats: b_ih + b_hh in accumulator column order
         const long long pitch_c = (long long)C * 4, pitch_h = (long long)C * 2, pitch_a = (long long)C * 8;
         const uint8_t* cprev_base = a.c_prev ? reinterpret_cast<const uint8_t*>(a.c_prev) + (long long)u_base * 4 : nullptr;
         uint8_t* cout_base = reinterpret_cast<uint8_t*>(a.c_out) + (long long)u_base * 4;
         uint8_t* h_base = reinterpret_cast<uint8_t*>(a.y) + (long long)u_base * 2;
         uint8_t* acts_base = a.acts ? reinterpret_cast<uint8_t*>(a.acts) + (long long)t.n0 * 2 : nullptr;
+        // both halves of c_prev and the tile's biases are requested before the first accumulator column is touched
+        if (cprev_base) {
+          seg_load(seg_c0, cprev_base, cpix, cmask, pitch_c, lane);
+          seg_load(seg_c0 + TC_SEG_BYTES, cprev_base + 128, cpix, cmask, pitch_c, lane);
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const int col = j * 32 + lane;                                  // column (k, gate, e) -> bias row gate*C + unit
+          const int uu = u_base + (col >> 6) * 16 + (col & 15), gate = (col >> 4) & 3;
+          const float b = __ldg(a.bias + gate * C + uu) + __ldg(a.bias2 + gate * C + uu);
+          asm volatile("st.shared.f32 [%0], %1;" ::"r"(bias_s + (uint32_t)col * 4), "f"(b) : "memory");
+        }
+        __syncwarp();
+        mbar_wait(&tfull_bar[acc], acc_phase);       // the loads above were in flight while the MMAs of this tile ran
+        tc_fence_after();
 #pragma unroll 1
         for (int pair = 0; pair < 2; ++pair) {
-          if (cprev_base) seg_load(seg_c, cprev_base + pair * 128, cpix, cmask, pitch_c, lane);
+          const uint32_t seg_c = seg_c0 + pair * TC_SEG_BYTES;
 #pragma unroll 1
           for (int kk = 0; kk < 2; ++kk) {
             const int k = pair * 2 + kk;
@@ -529,25 +553,22 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
               __syncwarp();
               if (lane == 0) mbar_arrive(&tempty_bar[acc]);
             }
-            const int u = u_base + k * 16;
             float hv[16], cv[16], ai[16], af[16], ag[16], ao[16];
 #pragma unroll
             for (int e = 0; e < 16; e += 4) {
               float4 cc = make_float4(0.f, 0.f, 0.f, 0.f);
               if (cprev_base) cc = lds128f(seg_c + stg_off(lane, kk * 4 + (e >> 2)));
               const float pc[4] = {cc.x, cc.y, cc.z, cc.w};
-              const int uu = u + e;
-              const float4 bi4 = ldg_add4(a.bias + uu, a.bias2 + uu), bf4 = ldg_add4(a.bias + C + uu, a.bias2 + C + uu);
-              const float4 bg4 = ldg_add4(a.bias + 2 * C + uu, a.bias2 + 2 * C + uu), bo4 = ldg_add4(a.bias + 3 * C + uu, a.bias2 + 3 * C + uu);
+              const float4 bi4 = lds128f(bias_s + (uint32_t)(k * 64 + e) * 4), bf4 = lds128f(bias_s + (uint32_t)(k * 64 + 16 + e) * 4);
+              const float4 bg4 = lds128f(bias_s + (uint32_t)(k * 64 + 32 + e) * 4), bo4 = lds128f(bias_s + (uint32_t)(k * 64 + 48 + e) * 4);
               const float pbi[4] = {bi4.x, bi4.y, bi4.z, bi4.w}, pbf[4] = {bf4.x, bf4.y, bf4.z, bf4.w};
               const float pbg[4] = {bg4.x, bg4.y, bg4.z, bg4.w}, pbo[4] = {bo4.x, bo4.y, bo4.z, bo4.w};
 #pragma unroll
               for (int z = 0; z < 4; ++z) {
-                const float bi = pbi[z], bf = pbf[z], bg = pbg[z], bo = pbo[z];
-                ai[e + z] = fast_sigmoid(__uint_as_float(ri[e + z]) + bi);
-                af[e + z] = fast_sigmoid(__uint_as_float(rf[e + z]) + bf);
-                ag[e + z] = fast_tanh(__uint_as_float(rg[e + z]) + bg);
-                ao[e + z] = fast_sigmoid(__uint_as_float(ro[e + z]) + bo);
+                ai[e + z] = tanh_sigmoid(__uint_as_float(ri[e + z]) + pbi[z]);
+                af[e + z] = tanh_sigmoid(__uint_as_float(rf[e + z]) + pbf[z]);
+                ag[e + z] = fast_tanh(__uint_as_float(rg[e + z]) + pbg[z]);
+                ao[e + z] = tanh_sigmoid(__uint_as_float(ro[e + z]) + pbo[z]);
                 cv[e + z] = af[e + z] * pc[z] + ai[e + z] * ag[e + z];
                 hv[e + z] = ao[e + z] * fast_tanh(cv[e + z]);
               }
