@@ -280,8 +280,12 @@ def run_own(args, rank, world, local_rank):
     # every rank runs the extra step (it contains the gradient all-reduce); only rank 0 records events
     prof = ops.KernelProfiler() if rank == 0 else None
     ops.set_profiler(prof)
+    from stf_unet_b200 import engine as _engine
+    _saved = (_engine.USE_WGRAD_STREAM, _engine.USE_LSTM_STREAMS)
+    _engine.USE_WGRAD_STREAM = _engine.USE_LSTM_STREAMS = False     # one stream: a kernel's event pair times that kernel alone
     eager_step(x_dev, t_dev)        # per-launch events need the eager path
     torch.cuda.synchronize()
+    _engine.USE_WGRAD_STREAM, _engine.USE_LSTM_STREAMS = _saved
     ops.set_profiler(None)
     if rank == 0:
         fam = prof.summary()
@@ -296,13 +300,22 @@ def run_own(args, rank, world, local_rank):
         membound = {k: v for k, v in fam.items() if v["flops"] == 0}
         fam = gemm
         if fam:
-            top = max(fam.items(), key=lambda kv: kv[1]["ms"])
-            name, d = top
-            ach = d["flops"] / (d["ms"] / 1e3) / 1e12
-            roof = {"bound": "tensor", "kernel": name, "achieved": round(ach, 2), "peak": pk["tflops"], "unit": "TFLOP/s",
-                    "frac": round(ach / pk["tflops"], 4), "traffic": None, "peak_source": pk["src"],
-                    "launches": d["n"], "avg_launch_us": round(1e3 * d["ms"] / d["n"], 2),
-                    "share_of_step": round(d["ms"] / ms_per_step, 3),
+            # dominant kernel = the (family, shape) group with the largest summed launch time in the step; `achieved` is
+            # its algorithmic FLOPs / its CUDA-event time, `traffic` the DRAM bytes per launch of the same shape from the
+            # committed ncu --set full capture (profiles/roofline_traffic.json), when there is one
+            groups = [g for g in prof.top(10000) if g[3] in fam]
+            t_ms, t_n, t_tf, t_family, t_tag = max(groups, key=lambda g: g[0])
+            traffic = None
+            tpath = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+            if os.path.exists(tpath):
+                traffic = json.load(open(tpath)).get(t_tag, {}).get("dram_bytes_per_launch")
+            d = fam[t_family]
+            roof = {"bound": "tensor", "kernel": f"{t_family}: {t_tag}", "achieved": round(t_tf, 2), "peak": pk["tflops"],
+                    "unit": "TFLOP/s", "frac": round(t_tf / pk["tflops"], 4), "traffic": traffic, "peak_source": pk["src"],
+                    "launches": t_n, "avg_launch_us": round(1e3 * t_ms / t_n, 2),
+                    "share_of_step": round(t_ms / ms_per_step, 3),
+                    "family_total": {"name": t_family, "ms": round(d["ms"], 3), "n": d["n"],
+                                     "tflops": round(d["flops"] / (d["ms"] / 1e3) / 1e12, 2)},
                     "families": {k: {"ms": round(v["ms"], 3), "n": v["n"],
                                      "tflops": round(v["flops"] / (v["ms"] / 1e3) / 1e12, 2) if v["ms"] > 0 else None}
                                  for k, v in fam.items()},

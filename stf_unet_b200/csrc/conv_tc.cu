@@ -280,19 +280,26 @@ __device__ __forceinline__ void epilogue_tile(const TcArgs& a, const TileCoord& 
           // channels 2l, 2l+1 of the segment and walks the warp's 32 rows in shared memory (conflict free)
           __syncwarp();
           const unsigned vmask = __ballot_sync(0xffffffffu, valid);
-          float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
-#pragma unroll 8
+          // all 32 loads first (independent), then four interleaved accumulation chains: the serial LDS -> unpack -> add
+          // form left the epilogue warps waiting on shared-memory latency (profiles/r01_ncu_halo_conv_l1_instep.txt)
+          uint32_t w[32];
+#pragma unroll
           for (int r = 0; r < 32; ++r) {
-            if ((vmask >> r) & 1u) {
-              uint32_t w;
+            w[r] = 0u;
+            if ((vmask >> r) & 1u)
               asm volatile("ld.shared.b32 %0, [%1];"
-                           : "=r"(w)
+                           : "=r"(w[r])
                            : "r"(stg + (uint32_t)(r * 128 + (((lane >> 2) ^ (r & 7)) << 4) + (lane & 3) * 4)));
-              const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w));
-              s0 += f.x; s1 += f.y;
-              q0 = fmaf(f.x, f.x, q0); q1 = fmaf(f.y, f.y, q1);
-            }
           }
+          float sa[4] = {0.f, 0.f, 0.f, 0.f}, sb[4] = {0.f, 0.f, 0.f, 0.f}, qa[4] = {0.f, 0.f, 0.f, 0.f}, qb[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+          for (int r = 0; r < 32; ++r) {
+            const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w[r]));
+            sa[r & 3] += f.x; sb[r & 3] += f.y;
+            qa[r & 3] = fmaf(f.x, f.x, qa[r & 3]); qb[r & 3] = fmaf(f.y, f.y, qb[r & 3]);
+          }
+          const float s0 = (sa[0] + sa[1]) + (sa[2] + sa[3]), s1 = (sb[0] + sb[1]) + (sb[2] + sb[3]);
+          const float q0 = (qa[0] + qa[1]) + (qa[2] + qa[3]), q1 = (qb[0] + qb[1]) + (qb[2] + qb[3]);
           const int g = (t.nb * a.TN) / a.stat_imgs;
           float* dst = a.stat_partial + ((long long)(blockIdx.x % a.stat_slots) * 2 * a.stat_groups + g) * a.Cout + t.n0 +
                        seg * SEGC + 2 * lane;
