@@ -643,8 +643,8 @@ __host__ __device__ constexpr uint32_t halo_tap_off(int tp) { return (uint32_t)(
 // accumulators (half the L2 -> SM weight traffic per output, twice the MMAs per barrier round trip).  Tiles 2p and 2p+1
 // of the same output-channel block form a "super tile"; TMEM holds MT * BN columns per buffer, double buffered when
 // 2 * MT * BN <= 512.  SB divides 9, so the weight slot of a tap is a compile-time constant of the unrolled tap loop.
-template <int BN, int MT, int SA, int SB, typename TO>
-__global__ void __launch_bounds__(TC_THREADS, 1) conv_halo_kernel(const __grid_constant__ CUtensorMap tmA,
+template <int BN, int MT, int SA, int SB, typename TO, int MINB = 1>
+__global__ void __launch_bounds__(TC_THREADS, MINB) conv_halo_kernel(const __grid_constant__ CUtensorMap tmA,
                                                                    const __grid_constant__ CUtensorMap tmA2,
                                                                    const __grid_constant__ CUtensorMap tmB, const TcArgs a) {
   static_assert(9 % SB == 0, "the weight ring must divide the nine taps");
@@ -924,20 +924,20 @@ static int launch_tc(const CUtensorMap& tA, const CUtensorMap& tA2, const CUtens
 }
 
 
-template <int BN, int MT, int SA, int SB, typename TO>
+template <int BN, int MT, int SA, int SB, typename TO, int MINB = 1>
 static int launch_halo(const CUtensorMap& tA, const CUtensorMap& tA2, const CUtensorMap& tB, const TcArgs& a, dim3 grid,
                        cudaStream_t st) {
   constexpr int smem = halo_smem_bytes<BN, SA, SB>();
   static_assert(smem <= 232448, "shared memory budget");
   static bool configured = false;
   if (!configured) {
-    if (cudaFuncSetAttribute(conv_halo_kernel<BN, MT, SA, SB, TO>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) {
+    if (cudaFuncSetAttribute(conv_halo_kernel<BN, MT, SA, SB, TO, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) {
       set_error("conv2d(tcgen05 halo): cannot reserve %d bytes of shared memory: %s", smem, cudaGetErrorString(cudaGetLastError()));
       return STFB_ECUDA;
     }
     configured = true;
   }
-  conv_halo_kernel<BN, MT, SA, SB, TO><<<grid, TC_THREADS, smem, st>>>(tA, tA2, tB, a);
+  conv_halo_kernel<BN, MT, SA, SB, TO, MINB><<<grid, TC_THREADS, smem, st>>>(tA, tA2, tB, a);
   return post_launch("conv2d(tcgen05 halo)");
 }
 
@@ -1083,13 +1083,28 @@ int conv2d_tcgen05(const stfb_conv_params* p, cudaStream_t st) {
 #define HALO_LAUNCH(BN_, MT_, SA_, SB_)                                                                        \
     return f32out ? launch_halo<BN_, MT_, SA_, SB_, float>(tA, tA2, tB, a, hgrid, st)                         \
                   : launch_halo<BN_, MT_, SA_, SB_, __nv_bfloat16>(tA, tA2, tB, a, hgrid, st)
+    // Two CTAs per SM (STFB_HALO_OCC2, default on for BN <= 128): the narrow layers are bound by the latency of their four
+    // epilogue warps, not by the tensor pipe; a second resident CTA doubles the warps that drain accumulators.  It needs
+    // <= 113 KB of shared memory and <= 168 registers per thread, so the weights stream (3-slot ring) instead of staying
+    // resident and the A ring is two blocks deep.
+    const char* occ_env = getenv("STFB_HALO_OCC2");
+    const bool occ2 = !mt2 && (occ_env ? atoi(occ_env) != 0 : true) && a.num_tiles >= 2 * num_sms();
+#define HALO_LAUNCH2(BN_, SA_, SB_)                                                                            \
+    return f32out ? launch_halo<BN_, 1, SA_, SB_, float, 2>(tA, tA2, tB, a, hgrid2, st)                       \
+                  : launch_halo<BN_, 1, SA_, SB_, __nv_bfloat16, 2>(tA, tA2, tB, a, hgrid2, st)
+    dim3 hgrid2((unsigned)(a.num_tiles < 2 * num_sms() ? a.num_tiles : 2 * num_sms()));
     switch (BN) {
       case 256: if (mt2) { HALO_LAUNCH(256, 2, 4, 3); } else { HALO_LAUNCH(256, 1, 3, 3); }
-      case 128: if (mt2) { HALO_LAUNCH(128, 2, 4, 3); } else { HALO_LAUNCH(128, 1, 4, 3); }
+      case 128:
+        if (mt2) { HALO_LAUNCH(128, 2, 4, 3); }
+        else if (occ2) { HALO_LAUNCH2(128, 2, 3); }
+        else { HALO_LAUNCH(128, 1, 4, 3); }
       case 64:
+        if (occ2) { a.w_resident = 0; HALO_LAUNCH2(64, 2, 3); }
         a.w_resident = (cpt == 1 && p->Cout == 64) ? 1 : 0;         // the whole 64 x 576 matrix = the 9-slot ring
         if (mt2) { HALO_LAUNCH(64, 2, 4, 9); } else { HALO_LAUNCH(64, 1, 4, 9); }
     }
+#undef HALO_LAUNCH2
 #undef HALO_LAUNCH
   }
 #define TC_LAUNCH(BN_, ST_, BK_)                                                                              \
