@@ -370,8 +370,8 @@ __device__ __forceinline__ void epilogue_tile(const TcArgs& a, const TileCoord& 
   }
 }
 
-template <int BN, int STAGES, typename TO, int BK, int EPI>
-__global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_constant__ CUtensorMap tmA,
+template <int BN, int STAGES, typename TO, int BK, int EPI, int MINB = 1>
+__global__ void __launch_bounds__(TC_THREADS, MINB) conv_tc_kernel(const __grid_constant__ CUtensorMap tmA,
                                                                  const __grid_constant__ CUtensorMap tmA2,
                                                                  const __grid_constant__ CUtensorMap tmB, const TcArgs a) {
   constexpr int TC_BK = BK;
@@ -906,20 +906,20 @@ bool encode_nhwc_map(EncodeTiledFn enc, CUtensorMap* tm, const void* base, int N
   return encode_nhwc_map_strided(enc, tm, base, N, H, W, C, TW, TH, TN, 1, 64);
 }
 
-template <int BN, int STAGES, typename TO, int BK, int EPI = 0>
+template <int BN, int STAGES, typename TO, int BK, int EPI = 0, int MINB = 1>
 static int launch_tc(const CUtensorMap& tA, const CUtensorMap& tA2, const CUtensorMap& tB, const TcArgs& a, dim3 grid,
                      cudaStream_t st) {
   constexpr int smem = tc_smem_bytes<BN, STAGES, BK, EPI>();
   static_assert(smem <= 232448, "shared memory budget");
   static bool configured = false;
   if (!configured) {
-    if (cudaFuncSetAttribute(conv_tc_kernel<BN, STAGES, TO, BK, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) {
+    if (cudaFuncSetAttribute(conv_tc_kernel<BN, STAGES, TO, BK, EPI, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) {
       set_error("conv2d(tcgen05): cannot reserve %d bytes of shared memory: %s", smem, cudaGetErrorString(cudaGetLastError()));
       return STFB_ECUDA;
     }
     configured = true;
   }
-  conv_tc_kernel<BN, STAGES, TO, BK, EPI><<<grid, TC_THREADS, smem, st>>>(tA, tA2, tB, a);
+  conv_tc_kernel<BN, STAGES, TO, BK, EPI, MINB><<<grid, TC_THREADS, smem, st>>>(tA, tA2, tB, a);
   return post_launch("conv2d(tcgen05)");
 }
 
@@ -1110,7 +1110,16 @@ int conv2d_tcgen05(const stfb_conv_params* p, cudaStream_t st) {
 #define TC_LAUNCH(BN_, ST_, BK_)                                                                              \
   return f32out ? launch_tc<BN_, ST_, float, BK_>(tA, tA2, tB, a, grid, st)                                 \
                 : launch_tc<BN_, ST_, __nv_bfloat16, BK_>(tA, tA2, tB, a, grid, st)
+  // two CTAs per SM for the 64-wide tiles when there is work for them (see the halo kernel): 3-stage ring.  (A 128-wide
+  // tile with three 32 KB stages + staging is 256 bytes over half an SM's shared memory.)
+  const char* occ_env2 = getenv("STFB_TC_OCC2");
+  const bool tc_occ2 = (occ_env2 ? atoi(occ_env2) != 0 : true) && a.num_tiles >= 2 * num_sms();
+  dim3 grid2((unsigned)(a.num_tiles < 2 * num_sms() ? a.num_tiles : 2 * num_sms()));
+#define TC_LAUNCH2(BN_, ST_)                                                                                  \
+  return f32out ? launch_tc<BN_, ST_, float, 64, 0, 2>(tA, tA2, tB, a, grid2, st)                            \
+                : launch_tc<BN_, ST_, __nv_bfloat16, 64, 0, 2>(tA, tA2, tB, a, grid2, st)
   if (BK == 64) {
+    if (tc_occ2 && BN == 64) { TC_LAUNCH2(64, 3); }        // 3 x 24 KB + staging = 89 KB
     switch (BN) {
       case 256: TC_LAUNCH(256, 4, 64);   // 4 x 48 KB
       case 128: TC_LAUNCH(128, 6, 64);   // 6 x 32 KB
@@ -1125,6 +1134,7 @@ int conv2d_tcgen05(const stfb_conv_params* p, cudaStream_t st) {
       case 32: TC_LAUNCH(32, 8, 32);
     }
   }
+#undef TC_LAUNCH2
 #undef TC_LAUNCH
   set_error("conv2d(tcgen05): no tile for Cout=%d", p->Cout);
   return STFB_ENOTSUP;
