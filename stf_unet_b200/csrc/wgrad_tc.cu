@@ -404,7 +404,8 @@ size_t wgrad_scratch_bytes() { return (size_t)num_sms() * 576 * 64 * sizeof(floa
 // reads (along co) and the writes (along (ci, tap), contiguous in the reference layout) are coalesced
 __global__ void __launch_bounds__(256) wgrad_scatter_kernel(const float* __restrict__ acc, float* __restrict__ dW, int Cp, int Cg,
                                                            int khw, int cg_off, int cg_total) {
-  __shared__ float tile[9][32][33];
+  __shared__ float tile[9][32 * 41 + 1];   // ci stride 41 = 9 (mod 32), tap stride 1313 = 1 (mod 32): the (ci, tap) walk of
+                                            // the write phase maps element e to bank (e + r) % 32 -- conflict free
   Cg = cg_total;   // the accumulation buffer spans the full ci axis
   (void)cg_off;
   const int ci0 = blockIdx.x * 32, co0 = blockIdx.y * 32;
@@ -412,7 +413,7 @@ __global__ void __launch_bounds__(256) wgrad_scatter_kernel(const float* __restr
   for (int tap = 0; tap < khw; ++tap)
     for (int r = ty; r < 32; r += 8) {
       const int ci = ci0 + r, co = co0 + tx;
-      tile[tap][r][tx] = (ci < Cg && co < Cp) ? acc[((long long)tap * Cg + ci) * Cp + co] : 0.f;
+      tile[tap][r * 41 + tx] = (ci < Cg && co < Cp) ? acc[((long long)tap * Cg + ci) * Cp + co] : 0.f;
     }
   __syncthreads();
   // one co row at a time: 32 ci x khw taps = a contiguous run of 32*khw floats in dW
@@ -423,7 +424,7 @@ __global__ void __launch_bounds__(256) wgrad_scatter_kernel(const float* __restr
     float* dst = dW + ((long long)co * cg_total + ci0) * khw;
     for (int e = tx; e < run; e += 32) {
       const int ci = e / khw, tap = e - ci * khw;
-      if (ci0 + ci < Cg) dst[e] += tile[tap][ci][r];
+      if (ci0 + ci < Cg) dst[e] += tile[tap][ci * 41 + r];
     }
   }
 }
@@ -561,7 +562,8 @@ size_t wgrad_tcgen05_workspace_bytes(int N, int H, int W, int Cp, int cg_total, 
 // one CTA = one 32 (ci) x 32 (co) tile of one weight, all taps, transposed through shared memory (coalesced both ways)
 __global__ void __launch_bounds__(256) wgrad_scatter_batched_kernel(const stfb_scatter_job* __restrict__ jobs, int njobs,
                                                                    const float* __restrict__ acc, float* __restrict__ grad) {
-  __shared__ float tile[9][32][33];
+  __shared__ float tile[9][32 * 41 + 1];   // ci stride 41 = 9 (mod 32), tap stride 1313 = 1 (mod 32): the (ci, tap) walk of
+                                            // the write phase maps element e to bank (e + r) % 32 -- conflict free
   __shared__ stfb_scatter_job jb;
   if (threadIdx.x == 0) {
     int lo = 0, hi = njobs - 1;
@@ -583,7 +585,7 @@ __global__ void __launch_bounds__(256) wgrad_scatter_batched_kernel(const stfb_s
   for (int tap = 0; tap < khw; ++tap)
     for (int r = ty; r < 32; r += 8) {
       const int ci = ci0 + r, co = co0 + tx;
-      tile[tap][r][tx] = (ci < Cg && co < Cp) ? a[((long long)tap * Cg + ci) * Cp + co] : 0.f;
+      tile[tap][r * 41 + tx] = (ci < Cg && co < Cp) ? a[((long long)tap * Cg + ci) * Cp + co] : 0.f;
     }
   __syncthreads();
   const int run = 32 * khw;
@@ -593,7 +595,7 @@ __global__ void __launch_bounds__(256) wgrad_scatter_batched_kernel(const stfb_s
     float* dst = g + ((long long)co * Cg + ci0) * khw;
     for (int e = tx; e < run; e += 32) {
       const int ci = e / khw, tap = e - ci * khw;
-      if (ci0 + ci < Cg) dst[e] += tile[tap][ci][r];
+      if (ci0 + ci < Cg) dst[e] += tile[tap][ci * 41 + r];
     }
   }
 }
