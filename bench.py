@@ -89,8 +89,8 @@ class ClockSampler:
 
 
 def make_batch(rank, batch=BATCH_PER_GPU, T=T_PHASES, hw=HW):
-    from oracle import weights as W
-    return W.synthetic_dce_batch(batch, T, hw, hw, seed=1234 + rank, half_res_target=True)
+    from stf_unet_b200.synthetic import synthetic_dce_batch      # product-side generator (the oracle has its own twin)
+    return synthetic_dce_batch(batch, T, hw, hw, seed=1234 + rank, half_res_target=True)
 
 
 # ------------------------------------------------------------------------------------------------

@@ -84,3 +84,17 @@ def test_criterion_rejects_unsupported_configuration():
         S.criterion({"out": torch.zeros(1, 2, 4, 4)}, torch.zeros(1, 4, 4, dtype=torch.long), ignore_index=255)
     with pytest.raises(ValueError, match="size mismatch"):
         S.ce_dice(torch.zeros(1, 2, 4, 4), torch.zeros(1, 8, 8, dtype=torch.long))
+
+
+def test_product_synthetic_generator_is_the_oracles_twin():
+    """bench.py's own arm draws batches from stf_unet_b200.synthetic (never from oracle/); same recipe, same bits."""
+    from stf_unet_b200.synthetic import synthetic_dce_batch, synthetic_dce_batch_u8
+    for args in [(3, 4, 64, 64, 1234, True), (2, 2, 32, 48, 7, False)]:
+        a, b = W.synthetic_dce_batch(*args), synthetic_dce_batch(*args)
+        assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1])
+    u8, tgt = synthetic_dce_batch_u8(2, 3, 32, 32, seed=5)
+    x, tgt2 = synthetic_dce_batch(2, 3, 32, 32, seed=5)
+    assert u8.dtype == torch.uint8 and u8.shape == (2, 3, 32, 32) and torch.equal(tgt, tgt2)
+    # the 8-bit series is the float series quantised to 1/255 before normalisation
+    back = (u8.float() / 255.0 - 0.709) / 0.127
+    assert (back - x[:, :, 0]).abs().max() <= 0.5 / 255.0 / 0.127 + 1e-5

@@ -211,7 +211,8 @@ def test_bn_fold_eval_matches_batch_norm():
 
 
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
-@pytest.mark.parametrize("k,s,p,H,W,C", [(3, 2, 1, 16, 16, 64), (3, 2, 1, 9, 13, 64), (2, 2, 0, 8, 8, 32), (2, 2, 0, 7, 9, 6)])
+@pytest.mark.parametrize("k,s,p,H,W,C", [(3, 2, 1, 16, 16, 64), (3, 2, 1, 9, 13, 64), (2, 2, 0, 8, 8, 32), (2, 2, 0, 7, 9, 6),
+                                             (3, 2, 1, 42, 38, 64), (3, 2, 1, 20, 12, 128), (2, 2, 0, 12, 20, 2056)])
 def test_maxpool(k, s, p, H, W, C, dtype):
     x = q(rnd(2, C, H, W, seed=1), dtype).requires_grad_(True)
     ref = F.max_pool2d(x, k, s, p)
@@ -230,7 +231,8 @@ def test_maxpool(k, s, p, H, W, C, dtype):
         assert torch.equal(dx2, dx)
     else:   # the bf16 fast path adds the (<= 4) window contributions of a pixel in bf16x2 instead of fp32
         assert rel(nchw(dx2), x.grad) < 1e-2 and rel(dx2, dx) < 1e-2
-        assert torch.equal(dx2 == 0, dx == 0)
+        # same routing: the zero patterns agree (up to the rare a + b == -c cancellation that only one rounding order hits)
+        assert ((dx2 == 0) != (dx == 0)).float().mean().item() < 1e-4
 
 
 @pytest.mark.parametrize("C", [4, 16])
@@ -564,7 +566,9 @@ def test_wgrad_tcgen05_conv_transpose():
     assert rel(dW, w.grad) < 1e-4
 
 
-@pytest.mark.parametrize("N,H,W,Cin,Cout,k,stride,pad", [(3, 20, 20, 1, 64, 7, 2, 3), (2, 16, 16, 8, 64, 3, 1, 1), (2, 33, 31, 1, 32, 3, 1, 1)])
+@pytest.mark.parametrize("N,H,W,Cin,Cout,k,stride,pad", [(3, 20, 20, 1, 64, 7, 2, 3), (2, 16, 16, 8, 64, 3, 1, 1), (2, 33, 31, 1, 32, 3, 1, 1),
+                                                            (2, 70, 138, 1, 64, 7, 2, 3), (2, 26, 74, 4, 64, 7, 2, 3), (1, 9, 70, 8, 64, 3, 1, 1),
+                                                            (1, 12, 12, 2, 64, 5, 1, 2)])
 def test_small_cin_conv_via_im2col(N, H, W, Cin, Cout, k, stride, pad):
     """7x7 stem / UNet first conv: im2col (K padded to 64) + 1x1 tcgen05 GEMM, and the wgrad through the same buffer."""
     dtype = torch.bfloat16

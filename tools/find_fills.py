@@ -3,14 +3,14 @@ import os, sys
 import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import stf_unet_b200 as S
-from oracle import weights as W
+from stf_unet_b200.synthetic import synthetic_dce_batch
 from stf_unet_b200.graph import GraphedStep
 from torch.profiler import profile, ProfilerActivity
 
 dev = "cuda"
 model = S.STFLSTMUNet(1, 2, 8).to(dev)
 opt = torch.optim.AdamW(model.parameters(), lr=1e-3, weight_decay=1e-4, fused=True)
-x, t = W.synthetic_dce_batch(2, 8, 64, 64, seed=1, half_res_target=True)
+x, t = synthetic_dce_batch(2, 8, 64, 64, seed=1, half_res_target=True)
 x, t = x.to(dev), t.to(dev)
 
 
