@@ -88,8 +88,9 @@ class ClockSampler:
                 "reasons": rs}
 
 
-def make_batch(rank, batch=BATCH_PER_GPU, T=T_PHASES, hw=HW):
+def make_batch(rank, batch=None, T=None, hw=None):
     from stf_unet_b200.synthetic import synthetic_dce_batch      # product-side generator (the oracle has its own twin)
+    batch, T, hw = batch or BATCH_PER_GPU, T or T_PHASES, hw or HW   # the workload's globals, read at call time
     return synthetic_dce_batch(batch, T, hw, hw, seed=1234 + rank, half_res_target=True)
 
 
@@ -116,7 +117,7 @@ def cpu_train_step_time(batch, iters, warmup, threads=None):
 def run_reference(args, rank):
     if rank != 0:
         return
-    batch = 2
+    batch = 2 if HW <= 256 else 1
     times, threads = cpu_train_step_time(batch, args.steps, args.warmup)
     ms = 1000.0 * sum(times) / len(times)
     val = batch / (ms / 1000.0)
@@ -131,11 +132,14 @@ def run_reference(args, rank):
     print(json.dumps(line), flush=True)
 
 
+CONFIG_NOTE = "BASELINE.json configs[2] = global batch 128 on 8 GPUs"
+
+
 def workload_config(n):
     return {"workload": f"STF-LSTM-UNet train fwd+CE/Dice+bwd+AdamW, T={T_PHASES} x 1x{HW}x{HW}, batch {BATCH_PER_GPU}/GPU "
-                        f"(BASELINE.json configs[2] = global batch 128 on 8 GPUs)",
+                        f"({CONFIG_NOTE})",
             "global_batch": BATCH_PER_GPU * n, "T": T_PHASES, "hw": HW, "parallelism": f"dp{n}", "launch": "CUDA graph (fwd+loss+bwd) + eager all-reduce/AdamW",
-            "l2": "per-step working set (activations ~4 GB) far exceeds the 126 MB L2; no flush needed"}
+            "l2": "per-step working set (activations of several GB) far exceeds the 126 MB L2; no flush needed"}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -326,10 +330,11 @@ def run_own(args, rank, world, local_rank):
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        times, threads = cpu_train_step_time(2, 3, 1)
-        v = 2 / (sum(times) / len(times))
+        cb, cn = (2, 3) if HW <= 256 else (1, 1)
+        times, threads = cpu_train_step_time(cb, cn, 1)
+        v = cb / (sum(times) / len(times))
         cpu = {"value": round(v, 4), "unit": "slices/s", "cores": threads, "kind": "port",
-               "sample": f"3 train steps of B=2 slices (T={T_PHASES}, {HW}x{HW}) fp32 on the oracle port, 1 warm-up"}
+               "sample": f"{cn} train step(s) of B={cb} slices (T={T_PHASES}, {HW}x{HW}) fp32 on the oracle port, 1 warm-up"}
 
     if rank == 0:
         pk = peaks()
@@ -443,6 +448,87 @@ def run_infer(args, rank, world, local_rank):
         dist.destroy_process_group()
 
 
+def run_volume(args, rank, world, local_rank):
+    """BASELINE.json configs[4]: whole-volume tumour-mask inference, one synthetic case of 160 slices x T=8 x 256x256,
+    sharded by slice across the ranks (strong scaling, no collective on the data path).  One "step" = one whole case:
+    host series in, uint8 masks out (every step is end to end by construction; `value` keeps the series resident)."""
+    import torch.distributed as dist
+    import stf_unet_b200 as S
+    from stf_unet_b200.volume import VolumePredictor, slice_range
+    from stf_unet_b200.synthetic import synthetic_dce_batch
+
+    SLICES, VB = 160, 20
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        import datetime
+        dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=180))
+    torch.manual_seed(0)
+    model = S.STFLSTMUNet(1, 2, T_PHASES).to(dev).eval()
+    lo, hi = slice_range(SLICES, rank, world)
+    # this rank's slices of the case (20 distinct synthetic slices tiled over the range: generation cost, not content, is bounded)
+    base, _ = synthetic_dce_batch(VB, T_PHASES, HW, HW, seed=1234 + rank)
+    series = base.repeat((hi - lo + VB - 1) // VB, 1, 1, 1, 1)[:hi - lo].contiguous().pin_memory()
+    pred = VolumePredictor(model, tuple(series.shape[1:]), batch=min(VB, max(1, hi - lo)))
+    masks = torch.empty((hi - lo, HW // 2, HW // 2), dtype=torch.uint8).pin_memory()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return ms.item()
+
+    for _ in range(max(args.warmup, 3)):
+        pred(series, out=masks)
+    r0 = pred.replays
+    with ClockSampler(local_rank) as clk:
+        e2e_ms = timed(lambda: pred(series, out=masks), args.steps) / args.steps
+    replays = pred.replays - r0
+    # device-resident variant: the same batches without the host copies (what `value` reports)
+    nb = (hi - lo + pred.batch - 1) // pred.batch
+
+    def resident_case():
+        for _ in range(nb):
+            pred.graph.replay()
+
+    resident_case()
+    ms = timed(resident_case, args.steps) / args.steps
+    # the same slice must give the same mask wherever it sits in the volume (slices are independent)
+    assert torch.equal(masks[:min(VB, hi - lo)], masks[VB:2 * VB][:min(VB, hi - lo)]) if hi - lo >= 2 * VB else True
+    if rank == 0:
+        pk = peaks()
+        value = SLICES / (ms / 1e3)
+        tf = value * INFER_GFLOP_PER_SLICE / 1e3
+        cfg = {"workload": f"whole-volume tumour-mask inference: {SLICES} slices x T={T_PHASES} x 1x{HW}x{HW} per synthetic case, "
+                           f"bf16, batches of {pred.batch} slices, sharded by slice over {world} GPU(s) (BASELINE.json configs[4])",
+               "slices_per_case": SLICES, "T": T_PHASES, "hw": HW, "parallelism": f"slices/{world} (no collective)",
+               "launch": "CUDA graph per batch", "l2": "activations of one batch (~2 GB) exceed the 126 MB L2; no flush needed"}
+        line = {"metric": "inference slices/s STF-LSTM-UNet (whole volume)", "value": round(value, 2), "unit": "slices/s",
+                "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": round(ms, 3),
+                "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+                "config": cfg, "clocks": clk.summary(),
+                "e2e": {"value": round(SLICES / (e2e_ms / 1e3), 2), "unit": "slices/s",
+                        "h2d_bytes_per_step": int(SLICES * T_PHASES * HW * HW * 4), "d2h_bytes_per_step": int(SLICES * (HW // 2) ** 2),
+                        "ms_per_step": round(e2e_ms, 3)},
+                "gpu_launches": int(pred.launches_per_replay * replays), "model_tflops": round(tf, 2),
+                "model_frac_of_bf16_peak": round(tf / world / pk["tflops"], 4), "roofline": None, "cpu_baseline": None}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -452,12 +538,19 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="enqueue every kernel from Python instead of replaying a CUDA graph")
     ap.add_argument("--profile-detail", action="store_true", help="print the slowest GEMM-family launches to stderr")
-    ap.add_argument("--workload", default="train", choices=["train", "infer"],
-                    help="train = BASELINE.json configs[2] sharded 16/GPU (the headline metric); infer = configs[1], eval forward")
+    ap.add_argument("--workload", default="train", choices=["train", "infer", "train512", "volume"],
+                    help="train = BASELINE.json configs[2] sharded 16/GPU (the headline metric); infer = configs[1], eval forward; "
+                         "train512 = configs[3] (T=16 x 512x512, 8 slices/GPU); volume = configs[4] (160-slice case, sharded by slice)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.workload == "train512":
+        # configs[3]: long-sequence, high-resolution stress.  8 slices per GPU: one step's activations are ~23 GB, and
+        # the per-pixel LSTMs see 4x the rows and 2x the steps of configs[2].  2 036.11 GFLOP per slice.
+        global T_PHASES, HW, BATCH_PER_GPU, TRAIN_GFLOP_PER_SLICE, CONFIG_NOTE
+        T_PHASES, HW, BATCH_PER_GPU, TRAIN_GFLOP_PER_SLICE = 16, 512, 8, 2036.11
+        CONFIG_NOTE = "BASELINE.json configs[3]: T=16 phases x 512x512, per-GPU batch chosen by memory"
     if args.impl == "reference":
         run_reference(args, rank)
         return
@@ -465,6 +558,9 @@ def main():
         raise SystemExit("bench.py: no CUDA device (the product path has no CPU fallback; use --impl reference for the CPU arm)")
     if args.workload == "infer":
         run_infer(args, rank, world, local_rank)
+        return
+    if args.workload == "volume":
+        run_volume(args, rank, world, local_rank)
         return
     run_own(args, rank, world, local_rank)
 

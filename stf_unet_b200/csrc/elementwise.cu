@@ -605,12 +605,16 @@ __host__ __device__ inline PixTile make_pix_tile(int CVn, int H, int W) {
 // vector).  Only 32-bit divisions by small numbers are left (the flat-index form decoded a 64-bit linear index with five
 // 64-bit div/mods per element: ~500 of the ~600 instructions a thread executed, 316 us for the stem's max-pool backward
 // against ~57 us of HBM time).
-__device__ __forceinline__ bool tile_slot(unsigned r, unsigned CVn, const PixTile& t, int H, int W, int& y, int& x, int& cv) {
+// A CTA walks MP_TPB consecutive tile rows (unrolled: the loads of several tiles are in flight together; one tile per CTA
+// was CTA-launch bound: 65 536 CTAs of one element per thread for the stem's map).
+constexpr int MP_TPB = 4;
+__device__ __forceinline__ bool tile_slot(unsigned r, unsigned CVn, const PixTile& t, int tile_row, int H, int W, int& y, int& x,
+                                          int& cv) {
   const unsigned p = r / CVn;
   cv = (int)(r - p * CVn);
   const unsigned ly = p / (unsigned)t.tw, lx = p - ly * (unsigned)t.tw;
   x = (int)(blockIdx.x * (unsigned)t.tw + lx);
-  y = (int)(blockIdx.y * (unsigned)t.th + ly);
+  y = (int)((unsigned)tile_row * (unsigned)t.th + ly);
   return x < W && y < H;
 }
 
@@ -626,9 +630,11 @@ __global__ void __launch_bounds__(256) maxpool_fwd_idx_kernel(const T* __restric
   const PixTile pt = make_pix_tile(CVn, Ho, Wo);
   const unsigned per_tile = (unsigned)(pt.tw * pt.th * CVn);
   for (int n = blockIdx.z; n < N; n += gridDim.z)
-  for (unsigned r_ = threadIdx.x; r_ < per_tile; r_ += blockDim.x) {
+  for (unsigned r_ = threadIdx.x; r_ < per_tile; r_ += blockDim.x)
+#pragma unroll
+  for (int tr_ = 0; tr_ < MP_TPB; ++tr_) {
     int oy, ox, cv;
-    if (!tile_slot(r_, (unsigned)CVn, pt, Ho, Wo, oy, ox, cv)) continue;
+    if (!tile_slot(r_, (unsigned)CVn, pt, blockIdx.y * MP_TPB + tr_, Ho, Wo, oy, ox, cv)) continue;
     float best[VEC];
     int arg[VEC];
 #pragma unroll
@@ -688,9 +694,11 @@ __global__ void __launch_bounds__(256) maxpool_bwd_idx_kernel(const unsigned cha
   const PixTile pt = make_pix_tile(CVn, H, W);
   const unsigned per_tile = (unsigned)(pt.tw * pt.th * CVn);
   for (int n = blockIdx.z; n < N; n += gridDim.z)
-  for (unsigned r_ = threadIdx.x; r_ < per_tile; r_ += blockDim.x) {
+  for (unsigned r_ = threadIdx.x; r_ < per_tile; r_ += blockDim.x)
+#pragma unroll
+  for (int tr_ = 0; tr_ < MP_TPB; ++tr_) {
     int iy, ix, cv;
-    if (!tile_slot(r_, (unsigned)CVn, pt, H, W, iy, ix, cv)) continue;
+    if (!tile_slot(r_, (unsigned)CVn, pt, blockIdx.y * MP_TPB + tr_, H, W, iy, ix, cv)) continue;
     float acc[VEC];
 #pragma unroll
     for (int j = 0; j < VEC; ++j) acc[j] = 0.f;
@@ -972,24 +980,29 @@ __global__ void __launch_bounds__(256) im2col_small_kernel(const __nv_bfloat16* 
   }
 }
 
-// Tiled form for the compile-time geometries: a CTA owns IM_TR output rows x IM_TP output columns of one image, stages the
-// input patch they touch ((IM_TR-1)*S + K rows x (IM_TP-1)*S + K columns x CIN channels, zero padded) in shared memory with
-// coalesced loads, and every thread then assembles 16-byte chunks of K-padded rows from shared memory.  All index
-// arithmetic is by compile-time constants; the flat form above ran 480 instructions per chunk (199 us for the stem
-// against 44 us of HBM time).
-constexpr int IM_TP = 32, IM_TR = 4;
+// Tiled form for the compile-time geometries (K padded to the next multiple of 64): a CTA of 128 threads owns IM_TR x IM_TP
+// output pixels of one image.  It stages the input patch they touch ((IM_TR-1)*S + K rows x (IM_TP-1)*S + K columns x CIN
+// channels, zero padded) in shared memory with coalesced loads; thread p then assembles pixel p's K-padded row 64 values
+// at a time -- every (ky, kx, ci) offset is a compile-time immediate -- into a padded staging tile, and the tile leaves
+// with 16-byte stores, 8 lanes per 128-byte row segment.  (The flat form above ran ~480 instructions per 16-byte chunk:
+// 199 us for the stem against 44 us of HBM time; a first tiled form with run-time chunk indices still took 160 us.)
+constexpr int IM_TP = 32, IM_TR = 4, IM_PIX = IM_TP * IM_TR;
 template <int KC, int CINC, int S>
-__global__ void __launch_bounds__(256) im2col_tiled_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ out,
-                                                           int N, int H, int W, int Ho, int Wo, int pad, int Kpad) {
+__global__ void __launch_bounds__(IM_PIX) im2col_tiled_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ out,
+                                                              int N, int H, int W, int Ho, int Wo, int pad) {
   constexpr int PW = (IM_TP - 1) * S + KC, PR = (IM_TR - 1) * S + KC, ROW = PW * CINC, KTOT = KC * KC * CINC;
-  __shared__ unsigned short patch[PR * ROW + 1];
+  constexpr int NSEG = (KTOT + 63) / 64, KPAD = NSEG * 64;
+  constexpr int SROW = 36;                                 // staging row: 32 words of payload + 4 of padding (conflict free)
+  __shared__ unsigned short patch[PR * ROW + 2];
+  __shared__ __align__(16) uint32_t stage[IM_PIX * SROW];
   const unsigned short* __restrict__ xs = reinterpret_cast<const unsigned short*>(x);
   const int ox0 = blockIdx.x * IM_TP, oy0 = blockIdx.y * IM_TR;
-  const int chunks = Kpad / 8;
+  const int tid = threadIdx.x;
+  const int lx = tid % IM_TP, ly = tid / IM_TP;
   for (int n = blockIdx.z; n < N; n += gridDim.z) {
     const int iy0 = oy0 * S - pad, ix0 = ox0 * S - pad;
     const unsigned short* __restrict__ xn = xs + (long long)n * H * W * CINC;
-    for (int e = threadIdx.x; e < PR * ROW; e += 256) {
+    for (int e = tid; e < PR * ROW; e += IM_PIX) {
       const int py = e / ROW, rem = e - py * ROW;          // rem = px * CINC + ci: contiguous in global memory
       const int px = rem / CINC;
       const int iy = iy0 + py, ix = ix0 + px;
@@ -997,27 +1010,36 @@ __global__ void __launch_bounds__(256) im2col_tiled_kernel(const __nv_bfloat16* 
       patch[e] = ok ? __ldg(xn + ((long long)iy * W + ix0) * CINC + rem) : (unsigned short)0;
     }
     __syncthreads();
-    const int slots = IM_TR * IM_TP * chunks;
-    for (int r = threadIdx.x; r < slots; r += 256) {
-      const int ch = r % chunks, pix = r / chunks;
-      const int lx = pix % IM_TP, ly = pix / IM_TP;
-      const int oy = oy0 + ly, ox = ox0 + lx;
-      if (oy >= Ho || ox >= Wo) continue;
-      const int base = (ly * S) * ROW + (lx * S) * CINC;
-      unsigned short v[8];
+    const unsigned short* __restrict__ pb = patch + (ly * S) * ROW + (lx * S) * CINC;
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const int kk = ch * 8 + j;
-        const int tap = kk / CINC, ci = kk - tap * CINC;
-        const int ky = tap / KC, kx = tap - ky * KC;
-        v[j] = kk < KTOT ? patch[base + ky * ROW + kx * CINC + ci] : (unsigned short)0;
+    for (int seg = 0; seg < NSEG; ++seg) {
+      uint32_t wv[32];
+#pragma unroll
+      for (int wd = 0; wd < 32; ++wd) {
+        uint32_t lo = 0u, hi = 0u;
+        {
+          constexpr int dummy = 0; (void)dummy;
+          const int k0 = seg * 64 + 2 * wd, k1 = k0 + 1;
+          if (k0 < KTOT) { const int tap = k0 / CINC, ci = k0 % CINC; lo = pb[(tap / KC) * ROW + (tap % KC) * CINC + ci]; }
+          if (k1 < KTOT) { const int tap = k1 / CINC, ci = k1 % CINC; hi = pb[(tap / KC) * ROW + (tap % KC) * CINC + ci]; }
+        }
+        wv[wd] = lo | (hi << 16);
       }
-      uint4 pk;
-      pk.x = v[0] | ((unsigned)v[1] << 16); pk.y = v[2] | ((unsigned)v[3] << 16);
-      pk.z = v[4] | ((unsigned)v[5] << 16); pk.w = v[6] | ((unsigned)v[7] << 16);
-      *reinterpret_cast<uint4*>(out + ((((long long)n * Ho + oy) * Wo + ox) * Kpad + ch * 8)) = pk;
+#pragma unroll
+      for (int q = 0; q < 8; ++q)
+        *reinterpret_cast<uint4*>(stage + tid * SROW + q * 4) = make_uint4(wv[4 * q], wv[4 * q + 1], wv[4 * q + 2], wv[4 * q + 3]);
+      __syncthreads();
+#pragma unroll
+      for (int it = 0; it < 8; ++it) {
+        const int q = it * IM_PIX + tid;
+        const int pix = q >> 3, c16 = q & 7;
+        const int oy = oy0 + pix / IM_TP, ox = ox0 + pix % IM_TP;
+        if (oy < Ho && ox < Wo)
+          *reinterpret_cast<uint4*>(out + ((((long long)n * Ho + oy) * Wo + ox) * KPAD + seg * 64 + c16 * 8)) =
+              *reinterpret_cast<const uint4*>(stage + pix * SROW + c16 * 4);
+      }
+      __syncthreads();
     }
-    __syncthreads();
   }
 }
 
@@ -1228,7 +1250,7 @@ extern "C" int stfb_maxpool_fwd_idx(const void* x, void* y, unsigned char* idx, 
   const PixTile ptile = make_pix_tile(C / (v ? 8 : 1), Ho, Wo);
   if (N == 0) return STFB_OK;
   STFB_REQUIRE(ptile.tiles_h <= 65535, "maxpool_fwd_idx: output too tall (%d rows)", Ho);
-  const dim3 grid((unsigned)ptile.tiles_w, (unsigned)ptile.tiles_h, (unsigned)(N < 65535 ? N : 65535));
+  const dim3 grid((unsigned)ptile.tiles_w, (unsigned)((ptile.tiles_h + MP_TPB - 1) / MP_TPB), (unsigned)(N < 65535 ? N : 65535));
 #define MP_FWD(V, KC) maxpool_fwd_idx_kernel<T, V, KC><<<grid, 256, 0, s>>>((const T*)x, (T*)y, idx, N, H, W, C, Ho, Wo, k, stride, pad)
   DISPATCH_T(dtype, {
     if (v) { if (k == 3) MP_FWD(8, 3); else if (k == 2) MP_FWD(8, 2); else MP_FWD(8, 0); }
@@ -1249,7 +1271,7 @@ extern "C" int stfb_maxpool_bwd_idx(const unsigned char* idx, const void* dy, vo
   const int wmax = (k + stride - 1) / stride;        // windows that can contain one input element, per axis
   STFB_REQUIRE(wmax <= 3, "maxpool_bwd_idx: k (%d) > 3 * stride (%d) is not supported", k, stride);
   STFB_REQUIRE(ptile.tiles_h <= 65535, "maxpool_bwd_idx: input too tall (%d rows)", H);
-  const dim3 grid((unsigned)ptile.tiles_w, (unsigned)ptile.tiles_h, (unsigned)(N < 65535 ? N : 65535));
+  const dim3 grid((unsigned)ptile.tiles_w, (unsigned)((ptile.tiles_h + MP_TPB - 1) / MP_TPB), (unsigned)(N < 65535 ? N : 65535));
 #define MP_BWD(V, WM) maxpool_bwd_idx_kernel<T, V, WM><<<grid, 256, 0, s>>>(idx, (const T*)dy, (T*)dx, N, H, W, C, Ho, Wo, k, stride, pad)
   DISPATCH_T(dtype, {
     if (v) { if (wmax == 1) MP_BWD(8, 1); else if (wmax == 2) MP_BWD(8, 2); else MP_BWD(8, 3); }
@@ -1383,9 +1405,9 @@ extern "C" int stfb_im2col_small(const void* x, void* out, int N, int H, int W, 
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   const int grid = grid_for(total);
   const dim3 tgrid((unsigned)((Wo + IM_TP - 1) / IM_TP), (unsigned)((Ho + IM_TR - 1) / IM_TR), (unsigned)(N < 65535 ? N : 65535));
-  const bool tiled_ok = tgrid.y <= 65535;
+  const bool tiled_ok = tgrid.y <= 65535 && Kpad == (k * k * Cin + 63) / 64 * 64;
 #define IM2COL_TILED(KC, CC, S_) \
-  im2col_tiled_kernel<KC, CC, S_><<<tgrid, 256, 0, s>>>((const __nv_bfloat16*)x, (__nv_bfloat16*)out, N, H, W, Ho, Wo, pad, Kpad)
+  im2col_tiled_kernel<KC, CC, S_><<<tgrid, IM_PIX, 0, s>>>((const __nv_bfloat16*)x, (__nv_bfloat16*)out, N, H, W, Ho, Wo, pad)
 #define IM2COL_LAUNCH(KC, CC)                                                                                         \
   im2col_small_kernel<KC, CC><<<grid, 256, 0, s>>>((const __nv_bfloat16*)x, (__nv_bfloat16*)out, N, H, W, Cin, Ho, Wo, k, \
                                                    stride, pad, Kpad, total)

@@ -98,3 +98,16 @@ def test_product_synthetic_generator_is_the_oracles_twin():
     # the 8-bit series is the float series quantised to 1/255 before normalisation
     back = (u8.float() / 255.0 - 0.709) / 0.127
     assert (back - x[:, :, 0]).abs().max() <= 0.5 / 255.0 / 0.127 + 1e-5
+
+
+def test_volume_slice_ranges_partition_the_case():
+    from stf_unet_b200.volume import slice_range
+    for n, world in [(160, 8), (160, 1), (11, 3), (5, 8), (0, 2)]:
+        ranges = [slice_range(n, r, world) for r in range(world)]
+        assert ranges[0][0] == 0 and ranges[-1][1] == n
+        assert all(a[1] == b[0] for a, b in zip(ranges, ranges[1:]))
+        sizes = [hi - lo for lo, hi in ranges]
+        assert max(sizes) - min(sizes) <= 1 and sizes == sorted(sizes, reverse=True)
+    assert slice_range(160, 3, 8) == (60, 80)
+    with pytest.raises(ValueError):
+        slice_range(10, 2, 2)

@@ -413,3 +413,59 @@ def test_unet_bf16_train_vs_oracle():
     r, a = rel(out, ref_logits), argmax_agree(out, ref_logits)
     print(f"unet bf16 train: rel={r:.3e} argmax={a:.5f}")
     assert r < 2e-2 and a >= 0.995
+
+
+def test_stf_long_sequence_train_fp32_vs_oracle():
+    """BASELINE.json configs[3] geometry in small (T=16 phases, non-square 128x96 slices): fp32 path against the oracle run
+    on this GPU (forward logits, loss, every gradient).  The gradient bar is relative to a float64 run of the oracle:
+    train-mode BatchNorm over two-sample batches amplifies fp32 summation-order noise (see check_grads_vs_golden), so
+    the bar is max(2e-3, 5 x the distance of the oracle's own fp32 run from its float64 run)."""
+    B, T, H, Wd = 2, 16, 128, 96
+    x, t = W.synthetic_dce_batch(B, T, H, Wd, seed=41)
+    sd = warm_stf_state()
+    sd_dev = {k: v.to(DEV) for k, v in sd.items()}
+    ref_logits, ref_loss, ref_grads, _ = O.loss_and_grads(sd_dev, x.to(DEV), t.to(DEV), model="stf", train=True)
+    sd64 = {k: (v.double() if v.is_floating_point() else v) for k, v in sd_dev.items()}
+    _, _, g64, _ = O.loss_and_grads(sd64, x.to(DEV).double(), t.to(DEV), model="stf", train=True)
+    m = load_model(S.STFLSTMUNet(1, 2, T), sd)
+    out, loss = _train_step(m, x.to(DEV), t.to(DEV))
+    assert rel(out, ref_logits) < 1e-4                       # north_star: fp32 logits rel-err <= 1e-4
+    assert abs(loss.item() - ref_loss.item()) < 1e-4
+    assert int(m.state_dict()["bn1.num_batches_tracked"]) == int(sd["bn1.num_batches_tracked"]) + T
+
+    def whole(gr):
+        num = sum((gr[n].double() - g64[n]).pow(2).sum().item() for n in g64)
+        return (num / sum(g64[n].pow(2).sum().item() for n in g64)) ** 0.5
+
+    mine, floor = whole({n: p.grad for n, p in m.named_parameters()}), whole(ref_grads)
+    print("long sequence: whole-gradient rel err vs float64 oracle: ours %.3e, fp32 oracle %.3e" % (mine, floor))
+    assert mine < max(2e-3, 5 * floor)
+
+
+def test_whole_volume_masks_match_per_batch_argmax():
+    """configs[4]: a case of 11 slices through VolumePredictor (batches of 4, ragged tail, double-buffered host copies)
+    gives the argmax masks of the model's own logits, slice by slice, and sharding by slice does not change them."""
+    from stf_unet_b200.volume import VolumePredictor, predict_volume, slice_range
+    Sn, T, HWs = 11, 3, 64
+    series, _ = W.synthetic_dce_batch(Sn, T, HWs, HWs, seed=51)
+    sd = warm_stf_state()
+    m = load_model(S.STFLSTMUNet(1, 2, T), sd).eval()
+    with torch.no_grad():
+        logits = torch.cat([m(series[i:i + 4].to(DEV))["out"] for i in range(0, Sn, 4)])      # fp32 path
+    ref = logits.argmax(1).to(torch.uint8).cpu()
+    pred = VolumePredictor(m, tuple(series.shape[1:]), batch=4, autocast_dtype=None)
+    masks = pred(series.pin_memory())
+    assert masks.dtype == torch.uint8 and masks.shape == (Sn, HWs // 2, HWs // 2)
+    assert torch.equal(masks, ref)
+    assert torch.equal(pred(series), ref)                     # second case through the same graph; pageable host memory
+    parts = []
+    for r in range(3):                                        # three "ranks" on one device: same masks, no exchange
+        (lo, hi), mk = predict_volume(m, series, batch=4, rank=r, world=3, autocast_dtype=None, predictor=pred)
+        assert (lo, hi) == slice_range(Sn, r, 3) and mk.shape[0] == hi - lo
+        parts.append(mk)
+    assert torch.equal(torch.cat(parts), ref)
+    # bf16 tensor-core path: the argmax agrees on >= 99.9 % of the pixels (north_star)
+    pred16 = VolumePredictor(m, tuple(series.shape[1:]), batch=4)
+    agree = (pred16(series) == ref).float().mean().item()
+    print("volume bf16 argmax agreement", agree)
+    assert agree >= 0.999

@@ -87,6 +87,78 @@ def main():
             ms3 = timeit(lambda: ops.bn_bwd(dy, y, x, st[2], st[3], gamma, dg, db, G, R, C, True, True), a.iters)
             print(f"bn     N{N} {H}x{W} C{C}: stats {ms * 1e3:7.1f} us ({S / ms / 1e6:7.1f} GB/s)  apply+res {ms2 * 1e3:7.1f} us "
                   f"({4 * S / ms2 / 1e6:7.1f} GB/s)  bwd(reduce+fin+apply) {ms3 * 1e3:7.1f} us ({8 * S / ms3 / 1e6:7.1f} GB/s)")
+    if a.what == "pool":
+        def gtime(fn, iters):
+            fn()
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                for _ in range(iters):
+                    fn()
+            g.replay()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            g.replay()
+            e1.record()
+            torch.cuda.synchronize()
+            return e0.elapsed_time(e1) / iters * 1e3
+        N, H, W, C = 128 * a.nmul, 128, 128, 64
+        x = torch.randn(N, H, W, C, device=DEV).to(bf)
+        y, idx = ops.maxpool_fwd_idx(x, 3, 2, 1)
+        dy = torch.randn_like(y)
+        t1 = gtime(lambda: ops.maxpool_fwd_idx(x, 3, 2, 1), a.iters)
+        t2 = gtime(lambda: ops.maxpool_bwd_idx(idx, dy, tuple(x.shape), 3, 2, 1), a.iters)
+        t3 = gtime(lambda: ops.maxpool_fwd(x, 3, 2, 1), a.iters)
+        xe, ye = x.numel() * 2 / 1e3, y.numel() * 2 / 1e3
+        print(f"pool   N{N} {H}x{W} C{C}: fwd_idx {t1:6.1f} us ({(xe + 1.5 * ye) / t1:6.0f} GB/s)  bwd_idx {t2:6.1f} us "
+              f"({(xe + 1.5 * ye) / t2:6.0f} GB/s)  fwd(eval) {t3:6.1f} us ({(xe + ye) / t3:6.0f} GB/s)")
+        img = torch.randn(N, 256, 256, 1, device=DEV).to(bf)
+        t4 = gtime(lambda: ops.im2col_small(img, 7, 2, 3, 64), a.iters)
+        print(f"im2col N{N} 256x256 k7 s2 -> [{N * 128 * 128}, 64]: {t4:6.1f} us ({(img.numel() * 2 + N * 128 * 128 * 128) / 1e3 / t4:6.0f} GB/s)")
+    if a.what == "bn2":
+        # every BatchNorm kernel of the training step on the five encoder shapes, each timed as a CUDA graph of `iters`
+        # back-to-back launches (no host launch overhead, L2 state as in a chain of kernels over the same tensors)
+        def graph_time(fn, iters):
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                fn()
+            torch.cuda.current_stream().wait_stream(side)
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                for _ in range(iters):
+                    fn()
+            g.replay()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            g.replay()
+            e1.record()
+            torch.cuda.synchronize()
+            return e0.elapsed_time(e1) / iters * 1e3      # us
+
+        for (N, H, W, C) in [(128, 128, 128, 64), (128, 64, 64, 64), (128, 32, 32, 128), (128, 16, 16, 256), (128, 8, 8, 512)]:
+            G, R = 8, (N // 8) * H * W
+            x = torch.randn(N, H, W, C, device=DEV).to(bf)
+            res = torch.randn_like(x)
+            dy = torch.randn_like(x)
+            gamma, beta = torch.ones(C, device=DEV), torch.zeros(C, device=DEV)
+            rm, rv, nbt = torch.zeros(C, device=DEV), torch.ones(C, device=DEV), torch.zeros((), device=DEV, dtype=torch.long)
+            S = x.numel() * 2 / 1e3     # KB of one tensor -> KB / us = GB/s
+            part = ops.bn_stats(x, G, R, C)
+            st = ops.bn_finalize_train(part, gamma, beta, rm, rv, nbt, G, R, C)
+            y = torch.empty_like(x)
+            dg, db = torch.zeros(C, device=DEV), torch.zeros(C, device=DEV)
+            dres = torch.zeros_like(x)
+            t_fin = graph_time(lambda: ops.bn_finalize_train(part, gamma, beta, rm, rv, nbt, G, R, C), a.iters)
+            t_app = graph_time(lambda: ops.bn_apply(x, st[0], st[1], G, R, C, True, None, out=y), a.iters)
+            t_apr = graph_time(lambda: ops.bn_apply(x, st[0], st[1], G, R, C, True, res, out=y), a.iters)
+            t_bwd = graph_time(lambda: ops.bn_bwd(dy, y, x, st[2], st[3], gamma, dg, db, G, R, C, True, False, scale=st[0], shift=st[1]), a.iters)
+            t_bwr = graph_time(lambda: ops.bn_bwd(dy, y, x, st[2], st[3], gamma, dg, db, G, R, C, True, True, dres_acc=dres), a.iters)
+            print(f"bn2    N{N} {H}x{W} C{C}: fin {t_fin:5.1f} us | apply {t_app:6.1f} us ({2 * S / t_app:6.0f} GB/s)  +res {t_apr:6.1f} us "
+                  f"({3 * S / t_apr:6.0f} GB/s) | bwd chain {t_bwd:6.1f} us ({5 * S / t_bwd:6.0f} GB/s)  +res {t_bwr:6.1f} us ({10 * S / t_bwr:6.0f} GB/s)")
 
 
 if __name__ == "__main__":
