@@ -138,7 +138,7 @@ CONFIG_NOTE = "BASELINE.json configs[2] = global batch 128 on 8 GPUs"
 def workload_config(n):
     return {"workload": f"STF-LSTM-UNet train fwd+CE/Dice+bwd+AdamW, T={T_PHASES} x 1x{HW}x{HW}, batch {BATCH_PER_GPU}/GPU "
                         f"({CONFIG_NOTE})",
-            "global_batch": BATCH_PER_GPU * n, "T": T_PHASES, "hw": HW, "parallelism": f"dp{n}", "launch": "CUDA graph (fwd+loss+bwd) + eager all-reduce/AdamW",
+            "global_batch": BATCH_PER_GPU * n, "T": T_PHASES, "hw": HW, "parallelism": f"dp{n}", "launch": "CUDA graph (fwd+loss+bwd) + eager all-reduce + one-launch flat AdamW",
             "l2": "per-step working set (activations of several GB) far exceeds the 126 MB L2; no flush needed"}
 
 
@@ -158,7 +158,8 @@ def run_own(args, rank, world, local_rank):
     torch.manual_seed(0)
     model = S.STFLSTMUNet(1, 2, T_PHASES).to(dev)
     net = parallel.DataParallel(model) if world > 1 else model
-    opt = torch.optim.AdamW(model.parameters(), lr=1e-3, weight_decay=1e-4, fused=True)
+    # one-launch AdamW over flat parameter / gradient / moment buffers (re-homes the parameters: before graph capture)
+    opt = S.FlatAdamW(model, lr=1e-3, weight_decay=1e-4)
     x_host, t_host = make_batch(rank)
     x_pin, t_pin = x_host.pin_memory(), t_host.pin_memory()
     x_dev, t_dev = x_pin.to(dev), t_pin.to(dev)
@@ -173,12 +174,14 @@ def run_own(args, rank, world, local_rank):
         opt.step()
         return loss
 
-    graphed = None
-    if not args.no_graph:
+    def make_graphed(x_example):
         from stf_unet_b200.graph import GraphedStep
-        graphed = GraphedStep(net.module if world > 1 else model, S.criterion, x_dev, t_dev)
+        g = GraphedStep(net.module if world > 1 else model, S.criterion, x_example, t_dev)
         if world > 1:
-            graphed._hook = net._on_grads
+            g._hook = net._on_grads
+        return g
+
+    graphed = None if args.no_graph else make_graphed(x_dev)
 
     def step(x, t):
         if graphed is None:
@@ -245,6 +248,40 @@ def run_own(args, rank, world, local_rank):
     e2e_step()
     e2e_ms = timed(e2e_step, args.steps) / args.steps
     e2e_val = BATCH_PER_GPU * world / (e2e_ms / 1000.0)
+
+    # ---- the same end-to-end step fed with RAW 8-bit series (what the reference's loader reads from disk): a quarter of
+    #      the host->device bytes, ToTensor + Normalize fused into the device-side layout pass ----
+    e2e_u8 = None
+    if graphed is not None:
+        from stf_unet_b200.synthetic import synthetic_dce_batch_u8
+        u8_host, _ = synthetic_dce_batch_u8(BATCH_PER_GPU, T_PHASES, HW, HW, seed=1234 + rank)
+        u8_pin = u8_host.unsqueeze(2).contiguous().pin_memory()              # [B, T, 1, H, W] uint8
+        u8buf = [u8_pin.to(dev), u8_pin.to(dev)]
+        graphed_u8 = make_graphed(u8buf[0])
+
+        def issue_copy_u8(slot):
+            with torch.cuda.stream(copy_stream):
+                u8buf[slot].copy_(u8_pin, non_blocking=True)
+                tbuf[slot].copy_(t_pin, non_blocking=True)
+                ready[slot].record(copy_stream)
+
+        def e2e_u8_step():
+            slot = state["i"] & 1
+            issue_copy_u8(slot ^ 1)
+            torch.cuda.current_stream().wait_event(ready[slot])
+            loss = graphed_u8(u8buf[slot], tbuf[slot])
+            opt.step()
+            state["i"] += 1
+            return loss.item()
+
+        torch.cuda.synchronize()
+        issue_copy_u8(state["i"] & 1)
+        e2e_u8_step()
+        u8_ms = timed(e2e_u8_step, args.steps) / args.steps
+        e2e_u8 = {"value": round(BATCH_PER_GPU * world / (u8_ms / 1000.0), 2), "unit": "slices/s",
+                  "h2d_bytes_per_step": int(u8_pin.numel() + t_pin.numel() * 8) * world, "d2h_bytes_per_step": 4 * world,
+                  "ms_per_step": round(u8_ms, 3), "input": "uint8 grey levels, normalised on the device"}
+        del graphed_u8
 
     # ---- numerics guard at the full bench size (the CPU oracle is too slow here): the bf16 tensor-core loss of this batch
     #      against the fp32 FFMA family of the same library on the same weights; a corrupted pipeline shows up here ----
@@ -345,7 +382,7 @@ def run_own(args, rank, world, local_rank):
                 "config": workload_config(world), "clocks": clk.summary(),
                 "e2e": {"value": round(e2e_val, 2), "unit": "slices/s", "h2d_bytes_per_step": int(x_pin.numel() * 4 + t_pin.numel() * 8) * world,
                         "d2h_bytes_per_step": 4 * world, "ms_per_step": round(e2e_ms, 3)},
-                "gpu_launches": int(launches),
+                "e2e_u8": e2e_u8, "gpu_launches": int(launches),
                 "model_tflops": round(model_tflops, 2), "model_frac_of_bf16_peak": round(model_tflops / world / pk["tflops"], 4),
                 "loss_check": loss_check, "roofline": roof, "cpu_baseline": cpu}
         print(json.dumps(line), flush=True)

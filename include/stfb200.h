@@ -260,6 +260,16 @@ int stfb_eval_metrics(const float* logits, const long long* target, unsigned cha
                       long long ignore_index, int use_ignore, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * Optimizer step over flat buffers (replaces torch.optim.AdamW(fused=True),
+ * /root/reference/train.py:227-237): decoupled weight decay, lerp first moment, bias-corrected step, in place on
+ * param / exp_avg / exp_avg_sq (n fp32 each).  `step` counts from 1; grad is multiplied by grad_scale first
+ * (1/world_size after a summing all-reduce, 1 otherwise).  Hyper-parameters are host doubles: 1 - beta and the bias
+ * corrections are formed in double and rounded once, as torch does.
+ * ---------------------------------------------------------------------------------------------- */
+int stfb_adamw_flat(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, long long n, double lr, double beta1,
+                    double beta2, double eps, double weight_decay, long long step, double grad_scale, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
  * Layout adapters at the API boundary (reference tensors are NCHW fp32).
  * ---------------------------------------------------------------------------------------------- */
 /* x [B, T, C, H, W] fp32  ->  y [T*B, H, W, C] dtype  (time-major image order n = t*B + b) */
@@ -268,6 +278,11 @@ int stfb_pack_series(const float* x, void* y, int B, int T, int C, int H, int W,
  * y [T*B, H, W, Cx+Cm] dtype (the torch.cat([x_t, pk_maps], 1) of every time step, time-major) */
 int stfb_pack_series_maps(const float* x, const float* maps, void* y, int B, int T, int Cx, int Cm, int H, int W, int dtype,
                           void* stream);
+/* Device-side input pipeline: 8-bit series x [B, T, H, W] -> y [T*B, H, W, 1] dtype with
+ * the loader's arithmetic fused in, ((x / 255) - mean) / std, operation for operation as ToTensor + Normalize do it
+ * (/root/reference/transforms.py, train.py:147-148: mean 0.709, std 0.127), so the fp32 result is bit-identical. */
+int stfb_pack_series_u8(const unsigned char* x, void* y, int B, int T, int H, int W, float mean, float std_, int dtype,
+                        void* stream);
 /* dst = `times` back-to-back copies of src (bytes each): a per-sample map repeated for every time step */
 int stfb_repeat(const void* src, void* dst, size_t bytes, int times, void* stream);
 /* y NHWC dtype [N,H,W,C] -> out NCHW fp32 [N,C,H,W] */

@@ -7,5 +7,6 @@ Public surface mirrors the reference's ``src`` package (/root/reference/src/__in
 from .stf_lstm_unet import STFLSTMUNet
 from .unet import UNet
 from .loss import criterion, ce_dice, dice_loss
+from .optim import FlatAdamW
 
-__all__ = ["STFLSTMUNet", "UNet", "criterion", "ce_dice", "dice_loss"]
+__all__ = ["STFLSTMUNet", "UNet", "criterion", "ce_dice", "dice_loss", "FlatAdamW"]

@@ -59,6 +59,8 @@ _SIGS = {
     "stfb_lstm_cell_bwd": [_vp] * 6 + [_ll, _i, _i, _i, _vp],
     "stfb_pack_series": [_vp, _vp] + [_i] * 6 + [_vp],
     "stfb_pack_series_maps": [_vp, _vp, _vp] + [_i] * 7 + [_vp],
+    "stfb_pack_series_u8": [_vp, _vp] + [_i] * 4 + [_f, _f, _i, _vp],
+    "stfb_adamw_flat": [_vp] * 4 + [_ll] + [C.c_double] * 5 + [_ll, C.c_double, _vp],
     "stfb_repeat": [_vp, _vp, C.c_size_t, _i, _vp],
     "stfb_nhwc_to_nchw": [_vp, _vp] + [_i] * 5 + [_vp],
     "stfb_nchw_to_nhwc": [_vp, _vp] + [_i] * 5 + [_vp],

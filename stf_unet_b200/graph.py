@@ -53,6 +53,7 @@ class GraphedStep:
         self.x.copy_(x, non_blocking=True)
         self.t.copy_(target, non_blocking=True)
         self.graph.replay()
+        self.model._last_flat_grad = self.flat_grad      # what a flat optimizer steps on (another graph / an eager step may have moved it)
         if self._hook is not None:
             self._hook(self.flat_grad)
         return self.loss

@@ -151,7 +151,7 @@ class B200Module(nn.Module):
     def _call(self, x):
         if not x.is_cuda:
             raise RuntimeError("stf_unet_b200 models run on CUDA (sm_100a) only; there is no CPU fallback")
-        x = x.contiguous().float()
+        x = x.contiguous() if x.dtype == torch.uint8 else x.contiguous().float()   # uint8: raw grey levels (STFLSTMUNet)
         trainable = [p for p in self.parameters() if p.requires_grad]
         if torch.is_grad_enabled() and self.training and trainable:
             logits = engine.ModelFunction.apply(self, x, *trainable)

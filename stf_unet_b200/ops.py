@@ -15,7 +15,7 @@ from ._lib import BF16, CONV_FWD, CONV_TRANSPOSED, F32, IMPL_AUTO, IMPL_SIMT, IM
 
 __all__ = ["dt_code", "conv2d", "conv2d_wgrad", "pack_weight", "bn_stats", "bn_finalize_train", "bn_fold_eval",
            "bn_apply", "bn_bwd", "colsum", "maxpool_fwd", "maxpool_bwd", "maxpool_fwd_idx", "maxpool_bwd_idx", "bilinear_fwd", "bilinear_bwd",
-           "tcgen05_ok", "conv_stats_fusable", "STAT_SLOTS", "im2col_small", "unpad_wgrad", "lstm_step_fused", "pack_lstm_xh", "lstm_cell_fwd", "lstm_cell_bwd", "pack_series", "pack_series_maps", "repeat_batch", "nhwc_to_nchw", "nchw_to_nhwc", "add_", "cast",
+           "tcgen05_ok", "conv_stats_fusable", "STAT_SLOTS", "im2col_small", "unpad_wgrad", "lstm_step_fused", "pack_lstm_xh", "lstm_cell_fwd", "lstm_cell_bwd", "pack_series", "pack_series_u8", "adamw_flat_", "pack_series_maps", "repeat_batch", "nhwc_to_nchw", "nchw_to_nhwc", "add_", "cast",
            "ce_dice_fwd", "ce_dice_bwd", "CONV_FWD", "CONV_TRANSPOSED", "IMPL_AUTO", "IMPL_SIMT", "IMPL_TCGEN05"]
 
 _DT = {torch.float32: F32, torch.bfloat16: BF16}
@@ -553,6 +553,35 @@ def pack_series(x, dtype):
     y = torch.empty((T * B, H, W, C_), dtype=dtype, device=x.device)
     check(_lib.load().stfb_pack_series(_p(x), _p(y), B, T, C_, H, W, dt_code(dtype), _stream()), "pack_series")
     return y
+
+
+def pack_series_u8(x, dtype, mean, std):
+    """8-bit series [B, T, H, W] (or [B, T, 1, H, W]) -> normalised [T*B, H, W, 1] `dtype`, time-major:
+    ((x / 255) - mean) / std, the loader's ToTensor + Normalize fused into the layout pass."""
+    _need_cuda(x)
+    if x.dtype != torch.uint8:
+        raise TypeError("pack_series_u8 takes uint8 grey levels")
+    if x.dim() == 5:
+        if x.shape[2] != 1:
+            raise ValueError("pack_series_u8: 8-bit input is single-channel ([B, T, 1, H, W])")
+        x = x[:, :, 0]
+    x = x.contiguous()
+    B, T, H, W = x.shape
+    y = torch.empty((T * B, H, W, 1), dtype=dtype, device=x.device)
+    check(_lib.load().stfb_pack_series_u8(_p(x), _p(y), B, T, H, W, float(mean), float(std), dt_code(dtype), _stream()),
+          "pack_series_u8")
+    return y
+
+
+def adamw_flat_(param, grad, exp_avg, exp_avg_sq, lr, beta1, beta2, eps, weight_decay, step, grad_scale=1.0):
+    """One AdamW step in place over flat fp32 buffers (ONE launch for the whole model)."""
+    _need_cuda(param, grad, exp_avg, exp_avg_sq)
+    n = param.numel()
+    for t in (param, grad, exp_avg, exp_avg_sq):
+        if t.dtype != torch.float32 or not t.is_contiguous() or t.numel() != n:
+            raise ValueError("adamw_flat_: four contiguous fp32 buffers of equal length are required")
+    check(_lib.load().stfb_adamw_flat(_p(param), _p(grad), _p(exp_avg), _p(exp_avg_sq), n, float(lr), float(beta1), float(beta2),
+                                      float(eps), float(weight_decay), int(step), float(grad_scale), _stream()), "adamw_flat")
 
 
 def pack_series_maps(x, maps, dtype):

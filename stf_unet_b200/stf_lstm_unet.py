@@ -48,6 +48,12 @@ class _DecoderBlock(nn.Module):
 
 
 class STFLSTMUNet(B200Module):
+    #: normalisation the reference's loader applies on the CPU (/root/reference/train.py:147-148); used when the series is
+    #: handed over as raw 8-bit grey levels (uint8 [B, T, 1, H, W]): the device then does ToTensor + Normalize itself,
+    #: fused into the layout pass.  Float input is taken as already normalised.
+    input_mean = 0.709
+    input_std = 0.127
+
     def __init__(self, in_channels=1, num_classes=2, time_steps=8, use_pk_maps=False, pk_channels=3):
         super().__init__()
         self.time_steps = time_steps
@@ -98,10 +104,15 @@ class STFLSTMUNet(B200Module):
             T = total - self.pk_channels
             if T < 1 or C != 1:
                 raise ValueError("use_pk_maps needs T + pk_channels steps of single-channel images")
+            if not x.is_floating_point():
+                raise TypeError("use_pk_maps: the PK maps are real-valued; pass a float tensor")
             maps = x[:, T:, 0].contiguous()                                   # [B, pk, H, W] (reference :149-153)
             series = x[:, :T].contiguous()
             pk = ops.nchw_to_nhwc(maps, ex.dtype)                             # [B, H, W, pk], resized per scale below
             xin = engine.Var(ops.pack_series_maps(series, maps, ex.dtype), needs_grad=False)   # cat([x_t, pk]) for all t
+        elif x.dtype == __import__("torch").uint8:
+            T = total
+            xin = engine.Var(ops.pack_series_u8(x, ex.dtype, self.input_mean, self.input_std), needs_grad=False)
         else:
             T = total
             xin = engine.Var(ops.pack_series(x, ex.dtype), needs_grad=False)  # [T*B, H, W, C] time-major

@@ -48,6 +48,8 @@ class UNet(B200Module):
     def _forward_impl(self, ex, x):
         if x.dim() != 4:
             raise ValueError(f"UNet expects [B, C, H, W], got {tuple(x.shape)}")
+        if not x.is_floating_point():
+            raise TypeError("UNet takes normalised float input (the 8-bit input path belongs to STFLSTMUNet)")
         if x.shape[2] % 16 or x.shape[3] % 16:
             raise ValueError("UNet needs H and W divisible by 16 (the reference's torch.cat fails otherwise)")
         xin = engine.Var(ops.nchw_to_nhwc(x, ex.dtype), needs_grad=False)

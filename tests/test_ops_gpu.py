@@ -716,3 +716,53 @@ def test_conv_fused_bn_statistics(case):
     st_f = ops.bn_finalize_train(partial, gamma, beta, None, None, None, G, R, Cout)
     st_2 = ops.bn_finalize_train(ops.bn_stats(y, G, R, Cout), gamma, beta, None, None, None, G, R, Cout)
     assert rel(st_f[0], st_2[0]) < 1e-5 and (st_f[1] - st_2[1]).abs().max().item() < 1e-4
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("B,T,H,W", [(3, 4, 32, 48), (2, 3, 9, 7), (1, 1, 16, 16)])
+def test_pack_series_u8_is_totensor_plus_normalize(B, T, H, W, dtype):
+    """8-bit series -> normalised time-major NHWC in one pass; fp32 is bit-identical to the loader's arithmetic
+    (ToTensor: x.float().div(255); Normalize: sub(mean).div(std); /root/reference/train.py:147-148)."""
+    g = torch.Generator().manual_seed(B * 100 + H)
+    u8 = torch.randint(0, 256, (B, T, H, W), generator=g, dtype=torch.uint8)
+    u8[0, 0, 0, :4] = torch.tensor([0, 1, 254, 255], dtype=torch.uint8)
+    ref = u8.float().div(255).sub(torch.tensor(0.709)).div(torch.tensor(0.127))          # [B,T,H,W] on the CPU
+    ref = ref.permute(1, 0, 2, 3).reshape(T * B, H, W, 1)
+    y = ops.pack_series_u8(u8.to(DEV), dtype, 0.709, 0.127)
+    assert y.shape == (T * B, H, W, 1) and y.dtype == dtype
+    if dtype == torch.float32:
+        assert torch.equal(y.cpu(), ref)
+    else:
+        assert torch.equal(y.cpu(), ref.to(torch.bfloat16))
+    y5 = ops.pack_series_u8(u8.to(DEV).unsqueeze(2), dtype, 0.709, 0.127)                  # [B,T,1,H,W] form
+    assert torch.equal(y5, y)
+    with pytest.raises(TypeError):
+        ops.pack_series_u8(u8.to(DEV).float(), dtype, 0.709, 0.127)
+
+
+@pytest.mark.parametrize("n", [1000003, 64, 5])
+def test_adamw_flat_matches_torch_adamw(n):
+    """stfb_adamw_flat against torch.optim.AdamW on the same flat tensor over several steps with a changing lr."""
+    torch.manual_seed(n)
+    p0 = torch.randn(n, device=DEV)
+    ref_p = p0.clone().requires_grad_(True)
+    opt = torch.optim.AdamW([ref_p], lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-2)
+    p, m, v = p0.clone(), torch.zeros(n, device=DEV), torch.zeros(n, device=DEV)
+    for step in range(1, 8):
+        lr = 1e-3 * (1.0 - step / 10.0)
+        g = torch.randn(n, device=DEV) * (0.1 if step % 2 else 3.0)
+        for grp in opt.param_groups:
+            grp["lr"] = lr
+        ref_p.grad = g.clone()
+        opt.step()
+        ops.adamw_flat_(p, g, m, v, lr, 0.9, 0.999, 1e-8, 1e-2, step)
+        assert rel(p, ref_p.detach()) < 1e-6, step
+    st = opt.state[ref_p]
+    assert rel(m, st["exp_avg"]) < 1e-6 and rel(v, st["exp_avg_sq"]) < 1e-6
+    # gradient pre-scaling (a summing all-reduce over 4 ranks): same as feeding g / 4
+    p1, m1, v1 = p0.clone(), torch.zeros(n, device=DEV), torch.zeros(n, device=DEV)
+    p2, m2, v2 = p0.clone(), torch.zeros(n, device=DEV), torch.zeros(n, device=DEV)
+    g = torch.randn(n, device=DEV)
+    ops.adamw_flat_(p1, g, m1, v1, 1e-3, 0.9, 0.999, 1e-8, 0.0, 1, grad_scale=0.25)
+    ops.adamw_flat_(p2, g * 0.25, m2, v2, 1e-3, 0.9, 0.999, 1e-8, 0.0, 1)
+    assert torch.equal(p1, p2) and torch.equal(v1, v2)
