@@ -196,6 +196,15 @@ int stfb_bn_bwd_finalize(const float* partial, int nblk, const float* gamma, con
 int stfb_bn_bwd_apply(const void* dy, const void* y, const void* x, const float* mean, const float* invstd,
                       const float* coef, const float* shift /* with y == NULL: mask = fma(x, coef0, shift) > 0 */, void* dx,
                       void* dres, int accum_dres, int G, long long R, int C, int relu, int dtype, void* stream);
+/* The same backward in ONE launch (reduce -> per-group barrier -> finalize -> apply; single-wave grid).  `scratch` holds
+ * stfb_bn_bwd_fused_scratch_floats(G, C) ZEROED floats (sums [G][2][C] + one arrival counter per group) and is left dirty.
+ * dgamma / dbeta (nullable) are accumulated into.  y may be null when relu is set and `shift` (the forward's [G][C]) is
+ * given: the mask is then recomputed from x.  dres (nullable): gradient of the residual input (= masked dy), added to its
+ * old content when accum_dres is set. */
+size_t stfb_bn_bwd_fused_scratch_floats(int G, int C);
+int stfb_bn_bwd_fused(const void* dy, const void* y, const void* x, const float* mean, const float* invstd, const float* gamma,
+                      const float* shift, float* scratch, float* dgamma, float* dbeta, void* dx, void* dres, int accum_dres,
+                      int G, long long R, int C, int relu, int dtype, void* stream);
 /* out[c] += sum_rows x[row][c]  (bias gradients: Conv2d/ConvTranspose2d bias, LSTM bias_ih/bias_hh) */
 int stfb_colsum(const void* x, float* out, long long R, int C, int dtype, void* stream);
 

@@ -25,7 +25,8 @@ class ConvParams(C.Structure):
 
 
 _vp, _i, _ll, _f = C.c_void_p, C.c_int, C.c_longlong, C.c_float
-_SIZE_T_FUNCS = {"stfb_conv2d_wgrad_workspace_bytes": [_vp, _vp] + [_i] * 14, "stfb_wgrad_scratch_bytes": []}
+_SIZE_T_FUNCS = {"stfb_conv2d_wgrad_workspace_bytes": [_vp, _vp] + [_i] * 14, "stfb_wgrad_scratch_bytes": [],
+                 "stfb_bn_bwd_fused_scratch_floats": [_i, _i]}
 _SIGS = {
     "stfb_conv2d": [C.POINTER(ConvParams), _vp],
     "stfb_conv2d_tcgen05_supported": [C.POINTER(ConvParams)],
@@ -48,6 +49,7 @@ _SIGS = {
     "stfb_bn_bwd_reduce": [_vp] * 8 + [_i, _i, _ll, _i, _i, _i, _vp],
     "stfb_bn_bwd_finalize": [_vp, _i] + [_vp] * 5 + [_i, _ll, _i, _vp],
     "stfb_bn_bwd_apply": [_vp] * 9 + [_i, _i, _ll, _i, _i, _i, _vp],
+    "stfb_bn_bwd_fused": [_vp] * 12 + [_i, _i, _ll, _i, _i, _i, _vp],
     "stfb_colsum": [_vp, _vp, _ll, _i, _i, _vp],
     "stfb_maxpool_fwd": [_vp, _vp] + [_i] * 10 + [_vp],
     "stfb_maxpool_bwd": [_vp, _vp, _vp] + [_i] * 10 + [_vp],

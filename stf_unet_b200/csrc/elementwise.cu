@@ -484,6 +484,195 @@ __global__ void __launch_bounds__(256, 4) bn_bwd_apply_kernel(const T* __restric
   }
 }
 
+// -------------------------------------------------------------------------------------------------
+// BatchNorm backward in ONE launch: reduce -> per-group barrier -> finalize -> apply.
+//
+// The three-launch chain (colreduce<1> -> bn_bwd_finalize -> bn_bwd_apply) costs two extra kernel boundaries and a
+// latency-bound finalize per layer: measured 29-36 us for the layer-3/4 maps whose HBM time is 7-10 us
+// (tools/kernel_probe.py bn2), 44 times per step.  Here a single-wave grid (every CTA co-resident) does
+//   phase 1: each CTA reduces (sum dz, sum dz*xhat) over ITS rows of its group and adds them into acc[g][2][C]
+//            (fp32 red.add into a zeroed buffer), then arrives at the group's counter;
+//   barrier: spins until all CTAs of the group arrived (the group's sums are complete);
+//   phase 2: every thread forms the coefficients of its own channels from acc (what the finalize kernel did) and
+//            applies dx = k0*dz + cb*x + cc over the SAME rows -- for the deep layers these are L2 hits.
+// CTA 0 of each group adds the group's sums into dgamma / dbeta.  The spin is safe because the grid never exceeds the
+// co-resident capacity the occupancy API reports; CTAs delayed by unrelated kernels on other streams only make the
+// others wait.  Two such kernels spinning on the same device at the same time (two models trained concurrently on two
+// streams of one process) could starve each other: STFB_NO_FUSED_BN_BWD=1 restores the three-launch chain.
+// -------------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+
+// LEAN: no y and no dres are touched (mask recomputed from x) -> two tensors per pass, so four rows per trip stay in flight
+template <typename T, int VEC, bool LEAN>
+__global__ void __launch_bounds__(256, 2) bn_bwd_fused_kernel(const T* __restrict__ dy, const T* __restrict__ y,
+                                                              const T* __restrict__ x, const float* __restrict__ mean,
+                                                              const float* __restrict__ invstd, const float* __restrict__ gamma,
+                                                              const float* __restrict__ shift, float* acc, unsigned* counters,
+                                                              float* dgamma, float* dbeta, T* dx, T* dres, long long R, int C,
+                                                              long long rows_per_block, int tpr, int relu, int accum_dres) {
+  __shared__ float red[256 * VEC * 2];
+  const int tid = threadIdx.x;
+  const int lanes = 256 / tpr;
+  const int cl = tid % tpr, rl = tid / tpr;
+  const int g = blockIdx.y, G = gridDim.y;
+  const int CVn = C / VEC;
+  const long long r0 = (long long)blockIdx.x * rows_per_block;
+  const long long r1 = min(R, r0 + rows_per_block);
+  const long long gbase = (long long)g * R;
+  const bool mask_from_x = relu && y == nullptr;
+  float* accs = acc + (long long)g * 2 * C;          // [2][C] of this group
+  (void)G;
+
+  // ---------------- phase 1: partial sums over this CTA's rows ----------------
+  for (int cv0 = 0; cv0 < CVn; cv0 += tpr) {
+    const int cv = cv0 + cl;
+    float s[VEC], q[VEC];
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) s[j] = q[j] = 0.f;
+    if (cv < CVn) {
+      const int c = cv * VEC;
+      float mu[VEC], is[VEC], sc[VEC], sh[VEC];
+#pragma unroll
+      for (int j = 0; j < VEC; ++j) {
+        const int gc = g * C + c + j;
+        mu[j] = mean[gc];
+        is[j] = invstd[gc];
+        sc[j] = mask_from_x ? gamma[c + j] * is[j] : 0.f;     // the forward's scale = gamma * invstd
+        sh[j] = mask_from_x ? shift[gc] : 0.f;
+      }
+      constexpr int U = LEAN ? 4 : 2;
+      long long r = r0 + rl;
+      for (; r + (long long)(U - 1) * lanes < r1; r += (long long)U * lanes) {
+        float va[U][VEC], vb[U][VEC], vc[U][VEC];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const long long off = (gbase + r + (long long)u * lanes) * C + c;
+          ldv<VEC>(dy + off, va[u]);
+          ldv<VEC>(x + off, vc[u]);
+          if (!LEAN && relu && !mask_from_x) ldv<VEC>(y + off, vb[u]);
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+#pragma unroll
+          for (int j = 0; j < VEC; ++j) {
+            const float yy = mask_from_x ? fmaf(vc[u][j], sc[j], sh[j]) : ((!LEAN && relu) ? vb[u][j] : 1.f);
+            const float dz = (relu && !(yy > 0.f)) ? 0.f : va[u][j];
+            s[j] += dz;
+            q[j] = fmaf(dz, (vc[u][j] - mu[j]) * is[j], q[j]);
+          }
+      }
+      for (; r < r1; r += lanes) {
+        const long long off = (gbase + r) * C + c;
+        float va[VEC], vb[VEC], vc[VEC];
+        ldv<VEC>(dy + off, va);
+        ldv<VEC>(x + off, vc);
+        if (!LEAN && relu && !mask_from_x) ldv<VEC>(y + off, vb);
+#pragma unroll
+        for (int j = 0; j < VEC; ++j) {
+          const float yy = mask_from_x ? fmaf(vc[j], sc[j], sh[j]) : ((!LEAN && relu) ? vb[j] : 1.f);
+          const float dz = (relu && !(yy > 0.f)) ? 0.f : va[j];
+          s[j] += dz;
+          q[j] = fmaf(dz, (vc[j] - mu[j]) * is[j], q[j]);
+        }
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) {
+      red[(tid * VEC + j) * 2] = s[j];
+      red[(tid * VEC + j) * 2 + 1] = q[j];
+    }
+    __syncthreads();
+    for (int t = tid; t < tpr * VEC; t += 256) {
+      const int ccl = t / VEC, j = t - ccl * VEC;
+      if (cv0 + ccl < CVn) {
+        float ds = 0.f, dq = 0.f;
+        for (int l = 0; l < lanes; ++l) {
+          ds += red[((l * tpr + ccl) * VEC + j) * 2];
+          dq += red[((l * tpr + ccl) * VEC + j) * 2 + 1];
+        }
+        const int c = (cv0 + ccl) * VEC + j;
+        atomicAdd(accs + c, ds);
+        atomicAdd(accs + C + c, dq);
+      }
+    }
+    __syncthreads();
+  }
+
+  // ---------------- barrier over the CTAs of this group ----------------
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) {
+    atomicAdd(counters + g, 1u);
+    while (ld_acquire_u32(counters + g) < gridDim.x) __nanosleep(40);
+  }
+  __syncthreads();
+
+  // ---------------- phase 2: coefficients of my channels, then the apply pass over the same rows ----------------
+  const float inv_n = 1.f / (float)R;
+  if (blockIdx.x == 0) {
+    for (int c = tid; c < C; c += 256) {
+      const float sg = __ldcg(accs + c), qg = __ldcg(accs + C + c);
+      if (dbeta) atomicAdd(dbeta + c, sg);
+      if (dgamma) atomicAdd(dgamma + c, qg);
+    }
+  }
+  for (int cv = cl; cv < CVn; cv += tpr) {
+    const int c = cv * VEC;
+    float k0[VEC], cb[VEC], cc[VEC], sh[VEC];
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) {
+      const int gc = g * C + c + j;
+      const float mu = mean[gc], is = invstd[gc];
+      const float a0 = gamma[c + j] * is, a1 = __ldcg(accs + c + j) * inv_n, a2 = __ldcg(accs + C + c + j) * inv_n;
+      k0[j] = a0;
+      cb[j] = -a0 * a2 * is;
+      cc[j] = a0 * (mu * is * a2 - a1);
+      sh[j] = mask_from_x ? shift[gc] : 0.f;
+    }
+    constexpr int U = LEAN ? 4 : 2;
+    for (long long r = r0 + rl; r < r1; r += (long long)U * lanes) {
+      float d[U][VEC], xv[U][VEC], yv[U][VEC], old[U][VEC];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const long long rr = r + (long long)u * lanes;
+        if (rr < r1) {
+          const long long off = (gbase + rr) * C + c;
+          ldv<VEC>(dy + off, d[u]);
+          ldv<VEC>(x + off, xv[u]);
+          if (!LEAN && relu && !mask_from_x) ldv<VEC>(y + off, yv[u]);
+          if (!LEAN && dres && accum_dres) ldv<VEC>(dres + off, old[u]);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const long long rr = r + (long long)u * lanes;
+        if (rr < r1) {
+          const long long off = (gbase + rr) * C + c;
+#pragma unroll
+          for (int j = 0; j < VEC; ++j) {
+            const float yy = mask_from_x ? fmaf(xv[u][j], k0[j], sh[j]) : ((!LEAN && relu) ? yv[u][j] : 1.f);
+            const float dz = (relu && !(yy > 0.f)) ? 0.f : d[u][j];
+            d[u][j] = dz;
+            xv[u][j] = fmaf(k0[j], dz, fmaf(cb[j], xv[u][j], cc[j]));
+          }
+          stv<VEC>(dx + off, xv[u]);
+          if (!LEAN && dres) {
+            if (accum_dres) {
+#pragma unroll
+              for (int j = 0; j < VEC; ++j) d[u][j] += old[u][j];
+            }
+            stv<VEC>(dres + off, d[u]);
+          }
+        }
+      }
+    }
+  }
+}
+
 // =================================================================================================
 // max-pool
 // =================================================================================================
@@ -1221,6 +1410,62 @@ extern "C" int stfb_colsum(const void* x, float* out, long long R, int C, int dt
   ColRedArgs A{};
   A.a = x; A.outf = out; A.G = 1; A.R = R; A.C = C;
   return launch_colreduce<2>(A, dtype, pick_vec(C, dtype, {x}), reinterpret_cast<cudaStream_t>(stream), "colsum");
+}
+
+// co-resident capacity of the fused kernel (CTAs per SM from the occupancy API, capped at the 2 its register budget is
+// sized for), per instantiation
+template <typename T, int VEC>
+static int bn_bwd_fused_capacity() {
+  static int cap = 0;
+  if (cap == 0) {
+    int per_sm = 0, per_sm_lean = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_lean, bn_bwd_fused_kernel<T, VEC, true>, 256, 0) != cudaSuccess) per_sm_lean = 1;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, bn_bwd_fused_kernel<T, VEC, false>, 256, 0) != cudaSuccess || per_sm < 1) per_sm = 1;
+    if (per_sm_lean < per_sm) per_sm = per_sm_lean;
+    if (per_sm > 2) per_sm = 2;
+    cap = per_sm * num_sms();
+  }
+  return cap;
+}
+
+extern "C" size_t stfb_bn_bwd_fused_scratch_floats(int G, int C) {
+  return (size_t)2 * G * C + (size_t)((G + 15) / 16 * 16);      // acc[G][2][C] + one arrival counter per group
+}
+
+extern "C" int stfb_bn_bwd_fused(const void* dy, const void* y, const void* x, const float* mean, const float* invstd,
+                                 const float* gamma, const float* shift, float* scratch, float* dgamma, float* dbeta, void* dx,
+                                 void* dres, int accum_dres, int G, long long R, int C, int relu, int dtype, void* stream) {
+  STFB_REQUIRE(dy && x && mean && invstd && gamma && scratch && dx && G > 0 && G <= 65535 && R >= 0 && C > 0 && DT_OK(dtype),
+               "bn_bwd_fused: bad arguments");
+  STFB_REQUIRE(!relu || y || shift, "bn_bwd_fused: relu needs y, or shift to recompute the mask from x");
+  STFB_DEVICE_OR_RETURN();
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  if ((long long)G * R == 0) return STFB_OK;
+  const int v = pick_vec(C, dtype, {dy, y, x, dx, dres});
+  int cap = 0;
+  DISPATCH_T(dtype, { cap = v == 8 ? bn_bwd_fused_capacity<T, 8>() : (v == 4 ? bn_bwd_fused_capacity<T, 4>() : bn_bwd_fused_capacity<T, 1>()); });
+  STFB_REQUIRE(G <= cap, "bn_bwd_fused: %d groups exceed the co-resident capacity (%d CTAs); use the three-launch chain", G, cap);
+  const int CVn = C / v;
+  int tpr = 1;
+  while (tpr * 2 <= CVn && tpr * 2 <= 256) tpr *= 2;
+  const long long lanes = 256 / tpr;
+  long long nblk = cap / G;                                   // single wave: G * nblk <= capacity
+  const long long by_rows = (R + lanes * 4 - 1) / (lanes * 4); // at least four row passes per CTA
+  if (nblk > by_rows) nblk = by_rows;
+  if (nblk < 1) nblk = 1;
+  const long long rpb = (R + nblk - 1) / nblk;
+  nblk = (R + rpb - 1) / rpb;
+  float* acc = scratch;
+  unsigned* counters = reinterpret_cast<unsigned*>(scratch + (size_t)2 * G * C);
+  dim3 grid((unsigned)nblk, (unsigned)G);
+  const bool lean = !dres && (!relu || !y);                   // nothing but dy and x is read
+#define BN_FUSED(V, L) bn_bwd_fused_kernel<T, V, L><<<grid, 256, 0, s>>>((const T*)dy, (const T*)y, (const T*)x, mean, invstd, gamma, shift, acc, counters, dgamma, dbeta, (T*)dx, (T*)dres, R, C, rpb, tpr, relu, accum_dres)
+  DISPATCH_T(dtype, {
+    if (lean) { if (v == 8) BN_FUSED(8, true); else if (v == 4) BN_FUSED(4, true); else BN_FUSED(1, true); }
+    else { if (v == 8) BN_FUSED(8, false); else if (v == 4) BN_FUSED(4, false); else BN_FUSED(1, false); }
+  });
+#undef BN_FUSED
+  return post_launch("bn_bwd_fused");
 }
 
 extern "C" int stfb_maxpool_fwd(const void* x, void* y, int N, int H, int W, int C, int Ho, int Wo, int k, int stride, int pad,

@@ -135,6 +135,18 @@ class Executor:
         self._stat_off += (n + 63) // 64 * 64
         return buf
 
+    def zeroed_scratch(self, n, device):
+        """n zeroed fp32 from the per-forward arena (the one-launch BatchNorm backward's group sums + counters)."""
+        arena = getattr(self, "_stat_arena", None)
+        if arena is None or self._stat_off + n > arena.numel():
+            if n > self.STAT_ARENA_FLOATS:
+                return torch.zeros(n, dtype=torch.float32, device=device)
+            arena = self._stat_arena = torch.zeros(self.STAT_ARENA_FLOATS, dtype=torch.float32, device=device)
+            self._stat_off = 0
+        buf = arena[self._stat_off:self._stat_off + n]
+        self._stat_off += (n + 63) // 64 * 64
+        return buf
+
     def wants_grad(self, name):
         return name in self.grads
 
@@ -294,6 +306,8 @@ class Executor:
         if not self.record:
             return out
         mean, invstd = st[2], st[3]
+        # zeroed now (one arena fill per forward), consumed by the one-launch backward
+        scratch = self.zeroed_scratch(ops.bn_bwd_scratch_floats(G, C), x.data.device) if ops.USE_FUSED_BN_BWD else None
 
         def bwd():
             dy = out.grad
@@ -306,7 +320,8 @@ class Executor:
             want_dres = residual is not None and residual.needs_grad
             dx, dres = ops.bn_bwd(dy, y, x.data, mean, invstd, P[gname], dgamma, dbeta, G, R, C, relu, want_dres,
                                   dres_acc=residual.grad if want_dres else None,
-                                  scale=st[0] if residual is None else None, shift=st[1] if residual is None else None)
+                                  scale=st[0] if residual is None else None, shift=st[1] if residual is None else None,
+                                  scratch=scratch)
             x.grad = dx
             if want_dres:
                 residual.grad = dres

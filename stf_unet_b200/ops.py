@@ -405,14 +405,36 @@ def bn_apply(x, scale, shift, G, R, C, relu, residual=None, out=None):
     return y
 
 
-def bn_bwd(dy, y, x, mean, invstd, gamma, dgamma, dbeta, G, R, C, relu, want_dres, dres_acc=None, scale=None, shift=None):
+USE_FUSED_BN_BWD = os.environ.get("STFB_NO_FUSED_BN_BWD", "0") != "1"
+
+
+def bn_bwd_scratch_floats(G, C):
+    """Zeroed fp32 scratch the one-launch BatchNorm backward needs (group sums + arrival counters)."""
+    return int(_lib.load().stfb_bn_bwd_fused_scratch_floats(G, C))
+
+
+def bn_bwd(dy, y, x, mean, invstd, gamma, dgamma, dbeta, G, R, C, relu, want_dres, dres_acc=None, scale=None, shift=None,
+           scratch=None):
     """Full BatchNorm(+ReLU)(+residual) backward: returns (dx, dres or None); dgamma/dbeta accumulated.
     dres_acc: existing gradient of the residual input, accumulated into in place.
-    scale/shift (the forward's, [G][C]): with relu and no residual the mask is recomputed from x and y is not read."""
+    scale/shift (the forward's, [G][C]): with relu and no residual the mask is recomputed from x and y is not read.
+    scratch: ZEROED fp32 buffer of bn_bwd_scratch_floats(G, C) elements -> the whole backward is ONE launch
+    (reduce -> per-group barrier -> finalize -> apply); without it, the three-launch chain."""
     lib = _lib.load()
     s = _stream()
     from_x = bool(relu) and not want_dres and dres_acc is None and scale is not None and shift is not None
     ym = None if (from_x or not relu) else y
+    dx = torch.empty_like(x)
+    dres = dres_acc if dres_acc is not None else (torch.empty_like(x) if want_dres else None)
+    # two tensors per pass (no y, no dres) over a map far beyond L2: the chain's deeper grids still stream faster
+    # (tools/kernel_probe.py bn2: 278 vs 307 us on the stem's 268 MB map, 81 vs 85 us on layer 1's 67 MB)
+    lean_and_large = ym is None and dres is None and x.numel() * x.element_size() > (48 << 20)
+    if scratch is not None and USE_FUSED_BN_BWD and not lean_and_large and not os.environ.get("STFB_EXP_SKIP_RED"):
+        with _timed("bn_bwd_fused", 2 * _nb(dy, x, ym) + _nb(dx, dres, dres_acc), f"C{C}"):
+            check(lib.stfb_bn_bwd_fused(_p(dy), _p(ym), _p(x), _p(mean), _p(invstd), _p(gamma), _p(shift) if from_x else None,
+                                        _p(scratch), _p(dgamma), _p(dbeta), _p(dx), _p(dres), int(dres_acc is not None), G, R, C,
+                                        int(bool(relu)), dt_code(x.dtype), s), "bn_bwd_fused")
+        return dx, dres
     nblk = lib.stfb_bn_partial_blocks(G, R)
     red = torch.empty((nblk, 2, G, C), dtype=torch.float32, device=x.device)
     with _timed("bn_bwd_reduce", _nb(dy, x, ym), f"C{C}"):
@@ -429,8 +451,6 @@ def bn_bwd(dy, y, x, mean, invstd, gamma, dgamma, dbeta, G, R, C, relu, want_dre
     else:
       check(lib.stfb_bn_bwd_finalize(_p(red), nblk, _p(gamma), _p(invstd), _p(dgamma), _p(dbeta), _p(coef), G, R, C, s),
           "bn_bwd_finalize")
-    dx = torch.empty_like(x)
-    dres = dres_acc if dres_acc is not None else (torch.empty_like(x) if want_dres else None)
     with _timed("bn_bwd_apply", _nb(dy, x, ym, dx, dres, dres_acc), f"C{C}"):
         check(lib.stfb_bn_bwd_apply(_p(dy), _p(ym), _p(x), _p(mean), _p(invstd), _p(coef), _p(shift) if from_x else None, _p(dx),
                                     _p(dres), int(dres_acc is not None), G, R, C, int(bool(relu)), dt_code(x.dtype), s),

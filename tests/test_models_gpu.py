@@ -332,8 +332,11 @@ def test_graphed_step_matches_eager(fused_stats, monkeypatch):
     BatchNorm statistics fused into the conv epilogue the per-channel sums are fp32 red.adds whose order differs from
     run to run, so that variant is compared at bf16 noise level instead of bit level."""
     from stf_unet_b200.graph import GraphedStep
-    from stf_unet_b200 import engine
+    from stf_unet_b200 import engine, ops
     monkeypatch.setattr(engine, "USE_FUSED_BN_STATS", fused_stats)
+    # the deterministic variant also takes the three-launch BatchNorm backward (the one-launch kernel adds its group sums
+    # with fp32 atomics: same noise class as the fused statistics)
+    monkeypatch.setattr(ops, "USE_FUSED_BN_BWD", fused_stats)
     ltol, gtol = (1e-2, 3e-2) if fused_stats else (1e-5, 1e-3)   # cold weights: the atomics-order noise is amplified
     torch.manual_seed(0)
     x, t = W.synthetic_dce_batch(2, 3, 64, 64, seed=71)

@@ -150,7 +150,8 @@ def test_conv_transposed_bwd(case, dtype):
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
 @pytest.mark.parametrize("G,B,H,W,C,relu,use_res", [(3, 2, 8, 8, 64, True, True), (1, 4, 5, 7, 32, True, False),
                                                     (2, 1, 6, 6, 128, False, False), (1, 2, 4, 4, 2, False, False),
-                                                    (4, 2, 16, 16, 512, True, True)])
+                                                    (4, 2, 16, 16, 512, True, True), (8, 4, 40, 36, 64, True, True),
+                                                    (8, 2, 24, 24, 256, True, False), (2, 3, 7, 5, 24, True, True)])
 def test_batchnorm_train_fwd_bwd(G, B, H, W, C, relu, use_res, dtype):
     N = G * B
     x = q(rnd(N, C, H, W, seed=1) * 2 + 0.5, dtype).requires_grad_(True)
@@ -199,6 +200,24 @@ def test_batchnorm_train_fwd_bwd(G, B, H, W, C, relu, use_res, dtype):
         acc = nhwc(torch.ones_like(res), dtype)
         _, dres2 = ops.bn_bwd(nhwc(dy, dtype), y, xn, st[2], st[3], gamma.detach(), None, None, G, R, C, relu, True, dres_acc=acc)
         assert rel(nchw(dres2), res.grad + 1) < t
+
+    # ---- the one-launch backward (reduce -> group barrier -> finalize -> apply) against the same reference ----
+    def scratch():
+        return torch.zeros(ops.bn_bwd_scratch_floats(G, C), device=DEV)
+    dg3, db3 = torch.ones(C, device=DEV), torch.full((C,), 2.0, device=DEV)          # accumulated into, not overwritten
+    dx3, dres3 = ops.bn_bwd(nhwc(dy, dtype), y, xn, st[2], st[3], gamma.detach(), dg3, db3, G, R, C, relu, use_res, scratch=scratch())
+    assert rel(nchw(dx3), x.grad) < t and rel(dx3, dx) < (1e-5 if dtype == torch.float32 else 1e-2)
+    assert rel(dg3 - 1, gamma.grad) < t and rel(db3 - 2, beta.grad) < t
+    if relu and not use_res:
+        dx4, _ = ops.bn_bwd(nhwc(dy, dtype), None, xn, st[2], st[3], gamma.detach(), None, None, G, R, C, relu, False,
+                            scale=st[0], shift=st[1], scratch=scratch())
+        assert rel(dx4, dx3) < (1e-6 if dtype == torch.float32 else 1e-2)
+    if use_res:
+        assert rel(nchw(dres3), res.grad) < t
+        acc = nhwc(torch.ones_like(res), dtype)
+        _, dres4 = ops.bn_bwd(nhwc(dy, dtype), y, xn, st[2], st[3], gamma.detach(), None, None, G, R, C, relu, True, dres_acc=acc,
+                              scratch=scratch())
+        assert rel(nchw(dres4), res.grad + 1) < t
 
 
 def test_bn_fold_eval_matches_batch_norm():

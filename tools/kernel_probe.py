@@ -157,6 +157,45 @@ def main():
             t_apr = graph_time(lambda: ops.bn_apply(x, st[0], st[1], G, R, C, True, res, out=y), a.iters)
             t_bwd = graph_time(lambda: ops.bn_bwd(dy, y, x, st[2], st[3], gamma, dg, db, G, R, C, True, False, scale=st[0], shift=st[1]), a.iters)
             t_bwr = graph_time(lambda: ops.bn_bwd(dy, y, x, st[2], st[3], gamma, dg, db, G, R, C, True, True, dres_acc=dres), a.iters)
+            nsc = ops.bn_bwd_scratch_floats(G, C)
+            arena = torch.zeros(nsc * a.iters * 2 + 64, device=DEV)       # one zeroed scratch per launch inside the graph
+            cnt = [0]
+
+            def fused(res_mode):
+                k = cnt[0] % (2 * a.iters)
+                cnt[0] += 1
+                sc = arena[k * nsc:(k + 1) * nsc]
+                if res_mode:
+                    ops.bn_bwd(dy, y, x, st[2], st[3], gamma, dg, db, G, R, C, True, True, dres_acc=dres, scratch=sc)
+                else:
+                    ops.bn_bwd(dy, y, x, st[2], st[3], gamma, dg, db, G, R, C, True, False, scale=st[0], shift=st[1], scratch=sc)
+
+            def timed_fused(res_mode):
+                # the graph consumes 2 * iters scratch slices (warm-up replay + timed replay): zero them, capture, time
+                def fn():
+                    fused(res_mode)
+                cnt[0] = 0
+                torch.cuda.synchronize()
+                side = torch.cuda.Stream()
+                with torch.cuda.stream(side):
+                    fn()
+                torch.cuda.synchronize()
+                cnt[0] = 0
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    for _ in range(a.iters):
+                        fn()
+                arena.zero_()
+                torch.cuda.synchronize()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                g.replay()
+                e1.record()
+                torch.cuda.synchronize()
+                return e0.elapsed_time(e1) / a.iters * 1e3
+
+            t_fu, t_fur = timed_fused(False), timed_fused(True)
+            print(f"bn2    N{N} {H}x{W} C{C}: ONE-LAUNCH bwd {t_fu:6.1f} us ({5 * S / t_fu:6.0f} GB/s)  +res {t_fur:6.1f} us ({10 * S / t_fur:6.0f} GB/s)")
             print(f"bn2    N{N} {H}x{W} C{C}: fin {t_fin:5.1f} us | apply {t_app:6.1f} us ({2 * S / t_app:6.0f} GB/s)  +res {t_apr:6.1f} us "
                   f"({3 * S / t_apr:6.0f} GB/s) | bwd chain {t_bwd:6.1f} us ({5 * S / t_bwd:6.0f} GB/s)  +res {t_bwr:6.1f} us ({10 * S / t_bwr:6.0f} GB/s)")
 
