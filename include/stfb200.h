@@ -182,6 +182,12 @@ int stfb_bn_fold_eval(const float* gamma, const float* beta, const float* runnin
 /* y = relu?( x*scale[g][c] + shift[g][c] + residual ) */
 int stfb_bn_apply(const void* x, const float* scale, const float* shift, const void* residual, void* y, int G,
                   long long R, int C, int relu, int dtype, void* stream);
+/* the same pass with scale/shift derived inside the kernel from nblk <= 8 statistics slots (the conv epilogue's), by the
+ * exact arithmetic of stfb_bn_finalize_train: the finalize launch then only updates the running statistics and saves
+ * mean / invstd for the backward pass, and need not precede this call */
+int stfb_bn_apply_from_stats(const void* x, const float* partial, int nblk, const float* gamma, const float* beta,
+                             const void* residual, void* y, int G, long long R, int C, float eps, int relu, int dtype,
+                             void* stream);
 /* backward, step 1: dz = dy * (y > 0 if relu); partial[blk][0][g][c] = sum dz, partial[blk][1][g][c] = sum dz*xhat */
 /* relu: the ReLU mask is y > 0; with y == NULL it is recomputed as fma(x, scale, shift) > 0 from the forward's scale and
  * shift (saves the read of y; only valid when no residual was added before the ReLU). */

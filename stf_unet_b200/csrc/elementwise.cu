@@ -243,6 +243,21 @@ __device__ __forceinline__ void sum_slots(const float* __restrict__ partial, int
   q = b0 + b1;
 }
 
+// scale / shift of (group g, channel c) from the partial slots: THE formula -- bn_finalize_train_kernel and the
+// self-finalizing bn_apply_kernel both call it, so the two routes give bit-identical coefficients
+__device__ __forceinline__ void bn_train_coefs(const float* __restrict__ partial, int nblk, int G, int C, int g, int c, double n,
+                                               float gamma_c, float beta_c, float eps, float& sc, float& sh, double& m, double& var,
+                                               float& is) {
+  double s, q;
+  sum_slots(partial, nblk, G, C, g, c, s, q);
+  m = s / n;
+  var = q / n - m * m;
+  if (var < 0.0) var = 0.0;
+  is = rsqrtf((float)var + eps);
+  sc = gamma_c * is;
+  sh = beta_c - (float)m * sc;
+}
+
 __global__ void __launch_bounds__(FIN_CH * FIN_MAXG) bn_finalize_train_kernel(
     const float* __restrict__ partial, int nblk, const float* __restrict__ gamma, const float* __restrict__ beta,
     float* running_mean, float* running_var, long long* nbt, float* scale, float* shift, float* mean, float* invstd, int G,
@@ -258,15 +273,11 @@ __global__ void __launch_bounds__(FIN_CH * FIN_MAXG) bn_finalize_train_kernel(
   for (int g0 = 0; g0 < G; g0 += gpb) {
     const int g = g0 + gl;
     if (g < G && c < C) {
-      double s, q;
-      sum_slots(partial, nblk, G, C, g, c, s, q);
-      const double m = s / n;
-      double var = q / n - m * m;
-      if (var < 0.0) var = 0.0;
-      const float is = rsqrtf((float)var + eps);
-      const float sc = gamma[c] * is;
+      float sc, sh, is;
+      double m, var;
+      bn_train_coefs(partial, nblk, G, C, g, c, n, gamma[c], beta[c], eps, sc, sh, m, var, is);
       scale[g * C + c] = sc;
-      shift[g * C + c] = beta[c] - (float)m * sc;
+      shift[g * C + c] = sh;
       mean[g * C + c] = (float)m;
       invstd[g * C + c] = is;
       sh_m[gl][cl] = (float)m;
@@ -300,10 +311,37 @@ __global__ void bn_fold_eval_kernel(const float* __restrict__ gamma, const float
 // Row-tiled elementwise kernels: thread (rl, cl) of a CTA owns channels [cl*VEC, cl*VEC + VEC) of every (256/tpr)-th row
 // of its row range inside ONE group (blockIdx.y), so the per-(group, channel) coefficients sit in registers and the
 // loop body is U independent 16-byte loads per tensor followed by the stores.
+// the coefficient table of one group in shared memory ([2][C]: scale, shift); a separate function so that its fp64 slot
+// sums do not share a register allocation with the streaming loop of the caller
+__device__ __noinline__ void bn_group_coefs_to_smem(const float* __restrict__ partial, int nblk, int G, int C, int g, long long R,
+                                                    const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
+                                                    const float* __restrict__ scale, const float* __restrict__ shift,
+                                                    float* coef_sm) {
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float sc_, sh_;
+    if (partial) {
+      float is_;
+      double m_, v_;
+      bn_train_coefs(partial, nblk, G, C, g, c, (double)R, gamma[c], beta[c], eps, sc_, sh_, m_, v_, is_);
+    } else {
+      sc_ = scale[g * C + c];
+      sh_ = shift[g * C + c];
+    }
+    coef_sm[c] = sc_;
+    coef_sm[C + c] = sh_;
+  }
+}
+
+// partial != nullptr: the CTA derives scale/shift of its group itself from the (few) statistics slots the conv epilogue
+// filled -- the finalize kernel (6 us of pure latency per layer, 44 layers) leaves the critical path and runs beside it,
+// only to update the running statistics and to save mean / invstd / scale / shift for the backward pass.
 template <typename T, int VEC>
 __global__ void __launch_bounds__(256, 4) bn_apply_kernel(const T* __restrict__ x, const float* __restrict__ scale,
                                                        const float* __restrict__ shift, const T* res, T* y, long long R, int C,
-                                                       long long rows_per_block, int tpr, int relu) {
+                                                       long long rows_per_block, int tpr, int relu,
+                                                       const float* __restrict__ partial, int nblk,
+                                                       const float* __restrict__ gamma, const float* __restrict__ beta, float eps) {
+  extern __shared__ float coef_sm[];                 // [2][C]: scale, shift of this CTA's group
   constexpr int U = 2;
   const int lanes = 256 / tpr;
   const int cl = threadIdx.x % tpr, rl = threadIdx.x / tpr;
@@ -312,11 +350,13 @@ __global__ void __launch_bounds__(256, 4) bn_apply_kernel(const T* __restrict__ 
   const long long r0 = (long long)blockIdx.x * rows_per_block;
   const long long r1 = min(R, r0 + rows_per_block);
   const long long gbase = (long long)g * R;
+  bn_group_coefs_to_smem(partial, nblk, gridDim.y, C, g, R, gamma, beta, eps, scale, shift, coef_sm);
+  __syncthreads();
   for (int cv = cl; cv < CVn; cv += tpr) {
     const int c = cv * VEC;
     float sc[VEC], sh[VEC];
 #pragma unroll
-    for (int j = 0; j < VEC; ++j) { sc[j] = scale[g * C + c + j]; sh[j] = shift[g * C + c + j]; }
+    for (int j = 0; j < VEC; ++j) { sc[j] = coef_sm[c + j]; sh[j] = coef_sm[C + c + j]; }
     long long r = r0 + rl;
     for (; r + (long long)(U - 1) * lanes < r1; r += (long long)U * lanes) {
       float v[U][VEC], rr[U][VEC];
@@ -1345,21 +1385,41 @@ extern "C" int stfb_bn_fold_eval(const float* gamma, const float* beta, const fl
   return post_launch("bn_fold_eval");
 }
 
-extern "C" int stfb_bn_apply(const void* x, const float* scale, const float* shift, const void* residual, void* y, int G,
-                             long long R, int C, int relu, int dtype, void* stream) {
-  STFB_REQUIRE(x && scale && shift && y && G > 0 && R >= 0 && C > 0 && DT_OK(dtype), "bn_apply: bad arguments");
-  STFB_DEVICE_OR_RETURN();
-  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+static int bn_apply_launch(const void* x, const float* scale, const float* shift, const void* residual, void* y, int G, long long R,
+                           int C, int relu, int dtype, const float* partial, int nblk, const float* gamma, const float* beta,
+                           float eps, cudaStream_t s) {
   const long long rows = (long long)G * R;
   if (rows == 0) return STFB_OK;
   const int v = pick_vec(C, dtype, {x, residual, y});
   const RowTile rt = row_tile(G, R, C, v, 2);
+  const size_t sm = (size_t)2 * C * sizeof(float);
+  STFB_REQUIRE(sm <= 48 * 1024, "bn_apply: %d channels exceed the shared-memory coefficient table", C);
+#define BN_APPLY(V) bn_apply_kernel<T, V><<<rt.grid, 256, sm, s>>>((const T*)x, scale, shift, (const T*)residual, (T*)y, R, C, rt.rows_per_block, rt.tpr, relu, partial, nblk, gamma, beta, eps)
   DISPATCH_T(dtype, {
-    if (v == 8) bn_apply_kernel<T, 8><<<rt.grid, 256, 0, s>>>((const T*)x, scale, shift, (const T*)residual, (T*)y, R, C, rt.rows_per_block, rt.tpr, relu);
-    else if (v == 4) bn_apply_kernel<T, 4><<<rt.grid, 256, 0, s>>>((const T*)x, scale, shift, (const T*)residual, (T*)y, R, C, rt.rows_per_block, rt.tpr, relu);
-    else bn_apply_kernel<T, 1><<<rt.grid, 256, 0, s>>>((const T*)x, scale, shift, (const T*)residual, (T*)y, R, C, rt.rows_per_block, rt.tpr, relu);
+    if (v == 8) BN_APPLY(8);
+    else if (v == 4) BN_APPLY(4);
+    else BN_APPLY(1);
   });
+#undef BN_APPLY
   return post_launch("bn_apply");
+}
+
+extern "C" int stfb_bn_apply(const void* x, const float* scale, const float* shift, const void* residual, void* y, int G,
+                             long long R, int C, int relu, int dtype, void* stream) {
+  STFB_REQUIRE(x && scale && shift && y && G > 0 && R >= 0 && C > 0 && DT_OK(dtype), "bn_apply: bad arguments");
+  STFB_DEVICE_OR_RETURN();
+  return bn_apply_launch(x, scale, shift, residual, y, G, R, C, relu, dtype, nullptr, 0, nullptr, nullptr, 0.f,
+                         reinterpret_cast<cudaStream_t>(stream));
+}
+
+extern "C" int stfb_bn_apply_from_stats(const void* x, const float* partial, int nblk, const float* gamma, const float* beta,
+                                        const void* residual, void* y, int G, long long R, int C, float eps, int relu, int dtype,
+                                        void* stream) {
+  STFB_REQUIRE(x && partial && gamma && beta && y && G > 0 && G <= 65535 && R > 0 && C > 0 && DT_OK(dtype), "bn_apply_from_stats: bad arguments");
+  STFB_REQUIRE(nblk >= 1 && nblk <= 8, "bn_apply_from_stats: 1..8 statistics slots (got %d); finalize first for more", nblk);
+  STFB_DEVICE_OR_RETURN();
+  return bn_apply_launch(x, nullptr, nullptr, residual, y, G, R, C, relu, dtype, partial, nblk, gamma, beta, eps,
+                         reinterpret_cast<cudaStream_t>(stream));
 }
 
 extern "C" int stfb_bn_bwd_reduce(const void* dy, const void* y, const void* x, const float* mean, const float* invstd,

@@ -23,6 +23,7 @@ USE_FUSED_LSTM = _os.environ.get("STFB_NO_FUSED_LSTM", "0") != "1"
 USE_FUSED_BN_STATS = _os.environ.get("STFB_NO_FUSED_BN_STATS", "0") != "1"
 USE_LSTM_STREAMS = _os.environ.get("STFB_NO_LSTM_STREAMS", "0") != "1"
 USE_WGRAD_STREAM = _os.environ.get("STFB_NO_WGRAD_STREAM", "0") != "1"
+USE_SIDE_FINALIZE = _os.environ.get("STFB_NO_SIDE_FINALIZE", "0") != "1"
 
 
 class Var:
@@ -71,6 +72,7 @@ class Executor:
         self.grad_offsets: Dict[str, int] = {}
         self._deferred = {}           # name -> (flat offset, Cp, Cg_total, khw)
         self._wg_keep = []            # (dy, x) pairs the side-stream wgrad launches still read
+        self._fin_keep = []           # (slots, coefficients) the side-stream BatchNorm finalize launches still touch
 
     # ---------------------------------------------------------------------------------------------
     def packed(self, name, k_is_dim1, n_major=False, flip=False, kpad=None, gate_c=0):
@@ -180,6 +182,18 @@ class Executor:
             w = self.params[wname]
             khw = 1 if w.dim() == 2 else w.shape[2] * w.shape[3]
             self._deferred[wname] = (self.grad_offsets[wname], w.shape[0], w.shape[1], khw)
+
+    _fin_streams = {}
+
+    def join_finalize(self):
+        """End of the forward pass: the side-stream BatchNorm finalize launches (running statistics, saved coefficients)
+        are ordered before whatever follows on the current stream."""
+        if self._fin_keep:
+            cur = torch.cuda.current_stream()
+            side = Executor._fin_streams.get(cur.device.index)
+            if side is not None:
+                cur.wait_stream(side)
+            self._fin_keep = []
 
     def join_wgrad(self):
         if self._wg_keep:
@@ -298,10 +312,27 @@ class Executor:
         P = self.params
         sums = x.bn_partial if x.bn_partial is not None else ops.bn_stats(x.data, G, R, C)
         x.bn_partial = None
-        st = ops.bn_finalize_train(sums, P[prefix + ".weight"], P[prefix + ".bias"], P[prefix + ".running_mean"],
-                                   P[prefix + ".running_var"], P[prefix + ".num_batches_tracked"], G, R, C, BN_EPS,
-                                   BN_MOMENTUM)
-        y = ops.bn_apply(x.data, st[0], st[1], G, R, C, relu, None if residual is None else residual.data)
+        resd = None if residual is None else residual.data
+        if USE_SIDE_FINALIZE and sums.shape[0] <= 8 and x.data.is_cuda and 2 * C * 4 <= 48 * 1024:
+            # few slots (the conv epilogue's): the apply kernel derives scale/shift itself and the finalize launch -- now
+            # only the running statistics and the coefficients the backward pass reads -- runs beside the main chain
+            st = torch.empty((4, G, C), dtype=torch.float32, device=x.data.device)
+            cur = torch.cuda.current_stream()
+            side = Executor._fin_streams.get(cur.device.index)
+            if side is None:
+                side = Executor._fin_streams[cur.device.index] = torch.cuda.Stream(device=cur.device)
+            side.wait_stream(cur)
+            with torch.cuda.stream(side):
+                ops.bn_finalize_train(sums, P[prefix + ".weight"], P[prefix + ".bias"], P[prefix + ".running_mean"],
+                                      P[prefix + ".running_var"], P[prefix + ".num_batches_tracked"], G, R, C, BN_EPS,
+                                      BN_MOMENTUM, out=st)
+            self._fin_keep.append((sums, st))
+            y = ops.bn_apply_from_stats(x.data, sums, P[prefix + ".weight"], P[prefix + ".bias"], G, R, C, relu, resd, eps=BN_EPS)
+        else:
+            st = ops.bn_finalize_train(sums, P[prefix + ".weight"], P[prefix + ".bias"], P[prefix + ".running_mean"],
+                                       P[prefix + ".running_var"], P[prefix + ".num_batches_tracked"], G, R, C, BN_EPS,
+                                       BN_MOMENTUM)
+            y = ops.bn_apply(x.data, st[0], st[1], G, R, C, relu, resd)
         out = Var(y, grad_dtype=self.dtype)
         if not self.record:
             return out

@@ -134,6 +134,7 @@ class B200Module(nn.Module):
         ex._mode_key = (ex.dtype, self.training, record)
         ex._owner = self
         head = self._forward_impl(ex, x)
+        ex.join_finalize()
         logits = ops.nhwc_to_nchw(head.data)
         if not record:
             self._learn_pack_plan(ex)

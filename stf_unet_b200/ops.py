@@ -15,7 +15,7 @@ from ._lib import BF16, CONV_FWD, CONV_TRANSPOSED, F32, IMPL_AUTO, IMPL_SIMT, IM
 
 __all__ = ["dt_code", "conv2d", "conv2d_wgrad", "pack_weight", "bn_stats", "bn_finalize_train", "bn_fold_eval",
            "bn_apply", "bn_bwd", "colsum", "maxpool_fwd", "maxpool_bwd", "maxpool_fwd_idx", "maxpool_bwd_idx", "bilinear_fwd", "bilinear_bwd",
-           "tcgen05_ok", "conv_stats_fusable", "STAT_SLOTS", "im2col_small", "unpad_wgrad", "lstm_step_fused", "pack_lstm_xh", "lstm_cell_fwd", "lstm_cell_bwd", "pack_series", "pack_series_u8", "adamw_flat_", "pack_series_maps", "repeat_batch", "nhwc_to_nchw", "nchw_to_nhwc", "add_", "cast",
+           "tcgen05_ok", "conv_stats_fusable", "STAT_SLOTS", "im2col_small", "unpad_wgrad", "lstm_step_fused", "pack_lstm_xh", "lstm_cell_fwd", "lstm_cell_bwd", "bn_apply_from_stats", "bn_bwd_scratch_floats", "pack_series", "pack_series_u8", "adamw_flat_", "pack_series_maps", "repeat_batch", "nhwc_to_nchw", "nchw_to_nhwc", "add_", "cast",
            "ce_dice_fwd", "ce_dice_bwd", "CONV_FWD", "CONV_TRANSPOSED", "IMPL_AUTO", "IMPL_SIMT", "IMPL_TCGEN05"]
 
 _DT = {torch.float32: F32, torch.bfloat16: BF16}
@@ -374,13 +374,14 @@ def bn_stats(x, G, R, C):
 _EXP_CONST = {}
 
 
-def bn_finalize_train(partial, gamma, beta, running_mean, running_var, nbt, G, R, C, eps=1e-5, momentum=0.1):
+def bn_finalize_train(partial, gamma, beta, running_mean, running_var, nbt, G, R, C, eps=1e-5, momentum=0.1, out=None):
     if os.environ.get("STFB_EXP_SKIP_FIN"):
         k = ("f", G, C)
         if k not in _EXP_CONST:
             _EXP_CONST[k] = torch.ones((4, G, C), dtype=torch.float32, device=partial.device)
         return _EXP_CONST[k]
-    out = torch.empty((4, G, C), dtype=torch.float32, device=partial.device)  # scale, shift, mean, invstd
+    if out is None:
+        out = torch.empty((4, G, C), dtype=torch.float32, device=partial.device)  # scale, shift, mean, invstd
     check(_lib.load().stfb_bn_finalize_train(_p(partial), partial.shape[0], _p(gamma), _p(beta), _p(running_mean),
                                              _p(running_var), _p(nbt), _p(out[0]), _p(out[1]), _p(out[2]), _p(out[3]), G, R,
                                              C, eps, momentum, _stream()), "bn_finalize_train")
@@ -393,6 +394,15 @@ def bn_fold_eval(gamma, beta, running_mean, running_var, eps=1e-5):
     check(_lib.load().stfb_bn_fold_eval(_p(gamma), _p(beta), _p(running_mean), _p(running_var), _p(out[0]), _p(out[1]), C_,
                                         eps, _stream()), "bn_fold_eval")
     return out
+
+
+def bn_apply_from_stats(x, partial, gamma, beta, G, R, C, relu, residual=None, out=None, eps=1e-5):
+    """bn_apply with scale/shift derived in-kernel from <= 8 statistics slots (same arithmetic as bn_finalize_train)."""
+    y = out if out is not None else torch.empty_like(x)
+    with _timed("bn_apply", _nb(x, residual, y), f"C{C}"):
+        check(_lib.load().stfb_bn_apply_from_stats(_p(x), _p(partial), partial.shape[0], _p(gamma), _p(beta), _p(residual), _p(y),
+                                                   G, R, C, eps, int(bool(relu)), dt_code(x.dtype), _stream()), "bn_apply_from_stats")
+    return y
 
 
 def bn_apply(x, scale, shift, G, R, C, relu, residual=None, out=None):
