@@ -232,6 +232,18 @@ __device__ __forceinline__ void sum_slots(const float* __restrict__ partial, int
   double a0 = 0.0, a1 = 0.0, b0 = 0.0, b1 = 0.0;
   const long long slot = 2LL * G * C;
   const float* p = partial + (long long)g * C + c;
+  if (nblk == 8) {
+    // the conv epilogue's eight slots: all sixteen loads are issued before the first add (the rolled loop below pays one
+    // L2 round trip per pair of slots: ~3 us of pure latency at the head of every BatchNorm-apply CTA); same add order
+    float sv[8], qv[8];
+#pragma unroll
+    for (int b = 0; b < 8; ++b) { sv[b] = p[(long long)b * slot]; qv[b] = p[(long long)b * slot + (long long)G * C]; }
+#pragma unroll
+    for (int b = 0; b < 8; b += 2) { a0 += (double)sv[b]; b0 += (double)qv[b]; a1 += (double)sv[b + 1]; b1 += (double)qv[b + 1]; }
+    s = a0 + a1;
+    q = b0 + b1;
+    return;
+  }
   int b = 0;
   for (; b + 1 < nblk; b += 2) {
     const float s0 = p[(long long)b * slot], q0 = p[(long long)b * slot + (long long)G * C];
@@ -993,6 +1005,66 @@ __global__ void __launch_bounds__(256) maxpool_bwd_idx_kernel(const unsigned cha
   }
 }
 
+// 3x3 / stride 2 / pad 1 (the ResNet stem pool), bf16, even H and W: one thread owns a 2x2 input block x 8 channels.  The
+// block lies in at most four windows -- (m, l), (m, l+1), (m+1, l), (m+1, l+1) -- whose index words and dy vectors are loaded
+// ONCE and feed all four outputs through nine (window, position) byte compares (the generic kernel loads and tests four
+// windows per input element: 16 window visits per block instead of 4).  Window (oy, ox) starts at input (2oy-1, 2ox-1), so
+//   (2m, 2l)     <- (m,l) pos 4              (2m, 2l+1)   <- (m,l) pos 5, (m,l+1) pos 3
+//   (2m+1, 2l)   <- (m,l) pos 7, (m+1,l) pos 1   (2m+1, 2l+1) <- (m,l) 8, (m,l+1) 6, (m+1,l) 2, (m+1,l+1) 0
+__device__ __forceinline__ void mp_masked_add(uint32_t* acc, const uint2& pk, const uint4& dv, unsigned pos) {
+  const uint32_t p4 = pos * 0x01010101u;
+  const uint32_t e0 = __vcmpeq4(pk.x, p4), e1 = __vcmpeq4(pk.y, p4);
+  const uint32_t w[4] = {dv.x & __byte_perm(e0, 0, 0x1100), dv.y & __byte_perm(e0, 0, 0x3322),
+                         dv.z & __byte_perm(e1, 0, 0x1100), dv.w & __byte_perm(e1, 0, 0x3322)};
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    __nv_bfloat162 s2 = __hadd2(*reinterpret_cast<const __nv_bfloat162*>(&acc[q]), *reinterpret_cast<const __nv_bfloat162*>(&w[q]));
+    acc[q] = *reinterpret_cast<const uint32_t*>(&s2);
+  }
+}
+
+constexpr int MP3_BW = 8, MP3_BH = 4, MP3_ROWS = 4;      // CTA: 8 x 4 blocks (x 8 channel vectors = 256 threads), 4 block rows deep
+__global__ void __launch_bounds__(256) maxpool3s2_bwd_idx_kernel(const unsigned char* __restrict__ idx,
+                                                                 const __nv_bfloat16* __restrict__ dy, __nv_bfloat16* __restrict__ dx,
+                                                                 int N, int H, int W, int C, int Ho, int Wo) {
+  const int CVn = C >> 3;                                 // launched with CVn == 8 channel vectors per CTA column slice
+  const int cv = blockIdx.x % ((CVn + 7) / 8) * 8 + (threadIdx.x & 7);
+  const int bxt = blockIdx.x / ((CVn + 7) / 8);
+  const int l = bxt * MP3_BW + ((threadIdx.x >> 3) & (MP3_BW - 1));
+  const int mrow = threadIdx.x >> 6;                      // 0..3
+  if (cv >= CVn || 2 * l >= W) return;
+  const bool ox1 = l + 1 < Wo;
+  for (int n = blockIdx.z; n < N; n += gridDim.z) {
+#pragma unroll
+    for (int it = 0; it < MP3_ROWS; ++it) {
+      const int m = (blockIdx.y * MP3_ROWS + it) * MP3_BH + mrow;
+      if (2 * m >= H) continue;
+      const bool oy1 = m + 1 < Ho;
+      const long long o00 = (((long long)n * Ho + m) * Wo + l) * C + cv * 8;
+      const long long o01 = ox1 ? o00 + C : o00, o10 = oy1 ? o00 + (long long)Wo * C : o00;
+      const long long o11 = (ox1 && oy1) ? o00 + (long long)Wo * C + C : o00;
+      uint2 i00 = *reinterpret_cast<const uint2*>(idx + o00), i01 = *reinterpret_cast<const uint2*>(idx + o01);
+      uint2 i10 = *reinterpret_cast<const uint2*>(idx + o10), i11 = *reinterpret_cast<const uint2*>(idx + o11);
+      const uint4 d00 = *reinterpret_cast<const uint4*>(dy + o00), d01 = *reinterpret_cast<const uint4*>(dy + o01);
+      const uint4 d10 = *reinterpret_cast<const uint4*>(dy + o10), d11 = *reinterpret_cast<const uint4*>(dy + o11);
+      // a missing neighbour window contributes nothing: 0xff never equals a window position
+      if (!ox1) i01 = make_uint2(0xffffffffu, 0xffffffffu);
+      if (!oy1) i10 = make_uint2(0xffffffffu, 0xffffffffu);
+      if (!(ox1 && oy1)) i11 = make_uint2(0xffffffffu, 0xffffffffu);
+      uint32_t a00[4] = {0u, 0u, 0u, 0u}, a01[4] = {0u, 0u, 0u, 0u}, a10[4] = {0u, 0u, 0u, 0u}, a11[4] = {0u, 0u, 0u, 0u};
+      mp_masked_add(a00, i00, d00, 4);
+      mp_masked_add(a01, i00, d00, 5); mp_masked_add(a01, i01, d01, 3);
+      mp_masked_add(a10, i00, d00, 7); mp_masked_add(a10, i10, d10, 1);
+      mp_masked_add(a11, i00, d00, 8); mp_masked_add(a11, i01, d01, 6); mp_masked_add(a11, i10, d10, 2); mp_masked_add(a11, i11, d11, 0);
+      const long long x00 = (((long long)n * H + 2 * m) * W + 2 * l) * C + cv * 8;
+      *reinterpret_cast<uint4*>(dx + x00) = make_uint4(a00[0], a00[1], a00[2], a00[3]);
+      *reinterpret_cast<uint4*>(dx + x00 + C) = make_uint4(a01[0], a01[1], a01[2], a01[3]);
+      *reinterpret_cast<uint4*>(dx + x00 + (long long)W * C) = make_uint4(a10[0], a10[1], a10[2], a10[3]);
+      *reinterpret_cast<uint4*>(dx + x00 + (long long)W * C + C) = make_uint4(a11[0], a11[1], a11[2], a11[3]);
+    }
+  }
+}
+
 // =================================================================================================
 // bilinear, align_corners=True
 // =================================================================================================
@@ -1575,6 +1647,15 @@ extern "C" int stfb_maxpool_bwd_idx(const unsigned char* idx, const void* dy, vo
   if (N == 0) return STFB_OK;
   const int wmax = (k + stride - 1) / stride;        // windows that can contain one input element, per axis
   STFB_REQUIRE(wmax <= 3, "maxpool_bwd_idx: k (%d) > 3 * stride (%d) is not supported", k, stride);
+  if (v && dtype == STFB_BF16 && k == 3 && stride == 2 && pad == 1 && H % 2 == 0 && W % 2 == 0 && Ho == H / 2 && Wo == W / 2) {
+    const int cslices = (C / 8 + 7) / 8;
+    const unsigned gy = (unsigned)((H / 2 + MP3_BH * MP3_ROWS - 1) / (MP3_BH * MP3_ROWS));
+    if (gy <= 65535) {
+      const dim3 g3((unsigned)(((W / 2 + MP3_BW - 1) / MP3_BW) * cslices), gy, (unsigned)(N < 65535 ? N : 65535));
+      maxpool3s2_bwd_idx_kernel<<<g3, 256, 0, s>>>(idx, (const __nv_bfloat16*)dy, (__nv_bfloat16*)dx, N, H, W, C, Ho, Wo);
+      return post_launch("maxpool_bwd_idx");
+    }
+  }
   STFB_REQUIRE(ptile.tiles_h <= 65535, "maxpool_bwd_idx: input too tall (%d rows)", H);
   const dim3 grid((unsigned)ptile.tiles_w, (unsigned)((ptile.tiles_h + MP_TPB - 1) / MP_TPB), (unsigned)(N < 65535 ? N : 65535));
 #define MP_BWD(V, WM) maxpool_bwd_idx_kernel<T, V, WM><<<grid, 256, 0, s>>>(idx, (const T*)dy, (T*)dx, N, H, W, C, Ho, Wo, k, stride, pad)

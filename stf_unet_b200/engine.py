@@ -162,8 +162,6 @@ class Executor:
         ONE side stream forked from the current one: the tensor-core bound wgrad kernels (192 threads, 130 KB of shared
         memory per SM) then share the SMs with the memory-bound BatchNorm-backward kernels of the main chain instead of
         alternating with them.  P and G are kept alive until the join at the end of the backward pass."""
-        if _os.environ.get("STFB_EXP_SKIP_WGRAD"):
-            return
         acc = self.acc.get(wname)
         side = None
         if USE_WGRAD_STREAM and self.dtype == torch.bfloat16 and P.is_cuda:

@@ -371,15 +371,7 @@ def bn_stats(x, G, R, C):
     return partial
 
 
-_EXP_CONST = {}
-
-
 def bn_finalize_train(partial, gamma, beta, running_mean, running_var, nbt, G, R, C, eps=1e-5, momentum=0.1, out=None):
-    if os.environ.get("STFB_EXP_SKIP_FIN"):
-        k = ("f", G, C)
-        if k not in _EXP_CONST:
-            _EXP_CONST[k] = torch.ones((4, G, C), dtype=torch.float32, device=partial.device)
-        return _EXP_CONST[k]
     if out is None:
         out = torch.empty((4, G, C), dtype=torch.float32, device=partial.device)  # scale, shift, mean, invstd
     check(_lib.load().stfb_bn_finalize_train(_p(partial), partial.shape[0], _p(gamma), _p(beta), _p(running_mean),
@@ -406,8 +398,6 @@ def bn_apply_from_stats(x, partial, gamma, beta, G, R, C, relu, residual=None, o
 
 
 def bn_apply(x, scale, shift, G, R, C, relu, residual=None, out=None):
-    if os.environ.get("STFB_EXP_SKIP_APPLY"):
-        return x
     y = out if out is not None else torch.empty_like(x)
     with _timed("bn_apply", _nb(x, residual, y), f"C{C}"):
         check(_lib.load().stfb_bn_apply(_p(x), _p(scale), _p(shift), _p(residual), _p(y), G, R, C, int(bool(relu)),
@@ -439,7 +429,7 @@ def bn_bwd(dy, y, x, mean, invstd, gamma, dgamma, dbeta, G, R, C, relu, want_dre
     # two tensors per pass (no y, no dres) over a map far beyond L2: the chain's deeper grids still stream faster
     # (tools/kernel_probe.py bn2: 278 vs 307 us on the stem's 268 MB map, 81 vs 85 us on layer 1's 67 MB)
     lean_and_large = ym is None and dres is None and x.numel() * x.element_size() > (48 << 20)
-    if scratch is not None and USE_FUSED_BN_BWD and not lean_and_large and not os.environ.get("STFB_EXP_SKIP_RED"):
+    if scratch is not None and USE_FUSED_BN_BWD and not lean_and_large:
         with _timed("bn_bwd_fused", 2 * _nb(dy, x, ym) + _nb(dx, dres, dres_acc), f"C{C}"):
             check(lib.stfb_bn_bwd_fused(_p(dy), _p(ym), _p(x), _p(mean), _p(invstd), _p(gamma), _p(shift) if from_x else None,
                                         _p(scratch), _p(dgamma), _p(dbeta), _p(dx), _p(dres), int(dres_acc is not None), G, R, C,
@@ -448,18 +438,11 @@ def bn_bwd(dy, y, x, mean, invstd, gamma, dgamma, dbeta, G, R, C, relu, want_dre
     nblk = lib.stfb_bn_partial_blocks(G, R)
     red = torch.empty((nblk, 2, G, C), dtype=torch.float32, device=x.device)
     with _timed("bn_bwd_reduce", _nb(dy, x, ym), f"C{C}"):
-      if not os.environ.get("STFB_EXP_SKIP_RED"):
         check(lib.stfb_bn_bwd_reduce(_p(dy), _p(ym), _p(x), _p(mean), _p(invstd), _p(scale) if from_x else None,
                                      _p(shift) if from_x else None, _p(red), nblk, G, R, C, int(bool(relu)), dt_code(x.dtype), s),
               "bn_bwd_reduce")
     coef = torch.empty((G, C, 3), dtype=torch.float32, device=x.device)
-    if os.environ.get("STFB_EXP_SKIP_FIN"):
-        k = ("b", G, C)
-        if k not in _EXP_CONST:
-            _EXP_CONST[k] = torch.ones((G, C, 3), dtype=torch.float32, device=x.device)
-        coef = _EXP_CONST[k]
-    else:
-      check(lib.stfb_bn_bwd_finalize(_p(red), nblk, _p(gamma), _p(invstd), _p(dgamma), _p(dbeta), _p(coef), G, R, C, s),
+    check(lib.stfb_bn_bwd_finalize(_p(red), nblk, _p(gamma), _p(invstd), _p(dgamma), _p(dbeta), _p(coef), G, R, C, s),
           "bn_bwd_finalize")
     with _timed("bn_bwd_apply", _nb(dy, x, ym, dx, dres, dres_acc), f"C{C}"):
         check(lib.stfb_bn_bwd_apply(_p(dy), _p(ym), _p(x), _p(mean), _p(invstd), _p(coef), _p(shift) if from_x else None, _p(dx),
