@@ -188,6 +188,14 @@ int stfb_bn_apply(const void* x, const float* scale, const float* shift, const v
 int stfb_bn_apply_from_stats(const void* x, const float* partial, int nblk, const float* gamma, const float* beta,
                              const void* residual, void* y, int G, long long R, int C, float eps, int relu, int dtype,
                              void* stream);
+/* the stem of the training step in one pass (src/stf_lstm_unet.py:177-180: bn1 -> relu -> maxpool): y = maxpool_k,stride,pad(
+ * relu(x * scale + shift)) with scale/shift derived from the statistics slots as above, plus the uint8 window position of
+ * the first maximum (as stfb_maxpool_fwd_idx).  Values and indices equal those of stfb_bn_apply_from_stats followed by
+ * stfb_maxpool_fwd_idx (every tap is rounded to bf16 before the comparison); the full-resolution post-BN map is never
+ * written.  x [N,H,W,C] bf16, N a multiple of G groups of images, k in {2, 3}. */
+int stfb_bn_relu_maxpool_from_stats(const void* x, const float* partial, int nblk, const float* gamma, const float* beta, void* y,
+                                    unsigned char* idx, int G, int N, int H, int W, int C, int Ho, int Wo, int k, int stride,
+                                    int pad, float eps, int dtype, void* stream);
 /* backward, step 1: dz = dy * (y > 0 if relu); partial[blk][0][g][c] = sum dz, partial[blk][1][g][c] = sum dz*xhat */
 /* relu: the ReLU mask is y > 0; with y == NULL it is recomputed as fma(x, scale, shift) > 0 from the forward's scale and
  * shift (saves the read of y; only valid when no residual was added before the ReLU). */

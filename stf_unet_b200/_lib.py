@@ -46,6 +46,7 @@ _SIGS = {
     "stfb_bn_finalize_train": [_vp, _i] + [_vp] * 9 + [_i, _ll, _i, _f, _f, _vp],
     "stfb_bn_fold_eval": [_vp] * 6 + [_i, _f, _vp],
     "stfb_bn_apply": [_vp] * 5 + [_i, _ll, _i, _i, _i, _vp],
+    "stfb_bn_relu_maxpool_from_stats": [_vp, _vp, _i, _vp, _vp, _vp, _vp] + [_i] * 10 + [_f, _i, _vp],
     "stfb_bn_apply_from_stats": [_vp, _vp, _i, _vp, _vp, _vp, _vp, _i, _ll, _i, _f, _i, _i, _vp],
     "stfb_bn_bwd_reduce": [_vp] * 8 + [_i, _i, _ll, _i, _i, _i, _vp],
     "stfb_bn_bwd_finalize": [_vp, _i] + [_vp] * 5 + [_i, _ll, _i, _vp],

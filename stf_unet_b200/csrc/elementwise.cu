@@ -925,6 +925,72 @@ __global__ void __launch_bounds__(256) maxpool_fwd_idx_kernel(const T* __restric
   }
 }
 
+// BatchNorm-apply + ReLU + max-pool (+ argmax index) in ONE pass over the raw conv output -- the stem of the training step
+// (src/stf_lstm_unet.py:177-180).  The post-BN map (268 MB at 128 x 128^2 x 64) is never written: the backward pass
+// recomputes the ReLU mask from x (bn_bwd, mask_from_x) and routes the pool gradient by index.  Every tap is normalised,
+// rectified and ROUNDED TO THE STORAGE TYPE before the comparison, so values, ties and indices are exactly those of
+// bn_apply followed by maxpool_fwd_idx.  One CTA serves one image (blockIdx.z): its group's scale/shift come from the
+// statistics slots by the finalize arithmetic (bn_group_coefs_to_smem).
+template <int KC>
+__global__ void __launch_bounds__(256) bn_relu_maxpool_idx_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y,
+                                                                  unsigned char* __restrict__ idx, const float* __restrict__ partial,
+                                                                  int nblk, const float* __restrict__ gamma,
+                                                                  const float* __restrict__ beta, float eps, int G, long long R,
+                                                                  int N, int H, int W, int C, int Ho, int Wo, int stride, int pad,
+                                                                  int row_groups) {
+  extern __shared__ float coef_sm[];                 // [2][C]
+  constexpr int VEC = 8;
+  const int n = blockIdx.z;
+  const int g = n / (N / G);
+  bn_group_coefs_to_smem(partial, nblk, G, C, g, R, gamma, beta, eps, nullptr, nullptr, coef_sm);
+  __syncthreads();
+  const int CVn = C / VEC;
+  const PixTile pt = make_pix_tile(CVn, Ho, Wo);
+  const unsigned per_tile = (unsigned)(pt.tw * pt.th * CVn);
+  const __nv_bfloat16* __restrict__ xn = x + (long long)n * H * W * C;
+  for (unsigned r_ = threadIdx.x; r_ < per_tile; r_ += blockDim.x) {
+    float sc[VEC], sh[VEC];
+    int cv_prev = -1;
+    for (int tg = blockIdx.y; tg < row_groups; tg += gridDim.y)     // several groups of tile rows per CTA: the
+#pragma unroll                                                    // coefficient preamble is paid once per CTA
+    for (int tr_ = 0; tr_ < MP_TPB; ++tr_) {
+      int oy, ox, cv;
+      if (!tile_slot(r_, (unsigned)CVn, pt, tg * MP_TPB + tr_, Ho, Wo, oy, ox, cv)) continue;
+      if (cv != cv_prev) {
+#pragma unroll
+        for (int j = 0; j < VEC; ++j) { sc[j] = coef_sm[cv * VEC + j]; sh[j] = coef_sm[C + cv * VEC + j]; }
+        cv_prev = cv;
+      }
+      float v[KC * KC][VEC];
+      bool ok[KC * KC];
+#pragma unroll
+      for (int t = 0; t < KC * KC; ++t) {
+        const int iy = oy * stride - pad + t / KC, ix = ox * stride - pad + t % KC;
+        ok[t] = iy >= 0 && iy < H && ix >= 0 && ix < W;
+        const long long off = ok[t] ? ((long long)iy * W + ix) * C : 0;
+        ldv<VEC>(xn + off + cv * VEC, v[t]);
+      }
+      float best[VEC];
+      int arg[VEC];
+#pragma unroll
+      for (int j = 0; j < VEC; ++j) { best[j] = -INFINITY; arg[j] = -1; }
+#pragma unroll
+      for (int t = 0; t < KC * KC; ++t)
+#pragma unroll
+        for (int j = 0; j < VEC; ++j) {
+          const float a = __bfloat162float(__float2bfloat16_rn(fmaxf(fmaf(v[t][j], sc[j], sh[j]), 0.f)));
+          if (ok[t] && (a > best[j] || arg[j] < 0)) { best[j] = a; arg[j] = t; }
+        }
+      const long long oo = (((long long)n * Ho + oy) * Wo + ox) * C + cv * VEC;
+      stv<VEC>(y + oo, best);
+      uint2 pk;
+      pk.x = (unsigned)arg[0] | ((unsigned)arg[1] << 8) | ((unsigned)arg[2] << 16) | ((unsigned)arg[3] << 24);
+      pk.y = (unsigned)arg[4] | ((unsigned)arg[5] << 8) | ((unsigned)arg[6] << 16) | ((unsigned)arg[7] << 24);
+      *reinterpret_cast<uint2*>(idx + oo) = pk;
+    }
+  }
+}
+
 // gather form: input element (iy, ix) belongs to at most WMAX x WMAX windows (WMAX = ceil(k / stride)); their index words
 // and dy vectors are all loaded up front (the branchy form waited on idx before it asked for dy: a dependent chain).
 template <typename T, int VEC, int WMAX>
@@ -1635,6 +1701,34 @@ extern "C" int stfb_maxpool_fwd_idx(const void* x, void* y, unsigned char* idx, 
   });
 #undef MP_FWD
   return post_launch("maxpool_fwd_idx");
+}
+
+extern "C" int stfb_bn_relu_maxpool_from_stats(const void* x, const float* partial, int nblk, const float* gamma, const float* beta,
+                                              void* y, unsigned char* idx, int G, int N, int H, int W, int C, int Ho, int Wo, int k,
+                                              int stride, int pad, float eps, int dtype, void* stream) {
+  STFB_REQUIRE(x && partial && gamma && beta && y && idx && G > 0 && N >= 0 && H > 0 && W > 0 && C > 0 && stride > 0 && pad >= 0,
+               "bn_relu_maxpool_from_stats: bad arguments");
+  STFB_REQUIRE(dtype == STFB_BF16 && C % 8 == 0 && (k == 2 || k == 3) && 2 * pad <= k, "bn_relu_maxpool_from_stats: bf16, C %% 8 == 0, k in {2, 3}");
+  STFB_REQUIRE(nblk >= 1 && nblk <= 8, "bn_relu_maxpool_from_stats: 1..8 statistics slots (got %d)", nblk);
+  STFB_REQUIRE(N % G == 0 && N <= 65535, "bn_relu_maxpool_from_stats: N (%d) must be a multiple of G (%d) and <= 65535", N, G);
+  STFB_REQUIRE(Ho == (H + 2 * pad - k) / stride + 1 && Wo == (W + 2 * pad - k) / stride + 1, "bn_relu_maxpool_from_stats: bad output size");
+  STFB_REQUIRE(aligned_to(x, 16) && aligned_to(y, 16) && aligned_to(idx, 8), "bn_relu_maxpool_from_stats: unaligned buffers");
+  STFB_REQUIRE((size_t)2 * C * sizeof(float) <= 48 * 1024, "bn_relu_maxpool_from_stats: too many channels (%d)", C);
+  STFB_DEVICE_OR_RETURN();
+  if (N == 0) return STFB_OK;
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  const PixTile ptile = make_pix_tile(C / 8, Ho, Wo);
+  const unsigned gy = (unsigned)((ptile.tiles_h + MP_TPB - 1) / MP_TPB);
+  STFB_REQUIRE(gy <= 65535, "bn_relu_maxpool_from_stats: output too tall (%d rows)", Ho);
+  const dim3 grid((unsigned)ptile.tiles_w, gy > 1 ? (gy + 1) / 2 : 1, (unsigned)N);
+  const size_t sm = (size_t)2 * C * sizeof(float);
+  const long long R = (long long)(N / G) * H * W;
+  const int row_groups = (int)gy;
+  if (k == 3)
+    bn_relu_maxpool_idx_kernel<3><<<grid, 256, sm, s>>>((const __nv_bfloat16*)x, (__nv_bfloat16*)y, idx, partial, nblk, gamma, beta, eps, G, R, N, H, W, C, Ho, Wo, stride, pad, row_groups);
+  else
+    bn_relu_maxpool_idx_kernel<2><<<grid, 256, sm, s>>>((const __nv_bfloat16*)x, (__nv_bfloat16*)y, idx, partial, nblk, gamma, beta, eps, G, R, N, H, W, C, Ho, Wo, stride, pad, row_groups);
+  return post_launch("bn_relu_maxpool_from_stats");
 }
 
 extern "C" int stfb_maxpool_bwd_idx(const unsigned char* idx, const void* dy, void* dx, int N, int H, int W, int C, int Ho, int Wo,

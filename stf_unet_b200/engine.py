@@ -24,6 +24,7 @@ USE_FUSED_BN_STATS = _os.environ.get("STFB_NO_FUSED_BN_STATS", "0") != "1"
 USE_LSTM_STREAMS = _os.environ.get("STFB_NO_LSTM_STREAMS", "0") != "1"
 USE_WGRAD_STREAM = _os.environ.get("STFB_NO_WGRAD_STREAM", "0") != "1"
 USE_SIDE_FINALIZE = _os.environ.get("STFB_NO_SIDE_FINALIZE", "0") != "1"
+USE_FUSED_STEM = _os.environ.get("STFB_NO_FUSED_STEM", "0") != "1"
 
 
 class Var:
@@ -354,6 +355,52 @@ class Executor:
             x.grad = dx
             if want_dres:
                 residual.grad = dres
+
+        self.tape.append(bwd)
+        return out
+
+    def bn_relu_pool(self, x: Var, prefix: str, G: int, k: int, stride: int, pad: int) -> Var:
+        """Train-mode BatchNorm2d -> ReLU -> MaxPool2d(k, stride, pad) of a raw conv output (the stem).  bf16 with the
+        statistics in the conv epilogue's slots: ONE pass, the full-resolution post-BN map is never written (the backward pass
+        recomputes the ReLU mask from x and routes the pool gradient by index); otherwise the two-launch route."""
+        N, H, W, C = x.data.shape
+        sums = x.bn_partial
+        fusable = (USE_FUSED_STEM and self.train and sums is not None and sums.shape[0] <= 8 and x.data.dtype == torch.bfloat16
+                   and C % 8 == 0 and N % G == 0 and N <= 65535 and k in (2, 3) and 2 * C * 4 <= 48 * 1024)
+        if not fusable:
+            return self.maxpool(self.bn(x, prefix, G, True), k, stride, pad)
+        x.bn_partial = None
+        R = (N // G) * H * W
+        P = self.params
+        st = torch.empty((4, G, C), dtype=torch.float32, device=x.data.device)
+        cur = torch.cuda.current_stream()
+        side = Executor._fin_streams.get(cur.device.index)
+        if side is None:
+            side = Executor._fin_streams[cur.device.index] = torch.cuda.Stream(device=cur.device)
+        side.wait_stream(cur)
+        with torch.cuda.stream(side):        # running statistics + the coefficients the backward pass reads
+            ops.bn_finalize_train(sums, P[prefix + ".weight"], P[prefix + ".bias"], P[prefix + ".running_mean"],
+                                  P[prefix + ".running_var"], P[prefix + ".num_batches_tracked"], G, R, C, BN_EPS, BN_MOMENTUM,
+                                  out=st)
+        self._fin_keep.append((sums, st))
+        y, idx = ops.bn_relu_maxpool_from_stats(x.data, sums, P[prefix + ".weight"], P[prefix + ".bias"], G, k, stride, pad,
+                                                eps=BN_EPS)
+        out = Var(y, grad_dtype=self.dtype)
+        if not self.record:
+            return out
+        scratch = self.zeroed_scratch(ops.bn_bwd_scratch_floats(G, C), x.data.device) if ops.USE_FUSED_BN_BWD else None
+        in_shape = (N, H, W, C)
+
+        def bwd():
+            dy = out.grad
+            out.grad = None
+            if dy is None:
+                return
+            dfull = ops.maxpool_bwd_idx(idx, dy, in_shape, k, stride, pad)      # gradient of the (never stored) post-BN map
+            gname, bname = prefix + ".weight", prefix + ".bias"
+            dx, _ = ops.bn_bwd(dfull, None, x.data, st[2], st[3], P[gname], self.grads.get(gname), self.grads.get(bname), G, R, C,
+                               True, False, scale=st[0], shift=st[1], scratch=scratch)
+            x.grad = dx
 
         self.tape.append(bwd)
         return out

@@ -15,7 +15,7 @@ from ._lib import BF16, CONV_FWD, CONV_TRANSPOSED, F32, IMPL_AUTO, IMPL_SIMT, IM
 
 __all__ = ["dt_code", "conv2d", "conv2d_wgrad", "pack_weight", "bn_stats", "bn_finalize_train", "bn_fold_eval",
            "bn_apply", "bn_bwd", "colsum", "maxpool_fwd", "maxpool_bwd", "maxpool_fwd_idx", "maxpool_bwd_idx", "bilinear_fwd", "bilinear_bwd",
-           "tcgen05_ok", "conv_stats_fusable", "STAT_SLOTS", "im2col_small", "unpad_wgrad", "lstm_step_fused", "pack_lstm_xh", "lstm_cell_fwd", "lstm_cell_bwd", "bn_apply_from_stats", "bn_bwd_scratch_floats", "pack_series", "pack_series_u8", "adamw_flat_", "pack_series_maps", "repeat_batch", "nhwc_to_nchw", "nchw_to_nhwc", "add_", "cast",
+           "tcgen05_ok", "conv_stats_fusable", "STAT_SLOTS", "im2col_small", "unpad_wgrad", "lstm_step_fused", "pack_lstm_xh", "lstm_cell_fwd", "lstm_cell_bwd", "bn_apply_from_stats", "bn_relu_maxpool_from_stats", "bn_bwd_scratch_floats", "pack_series", "pack_series_u8", "adamw_flat_", "pack_series_maps", "repeat_batch", "nhwc_to_nchw", "nchw_to_nhwc", "add_", "cast",
            "ce_dice_fwd", "ce_dice_bwd", "CONV_FWD", "CONV_TRANSPOSED", "IMPL_AUTO", "IMPL_SIMT", "IMPL_TCGEN05"]
 
 _DT = {torch.float32: F32, torch.bfloat16: BF16}
@@ -395,6 +395,20 @@ def bn_apply_from_stats(x, partial, gamma, beta, G, R, C, relu, residual=None, o
         check(_lib.load().stfb_bn_apply_from_stats(_p(x), _p(partial), partial.shape[0], _p(gamma), _p(beta), _p(residual), _p(y),
                                                    G, R, C, eps, int(bool(relu)), dt_code(x.dtype), _stream()), "bn_apply_from_stats")
     return y
+
+
+def bn_relu_maxpool_from_stats(x, partial, gamma, beta, G, k, stride, pad, eps=1e-5):
+    """maxpool(relu(batchnorm(x))) + argmax index in one pass; scale/shift derived in-kernel from <= 8 statistics slots.
+    -> (y [N,Ho,Wo,C], idx uint8): exactly what bn_apply_from_stats + maxpool_fwd_idx give, without the full-size map."""
+    N, H, W, C_ = x.shape
+    Ho, Wo = (H + 2 * pad - k) // stride + 1, (W + 2 * pad - k) // stride + 1
+    y = torch.empty((N, Ho, Wo, C_), dtype=x.dtype, device=x.device)
+    idx = torch.empty((N, Ho, Wo, C_), dtype=torch.uint8, device=x.device)
+    with _timed("bn_relu_maxpool", _nb(x, y) + idx.numel(), f"C{C_}"):
+        check(_lib.load().stfb_bn_relu_maxpool_from_stats(_p(x), _p(partial), partial.shape[0], _p(gamma), _p(beta), _p(y), _p(idx),
+                                                          G, N, H, W, C_, Ho, Wo, k, stride, pad, eps, dt_code(x.dtype), _stream()),
+              "bn_relu_maxpool_from_stats")
+    return y, idx
 
 
 def bn_apply(x, scale, shift, G, R, C, relu, residual=None, out=None):

@@ -116,8 +116,12 @@ class STFLSTMUNet(B200Module):
         else:
             T = total
             xin = engine.Var(ops.pack_series(x, ex.dtype), needs_grad=False)  # [T*B, H, W, C] time-major
-        s = ex.conv_bn(xin, "conv1.weight", "bn1", k=7, stride=2, pad=3, relu=True, G=T)
-        e = ex.maxpool(s, 3, 2, 1)
+        if ex.train:     # stem: conv (statistics in the epilogue) -> BatchNorm + ReLU + max-pool in one pass
+            raw = ex.conv(xin, "conv1.weight", k=7, stride=2, pad=3, stats_G=T)
+            e = ex.bn_relu_pool(raw, "bn1", T, 3, 2, 1)
+        else:
+            s = ex.conv_bn(xin, "conv1.weight", "bn1", k=7, stride=2, pad=3, relu=True, G=T)
+            e = ex.maxpool(s, 3, 2, 1)
         feats = []
         for li, (c, n) in enumerate(RESNET34_LAYERS, start=1):
             for b in range(n):

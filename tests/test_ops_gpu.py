@@ -785,3 +785,29 @@ def test_adamw_flat_matches_torch_adamw(n):
     ops.adamw_flat_(p1, g, m1, v1, 1e-3, 0.9, 0.999, 1e-8, 0.0, 1, grad_scale=0.25)
     ops.adamw_flat_(p2, g * 0.25, m2, v2, 1e-3, 0.9, 0.999, 1e-8, 0.0, 1)
     assert torch.equal(p1, p2) and torch.equal(v1, v2)
+
+
+@pytest.mark.parametrize("G,B,H,W,C,k,s,p", [(2, 2, 16, 16, 64, 3, 2, 1), (3, 1, 22, 18, 32, 3, 2, 1), (1, 2, 8, 12, 16, 2, 2, 0)])
+def test_bn_relu_maxpool_one_pass_equals_two_launches(G, B, H, W, C, k, s, p):
+    """The fused stem pass (BatchNorm apply + ReLU + max-pool + argmax index from the statistics slots) gives exactly the
+    pooled values and indices of bn_apply_from_stats followed by maxpool_fwd_idx, and of torch on the same bf16 map."""
+    N = G * B
+    x = q(rnd(N, C, H, W, seed=1) * 1.5 + 0.3, torch.bfloat16)
+    xn = nhwc(x, torch.bfloat16)
+    gamma, beta = rnd(C, seed=2).abs() + 0.5, rnd(C, seed=3)
+    gamma[::3] *= -1                                    # negative scales: max-pool does not commute with the affine map
+    R = B * H * W
+    xg = xn.float().view(G, R, C)
+    slots = torch.zeros(ops.STAT_SLOTS, 2, G, C, device=DEV)
+    for sl in range(ops.STAT_SLOTS):                    # spread the rows over the eight slots like the conv epilogue does
+        part = xg[:, sl::ops.STAT_SLOTS]
+        slots[sl, 0], slots[sl, 1] = part.sum(1), (part * part).sum(1)
+    y_full = ops.bn_apply_from_stats(xn, slots, gamma, beta, G, R, C, True)
+    y2, idx2 = ops.maxpool_fwd_idx(y_full, k, s, p)
+    y1, idx1 = ops.bn_relu_maxpool_from_stats(xn, slots, gamma, beta, G, k, s, p)
+    assert torch.equal(y1, y2) and torch.equal(idx1, idx2)
+    ref = F.max_pool2d(nchw(y_full), k, s, p)
+    assert torch.equal(nchw(y1), ref)
+    # and the apply kernel's in-kernel coefficients are those of the finalize kernel
+    st = ops.bn_finalize_train(slots, gamma, beta, None, None, None, G, R, C)
+    assert torch.equal(ops.bn_apply(xn, st[0], st[1], G, R, C, True), y_full)
