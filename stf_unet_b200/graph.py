@@ -11,6 +11,9 @@ from __future__ import annotations
 import torch
 
 
+_CAPTURE_STREAMS = {}
+
+
 class GraphedStep:
     """loss = step(x, target): copies the batch into static buffers, replays fwd + loss + bwd; gradients land in the
     parameters' persistent ``.grad`` views (one flat buffer), ready for all-reduce / optimizer.step()."""
@@ -42,7 +45,18 @@ class GraphedStep:
         from . import _lib
         self.graph = torch.cuda.CUDAGraph()
         n0 = _lib.launch_count()
-        with torch.cuda.graph(self.graph):
+        # captured on a HIGH-priority stream: kernel nodes keep the priority of the stream they were captured on, and the
+        # weight-gradient side streams (default = lowest priority) then only fill the SM slots the main chain leaves free
+        from . import engine
+        # (ONE capture stream per device, shared by every GraphedStep like torch's own default capture stream: a second
+        # capture on a fresh stream fails with cudaErrorStreamCaptureIsolation in the autograd engine's stream hand-off)
+        cap_stream = None
+        if engine.MAIN_PRIO:
+            dev_index = self.x.device.index if self.x.device.index is not None else torch.cuda.current_device()
+            cap_stream = _CAPTURE_STREAMS.get(dev_index)
+            if cap_stream is None:
+                cap_stream = _CAPTURE_STREAMS[dev_index] = torch.cuda.Stream(device=self.x.device, priority=engine.MAIN_PRIO)
+        with torch.cuda.graph(self.graph, stream=cap_stream):
             self.loss = fwd_bwd()
         self.launches_per_replay = _lib.launch_count() - n0      # libstfb200 kernels inside the captured graph
         self.flat_grad = model._last_flat_grad
