@@ -161,6 +161,23 @@ class Executor:
 
     _wg_streams = {}
 
+    def side_launch(self, keep, fn):
+        """Run fn() -- launches whose results only the optimizer reads (weight / bias gradients) -- on one of the
+        low-priority side streams forked from the current stream (bf16 path; otherwise inline).  `keep`: the tensors the
+        launches read, kept alive until the join at the end of the backward pass (their Python owners drop them earlier
+        and the caching allocator would hand the memory to the main stream)."""
+        if USE_WGRAD_STREAM and self.dtype == torch.bfloat16 and keep[0].is_cuda:
+            cur = torch.cuda.current_stream()
+            pool = Executor._wg_streams.get(cur.device.index)
+            if pool is None:
+                pool = Executor._wg_streams[cur.device.index] = [torch.cuda.Stream(device=cur.device) for _ in range(max(1, WGRAD_STREAMS))]
+            side = pool[len(self._wg_keep) % len(pool)]
+            side.wait_stream(cur)
+            self._wg_keep.append(keep)
+            with torch.cuda.stream(side):
+                return fn()
+        return fn()
+
     def wgrad(self, wname, P, G, k, stride, pad, cg_off=0, cg_total=None):
         """Weight gradient of `wname`; tcgen05 launches accumulate in the side buffer and are folded in once, at the
         end of the backward pass (Executor.backward).
@@ -170,20 +187,8 @@ class Executor:
         memory per SM) then share the SMs with the memory-bound BatchNorm-backward kernels of the main chain instead of
         alternating with them.  P and G are kept alive until the join at the end of the backward pass."""
         acc = self.acc.get(wname)
-        side = None
-        if USE_WGRAD_STREAM and self.dtype == torch.bfloat16 and P.is_cuda:
-            cur = torch.cuda.current_stream()
-            pool = Executor._wg_streams.get(cur.device.index)
-            if pool is None:
-                pool = Executor._wg_streams[cur.device.index] = [torch.cuda.Stream(device=cur.device) for _ in range(max(1, WGRAD_STREAMS))]
-            side = pool[len(self._wg_keep) % len(pool)]
-            side.wait_stream(cur)
-            self._wg_keep.append((P, G))
-        if side is not None:
-            with torch.cuda.stream(side):
-                deferred = ops.conv2d_wgrad(P, G, self.grads[wname], k, stride, pad, cg_off, cg_total, acc=acc)
-        else:
-            deferred = ops.conv2d_wgrad(P, G, self.grads[wname], k, stride, pad, cg_off, cg_total, acc=acc)
+        deferred = self.side_launch((P, G), lambda: ops.conv2d_wgrad(P, G, self.grads[wname], k, stride, pad, cg_off, cg_total,
+                                                                     acc=acc))
         if deferred:
             w = self.params[wname]
             khw = 1 if w.dim() == 2 else w.shape[2] * w.shape[3]
@@ -248,7 +253,7 @@ class Executor:
                 return
             rows = dy.shape[0] * dy.shape[1] * dy.shape[2]
             if bname and self.wants_grad(bname):
-                ops.colsum(dy, self.grads[bname], rows, Cout)
+                self.side_launch((dy,), lambda: ops.colsum(dy, self.grads[bname], rows, Cout))
             if self.wants_grad(wname):
                 if not transposed:
                     self.wgrad(wname, dy, x.data, k, stride, pad, 0, C1 + C2)
@@ -299,11 +304,14 @@ class Executor:
             if dy is None:
                 return
             if bname and self.wants_grad(bname):
-                ops.colsum(dy, self.grads[bname], dy.shape[0] * dy.shape[1] * dy.shape[2], Cout)
+                self.side_launch((dy,), lambda: ops.colsum(dy, self.grads[bname], dy.shape[0] * dy.shape[1] * dy.shape[2], Cout))
             if self.wants_grad(wname):
-                scratch = torch.zeros((Cout, kpad), dtype=torch.float32, device=dy.device)
-                ops.conv2d_wgrad(dy, col, scratch, 1, 1, 0, 0, kpad)
-                ops.unpad_wgrad(self.grads[wname], scratch)
+                def small_wgrad():
+                    scratch = torch.zeros((Cout, kpad), dtype=torch.float32, device=dy.device)
+                    ops.conv2d_wgrad(dy, col, scratch, 1, 1, 0, 0, kpad)
+                    ops.unpad_wgrad(self.grads[wname], scratch)
+                    self._wg_keep.append((scratch,))
+                self.side_launch((dy, col), small_wgrad)
 
         self.tape.append(bwd)
         return out
@@ -520,12 +528,14 @@ class Executor:
             if self.wants_grad(whh) and T > 1:
                 self.wgrad(whh, dG[1:].reshape((T - 1) * B, h, w, 4 * C), hs[:T - 1].reshape((T - 1) * B, h, w, C), 1, 1, 0)
             # d b_ih == d b_hh == column sums of dG: reduce once, add the (tiny) result into the second bias
-            if self.wants_grad(bih):
-                ops.colsum(dG_all, self.grads[bih], T * R, 4 * C)
-                if self.wants_grad(bhh):
-                    ops.add_(self.grads[bhh], self.grads[bih])
-            elif self.wants_grad(bhh):
-                ops.colsum(dG_all, self.grads[bhh], T * R, 4 * C)
+            def bias_grads():
+                if self.wants_grad(bih):
+                    ops.colsum(dG_all, self.grads[bih], T * R, 4 * C)
+                    if self.wants_grad(bhh):
+                        ops.add_(self.grads[bhh], self.grads[bih])
+                elif self.wants_grad(bhh):
+                    ops.colsum(dG_all, self.grads[bhh], T * R, 4 * C)
+            self.side_launch((dG_all,), bias_grads)        # only the optimizer reads them: off the LSTM chain
             if seq.needs_grad:
                 tca = self.use_tc(dG_all, C, 1, 1, 0)
                 seq.grad = ops.conv2d(dG_all, self.packed(wih, False, n_major=tca), C, 1, 1, 0, residual=seq.grad,
