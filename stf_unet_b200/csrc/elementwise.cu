@@ -641,14 +641,14 @@ __global__ void __launch_bounds__(256, 2) bn_bwd_fused_kernel(const T* __restric
     for (int t = tid; t < tpr * VEC; t += 256) {
       const int ccl = t / VEC, j = t - ccl * VEC;
       if (cv0 + ccl < CVn) {
-        float ds = 0.f, dq = 0.f;
+        double ds = 0.0, dq = 0.0;
         for (int l = 0; l < lanes; ++l) {
-          ds += red[((l * tpr + ccl) * VEC + j) * 2];
-          dq += red[((l * tpr + ccl) * VEC + j) * 2 + 1];
+          ds += (double)red[((l * tpr + ccl) * VEC + j) * 2];
+          dq += (double)red[((l * tpr + ccl) * VEC + j) * 2 + 1];
         }
         const int c = (cv0 + ccl) * VEC + j;
-        atomicAdd(accs + c, ds);
-        atomicAdd(accs + C + c, dq);
+        atomicAdd(accs + c, (float)ds);
+        atomicAdd(accs + C + c, (float)dq);
       }
     }
     __syncthreads();

@@ -351,7 +351,10 @@ class Executor:
             return out
         mean, invstd = st[2], st[3]
         # zeroed now (one arena fill per forward), consumed by the one-launch backward
-        scratch = self.zeroed_scratch(ops.bn_bwd_scratch_floats(G, C), x.data.device) if ops.USE_FUSED_BN_BWD else None
+        # (bf16 path only: the fp32-accurate path keeps the three-launch chain with its fp64 slot sums -- the one-launch
+        # kernel meets its group sums through fp32 atomics, which tiny-batch BatchNorm amplifies beyond the fp32 bars)
+        scratch = (self.zeroed_scratch(ops.bn_bwd_scratch_floats(G, C), x.data.device)
+                   if ops.USE_FUSED_BN_BWD and self.dtype == torch.bfloat16 else None)
 
         def bwd():
             dy = out.grad
