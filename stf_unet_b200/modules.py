@@ -108,7 +108,18 @@ class B200Module(nn.Module):
         plans = self.__dict__.setdefault("_pack_plans", {})
         plan = plans.get((ex.dtype, self.training, record))
         if plan is not None and plan.valid_for(ex.params, ex.dtype):
-            ex._packed = plan.run()
+            # inference (eval mode, no tape): the fp32 masters do not move between forwards, so the packed operands are
+            # reused until a parameter changes -- torch-side updates bump Parameter._version, FlatAdamW (a raw-pointer
+            # kernel) bumps the module's _pack_epoch.  0.23 ms of a 2.7 ms inference step.  A CUDA graph captured in this
+            # mode therefore bakes the weights of capture time in (a training-mode graph re-packs on every replay).
+            stamp = None
+            if not self.training and not record:
+                stamp = (self.__dict__.get("_pack_epoch", 0), tuple(p._version for _, p in named))
+            if stamp is not None and getattr(plan, "stamp", None) == stamp:
+                ex._packed = dict(plan.buffers)
+            else:
+                ex._packed = plan.run()
+                plan.stamp = stamp
         else:
             plans.pop((ex.dtype, self.training, record), None)
         return ex

@@ -63,6 +63,9 @@ class FlatAdamW(torch.optim.Optimizer):
         self.steps += 1
         ops.adamw_flat_(self.flat_param, self._flat_grad(), self.exp_avg, self.exp_avg_sq, grp["lr"], grp["betas"][0],
                         grp["betas"][1], grp["eps"], grp["weight_decay"], self.steps, self.grad_scale)
+        # the kernel writes through raw pointers (no Parameter._version bump): tell the module its cached eval-mode weight
+        # packs are stale
+        self.model.__dict__["_pack_epoch"] = self.model.__dict__.get("_pack_epoch", 0) + 1
         return loss
 
     # ---- checkpointing: one flat state instead of per-parameter dicts ------------------------------------------

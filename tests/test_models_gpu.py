@@ -526,3 +526,40 @@ def test_flat_adamw_training_matches_torch_adamw():
     oc = S.FlatAdamW(load_model(S.STFLSTMUNet(1, 2, 2), mb.state_dict()), lr=1.0)
     oc.load_state_dict(st)
     assert oc.steps == 3 and torch.equal(oc.exp_avg, ob.exp_avg) and oc.param_groups[0]["lr"] == ob.param_groups[0]["lr"]
+
+
+def test_eval_weight_packs_are_cached_until_a_parameter_changes():
+    """Eval-mode forwards reuse the packed bf16 operands (no pack launch) until a weight moves: torch-side updates are seen
+    through Parameter._version, the raw-pointer FlatAdamW step through the module's pack epoch."""
+    from stf_unet_b200 import _lib
+    x, t = W.synthetic_dce_batch(2, 2, 64, 64, seed=81)
+    x, t = x.to(DEV), t.to(DEV)
+    m = load_model(S.STFLSTMUNet(1, 2, 2), warm_stf_state()).eval()
+
+    def fwd():
+        n0 = _lib.launch_count()
+        with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16):
+            y = m(x)["out"]
+        return y, _lib.launch_count() - n0
+
+    fwd()                                   # learns the pack plan
+    y1, n1 = fwd()                          # packs through the plan
+    y2, n2 = fwd()                          # reuses
+    assert n2 == n1 - 1 and torch.equal(y1, y2)
+    with torch.no_grad():
+        m.final.bias.add_(1.0)              # torch-side update: version bump
+    y3, n3 = fwd()
+    assert n3 == n1 and rel(y3, y1 + 1.0) < 1e-3
+    opt = S.FlatAdamW(m, lr=1e-2, weight_decay=0.0)      # re-homes the parameters (new addresses: plan rebuilt)
+    fwd(); fwd()
+    y4, n4 = fwd()
+    assert n4 == n1 - 1
+    m.train()
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        S.criterion(m(x), t).backward()
+    opt.step()                              # raw-pointer update
+    m.eval()
+    y5, n5 = fwd()
+    assert n5 == n1 and not torch.equal(y5, y4)
+    y6, n6 = fwd()
+    assert n6 == n1 - 1 and torch.equal(y6, y5)
