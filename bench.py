@@ -30,6 +30,26 @@ T_PHASES, HW, BATCH_PER_GPU = 8, 256, 16
 TRAIN_GFLOP_PER_SLICE = 259.35        # BASELINE.md section 3 (fwd + dgrad + wgrad, conv + LSTM GEMMs)
 
 
+_JSON_OUT = None
+
+
+def claim_stdout():
+    """stdout carries exactly ONE JSON line.  Libraries write to file descriptor 1 behind Python's back (NCCL prints its
+    version banner there at communicator creation, more with NCCL_DEBUG=INFO): keep a private duplicate of the real stdout
+    for the JSON line and point descriptor 1 at stderr for everything else."""
+    global _JSON_OUT
+    if _JSON_OUT is None:
+        sys.stdout.flush()
+        _JSON_OUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
+
+def emit(line):
+    out = _JSON_OUT if _JSON_OUT is not None else sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 def peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -129,7 +149,7 @@ def run_reference(args, rank):
             "cpu_baseline": {"value": round(val, 4), "unit": "slices/s", "cores": threads, "kind": "port", "sample": sample},
             "e2e": {"value": round(val, 4), "unit": "slices/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 CONFIG_NOTE = "BASELINE.json configs[2] = global batch 128 on 8 GPUs"
@@ -385,7 +405,7 @@ def run_own(args, rank, world, local_rank):
                 "e2e_u8": e2e_u8, "gpu_launches": int(launches),
                 "model_tflops": round(model_tflops, 2), "model_frac_of_bf16_peak": round(model_tflops / world / pk["tflops"], 4),
                 "loss_check": loss_check, "roofline": roof, "cpu_baseline": cpu}
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
@@ -480,7 +500,7 @@ def run_infer(args, rank, world, local_rank):
                         "ms_per_step": round(e2e_ms, 3)},
                 "gpu_launches": int(per_replay * args.steps), "model_tflops": round(tf, 2),
                 "model_frac_of_bf16_peak": round(tf / world / pk["tflops"], 4), "roofline": None, "cpu_baseline": None}
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
@@ -561,7 +581,7 @@ def run_volume(args, rank, world, local_rank):
                         "ms_per_step": round(e2e_ms, 3)},
                 "gpu_launches": int(pred.launches_per_replay * replays), "model_tflops": round(tf, 2),
                 "model_frac_of_bf16_peak": round(tf / world / pk["tflops"], 4), "roofline": None, "cpu_baseline": None}
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
@@ -579,6 +599,7 @@ def main():
                     help="train = BASELINE.json configs[2] sharded 16/GPU (the headline metric); infer = configs[1], eval forward; "
                          "train512 = configs[3] (T=16 x 512x512, 8 slices/GPU); volume = configs[4] (160-slice case, sharded by slice)")
     args = ap.parse_args()
+    claim_stdout()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
