@@ -570,14 +570,13 @@ __global__ void __launch_bounds__(256, 2) bn_bwd_fused_kernel(const T* __restric
   const int tid = threadIdx.x;
   const int lanes = 256 / tpr;
   const int cl = tid % tpr, rl = tid / tpr;
-  const int g = blockIdx.y, G = gridDim.y;
+  const int g = blockIdx.y;
   const int CVn = C / VEC;
   const long long r0 = (long long)blockIdx.x * rows_per_block;
   const long long r1 = min(R, r0 + rows_per_block);
   const long long gbase = (long long)g * R;
   const bool mask_from_x = relu && y == nullptr;
   float* accs = acc + (long long)g * 2 * C;          // [2][C] of this group
-  (void)G;
 
   // ---------------- phase 1: partial sums over this CTA's rows ----------------
   for (int cv0 = 0; cv0 < CVn; cv0 += tpr) {
@@ -1422,12 +1421,9 @@ __global__ void __launch_bounds__(IM_PIX) im2col_tiled_kernel(const __nv_bfloat1
 #pragma unroll
       for (int wd = 0; wd < 32; ++wd) {
         uint32_t lo = 0u, hi = 0u;
-        {
-          constexpr int dummy = 0; (void)dummy;
-          const int k0 = seg * 64 + 2 * wd, k1 = k0 + 1;
-          if (k0 < KTOT) { const int tap = k0 / CINC, ci = k0 % CINC; lo = pb[(tap / KC) * ROW + (tap % KC) * CINC + ci]; }
-          if (k1 < KTOT) { const int tap = k1 / CINC, ci = k1 % CINC; hi = pb[(tap / KC) * ROW + (tap % KC) * CINC + ci]; }
-        }
+        const int k0 = seg * 64 + 2 * wd, k1 = k0 + 1;          // compile-time after unrolling: every offset is an immediate
+        if (k0 < KTOT) { const int tap = k0 / CINC, ci = k0 % CINC; lo = pb[(tap / KC) * ROW + (tap % KC) * CINC + ci]; }
+        if (k1 < KTOT) { const int tap = k1 / CINC, ci = k1 % CINC; hi = pb[(tap / KC) * ROW + (tap % KC) * CINC + ci]; }
         wv[wd] = lo | (hi << 16);
       }
 #pragma unroll
