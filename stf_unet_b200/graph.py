@@ -1,6 +1,6 @@
 """CUDA-graph capture of the hot path: forward + criterion + backward as ONE graph launch.
 
-A training step of STF-LSTM-UNet is ~590 kernel launches; enqueueing them from Python costs ~14 ms of host time per
+A training step of STF-LSTM-UNet is ~480 kernel launches; enqueueing them from Python costs ~14 ms of host time per
 step, which is more than the GPU needs once the kernels are fast.  Every libstfb200 launch is capture-safe (no host
 syncs, no allocation, tensor maps are by-value kernel parameters), so the whole step is captured once and replayed.
 The optimizer and the data-parallel all-reduce stay outside the graph (a handful of launches) so the same object
