@@ -111,3 +111,32 @@ def test_volume_slice_ranges_partition_the_case():
     assert slice_range(160, 3, 8) == (60, 80)
     with pytest.raises(ValueError):
         slice_range(10, 2, 2)
+
+
+def test_header_is_plain_c_and_a_c_program_links_against_the_library(tmp_path):
+    """The drop-in boundary is a C ABI: include/stfb200.h must compile as C99 and as C++, and a plain C program must link
+    against libstfb200.so and reach the no-device error path (no torch, no Python in between)."""
+    import shutil
+    import subprocess
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("no gcc")
+    hdr = os.path.join(ROOT, "include", "stfb200.h")
+    subprocess.run([gcc, "-x", "c", "-std=c99", "-fsyntax-only", "-Wall", "-Werror", hdr], check=True)
+    gxx = shutil.which("g++")
+    if gxx:
+        subprocess.run([gxx, "-x", "c++", "-fsyntax-only", hdr], check=True)
+    src = tmp_path / "abi.c"
+    src.write_text('#include <stdio.h>\n#include "stfb200.h"\n'
+                   'int main(void) {\n'
+                   '  if (stfb_version() < 100) return 2;\n'
+                   '  int st = stfb_maxpool_fwd(0, 0, 1, 4, 4, 4, 2, 2, 2, 2, 0, 0, 0);   /* null pointers: argument error */\n'
+                   '  printf("%d %s\\n", st, stfb_last_error());\n'
+                   '  return st == STFB_EINVAL ? 0 : 3;\n}\n')
+    exe = tmp_path / "abi"
+    libdir = os.path.join(ROOT, "stf_unet_b200")
+    subprocess.run([gcc, "-std=c99", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe), "-L", libdir,
+                    "-l:libstfb200.so", "-Wl,-rpath," + libdir], check=True)
+    r = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert r.returncode == 0, (r.returncode, r.stdout, r.stderr)
+    assert "maxpool_fwd" in r.stdout
