@@ -2,6 +2,7 @@
 // max-pool, bilinear resize, LSTM cell update, layout adapters.  All NHWC, 4-wide vector accesses along the
 // channel axis when C % 4 == 0, warp-shuffle-free smem column reductions with fp64 global accumulation.
 #include "common.cuh"
+#include <stdlib.h>
 
 namespace stfb {
 
@@ -1511,7 +1512,11 @@ static RowTile row_tile(int G, long long R, int C, int vec, int unroll) {
   while (tpr * 2 <= CVn && tpr * 2 <= 256) tpr *= 2;
   t.tpr = tpr;
   const long long lanes = 256 / tpr;
-  long long want = (8LL * num_sms() + G - 1) / G;
+  // CTAs per SM the grid is sized for: 4 = one resident wave (the kernels hold 4 CTAs of 256 threads per SM), so the
+  // per-CTA coefficient preamble is paid once per SM slot; measured on the graph step: 4 -> 9.85 ms, 8 -> 9.93, 16 -> 9.97
+  static int per_sm = 0;
+  if (per_sm == 0) { const char* e = getenv("STFB_ROWTILE_CTAS_PER_SM"); per_sm = e ? atoi(e) : 4; if (per_sm < 1 || per_sm > 64) per_sm = 4; }
+  long long want = ((long long)per_sm * num_sms() + G - 1) / G;
   long long cap = (R + lanes * unroll * 2 - 1) / (lanes * unroll * 2);
   long long nblk = want < cap ? want : cap;
   if (nblk < 1) nblk = 1;
