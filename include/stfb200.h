@@ -303,7 +303,7 @@ int stfb_pack_series_maps(const float* x, const float* maps, void* y, int B, int
                           void* stream);
 /* Device-side input pipeline: 8-bit series x [B, T, H, W] -> y [T*B, H, W, 1] dtype with
  * the loader's arithmetic fused in, ((x / 255) - mean) / std, operation for operation as ToTensor + Normalize do it
- * (/root/reference/transforms.py, train.py:147-148: mean 0.709, std 0.127), so the fp32 result is bit-identical. */
+ * (/root/reference/transforms.py:120-134, train.py:147-148: mean 0.709, std 0.127), so the fp32 result is bit-identical. */
 int stfb_pack_series_u8(const unsigned char* x, void* y, int B, int T, int H, int W, float mean, float std_, int dtype,
                         void* stream);
 /* dst = `times` back-to-back copies of src (bytes each): a per-sample map repeated for every time step */

@@ -1,7 +1,7 @@
 // The two steps either side of the hot path, both pure HBM streaming:
 //
 //  * stfb_pack_series_u8: the reference's loader turns 8-bit grey images into normalised fp32 tensors on the CPU, one PIL
-//    image per phase (/root/reference/my_dataset.py:143-232, transforms.py ToTensor + Normalize, train.py:147-148) and the
+//    image per phase (/root/reference/my_dataset.py:143-232, transforms.py:120-134 ToTensor + Normalize, train.py:147-148) and the
 //    model then re-lays them out.  Here the uint8 series [B,T,H,W] goes to the device as it is (a quarter of the fp32
 //    bytes over PCIe) and ONE pass does x/255 -> (v - mean)/std -> dtype, written straight in the encoder's time-major
 //    NHWC order [T*B, H, W, 1].  The arithmetic is the reference's, operation for operation (IEEE division, no
