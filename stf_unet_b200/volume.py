@@ -1,7 +1,9 @@
 """Whole-volume tumour-mask inference (BASELINE.json configs[4]; SURVEY.md section 8(e) "inference partitioning").
 
-The reference segments a case slice by slice (/root/reference/test.py:150-186: one ``model(image)`` + ``argmax`` per
-slice, masks written as 8-bit images).  Here a case is a ``[S, T, 1, H, W]`` series in (pinned) host memory; its
+The reference walks the test set one slice per ``model(inputs)`` call (``DataLoader(batch_size=1)``,
+/root/reference/test.py:156-175; its overlay images threshold ``sigmoid`` of channel 0) and scores it with the argmax
+masks of ``evaluate`` (train_utils/train_and_eval.py:322-336).  The product here is the argmax mask of every slice as
+uint8.  A case is a ``[S, T, 1, H, W]`` series in (pinned) host memory; its
 slices are independent, so rank r of N takes one contiguous range of slices (no collective on the data path) and
 pushes it through the eval-mode forward in fixed-size batches:
 
