@@ -115,41 +115,152 @@ def make_batch(rank, batch=None, T=None, hw=None):
 
 
 # ------------------------------------------------------------------------------------------------
-# reference arm / cpu baseline: the oracle (CPU restatement of the reference) on the host cores
+# reference arm / cpu baseline: the UNMODIFIED reference modules (baseline/_ref, installed by tools/install_ref.sh; it
+# travels to the GPU box) on the host cores; the oracle port only when that install is missing
 # ------------------------------------------------------------------------------------------------
-def cpu_train_step_time(batch, iters, warmup, threads=None):
-    from oracle import stf_oracle as O
-    from oracle import weights as W
+def reference_root():
+    for p in (os.path.join(ROOT, "baseline", "_ref"), "/root/reference"):
+        if os.path.isdir(os.path.join(p, "src")) and os.path.isdir(os.path.join(p, "train_utils")):
+            return p
+    return None
+
+
+_REF = None
+
+
+def import_reference():
+    """-> namespace with the reference's STFLSTMUNet, UNet, criterion, train_one_epoch, evaluate (or None)."""
+    global _REF
+    if _REF is None:
+        root = reference_root()
+        if root is None:
+            _REF = False
+        else:
+            sys.dont_write_bytecode = True
+            if root not in sys.path:
+                sys.path.insert(0, root)
+            import types
+            from src import STFLSTMUNet, UNet                                  # noqa: E402  (the reference's own package)
+            from train_utils import train_and_eval as te                        # noqa: E402
+            _REF = types.SimpleNamespace(root=root, STFLSTMUNet=STFLSTMUNet, UNet=UNet, criterion=te.criterion,
+                                         train_one_epoch=te.train_one_epoch, evaluate=te.evaluate,
+                                         create_lr_scheduler=te.create_lr_scheduler)
+    return _REF or None
+
+
+def cpu_train_step_time(batch, iters, warmup, threads=None, workload="train"):
+    """Seconds per training step (fwd + criterion + bwd + AdamW) of the reference on the host cores -> (times, threads, kind)."""
     threads = threads or os.cpu_count()
     torch.set_num_threads(threads)
-    sd = W.make_state_dict(W.stf_param_spec(1, 2), seed=0)
-    x, t = make_batch(0, batch=batch)
+    ref = import_reference()
+    if workload == "unet":
+        from stf_unet_b200.synthetic import synthetic_dce_batch
+        x, t = synthetic_dce_batch(batch, 1, HW, HW, seed=1234, half_res_target=False)
+        x = x[:, 0]                                                             # [B, 1, H, W]
+    else:
+        x, t = make_batch(0, batch=batch)
     times = []
+    if ref is not None:
+        torch.manual_seed(0)
+        model = (ref.UNet(1, 2, 64) if workload == "unet" else ref.STFLSTMUNet(1, 2, T_PHASES)).train()
+        opt = torch.optim.AdamW(model.parameters(), lr=1e-3, weight_decay=1e-4)
+        for i in range(warmup + iters):
+            t0 = time.perf_counter()
+            loss = ref.criterion(model(x), t)
+            opt.zero_grad()
+            loss.backward()
+            opt.step()
+            dt = time.perf_counter() - t0
+            if i >= warmup:
+                times.append(dt)
+        return times, threads, "reference"
+    from oracle import stf_oracle as O
+    from oracle import weights as W
+    sd = W.make_state_dict(W.unet_param_spec(1, 2, 64) if workload == "unet" else W.stf_param_spec(1, 2), seed=0)
     for i in range(warmup + iters):
         t0 = time.perf_counter()
-        O.loss_and_grads(sd, x, t, model="stf", train=True)
+        O.loss_and_grads(sd, x, t, model="unet" if workload == "unet" else "stf", train=True)
         dt = time.perf_counter() - t0
         if i >= warmup:
             times.append(dt)
-    return times, threads
+    return times, threads, "port"
 
 
 def run_reference(args, rank):
     if rank != 0:
         return
-    batch = 2 if HW <= 256 else 1
-    times, threads = cpu_train_step_time(batch, args.steps, args.warmup)
+    unet = args.workload == "unet"
+    batch = 4 if unet else (2 if HW <= 256 else 1)
+    times, threads, kind = cpu_train_step_time(batch, args.steps, args.warmup, workload="unet" if unet else "train")
     ms = 1000.0 * sum(times) / len(times)
     val = batch / (ms / 1000.0)
-    sample = f"fwd+CE/Dice+bwd of B={batch} slices (T={T_PHASES}, {HW}x{HW}) per step, fp32, oracle port of the reference"
-    line = {"impl": "reference", "metric": "train slices/s STF-LSTM-UNet", "value": round(val, 4), "unit": "slices/s",
+    what = "the unmodified reference modules (baseline/_ref)" if kind == "reference" else "the oracle port of the reference"
+    if unet:
+        sample = f"fwd+CE/Dice+bwd+AdamW of B={batch} images (1x{HW}x{HW}) per step, fp32, {what}: BASELINE.json configs[0] as written"
+        cfg = unet_config(1)
+        metric = "train images/s UNet"
+    else:
+        sample = (f"fwd+CE/Dice+bwd+AdamW of B={batch} slices (T={T_PHASES}, {HW}x{HW}) per step -- a bounded sample of the "
+                  f"{BATCH_PER_GPU}-slice step --, fp32, {what}")
+        cfg = workload_config(args.gpus)
+        metric = "train slices/s STF-LSTM-UNet"
+    cfg = dict(cfg)
+    cfg["launch"] = f"reference arm: PyTorch CPU backend (oneDNN/MKL), {threads} host threads, eager"
+    cfg["l2"] = "n/a (host CPU)"
+    line = {"impl": "reference", "metric": metric, "value": round(val, 4), "unit": "images/s" if unet else "slices/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms, 2),
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": workload_config(args.gpus),
-            "cpu_baseline": {"value": round(val, 4), "unit": "slices/s", "cores": threads, "kind": "port", "sample": sample},
-            "e2e": {"value": round(val, 4), "unit": "slices/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "config": cfg,
+            "cpu_baseline": {"value": round(val, 4), "unit": "images/s" if unet else "slices/s", "cores": threads, "kind": kind,
+                             "sample": sample},
+            "e2e": {"value": round(val, 4), "unit": "images/s" if unet else "slices/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     emit(line)
+
+
+def gpu_eager_baseline(dev, x_dev, t_dev, steps=3, warmup=2, unet=False):
+    """The practical bar (SURVEY.md section 8(d) last row): the UNMODIFIED reference module on this
+    same B200 through PyTorch eager / cuDNN, same batch, fwd + criterion + bwd + AdamW(fused), CUDA events after warm-up;
+    fp32 with TF32 off (the parity oracle's arithmetic) and torch.autocast(bf16) (the like-for-like precision)."""
+    ref = import_reference()
+    if ref is None:
+        return {"unavailable": "baseline/_ref not installed (tools/install_ref.sh)"}
+    saved = (torch.backends.cudnn.benchmark, torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    torch.backends.cudnn.benchmark = True
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    out = {"what": "reference nn.Module (baseline/_ref) on the same GPU, PyTorch eager + cuDNN, cudnn.benchmark=True, "
+                   "fwd+criterion+bwd+AdamW(fused), same batch", "batch": int(x_dev.shape[0])}
+    try:
+        for tag, dt in (("fp32_tf32_off", None), ("autocast_bf16", torch.bfloat16)):
+            torch.manual_seed(0)
+            model = (ref.UNet(1, 2, 64) if unet else ref.STFLSTMUNet(1, 2, int(x_dev.shape[1]))).to(dev).train()
+            opt = torch.optim.AdamW(model.parameters(), lr=1e-3, weight_decay=1e-4, fused=True)
+
+            def step():
+                with torch.autocast("cuda", dtype=torch.bfloat16, enabled=dt is not None):
+                    loss = ref.criterion(model(x_dev), t_dev)
+                opt.zero_grad()
+                loss.backward()
+                opt.step()
+                return loss
+
+            for _ in range(warmup):
+                step()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(steps):
+                step()
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / steps
+            out[tag] = {"ms_per_step": round(ms, 3), "per_s": round(x_dev.shape[0] / (ms / 1e3), 2)}
+            del model, opt
+            torch.cuda.empty_cache()
+    finally:
+        torch.backends.cudnn.benchmark, torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = saved
+    return out
 
 
 CONFIG_NOTE = "BASELINE.json configs[2] = global batch 128 on 8 GPUs"
@@ -386,12 +497,22 @@ def run_own(args, rank, world, local_rank):
                                      for k, v in membound.items()}}
 
     cpu = None
+    gpu_ref = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cb, cn = (2, 3) if HW <= 256 else (1, 1)
-        times, threads = cpu_train_step_time(cb, cn, 1)
+        times, threads, kind = cpu_train_step_time(cb, cn, 1)
         v = cb / (sum(times) / len(times))
-        cpu = {"value": round(v, 4), "unit": "slices/s", "cores": threads, "kind": "port",
-               "sample": f"{cn} train step(s) of B={cb} slices (T={T_PHASES}, {HW}x{HW}) fp32 on the oracle port, 1 warm-up"}
+        what = "the unmodified reference modules (baseline/_ref)" if kind == "reference" else "the oracle port"
+        cpu = {"value": round(v, 4), "unit": "slices/s", "cores": threads, "kind": kind,
+               "sample": f"{cn} train step(s) (fwd+CE/Dice+bwd+AdamW) of B={cb} slices (T={T_PHASES}, {HW}x{HW}) fp32 on {what}, 1 warm-up"}
+    if rank == 0 and world == 1 and not args.no_gpu_baseline:
+        # free this arm's graphs and buffers first: the reference keeps every fp32 activation of the step alive
+        graphed = None
+        torch.cuda.empty_cache()
+        try:
+            gpu_ref = gpu_eager_baseline(dev, x_dev, t_dev)
+        except Exception as e:       # the baseline must never take the product's number down with it
+            gpu_ref = {"unavailable": f"{type(e).__name__}: {e}"[:200]}
 
     if rank == 0:
         pk = peaks()
@@ -404,10 +525,118 @@ def run_own(args, rank, world, local_rank):
                         "d2h_bytes_per_step": 4 * world, "ms_per_step": round(e2e_ms, 3)},
                 "e2e_u8": e2e_u8, "gpu_launches": int(launches),
                 "model_tflops": round(model_tflops, 2), "model_frac_of_bf16_peak": round(model_tflops / world / pk["tflops"], 4),
-                "loss_check": loss_check, "roofline": roof, "cpu_baseline": cpu}
+                "loss_check": loss_check, "roofline": roof, "cpu_baseline": cpu, "gpu_eager_baseline": gpu_ref}
         emit(line)
     if world > 1:
         dist.destroy_process_group()
+
+
+UNET_TRAIN_GFLOP_PER_IMAGE = 288.50     # BASELINE.md section 3 (UNet in=1, 256x256: fwd + dgrad + wgrad)
+
+
+def unet_config(n):
+    return {"workload": f"UNet(in_channels=1, num_classes=2, base_c=64) train fwd+CE/Dice+bwd+AdamW, batch 4 x 1x{HW}x{HW} "
+                        "(BASELINE.json configs[0], the reference's CPU-runnable case)",
+            "global_batch": 4 * n, "T": 1, "hw": HW, "parallelism": f"dp{n}",
+            "launch": "CUDA graph (fwd+loss+bwd) + one-launch flat AdamW",
+            "l2": "a 67 MB buffer is rewritten between timed steps (the step's activations, ~0.9 GB fp32, exceed L2 anyway)"}
+
+
+def run_unet(args, rank, world, local_rank):
+    """BASELINE.json configs[0]: UNet(1, 2, 64), batch 4 x 1x256x256, fwd + CE/Dice + bwd (+ AdamW).  The reference states it
+    in fp32 on the CPU; here `value` is the fp32-accurate mode (the 1e-4 parity mode: FFMA implicit GEMM, fp32 storage) and
+    `bf16` the tensor-core mode of the same step, next to the reference's CPU time and its eager-cuDNN time on this GPU."""
+    import stf_unet_b200 as S
+    from stf_unet_b200 import _lib
+    from stf_unet_b200.graph import GraphedStep
+    from stf_unet_b200.synthetic import synthetic_dce_batch
+    if world > 1:
+        raise SystemExit("bench.py --workload unet is a single-GPU configuration (configs[0])")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    B = 4
+    x_host, t_host = synthetic_dce_batch(B, 1, HW, HW, seed=1234, half_res_target=False)
+    x_pin, t_pin = x_host[:, 0].contiguous().pin_memory(), t_host.pin_memory()
+    x_dev, t_dev = x_pin.to(dev), t_pin.to(dev)
+    flush = torch.empty(64 << 20, dtype=torch.uint8, device=dev)
+    results = {}
+    launches = 0
+    clk_summary = None
+    for tag, dt in (("fp32", None), ("bf16", torch.bfloat16)):
+        torch.manual_seed(0)
+        model = S.UNet(1, 2, 64).to(dev)
+        opt = S.FlatAdamW(model, lr=1e-3, weight_decay=1e-4)
+        g = GraphedStep(model, S.criterion, x_dev, t_dev, autocast_dtype=dt)
+
+        def step(x, t):
+            loss = g(x, t)
+            opt.step()
+            return loss
+
+        def timed(fn, steps):
+            tot = 0.0
+            for _ in range(steps):
+                flush.fill_(1)
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                fn()
+                e1.record()
+                torch.cuda.synchronize()
+                tot += e0.elapsed_time(e1)
+            return tot / steps
+
+        for _ in range(max(args.warmup, 3)):
+            step(x_dev, t_dev)
+        torch.cuda.synchronize()
+        n0 = _lib.launch_count()
+        with ClockSampler(local_rank) as clk:
+            ms = timed(lambda: step(x_dev, t_dev), args.steps)
+        if dt is None:
+            launches = _lib.launch_count() - n0 + g.launches_per_replay * args.steps
+            clk_summary = clk.summary()
+
+        def e2e_step():
+            x_dev.copy_(x_pin, non_blocking=True)
+            t_dev.copy_(t_pin, non_blocking=True)
+            return step(x_dev, t_dev).item()
+
+        e2e_step()
+        e2e_ms = timed(e2e_step, args.steps)
+        results[tag] = {"ms_per_step": round(ms, 3), "images_per_s": round(B / (ms / 1e3), 2), "e2e_ms_per_step": round(e2e_ms, 3),
+                        "e2e_images_per_s": round(B / (e2e_ms / 1e3), 2), "loss": round(g.loss.item(), 6),
+                        "model_tflops": round(B / (ms / 1e3) * UNET_TRAIN_GFLOP_PER_IMAGE / 1e3, 2)}
+        del g, opt, model
+        torch.cuda.empty_cache()
+    cpu = None
+    if not args.no_cpu_baseline:
+        times, threads, kind = cpu_train_step_time(B, 3, 1, workload="unet")
+        v = B / (sum(times) / len(times))
+        what = "the unmodified reference modules (baseline/_ref)" if kind == "reference" else "the oracle port"
+        cpu = {"value": round(v, 4), "unit": "images/s", "cores": threads, "kind": kind,
+               "sample": f"3 train steps (fwd+CE/Dice+bwd+AdamW) of B={B} images (1x{HW}x{HW}) fp32 on {what}, 1 warm-up: configs[0] as written"}
+    gpu_ref = None
+    if not args.no_gpu_baseline:
+        try:
+            gpu_ref = gpu_eager_baseline(dev, x_dev, t_dev, unet=True)
+        except Exception as e:
+            gpu_ref = {"unavailable": f"{type(e).__name__}: {e}"[:200]}
+    pk = peaks()
+    f32 = results["fp32"]
+    # fp32-accurate mode: FFMA implicit GEMM.  148 SMs x 128 FMA lanes x 2 x 1.965 GHz = 74.4 TFLOP/s is its own ceiling; the
+    # contract's roofline object is quoted against the measured bf16 tensor peak like every GEMM-shaped kernel of this repo
+    roof = {"bound": "tensor", "kernel": "igemm_simt_kernel<float> + wgrad_simt_kernel<float> (whole fp32 step)",
+            "achieved": f32["model_tflops"], "peak": pk["tflops"], "unit": "TFLOP/s", "frac": round(f32["model_tflops"] / pk["tflops"], 4),
+            "traffic": None, "peak_source": pk["src"], "fp32_ffma_peak_tflops": 74.4,
+            "frac_of_fp32_ffma_peak": round(f32["model_tflops"] / 74.4, 4),
+            "bf16_tensor_mode": {"tflops": results["bf16"]["model_tflops"], "frac": round(results["bf16"]["model_tflops"] / pk["tflops"], 4)}}
+    line = {"metric": "train images/s UNet", "value": f32["images_per_s"], "unit": "images/s", "n_gpus": 1, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": f32["ms_per_step"], "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": unet_config(1), "clocks": clk_summary,
+            "e2e": {"value": f32["e2e_images_per_s"], "unit": "images/s", "h2d_bytes_per_step": int(x_pin.numel() * 4 + t_pin.numel() * 8),
+                    "d2h_bytes_per_step": 4, "ms_per_step": f32["e2e_ms_per_step"]},
+            "gpu_launches": int(launches), "model_tflops": f32["model_tflops"], "modes": results, "roofline": roof,
+            "cpu_baseline": cpu, "gpu_eager_baseline": gpu_ref}
+    emit(line)
 
 
 INFER_GFLOP_PER_SLICE = 86.72          # BASELINE.md / SURVEY.md section 8(d): forward conv + LSTM GEMMs
@@ -593,11 +822,13 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="own", choices=["own", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-gpu-baseline", action="store_true", help="skip the reference-on-this-GPU (eager cuDNN) leg")
     ap.add_argument("--no-graph", action="store_true", help="enqueue every kernel from Python instead of replaying a CUDA graph")
     ap.add_argument("--profile-detail", action="store_true", help="print the slowest GEMM-family launches to stderr")
-    ap.add_argument("--workload", default="train", choices=["train", "infer", "train512", "volume"],
+    ap.add_argument("--workload", default="train", choices=["train", "infer", "train512", "volume", "unet"],
                     help="train = BASELINE.json configs[2] sharded 16/GPU (the headline metric); infer = configs[1], eval forward; "
-                         "train512 = configs[3] (T=16 x 512x512, 8 slices/GPU); volume = configs[4] (160-slice case, sharded by slice)")
+                         "train512 = configs[3] (T=16 x 512x512, 8 slices/GPU); volume = configs[4] (160-slice case, sharded by slice); "
+                         "unet = configs[0] (UNet fp32, batch 4)")
     args = ap.parse_args()
     claim_stdout()
     rank = int(os.environ.get("RANK", "0"))
@@ -619,6 +850,9 @@ def main():
         return
     if args.workload == "volume":
         run_volume(args, rank, world, local_rank)
+        return
+    if args.workload == "unet":
+        run_unet(args, rank, world, local_rank)
         return
     run_own(args, rank, world, local_rank)
 

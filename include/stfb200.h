@@ -109,8 +109,10 @@ int stfb_conv2d_stats_fusable(const stfb_conv_params* p, int groups);
 size_t stfb_conv2d_wgrad_workspace_bytes(const void* P, const void* G, int N, int Hp, int Wp, int Cp, int Hg, int Wg, int Cg,
                                          int cg_total, int kh, int kw, int stride, int pad, int dtype, int impl);
 /* Optional caller-owned scratch for the tcgen05 weight-gradient kernels (per-split partial tiles, summed by a second
- * kernel, instead of fp32 atomics from every CTA).  Register stfb_wgrad_scratch_bytes() bytes once per process (one process
- * drives one GPU); NULL unregisters.  The buffer must stay alive, and is used on the stream of each wgrad call. */
+ * kernel, instead of fp32 atomics from every CTA).  Register a multiple of stfb_wgrad_scratch_bytes() bytes once per
+ * process (one process drives one GPU); NULL unregisters.  The buffer must stay alive.  It is cut into slots of
+ * stfb_wgrad_scratch_bytes() and every STREAM that launches such a weight gradient owns one slot (first come, first
+ * served, up to 16), so launches on different streams never share partial tiles; a stream without a slot uses atomics. */
 size_t stfb_wgrad_scratch_bytes(void);
 int stfb_set_wgrad_scratch(void* scratch, size_t bytes);
 typedef struct stfb_scatter_job {
@@ -319,15 +321,28 @@ int stfb_cast(const void* src, int src_dtype, void* dst, int dst_dtype, long lon
 
 /* ------------------------------------------------------------------------------------------------
  * criterion = cross_entropy(mean) + multiclass softmax-Dice  (train_utils/train_and_eval.py:299-313,
- * train_utils/dice_coefficient_loss.py:5-55).  logits NCHW fp32 [B,C,h,w], target int64 [B,h,w] in [0,C).
- * stats fp64 [B*C*3 + 1] scratch (zeroed inside): per (b,c) {sum p*t, sum p, sum t}, then total NLL.
+ * train_utils/dice_coefficient_loss.py:5-55).  logits NCHW fp32 [B,C,h,w], target int64 [B,h,w].
+ * stats fp64 [B*C*3 + 3] scratch (zeroed inside): per (b,c) {sum p*t, sum p, sum t} over the valid pixels, then
+ * {sum w[t]*nll, sum w[t], number of labels outside [0,C) that are not ignore_index}.
  * loss_out fp32 [3] = {total, ce, dice_loss}.
+ * _ex: the full signature of the reference's criterion -- class_weight fp32 [C] or NULL (F.cross_entropy's `weight`),
+ * ignore_index (pixels with that label enter neither term: cross-entropy is the weighted mean over the others, the
+ * per-image Dice sums run over the others; build_target / dice_coeff, dice_coefficient_loss.py:5-39), with_dice = 0 drops
+ * the Dice term.  A label outside [0,C) that is not ignore_index makes the reference raise; here every output turns
+ * NaN (no host synchronisation).  The plain entry points are the reference's training configuration
+ * (no weights, ignore_index = -100, Dice on).
  * ---------------------------------------------------------------------------------------------- */
 int stfb_ce_dice_fwd(const float* logits, const long long* target, double* stats, float* loss_out, int B, int C,
                      int HW, float eps, void* stream);
+int stfb_ce_dice_fwd_ex(const float* logits, const long long* target, const float* class_weight, double* stats,
+                        float* loss_out, int B, int C, int HW, float eps, long long ignore_index, int with_dice,
+                        void* stream);
 /* dlogits = dloss[0] * d(total)/d(logits); dloss is a device fp32 scalar (NULL = 1.0). */
 int stfb_ce_dice_bwd(const float* logits, const long long* target, const double* stats, const float* dloss,
                      float* dlogits, int B, int C, int HW, float eps, void* stream);
+int stfb_ce_dice_bwd_ex(const float* logits, const long long* target, const float* class_weight, const double* stats,
+                        const float* dloss, float* dlogits, int B, int C, int HW, float eps, long long ignore_index,
+                        int with_dice, void* stream);
 
 #ifdef __cplusplus
 }

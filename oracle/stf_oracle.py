@@ -176,25 +176,36 @@ def unet_forward(sd, x, train=False, return_buffers=False):
     return (out, st.buffers) if return_buffers else out
 
 
-def dice_loss(logits, target, eps=1e-6):
-    """1 - mean_c mean_b (2*sum(p*t)+eps)/(sum(p)+sum(t)+eps), p = softmax(logits).
+def dice_loss(logits, target, eps=1e-6, ignore_index=-100):
+    """1 - mean_c mean_b (2*sum(p*t)+eps)/(sum(p)+sum(t)+eps), p = softmax(logits), sums over the pixels whose
+    label is not ignore_index.
 
-    /root/reference/train_utils/dice_coefficient_loss.py:5-55 with ignore_index=-100
-    (the ignore branch is dead for a negative index) and multiclass=True.  The
-    ``sets_sum == 0`` branch (:34) cannot fire because softmax sums to one."""
+    /root/reference/train_utils/dice_coefficient_loss.py:5-55 with multiclass=True.  build_target (:5-17) writes
+    ignore_index into every channel of an ignored pixel and dice_coeff (:27-31) drops those pixels from both x
+    and t; a negative ignore_index makes both branches dead.  The ``sets_sum == 0`` branch (:34-35) fires only for
+    an image with no valid pixel (softmax sums to one elsewhere): then sets_sum = 2*inter = 0 and d += eps/eps."""
     C = logits.shape[1]
     p = torch.softmax(logits.float(), dim=1)
-    t = F.one_hot(target, C).permute(0, 3, 1, 2).to(p.dtype)
+    if ignore_index >= 0:
+        valid = target != ignore_index
+        t = F.one_hot(torch.where(valid, target, torch.zeros_like(target)), C).permute(0, 3, 1, 2).to(p.dtype)
+        m = valid.unsqueeze(1).to(p.dtype)
+        p, t = p * m, t * m
+    else:
+        t = F.one_hot(target, C).permute(0, 3, 1, 2).to(p.dtype)
     inter = (p * t).sum(dim=(2, 3))
     sets = p.sum(dim=(2, 3)) + t.sum(dim=(2, 3))
-    dice = (2 * inter + eps) / (sets + eps)            # [B, C]
+    dice = torch.where(sets == 0, torch.ones_like(sets), (2 * inter + eps) / (sets + eps))   # [B, C]
     return 1 - dice.mean(dim=0).mean()
 
 
-def criterion(logits, target):
-    """CE(mean over pixels) + Dice: /root/reference/train_utils/train_and_eval.py:299-313
+def criterion(logits, target, loss_weight=None, dice=True, ignore_index=-100):
+    """CE(weighted mean over the non-ignored pixels) + Dice: /root/reference/train_utils/train_and_eval.py:299-313
     for the single 'out' head."""
-    return F.cross_entropy(logits.float(), target) + dice_loss(logits, target)
+    loss = F.cross_entropy(logits.float(), target, ignore_index=ignore_index, weight=loss_weight)
+    if dice:
+        loss = loss + dice_loss(logits, target, ignore_index=ignore_index)
+    return loss
 
 
 def loss_and_grads(sd, x, target, model="stf", train=True, **kw):

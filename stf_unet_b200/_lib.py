@@ -73,6 +73,8 @@ _SIGS = {
     "stfb_ce_dice_fwd": [_vp] * 4 + [_i, _i, _i, _f, _vp],
     "stfb_eval_metrics": [_vp] * 7 + [_i, _i, _i, _ll, _i, _vp],
     "stfb_ce_dice_bwd": [_vp] * 5 + [_i, _i, _i, _f, _vp],
+    "stfb_ce_dice_fwd_ex": [_vp] * 5 + [_i, _i, _i, _f, _ll, _i, _vp],
+    "stfb_ce_dice_bwd_ex": [_vp] * 6 + [_i, _i, _i, _f, _ll, _i, _vp],
 }
 EXPORTS = sorted(list(_SIGS) + list(_SIZE_T_FUNCS) + ["stfb_version", "stfb_last_error", "stfb_launch_count"])
 

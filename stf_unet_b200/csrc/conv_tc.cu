@@ -199,7 +199,8 @@ __device__ __forceinline__ void seg_store(uint32_t seg, uint8_t* base, const int
 // kernels.  `taddr` = this warp's TMEM lane quadrant + accumulator buffer, `stg` = its staging segment (shared space).
 template <int BN, typename TO>
 __device__ __forceinline__ void epilogue_tile(const TcArgs& a, const TileCoord& t, uint32_t taddr, uint32_t stg, const int* cpix,
-                                              unsigned cmask, bool valid, int on, int oh, int ow, uint64_t* tempty, int lane) {
+                                              unsigned cmask, bool valid, int on, int oh, int ow, uint64_t* tempty, int lane,
+                                              uint32_t tempty_cluster = 0) {
   if constexpr (BN * (int)sizeof(TO) >= 128) {
     // ===== staged epilogue: one 128-byte row segment (64 bf16 / 32 fp32 channels) at a time
     constexpr int ESZ = (int)sizeof(TO);
@@ -225,7 +226,7 @@ __device__ __forceinline__ void epilogue_tile(const TcArgs& a, const TileCoord& 
         if (c0 + 32 >= BN) {         // last chunk is in registers: hand the accumulator buffer back to the MMA warp
           tc_fence_before();
           __syncwarp();
-          if (lane == 0 && tempty) mbar_arrive(tempty);
+          if (lane == 0) { if (tempty) mbar_arrive(tempty); else if (tempty_cluster) mbar_arrive_cluster(tempty_cluster); }
         }
         float v[32];
         const int cg = t.n0 + c0;
@@ -332,7 +333,7 @@ __device__ __forceinline__ void epilogue_tile(const TcArgs& a, const TileCoord& 
       if (c0 + 32 >= BN) {
         tc_fence_before();
         __syncwarp();
-        if (lane == 0 && tempty) mbar_arrive(tempty);
+        if (lane == 0) { if (tempty) mbar_arrive(tempty); else if (tempty_cluster) mbar_arrive_cluster(tempty_cluster); }
       }
       if (valid && a.debug != 3) {
         float v[32];
@@ -835,6 +836,192 @@ __global__ void __launch_bounds__(TC_THREADS, MINB) conv_halo_kernel(const __gri
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// CTA-pair variant of the halo kernel (tcgen05 cta_group::2): the two CTAs of a (2,1,1) cluster -- the two SMs of a TPC --
+// compute two neighbouring 128-pixel tiles against the SAME output-channel block as ONE M = 256 MMA.  Each CTA stages its
+// own halo block (A is split along M) and only HALF of every weight block (B is split along N: rows
+// [rank * BN/2, +BN/2) of the tap's K-major tile), so a weight byte crosses the L2 -> SM fabric once per 256 pixels instead
+// of once per 128 and the shared-memory reads per MMA drop from A + B to A + B/2 per SM: the 1-CTA kernel is bound by
+// exactly these two (layers 2/3: ~310 KB of L2 reads per 4.6 k MMA cycles per SM, 1.6x the chip's L2 bandwidth; layer 1:
+// 6 KB of operand reads per 32-cycle N = 64 MMA against 128 B/clk of shared-memory bandwidth).
+//   * barriers: the "full" barriers live in the leader (rank 0): it arms them with the bytes of BOTH CTAs and both CTAs'
+//     TMA loads complete_tx on them; the MMA warp of the leader frees ring slots and
+//     publishes accumulators with multicast commits that arrive in both CTAs; the epilogue warps of both CTAs hand the
+//     accumulator back by arriving on the leader's "tmem empty" barrier.
+//   * 8 epilogue warps in two groups: group g drains accumulator buffer g (tiles alternate between the two TMEM buffers),
+//     so every group has two MMA periods per tile -- the narrow layers were bound by their four epilogue warps.
+constexpr int HALO2_THREADS = 320;
+template <int BN, int SA, int SB>
+constexpr int halo2_smem_bytes() {
+  return SA * HALO_BLK_BYTES + SB * (BN / 2) * 128 + 8 * TC_SEG_BYTES + 512 + 1024;
+}
+
+template <int BN, int SA, int SB, typename TO>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(HALO2_THREADS, 1)
+    conv_halo2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmA2,
+                      const __grid_constant__ CUtensorMap tmB, const TcArgs a) {
+  static_assert(9 % SB == 0, "the weight ring must divide the nine taps");
+  constexpr int BH_BYTES = (BN / 2) * 128;            // this CTA's half of one (tap, 64-channel) weight block
+  constexpr int TMEM_COLS = (2 * BN < 32) ? 32 : 2 * BN;
+  constexpr int WRAPS = 9 / SB;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const uint32_t sA = smem_u32(smem);
+  const uint32_t sB = sA + SA * HALO_BLK_BYTES;
+  const uint32_t sStg = sB + SB * BH_BYTES;
+  uint64_t* afull = reinterpret_cast<uint64_t*>(smem + SA * HALO_BLK_BYTES + SB * BH_BYTES + 8 * TC_SEG_BYTES);
+  uint64_t* aempty = afull + SA;
+  uint64_t* bfull = aempty + SA;
+  uint64_t* bempty = bfull + SB;
+  uint64_t* tfull_bar = bempty + SB;
+  uint64_t* tempty_bar = tfull_bar + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+  const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+  const int Cin = a.C1 + a.C2;
+  const int cpt = Cin / 64;
+  const int n_tiles = a.Cout / BN;
+  const int pix_tiles = a.num_tiles / n_tiles;                  // even (checked on the host)
+  const int n_super = (pix_tiles / 2) * n_tiles;                // super tile = n-tile fastest, then pixel-tile pairs
+  const int cid = (int)cluster_id_x(), ncl = (int)num_clusters_x();
+
+  if (threadIdx.x == 0) {
+    // full barriers (used in the leader only): ONE arrival, the leader's arrive.expect_tx with the bytes of both CTAs.  The
+    // peer needs no arrival of its own: it cannot issue the loads of a slot's next use before the leader has consumed the
+    // current one (its "empty" barrier is released by the same multicast commit), and bytes that land before the leader
+    // has armed the barrier only drive the transaction count negative for a moment.
+    for (int s = 0; s < SA; ++s) { mbar_init(&afull[s], 1); mbar_init(&aempty[s], 1); }
+    for (int s = 0; s < SB; ++s) { mbar_init(&bfull[s], 1); mbar_init(&bempty[s], 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&tfull_bar[s], 1); mbar_init(&tempty_bar[s], 8); }   // 4 warps x 2 CTAs
+    fence_barrier_init();
+    prefetch_tensormap(&tmA);
+    prefetch_tensormap(&tmB);
+    if (a.C2 > 0) prefetch_tensormap(&tmA2);
+  }
+  if (warp == 1) {
+    tmem_alloc_pair(tmem_slot, TMEM_COLS);
+    tmem_relinquish_pair();
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();               // the peer's barriers are initialised before anything arrives on them
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ================= TMA producer (both CTAs: own halo block, own half of the weights) =================
+    if (elect_one()) {
+      int sa = 0;
+      uint32_t pa = 0, nblk = 0;
+      for (int st = cid; st < n_super; st += ncl) {
+        const int nt = st % n_tiles, pp = st / n_tiles;
+        const TileCoord t = decode_tile<BN>(a, (pp * 2 + (int)rank) * n_tiles + nt, n_tiles, cpt);
+        const int w0 = t.wb * HALO_TW - 1, h0 = t.hb * HALO_TH - 1;
+        for (int c = 0; c < cpt; ++c, ++nblk) {
+          const int cc = c * 64;
+          mbar_wait(&aempty[sa], pa ^ 1);
+          const uint32_t af = mapa_shared(smem_u32(&afull[sa]), 0);
+          if (leader) mbar_arrive_expect_tx(&afull[sa], 2 * HALO_TX_BYTES);
+          if (cc < a.C1) tma_load_4d_pair(sA + sa * HALO_BLK_BYTES, &tmA, af, cc, w0, h0, t.nb);
+          else tma_load_4d_pair(sA + sa * HALO_BLK_BYTES, &tmA2, af, cc - a.C1, w0, h0, t.nb);
+          if (++sa == SA) { sa = 0; pa ^= 1; }
+#pragma unroll
+          for (int tp = 0; tp < 9; ++tp) {
+            const int sb = tp % SB;
+            mbar_wait(&bempty[sb], ((nblk * WRAPS + tp / SB) & 1) ^ 1);
+            const uint32_t bf = mapa_shared(smem_u32(&bfull[sb]), 0);
+            if (leader) mbar_arrive_expect_tx(&bfull[sb], 2 * BH_BYTES);
+            tma_load_2d_pair(sB + sb * BH_BYTES, &tmB, bf, (int)a.ktap[0][tp] * Cin + cc, nt * BN + (int)rank * (BN / 2));
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================= MMA issuer (leader only) =================
+    if (leader) {
+      constexpr uint32_t idesc = make_idesc_bf16(256, BN);
+      int sa = 0;
+      uint32_t pa = 0, nblk = 0, it = 0;
+      for (int st = cid; st < n_super; st += ncl, ++it) {
+        const int acc = (int)(it & 1);
+        mbar_wait(&tempty_bar[acc], ((it >> 1) & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t tmem_acc = tmem_base + (uint32_t)(acc * BN);
+        for (int c = 0; c < cpt; ++c, ++nblk) {
+          mbar_wait(&afull[sa], pa);
+          const uint32_t ablk = sA + sa * HALO_BLK_BYTES;
+          const int sa_used = sa;
+          if (++sa == SA) { sa = 0; pa ^= 1; }
+          tc_fence_after();
+          if (elect_one()) {
+#pragma unroll
+            for (int tp = 0; tp < 9; ++tp) {
+              const int sb = tp % SB;
+              mbar_wait(&bfull[sb], (nblk * WRAPS + tp / SB) & 1);
+              tc_fence_after();
+              const uint64_t bdesc = make_kmajor_sw128_desc(sB + sb * BH_BYTES);
+              const uint64_t adesc = make_halo_a_desc(ablk + halo_tap_off(tp));
+#pragma unroll
+              for (int k = 0; k < 4; ++k)
+                umma_bf16_pair(tmem_acc, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (c | tp | k) != 0);
+              umma_commit_pair(&bempty[sb]);
+            }
+            umma_commit_pair(&aempty[sa_used]);
+            if (c == cpt - 1) umma_commit_pair(&tfull_bar[acc]);
+          }
+          __syncwarp();
+        }
+      }
+    }
+  } else {
+    // ================= epilogue: group g = (warp - 2) / 4 drains accumulator buffer g =================
+    const int g = (warp - 2) >> 2;
+    const int q = warp & 3;
+    const uint32_t stg = sStg + (uint32_t)(g * 4 + q) * TC_SEG_BYTES;
+    const int m_ = q * 32 + lane;
+    const int tw = m_ % HALO_TW, th = m_ / HALO_TW;
+    int cpk[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int mm = q * 32 + i * 4 + (lane >> 3);
+      cpk[i] = (mm % HALO_TW) | ((mm / HALO_TW) << 8);
+    }
+    const uint32_t tempty_leader = mapa_shared(smem_u32(&tempty_bar[g]), 0);
+    uint32_t it = 0;
+    for (int st = cid; st < n_super; st += ncl, ++it) {
+      if ((int)(it & 1) != g) continue;
+      const int nt = st % n_tiles, pp = st / n_tiles;
+      mbar_wait(&tfull_bar[g], (it >> 1) & 1);
+      tc_fence_after();
+      const TileCoord t = decode_tile<BN>(a, (pp * 2 + (int)rank) * n_tiles + nt, n_tiles, cpt);
+      const int ow = t.wb * HALO_TW + tw, oh = t.hb * HALO_TH + th, on = t.nb;
+      const bool valid = ow < a.Wout && oh < a.Hout && on < a.N;
+      int cpix[8];
+      unsigned cmask = 0;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int cw = t.wb * HALO_TW + (cpk[i] & 0xFF), chh = t.hb * HALO_TH + (cpk[i] >> 8);
+        const bool ok = cw < a.Wout && chh < a.Hout && on < a.N;
+        cpix[i] = ok ? (on * a.Hout + chh) * a.Wout + cw : 0;
+        cmask |= (ok ? 1u : 0u) << i;
+      }
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(g * BN);
+      epilogue_tile<BN, TO>(a, t, taddr, stg, cpix, cmask, valid, on, oh, ow, nullptr, lane, tempty_leader);
+    }
+  }
+  // neither CTA may leave (or free its tensor memory) while the pair's MMAs can still touch its shared / tensor memory
+  tc_fence_before();
+  __syncwarp();
+  cluster_sync_all();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc_pair(tmem_base, TMEM_COLS);
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------
@@ -939,6 +1126,39 @@ static int launch_halo(const CUtensorMap& tA, const CUtensorMap& tA2, const CUte
   }
   conv_halo_kernel<BN, MT, SA, SB, TO, MINB><<<grid, TC_THREADS, smem, st>>>(tA, tA2, tB, a);
   return post_launch("conv2d(tcgen05 halo)");
+}
+
+template <int BN, int SA, int SB, typename TO>
+static int launch_halo2(const CUtensorMap& tA, const CUtensorMap& tA2, const CUtensorMap& tB, const TcArgs& a, int n_super,
+                        cudaStream_t st) {
+  constexpr int smem = halo2_smem_bytes<BN, SA, SB>();
+  static_assert(smem <= 232448, "shared memory budget");
+  static int max_clusters = -1;
+  if (max_clusters < 0) {
+    if (cudaFuncSetAttribute(conv_halo2_kernel<BN, SA, SB, TO>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) {
+      set_error("conv2d(tcgen05 pair): cannot reserve %d bytes of shared memory: %s", smem, cudaGetErrorString(cudaGetLastError()));
+      return STFB_ECUDA;
+    }
+    // how many CTA pairs fit at once (a TPC with a disabled SM cannot host one)
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((unsigned)num_sms() / 2 * 2);
+    cfg.blockDim = dim3(HALO2_THREADS);
+    cfg.dynamicSmemBytes = smem;
+    cudaLaunchAttribute cattr[1];
+    cattr[0].id = cudaLaunchAttributeClusterDimension;
+    cattr[0].val.clusterDim.x = 2; cattr[0].val.clusterDim.y = 1; cattr[0].val.clusterDim.z = 1;
+    cfg.attrs = cattr;
+    cfg.numAttrs = 1;
+    int nc = 0;
+    if (cudaOccupancyMaxActiveClusters(&nc, conv_halo2_kernel<BN, SA, SB, TO>, &cfg) != cudaSuccess || nc <= 0) {
+      cudaGetLastError();
+      nc = num_sms() / 2;
+    }
+    max_clusters = nc < num_sms() / 2 ? nc : num_sms() / 2;
+  }
+  const int ncl = n_super < max_clusters ? n_super : max_clusters;
+  conv_halo2_kernel<BN, SA, SB, TO><<<dim3((unsigned)(2 * ncl)), HALO2_THREADS, smem, st>>>(tA, tA2, tB, a);
+  return post_launch("conv2d(tcgen05 pair)");
 }
 
 static bool halo_ok(const stfb_conv_params* p, int BN);
@@ -1071,13 +1291,51 @@ int conv2d_tcgen05(const stfb_conv_params* p, cudaStream_t st) {
       for (int tp = 0; tp < 9; ++tp) { a.ktap[0][tp] = kt[tp]; a.dh[0][tp] = (signed char)(tp / 3 - 1); a.dw[0][tp] = (signed char)(tp % 3 - 1); }
     }
     const int n_tiles_ = p->Cout / BN, pix_tiles = a.num_tiles / n_tiles_;
+    {
+      // CTA pairs (cta_group::2) whenever the pixel tiles pair up and there is at least one pair per two SMs worth of work
+      const char* pe = getenv("STFB_HALO_PAIR");           // read per launch: tests switch it
+      const int pair_mode = pe ? atoi(pe) : 1;
+      if (pair_mode != 0 && pix_tiles % 2 == 0 && (pix_tiles / 2) * n_tiles_ >= 16) {
+        CUtensorMap tBh;
+        cuuint64_t dims[2] = {(cuuint64_t)Ktot, (cuuint64_t)p->Cout};
+        cuuint64_t strides[1] = {(cuuint64_t)p->ldw * 2};
+        cuuint32_t box[2] = {64, (cuuint32_t)(BN / 2)};
+        cuuint32_t estr[2] = {1, 1};
+        if (enc(&tBh, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(p->w), dims, strides, box, estr,
+                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS) {
+          set_error("conv2d(tcgen05 pair): cuTensorMapEncodeTiled failed for the weights"); return STFB_ECUDA;
+        }
+        const int n_super2 = (pix_tiles / 2) * n_tiles_;
+        a.w_resident = 0;
+#define HALO2_LAUNCH(BN_, SA_, SB_)                                                                            \
+        return f32out ? launch_halo2<BN_, SA_, SB_, float>(tA, tA2, tBh, a, n_super2, st)                     \
+                      : launch_halo2<BN_, SA_, SB_, __nv_bfloat16>(tA, tA2, tBh, a, n_super2, st)
+        switch (BN) {
+          case 256: HALO2_LAUNCH(256, 4, 3);      // 94 KB halo ring + 3 x 16 KB weight halves
+          case 128: HALO2_LAUNCH(128, 4, 9);      // + the whole tap set of a channel block: 9 x 8 KB
+          case 64: HALO2_LAUNCH(64, 4, 9);        // 9 x 4 KB
+        }
+#undef HALO2_LAUNCH
+      }
+    }
     // MT = 2 halves the weight traffic per pixel but needs enough super tiles to keep the SMs busy
     // Pairing two pixel tiles per weight pass (MT = 2) halves the weight traffic and wins on L2-warm microbenchmarks
     // (64->64: 70 -> 52 us, 128->128: 47 -> 41 us) but loses inside the training step (13.45 vs 13.85 ms), where the tiles
     // stream from DRAM and the longer super-tile epilogue is exposed: off unless STFB_HALO_MT=2.
     const char* mt_env = getenv("STFB_HALO_MT");       // read per launch: tests switch it
     const int mt_mode = mt_env ? atoi(mt_env) : 0;
-    const bool mt2 = mt_mode == 2 && ((pix_tiles + 1) / 2) * n_tiles_ >= (num_sms() * 3) / 4;
+    const char* mt_bn = getenv("STFB_HALO_MT_BN");     // optional filter: comma list of the BN values MT = 2 applies to
+    bool bn_sel = true;
+    if (mt_bn && *mt_bn) {
+      bn_sel = false;
+      for (const char* q = mt_bn; *q;) {
+        if (atoi(q) == BN) bn_sel = true;
+        while (*q && *q != ',') ++q;
+        if (*q == ',') ++q;
+      }
+    }
+    const bool mt2 = mt_mode == 2 && bn_sel && ((pix_tiles + 1) / 2) * n_tiles_ >= (num_sms() * 3) / 4;
     const int n_super = mt2 ? ((pix_tiles + 1) / 2) * n_tiles_ : a.num_tiles;
     dim3 hgrid((unsigned)(n_super < num_sms() ? n_super : num_sms()));
 #define HALO_LAUNCH(BN_, MT_, SA_, SB_)                                                                        \

@@ -16,6 +16,7 @@
 //     launch -- profiles/r01_ncu_wgrad_atomics.txt; v2 wrote per-split partial tiles: 38 MB out + 38 MB back per launch.)
 #include "tc_common.cuh"
 #include <stdlib.h>
+#include <mutex>
 
 namespace stfb {
 
@@ -394,11 +395,38 @@ __global__ void __launch_bounds__(256) wgrad_halo_reduce_kernel(const float* __r
   }
 }
 
-// caller-owned scratch for the per-split partial tiles (registered once per process: one process drives one GPU)
+// caller-owned scratch for the per-split partial tiles (registered once per process: one process drives one GPU).
+// The buffer is cut into SLOTS of wgrad_scratch_bytes() each and every stream that launches a halo wgrad gets its own slot
+// (first come, first served): the partials of a launch are read back by the reduce kernel that follows it on the SAME
+// stream, so launches on different streams -- the engine rotates weight gradients over several side streams, and they
+// become parallel branches of a captured graph -- must not share partial tiles.  A stream that finds no free slot falls
+// back to the red.add epilogue (slower, still correct).
 static float* g_wg_scratch = nullptr;
 static size_t g_wg_scratch_bytes = 0;
-void wgrad_set_scratch(void* p, size_t bytes) { g_wg_scratch = reinterpret_cast<float*>(p); g_wg_scratch_bytes = bytes; }
+constexpr int WG_MAX_SLOTS = 16;
+static cudaStream_t g_wg_slot_stream[WG_MAX_SLOTS];
+static int g_wg_slots_used = 0;
+static std::mutex g_wg_mu;
+void wgrad_set_scratch(void* p, size_t bytes) {
+  std::lock_guard<std::mutex> lk(g_wg_mu);
+  g_wg_scratch = reinterpret_cast<float*>(p);
+  g_wg_scratch_bytes = bytes;
+  g_wg_slots_used = 0;
+}
 size_t wgrad_scratch_bytes() { return (size_t)num_sms() * 576 * 64 * sizeof(float); }
+// the slot of stream `st` (NULL: none registered / all taken / a slot cannot hold `need` bytes)
+static float* wgrad_scratch_slot(cudaStream_t st, size_t need) {
+  std::lock_guard<std::mutex> lk(g_wg_mu);
+  const size_t per = wgrad_scratch_bytes();
+  if (g_wg_scratch == nullptr || need > per || (reinterpret_cast<uintptr_t>(g_wg_scratch) % 16) != 0) return nullptr;
+  int nslots = (int)(g_wg_scratch_bytes / per);
+  if (nslots > WG_MAX_SLOTS) nslots = WG_MAX_SLOTS;
+  for (int i = 0; i < g_wg_slots_used; ++i)
+    if (g_wg_slot_stream[i] == st) return g_wg_scratch + (size_t)i * (per / sizeof(float));
+  if (g_wg_slots_used >= nslots) return nullptr;
+  g_wg_slot_stream[g_wg_slots_used] = st;
+  return g_wg_scratch + (size_t)(g_wg_slots_used++) * (per / sizeof(float));
+}
 
 // dW[co][cg_off + ci][tap] += acc[(tap, ci)][co]: 32 ci x 32 co tiles transposed through shared memory so that both the
 // reads (along co) and the writes (along (ci, tap), contiguous in the reference layout) are coalesced
@@ -660,9 +688,9 @@ int wgrad_tcgen05(const void* P, const void* G, const void* G2, float* dW, int N
       if (dW != nullptr) cudaMemsetAsync(ws, 0, need, st);
       dim3 hgrid((unsigned)((C1 + C2) / 64), (unsigned)(Cp / 64), (unsigned)splits);
       const size_t part_bytes = (size_t)pairs * splits * 576 * 64 * sizeof(float);
-      const bool use_partials = g_wg_scratch != nullptr && part_bytes <= g_wg_scratch_bytes &&
-                                (reinterpret_cast<uintptr_t>(g_wg_scratch) % 16) == 0 && Cp % 4 == 0;
-      a.partial = use_partials ? g_wg_scratch : nullptr;
+      float* slot = Cp % 4 == 0 ? wgrad_scratch_slot(st, part_bytes) : nullptr;
+      const bool use_partials = slot != nullptr;
+      a.partial = slot;
       wgrad_halo_kernel<<<hgrid, WG_THREADS, wh_smem_bytes(), st>>>(tG, tG2, tP, a);
       int rc = post_launch("conv2d_wgrad(tcgen05 halo)");
       if (rc == STFB_OK && use_partials) {
@@ -672,7 +700,7 @@ int wgrad_tcgen05(const void* P, const void* G, const void* G2, float* dW, int N
         if (zc > 16) zc = 16;
         if (zc < 1) zc = 1;
         dim3 rgrid(576 * 64 / 4 / 256, (unsigned)pairs, (unsigned)zc);
-        wgrad_halo_reduce_kernel<<<rgrid, 256, 0, st>>>(g_wg_scratch, ws, (int)splits, (C1 + C2) / 64, Cp / 64, Cp, cg_off, cg_total);
+        wgrad_halo_reduce_kernel<<<rgrid, 256, 0, st>>>(slot, ws, (int)splits, (C1 + C2) / 64, Cp / 64, Cp, cg_off, cg_total);
         rc = post_launch("conv2d_wgrad(halo reduce)");
       }
       if (rc != STFB_OK || dW == nullptr) return rc;

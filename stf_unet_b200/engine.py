@@ -78,6 +78,7 @@ class Executor:
         self.acc: Dict[str, torch.Tensor] = {}
         self.grad_offsets: Dict[str, int] = {}
         self._deferred = {}           # name -> (flat offset, Cp, Cg_total, khw)
+        self.flat = None              # this forward's flat gradient buffer (self.grads are views of it)
         self._wg_keep = []            # (dy, x) pairs the side-stream wgrad launches still read
         self._fin_keep = []           # (slots, coefficients) the side-stream BatchNorm finalize launches still touch
 
@@ -626,21 +627,50 @@ class ModelFunction(torch.autograd.Function):
     @staticmethod
     def backward(ctx, dlogits):
         ex, module = ctx.ex, ctx.module
+        if ex is None:
+            raise RuntimeError("stf_unet_b200: backward through the same forward twice (the tape is consumed by the first one)")
+        flat = ex.flat                     # THIS forward's gradient buffer (another forward may have run since)
         d = ops.nchw_to_nhwc(dlogits.contiguous().float(), ex.dtype)
-        ex.backward(ctx.out_var, d, flat_grad=module._last_flat_grad, owner=module)
-        # Gradients live in ONE flat fp32 buffer (module._last_flat_grad); each parameter's .grad is a view of it,
-        # assigned directly so that autograd does not clone 110 MB per step and the data-parallel all-reduce can
-        # run on the flat buffer.  A second backward before zero_grad() accumulates, as autograd would.
-        params = dict(module.named_parameters())
-        for n in ctx.names:
-            p = params[n]
-            if p.grad is None:
-                p.grad = ex.grads[n]
-            else:
-                ops.add_(p.grad, ex.grads[n]) if p.grad.is_contiguous() else p.grad.add_(ex.grads[n])
+        ex.backward(ctx.out_var, d, flat_grad=flat, owner=module)
+        # Gradients live in ONE flat fp32 buffer; each parameter's .grad is a view of it, assigned directly so that autograd
+        # does not clone 110 MB per step and the data-parallel all-reduce / the flat optimizer work on the flat buffer.
+        # module._last_flat_grad is always the buffer the parameters' .grad VIEW: a backward that finds gradients already
+        # there (gradient accumulation, zero_grad(set_to_none=False), a second forward/backward before the optimizer step)
+        # adds into that buffer, as autograd would, instead of re-pointing the optimizer at a fresh one.
+        params = module._param_cache()
+        names = ctx.names
+        cur = getattr(module, "_last_flat_grad", None)
+        have = [params[n].grad is not None for n in names]
+        if not any(have):
+            for n in names:
+                params[n].grad = ex.grads[n]
+            module._last_flat_grad = flat
+        elif all(have) and cur is not None and cur is not flat and _views_of(cur, [params[n].grad for n in names], ex.grad_offsets, names):
+            ops.add_(cur, flat)            # one launch: both buffers share the layout
+        else:
+            for n in names:
+                p = params[n]
+                if p.grad is None:
+                    p.grad = ex.grads[n].clone()
+                elif p.grad.is_contiguous() and p.grad.dtype == torch.float32:
+                    ops.add_(p.grad, ex.grads[n])
+                else:
+                    p.grad.add_(ex.grads[n])
+            # the parameters' gradients no longer form one flat buffer this engine knows: flat consumers must say so
+            if cur is None or not _views_of(cur, [params[n].grad for n in names], ex.grad_offsets, names):
+                module._last_flat_grad = None
         hook = getattr(module, "_grad_ready_hook", None)
         if hook is not None:
             hook(module._last_flat_grad)
         module._learn_pack_plan(ex)
         ctx.ex = ctx.out_var = None
         return (None, None) + (None,) * len(ctx.names)
+
+
+def _views_of(flat, grads, offsets, names):
+    """Are `grads` exactly the per-parameter views of `flat` (same storage, the engine's offsets)?"""
+    base = flat.data_ptr()
+    for n, g in zip(names, grads):
+        if g is None or g.dtype != torch.float32 or g.data_ptr() != base + 4 * offsets[n]:
+            return False
+    return True

@@ -60,6 +60,9 @@ class GraphedStep:
             self.loss = fwd_bwd()
         self.launches_per_replay = _lib.launch_count() - n0      # libstfb200 kernels inside the captured graph
         self.flat_grad = model._last_flat_grad
+        # replay runs no Python: the .grad views assigned during capture are re-bound after every replay, so a caller that
+        # did zero_grad() (set_to_none=True is torch's default) in between still sees gradients -- with ANY optimizer
+        self._grad_views = [(p, p.grad) for p in model.parameters() if p.requires_grad and p.grad is not None]
         if self._hook is not None:
             model._grad_ready_hook = self._hook
 
@@ -68,6 +71,9 @@ class GraphedStep:
         self.t.copy_(target, non_blocking=True)
         self.graph.replay()
         self.model._last_flat_grad = self.flat_grad      # what a flat optimizer steps on (another graph / an eager step may have moved it)
+        for p, g in self._grad_views:                    # the graph OVERWRITES its flat buffer: replay == zero_grad + backward
+            if p.grad is not g:
+                p.grad = g
         if self._hook is not None:
             self._hook(self.flat_grad)
         return self.loss

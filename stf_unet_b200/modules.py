@@ -95,14 +95,20 @@ class B200Module(nn.Module):
                                    "fallback; call model.to('cuda'))")
         grads, offsets, flat = {}, {}, None
         if record:
+            for n, p in named:
+                if p.requires_grad and (p._backward_hooks or getattr(p, "_post_accumulate_grad_hooks", None)):
+                    raise RuntimeError(
+                        f"parameter {n} carries autograd hooks (torch DistributedDataParallel / register_hook): the whole "
+                        "model is ONE autograd node here and writes .grad itself, so per-parameter hooks never fire. Use "
+                        "stf_unet_b200.parallel.DataParallel for data parallelism.")
             flat, grads, offsets = engine.flat_grads(named, with_offsets=True)
-            self._last_flat_grad = flat
             self._trainable_names = [n for n, p in named if p.requires_grad]
         ex = engine.Executor(self._state(), self._select_dtype(), self.training, record, grads)
+        ex.flat = flat
+        ex.grad_offsets = offsets
         if record and flat is not None and ex.dtype == torch.bfloat16:
             # side buffer (same offsets as the flat gradient) the tcgen05 weight-gradient kernels accumulate into
             ex.acc_flat = torch.zeros_like(flat)
-            ex.grad_offsets = offsets
             ex.acc = {n: ex.acc_flat[o:o + self._numel(n)] for n, o in offsets.items() if self._is_matrix(n)}
         # one batched launch re-packs every weight this mode needs (plan learned on the first forward of the mode)
         plans = self.__dict__.setdefault("_pack_plans", {})

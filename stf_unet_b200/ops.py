@@ -163,12 +163,16 @@ def conv2d(x, wp, Cout, k, stride, pad, *, mode=CONV_FWD, out_hw=None, x2=None, 
 _wg_scratch = {}
 
 
+WGRAD_SCRATCH_SLOTS = 8   # one slot per stream that launches weight gradients (3 side streams, 4 LSTM forks, the main one)
+
+
 def _ensure_wgrad_scratch(device):
-    """Registers (once per device) the scratch buffer the tcgen05 wgrad kernels keep their per-split partial tiles in."""
+    """Registers (once per device) the scratch buffer the tcgen05 wgrad kernels keep their per-split partial tiles in:
+    WGRAD_SCRATCH_SLOTS slots, one per launching stream (launches on different streams must not share partial tiles)."""
     key = (device.type, device.index if device.index is not None else torch.cuda.current_device())
     if key not in _wg_scratch:
         lib = _lib.load()
-        n = lib.stfb_wgrad_scratch_bytes()
+        n = lib.stfb_wgrad_scratch_bytes() * WGRAD_SCRATCH_SLOTS
         buf = torch.empty((max(n, 16) // 4,), dtype=torch.float32, device=device)
         check(lib.stfb_set_wgrad_scratch(buf.data_ptr(), buf.numel() * 4), "set_wgrad_scratch")
         _wg_scratch[key] = buf
@@ -656,19 +660,21 @@ def cast(src, dtype):
     return dst
 
 
-def ce_dice_fwd(logits, target, eps=1e-6):
-    """logits NCHW fp32, target int64 -> (loss_out[3] = {total, ce, dice}, stats)."""
-    _need_cuda(logits, target)
+def ce_dice_fwd(logits, target, eps=1e-6, weight=None, ignore_index=-100, dice=True):
+    """logits NCHW fp32, target int64 -> (loss_out[3] = {total, ce, dice}, stats).  weight: fp32 [C] class weights of the
+    cross-entropy term or None; pixels labelled ignore_index enter neither term; dice=False drops the Dice term."""
+    _need_cuda(logits, target, weight)
     B, C_, H, W = logits.shape
-    stats = torch.empty((B * C_ * 3 + 1,), dtype=torch.float64, device=logits.device)
+    stats = torch.empty((B * C_ * 3 + 3,), dtype=torch.float64, device=logits.device)
     out = torch.empty((3,), dtype=torch.float32, device=logits.device)
-    check(_lib.load().stfb_ce_dice_fwd(_p(logits), _p(target), _p(stats), _p(out), B, C_, H * W, eps, _stream()), "ce_dice_fwd")
+    check(_lib.load().stfb_ce_dice_fwd_ex(_p(logits), _p(target), _p(weight), _p(stats), _p(out), B, C_, H * W, eps,
+                                          int(ignore_index), int(bool(dice)), _stream()), "ce_dice_fwd")
     return out, stats
 
 
-def ce_dice_bwd(logits, target, stats, dloss, eps=1e-6):
+def ce_dice_bwd(logits, target, stats, dloss, eps=1e-6, weight=None, ignore_index=-100, dice=True):
     B, C_, H, W = logits.shape
     dl = torch.empty_like(logits)
-    check(_lib.load().stfb_ce_dice_bwd(_p(logits), _p(target), _p(stats), _p(dloss), _p(dl), B, C_, H * W, eps, _stream()),
-          "ce_dice_bwd")
+    check(_lib.load().stfb_ce_dice_bwd_ex(_p(logits), _p(target), _p(weight), _p(stats), _p(dloss), _p(dl), B, C_, H * W, eps,
+                                          int(ignore_index), int(bool(dice)), _stream()), "ce_dice_bwd")
     return dl

@@ -50,7 +50,15 @@ class FlatAdamW(torch.optim.Optimizer):
     def _flat_grad(self):
         g = getattr(self.model, "_last_flat_grad", None)
         if g is None or g.numel() != self.flat_param.numel():
-            raise RuntimeError("FlatAdamW.step(): no flat gradient buffer -- run a forward/backward of the model first")
+            raise RuntimeError("FlatAdamW.step(): no flat gradient buffer -- run a forward/backward of the model first (or the "
+                               "parameters' .grad tensors were replaced by something other than the engine's flat views)")
+        # the flat buffer must be what the parameters' .grad view (engine.ModelFunction keeps that invariant; a foreign
+        # optimizer / user code that re-assigns .grad breaks it): checked on the first and last parameter, every step
+        first, last = self.param_groups[0]["params"][0], self.param_groups[0]["params"][-1]
+        if (first.grad is None or first.grad.data_ptr() != g.data_ptr()
+                or last.grad is None or last.grad.data_ptr() != g.data_ptr() + 4 * (g.numel() - last.numel())):
+            raise RuntimeError("FlatAdamW.step(): the parameters' .grad are not views of the model's flat gradient buffer "
+                               "(zero_grad(set_to_none=True) without a following backward, or gradients assigned by hand)")
         return g
 
     @torch.no_grad()

@@ -141,9 +141,37 @@ def metrics_case():
     print("metrics:", out["mat1"].tolist(), out["dice"].tolist())
 
 
+def criterion_options_case():
+    """criterion with the arguments the reference's signature accepts beyond its training defaults
+    (train_utils/train_and_eval.py:299-313): class weights, ignore_index = 255 (the value collate_fn pads targets with,
+    my_dataset.py:243), dice on / off; one image is ignored entirely (the `sets_sum == 0` branch,
+    dice_coefficient_loss.py:34-35)."""
+    g = np.random.Generator(np.random.PCG64(15))
+    out = {}
+    base = torch.from_numpy(g.standard_normal((4, 3, 20, 28)).astype(np.float32) * 2)
+    tgt = torch.from_numpy(g.integers(0, 3, size=(4, 20, 28)).astype(np.int64))
+    tgt[torch.from_numpy(g.uniform(size=(4, 20, 28)) < 0.15)] = 255
+    tgt[3] = 255                                       # a fully ignored image
+    w = torch.tensor([0.2, 1.0, 2.5])
+    out["logits"], out["target"], out["weight"] = base.numpy(), tgt.numpy(), w.numpy()
+    for tag, kw in (("w_ign_dice", dict(loss_weight=w, num_classes=3, dice=True, ignore_index=255)),
+                    ("ign_dice", dict(loss_weight=None, num_classes=3, dice=True, ignore_index=255)),
+                    ("w_ign_nodice", dict(loss_weight=w, num_classes=3, dice=False, ignore_index=255))):
+        logits = base.clone().requires_grad_(True)
+        loss = ref_criterion({"out": logits}, tgt, **kw)
+        loss.backward()
+        out["loss_" + tag] = np.float64(loss.item())
+        out["grad_" + tag] = logits.grad.numpy()
+        print("criterion", tag, loss.item())
+    np.savez_compressed(os.path.join(HERE, "criterion_options_4x3x20x28.npz"), **out)
+
+
 if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "metrics":
         metrics_case()
+    elif len(sys.argv) > 1 and sys.argv[1] == "criterion":
+        criterion_options_case()
     else:
         main()
         metrics_case()
+        criterion_options_case()

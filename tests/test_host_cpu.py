@@ -79,11 +79,22 @@ def test_param_counts_match_reference():
     assert sum(p.numel() for p in S.UNet(1, 2, 64).parameters()) == 31042434
 
 
-def test_criterion_rejects_unsupported_configuration():
-    with pytest.raises(NotImplementedError):
+def test_criterion_argument_checks_and_no_cpu_fallback():
+    """Every argument of the reference's criterion is accepted (loss_weight, dice, ignore_index); shape / class-count
+    mismatches raise before any launch; CPU tensors raise (no fallback)."""
+    with pytest.raises(RuntimeError, match="CUDA tensors"):
         S.criterion({"out": torch.zeros(1, 2, 4, 4)}, torch.zeros(1, 4, 4, dtype=torch.long), ignore_index=255)
     with pytest.raises(ValueError, match="size mismatch"):
         S.ce_dice(torch.zeros(1, 2, 4, 4), torch.zeros(1, 8, 8, dtype=torch.long))
+    with pytest.raises(ValueError, match="loss_weight"):
+        S.criterion({"out": torch.zeros(1, 2, 4, 4)}, torch.zeros(1, 4, 4, dtype=torch.long), loss_weight=torch.ones(3))
+    with pytest.raises(TypeError):
+        S.ce_dice(torch.zeros(1, 2, 4, 4), torch.zeros(1, 4, 4, dtype=torch.int32))
+    # build_target mirrors dice_coefficient_loss.py:5-17 (ignored pixels carry ignore_index in every channel)
+    from stf_unet_b200.loss import build_target
+    t = torch.tensor([[[0, 1], [255, 1]]])
+    bt = build_target(t, 2, 255)
+    assert bt.shape == (1, 2, 2, 2) and bt[0, :, 1, 0].tolist() == [255.0, 255.0] and bt[0, :, 0, 1].tolist() == [0.0, 1.0]
 
 
 def test_product_synthetic_generator_is_the_oracles_twin():

@@ -563,3 +563,98 @@ def test_eval_weight_packs_are_cached_until_a_parameter_changes():
     assert n5 == n1 and not torch.equal(y5, y4)
     y6, n6 = fwd()
     assert n6 == n1 - 1 and torch.equal(y6, y5)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# bf16 parity AT THE BENCHMARKED SIZES (BASELINE.json configs[1..3]) against the oracle run in fp32 (TF32 off) through cuDNN on
+# the same GPU.  These sizes engage code paths the small cases never reach: the two-kernel BatchNorm backward for maps
+# > 48 MB, 57-patch split-K weight gradients, several tiles per persistent CTA, CTA pairs on every 3x3 layer.
+# ---------------------------------------------------------------------------------------------------------------------
+def _grad_report(named_params, ref_grads, floor_grads=None):
+    """-> (cosine, norm ratio, worst per-parameter rel-L2 among parameters carrying >= 1e-3 of the gradient norm, its name,
+    the same worst figure for `floor_grads` = torch's own bf16-autocast gradients of the oracle)."""
+    num = den1 = den2 = 0.0
+    per, per_floor = {}, {}
+    for n, p in named_params:
+        gr = ref_grads[n].double().flatten()
+        gm = p.grad.double().flatten()
+        num += (gr * gm).sum().item()
+        den1 += (gr * gr).sum().item()
+        den2 += (gm * gm).sum().item()
+        per[n] = ((gm - gr).norm().item(), gr.norm().item())
+        if floor_grads is not None:
+            per_floor[n] = ((floor_grads[n].double().flatten() - gr).norm().item(), gr.norm().item())
+    total = den1 ** 0.5
+    big = [n for n, (_, nr) in per.items() if nr >= 1e-3 * total]
+    worst = max(big, key=lambda n: per[n][0] / per[n][1])
+    wf = max((per_floor[n][0] / per_floor[n][1] for n in big), default=float("nan")) if per_floor else float("nan")
+    return num / (den1 ** 0.5 * den2 ** 0.5), (den2 / den1) ** 0.5, per[worst][0] / per[worst][1], worst, wf
+
+
+def _train_parity_case(B, T, HW, seed, check_buffers=True):
+    x, t = W.synthetic_dce_batch(B, T, HW, HW, seed=seed)
+    x, t = x.to(DEV), t.to(DEV)
+    sd = warm_stf_state()
+    sd_dev = {k: v.to(DEV) for k, v in sd.items()}
+    ref_logits, ref_loss, ref_grads, ref_bufs = O.loss_and_grads(sd_dev, x, t, model="stf", train=True)
+    with torch.autocast("cuda", dtype=torch.bfloat16):          # the reference arithmetic's own bf16 gap: the noise floor
+        fl_logits, fl_loss, fl_grads, _ = O.loss_and_grads(sd_dev, x, t, model="stf", train=True)
+    fl_grads = {k: (None if v is None else v.float()) for k, v in fl_grads.items()}
+    floor = (rel(fl_logits.float(), ref_logits), argmax_agree(fl_logits.float(), ref_logits))
+    torch.cuda.empty_cache()
+    m = load_model(S.STFLSTMUNet(1, 2, T), sd)
+    m.train()
+    nbt0 = int(m.bn1.num_batches_tracked)
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        out = m(x)["out"]
+        loss = S.criterion({"out": out}, t)
+    loss.backward()
+    r, a = rel(out, ref_logits), argmax_agree(out, ref_logits)
+    cos, ratio, worst, wname, wfloor = _grad_report(list(m.named_parameters()), ref_grads, fl_grads)
+    print(f"train bf16 B={B} T={T} {HW}^2: logits rel={r:.3e} argmax={a:.5f} loss {loss.item():.6f} vs {ref_loss.item():.6f} | "
+          f"grad cos={cos:.5f} norm ratio={ratio:.4f} worst param rel={worst:.3e} ({wname}) | torch-autocast floor: logits "
+          f"rel={floor[0]:.3e} argmax={floor[1]:.5f} worst param rel={wfloor:.3e}")
+    assert r < 2e-2 and a >= 0.999                               # north_star: bf16 <= 2e-2, argmax >= 99.9 %
+    assert abs(loss.item() - ref_loss.item()) < 2e-2 * abs(ref_loss.item())
+    assert cos > 0.99 and 0.95 < ratio < 1.05
+    assert worst < max(5e-2, 2.0 * wfloor), (wname, worst, wfloor)   # no parameter may be worse than twice torch's own bf16
+    if check_buffers:
+        assert int(m.bn1.num_batches_tracked) == nbt0 + T            # T BatchNorm calls per forward (stf_lstm_unet.py:168-186)
+        assert int(m.decoder2.res_conv.conv_block["1"].num_batches_tracked) == int(sd["decoder2.res_conv.conv_block.1.num_batches_tracked"]) + 1
+        mine = m.state_dict()
+        for k, v in ref_bufs.items():
+            if k.endswith("num_batches_tracked"):
+                assert int(mine[k]) == int(v), k
+            else:
+                assert rel(mine[k], v) < 2e-2, (k, rel(mine[k], v))
+    return r, a
+
+
+def test_bench_size_eval_bf16_vs_oracle():
+    """BASELINE.json configs[1]: eval forward, batch 16 x T=8 x 256x256, bf16 vs the fp32 oracle on warm weights."""
+    x, _ = W.synthetic_dce_batch(16, 8, 256, 256, seed=1234)
+    x = x.to(DEV)
+    sd = warm_stf_state()
+    sd_dev = {k: v.to(DEV) for k, v in sd.items()}
+    with torch.no_grad():
+        ref = O.stf_forward(sd_dev, x, train=False)
+    floor = oracle_bf16_floor(sd_dev, x, False)
+    m = load_model(S.STFLSTMUNet(1, 2, 8), sd).eval()
+    with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16):
+        y = m(x)["out"]
+    r, a = rel(y, ref), argmax_agree(y, ref)
+    print(f"configs[1] eval bf16: rel={r:.3e} argmax={a:.5f} | torch-autocast floor rel={floor[0]:.3e} argmax={floor[1]:.5f}")
+    assert y.shape == (16, 2, 128, 128)
+    assert r < 2e-2 and a >= 0.999
+
+
+def test_bench_size_train_step_bf16_vs_oracle():
+    """BASELINE.json configs[2], one GPU's shard: 16 slices x T=8 x 256x256, train-mode forward + CE/Dice + backward in
+    bf16 vs the fp32 oracle: logits, argmax, loss, the whole gradient (cosine / norm / worst parameter against torch's own
+    bf16-autocast floor), every BatchNorm buffer, num_batches_tracked += 8."""
+    _train_parity_case(16, 8, 256, 1234)
+
+
+def test_config3_train_step_bf16_vs_oracle():
+    """BASELINE.json configs[3]: T=16 phases x 512x512 (B=2 here: the oracle keeps every fp32 activation alive)."""
+    _train_parity_case(2, 16, 512, 4321)

@@ -357,6 +357,39 @@ def test_ce_dice_golden(golden_dir):
     assert rel(dl.cpu(), torch.from_numpy(g["grad"])) < 2e-5
 
 
+@pytest.mark.parametrize("tag,weighted,dice", [("w_ign_dice", True, True), ("ign_dice", False, True), ("w_ign_nodice", True, False)])
+def test_ce_dice_options_golden(golden_dir, tag, weighted, dice):
+    """criterion(loss_weight, ignore_index=255, dice) through stf_unet_b200.criterion == the reference's own criterion
+    (train_utils/train_and_eval.py:299-313) on a fixture with ignored pixels and one fully ignored image."""
+    import numpy as np
+    import os
+    import stf_unet_b200 as S
+    g = np.load(os.path.join(golden_dir, "criterion_options_4x3x20x28.npz"))
+    logits = torch.from_numpy(g["logits"]).to(DEV).requires_grad_(True)
+    target = torch.from_numpy(g["target"]).to(DEV)
+    w = torch.from_numpy(g["weight"]).to(DEV) if weighted else None
+    loss = S.criterion({"out": logits}, target, loss_weight=w, num_classes=3, dice=dice, ignore_index=255)
+    loss.backward()
+    assert abs(loss.item() - float(g["loss_" + tag])) < 2e-6 * max(1.0, abs(float(g["loss_" + tag])))
+    assert rel(logits.grad.cpu(), torch.from_numpy(g["grad_" + tag])) < 2e-5
+    # ignored pixels carry exactly zero gradient
+    assert logits.grad[3].abs().max().item() == 0.0
+
+
+def test_ce_dice_flags_labels_out_of_range(monkeypatch):
+    """A label outside [0, C) that is not ignore_index: the reference raises; here the loss is NaN (no host sync), or an
+    IndexError with STFB_CHECK_TARGETS=1."""
+    import stf_unet_b200 as S
+    logits = rnd(2, 2, 8, 8, seed=1)
+    target = torch.zeros(2, 8, 8, dtype=torch.int64, device=DEV)
+    target[0, 0, 0] = 255
+    assert torch.isnan(S.criterion({"out": logits}, target))
+    assert torch.isfinite(S.criterion({"out": logits}, target, ignore_index=255))
+    monkeypatch.setenv("STFB_CHECK_TARGETS", "1")
+    with pytest.raises(IndexError):
+        S.criterion({"out": logits}, target)
+
+
 def test_errors_are_raised_not_swallowed():
     x = torch.zeros(1, 4, 4, 8, device=DEV)
     wp = torch.zeros(8, 8, device=DEV)
@@ -400,13 +433,18 @@ TC_CASES = [
 ]
 
 
-@pytest.mark.parametrize("halo_mt", ["0", "2"])
+@pytest.mark.parametrize("halo_mode", ["single", "mt2", "pair"])
 @pytest.mark.parametrize("case", TC_CASES)
-def test_conv_tcgen05_matches_reference(case, halo_mt, monkeypatch):
+def test_conv_tcgen05_matches_reference(case, halo_mode, monkeypatch):
+    """single: one CTA per tile; mt2: two pixel tiles per weight pass (STFB_HALO_MT=2); pair: CTA pairs driving M = 256
+    MMAs (tcgen05 cta_group::2, the default whenever a 3x3 layer's pixel tiles pair up)."""
     N, H, W, C1, C2, Cout, k = case
-    if halo_mt == "2" and not (k == 3 and N * H * W >= 148 * 96):
+    if halo_mode == "mt2" and not (k == 3 and N * H * W >= 148 * 96):
         pytest.skip("tile pairing (STFB_HALO_MT=2) only engages on 3x3 layers with >= 111 super tiles")
-    monkeypatch.setenv("STFB_HALO_MT", halo_mt)
+    if halo_mode == "pair" and not (k == 3 and H >= 12 and W >= 8):
+        pytest.skip("CTA pairs only engage on the halo (3x3 / stride 1, maps >= 12 x 8) path")
+    monkeypatch.setenv("STFB_HALO_MT", "2" if halo_mode == "mt2" else "0")
+    monkeypatch.setenv("STFB_HALO_PAIR", "1" if halo_mode == "pair" else "0")
     dtype = torch.bfloat16
     pad = (k - 1) // 2
     x = q(rnd(N, C1 + C2, H, W, seed=1), dtype)
@@ -710,11 +748,13 @@ def test_eval_metrics_kernel_matches_golden_and_oracle(golden_dir):
 @pytest.mark.parametrize("case", [(16, 32, 32, 64, 64, 3, 1, 8), (8, 16, 16, 128, 256, 3, 1, 4), (32, 8, 8, 128, 128, 3, 1, 8),
                                   (6, 25, 19, 64, 128, 3, 1, 3), (8, 32, 32, 64, 128, 3, 2, 2), (12, 16, 16, 64, 64, 1, 1, 4),
                                   (40, 32, 32, 64, 64, 3, 1, 5)])
-def test_conv_fused_bn_statistics(case):
+@pytest.mark.parametrize("pair", ["0", "1"])
+def test_conv_fused_bn_statistics(case, pair, monkeypatch):
     """Train-mode BatchNorm statistics (per image group sum / sum of squares of the bf16 outputs) reduced in the conv
     epilogue == the separate bn_stats pass over the stored output (reference: nn.BatchNorm2d after every conv,
     src/stf_lstm_unet.py:14,17 ; one call per time step -> per-group statistics, :168-186)."""
     N, H, W, Cin, Cout, k, stride, G = case
+    monkeypatch.setenv("STFB_HALO_PAIR", pair)
     dtype = torch.bfloat16
     pad = (k - 1) // 2
     x = nhwc(q(rnd(N, Cin, H, W, seed=1), dtype), dtype)

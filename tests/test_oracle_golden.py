@@ -107,6 +107,19 @@ def test_criterion(golden_dir):
     assert rel(logits.grad.numpy(), g["grad"]) < 1e-5
 
 
+@pytest.mark.parametrize("tag,kw", [("w_ign_dice", dict(weighted=True, dice=True)), ("ign_dice", dict(weighted=False, dice=True)),
+                                    ("w_ign_nodice", dict(weighted=True, dice=False))])
+def test_criterion_options(golden_dir, tag, kw):
+    """class weights / ignore_index=255 / dice off, one image ignored entirely: fixture from the reference's criterion."""
+    g = load(golden_dir, "criterion_options_4x3x20x28")
+    logits = torch.from_numpy(g["logits"]).requires_grad_(True)
+    w = torch.from_numpy(g["weight"]) if kw["weighted"] else None
+    loss = O.criterion(logits, torch.from_numpy(g["target"]), loss_weight=w, dice=kw["dice"], ignore_index=255)
+    loss.backward()
+    assert abs(loss.item() - float(g["loss_" + tag])) < 1e-6
+    assert rel(logits.grad.numpy(), g["grad_" + tag]) < 1e-5
+
+
 def test_eval_metrics_oracle_matches_reference_classes(golden_dir):
     """oracle.eval_metrics_batch == ConfusionMatrix / DiceCoefficient of the live reference (fixture from make_golden.py)."""
     g = load(golden_dir, "eval_metrics_2x3x2x24x40")
