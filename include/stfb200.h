@@ -344,6 +344,28 @@ int stfb_ce_dice_bwd_ex(const float* logits, const long long* target, const floa
                         const float* dloss, float* dlogits, int B, int C, int HW, float eps, long long ignore_index,
                         int with_dice, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Extended Tofts pharmacokinetic model per pixel (offline PK-map preprocessing).
+ * Replaces: ToftsModelFitter.extended_tofts_model_batch (pk_fitting.py:193-231) and the Adam fitting loop of
+ * ToftsModelFitter.fit_volume_gpu (pk_fitting.py:288-368).
+ * Tables (device, fp32): t[T] acquisition times, aif_t[T] = aif(t), t_conv[M] = arange(0, t_max, dt), aif_conv[M] =
+ * aif(t_conv), nvalid[T] (int32) = number of grid points with t_conv < t[i].  T <= 32.
+ *   stfb_tofts_forward: out[N,T] = vp*aif(t_i) + Ktrans*dt*sum_{tc_j < t_i} aif(tc_j) exp(-Ktrans (t_i - tc_j)/ve)
+ *   stfb_tofts_fit:     pixels[N,T] observed curves; ktrans/ve/vp[N] initial values in, fitted values out.  Replays the
+ *     reference's optimisation exactly: ONE Adam state over all N pixels stepped once per batch of `batch_size` consecutive
+ *     pixels (pixels outside the batch see a zero gradient and still move by their momentum), MSE mean over the batch,
+ *     clamp to [clamp_lo, clamp_hi] (host arrays of 3: Ktrans, ve, vp) after every step.  step_size / bc2_sqrt: device
+ *     arrays [epochs * ceil(N / batch_size)] with lr / (1 - beta1^s) and sqrt(1 - beta2^s), s = 1, 2, ... (formed in
+ *     double on the host like torch).  epoch_loss: optional device fp32 [epochs], mean batch loss per epoch.
+ * ---------------------------------------------------------------------------------------------- */
+int stfb_tofts_forward(const float* t, const float* aif_t, const float* t_conv, const float* aif_conv, const int* nvalid,
+                       int T, int M, float dt, const float* ktrans, const float* ve, const float* vp, float* out,
+                       long long N, void* stream);
+int stfb_tofts_fit(const float* pixels, const float* t, const float* aif_t, const float* t_conv, const float* aif_conv,
+                   const int* nvalid, int T, int M, float dt, float* ktrans, float* ve, float* vp, long long N,
+                   int batch_size, int epochs, const float* step_size, const float* bc2_sqrt, float beta1, float beta2,
+                   float eps, const float* clamp_lo, const float* clamp_hi, float* epoch_loss, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

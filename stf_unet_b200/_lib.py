@@ -75,6 +75,8 @@ _SIGS = {
     "stfb_ce_dice_bwd": [_vp] * 5 + [_i, _i, _i, _f, _vp],
     "stfb_ce_dice_fwd_ex": [_vp] * 5 + [_i, _i, _i, _f, _ll, _i, _vp],
     "stfb_ce_dice_bwd_ex": [_vp] * 6 + [_i, _i, _i, _f, _ll, _i, _vp],
+    "stfb_tofts_forward": [_vp] * 5 + [_i, _i, _f] + [_vp] * 4 + [_ll, _vp],
+    "stfb_tofts_fit": [_vp] * 6 + [_i, _i, _f] + [_vp] * 3 + [_ll, _i, _i, _vp, _vp, _f, _f, _f, _vp, _vp, _vp, _vp],
 }
 EXPORTS = sorted(list(_SIGS) + list(_SIZE_T_FUNCS) + ["stfb_version", "stfb_last_error", "stfb_launch_count"])
 

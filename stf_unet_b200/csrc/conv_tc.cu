@@ -916,6 +916,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(HALO2_THREADS, 1)
     if (elect_one()) {
       int sa = 0;
       uint32_t pa = 0, nblk = 0;
+      bool first = true;
       for (int st = cid; st < n_super; st += ncl) {
         const int nt = st % n_tiles, pp = st / n_tiles;
         const TileCoord t = decode_tile<BN>(a, (pp * 2 + (int)rank) * n_tiles + nt, n_tiles, cpt);
@@ -928,6 +929,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(HALO2_THREADS, 1)
           if (cc < a.C1) tma_load_4d_pair(sA + sa * HALO_BLK_BYTES, &tmA, af, cc, w0, h0, t.nb);
           else tma_load_4d_pair(sA + sa * HALO_BLK_BYTES, &tmA2, af, cc - a.C1, w0, h0, t.nb);
           if (++sa == SA) { sa = 0; pa ^= 1; }
+          if (!first && a.w_resident) continue;        // the whole (half) weight matrix sits in the 9-slot ring since the first tile
 #pragma unroll
           for (int tp = 0; tp < 9; ++tp) {
             const int sb = tp % SB;
@@ -937,6 +939,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(HALO2_THREADS, 1)
             tma_load_2d_pair(sB + sb * BH_BYTES, &tmB, bf, (int)a.ktap[0][tp] * Cin + cc, nt * BN + (int)rank * (BN / 2));
           }
         }
+        first = false;
       }
     }
   } else if (warp == 1) {
@@ -945,6 +948,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(HALO2_THREADS, 1)
       constexpr uint32_t idesc = make_idesc_bf16(256, BN);
       int sa = 0;
       uint32_t pa = 0, nblk = 0, it = 0;
+      bool first = true;
       for (int st = cid; st < n_super; st += ncl, ++it) {
         const int acc = (int)(it & 1);
         mbar_wait(&tempty_bar[acc], ((it >> 1) & 1) ^ 1);
@@ -956,24 +960,28 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(HALO2_THREADS, 1)
           const int sa_used = sa;
           if (++sa == SA) { sa = 0; pa ^= 1; }
           tc_fence_after();
+          const bool streamed = first || !a.w_resident;
           if (elect_one()) {
 #pragma unroll
             for (int tp = 0; tp < 9; ++tp) {
               const int sb = tp % SB;
-              mbar_wait(&bfull[sb], (nblk * WRAPS + tp / SB) & 1);
-              tc_fence_after();
+              if (streamed) {
+                mbar_wait(&bfull[sb], (nblk * WRAPS + tp / SB) & 1);
+                tc_fence_after();
+              }
               const uint64_t bdesc = make_kmajor_sw128_desc(sB + sb * BH_BYTES);
               const uint64_t adesc = make_halo_a_desc(ablk + halo_tap_off(tp));
 #pragma unroll
               for (int k = 0; k < 4; ++k)
                 umma_bf16_pair(tmem_acc, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (c | tp | k) != 0);
-              umma_commit_pair(&bempty[sb]);
+              if (!a.w_resident) umma_commit_pair(&bempty[sb]);
             }
             umma_commit_pair(&aempty[sa_used]);
             if (c == cpt - 1) umma_commit_pair(&tfull_bar[acc]);
           }
           __syncwarp();
         }
+        first = false;
       }
     }
   } else {
@@ -1307,7 +1315,9 @@ int conv2d_tcgen05(const stfb_conv_params* p, cudaStream_t st) {
           set_error("conv2d(tcgen05 pair): cuTensorMapEncodeTiled failed for the weights"); return STFB_ECUDA;
         }
         const int n_super2 = (pix_tiles / 2) * n_tiles_;
-        a.w_resident = 0;
+        // one channel block, one output-channel block, nine ring slots: the CTA's half of the weight matrix (36 KB at 64 -> 64)
+        // is loaded once and stays resident
+        a.w_resident = (cpt == 1 && n_tiles_ == 1 && BN <= 128) ? 1 : 0;
 #define HALO2_LAUNCH(BN_, SA_, SB_)                                                                            \
         return f32out ? launch_halo2<BN_, SA_, SB_, float>(tA, tA2, tBh, a, n_super2, st)                     \
                       : launch_halo2<BN_, SA_, SB_, __nv_bfloat16>(tA, tA2, tBh, a, n_super2, st)

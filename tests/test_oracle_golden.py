@@ -132,3 +132,21 @@ def test_eval_metrics_oracle_matches_reference_classes(golden_dir):
         assert np.array_equal(mat.numpy(), g[f"mat{i}"])
         assert np.allclose(cum.numpy(), g[f"dice_cum{i}"], rtol=0, atol=1e-6)
     assert np.allclose((cum / 2).numpy(), g["dice"], atol=1e-6)
+
+
+def test_tofts_oracle_matches_reference_class(golden_dir):
+    """oracle.tofts_oracle == ToftsModelFitter (pk_fitting.py:193-231, :288-368): fixture from the live reference class."""
+    from oracle import tofts_oracle as TO
+    g = load(golden_dir, "tofts_fit_80x80")
+    t = torch.arange(8, dtype=torch.float32)
+    k, e, v = (torch.from_numpy(g[n]) for n in ("fwd_k", "fwd_ve", "fwd_vp"))
+    assert np.array_equal(TO.extended_tofts_model_batch(t, k, e, v).numpy(), g["fwd_out"])
+    short = torch.from_numpy(g["fwd_t_short"])
+    assert np.array_equal(TO.extended_tofts_model_batch(short, k, e, v).numpy(), g["fwd_out_short"])
+    mask = torch.from_numpy(g["tissue_mask"]).reshape(-1)
+    assert int(mask.sum()) > 1024                       # more than one Adam batch: the zero-gradient momentum steps are exercised
+    valid = (torch.from_numpy(g["series"]).float() / 255.0).permute(1, 2, 0).reshape(-1, 8)[mask]
+    kk, ee, vv, losses = TO.fit_pixels(t, valid, epochs=100)
+    maps = g["maps_100"].reshape(3, -1)[:, mask.numpy()]
+    assert np.array_equal(np.stack([kk.numpy(), ee.numpy(), vv.numpy()]), maps)
+    assert np.allclose(losses.numpy(), g["losses_100"], rtol=0, atol=0)

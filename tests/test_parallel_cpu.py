@@ -93,10 +93,29 @@ def test_bench_reference_arm_prints_contract_line(impl, capsys, monkeypatch):
     monkeypatch.setattr(bench, "T_PHASES", 2)
 
     class A:
-        steps, warmup, gpus = 1, 0, 1
+        steps, warmup, gpus, workload = 1, 0, 1, "train"
     bench.run_reference(A, 0)
     line = json.loads(capsys.readouterr().out.strip().splitlines()[-1])
     assert line["impl"] == "reference" and line["unit"] == "slices/s" and line["value"] > 0
-    assert line["cpu_baseline"]["kind"] == "port" and line["e2e"]["h2d_bytes_per_step"] == 0
+    # the unmodified reference when it is installed (baseline/_ref or the build container's /root/reference), else the port
+    want = "reference" if bench.reference_root() is not None else "port"
+    assert line["cpu_baseline"]["kind"] == want and line["e2e"]["h2d_bytes_per_step"] == 0
+    assert "CUDA graph" not in line["config"]["launch"]         # the arm's own launch description, not the GPU arm's
+    assert line["config"]["workload"] == bench.workload_config(1)["workload"]
     bench.run_reference(A, 1)                                   # non-zero ranks print nothing
     assert capsys.readouterr().out == ""
+
+
+def test_bench_reference_arm_falls_back_to_the_oracle_port(capsys, monkeypatch):
+    """Without baseline/_ref (a checkout where tools/install_ref.sh never ran) the arm still answers: kind = "port"."""
+    import json
+    import bench
+    monkeypatch.setattr(bench, "HW", 32)
+    monkeypatch.setattr(bench, "T_PHASES", 2)
+    monkeypatch.setattr(bench, "_REF", False)
+
+    class A:
+        steps, warmup, gpus, workload = 1, 0, 1, "train"
+    bench.run_reference(A, 0)
+    line = json.loads(capsys.readouterr().out.strip().splitlines()[-1])
+    assert line["cpu_baseline"]["kind"] == "port" and line["value"] > 0
