@@ -366,6 +366,33 @@ int stfb_tofts_fit(const float* pixels, const float* t, const float* aif_t, cons
                    int batch_size, int epochs, const float* step_size, const float* bc2_sqrt, float beta1, float beta2,
                    float eps, const float* clamp_lo, const float* clamp_hi, float* epoch_loss, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Paired train-time augmentation on the device.
+ * Replaces: get_transform(train=True) (train.py:51-67) = transforms.py RandomResize :18-33, RandomHorizontalFlip :36-45,
+ * RandomVerticalFlip :48-57, RandomRotation :136-157, RandomCrop :60-117, ToTensor :120-125, Normalize :127-134, which the
+ * reference's loader applies per phase on the CPU through PIL (my_dataset.py:173-179).
+ * series uint8 [B,T,H,W], masks uint8 [B,H,W] (values {0,1}; NULL when no target is wanted); x_out fp32 [B,T,1,S,S]
+ * normalised crops, target_out int64 [B, ceil(S/stride), ceil(S/stride)] (the mask crop, every stride-th pixel; NULL = skip).
+ * samples_dev: one stfb_aug_sample per batch element (host-drawn geometry, shared by all phases and the mask);
+ * tables_dev: int32 tables, per sample at tab_off: hb[rw][2], hk[rw][ksize_h], vb[rh][2], vk[rh][ksize_v] (Pillow's bilinear
+ * resize: first source index / tap count and 22-bit fixed-point coefficients per output index; ksize == 0: that pass is the
+ * identity), xtab[rw], ytab[rh] (source index of Pillow's nearest resize, -1 = outside).
+ * Output is bit-identical to the PIL pipeline on 8-bit single-channel images.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct stfb_aug_sample {
+  int rh, rw;              /* size after RandomResize */
+  int hflip, vflip, rot;   /* 0 / 1 */
+  int h0, w0;              /* RandomCrop origin in the (zero padded) image */
+  int tab_off;             /* offset of this sample's tables in tables_dev, in ints */
+  int ksize_h, ksize_v;    /* taps per output index of the horizontal / vertical resize pass (0: pass skipped) */
+  int fix[6];              /* 16.16 fixed-point affine of Image.rotate(NEAREST): a0, a1, a2, a3, a4, a5 */
+  int pad_;
+  double m[6];             /* double affine of Image.rotate(BILINEAR): output pixel centre -> input coordinate */
+} stfb_aug_sample;
+int stfb_augment_series_u8(const unsigned char* series, const unsigned char* masks, const stfb_aug_sample* samples_dev,
+                           const int* tables_dev, float* x_out, long long* target_out, int B, int T, int H, int W, int S,
+                           int target_stride, float mean, float stdv, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -159,8 +159,9 @@ extern "C" int stfb_tofts_forward(const float* t, const float* aif_t, const floa
   ToftsTables tb{t, aif_t, t_conv, aif_conv, nvalid, T, M, dt};
   int st = check_tables(tb, "tofts_forward");
   if (st != STFB_OK) return st;
-  STFB_REQUIRE(ktrans && ve && vp && out && N >= 0, "tofts_forward: bad arguments");
-  if (N == 0) return STFB_OK;
+  STFB_REQUIRE(N >= 0, "tofts_forward: negative pixel count");
+  if (N == 0) return STFB_OK;                              // empty batch: nothing to launch (pointers may be null)
+  STFB_REQUIRE(ktrans && ve && vp && out, "tofts_forward: null argument");
   const size_t smem = (size_t)M * 8;
   st = reserve_smem(tofts_forward_kernel, smem, "tofts_forward");
   if (st != STFB_OK) return st;
@@ -178,9 +179,9 @@ extern "C" int stfb_tofts_fit(const float* pixels, const float* t, const float* 
   ToftsTables tb{t, aif_t, t_conv, aif_conv, nvalid, T, M, dt};
   int st = check_tables(tb, "tofts_fit");
   if (st != STFB_OK) return st;
-  STFB_REQUIRE(pixels && ktrans && ve && vp && step_size && bc2_sqrt && clamp_lo && clamp_hi, "tofts_fit: null argument");
   STFB_REQUIRE(N >= 0 && batch_size > 0 && epochs >= 0, "tofts_fit: bad sizes");
   if (N == 0 || epochs == 0) return STFB_OK;
+  STFB_REQUIRE(pixels && ktrans && ve && vp && step_size && bc2_sqrt && clamp_lo && clamp_hi, "tofts_fit: null argument");
   ToftsFit f{};
   f.batch_size = batch_size; f.epochs = epochs; f.num_batches = (int)((N + batch_size - 1) / batch_size);
   f.step_size = step_size; f.bc2_sqrt = bc2_sqrt;

@@ -25,6 +25,13 @@ USE_LSTM_STREAMS = _os.environ.get("STFB_NO_LSTM_STREAMS", "0") != "1"
 USE_WGRAD_STREAM = _os.environ.get("STFB_NO_WGRAD_STREAM", "0") != "1"
 USE_SIDE_FINALIZE = _os.environ.get("STFB_NO_SIDE_FINALIZE", "0") != "1"
 USE_FUSED_STEM = _os.environ.get("STFB_NO_FUSED_STEM", "0") != "1"
+# Two forward chains: the encoder's time steps are independent until the LSTMs (BatchNorm statistics are per time step), so
+# in the training forward every encoder layer is launched as two half-batch launches (time steps [0, T/2) and [T/2, T)) on two
+# streams.  Each chain alternates tensor-bound convolutions with HBM-bound BatchNorm passes; the two chains drift out of
+# phase and the block scheduler co-runs one chain's BatchNorm pass with the other's convolution (nothing else is
+# independent of the main chain in the forward pass).  Tensors stay whole (a half is a leading-dimension view), so the backward
+# tape is unchanged.  STFB_NO_FWD_SPLIT=1 disables.
+USE_FWD_SPLIT = _os.environ.get("STFB_NO_FWD_SPLIT", "0") != "1"
 # Stream priorities: the main chain (graph capture stream, LSTM forks, BatchNorm finalize) is HIGH priority and the
 # weight-gradient side streams stay at the default (lowest) one, so the block scheduler hands freed SM slots to the critical
 # path first and the tensor-bound wgrad CTAs fill what is left.  Measured on the graph step: 10.29 -> 10.08 ms with one wgrad
@@ -79,10 +86,46 @@ class Executor:
         self.grad_offsets: Dict[str, int] = {}
         self._deferred = {}           # name -> (flat offset, Cp, Cg_total, khw)
         self.flat = None              # this forward's flat gradient buffer (self.grads are views of it)
+        self.segment_hook = None      # callable(flat_slice): gradient range final (data-parallel all-reduce); None = off
+        self._seg_end = None
+        self._comm_used = False
+        self._owner_for_plans = None
         self._wg_keep = []            # (dy, x) pairs the side-stream wgrad launches still read
         self._fin_keep = []           # (slots, coefficients) the side-stream BatchNorm finalize launches still touch
 
     # ---------------------------------------------------------------------------------------------
+    _split_streams = {}
+
+    def begin_split(self, G):
+        """Start the two-chain section (see USE_FWD_SPLIT): only in the recording bf16 training forward -- every tensor is
+        then kept alive by the tape until the backward pass, so no allocation made on the main stream is recycled while a
+        chain stream still reads it."""
+        self._split = None
+        if not (USE_FWD_SPLIT and self.record and self.train and self.dtype == torch.bfloat16 and G >= 2 and G % 2 == 0):
+            return
+        cur = torch.cuda.current_stream()
+        pool = Executor._split_streams.get(cur.device.index)
+        if pool is None:
+            pool = Executor._split_streams[cur.device.index] = [torch.cuda.Stream(device=cur.device, priority=MAIN_PRIO) for _ in range(2)]
+        for st_ in pool:
+            st_.wait_stream(cur)
+        self._split = pool
+
+    def end_split(self):
+        if getattr(self, "_split", None):
+            cur = torch.cuda.current_stream()
+            for st_ in self._split:
+                cur.wait_stream(st_)
+        self._split = None
+
+    def _halves(self, N, G):
+        """[(stream, n0, n1, g0, g1)] of the two chains, or None when this tensor cannot be halved on a group boundary."""
+        sp = getattr(self, "_split", None)
+        if not sp or G < 2 or G % 2 or N % G:
+            return None
+        nh, gh = (N // G) * (G // 2), G // 2
+        return [(sp[0], 0, nh, 0, gh), (sp[1], nh, N, gh, G)]
+
     def packed(self, name, k_is_dim1, n_major=False, flip=False, kpad=None, gate_c=0):
         key = (name, bool(k_is_dim1), bool(n_major), bool(flip), kpad, int(gate_c))
         wp = self._packed.get(key)
@@ -238,9 +281,23 @@ class Executor:
         if stats_G and tc and not transposed and y_dtype in (None, torch.bfloat16) and self.stats_fusable(x.data, Cout, k, stride, pad, stats_G, x2d):
             # train-mode BatchNorm statistics of the output come out of the conv epilogue (no separate pass over y)
             partial = self.stat_buffer(stats_G, Cout, x.data.device)
-        y = ops.conv2d(x.data, wp, Cout, k, stride, pad, mode=mode, out_hw=out_hw, x2=x2d,
-                       bias=bias, scale=scale, shift=shift, residual=residual, relu=relu, y_dtype=y_dtype,
-                       impl=ops.IMPL_TCGEN05 if tc else ops.IMPL_SIMT, stat_partial=partial, stat_groups=stats_G if partial is not None else 0)
+        halves = self._halves(N, stats_G) if (stats_G and scale is None and residual is None and not relu) else None
+        if halves is not None:
+            y = torch.empty((N, out_hw[0], out_hw[1], Cout), dtype=y_dtype or x.data.dtype, device=x.data.device)
+            plist = None
+            if partial is not None:       # one statistics buffer per chain (groups are renumbered inside each half)
+                plist = [partial.view(-1)[:partial.numel() // 2].view(ops.STAT_SLOTS, 2, stats_G // 2, Cout),
+                         partial.view(-1)[partial.numel() // 2:].view(ops.STAT_SLOTS, 2, stats_G // 2, Cout)]
+            for h, (st_, n0, n1, g0, g1) in enumerate(halves):
+                with torch.cuda.stream(st_):
+                    ops.conv2d(x.data[n0:n1], wp, Cout, k, stride, pad, mode=mode, out_hw=out_hw, x2=None if x2d is None else x2d[n0:n1],
+                               bias=bias, y_dtype=y_dtype, out=y[n0:n1], impl=ops.IMPL_TCGEN05 if tc else ops.IMPL_SIMT,
+                               stat_partial=None if plist is None else plist[h], stat_groups=(g1 - g0) if plist is not None else 0)
+            partial = plist
+        else:
+            y = ops.conv2d(x.data, wp, Cout, k, stride, pad, mode=mode, out_hw=out_hw, x2=x2d,
+                           bias=bias, scale=scale, shift=shift, residual=residual, relu=relu, y_dtype=y_dtype,
+                           impl=ops.IMPL_TCGEN05 if tc else ops.IMPL_SIMT, stat_partial=partial, stat_groups=stats_G if partial is not None else 0)
         out = Var(y, grad_dtype=self.dtype)
         out.bn_partial = partial
         if not self.record:
@@ -285,14 +342,31 @@ class Executor:
         w = self.params[wname]
         Cout, Cin = w.shape[0], w.shape[1]
         kpad = (Cin * k * k + 63) // 64 * 64
-        col = ops.im2col_small(x.data, k, stride, pad, kpad)
         wp = self.packed(wname, True, n_major=True, kpad=kpad)
         bias = self.params[bname] if bname else None
-        partial = None
-        if stats_G and y_dtype in (None, torch.bfloat16) and self.stats_fusable(col, Cout, 1, 1, 0, stats_G):
-            partial = self.stat_buffer(stats_G, Cout, col.device)
-        y = ops.conv2d(col, wp, Cout, 1, 1, 0, bias=bias, scale=scale, shift=shift, relu=relu, y_dtype=y_dtype,
-                       impl=ops.IMPL_TCGEN05, stat_partial=partial, stat_groups=stats_G if partial is not None else 0)
+        N = x.data.shape[0]
+        halves = self._halves(N, stats_G) if (stats_G and scale is None and not relu) else None
+        if halves is not None:
+            Ho, Wo = ops.conv_out_hw(x.data.shape[1], x.data.shape[2], k, stride, pad)
+            col = torch.empty((N, Ho, Wo, kpad), dtype=torch.bfloat16, device=x.data.device)
+            y = torch.empty((N, Ho, Wo, Cout), dtype=y_dtype or torch.bfloat16, device=x.data.device)
+            partial = None
+            if y_dtype in (None, torch.bfloat16) and self.stats_fusable(col[halves[0][1]:halves[0][2]], Cout, 1, 1, 0, stats_G // 2):
+                whole = self.stat_buffer(stats_G, Cout, col.device)
+                partial = [whole.view(-1)[:whole.numel() // 2].view(ops.STAT_SLOTS, 2, stats_G // 2, Cout),
+                           whole.view(-1)[whole.numel() // 2:].view(ops.STAT_SLOTS, 2, stats_G // 2, Cout)]
+            for h, (st_, n0, n1, g0, g1) in enumerate(halves):
+                with torch.cuda.stream(st_):
+                    ops.im2col_small(x.data[n0:n1], k, stride, pad, kpad, out=col[n0:n1])
+                    ops.conv2d(col[n0:n1], wp, Cout, 1, 1, 0, bias=bias, y_dtype=y_dtype, out=y[n0:n1], impl=ops.IMPL_TCGEN05,
+                               stat_partial=None if partial is None else partial[h], stat_groups=(g1 - g0) if partial is not None else 0)
+        else:
+            col = ops.im2col_small(x.data, k, stride, pad, kpad)
+            partial = None
+            if stats_G and y_dtype in (None, torch.bfloat16) and self.stats_fusable(col, Cout, 1, 1, 0, stats_G):
+                partial = self.stat_buffer(stats_G, Cout, col.device)
+            y = ops.conv2d(col, wp, Cout, 1, 1, 0, bias=bias, scale=scale, shift=shift, relu=relu, y_dtype=y_dtype,
+                           impl=ops.IMPL_TCGEN05, stat_partial=partial, stat_groups=stats_G if partial is not None else 0)
         out = Var(y, grad_dtype=self.dtype)
         out.bn_partial = partial
         if not self.record:
@@ -318,19 +392,16 @@ class Executor:
         return out
 
     # ---------------------------------------------------------------------------------------------
-    def bn(self, x: Var, prefix: str, G: int, relu: bool, residual: Optional[Var] = None) -> Var:
-        """Train-mode BatchNorm2d over G row groups (+residual)(+ReLU)."""
-        N, H, W, C = x.data.shape
-        assert N % G == 0
-        R = (N // G) * H * W
+    def _bn_forward(self, xd, sums, prefix, G, R, C, relu, resd, y_out, st_out):
+        """Statistics (unless the conv epilogue produced them) -> finalize -> apply on the CURRENT stream; -> (y, st) with
+        st = [scale, shift, mean, invstd] x [G, C].  y_out / st_out: views to fill (two-chain section)."""
         P = self.params
-        sums = x.bn_partial if x.bn_partial is not None else ops.bn_stats(x.data, G, R, C)
-        x.bn_partial = None
-        resd = None if residual is None else residual.data
-        if USE_SIDE_FINALIZE and sums.shape[0] <= 8 and x.data.is_cuda and 2 * C * 4 <= 48 * 1024:
+        if sums is None:
+            sums = ops.bn_stats(xd, G, R, C)
+        st = st_out if st_out is not None else torch.empty((4, G, C), dtype=torch.float32, device=xd.device)
+        if USE_SIDE_FINALIZE and sums.shape[0] <= 8 and xd.is_cuda and 2 * C * 4 <= 48 * 1024:
             # few slots (the conv epilogue's): the apply kernel derives scale/shift itself and the finalize launch -- now
             # only the running statistics and the coefficients the backward pass reads -- runs beside the main chain
-            st = torch.empty((4, G, C), dtype=torch.float32, device=x.data.device)
             cur = torch.cuda.current_stream()
             side = Executor._fin_streams.get(cur.device.index)
             if side is None:
@@ -341,12 +412,37 @@ class Executor:
                                       P[prefix + ".running_var"], P[prefix + ".num_batches_tracked"], G, R, C, BN_EPS,
                                       BN_MOMENTUM, out=st)
             self._fin_keep.append((sums, st))
-            y = ops.bn_apply_from_stats(x.data, sums, P[prefix + ".weight"], P[prefix + ".bias"], G, R, C, relu, resd, eps=BN_EPS)
+            y = ops.bn_apply_from_stats(xd, sums, P[prefix + ".weight"], P[prefix + ".bias"], G, R, C, relu, resd, out=y_out, eps=BN_EPS)
         else:
-            st = ops.bn_finalize_train(sums, P[prefix + ".weight"], P[prefix + ".bias"], P[prefix + ".running_mean"],
-                                       P[prefix + ".running_var"], P[prefix + ".num_batches_tracked"], G, R, C, BN_EPS,
-                                       BN_MOMENTUM)
-            y = ops.bn_apply(x.data, st[0], st[1], G, R, C, relu, resd)
+            ops.bn_finalize_train(sums, P[prefix + ".weight"], P[prefix + ".bias"], P[prefix + ".running_mean"],
+                                  P[prefix + ".running_var"], P[prefix + ".num_batches_tracked"], G, R, C, BN_EPS,
+                                  BN_MOMENTUM, out=st)
+            y = ops.bn_apply(xd, st[0], st[1], G, R, C, relu, resd, out=y_out)
+        return y, st
+
+    def bn(self, x: Var, prefix: str, G: int, relu: bool, residual: Optional[Var] = None) -> Var:
+        """Train-mode BatchNorm2d over G row groups (+residual)(+ReLU)."""
+        N, H, W, C = x.data.shape
+        assert N % G == 0
+        R = (N // G) * H * W
+        P = self.params
+        resd = None if residual is None else residual.data
+        halves = self._halves(N, G)
+        if halves is None:
+            assert not isinstance(x.bn_partial, list), "a tensor of the two-chain section reached a whole-batch BatchNorm"
+            y, st = self._bn_forward(x.data, x.bn_partial, prefix, G, R, C, relu, resd, None, None)
+        else:
+            # two chains: each half normalises its own time steps; the running statistics still see the groups in order
+            # (the finalize launches of both halves go to ONE side stream, first half first)
+            y = torch.empty_like(x.data)
+            st = torch.empty((4, G, C), dtype=torch.float32, device=x.data.device)
+            plist = x.bn_partial if isinstance(x.bn_partial, list) else [None, None]
+            assert x.bn_partial is None or isinstance(x.bn_partial, list)
+            for h, (st_, n0, n1, g0, g1) in enumerate(halves):
+                with torch.cuda.stream(st_):
+                    self._bn_forward(x.data[n0:n1], plist[h], prefix, g1 - g0, R, C, relu, None if resd is None else resd[n0:n1],
+                                     y[n0:n1], st[:, g0:g1])
+        x.bn_partial = None
         out = Var(y, grad_dtype=self.dtype)
         if not self.record:
             return out
@@ -383,26 +479,42 @@ class Executor:
         recomputes the ReLU mask from x and routes the pool gradient by index); otherwise the two-launch route."""
         N, H, W, C = x.data.shape
         sums = x.bn_partial
-        fusable = (USE_FUSED_STEM and self.train and sums is not None and sums.shape[0] <= 8 and x.data.dtype == torch.bfloat16
+        split = isinstance(sums, list)
+        s0 = sums[0] if split else sums
+        fusable = (USE_FUSED_STEM and self.train and s0 is not None and s0.shape[0] <= 8 and x.data.dtype == torch.bfloat16
                    and C % 8 == 0 and N % G == 0 and N <= 65535 and k in (2, 3) and 2 * C * 4 <= 48 * 1024)
+        halves = self._halves(N, G) if split else None
+        assert not split or halves is not None
         if not fusable:
             return self.maxpool(self.bn(x, prefix, G, True), k, stride, pad)
         x.bn_partial = None
         R = (N // G) * H * W
         P = self.params
         st = torch.empty((4, G, C), dtype=torch.float32, device=x.data.device)
-        cur = torch.cuda.current_stream()
-        side = Executor._fin_streams.get(cur.device.index)
-        if side is None:
-            side = Executor._fin_streams[cur.device.index] = torch.cuda.Stream(device=cur.device, priority=MAIN_PRIO)
-        side.wait_stream(cur)
-        with torch.cuda.stream(side):        # running statistics + the coefficients the backward pass reads
-            ops.bn_finalize_train(sums, P[prefix + ".weight"], P[prefix + ".bias"], P[prefix + ".running_mean"],
-                                  P[prefix + ".running_var"], P[prefix + ".num_batches_tracked"], G, R, C, BN_EPS, BN_MOMENTUM,
-                                  out=st)
-        self._fin_keep.append((sums, st))
-        y, idx = ops.bn_relu_maxpool_from_stats(x.data, sums, P[prefix + ".weight"], P[prefix + ".bias"], G, k, stride, pad,
-                                                eps=BN_EPS)
+        Ho, Wo = (H + 2 * pad - k) // stride + 1, (W + 2 * pad - k) // stride + 1
+        y = torch.empty((N, Ho, Wo, C), dtype=x.data.dtype, device=x.data.device)
+        idx = torch.empty((N, Ho, Wo, C), dtype=torch.uint8, device=x.data.device)
+
+        def one(xd, sm, Gh, st_view, y_view, idx_view):
+            cur = torch.cuda.current_stream()
+            side = Executor._fin_streams.get(cur.device.index)
+            if side is None:
+                side = Executor._fin_streams[cur.device.index] = torch.cuda.Stream(device=cur.device, priority=MAIN_PRIO)
+            side.wait_stream(cur)
+            with torch.cuda.stream(side):        # running statistics + the coefficients the backward pass reads
+                ops.bn_finalize_train(sm, P[prefix + ".weight"], P[prefix + ".bias"], P[prefix + ".running_mean"],
+                                      P[prefix + ".running_var"], P[prefix + ".num_batches_tracked"], Gh, R, C, BN_EPS, BN_MOMENTUM,
+                                      out=st_view)
+            self._fin_keep.append((sm, st))
+            ops.bn_relu_maxpool_from_stats(xd, sm, P[prefix + ".weight"], P[prefix + ".bias"], Gh, k, stride, pad, eps=BN_EPS,
+                                           out=(y_view, idx_view))
+
+        if halves is None:
+            one(x.data, sums, G, st, y, idx)
+        else:
+            for h, (st_, n0, n1, g0, g1) in enumerate(halves):
+                with torch.cuda.stream(st_):
+                    one(x.data[n0:n1], sums[h], g1 - g0, st[:, g0:g1], y[n0:n1], idx[n0:n1])
         out = Var(y, grad_dtype=self.dtype)
         if not self.record:
             return out
@@ -582,19 +694,67 @@ class Executor:
             self.tape.append(lambda: self.fork_join(list(reversed(bwds))))
         return outs
 
+    # ---------------------------------------------------------------------------------------------
+    # Gradient segments.  Parameters sit in the flat gradient buffer in registration order, which is also the order of
+    # their first use in the forward pass; the backward pass walks the tape in reverse, so when it passes the point where
+    # parameter `name` was first used, every gradient at flat offset >= offset(name) is final.  A forward pass marks such
+    # points (mark_grad_segment); with a segment hook installed (data parallelism) the backward pass then
+    # folds the deferred weight gradients of the finished range into the flat buffer and hands the range to the hook ON A
+    # COMMUNICATION STREAM, ordered after the main chain and the weight-gradient side streams as of that moment -- the
+    # all-reduce of the decoder / LSTM / layer-4 gradients runs under the backward pass of layers 3..1 instead of after it.
+    _comm_streams = {}
+
+    def mark_grad_segment(self, first_param):
+        if not self.record or self.segment_hook is None or first_param not in self.grad_offsets:
+            return
+        start = self.grad_offsets[first_param]
+        self.tape.append(lambda: self._segment_ready(start))
+
+    def _scatter_range(self, lo, hi, flat_grad, owner):
+        """Fold the deferred tcgen05 weight gradients whose flat offset lies in [lo, hi) into the flat gradient."""
+        entries = sorted(e for e in self._deferred.values() if lo <= e[0] < hi)
+        if not entries or flat_grad is None:
+            return
+        plans = owner.__dict__.setdefault("_scatter_plans", {}) if owner is not None else {}
+        plan = plans.get(tuple(entries))
+        if plan is None:
+            plan = plans[tuple(entries)] = ops.ScatterPlan(entries, flat_grad.device)
+        plan.run(self.acc_flat, flat_grad)
+        for k in [k for k, e in self._deferred.items() if lo <= e[0] < hi]:
+            del self._deferred[k]
+
+    def _segment_ready(self, start):
+        end = self._seg_end if self._seg_end is not None else self.flat.numel()
+        if self.segment_hook is None or start >= end:
+            return
+        cur = torch.cuda.current_stream()
+        comm = Executor._comm_streams.get(cur.device.index)
+        if comm is None:
+            comm = Executor._comm_streams[cur.device.index] = torch.cuda.Stream(device=cur.device, priority=MAIN_PRIO)
+        comm.wait_stream(cur)
+        for side in Executor._wg_streams.get(cur.device.index) or []:
+            comm.wait_stream(side)
+        with torch.cuda.stream(comm):
+            self._scatter_range(start, end, self.flat, self._owner_for_plans)
+            self.segment_hook(self.flat[start:end])
+        self._seg_end = start
+        self._comm_used = True
+
     def backward(self, out: Var, dout, flat_grad=None, owner=None):
         out.grad = dout
+        self._owner_for_plans = owner
+        self._seg_end = None
+        self._comm_used = False
         for fn in reversed(self.tape):
             fn()
         self.join_wgrad()
-        if self._deferred and flat_grad is not None:
-            entries = sorted(self._deferred.values())
-            plan = getattr(owner, "_scatter_plan", None) if owner is not None else None
-            if plan is None or plan.key != tuple(entries):
-                plan = ops.ScatterPlan(entries, flat_grad.device)
-                if owner is not None:
-                    owner._scatter_plan = plan
-            plan.run(self.acc_flat, flat_grad)
+        end = self._seg_end if self._seg_end is not None else (flat_grad.numel() if flat_grad is not None else 0)
+        self._scatter_range(0, end, flat_grad, owner)
+        if self.segment_hook is not None and flat_grad is not None and end > 0:
+            self.segment_hook(flat_grad[:end])           # what no segment mark covered (the stem and the first layers)
+        if self._comm_used:
+            cur = torch.cuda.current_stream()
+            cur.wait_stream(Executor._comm_streams[cur.device.index])
         self.tape = []
         self._packed = {}
 
@@ -660,8 +820,12 @@ class ModelFunction(torch.autograd.Function):
             if cur is None or not _views_of(cur, [params[n].grad for n in names], ex.grad_offsets, names):
                 module._last_flat_grad = None
         hook = getattr(module, "_grad_ready_hook", None)
-        if hook is not None:
+        if hook is not None and ex.segment_hook is None:
             hook(module._last_flat_grad)
+        elif ex.segment_hook is not None and module._last_flat_grad is not flat:
+            # gradient accumulation into an older buffer: the segments reduced THIS step's buffer before it was added in;
+            # averaging is linear, so the accumulated buffer is consistent across ranks without another exchange
+            pass
         module._learn_pack_plan(ex)
         ctx.ex = ctx.out_var = None
         return (None, None) + (None,) * len(ctx.names)

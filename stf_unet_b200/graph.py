@@ -18,11 +18,17 @@ class GraphedStep:
     """loss = step(x, target): copies the batch into static buffers, replays fwd + loss + bwd; gradients land in the
     parameters' persistent ``.grad`` views (one flat buffer), ready for all-reduce / optimizer.step()."""
 
-    def __init__(self, model, criterion, example_x, example_target, autocast_dtype=torch.bfloat16, warmup=3):
+    def __init__(self, model, criterion, example_x, example_target, autocast_dtype=torch.bfloat16, warmup=3,
+                 capture_collectives=True):
         self.model = model
         self.x = example_x.clone()
         self.t = example_target.clone()
-        self._hook = model.__dict__.pop("_grad_ready_hook", None)   # collectives stay outside the graph
+        # Data parallelism: with a per-segment hook (parallel.DataParallel(overlap=True)) the NCCL all-reduces are part of the
+        # backward pass and are captured INSIDE the graph, on their own branch, overlapping the rest of the backward pass;
+        # without one the exchange runs after every replay (self._hook).
+        self._in_graph_comm = capture_collectives and model.__dict__.get("_grad_segment_hook") is not None
+        self._seg_hook = None if self._in_graph_comm else model.__dict__.pop("_grad_segment_hook", None)
+        self._hook = model.__dict__.pop("_grad_ready_hook", None)   # the after-replay exchange (unused with in-graph collectives)
 
         def fwd_bwd():
             with torch.autocast("cuda", dtype=autocast_dtype, enabled=autocast_dtype is not None):
@@ -56,7 +62,8 @@ class GraphedStep:
             cap_stream = _CAPTURE_STREAMS.get(dev_index)
             if cap_stream is None:
                 cap_stream = _CAPTURE_STREAMS[dev_index] = torch.cuda.Stream(device=self.x.device, priority=engine.MAIN_PRIO)
-        with torch.cuda.graph(self.graph, stream=cap_stream):
+        # thread_local: NCCL's watchdog thread polls events while the collectives of this step are being captured
+        with torch.cuda.graph(self.graph, stream=cap_stream, capture_error_mode="thread_local" if self._in_graph_comm else "global"):
             self.loss = fwd_bwd()
         self.launches_per_replay = _lib.launch_count() - n0      # libstfb200 kernels inside the captured graph
         self.flat_grad = model._last_flat_grad
@@ -65,6 +72,8 @@ class GraphedStep:
         self._grad_views = [(p, p.grad) for p in model.parameters() if p.requires_grad and p.grad is not None]
         if self._hook is not None:
             model._grad_ready_hook = self._hook
+        if self._seg_hook is not None:
+            model._grad_segment_hook = self._seg_hook
 
     def __call__(self, x, target):
         self.x.copy_(x, non_blocking=True)
@@ -74,6 +83,6 @@ class GraphedStep:
         for p, g in self._grad_views:                    # the graph OVERWRITES its flat buffer: replay == zero_grad + backward
             if p.grad is not g:
                 p.grad = g
-        if self._hook is not None:
+        if self._hook is not None and not self._in_graph_comm:
             self._hook(self.flat_grad)
         return self.loss

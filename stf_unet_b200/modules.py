@@ -106,6 +106,9 @@ class B200Module(nn.Module):
         ex = engine.Executor(self._state(), self._select_dtype(), self.training, record, grads)
         ex.flat = flat
         ex.grad_offsets = offsets
+        if record:
+            # data parallelism with overlapped exchange: a per-range hook (parallel.DataParallel installs it)
+            ex.segment_hook = self.__dict__.get("_grad_segment_hook")
         if record and flat is not None and ex.dtype == torch.bfloat16:
             # side buffer (same offsets as the flat gradient) the tcgen05 weight-gradient kernels accumulate into
             ex.acc_flat = torch.zeros_like(flat)

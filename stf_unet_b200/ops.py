@@ -328,11 +328,12 @@ class PackPlan:
         return dict(self.buffers)
 
 
-def im2col_small(x, k, stride, pad, kpad):
+def im2col_small(x, k, stride, pad, kpad, out=None):
     """bf16 [N,H,W,Cin] -> [N,Ho,Wo,kpad]: K order (ky,kx,ci), zero padded (small-channel convs on the tensor cores)."""
     N, H, W, Cin = x.shape
     Ho, Wo = conv_out_hw(H, W, k, stride, pad)
-    out = torch.empty((N, Ho, Wo, kpad), dtype=torch.bfloat16, device=x.device)
+    if out is None:
+        out = torch.empty((N, Ho, Wo, kpad), dtype=torch.bfloat16, device=x.device)
     with _timed("im2col_small", _nb(x, out)):
         check(_lib.load().stfb_im2col_small(_p(x), _p(out), N, H, W, Cin, Ho, Wo, k, stride, pad, kpad, _stream()),
               "im2col_small")
@@ -401,13 +402,16 @@ def bn_apply_from_stats(x, partial, gamma, beta, G, R, C, relu, residual=None, o
     return y
 
 
-def bn_relu_maxpool_from_stats(x, partial, gamma, beta, G, k, stride, pad, eps=1e-5):
+def bn_relu_maxpool_from_stats(x, partial, gamma, beta, G, k, stride, pad, eps=1e-5, out=None):
     """maxpool(relu(batchnorm(x))) + argmax index in one pass; scale/shift derived in-kernel from <= 8 statistics slots.
     -> (y [N,Ho,Wo,C], idx uint8): exactly what bn_apply_from_stats + maxpool_fwd_idx give, without the full-size map."""
     N, H, W, C_ = x.shape
     Ho, Wo = (H + 2 * pad - k) // stride + 1, (W + 2 * pad - k) // stride + 1
-    y = torch.empty((N, Ho, Wo, C_), dtype=x.dtype, device=x.device)
-    idx = torch.empty((N, Ho, Wo, C_), dtype=torch.uint8, device=x.device)
+    if out is not None:
+        y, idx = out
+    else:
+        y = torch.empty((N, Ho, Wo, C_), dtype=x.dtype, device=x.device)
+        idx = torch.empty((N, Ho, Wo, C_), dtype=torch.uint8, device=x.device)
     with _timed("bn_relu_maxpool", _nb(x, y) + idx.numel(), f"C{C_}"):
         check(_lib.load().stfb_bn_relu_maxpool_from_stats(_p(x), _p(partial), partial.shape[0], _p(gamma), _p(beta), _p(y), _p(idx),
                                                           G, N, H, W, C_, Ho, Wo, k, stride, pad, eps, dt_code(x.dtype), _stream()),

@@ -116,6 +116,7 @@ class STFLSTMUNet(B200Module):
         else:
             T = total
             xin = engine.Var(ops.pack_series(x, ex.dtype), needs_grad=False)  # [T*B, H, W, C] time-major
+        ex.begin_split(T)      # two half-batch chains through the encoder (training forward, bf16): engine.USE_FWD_SPLIT
         if ex.train:     # stem: conv (statistics in the epilogue) -> BatchNorm + ReLU + max-pool in one pass
             raw = ex.conv(xin, "conv1.weight", k=7, stride=2, pad=3, stats_G=T)
             e = ex.bn_relu_pool(raw, "bn1", T, 3, 2, 1)
@@ -124,6 +125,8 @@ class STFLSTMUNet(B200Module):
             e = ex.maxpool(s, 3, 2, 1)
         feats = []
         for li, (c, n) in enumerate(RESNET34_LAYERS, start=1):
+            if li >= 3:        # layers 3 and 4 hold 73 % of the parameters: their gradients are exchanged while layers 2, 1 run
+                ex.mark_grad_segment(f"layer{li}.0.conv1.weight")
             for b in range(n):
                 p = f"layer{li}.{b}"
                 down = b == 0 and li > 1
@@ -134,6 +137,9 @@ class STFLSTMUNet(B200Module):
                                      relu=False, G=T)
                 e = ex.conv_bn(o, p + ".conv2.weight", p + ".bn2", k=3, pad=1, relu=True, residual=idt, G=T)
             feats.append(e)
+        ex.end_split()
+        # everything registered after the encoder (PK fusion, LSTMs, decoder, head) is final once its backward is done
+        ex.mark_grad_segment("pk_fusion1.weight" if pk is not None else "lstm1.weight_ih_l0")
         if pk is not None:
             feats = [self._pk_fuse(ex, f, pk, k + 1, T) for k, f in enumerate(feats)]
         enc = ex.lstm_levels(feats, [f"lstm{k + 1}" for k in range(len(feats))], T)

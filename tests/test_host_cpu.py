@@ -151,3 +151,27 @@ def test_header_is_plain_c_and_a_c_program_links_against_the_library(tmp_path):
     r = subprocess.run([str(exe)], capture_output=True, text=True)
     assert r.returncode == 0, (r.returncode, r.stdout, r.stderr)
     assert "maxpool_fwd" in r.stdout
+
+
+def test_augment_host_tables_and_draw_order_match_oracle():
+    """The host half of the device-side augmentation (stf_unet_b200/augment.py): Pillow's resize coefficient tables, the nearest
+    tables, the rotation matrices and the order of the random draws equal the oracle's (which is pinned to the reference's own
+    transforms by tests/golden/make_golden_augment.py).  No GPU involved."""
+    import random
+    import numpy as np
+    from oracle import augment_oracle as AO
+    from stf_unet_b200 import augment as A
+    for insz, out in [(256, 128), (256, 307), (256, 224), (256, 255), (200, 173), (312, 270), (150, 224)]:
+        b, k = A._bilinear_tables(insz, out)
+        bo, ko = AO.resize_coeffs(insz, out)
+        assert np.array_equal(b, bo) and np.array_equal(k, ko), (insz, out)
+        assert np.array_equal(A._nearest_table(out, insz), AO.nearest_table(out, insz))
+    assert A._bilinear_tables(256, 256) == (None, None)
+    for seed in range(20):
+        aug = A.PairedAugment(train=True, rng=random.Random(seed))
+        p = aug.draw((256, 256))
+        assert p == {k: v for k, v in AO.draw_params(random.Random(seed)).items() if k != "crop"}
+        if p["rot"]:
+            assert A._rotate_matrix(p["angle"], p["rw"], p["rh"]) == AO.rotate_matrix(p["angle"], p["rw"], p["rh"])
+    _, samples, tables = A.PairedAugment(train=True, rng=random.Random(5)).plan(3, 256, 256)
+    assert len(bytes(samples)) == 3 * 120 and tables.dtype == np.int32 and samples[1].tab_off > 0

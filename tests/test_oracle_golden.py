@@ -150,3 +150,19 @@ def test_tofts_oracle_matches_reference_class(golden_dir):
     maps = g["maps_100"].reshape(3, -1)[:, mask.numpy()]
     assert np.array_equal(np.stack([kk.numpy(), ee.numpy(), vv.numpy()]), maps)
     assert np.allclose(losses.numpy(), g["losses_100"], rtol=0, atol=0)
+
+
+def test_augment_oracle_matches_reference_pipeline(golden_dir):
+    """oracle.augment_oracle (numpy restatement of Pillow / torchvision arithmetic + the reference's draw order) against the
+    fixture generated from /root/reference/transforms.py composed as train.py:58-67: every sample bit for bit."""
+    import random
+    from oracle import augment_oracle as AO
+    g = load(golden_dir, "augment_6x3x256")
+    u8, masks = AO.fixture_inputs()
+    assert AO.digest(u8) == str(g["series_digest"]) and AO.digest(masks) == str(g["masks_digest"])
+    for b, seed in enumerate(g["seeds"]):
+        p = AO.draw_params(random.Random(int(seed)))
+        x, t = AO.apply(u8[b], masks[b], p)
+        assert AO.digest(x) == str(g[f"xdigest{b}"]) and AO.digest(t) == str(g[f"tdigest{b}"]), b
+        if b == 1:
+            assert np.array_equal(x, g["x1"]) and np.array_equal(t, g["t1"].astype(np.int64))
