@@ -79,8 +79,12 @@ __global__ void __launch_bounds__(128) augment_series_u8_kernel(const unsigned c
   double dx = 0.0, dy = 0.0;
   bool live = in_img, y1ok = false, blend = false;
   if (in_img && sm.rot) {
-    const double xi = sm.m[0] * (xc + 0.5) + sm.m[1] * (yc + 0.5) + sm.m[2];
-    const double yi = sm.m[3] * (xc + 0.5) + sm.m[4] * (yc + 0.5) + sm.m[5];
+    // Pillow is plain C without fused multiply-adds: a0 * xin + a1 * yin + a2 rounds after every operation.  Spelled with the
+    // _rn intrinsics so that nvcc does not contract the expression into FMAs (one ulp in the coordinate moves a pixel whose
+    // blend lands exactly on an integer across the truncation below).
+    const double xin = (double)xc + 0.5, yin = (double)yc + 0.5;
+    const double xi = __dadd_rn(__dadd_rn(__dmul_rn(sm.m[0], xin), __dmul_rn(sm.m[1], yin)), sm.m[2]);
+    const double yi = __dadd_rn(__dadd_rn(__dmul_rn(sm.m[3], xin), __dmul_rn(sm.m[4], yin)), sm.m[5]);
     live = xi >= 0.0 && xi < (double)sm.rw && yi >= 0.0 && yi < (double)sm.rh;
     if (live) {
       const double xf = xi - 0.5, yf = yi - 0.5;
@@ -107,13 +111,14 @@ __global__ void __launch_bounds__(128) augment_series_u8_kernel(const unsigned c
       if (!blend) {
         v = aug_resized(g, ry[0], rx[0]);
       } else {
+        // BILINEAR(v, a, b, d): v = a + (b - a) * d, again without contraction
         const double a00 = aug_resized(g, ry[0], rx[0]), a01 = aug_resized(g, ry[0], rx[1]);
-        double v1 = a00 + (a01 - a00) * dx, v2 = v1;
+        double v1 = __dadd_rn(a00, __dmul_rn(a01 - a00, dx)), v2 = v1;
         if (y1ok) {
           const double a10 = aug_resized(g, ry[1], rx[0]), a11 = aug_resized(g, ry[1], rx[1]);
-          v2 = a10 + (a11 - a10) * dx;
+          v2 = __dadd_rn(a10, __dmul_rn(a11 - a10, dx));
         }
-        v = (int)(v1 + (v2 - v1) * dy);                      // (UINT8) cast: truncation
+        v = (int)__dadd_rn(v1, __dmul_rn(v2 - v1, dy));      // (UINT8) cast: truncation
       }
     }
     // ToTensor: x / 255; Normalize: (x - mean) / std -- IEEE divisions in the loader's order, like stfb_pack_series_u8

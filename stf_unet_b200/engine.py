@@ -30,8 +30,11 @@ USE_FUSED_STEM = _os.environ.get("STFB_NO_FUSED_STEM", "0") != "1"
 # streams.  Each chain alternates tensor-bound convolutions with HBM-bound BatchNorm passes; the two chains drift out of
 # phase and the block scheduler co-runs one chain's BatchNorm pass with the other's convolution (nothing else is
 # independent of the main chain in the forward pass).  Tensors stay whole (a half is a leading-dimension view), so the backward
-# tape is unchanged.  STFB_NO_FWD_SPLIT=1 disables.
-USE_FWD_SPLIT = _os.environ.get("STFB_NO_FWD_SPLIT", "0") != "1"
+# tape is unchanged.  MEASURED (round 2, graph step at the headline size): 9.87 ms with the split against 9.82 ms without --
+# the half-batch launches cost more (109 extra launches, half the tiles per launch) than the overlap returns, because a
+# persistent convolution CTA holds 160-200 KB of shared memory and 54 k registers of its SM and leaves the other chain's
+# BatchNorm CTAs almost no room to co-reside.  OFF by default; STFB_FWD_SPLIT=1 enables it (kept tested).
+USE_FWD_SPLIT = _os.environ.get("STFB_FWD_SPLIT", "0") == "1"
 # Stream priorities: the main chain (graph capture stream, LSTM forks, BatchNorm finalize) is HIGH priority and the
 # weight-gradient side streams stay at the default (lowest) one, so the block scheduler hands freed SM slots to the critical
 # path first and the tensor-bound wgrad CTAs fill what is left.  Measured on the graph step: 10.29 -> 10.08 ms with one wgrad
@@ -107,6 +110,9 @@ class Executor:
         pool = Executor._split_streams.get(cur.device.index)
         if pool is None:
             pool = Executor._split_streams[cur.device.index] = [torch.cuda.Stream(device=cur.device, priority=MAIN_PRIO) for _ in range(2)]
+        if getattr(self, "_stat_arena", None) is None:        # the zero fill of the statistics arena precedes the fork
+            self._stat_arena = torch.zeros(self.STAT_ARENA_FLOATS, dtype=torch.float32, device=cur.device)
+            self._stat_off = 0
         for st_ in pool:
             st_.wait_stream(cur)
         self._split = pool
@@ -134,6 +140,7 @@ class Executor:
                                  gate_c=gate_c)
             self._packed[key] = wp
             self._new_pack_keys.append(key)
+            self._split_wait_current()     # a pack launched after the fork (first forward of a mode, before the plan exists)
         return wp
 
     def packed_lstm_xh(self, wih, whh, C):
@@ -175,30 +182,39 @@ class Executor:
 
     STAT_ARENA_FLOATS = 1 << 21        # 8 MB of zeroed fp32 per forward: one fill instead of one per BatchNorm layer
 
-    def stat_buffer(self, G, C, device):
-        """Zeroed [STAT_SLOTS, 2, G, C] fp32 for the fused BatchNorm statistics, carved from one arena per forward."""
-        n = ops.STAT_SLOTS * 2 * G * C
-        arena = getattr(self, "_stat_arena", None)
-        if arena is None or self._stat_off + n > arena.numel():
-            if n > self.STAT_ARENA_FLOATS:
-                return torch.zeros((ops.STAT_SLOTS, 2, G, C), dtype=torch.float32, device=device)
-            arena = self._stat_arena = torch.zeros(self.STAT_ARENA_FLOATS, dtype=torch.float32, device=device)
-            self._stat_off = 0
-        buf = arena[self._stat_off:self._stat_off + n].view(ops.STAT_SLOTS, 2, G, C)
-        self._stat_off += (n + 63) // 64 * 64
-        return buf
+    def _split_wait_current(self):
+        """Inside the two-chain section: work just enqueued on the CURRENT stream (a zero fill, a weight pack) that the chain
+        streams -- forked earlier -- are about to consume is ordered before them."""
+        if getattr(self, "_split", None):
+            cur = torch.cuda.current_stream()
+            for st_ in self._split:
+                if st_ != cur:
+                    st_.wait_stream(cur)
 
-    def zeroed_scratch(self, n, device):
-        """n zeroed fp32 from the per-forward arena (the one-launch BatchNorm backward's group sums + counters)."""
+    def _fresh_zeros(self, n, device):
+        """n zeroed fp32 filled on the current stream (the chain streams accumulate into these buffers with red.add)."""
+        z = torch.zeros(n, dtype=torch.float32, device=device)
+        self._split_wait_current()
+        return z
+
+    def _arena_take(self, n, device):
         arena = getattr(self, "_stat_arena", None)
         if arena is None or self._stat_off + n > arena.numel():
             if n > self.STAT_ARENA_FLOATS:
-                return torch.zeros(n, dtype=torch.float32, device=device)
-            arena = self._stat_arena = torch.zeros(self.STAT_ARENA_FLOATS, dtype=torch.float32, device=device)
+                return self._fresh_zeros(n, device)
+            arena = self._stat_arena = self._fresh_zeros(self.STAT_ARENA_FLOATS, device)
             self._stat_off = 0
         buf = arena[self._stat_off:self._stat_off + n]
         self._stat_off += (n + 63) // 64 * 64
         return buf
+
+    def stat_buffer(self, G, C, device):
+        """Zeroed [STAT_SLOTS, 2, G, C] fp32 for the fused BatchNorm statistics, carved from one arena per forward."""
+        return self._arena_take(ops.STAT_SLOTS * 2 * G * C, device).view(ops.STAT_SLOTS, 2, G, C)
+
+    def zeroed_scratch(self, n, device):
+        """n zeroed fp32 from the per-forward arena (the one-launch BatchNorm backward's group sums + counters)."""
+        return self._arena_take(n, device)
 
     def wants_grad(self, name):
         return name in self.grads

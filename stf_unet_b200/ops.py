@@ -452,7 +452,9 @@ def bn_bwd(dy, y, x, mean, invstd, gamma, dgamma, dbeta, G, R, C, relu, want_dre
     # (tools/kernel_probe.py bn2: 278 vs 307 us on the stem's 268 MB map, 81 vs 85 us on layer 1's 67 MB)
     lean_and_large = ym is None and dres is None and x.numel() * x.element_size() > (48 << 20)
     if scratch is not None and USE_FUSED_BN_BWD and not lean_and_large:
-        with _timed("bn_bwd_fused", 2 * _nb(dy, x, ym) + _nb(dx, dres, dres_acc), f"C{C}"):
+        # algorithmic bytes: every input once (dy, x, the ReLU mask source, the residual gradient being
+        # accumulated into) + every output once (dx, dres); the kernel's second pass over dy / x is NOT counted
+        with _timed("bn_bwd_fused", _nb(dy, x, ym, dres_acc) + _nb(dx, dres), f"C{C}"):
             check(lib.stfb_bn_bwd_fused(_p(dy), _p(ym), _p(x), _p(mean), _p(invstd), _p(gamma), _p(shift) if from_x else None,
                                         _p(scratch), _p(dgamma), _p(dbeta), _p(dx), _p(dres), int(dres_acc is not None), G, R, C,
                                         int(bool(relu)), dt_code(x.dtype), s), "bn_bwd_fused")
@@ -466,7 +468,7 @@ def bn_bwd(dy, y, x, mean, invstd, gamma, dgamma, dbeta, G, R, C, relu, want_dre
     coef = torch.empty((G, C, 3), dtype=torch.float32, device=x.device)
     check(lib.stfb_bn_bwd_finalize(_p(red), nblk, _p(gamma), _p(invstd), _p(dgamma), _p(dbeta), _p(coef), G, R, C, s),
           "bn_bwd_finalize")
-    with _timed("bn_bwd_apply", _nb(dy, x, ym, dx, dres, dres_acc), f"C{C}"):
+    with _timed("bn_bwd_apply", _nb(dy, x, ym, dres_acc) + _nb(dx, dres), f"C{C}"):
         check(lib.stfb_bn_bwd_apply(_p(dy), _p(ym), _p(x), _p(mean), _p(invstd), _p(coef), _p(shift) if from_x else None, _p(dx),
                                     _p(dres), int(dres_acc is not None), G, R, C, int(bool(relu)), dt_code(x.dtype), s),
               "bn_bwd_apply")

@@ -57,6 +57,7 @@ def main():
             g = m._last_flat_grad.detach().clone()
             expect = g if expect is None else expect + g
         expect /= world
+        print(f"DP_PROGRESS rank={rank} {tag}: expectation done", flush=True)
         x, t = shards[rank]
         results = {}
         for mode in ("after", "overlap"):
@@ -66,6 +67,7 @@ def main():
             step(net, x, t)
             torch.cuda.synchronize()
             results[mode] = rel(m._last_flat_grad, expect)
+            print(f"DP_PROGRESS rank={rank} {tag}: {mode} {results[mode]:.3e}", flush=True)
         m = fresh()
         net = parallel.DataParallel(m, overlap=True)
         g = GraphedStep(m, S.criterion, x, t, autocast_dtype=dt)
@@ -73,8 +75,7 @@ def main():
         for _ in range(2):
             g(x, t)
         torch.cuda.synchronize()
-        m2 = fresh()                               # the graph's replays moved the running stats, not the weights: same gradient
-        results["graph"] = rel(g.flat_grad, expect)
+        results["graph"] = rel(g.flat_grad, expect)   # replays move the running stats, not the weights: same gradient every time
         # every rank must hold the SAME averaged gradient
         mine = g.flat_grad.detach().clone()
         other = mine.clone()
@@ -84,12 +85,20 @@ def main():
         good = all(v < tol for k, v in results.items() if k != "rank_spread") and results["rank_spread"] == 0.0
         print(f"DP_CHECK rank={rank} world={world} {tag}: {line} tol={tol:.0e} {'OK' if good else 'FAIL'}", flush=True)
         ok = ok and good
+        # a communicator can only be torn down after every CUDA graph that captured its collectives is gone
+        del g, net, m
+        import gc
+        gc.collect()
+        torch.cuda.synchronize()
     flag = torch.tensor([1 if ok else 0], device=dev)
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
-    dist.destroy_process_group()
+    good = int(flag) == 1
     if rank == 0:
-        print("DP_OK" if int(flag) == 1 else "DP_FAIL", flush=True)
-    sys.exit(0 if int(flag) == 1 else 1)
+        print("DP_OK" if good else "DP_FAIL", flush=True)
+    dist.barrier()
+    torch.cuda.synchronize()
+    dist.destroy_process_group()
+    sys.exit(0 if good else 1)
 
 
 if __name__ == "__main__":

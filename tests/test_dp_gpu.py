@@ -22,7 +22,7 @@ def test_dp_gradients_equal_mean_of_shard_gradients():
     env = dict(os.environ, MASTER_ADDR="127.0.0.1")
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr", "127.0.0.1",
            "--master-port", "29533", os.path.join(ROOT, "tests", "dp_worker.py")]
-    r = subprocess.run(cmd, env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=900)
+    r = subprocess.run(cmd, env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=420)
     print(r.stdout[-4000:])
     assert r.returncode == 0 and "DP_OK" in r.stdout, r.stdout[-4000:]
     assert r.stdout.count("DP_CHECK") == 2 * world
