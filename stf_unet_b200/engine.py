@@ -721,7 +721,9 @@ class Executor:
     _comm_streams = {}
 
     def mark_grad_segment(self, first_param):
-        if not self.record or self.segment_hook is None or first_param not in self.grad_offsets:
+        # also without a hook (one GPU): the fold of the segment's deferred weight gradients into the flat buffer then runs
+        # beside the backward pass instead of as one 175 us launch after it (the step's tail is the stem's serial chain)
+        if not self.record or first_param not in self.grad_offsets or (self.segment_hook is None and self.acc_flat is None):
             return
         start = self.grad_offsets[first_param]
         self.tape.append(lambda: self._segment_ready(start))
@@ -741,7 +743,7 @@ class Executor:
 
     def _segment_ready(self, start):
         end = self._seg_end if self._seg_end is not None else self.flat.numel()
-        if self.segment_hook is None or start >= end:
+        if start >= end:
             return
         cur = torch.cuda.current_stream()
         comm = Executor._comm_streams.get(cur.device.index)
@@ -752,7 +754,8 @@ class Executor:
             comm.wait_stream(side)
         with torch.cuda.stream(comm):
             self._scatter_range(start, end, self.flat, self._owner_for_plans)
-            self.segment_hook(self.flat[start:end])
+            if self.segment_hook is not None:
+                self.segment_hook(self.flat[start:end])
         self._seg_end = start
         self._comm_used = True
 

@@ -1,0 +1,4 @@
+#!/bin/bash
+set -x
+timeout 600 python -m pytest tests/test_models_gpu.py -x -q -m gpu 2>&1 | tail -4
+timeout 200 python tools/step_time.py --iters 20
