@@ -488,7 +488,9 @@ def run_own(args, rank, world, local_rank):
             tpath = os.path.join(ROOT, "profiles", "roofline_traffic.json")
             if os.path.exists(tpath):
                 traffic = json.load(open(tpath)).get(t_tag, {}).get("dram_bytes_per_launch")
-            names = {"conv_tcgen05": "conv_halo2_kernel / conv_halo_kernel / conv_tc_kernel (tcgen05 implicit-GEMM convolutions: forward, dgrad, fused LSTM steps)",
+            names = {"conv3x3_halo_tcgen05": "conv_halo2_kernel (CTA pairs, tcgen05 cta_group::2) / conv_halo_kernel: 3x3 stride-1 implicit-GEMM convolutions, forward + dgrad",
+                     "conv_other_tcgen05": "conv_tc_kernel: stride-2 / 1x1 / transposed / 8x8-map / 32-channel convolutions and the LSTM backward GEMMs",
+                     "lstm_step_tcgen05": "conv_tc_kernel<EPI=1>: fused LSTM time step (gate GEMM + cell update)",
                      "wgrad_tcgen05": "wgrad_halo_kernel / wgrad_tc_kernel (tcgen05 weight gradients)"}
             whole_tf = value / world * TRAIN_GFLOP_PER_SLICE / 1e3
             roof = {"bound": "tensor", "kernel": f"{t_family}: {names.get(t_family, t_family)}", "achieved": round(f_tf, 2),

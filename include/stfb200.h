@@ -259,6 +259,15 @@ int stfb_bilinear_bwd(const void* dy, float* dx, int N, int H, int W, int C, int
  * [0, C) and the same for W_hh into columns [C, 2C); h_out must not alias x_t or h_prev; all pointers 16-byte aligned. */
 int stfb_lstm_step_fused(const void* x_t, const void* h_prev, const void* w_xh_il, const float* b_ih, const float* b_hh,
                          const float* c_prev, float* c_out, void* h_out, void* acts, int N, int H, int W, int C, void* stream);
+/* ALL T steps of one LSTM level in ONE launch (hidden size 64; stfb_lstm_seq_supported says whether a geometry fits): the CTA
+ * that owns a 128-pixel tile keeps [W_ih | W_hh] (64 KB), c (fp32) and h_{t-1} (bf16, the next step's MMA operand) in shared
+ * memory for t = 0..T-1; x_seq = [T*B, H, W, C] bf16 time-major.  keep != 0 (training): c_all fp32 [T][rows][C], h_all bf16
+ * [T][rows][C], acts_all bf16 [T][rows][4C] (accumulator column order, as above) are written for every step; keep == 0
+ * (inference): only h_all = h_T [rows][C].  Bit-identical to T calls of stfb_lstm_step_fused.
+ * Replaces: the time loop inside nn.LSTM (src/stf_lstm_unet.py:124-127, :216-221) for the first encoder level. */
+int stfb_lstm_seq_supported(int T, int B, int H, int W, int C);
+int stfb_lstm_seq_fused(const void* x_seq, const void* w_xh_il, const float* b_ih, const float* b_hh, float* c_all, void* h_all,
+                        void* acts_all, int T, int B, int H, int W, int C, int keep, void* stream);
 /* c_prev may be NULL (t = 0, zero state).  acts (dtype, [R][4C]) may be NULL in eval mode.
  * c_out fp32 [R][C]; h_out dtype [R][C]. */
 int stfb_lstm_cell_fwd(const float* gates, const float* c_prev, void* acts, float* c_out, void* h_out, long long R,

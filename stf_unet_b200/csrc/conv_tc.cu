@@ -1030,6 +1030,248 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(HALO2_THREADS, 1)
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// The whole time loop of a per-pixel LSTM level in ONE kernel (hidden size 64: [W_ih | W_hh] = 64 KB of bf16 stays in shared
+// memory).  Reference: nn.LSTM(C, C) over [B*h*w, T, C] (/root/reference/src/stf_lstm_unet.py:124-127, :216-221).
+// A CTA owns a 128-pixel tile for t = 0 .. T-1:
+//   * x_t tiles stream through a TMA ring; h_{t-1} never leaves the SM: the epilogue writes h_t (bf16) straight into a
+//     shared-memory tile in the K-major SWIZZLE_128B layout (fence.proxy.async, mbarrier) and the next step's MMAs read it as
+//     their A operand; c stays in the epilogue warps' staging segments (fp32) from step to step.
+//   * two TMEM accumulators alternate by time step: the x_{t+1} W_ih^T half of step t+1 is issued while the epilogue of step t
+//     still runs; only the four h_t W_hh^T MMAs wait for it.
+//   * training writes c_t, h_t and the gate activations of every step (the backward pass needs them); inference writes h_T only.
+// Same arithmetic, same accumulation order as conv_tc_kernel<EPI = 1> launched once per step: results are bit-identical.
+struct LstmSeqArgs {
+  const float* bias;        // b_ih [4C]
+  const float* bias2;       // b_hh [4C]
+  float* c_all;             // [T][rows][64] fp32 (training) or NULL
+  void* h_all;              // training: [T][rows][64] bf16; inference: [rows][64] = h_T
+  void* acts_all;           // [T][rows][256] bf16 in accumulator column order (training) or NULL
+  long long rows;           // B * H * W
+  int T, B, H, W;
+  int TW, TH, TN, tiles_w, tiles_h, tiles_n, num_tiles;
+  int keep;                 // 1: training (every step is stored)
+};
+constexpr int LSEQ_XS = 3;
+constexpr int LSEQ_W_BYTES = 2 * 256 * 128;              // W_ih block + W_hh block, 256 gate rows x 64 k each
+constexpr int LSEQ_X_BYTES = TC_BM * 128;
+constexpr int LSEQ_WARP_STG = 2 * TC_SEG_BYTES + TC_SEG_BYTES + 1024;   // c (two segments), activations, biases
+constexpr int lseq_smem_bytes() { return LSEQ_W_BYTES + LSEQ_XS * LSEQ_X_BYTES + LSEQ_X_BYTES + 4 * LSEQ_WARP_STG + 256 + 1024; }
+
+__global__ void __launch_bounds__(TC_THREADS, 1) lstm_seq64_kernel(const __grid_constant__ CUtensorMap tmX,
+                                                                   const __grid_constant__ CUtensorMap tmW, const LstmSeqArgs a) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const uint32_t sW = smem_u32(smem);
+  const uint32_t sX = sW + LSEQ_W_BYTES;
+  const uint32_t sH = sX + LSEQ_XS * LSEQ_X_BYTES;
+  const uint32_t sStg = sH + LSEQ_X_BYTES;
+  uint64_t* wfull = reinterpret_cast<uint64_t*>(smem + LSEQ_W_BYTES + (LSEQ_XS + 1) * LSEQ_X_BYTES + 4 * LSEQ_WARP_STG);
+  uint64_t* xfull = wfull + 1;
+  uint64_t* xempty = xfull + LSEQ_XS;
+  uint64_t* hfull = xempty + LSEQ_XS;
+  uint64_t* tfull_bar = hfull + 1;
+  uint64_t* tempty_bar = tfull_bar + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+  const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+  const int T = a.T;
+
+  if (threadIdx.x == 0) {
+    mbar_init(wfull, 1);
+    for (int s = 0; s < LSEQ_XS; ++s) { mbar_init(&xfull[s], 1); mbar_init(&xempty[s], 1); }
+    mbar_init(hfull, 4);
+    for (int s = 0; s < 2; ++s) { mbar_init(&tfull_bar[s], 1); mbar_init(&tempty_bar[s], 4); }
+    fence_barrier_init();
+    prefetch_tensormap(&tmX);
+    prefetch_tensormap(&tmW);
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ================= TMA producer: the weights once, then one x_t tile per (tile, step) =================
+    if (elect_one()) {
+      mbar_arrive_expect_tx(wfull, LSEQ_W_BYTES);
+      tma_load_2d(smem, &tmW, wfull, 0, 0);                              // W_ih: k in [0, 64)
+      tma_load_2d(smem + 256 * 128, &tmW, wfull, 64, 0);                 // W_hh: k in [64, 128)
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x) {
+        int r = tile;
+        const int wb = r % a.tiles_w; r /= a.tiles_w;
+        const int hb = r % a.tiles_h;
+        const int nb = r / a.tiles_h;
+        for (int t = 0; t < T; ++t) {
+          mbar_wait(&xempty[stage], phase ^ 1);
+          mbar_arrive_expect_tx(&xfull[stage], LSEQ_X_BYTES);
+          tma_load_4d(smem + LSEQ_W_BYTES + stage * LSEQ_X_BYTES, &tmX, &xfull[stage], 0, wb * a.TW, hb * a.TH, t * a.B + nb * a.TN);
+          if (++stage == LSEQ_XS) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================= MMA issuer =================
+    constexpr uint32_t idesc = make_idesc_bf16(TC_BM, 256);
+    mbar_wait(wfull, 0);
+    tc_fence_after();
+    int stage = 0;
+    uint32_t phase = 0, s = 0, hp = 0;
+    for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x) {
+      for (int t = 0; t < T; ++t, ++s) {
+        const int acc = (int)(s & 1);
+        mbar_wait(&tempty_bar[acc], ((s >> 1) & 1) ^ 1);
+        mbar_wait(&xfull[stage], phase);
+        tc_fence_after();
+        const uint32_t tmem_acc = tmem_base + (uint32_t)(acc * 256);
+        if (elect_one()) {
+          const uint64_t adesc = make_kmajor_sw128_desc(sX + stage * LSEQ_X_BYTES), bdesc = make_kmajor_sw128_desc(sW);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) umma_bf16(tmem_acc, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, k != 0);
+          umma_commit(&xempty[stage]);
+          if (t == 0) umma_commit(&tfull_bar[acc]);          // zero initial state: no recurrent half
+        }
+        __syncwarp();
+        if (++stage == LSEQ_XS) { stage = 0; phase ^= 1; }
+        if (t > 0) {
+          mbar_wait(hfull, hp & 1);                          // h_{t-1} of this tile is in shared memory
+          ++hp;
+          tc_fence_after();
+          if (elect_one()) {
+            const uint64_t adesc = make_kmajor_sw128_desc(sH), bdesc = make_kmajor_sw128_desc(sW + 256 * 128);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) umma_bf16(tmem_acc, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, 1u);
+            umma_commit(&tfull_bar[acc]);
+          }
+          __syncwarp();
+        }
+      }
+    }
+  } else {
+    // ================= epilogue: gates -> cell update; c and h stay on the SM between steps =================
+    const int q = warp & 3;
+    const uint32_t stg = sStg + q * LSEQ_WARP_STG;
+    const uint32_t seg_c0 = stg, seg_a = stg + 2 * TC_SEG_BYTES, bias_s = stg + 3 * TC_SEG_BYTES;
+    const uint32_t seg_h = sH + q * TC_SEG_BYTES;            // rows q*32 .. q*32+31 of the next step's A operand
+    const int m = q * 32 + lane;
+    const int tw = m % a.TW, th = (m / a.TW) % a.TH, tn = m / (a.TW * a.TH);
+    (void)tw; (void)th; (void)tn;
+    int cpk[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int mm = q * 32 + i * 4 + (lane >> 3);
+      cpk[i] = (mm % a.TW) | (((mm / a.TW) % a.TH) << 8) | ((mm / (a.TW * a.TH)) << 16);
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {                            // biases once per CTA (column (k, gate, e) -> bias row gate*64 + unit)
+      const int col = j * 32 + lane;
+      const int uu = (col >> 6) * 16 + (col & 15), gate = (col >> 4) & 3;
+      const float b = __ldg(a.bias + gate * 64 + uu) + __ldg(a.bias2 + gate * 64 + uu);
+      asm volatile("st.shared.f32 [%0], %1;" ::"r"(bias_s + (uint32_t)col * 4), "f"(b) : "memory");
+    }
+    __syncwarp();
+    const long long pitch_c = 64 * 4, pitch_h = 64 * 2, pitch_a = 256 * 2;
+    uint32_t s = 0;
+    for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x) {
+      int r = tile;
+      const int wb = r % a.tiles_w; r /= a.tiles_w;
+      const int hb = r % a.tiles_h;
+      const int nb = r / a.tiles_h;
+      int cpix[8];
+      unsigned cmask = 0;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int cw = wb * a.TW + (cpk[i] & 0xFF), chh = hb * a.TH + ((cpk[i] >> 8) & 0xFF), cn = nb * a.TN + (cpk[i] >> 16);
+        const bool ok = cw < a.W && chh < a.H && cn < a.B;
+        cpix[i] = ok ? (cn * a.H + chh) * a.W + cw : 0;
+        cmask |= (ok ? 1u : 0u) << i;
+      }
+      for (int t = 0; t < T; ++t, ++s) {
+        const int acc = (int)(s & 1);
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * 256);
+        const bool store_h = a.keep || t == T - 1;
+        uint8_t* c_base = a.keep ? reinterpret_cast<uint8_t*>(a.c_all) + (long long)t * a.rows * pitch_c : nullptr;
+        uint8_t* h_base = reinterpret_cast<uint8_t*>(a.h_all) + (a.keep ? (long long)t * a.rows * pitch_h : 0);
+        uint8_t* acts_base = (a.keep && a.acts_all) ? reinterpret_cast<uint8_t*>(a.acts_all) + (long long)t * a.rows * pitch_a : nullptr;
+        mbar_wait(&tfull_bar[acc], (s >> 1) & 1);
+        tc_fence_after();
+#pragma unroll 1
+        for (int pair = 0; pair < 2; ++pair) {
+          const uint32_t seg_c = seg_c0 + pair * TC_SEG_BYTES;
+#pragma unroll 1
+          for (int kk = 0; kk < 2; ++kk) {
+            const int k = pair * 2 + kk;
+            uint32_t ri[16], rf[16], rg[16], ro[16];
+            tmem_ld_x16(taddr + k * 64, ri);
+            tmem_ld_x16(taddr + k * 64 + 16, rf);
+            tmem_ld_x16(taddr + k * 64 + 32, rg);
+            tmem_ld_x16(taddr + k * 64 + 48, ro);
+            tmem_ld_wait();
+            if (k == 3) {
+              tc_fence_before();
+              __syncwarp();
+              if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+            }
+            float hv[16], cv[16], ai[16], af[16], ag[16], ao[16];
+#pragma unroll
+            for (int e = 0; e < 16; e += 4) {
+              float4 cc = make_float4(0.f, 0.f, 0.f, 0.f);
+              if (t > 0) cc = lds128f(seg_c + stg_off(lane, kk * 4 + (e >> 2)));      // c_{t-1}: left here by the previous step
+              const float pc[4] = {cc.x, cc.y, cc.z, cc.w};
+              const float4 bi4 = lds128f(bias_s + (uint32_t)(k * 64 + e) * 4), bf4 = lds128f(bias_s + (uint32_t)(k * 64 + 16 + e) * 4);
+              const float4 bg4 = lds128f(bias_s + (uint32_t)(k * 64 + 32 + e) * 4), bo4 = lds128f(bias_s + (uint32_t)(k * 64 + 48 + e) * 4);
+              const float pbi[4] = {bi4.x, bi4.y, bi4.z, bi4.w}, pbf[4] = {bf4.x, bf4.y, bf4.z, bf4.w};
+              const float pbg[4] = {bg4.x, bg4.y, bg4.z, bg4.w}, pbo[4] = {bo4.x, bo4.y, bo4.z, bo4.w};
+#pragma unroll
+              for (int z = 0; z < 4; ++z) {
+                ai[e + z] = tanh_sigmoid(__uint_as_float(ri[e + z]) + pbi[z]);
+                af[e + z] = tanh_sigmoid(__uint_as_float(rf[e + z]) + pbf[z]);
+                ag[e + z] = fast_tanh(__uint_as_float(rg[e + z]) + pbg[z]);
+                ao[e + z] = tanh_sigmoid(__uint_as_float(ro[e + z]) + pbo[z]);
+                cv[e + z] = af[e + z] * pc[z] + ai[e + z] * ag[e + z];
+                hv[e + z] = ao[e + z] * fast_tanh(cv[e + z]);
+              }
+              sts128f(seg_c + stg_off(lane, kk * 4 + (e >> 2)), cv[e], cv[e + 1], cv[e + 2], cv[e + 3]);
+            }
+            sts128(seg_h + stg_off(lane, k * 2), pack8_bf16(hv));
+            sts128(seg_h + stg_off(lane, k * 2 + 1), pack8_bf16(hv + 8));
+            if (acts_base) {
+              sts128(seg_a + stg_off(lane, 0), pack8_bf16(ai));
+              sts128(seg_a + stg_off(lane, 1), pack8_bf16(ai + 8));
+              sts128(seg_a + stg_off(lane, 2), pack8_bf16(af));
+              sts128(seg_a + stg_off(lane, 3), pack8_bf16(af + 8));
+              sts128(seg_a + stg_off(lane, 4), pack8_bf16(ag));
+              sts128(seg_a + stg_off(lane, 5), pack8_bf16(ag + 8));
+              sts128(seg_a + stg_off(lane, 6), pack8_bf16(ao));
+              sts128(seg_a + stg_off(lane, 7), pack8_bf16(ao + 8));
+              seg_store(seg_a, acts_base + k * 128, cpix, cmask, pitch_a, lane);
+            }
+          }
+          if (c_base) seg_store(seg_c, c_base + pair * 128, cpix, cmask, pitch_c, lane);
+        }
+        // h_t is complete in shared memory: make it visible to the tensor core (async proxy) and release the next step
+        fence_proxy_async();
+        __syncwarp();
+        if (t < T - 1 && lane == 0) mbar_arrive(hfull);
+        if (store_h) seg_store(seg_h, h_base, cpix, cmask, pitch_h, lane);
+        else __syncwarp();
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------
@@ -1448,6 +1690,60 @@ int lstm_step_tcgen05(const void* x_t, const void* h_prev, const void* w_xh_il, 
   }
   dim3 grid((unsigned)(a.num_tiles < num_sms() ? a.num_tiles : num_sms()));
   return launch_tc<256, 3, __nv_bfloat16, 64, 1>(tA, tA2, tB, a, grid, st);
+}
+
+
+// All T steps of a 64-unit per-pixel LSTM in one launch (lstm_seq64_kernel).  x_seq: [T*B, H, W, 64] bf16 time-major;
+// h_all: training [T][B,H,W,64], inference [B,H,W,64] (= h_T); c_all [T][rows][64] fp32 and acts_all [T][rows][256] bf16 only in
+// training (keep != 0).  -> STFB_ENOTSUP when the geometry does not fit (caller falls back to one launch per step).
+int lstm_seq_supported(int T, int B, int H, int W, int C) {
+  if (C != 64 || T < 1 || B < 1) return 0;
+  int TW, TH, TN;
+  pick_patch(H, W, TW, TH, TN);
+  return (B % TN == 0) ? 1 : 0;            // a tile must not straddle two time steps
+}
+
+int lstm_seq_tcgen05(const void* x_seq, const void* w_xh_il, const float* b_ih, const float* b_hh, float* c_all, void* h_all,
+                     void* acts_all, int T, int B, int H, int W, int C, int keep, cudaStream_t st) {
+  EncodeTiledFn enc = get_tensormap_encoder();
+  if (!enc) { set_error("lstm_seq(tcgen05): cuTensorMapEncodeTiled not available"); return STFB_ECUDA; }
+  if (!lstm_seq_supported(T, B, H, W, C)) { set_error("lstm_seq(tcgen05): unsupported geometry (C=%d, B=%d, %dx%d)", C, B, H, W); return STFB_ENOTSUP; }
+  if ((long long)B * H * W == 0) return STFB_OK;
+  LstmSeqArgs a{};
+  a.bias = b_ih; a.bias2 = b_hh; a.c_all = keep ? c_all : nullptr; a.h_all = h_all; a.acts_all = keep ? acts_all : nullptr;
+  a.rows = (long long)B * H * W; a.T = T; a.B = B; a.H = H; a.W = W; a.keep = keep ? 1 : 0;
+  pick_patch(H, W, a.TW, a.TH, a.TN);
+  a.tiles_w = (W + a.TW - 1) / a.TW;
+  a.tiles_h = (H + a.TH - 1) / a.TH;
+  a.tiles_n = B / a.TN;
+  a.num_tiles = a.tiles_n * a.tiles_h * a.tiles_w;
+  CUtensorMap tX, tW;
+  if (!encode_nhwc_map_strided(enc, &tX, x_seq, T * B, H, W, C, a.TW, a.TH, a.TN, 1, 64)) {
+    set_error("lstm_seq(tcgen05): tensor map (x) failed"); return STFB_ECUDA;
+  }
+  {
+    cuuint64_t dims[2] = {(cuuint64_t)(2 * C), (cuuint64_t)(4 * C)};
+    cuuint64_t strides[1] = {(cuuint64_t)(2 * C) * 2};
+    cuuint32_t box[2] = {64, 256};
+    cuuint32_t estr[2] = {1, 1};
+    if (enc(&tW, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(w_xh_il), dims, strides, box, estr,
+            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS) {
+      set_error("lstm_seq(tcgen05): tensor map (W) failed"); return STFB_ECUDA;
+    }
+  }
+  static bool configured = false;
+  if (!configured) {
+    if (cudaFuncSetAttribute(lstm_seq64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, lseq_smem_bytes()) != cudaSuccess) {
+      set_error("lstm_seq(tcgen05): cannot reserve %d bytes of shared memory", lseq_smem_bytes());
+      cudaGetLastError();
+      return STFB_ECUDA;
+    }
+    configured = true;
+  }
+  dim3 grid((unsigned)(a.num_tiles < num_sms() ? a.num_tiles : num_sms()));
+  lstm_seq64_kernel<<<grid, TC_THREADS, lseq_smem_bytes(), st>>>(tX, tW, a);
+  return post_launch("lstm_seq(tcgen05)");
 }
 
 }  // namespace stfb

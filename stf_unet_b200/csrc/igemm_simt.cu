@@ -231,7 +231,100 @@ static int launch_igemm(const ConvArgs& a, cudaStream_t st) {
   return post_launch("conv2d(simt)");
 }
 
+// ---- pointwise convolutions with a handful of channels on one side (the 32 -> 2 segmentation head, forward and dgrad) ---------
+// The implicit-GEMM tile above is 128 pixels x 64 channels: with 2 output channels 97 % of it is padding and the launch takes
+// 51 us for a 17 MB map (profiles/r02_timeline_summary.txt).  These are plain streaming kernels: one pass over the pixels,
+// weights (<= 8 x C floats) in shared memory.  Weight packing is the SIMT family's [(k)][n] with row stride ldw.
+//   narrow OUT (Cout <= 8): one thread per pixel reads its C channels in 16-byte pieces and keeps Cout accumulators;
+//   narrow IN  (Cin  <= 8): one thread per (pixel, 8 output channels).
+template <typename TI, typename TO>
+__global__ void __launch_bounds__(256) pointwise_narrow_out_kernel(const TI* __restrict__ x, const TI* __restrict__ w, const float* __restrict__ bias,
+                                                                   TO* __restrict__ y, long long P, int Cin, int Cout, int ldw, int relu) {
+  extern __shared__ float s_w[];                       // [Cin][8]
+  for (int i = threadIdx.x; i < Cin * 8; i += blockDim.x) {
+    const int k = i >> 3, n = i & 7;
+    s_w[i] = n < Cout ? ld1(w + (long long)k * ldw + n) : 0.f;
+  }
+  __syncthreads();
+  for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < P; p += (long long)gridDim.x * blockDim.x) {
+    float acc[8];
+#pragma unroll
+    for (int n = 0; n < 8; ++n) acc[n] = (bias != nullptr && n < Cout) ? __ldg(bias + n) : 0.f;
+    const TI* xp = x + p * Cin;
+    for (int k = 0; k < Cin; k += 8) {
+      const f8 v = ld8(xp + k);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const float4 w0 = *reinterpret_cast<const float4*>(s_w + (k + e) * 8), w1 = *reinterpret_cast<const float4*>(s_w + (k + e) * 8 + 4);
+        acc[0] = fmaf(v.v[e], w0.x, acc[0]); acc[1] = fmaf(v.v[e], w0.y, acc[1]); acc[2] = fmaf(v.v[e], w0.z, acc[2]); acc[3] = fmaf(v.v[e], w0.w, acc[3]);
+        acc[4] = fmaf(v.v[e], w1.x, acc[4]); acc[5] = fmaf(v.v[e], w1.y, acc[5]); acc[6] = fmaf(v.v[e], w1.z, acc[6]); acc[7] = fmaf(v.v[e], w1.w, acc[7]);
+      }
+    }
+    for (int n = 0; n < Cout; ++n) st1(y + p * Cout + n, relu ? fmaxf(acc[n], 0.f) : acc[n]);
+  }
+}
+
+template <typename TI, typename TO>
+__global__ void __launch_bounds__(256) pointwise_narrow_in_kernel(const TI* __restrict__ x, const TI* __restrict__ w, const float* __restrict__ bias,
+                                                                  TO* __restrict__ y, long long P, int Cin, int Cout, int ldw, int relu) {
+  extern __shared__ float s_w[];                       // [Cin][Cout]
+  for (int i = threadIdx.x; i < Cin * Cout; i += blockDim.x) s_w[i] = ld1(w + (long long)(i / Cout) * ldw + (i % Cout));
+  __syncthreads();
+  const int chunks = Cout / 8;
+  const long long total = P * chunks;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long p = i / chunks;
+    const int c0 = (int)(i - p * chunks) * 8;
+    float acc[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) acc[e] = bias ? __ldg(bias + c0 + e) : 0.f;
+    for (int k = 0; k < Cin; ++k) {
+      const float xv = ld1(x + p * Cin + k);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) acc[e] = fmaf(xv, s_w[k * Cout + c0 + e], acc[e]);
+    }
+    if (relu) {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) acc[e] = fmaxf(acc[e], 0.f);
+    }
+    st8(y + p * Cout + c0, acc);
+  }
+}
+
+// -> STFB_OK when the launch was taken, 1 when the shape is not one of the narrow pointwise cases
+template <typename TI, typename TO>
+static int launch_pointwise_narrow(const stfb_conv_params* p, cudaStream_t st) {
+  const int Cin = p->C1;
+  const long long P = (long long)p->N * p->Ho * p->Wo;
+  auto aligned = [](const void* q, int b) { return (reinterpret_cast<uintptr_t>(q) % b) == 0; };
+  if (p->kh != 1 || p->kw != 1 || p->stride != 1 || p->pad != 0 || p->C2 != 0 || p->x2 != nullptr || p->scale != nullptr ||
+      p->residual != nullptr || p->bias2 != nullptr || p->Ho != p->H || p->Wo != p->W)
+    return 1;
+  long long blocks = (P + 255) / 256;
+  if (p->Cout <= 8 && Cin % 8 == 0 && Cin <= 512 && aligned(p->x, 16)) {
+    if (blocks > 16LL * num_sms()) blocks = 16LL * num_sms();
+    pointwise_narrow_out_kernel<TI, TO><<<(unsigned)blocks, 256, (size_t)Cin * 8 * sizeof(float), st>>>(
+        reinterpret_cast<const TI*>(p->x), reinterpret_cast<const TI*>(p->w), p->bias, reinterpret_cast<TO*>(p->y), P, Cin, p->Cout, p->ldw, p->relu);
+    return post_launch("conv2d(pointwise, narrow out)");
+  }
+  if (Cin <= 8 && p->Cout % 8 == 0 && p->Cout <= 512 && aligned(p->y, 16)) {
+    blocks = (P * (p->Cout / 8) + 255) / 256;
+    if (blocks > 16LL * num_sms()) blocks = 16LL * num_sms();
+    pointwise_narrow_in_kernel<TI, TO><<<(unsigned)blocks, 256, (size_t)Cin * p->Cout * sizeof(float), st>>>(
+        reinterpret_cast<const TI*>(p->x), reinterpret_cast<const TI*>(p->w), p->bias, reinterpret_cast<TO*>(p->y), P, Cin, p->Cout, p->ldw, p->relu);
+    return post_launch("conv2d(pointwise, narrow in)");
+  }
+  return 1;
+}
+
 int conv2d_simt(const stfb_conv_params* p, cudaStream_t st) {
+  if ((long long)p->N * p->Ho * p->Wo > 0 && (p->Cout <= 8 || p->C1 + p->C2 <= 8)) {
+    int rc = 1;
+    if (p->x_dtype == STFB_F32 && p->y_dtype == STFB_F32) rc = launch_pointwise_narrow<float, float>(p, st);
+    else if (p->x_dtype == STFB_BF16 && p->y_dtype == STFB_BF16) rc = launch_pointwise_narrow<__nv_bfloat16, __nv_bfloat16>(p, st);
+    else if (p->x_dtype == STFB_BF16 && p->y_dtype == STFB_F32) rc = launch_pointwise_narrow<__nv_bfloat16, float>(p, st);
+    if (rc != 1) return rc;
+  }
   ConvArgs a;
   a.p = *p;
   a.M = (long long)p->N * p->Ho * p->Wo;
@@ -734,6 +827,27 @@ extern "C" int stfb_pack_weight_ex(const float* w, void* wp, int D0, int D1, int
 extern "C" int stfb_pack_weight(const float* w, void* wp, int D0, int D1, int kh, int kw, int k_is_dim1, int dtype,
                                 void* stream) {
   return stfb_pack_weight_ex(w, wp, D0, D1, kh, kw, k_is_dim1, 0, 0, 0, 0, dtype, stream);
+}
+
+namespace stfb {
+int lstm_seq_supported(int T, int B, int H, int W, int C);
+int lstm_seq_tcgen05(const void* x_seq, const void* w_xh_il, const float* b_ih, const float* b_hh, float* c_all, void* h_all,
+                     void* acts_all, int T, int B, int H, int W, int C, int keep, cudaStream_t st);
+}
+
+extern "C" int stfb_lstm_seq_supported(int T, int B, int H, int W, int C) { return stfb::lstm_seq_supported(T, B, H, W, C); }
+
+extern "C" int stfb_lstm_seq_fused(const void* x_seq, const void* w_xh_il, const float* b_ih, const float* b_hh, float* c_all,
+                                   void* h_all, void* acts_all, int T, int B, int H, int W, int C, int keep, void* stream) {
+  STFB_REQUIRE(x_seq && w_xh_il && b_ih && b_hh && h_all && T > 0 && B >= 0 && H > 0 && W > 0, "lstm_seq_fused: bad arguments");
+  STFB_REQUIRE(!keep || (c_all && acts_all), "lstm_seq_fused: training (keep) needs c_all and acts_all");
+  STFB_REQUIRE((long long)T * B * H * W < 2000000000LL, "lstm_seq_fused: too many rows");
+  auto al = [](const void* q) { return q == nullptr || (reinterpret_cast<uintptr_t>(q) % 16) == 0; };
+  STFB_REQUIRE(al(x_seq) && al(w_xh_il) && al(b_ih) && al(b_hh) && al(c_all) && al(h_all) && al(acts_all),
+               "lstm_seq_fused: pointers must be 16-byte aligned");
+  STFB_DEVICE_OR_RETURN();
+  return stfb::lstm_seq_tcgen05(x_seq, w_xh_il, b_ih, b_hh, c_all, h_all, acts_all, T, B, H, W, C, keep,
+                                reinterpret_cast<cudaStream_t>(stream));
 }
 
 extern "C" int stfb_lstm_step_fused(const void* x_t, const void* h_prev, const void* w_xh_il, const float* b_ih,

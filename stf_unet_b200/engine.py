@@ -20,6 +20,7 @@ BN_MOMENTUM = 0.1
 import os as _os
 USE_TCGEN05 = _os.environ.get("STFB_NO_TCGEN05", "0") != "1"
 USE_FUSED_LSTM = _os.environ.get("STFB_NO_FUSED_LSTM", "0") != "1"
+USE_LSTM_SEQ = _os.environ.get("STFB_NO_LSTM_SEQ", "0") != "1"      # all-T kernel for 64-unit levels (csrc/conv_tc.cu lstm_seq64_kernel)
 USE_FUSED_BN_STATS = _os.environ.get("STFB_NO_FUSED_BN_STATS", "0") != "1"
 USE_LSTM_STREAMS = _os.environ.get("STFB_NO_LSTM_STREAMS", "0") != "1"
 USE_WGRAD_STREAM = _os.environ.get("STFB_NO_WGRAD_STREAM", "0") != "1"
@@ -612,7 +613,15 @@ class Executor:
         cs = torch.empty((T if keep else 2, R, C), dtype=torch.float32, device=dev)
         hs = torch.empty((T if keep else 2, B, h, w, C), dtype=self.dtype, device=dev)
         fused = tc and C % 64 == 0 and USE_FUSED_LSTM
-        if fused:
+        if fused and USE_LSTM_SEQ and ops.lstm_seq_supported(T, B, h, w, C):
+            # hidden size 64: the whole time loop in ONE kernel -- weights, c and h_{t-1} stay in shared memory, x_t streams
+            # through a TMA ring; inference writes nothing but h_T
+            wxh = self.packed_lstm_xh(wih, whh, C)
+            if keep:
+                ops.lstm_seq_fused(seq.data, wxh, P[bih], P[bhh], T, cs, hs, acts)
+            else:
+                ops.lstm_seq_fused(seq.data, wxh, P[bih], P[bhh], T, None, hs[(T - 1) % 2], None)
+        elif fused:
             # one kernel per time step: implicit GEMM over [x_t, h_{t-1}] -> four gates in TMEM -> cell update in the
             # epilogue; the gate pre-activations never exist in memory
             wxh = self.packed_lstm_xh(wih, whh, C)

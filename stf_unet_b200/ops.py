@@ -15,7 +15,7 @@ from ._lib import BF16, CONV_FWD, CONV_TRANSPOSED, F32, IMPL_AUTO, IMPL_SIMT, IM
 
 __all__ = ["dt_code", "conv2d", "conv2d_wgrad", "pack_weight", "bn_stats", "bn_finalize_train", "bn_fold_eval",
            "bn_apply", "bn_bwd", "colsum", "maxpool_fwd", "maxpool_bwd", "maxpool_fwd_idx", "maxpool_bwd_idx", "bilinear_fwd", "bilinear_bwd",
-           "tcgen05_ok", "conv_stats_fusable", "STAT_SLOTS", "im2col_small", "unpad_wgrad", "lstm_step_fused", "pack_lstm_xh", "lstm_cell_fwd", "lstm_cell_bwd", "bn_apply_from_stats", "bn_relu_maxpool_from_stats", "bn_bwd_scratch_floats", "pack_series", "pack_series_u8", "adamw_flat_", "pack_series_maps", "repeat_batch", "nhwc_to_nchw", "nchw_to_nhwc", "add_", "cast",
+           "tcgen05_ok", "conv_stats_fusable", "STAT_SLOTS", "im2col_small", "unpad_wgrad", "lstm_step_fused", "lstm_seq_fused", "lstm_seq_supported", "pack_lstm_xh", "lstm_cell_fwd", "lstm_cell_bwd", "bn_apply_from_stats", "bn_relu_maxpool_from_stats", "bn_bwd_scratch_floats", "pack_series", "pack_series_u8", "adamw_flat_", "pack_series_maps", "repeat_batch", "nhwc_to_nchw", "nchw_to_nhwc", "add_", "cast",
            "ce_dice_fwd", "ce_dice_bwd", "CONV_FWD", "CONV_TRANSPOSED", "IMPL_AUTO", "IMPL_SIMT", "IMPL_TCGEN05"]
 
 _DT = {torch.float32: F32, torch.bfloat16: BF16}
@@ -155,8 +155,12 @@ def conv2d(x, wp, Cout, k, stride, pad, *, mode=CONV_FWD, out_hw=None, x2=None, 
     nbytes = (x.numel() + (0 if x2 is None else x2.numel())) * esz + y.numel() * y.element_size() + wp.numel() * esz
     e0 = _prof.begin()
     check(lib.stfb_conv2d(C.byref(p), _stream()), "conv2d")
-    _prof.end(e0, "conv_tcgen05" if tc else "conv_simt_" + ("bf16" if esz == 2 else "f32"), flops, nbytes,
-              f"x{tuple(x.shape)}+{C2} ->{Cout} k{kh} s{stride} m{mode}")
+    # families follow the kernels: 3x3 / stride-1 "same" layers of 64-channel multiples on maps >= 12 x 8 run the halo kernels
+    # (conv_halo2_kernel on CTA pairs, conv_halo_kernel otherwise), every other geometry the streaming conv_tc_kernel
+    halo = tc and kh == 3 and kw == 3 and stride == 1 and C1 % 64 == 0 and C2 % 64 == 0 and Cout % 64 == 0 and Ho >= 12 and Wo >= 8 \
+        and Ho == H and Wo == W
+    fam = ("conv3x3_halo_tcgen05" if halo else "conv_other_tcgen05") if tc else "conv_simt_" + ("bf16" if esz == 2 else "f32")
+    _prof.end(e0, fam, flops, nbytes, f"x{tuple(x.shape)}+{C2} ->{Cout} k{kh} s{stride} m{mode}")
     return y
 
 
@@ -544,9 +548,28 @@ def lstm_step_fused(x_t, h_prev, w_xh_il, b_ih, b_hh, c_prev, c_out, h_out, acts
     if e0 is not None:
         rows = N * H * W
         kc = C_ * (2 if h_prev is not None else 1)
-        _prof.end(e0, "conv_tcgen05", 2.0 * rows * kc * 4 * C_,
+        _prof.end(e0, "lstm_step_tcgen05", 2.0 * rows * kc * 4 * C_,
                   rows * C_ * (2 + 4 + 2 + (2 + 4 if h_prev is not None else 0) + (8 if acts is not None else 0)),
                   f"lstm_step_fused rows{rows} C{C_} K{kc}")
+
+
+def lstm_seq_supported(T, B, H, W, C_):
+    return _lib.load().stfb_lstm_seq_supported(T, B, H, W, C_) == 1
+
+
+def lstm_seq_fused(x_seq, w_xh_il, b_ih, b_hh, T, c_all, h_all, acts_all):
+    """All T steps of a 64-unit per-pixel LSTM level in one launch.  x_seq [T*B, H, W, C] bf16 time-major.  Training: c_all
+    [T,R,C] fp32, h_all [T,B,H,W,C], acts_all [T,R,4C]; inference: c_all = acts_all = None and h_all [B,H,W,C] receives h_T."""
+    TB, H, W, C_ = x_seq.shape
+    B = TB // T
+    keep = c_all is not None
+    e0 = _prof.begin() if _prof is not None else None
+    check(_lib.load().stfb_lstm_seq_fused(_p(x_seq), _p(w_xh_il), _p(b_ih), _p(b_hh), _p(c_all), _p(h_all), _p(acts_all), T, B, H, W,
+                                          C_, int(keep), _stream()), "lstm_seq_fused")
+    if e0 is not None:
+        rows = B * H * W
+        _prof.end(e0, "lstm_step_tcgen05", 2.0 * rows * C_ * 4 * C_ * (2 * T - 1),
+                  rows * C_ * (2 * T + ((4 + 2 + 8) * T if keep else 2)), f"lstm_seq_fused rows{rows} C{C_} T{T}")
 
 
 def pack_lstm_xh(w_ih, w_hh, dtype):

@@ -696,6 +696,49 @@ def test_lstm_step_fused_matches_reference(B, h, w, C):
         assert rel(c2, c_ref) < 3e-3
 
 
+@pytest.mark.parametrize("B,T,h,w", [(4, 5, 16, 16), (2, 8, 64, 64), (6, 3, 8, 8), (3, 4, 20, 20), (1, 1, 16, 16)])
+def test_lstm_seq_fused_equals_step_by_step_and_oracle(B, T, h, w):
+    """The all-T kernel (hidden size 64: weights, c and h resident in shared memory for the whole time loop) against T launches
+    of the per-step kernel -- same arithmetic, same accumulation order: bit-identical c, h and saved activations -- and against
+    the oracle's gate-by-gate LSTM (reference: nn.LSTM over [B*h*w, T, C], src/stf_lstm_unet.py:124-127, :216-221)."""
+    from oracle import stf_oracle as O
+    C = 64
+    bf = torch.bfloat16
+    R = B * h * w
+    assert ops.lstm_seq_supported(T, B, h, w, C)
+    x = q(rnd(T * B, h, w, C, seed=3) * 0.7, bf).to(bf).contiguous()
+    wih = q(rnd(4 * C, C, seed=5, scale=1.0 / C ** 0.5), bf)
+    whh = q(rnd(4 * C, C, seed=2, scale=1.0 / C ** 0.5), bf)
+    bih, bhh = rnd(4 * C, seed=3) * 0.1, rnd(4 * C, seed=6) * 0.1
+    wp = ops.pack_lstm_xh(wih.contiguous(), whh.contiguous(), bf)
+    # step by step
+    cs = torch.empty(T, R, C, device=DEV)
+    hs = torch.empty(T, B, h, w, C, device=DEV, dtype=bf)
+    acts = torch.empty(T, R, 4 * C, device=DEV, dtype=bf)
+    xs = x.view(T, B, h, w, C)
+    for t in range(T):
+        ops.lstm_step_fused(xs[t], hs[t - 1] if t else None, wp, bih, bhh, cs[t - 1] if t else None, cs[t], hs[t],
+                            acts[t].view(B, h, w, 4 * C))
+    # one launch, training form
+    cs2, hs2, acts2 = torch.full_like(cs, float("nan")), torch.zeros_like(hs), torch.zeros_like(acts)
+    ops.lstm_seq_fused(x, wp, bih, bhh, T, cs2, hs2, acts2)
+    torch.cuda.synchronize()
+    assert torch.equal(cs2, cs) and torch.equal(hs2, hs) and torch.equal(acts2, acts)
+    # inference form: h_T only
+    hT = torch.zeros(B, h, w, C, device=DEV, dtype=bf)
+    ops.lstm_seq_fused(x, wp, bih, bhh, T, None, hT, None)
+    assert torch.equal(hT, hs[T - 1])
+    # oracle: seq [B, T, C, h, w] -> h_T [B, C, h, w]
+    seq = x.float().view(T, B, h, w, C).permute(1, 0, 4, 2, 3).contiguous()
+    h_ref = O.pixel_lstm_last(seq, wih, whh, bih, bhh)
+    assert rel(hT.float().permute(0, 3, 1, 2), h_ref) < 1e-2
+
+
+def test_lstm_seq_fused_rejects_what_it_cannot_tile():
+    assert not ops.lstm_seq_supported(8, 16, 32, 32, 128)      # hidden size 128: weights do not fit shared memory
+    assert not ops.lstm_seq_supported(4, 3, 8, 8, 64)          # two 8x8 images per tile, odd batch: a tile would straddle steps
+
+
 def test_lstm_cell_bwd_interleaved_acts_matches_gate_major():
     """lstm_cell_bwd reads the fused step's activation layout (acts_il) and must agree with the gate-major form."""
     bf = torch.bfloat16
