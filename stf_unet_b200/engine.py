@@ -26,6 +26,9 @@ USE_LSTM_STREAMS = _os.environ.get("STFB_NO_LSTM_STREAMS", "0") != "1"
 USE_WGRAD_STREAM = _os.environ.get("STFB_NO_WGRAD_STREAM", "0") != "1"
 USE_SIDE_FINALIZE = _os.environ.get("STFB_NO_SIDE_FINALIZE", "0") != "1"
 USE_FUSED_STEM = _os.environ.get("STFB_NO_FUSED_STEM", "0") != "1"
+# the training step's weight pack (223 us for 27 M parameters) split in two: the stem's weights at once, the rest on a
+# low-priority side stream beside the stem's memory-bound kernels.  STFB_NO_PACK_OVERLAP=1 disables.
+USE_PACK_OVERLAP = _os.environ.get("STFB_NO_PACK_OVERLAP", "0") != "1"
 # Two forward chains: the encoder's time steps are independent until the LSTMs (BatchNorm statistics are per time step), so
 # in the training forward every encoder layer is launched as two half-batch launches (time steps [0, T/2) and [T/2, T)) on two
 # streams.  Each chain alternates tensor-bound convolutions with HBM-bound BatchNorm passes; the two chains drift out of
@@ -89,6 +92,8 @@ class Executor:
         self.acc: Dict[str, torch.Tensor] = {}
         self.grad_offsets: Dict[str, int] = {}
         self._deferred = {}           # name -> (flat offset, Cp, Cg_total, khw)
+        self._pack_join = None        # side stream still packing the late weights (joined by the first consumer)
+        self._owner = None
         self.flat = None              # this forward's flat gradient buffer (self.grads are views of it)
         self.segment_hook = None      # callable(flat_slice): gradient range final (data-parallel all-reduce); None = off
         self._seg_end = None
@@ -133,8 +138,17 @@ class Executor:
         nh, gh = (N // G) * (G // 2), G // 2
         return [(sp[0], 0, nh, 0, gh), (sp[1], nh, N, gh, G)]
 
+    def _join_late_packs(self, name):
+        """The first consumer of a weight that was packed on the side stream (ops.PackPlan.run(early=...)) waits for it; every
+        later consumer is ordered behind this point through the streams it forks from."""
+        j = self._pack_join
+        if j is not None and not (self._owner is not None and self._owner._early_pack is not None and self._owner._early_pack(name)):
+            torch.cuda.current_stream().wait_stream(j)
+            self._pack_join = None
+
     def packed(self, name, k_is_dim1, n_major=False, flip=False, kpad=None, gate_c=0):
         key = (name, bool(k_is_dim1), bool(n_major), bool(flip), kpad, int(gate_c))
+        self._join_late_packs(name)
         wp = self._packed.get(key)
         if wp is None:
             wp = ops.pack_weight(self.params[name], k_is_dim1, self.dtype, n_major=n_major, flip=flip, kpad=kpad,
@@ -149,6 +163,7 @@ class Executor:
         cat = "xh:" + wih
         k1 = (wih, True, True, False, None, int(C), (cat, 0, 2 * C))
         k2 = (whh, True, True, False, None, int(C), (cat, C, 2 * C))
+        self._join_late_packs(wih)
         wp = self._packed.get(k1)
         if wp is None:
             wp = ops.pack_lstm_xh(self.params[wih], self.params[whh], self.dtype)
@@ -260,6 +275,9 @@ class Executor:
     def join_finalize(self):
         """End of the forward pass: the side-stream BatchNorm finalize launches (running statistics, saved coefficients)
         are ordered before whatever follows on the current stream."""
+        if self._pack_join is not None:           # nobody consumed a late pack (cannot happen in the models here): join anyway
+            torch.cuda.current_stream().wait_stream(self._pack_join)
+            self._pack_join = None
         if self._fin_keep:
             cur = torch.cuda.current_stream()
             side = Executor._fin_streams.get(cur.device.index)

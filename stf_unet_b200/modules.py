@@ -127,11 +127,17 @@ class B200Module(nn.Module):
             if stamp is not None and getattr(plan, "stamp", None) == stamp:
                 ex._packed = dict(plan.buffers)
             else:
-                ex._packed = plan.run()
+                # training step: only the stem's weights are needed at once; everything else is packed on a low-priority side
+                # stream beside the stem's memory-bound kernels and joined at the first layer that needs it (engine.packed)
+                early = self._early_pack if (self.training and record and engine.USE_PACK_OVERLAP) else None
+                ex._packed, ex._pack_join = plan.run(early)
                 plan.stamp = stamp
         else:
             plans.pop((ex.dtype, self.training, record), None)
         return ex
+
+    #: parameters whose packed copies the forward pass needs first (subclasses override); None = no early / late split
+    _early_pack = None
 
     def _numel(self, name):
         return self._param_cache()[name].numel()

@@ -316,6 +316,7 @@ class PackPlan:
                        ld if n_major else 0, int(gate_c))
             start += D0 * D1                      # one work item per (d0, d1) position, all taps
         self.total = start
+        self._job_dtype = job_t
         self.table = torch.from_numpy(jobs.view(np.uint8)).to(dev)
         self.signature = tuple(params[k[0]].data_ptr() for k in self.keys)
 
@@ -325,11 +326,45 @@ class PackPlan:
         except KeyError:
             return False
 
-    def run(self):
-        with _timed("pack_weight", 0):
-            check(_lib.load().stfb_pack_weights_batched(_p(self.table), len(self.keys), self.total, dt_code(self.dtype),
-                                                        _stream()), "pack_weights_batched")
-        return dict(self.buffers)
+    def run(self, early=None):
+        """One launch for every pack -- or, with `early` (a predicate on the parameter name), two: the packs the first layers
+        need on the current stream, the rest on a low-priority side stream beside them.  -> (buffers, side stream or None);
+        the caller orders the first consumer of a late pack behind the side stream."""
+        lib = _lib.load()
+        if early is None or not torch.cuda.is_available():
+            with _timed("pack_weight", 0):
+                check(lib.stfb_pack_weights_batched(_p(self.table), len(self.keys), self.total, dt_code(self.dtype), _stream()),
+                      "pack_weights_batched")
+            return dict(self.buffers), None
+        split = getattr(self, "_split", None)
+        if split is None:
+            import numpy as np
+            raw = self.table.cpu().numpy().view(self._job_dtype)
+            idx_e = [j for j, k in enumerate(self.keys) if early(k[0])]
+            idx_l = [j for j, k in enumerate(self.keys) if not early(k[0])]
+            parts = []
+            for idx in (idx_e, idx_l):
+                jobs = raw[idx].copy()
+                start = 0
+                for j in range(len(jobs)):
+                    jobs[j]["start"] = start
+                    start += int(jobs[j]["D0"]) * int(jobs[j]["D1"])
+                parts.append((torch.from_numpy(jobs.view(np.uint8).copy()).to(self.table.device), len(idx), start))
+            split = self._split = parts
+        cur = torch.cuda.current_stream()
+        side = PackPlan._side.get(cur.device.index)
+        if side is None:
+            side = PackPlan._side[cur.device.index] = torch.cuda.Stream(device=cur.device)      # default = lowest priority
+        (te, ne, tote), (tl, nl, totl) = split
+        if nl:
+            side.wait_stream(cur)
+            with torch.cuda.stream(side):
+                check(lib.stfb_pack_weights_batched(_p(tl), nl, totl, dt_code(self.dtype), side.cuda_stream), "pack_weights_batched")
+        if ne:
+            check(lib.stfb_pack_weights_batched(_p(te), ne, tote, dt_code(self.dtype), _stream()), "pack_weights_batched")
+        return dict(self.buffers), (side if nl else None)
+
+    _side = {}
 
 
 def im2col_small(x, k, stride, pad, kpad, out=None):

@@ -54,6 +54,10 @@ class STFLSTMUNet(B200Module):
     input_mean = 0.709
     input_std = 0.127
 
+    @staticmethod
+    def _early_pack(name):
+        return name.startswith("conv1.")          # the stem; every other weight is packed beside it
+
     def __init__(self, in_channels=1, num_classes=2, time_steps=8, use_pk_maps=False, pk_channels=3):
         super().__init__()
         self.time_steps = time_steps

@@ -658,3 +658,104 @@ def test_bench_size_train_step_bf16_vs_oracle():
 def test_config3_train_step_bf16_vs_oracle():
     """BASELINE.json configs[3]: T=16 phases x 512x512 (B=2 here: the oracle keeps every fp32 activation alive)."""
     _train_parity_case(2, 16, 512, 4321)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# round-1 advisor findings, pinned
+# ---------------------------------------------------------------------------------------------------------------------
+def _bf16_grads(model, x, t):
+    for p in model.parameters():
+        p.grad = None
+    model.train()
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        loss = S.criterion(model(x), t)
+    loss.backward()
+    torch.cuda.synchronize()
+    return {n: p.grad.detach().clone() for n, p in model.named_parameters()}
+
+
+def test_wgrad_side_streams_do_not_share_partial_tiles(monkeypatch):
+    """Halo weight gradients write per-split partial tiles that a second kernel sums; launches rotate over three side streams
+    that are ordered only against the main stream.  Every stream owns its own scratch slot (csrc/wgrad_tc.cu): the gradients with
+    three side streams equal the single-stream gradients (deterministic BatchNorm routes; the partial sums meet through fp32
+    red.adds, so equality is to rounding, 1e-5 -- an overwritten partial tile shows up as O(1))."""
+    from stf_unet_b200 import engine, ops
+    monkeypatch.setattr(engine, "USE_FUSED_BN_STATS", False)
+    monkeypatch.setattr(ops, "USE_FUSED_BN_BWD", False)
+    x, t = W.synthetic_dce_batch(8, 4, 128, 128, seed=81)
+    x, t = x.to(DEV), t.to(DEV)
+    sd = warm_stf_state()
+    m = load_model(S.STFLSTMUNet(1, 2, 4), sd)
+    monkeypatch.setattr(engine, "USE_WGRAD_STREAM", False)
+    ref = _bf16_grads(m, x, t)
+    monkeypatch.setattr(engine, "USE_WGRAD_STREAM", True)
+    for _ in range(3):                                      # several runs: the race was timing dependent
+        m.load_state_dict(sd)
+        got = _bf16_grads(m, x, t)
+        for n in ref:
+            assert rel(got[n], ref[n]) < 1e-5, n
+
+
+def test_two_forwards_before_backward_and_gradient_accumulation():
+    """engine.ModelFunction scatters into THE flat buffer of its own forward (not the latest one) and accumulates into the buffer
+    the parameters' .grad view when gradients already exist (zero_grad(set_to_none=False), micro-batches)."""
+    sd = W.make_state_dict(W.stf_param_spec(1, 2), seed=0)
+    xa, ta = (v.to(DEV) for v in W.synthetic_dce_batch(2, 2, 64, 64, seed=91))
+    xb, tb = (v.to(DEV) for v in W.synthetic_dce_batch(2, 2, 64, 64, seed=92))
+    m = load_model(S.STFLSTMUNet(1, 2, 2), sd).train()
+
+    def grads_of(x, t):
+        m.load_state_dict(sd)
+        for p in m.parameters():
+            p.grad = None
+        S.criterion(m(x), t).backward()
+        return {n: p.grad.detach().clone() for n, p in m.named_parameters()}
+
+    ga, gb = grads_of(xa, ta), grads_of(xb, tb)
+    # two forwards, then both backwards: the sum of the two gradients (running stats are irrelevant to train-mode gradients)
+    m.load_state_dict(sd)
+    for p in m.parameters():
+        p.grad = None
+    la = S.criterion(m(xa), ta)
+    lb = S.criterion(m(xb), tb)
+    la.backward()
+    lb.backward()
+    flat = m._last_flat_grad
+    for n, p in m.named_parameters():
+        assert rel(p.grad, ga[n] + gb[n]) < 2e-4, n
+    assert m.conv1.weight.grad.data_ptr() == flat.data_ptr()          # .grad still views the flat buffer the optimizer steps on
+    # zero_grad(set_to_none=False) keeps the views; the next backward adds into the same buffer
+    opt = torch.optim.SGD(m.parameters(), lr=0.0)
+    opt.zero_grad(set_to_none=False)
+    S.criterion(m(xa), ta).backward()
+    assert m._last_flat_grad is flat
+    for n, p in m.named_parameters():
+        assert rel(p.grad, ga[n]) < 2e-4, n
+
+
+def test_graphed_step_rebinds_grads_for_any_optimizer():
+    """Graph replay runs no Python; GraphedStep re-binds the .grad views after every replay, so torch.optim.AdamW with its
+    default zero_grad(set_to_none=True) between steps keeps training (it silently skipped every parameter before)."""
+    from stf_unet_b200.graph import GraphedStep
+    torch.manual_seed(0)
+    x, t = (v.to(DEV) for v in W.synthetic_dce_batch(2, 2, 64, 64, seed=95))
+    m = S.STFLSTMUNet(1, 2, 2).to(DEV)
+    opt = torch.optim.AdamW(m.parameters(), lr=1e-3, fused=True)
+    g = GraphedStep(m, S.criterion, x, t, warmup=2)
+    w0 = m.final.weight.detach().clone()
+    losses = []
+    for _ in range(4):
+        opt.zero_grad()                                   # set_to_none=True
+        losses.append(g(x, t).item())
+        assert m.final.weight.grad is not None
+        opt.step()
+    assert not torch.equal(w0, m.final.weight) and losses[-1] < losses[0]
+
+
+def test_parameter_hooks_are_refused():
+    """torch DDP / register_hook rely on per-parameter autograd hooks that never fire here (one autograd node): refuse loudly."""
+    m = S.STFLSTMUNet(1, 2, 2).to(DEV).train()
+    m.final.weight.register_hook(lambda g: g)
+    x, _ = W.synthetic_dce_batch(1, 2, 64, 64, seed=3)
+    with pytest.raises(RuntimeError, match="hooks"):
+        m(x.to(DEV))
