@@ -444,7 +444,10 @@ def run_own(args, rank, world, local_rank):
                       "rel_diff": round(abs(l16 - l32) / max(abs(l32), 1e-12), 6),
                       "grad_rel_err_bf16_vs_fp32_max": round(max(gerr.values()), 5),
                       "grad_rel_err_worst": max(gerr, key=gerr.get)}
-        if not (abs(l16 - l32) <= 5e-2 * max(abs(l32), 1e-6)) or not (max(gerr.values()) < 0.3):
+        # bars: eval loss within 2e-2 (north_star's bf16 tolerance); every sampled gradient within 0.15 -- torch's OWN bf16
+        # autocast of the reference arithmetic is 9.2e-2 away from fp32 on its worst parameter at this size
+        # (tests/test_models_gpu.py::test_bench_size_train_step_bf16_vs_oracle), this library measures 3-4e-2 here
+        if not (abs(l16 - l32) <= 2e-2 * max(abs(l32), 1e-6)) or not (max(gerr.values()) < 0.15):
             raise SystemExit(f"bench.py: bf16 and fp32 paths disagree on the bench batch: {loss_check} {gerr}")
 
     # ---- roofline of the dominant kernel family: per-launch CUDA events over one extra step ----

@@ -268,6 +268,14 @@ int stfb_lstm_step_fused(const void* x_t, const void* h_prev, const void* w_xh_i
 int stfb_lstm_seq_supported(int T, int B, int H, int W, int C);
 int stfb_lstm_seq_fused(const void* x_seq, const void* w_xh_il, const float* b_ih, const float* b_hh, float* c_all, void* h_all,
                         void* acts_all, int T, int B, int H, int W, int C, int keep, void* stream);
+/* One LSTM BACKWARD step as one tcgen05 kernel: dh_{t-1} = dG_t W_hh accumulated in TMEM, and the epilogue differentiates the
+ * cell of step t-1 on the spot (the arithmetic of stfb_lstm_cell_bwd): dg_out = dG_{t-1} (bf16 [rows][4C], gate-major i,f,g,o),
+ * dc rewritten in place; dh never exists in memory.  dg_next = dG_t [N,H,W,4C] bf16; w_hh_d = W_hh packed for dgrad
+ * (stfb_pack_weight_ex(W_hh, k_is_dim1 = 0, n_major = 1): [C][4C]); acts (accumulator column order, from stfb_lstm_step_fused /
+ * stfb_lstm_seq_fused), c_cur and c_prev belong to step t-1 (c_prev = NULL when t-1 == 0).  Replaces one
+ * stfb_lstm_cell_bwd + one stfb_conv2d launch of the backward time loop (autograd of nn.LSTM, src/stf_lstm_unet.py:216-242). */
+int stfb_lstm_bwd_step_fused(const void* dg_next, const void* w_hh_d, const void* acts, const float* c_prev, const float* c_cur,
+                             float* dc, void* dg_out, int N, int H, int W, int C, void* stream);
 /* c_prev may be NULL (t = 0, zero state).  acts (dtype, [R][4C]) may be NULL in eval mode.
  * c_out fp32 [R][C]; h_out dtype [R][C]. */
 int stfb_lstm_cell_fwd(const float* gates, const float* c_prev, void* acts, float* c_out, void* h_out, long long R,

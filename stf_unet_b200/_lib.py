@@ -75,6 +75,7 @@ _SIGS = {
     "stfb_ce_dice_bwd": [_vp] * 5 + [_i, _i, _i, _f, _vp],
     "stfb_ce_dice_fwd_ex": [_vp] * 5 + [_i, _i, _i, _f, _ll, _i, _vp],
     "stfb_ce_dice_bwd_ex": [_vp] * 6 + [_i, _i, _i, _f, _ll, _i, _vp],
+    "stfb_lstm_bwd_step_fused": [_vp] * 7 + [_i] * 4 + [_vp],
     "stfb_lstm_seq_supported": [_i] * 5,
     "stfb_lstm_seq_fused": [_vp] * 7 + [_i] * 6 + [_vp],
     "stfb_augment_series_u8": [_vp] * 6 + [_i] * 6 + [_f, _f, _vp],

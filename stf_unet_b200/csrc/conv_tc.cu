@@ -46,7 +46,8 @@ struct TcArgs {
   // fused LSTM cell epilogue (EPI == 1): accumulator = [x_t, h_{t-1}] [W_ih | W_hh]^T with chunk-interleaved columns
   // (column j of a 256-wide tile: 16-unit chunk j / 64, gate (j % 64) / 16, unit u_base + 16 * chunk + j % 16)
   const float* c_prev;   // [rows][Chid] fp32 or NULL (t = 0)
-  float* c_out;          // [rows][Chid] fp32
+  const float* c_cur;    // EPI == 2 (LSTM backward step): cell state of the step being differentiated, [rows][Chid] fp32
+  float* c_out;          // [rows][Chid] fp32 (EPI == 2: the running d(cell) gradient, read and rewritten in place)
   void* acts;            // [rows][4*Chid] bf16 post-activation gates in accumulator column order (NULL in eval)
   int Chid;
   float* stat_partial;   // fused BatchNorm statistics: [stat_slots][2][stat_groups][Cout] fp32 (NULL = off)
@@ -599,6 +600,70 @@ __global__ void __launch_bounds__(TC_THREADS, MINB) conv_tc_kernel(const __grid_
           seg_store(seg_c, cout_base + pair * 128, cpix, cmask, pitch_c, lane);
         }
         seg_store(seg_h, h_base, cpix, cmask, pitch_h, lane);
+      } else if constexpr (EPI == 2) {
+        // ===== fused LSTM backward step.  The accumulator is dh_{t-1} = dG_t W_hh for hidden units [n0, n0 + BN); the
+        // epilogue differentiates the cell of step t-1 right there (the arithmetic of lstm_cell_bwd_kernel, operation for
+        // operation) and writes dG_{t-1} (bf16, gate-major [rows][4C]) and the running d(cell): dh never exists in memory
+        // and the step is one launch instead of two.  Row per lane, 8 hidden units at a time: the saved activations of a
+        // 16-unit chunk are one contiguous 128-byte run per row (accumulator column order), c / dc are 32-byte runs.
+        const int C = a.Chid;
+        const long long row = ((long long)on * a.Hout + oh) * a.Wout + ow;
+        const __nv_bfloat16* acts_r = reinterpret_cast<const __nv_bfloat16*>(a.acts) + row * 4 * C;
+        __nv_bfloat16* dg_r = reinterpret_cast<__nv_bfloat16*>(a.y) + row * 4 * C;
+        const float* cc_r = a.c_cur + row * C;
+        const float* cp_r = a.c_prev ? a.c_prev + row * C : nullptr;
+        float* dc_r = a.c_out + row * C;
+#pragma unroll 1
+        for (int c0 = 0; c0 < BN; c0 += 16) {
+          uint32_t r[16];
+          tmem_ld_x16(taddr + c0, r);
+          tmem_ld_wait();
+          if (c0 + 16 >= BN) {
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+          }
+          if (!valid) continue;
+#pragma unroll
+          for (int hlf = 0; hlf < 2; ++hlf) {
+            const int u0 = t.n0 + c0 + hlf * 8;                                // first of 8 hidden units
+            const __nv_bfloat16* ap = acts_r + (u0 >> 4) * 64 + (u0 & 15);     // (chunk, gate, unit) order
+            float ai[8], af[8], ag[8], ao[8], cc[8], cp[8], dc[8];
+            unpack8_bf16(*reinterpret_cast<const uint4*>(ap), ai);
+            unpack8_bf16(*reinterpret_cast<const uint4*>(ap + 16), af);
+            unpack8_bf16(*reinterpret_cast<const uint4*>(ap + 32), ag);
+            unpack8_bf16(*reinterpret_cast<const uint4*>(ap + 48), ao);
+            *reinterpret_cast<float4*>(cc) = *reinterpret_cast<const float4*>(cc_r + u0);
+            *reinterpret_cast<float4*>(cc + 4) = *reinterpret_cast<const float4*>(cc_r + u0 + 4);
+            *reinterpret_cast<float4*>(dc) = *reinterpret_cast<const float4*>(dc_r + u0);
+            *reinterpret_cast<float4*>(dc + 4) = *reinterpret_cast<const float4*>(dc_r + u0 + 4);
+            if (cp_r) {
+              *reinterpret_cast<float4*>(cp) = *reinterpret_cast<const float4*>(cp_r + u0);
+              *reinterpret_cast<float4*>(cp + 4) = *reinterpret_cast<const float4*>(cp_r + u0 + 4);
+            } else {
+#pragma unroll
+              for (int j = 0; j < 8; ++j) cp[j] = 0.f;
+            }
+            float di[8], df[8], dg[8], dO[8], dcp[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float vdh = __uint_as_float(r[hlf * 8 + j]);
+              const float tc = tanhf(cc[j]);
+              dO[j] = vdh * tc * ao[j] * (1.f - ao[j]);
+              const float dct = dc[j] + vdh * ao[j] * (1.f - tc * tc);
+              di[j] = dct * ag[j] * ai[j] * (1.f - ai[j]);
+              df[j] = dct * cp[j] * af[j] * (1.f - af[j]);
+              dg[j] = dct * ai[j] * (1.f - ag[j] * ag[j]);
+              dcp[j] = dct * af[j];
+            }
+            *reinterpret_cast<uint4*>(dg_r + u0) = pack8_bf16(di);
+            *reinterpret_cast<uint4*>(dg_r + C + u0) = pack8_bf16(df);
+            *reinterpret_cast<uint4*>(dg_r + 2 * C + u0) = pack8_bf16(dg);
+            *reinterpret_cast<uint4*>(dg_r + 3 * C + u0) = pack8_bf16(dO);
+            *reinterpret_cast<float4*>(dc_r + u0) = *reinterpret_cast<float4*>(dcp);
+            *reinterpret_cast<float4*>(dc_r + u0 + 4) = *reinterpret_cast<float4*>(dcp + 4);
+          }
+        }
       } else {
         epilogue_tile<BN, TO>(a, t, taddr, stg, cpix, cmask, valid, on, oh, ow, &tempty_bar[acc], lane);
       }
@@ -1744,6 +1809,50 @@ int lstm_seq_tcgen05(const void* x_seq, const void* w_xh_il, const float* b_ih, 
   dim3 grid((unsigned)(a.num_tiles < num_sms() ? a.num_tiles : num_sms()));
   lstm_seq64_kernel<<<grid, TC_THREADS, lseq_smem_bytes(), st>>>(tX, tW, a);
   return post_launch("lstm_seq(tcgen05)");
+}
+
+
+// One LSTM BACKWARD step on the tensor cores with the cell backward in the epilogue (conv_tc_kernel<EPI = 2>):
+//   dh_{t-1} = dG_t W_hh (TMEM)  ->  dG_{t-1}, dc  (lstm_cell_bwd arithmetic on step t-1's saved activations and cell states)
+// dg_next = dG_t [N,H,W,4C] bf16 gate-major; w_hh_d = W_hh packed for dgrad ([C][4C], K-major rows = hidden unit); acts / c_cur /
+// c_prev belong to step t-1 (c_prev == NULL when t-1 == 0); dc is read and rewritten in place; dg_out = dG_{t-1}.
+int lstm_bwd_step_tcgen05(const void* dg_next, const void* w_hh_d, const void* acts, const float* c_prev, const float* c_cur,
+                          float* dc, void* dg_out, int N, int H, int W, int C, cudaStream_t st) {
+  EncodeTiledFn enc = get_tensormap_encoder();
+  if (!enc) { set_error("lstm_bwd_step(tcgen05): cuTensorMapEncodeTiled not available"); return STFB_ECUDA; }
+  if ((long long)N * H * W == 0) return STFB_OK;
+  const int BN = C % 256 == 0 ? 256 : (C % 128 == 0 ? 128 : 64);
+  TcArgs a{};
+  a.y = dg_out; a.acts = const_cast<void*>(acts); a.c_prev = c_prev; a.c_cur = c_cur; a.c_out = dc; a.Chid = C;
+  a.N = N; a.Hout = H; a.Wout = W; a.Cout = C; a.C1 = 4 * C; a.C2 = 0;
+  a.a_scale = 1; a.o_scale = 1; a.nphase_w = 1;
+  a.ntaps[0] = 1; a.dh[0][0] = 0; a.dw[0][0] = 0; a.ktap[0][0] = 0;
+  pick_patch(H, W, a.TW, a.TH, a.TN);
+  a.tiles_w = (W + a.TW - 1) / a.TW;
+  a.tiles_h = (H + a.TH - 1) / a.TH;
+  a.tiles_n = (N + a.TN - 1) / a.TN;
+  a.num_tiles = a.tiles_n * a.tiles_h * a.tiles_w * (C / BN);
+  CUtensorMap tA, tB;
+  if (!encode_nhwc_map_strided(enc, &tA, dg_next, N, H, W, 4 * C, a.TW, a.TH, a.TN, 1, 64)) {
+    set_error("lstm_bwd_step(tcgen05): tensor map (dG) failed"); return STFB_ECUDA;
+  }
+  {
+    cuuint64_t dims[2] = {(cuuint64_t)(4 * C), (cuuint64_t)C};
+    cuuint64_t strides[1] = {(cuuint64_t)(4 * C) * 2};
+    cuuint32_t box[2] = {64, (cuuint32_t)BN};
+    cuuint32_t estr[2] = {1, 1};
+    if (enc(&tB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(w_hh_d), dims, strides, box, estr,
+            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS) {
+      set_error("lstm_bwd_step(tcgen05): tensor map (W) failed"); return STFB_ECUDA;
+    }
+  }
+  dim3 grid((unsigned)(a.num_tiles < num_sms() ? a.num_tiles : num_sms()));
+  switch (BN) {
+    case 256: return launch_tc<256, 4, __nv_bfloat16, 64, 2>(tA, tA, tB, a, grid, st);
+    case 128: return launch_tc<128, 6, __nv_bfloat16, 64, 2>(tA, tA, tB, a, grid, st);
+    default: return launch_tc<64, 8, __nv_bfloat16, 64, 2>(tA, tA, tB, a, grid, st);
+  }
 }
 
 }  // namespace stfb

@@ -835,6 +835,25 @@ int lstm_seq_tcgen05(const void* x_seq, const void* w_xh_il, const float* b_ih, 
                      void* acts_all, int T, int B, int H, int W, int C, int keep, cudaStream_t st);
 }
 
+namespace stfb {
+int lstm_bwd_step_tcgen05(const void* dg_next, const void* w_hh_d, const void* acts, const float* c_prev, const float* c_cur,
+                          float* dc, void* dg_out, int N, int H, int W, int C, cudaStream_t st);
+}
+
+extern "C" int stfb_lstm_bwd_step_fused(const void* dg_next, const void* w_hh_d, const void* acts, const float* c_prev,
+                                        const float* c_cur, float* dc, void* dg_out, int N, int H, int W, int C, void* stream) {
+  STFB_REQUIRE(dg_next && w_hh_d && acts && c_cur && dc && dg_out && N >= 0 && H > 0 && W > 0, "lstm_bwd_step_fused: bad arguments");
+  STFB_REQUIRE(C > 0 && C % 64 == 0, "lstm_bwd_step_fused: hidden size must be a multiple of 64 (got %d)", C);
+  STFB_REQUIRE(dg_next != dg_out, "lstm_bwd_step_fused: dg_out must not alias dg_next (other tiles still read it)");
+  STFB_REQUIRE((long long)N * H * W < 2000000000LL, "lstm_bwd_step_fused: too many rows");
+  auto al = [](const void* q) { return q == nullptr || (reinterpret_cast<uintptr_t>(q) % 16) == 0; };
+  STFB_REQUIRE(al(dg_next) && al(w_hh_d) && al(acts) && al(c_prev) && al(c_cur) && al(dc) && al(dg_out),
+               "lstm_bwd_step_fused: pointers must be 16-byte aligned");
+  STFB_DEVICE_OR_RETURN();
+  return stfb::lstm_bwd_step_tcgen05(dg_next, w_hh_d, acts, c_prev, c_cur, dc, dg_out, N, H, W, C,
+                                     reinterpret_cast<cudaStream_t>(stream));
+}
+
 extern "C" int stfb_lstm_seq_supported(int T, int B, int H, int W, int C) { return stfb::lstm_seq_supported(T, B, H, W, C); }
 
 extern "C" int stfb_lstm_seq_fused(const void* x_seq, const void* w_xh_il, const float* b_ih, const float* b_hh, float* c_all,

@@ -20,6 +20,11 @@ BN_MOMENTUM = 0.1
 import os as _os
 USE_TCGEN05 = _os.environ.get("STFB_NO_TCGEN05", "0") != "1"
 USE_FUSED_LSTM = _os.environ.get("STFB_NO_FUSED_LSTM", "0") != "1"
+# cell backward in the recurrent GEMM's epilogue (stfb_lstm_bwd_step_fused: one launch per backward time step instead of two,
+# dh never in memory).  Correct (tests/test_ops_gpu.py) but MEASURED SLOWER in the step: 9.88 ms against 9.59 -- its epilogue
+# reads the saved state row-per-lane (32 lines per load instruction) where the separate lstm_cell_bwd kernel streams
+# coalesced; it needs the staged segment moves of the forward kernel before it pays.  OFF by default; STFB_FUSED_LSTM_BWD=1.
+USE_FUSED_LSTM_BWD = _os.environ.get("STFB_FUSED_LSTM_BWD", "0") == "1"
 USE_LSTM_SEQ = _os.environ.get("STFB_NO_LSTM_SEQ", "0") != "1"      # all-T kernel for 64-unit levels (csrc/conv_tc.cu lstm_seq64_kernel)
 USE_FUSED_BN_STATS = _os.environ.get("STFB_NO_FUSED_BN_STATS", "0") != "1"
 USE_LSTM_STREAMS = _os.environ.get("STFB_NO_LSTM_STREAMS", "0") != "1"
@@ -27,8 +32,10 @@ USE_WGRAD_STREAM = _os.environ.get("STFB_NO_WGRAD_STREAM", "0") != "1"
 USE_SIDE_FINALIZE = _os.environ.get("STFB_NO_SIDE_FINALIZE", "0") != "1"
 USE_FUSED_STEM = _os.environ.get("STFB_NO_FUSED_STEM", "0") != "1"
 # the training step's weight pack (223 us for 27 M parameters) split in two: the stem's weights at once, the rest on a
-# low-priority side stream beside the stem's memory-bound kernels.  STFB_NO_PACK_OVERLAP=1 disables.
-USE_PACK_OVERLAP = _os.environ.get("STFB_NO_PACK_OVERLAP", "0") != "1"
+# low-priority side stream beside the stem's memory-bound kernels.  MEASURED (round 2): 9.547 ms with it, 9.506 ms without --
+# the pack competes with the stem for HBM and delays layer 1 by as much as it saves (same finding as round 1, now with the
+# mechanism in the tree).  OFF by default; STFB_PACK_OVERLAP=1 enables it.
+USE_PACK_OVERLAP = _os.environ.get("STFB_PACK_OVERLAP", "0") == "1"
 # Two forward chains: the encoder's time steps are independent until the LSTMs (BatchNorm statistics are per time step), so
 # in the training forward every encoder layer is launched as two half-batch launches (time steps [0, T/2) and [T/2, T)) on two
 # streams.  Each chain alternates tensor-bound convolutions with HBM-bound BatchNorm passes; the two chains drift out of
@@ -677,10 +684,18 @@ class Executor:
             tcb = self.use_tc(dG[0], C, 1, 1, 0)
             implb = ops.IMPL_TCGEN05 if tcb else ops.IMPL_SIMT
             whh_d = self.packed(whh, False, n_major=tcb)
-            for t in range(T - 1, -1, -1):
-                ops.lstm_cell_bwd(dh, dc, acts[t], cs[t - 1] if t > 0 else None, cs[t], dG[t], R, C, acts_il=fused)
-                if t > 0:
-                    dh = ops.conv2d(dG[t], whh_d, C, 1, 1, 0, y_dtype=torch.float32, impl=implb)
+            if fused and tcb and USE_FUSED_LSTM_BWD:
+                # t = T-1 takes the upstream gradient; every earlier step is ONE launch: dG_t W_hh in TMEM, the cell backward of
+                # step t-1 in the epilogue (dh never exists in memory)
+                ops.lstm_cell_bwd(dh, dc, acts[T - 1], cs[T - 2] if T > 1 else None, cs[T - 1], dG[T - 1], R, C, acts_il=True)
+                for t in range(T - 1, 0, -1):
+                    ops.lstm_bwd_step_fused(dG[t], whh_d, acts[t - 1].view(B, h, w, 4 * C), cs[t - 2] if t > 1 else None, cs[t - 1], dc,
+                                            dG[t - 1])
+            else:
+                for t in range(T - 1, -1, -1):
+                    ops.lstm_cell_bwd(dh, dc, acts[t], cs[t - 1] if t > 0 else None, cs[t], dG[t], R, C, acts_il=fused)
+                    if t > 0:
+                        dh = ops.conv2d(dG[t], whh_d, C, 1, 1, 0, y_dtype=torch.float32, impl=implb)
             dG_all = dG.view(T * B, h, w, 4 * C)
             if self.wants_grad(wih):
                 self.wgrad(wih, dG_all, seq.data, 1, 1, 0)

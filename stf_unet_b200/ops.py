@@ -15,7 +15,7 @@ from ._lib import BF16, CONV_FWD, CONV_TRANSPOSED, F32, IMPL_AUTO, IMPL_SIMT, IM
 
 __all__ = ["dt_code", "conv2d", "conv2d_wgrad", "pack_weight", "bn_stats", "bn_finalize_train", "bn_fold_eval",
            "bn_apply", "bn_bwd", "colsum", "maxpool_fwd", "maxpool_bwd", "maxpool_fwd_idx", "maxpool_bwd_idx", "bilinear_fwd", "bilinear_bwd",
-           "tcgen05_ok", "conv_stats_fusable", "STAT_SLOTS", "im2col_small", "unpad_wgrad", "lstm_step_fused", "lstm_seq_fused", "lstm_seq_supported", "pack_lstm_xh", "lstm_cell_fwd", "lstm_cell_bwd", "bn_apply_from_stats", "bn_relu_maxpool_from_stats", "bn_bwd_scratch_floats", "pack_series", "pack_series_u8", "adamw_flat_", "pack_series_maps", "repeat_batch", "nhwc_to_nchw", "nchw_to_nhwc", "add_", "cast",
+           "tcgen05_ok", "conv_stats_fusable", "STAT_SLOTS", "im2col_small", "unpad_wgrad", "lstm_step_fused", "lstm_bwd_step_fused", "lstm_seq_fused", "lstm_seq_supported", "pack_lstm_xh", "lstm_cell_fwd", "lstm_cell_bwd", "bn_apply_from_stats", "bn_relu_maxpool_from_stats", "bn_bwd_scratch_floats", "pack_series", "pack_series_u8", "adamw_flat_", "pack_series_maps", "repeat_batch", "nhwc_to_nchw", "nchw_to_nhwc", "add_", "cast",
            "ce_dice_fwd", "ce_dice_bwd", "CONV_FWD", "CONV_TRANSPOSED", "IMPL_AUTO", "IMPL_SIMT", "IMPL_TCGEN05"]
 
 _DT = {torch.float32: F32, torch.bfloat16: BF16}
@@ -586,6 +586,19 @@ def lstm_step_fused(x_t, h_prev, w_xh_il, b_ih, b_hh, c_prev, c_out, h_out, acts
         _prof.end(e0, "lstm_step_tcgen05", 2.0 * rows * kc * 4 * C_,
                   rows * C_ * (2 + 4 + 2 + (2 + 4 if h_prev is not None else 0) + (8 if acts is not None else 0)),
                   f"lstm_step_fused rows{rows} C{C_} K{kc}")
+
+
+def lstm_bwd_step_fused(dg_next, w_hh_d, acts, c_prev, c_cur, dc, dg_out):
+    """dG_{t-1}, dc <- (dG_t W_hh, saved state of step t-1): the recurrent GEMM of the LSTM backward pass with the cell backward
+    in its epilogue.  dg_next / dg_out [N,H,W,4C] bf16 (gate-major), acts [N,H,W,4C] in accumulator column order."""
+    N, H, W, C4 = dg_next.shape
+    C_ = C4 // 4
+    e0 = _prof.begin() if _prof is not None else None
+    check(_lib.load().stfb_lstm_bwd_step_fused(_p(dg_next), _p(w_hh_d), _p(acts), _p(c_prev), _p(c_cur), _p(dc), _p(dg_out), N, H, W,
+                                               C_, _stream()), "lstm_bwd_step_fused")
+    if e0 is not None:
+        rows = N * H * W
+        _prof.end(e0, "lstm_step_tcgen05", 2.0 * rows * C4 * C_, rows * C_ * 40, f"lstm_bwd_step_fused rows{rows} C{C_}")
 
 
 def lstm_seq_supported(T, B, H, W, C_):

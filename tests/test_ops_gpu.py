@@ -734,6 +734,34 @@ def test_lstm_seq_fused_equals_step_by_step_and_oracle(B, T, h, w):
     assert rel(hT.float().permute(0, 3, 1, 2), h_ref) < 1e-2
 
 
+@pytest.mark.parametrize("B,h,w,C", [(4, 16, 16, 64), (2, 32, 32, 128), (3, 8, 8, 256), (2, 8, 8, 512), (1, 20, 20, 64)])
+def test_lstm_bwd_step_fused_equals_two_kernel_route(B, h, w, C):
+    """One backward time step as ONE kernel (dG_t W_hh on the tensor cores, cell backward of step t-1 in the epilogue) against
+    the two-launch route (recurrent GEMM to an fp32 dh, then lstm_cell_bwd): same arithmetic -> identical dG_{t-1} and dc;
+    with and without a previous cell state (autograd of nn.LSTM, src/stf_lstm_unet.py:216-242)."""
+    bf = torch.bfloat16
+    R = B * h * w
+    dg_next = q(rnd(B, h, w, 4 * C, seed=11) * 0.3, bf).to(bf).contiguous()
+    whh = q(rnd(4 * C, C, seed=2, scale=1.0 / C ** 0.5), bf)
+    whh_d = ops.pack_weight(whh.contiguous(), False, bf, n_major=True)          # [C][4C]: dgrad operand of W_hh
+    acts = torch.sigmoid(rnd(R, 4 * C, seed=5)).to(bf).contiguous()            # post-activation gates, interleaved layout
+    cc, cp = rnd(R, C, seed=6), rnd(R, C, seed=7)
+    for with_prev in (True, False):
+        dc_ref = rnd(R, C, seed=8) * 0.2
+        dc_new = dc_ref.clone()
+        dh = ops.conv2d(dg_next, whh_d, C, 1, 1, 0, y_dtype=torch.float32, impl=ops.IMPL_TCGEN05)
+        dg_ref = torch.empty(R, 4 * C, device=DEV, dtype=bf)
+        ops.lstm_cell_bwd(dh.view(R, C), dc_ref, acts, cp if with_prev else None, cc, dg_ref, R, C, acts_il=True)
+        dg_new = torch.zeros(B, h, w, 4 * C, device=DEV, dtype=bf)
+        ops.lstm_bwd_step_fused(dg_next, whh_d, acts.view(B, h, w, 4 * C), cp if with_prev else None, cc, dc_new, dg_new)
+        torch.cuda.synchronize()
+        # same operations in the same order; the compiler may contract a multiply-add differently in the two kernels, which
+        # can flip the last bf16 bit of an element here and there
+        assert rel(dg_new.view(R, 4 * C), dg_ref) < 1e-4
+        assert rel(dc_new, dc_ref) < 1e-6
+        assert (dg_new.view(R, 4 * C) != dg_ref).float().mean().item() < 1e-3
+
+
 def test_lstm_seq_fused_rejects_what_it_cannot_tile():
     assert not ops.lstm_seq_supported(8, 16, 32, 32, 128)      # hidden size 128: weights do not fit shared memory
     assert not ops.lstm_seq_supported(4, 3, 8, 8, 64)          # two 8x8 images per tile, odd batch: a tile would straddle steps
