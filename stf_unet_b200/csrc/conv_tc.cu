@@ -70,7 +70,7 @@ constexpr int TC_THREADS = 192;
 // the residual / previous-cell-state loads).
 constexpr int TC_SEG_BYTES = 32 * 128;
 template <int EPI>
-__host__ __device__ constexpr int tc_stg_segs() { return EPI == 1 ? 5 : 1; }   // LSTM: c x2, h, acts, (bias in the 5th)
+__host__ __device__ constexpr int tc_stg_segs() { return EPI == 1 ? 5 : (EPI == 2 ? 2 : 1); }   // LSTM: c x2, h, acts, (bias in the 5th); LSTM backward: dh x2
 template <int BN, int STAGES, int BK, int EPI = 0>
 constexpr int tc_smem_bytes() {
   return STAGES * (TC_BM * BK * 2 + BN * BK * 2) + 4 * tc_stg_segs<EPI>() * TC_SEG_BYTES + 256 + 1024;
@@ -604,65 +604,64 @@ __global__ void __launch_bounds__(TC_THREADS, MINB) conv_tc_kernel(const __grid_
         // ===== fused LSTM backward step.  The accumulator is dh_{t-1} = dG_t W_hh for hidden units [n0, n0 + BN); the
         // epilogue differentiates the cell of step t-1 right there (the arithmetic of lstm_cell_bwd_kernel, operation for
         // operation) and writes dG_{t-1} (bf16, gate-major [rows][4C]) and the running d(cell): dh never exists in memory
-        // and the step is one launch instead of two.  Row per lane, 8 hidden units at a time: the saved activations of a
-        // 16-unit chunk are one contiguous 128-byte run per row (accumulator column order), c / dc are 32-byte runs.
+        // and the step is one launch instead of two.
+        // Accumulator rows live one per lane, but the saved state is row-major in memory: 64 units of dh at a time go through
+        // the warp's staging segments (two 32-unit halves, fp32) and are then processed in the elementwise kernel's mapping
+        // -- 16 lanes x 4 units per row, two rows per instruction -- so every global access is a 256-byte (c, dc, dh) or
+        // 128-byte (dG) contiguous run.  (The first version read row-per-lane: 32 lines per load instruction, and the step
+        // got SLOWER than the two-launch route.)
         const int C = a.Chid;
-        const long long row = ((long long)on * a.Hout + oh) * a.Wout + ow;
-        const __nv_bfloat16* acts_r = reinterpret_cast<const __nv_bfloat16*>(a.acts) + row * 4 * C;
-        __nv_bfloat16* dg_r = reinterpret_cast<__nv_bfloat16*>(a.y) + row * 4 * C;
-        const float* cc_r = a.c_cur + row * C;
-        const float* cp_r = a.c_prev ? a.c_prev + row * C : nullptr;
-        float* dc_r = a.c_out + row * C;
+        const long long row_l = valid ? ((long long)on * a.Hout + oh) * a.Wout + ow : -1;
+        const uint32_t ridx_s = stg + 2 * TC_SEG_BYTES - 0;                 // (segments: [0] units 0..31, [1] units 32..63)
+        (void)ridx_s;
 #pragma unroll 1
-        for (int c0 = 0; c0 < BN; c0 += 16) {
-          uint32_t r[16];
-          tmem_ld_x16(taddr + c0, r);
-          tmem_ld_wait();
-          if (c0 + 16 >= BN) {
+        for (int c64 = 0; c64 < BN; c64 += 64) {
+#pragma unroll
+          for (int hseg = 0; hseg < 2; ++hseg) {
+            uint32_t r[32];
+            tmem_ld_x32(taddr + c64 + hseg * 32, r);
+            tmem_ld_wait();
+#pragma unroll
+            for (int k = 0; k < 8; ++k)
+              sts128(stg + hseg * TC_SEG_BYTES + stg_off(lane, k), make_uint4(r[4 * k], r[4 * k + 1], r[4 * k + 2], r[4 * k + 3]));
+          }
+          if (c64 + 64 >= BN) {
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&tempty_bar[acc]);
           }
-          if (!valid) continue;
+          __syncwarp();
+          const int u_base = t.n0 + c64;
+#pragma unroll 2
+          for (int it = 0; it < 16; ++it) {
+            const int rl = it * 2 + (lane >> 4);                          // row of this warp's 32
+            const int c = (lane & 15) * 4;                                // 4 units of the 64
+            const long long row = __shfl_sync(0xffffffffu, row_l, rl);
+            if (row < 0) continue;
+            const float4 vdh4 = lds128f(stg + (c >> 5) * TC_SEG_BYTES + stg_off(rl, (c & 31) >> 2));
+            const int u0 = u_base + c;
+            const __nv_bfloat16* ap = reinterpret_cast<const __nv_bfloat16*>(a.acts) + row * 4 * C + (u0 >> 4) * 64 + (u0 & 15);
+            const f4 ai = ld4(ap), af = ld4(ap + 16), ag = ld4(ap + 32), ao = ld4(ap + 48);
+            const f4 cc = ld4(a.c_cur + row * C + u0), vdc = ld4(a.c_out + row * C + u0);
+            f4 cp{{0.f, 0.f, 0.f, 0.f}};
+            if (a.c_prev) cp = ld4(a.c_prev + row * C + u0);
+            const float vdh[4] = {vdh4.x, vdh4.y, vdh4.z, vdh4.w};
+            f4 di, df, dg, dO, dcp;
 #pragma unroll
-          for (int hlf = 0; hlf < 2; ++hlf) {
-            const int u0 = t.n0 + c0 + hlf * 8;                                // first of 8 hidden units
-            const __nv_bfloat16* ap = acts_r + (u0 >> 4) * 64 + (u0 & 15);     // (chunk, gate, unit) order
-            float ai[8], af[8], ag[8], ao[8], cc[8], cp[8], dc[8];
-            unpack8_bf16(*reinterpret_cast<const uint4*>(ap), ai);
-            unpack8_bf16(*reinterpret_cast<const uint4*>(ap + 16), af);
-            unpack8_bf16(*reinterpret_cast<const uint4*>(ap + 32), ag);
-            unpack8_bf16(*reinterpret_cast<const uint4*>(ap + 48), ao);
-            *reinterpret_cast<float4*>(cc) = *reinterpret_cast<const float4*>(cc_r + u0);
-            *reinterpret_cast<float4*>(cc + 4) = *reinterpret_cast<const float4*>(cc_r + u0 + 4);
-            *reinterpret_cast<float4*>(dc) = *reinterpret_cast<const float4*>(dc_r + u0);
-            *reinterpret_cast<float4*>(dc + 4) = *reinterpret_cast<const float4*>(dc_r + u0 + 4);
-            if (cp_r) {
-              *reinterpret_cast<float4*>(cp) = *reinterpret_cast<const float4*>(cp_r + u0);
-              *reinterpret_cast<float4*>(cp + 4) = *reinterpret_cast<const float4*>(cp_r + u0 + 4);
-            } else {
-#pragma unroll
-              for (int j = 0; j < 8; ++j) cp[j] = 0.f;
+            for (int j = 0; j < 4; ++j) {
+              const float tc = tanhf(cc.v[j]);
+              dO.v[j] = vdh[j] * tc * ao.v[j] * (1.f - ao.v[j]);
+              const float dct = vdc.v[j] + vdh[j] * ao.v[j] * (1.f - tc * tc);
+              di.v[j] = dct * ag.v[j] * ai.v[j] * (1.f - ai.v[j]);
+              df.v[j] = dct * cp.v[j] * af.v[j] * (1.f - af.v[j]);
+              dg.v[j] = dct * ai.v[j] * (1.f - ag.v[j] * ag.v[j]);
+              dcp.v[j] = dct * af.v[j];
             }
-            float di[8], df[8], dg[8], dO[8], dcp[8];
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              const float vdh = __uint_as_float(r[hlf * 8 + j]);
-              const float tc = tanhf(cc[j]);
-              dO[j] = vdh * tc * ao[j] * (1.f - ao[j]);
-              const float dct = dc[j] + vdh * ao[j] * (1.f - tc * tc);
-              di[j] = dct * ag[j] * ai[j] * (1.f - ai[j]);
-              df[j] = dct * cp[j] * af[j] * (1.f - af[j]);
-              dg[j] = dct * ai[j] * (1.f - ag[j] * ag[j]);
-              dcp[j] = dct * af[j];
-            }
-            *reinterpret_cast<uint4*>(dg_r + u0) = pack8_bf16(di);
-            *reinterpret_cast<uint4*>(dg_r + C + u0) = pack8_bf16(df);
-            *reinterpret_cast<uint4*>(dg_r + 2 * C + u0) = pack8_bf16(dg);
-            *reinterpret_cast<uint4*>(dg_r + 3 * C + u0) = pack8_bf16(dO);
-            *reinterpret_cast<float4*>(dc_r + u0) = *reinterpret_cast<float4*>(dcp);
-            *reinterpret_cast<float4*>(dc_r + u0 + 4) = *reinterpret_cast<float4*>(dcp + 4);
+            __nv_bfloat16* gp = reinterpret_cast<__nv_bfloat16*>(a.y) + row * 4 * C + u0;
+            st4(gp, di); st4(gp + C, df); st4(gp + 2 * C, dg); st4(gp + 3 * C, dO);
+            st4(a.c_out + row * C + u0, dcp);
           }
+          __syncwarp();
         }
       } else {
         epilogue_tile<BN, TO>(a, t, taddr, stg, cpix, cmask, valid, on, oh, ow, &tempty_bar[acc], lane);
@@ -1847,11 +1846,14 @@ int lstm_bwd_step_tcgen05(const void* dg_next, const void* w_hh_d, const void* a
       set_error("lstm_bwd_step(tcgen05): tensor map (W) failed"); return STFB_ECUDA;
     }
   }
+  // Shallow rings (K = 4C is only 4..32 k-blocks) and, where it fits, two CTAs per SM: the four LSTM levels run their backward
+  // chains concurrently on four streams, and a CTA that takes a whole SM's shared memory serialises them.
   dim3 grid((unsigned)(a.num_tiles < num_sms() ? a.num_tiles : num_sms()));
+  dim3 grid2((unsigned)(a.num_tiles < 2 * num_sms() ? a.num_tiles : 2 * num_sms()));
   switch (BN) {
-    case 256: return launch_tc<256, 4, __nv_bfloat16, 64, 2>(tA, tA, tB, a, grid, st);
-    case 128: return launch_tc<128, 6, __nv_bfloat16, 64, 2>(tA, tA, tB, a, grid, st);
-    default: return launch_tc<64, 8, __nv_bfloat16, 64, 2>(tA, tA, tB, a, grid, st);
+    case 256: return launch_tc<256, 2, __nv_bfloat16, 64, 2>(tA, tA, tB, a, grid, st);        // 2 x 48 KB + 32 KB staging
+    case 128: return launch_tc<128, 2, __nv_bfloat16, 64, 2, 2>(tA, tA, tB, a, grid2, st);    // 2 x 32 KB + 32 KB: two per SM
+    default: return launch_tc<64, 3, __nv_bfloat16, 64, 2, 2>(tA, tA, tB, a, grid2, st);      // 3 x 24 KB + 32 KB: two per SM
   }
 }
 

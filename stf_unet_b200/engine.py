@@ -21,9 +21,12 @@ import os as _os
 USE_TCGEN05 = _os.environ.get("STFB_NO_TCGEN05", "0") != "1"
 USE_FUSED_LSTM = _os.environ.get("STFB_NO_FUSED_LSTM", "0") != "1"
 # cell backward in the recurrent GEMM's epilogue (stfb_lstm_bwd_step_fused: one launch per backward time step instead of two,
-# dh never in memory).  Correct (tests/test_ops_gpu.py) but MEASURED SLOWER in the step: 9.88 ms against 9.59 -- its epilogue
-# reads the saved state row-per-lane (32 lines per load instruction) where the separate lstm_cell_bwd kernel streams
-# coalesced; it needs the staged segment moves of the forward kernel before it pays.  OFF by default; STFB_FUSED_LSTM_BWD=1.
+# dh never in memory).  Correct (tests/test_ops_gpu.py) but MEASURED SLOWER in the step, three times: 9.88 ms against 9.59 with a
+# row-per-lane epilogue, 9.86 against 9.57 with the coalesced one (dh staged through shared memory, the elementwise kernel's
+# 16-lanes-per-row mapping), 9.88 against 9.56 with shallow rings and two CTAs per SM.  The four levels' backward chains run
+# concurrently: the separate lstm_cell_bwd launches are light elementwise grids that fill the SMs between the other levels'
+# GEMMs, while a fused step moves all of that traffic through four epilogue warps per tensor-core CTA.  OFF by default;
+# STFB_FUSED_LSTM_BWD=1 enables it.
 USE_FUSED_LSTM_BWD = _os.environ.get("STFB_FUSED_LSTM_BWD", "0") == "1"
 USE_LSTM_SEQ = _os.environ.get("STFB_NO_LSTM_SEQ", "0") != "1"      # all-T kernel for 64-unit levels (csrc/conv_tc.cu lstm_seq64_kernel)
 USE_FUSED_BN_STATS = _os.environ.get("STFB_NO_FUSED_BN_STATS", "0") != "1"

@@ -1,0 +1,5 @@
+#!/bin/bash
+set -x
+timeout 300 python -m pytest tests/test_ops_gpu.py -x -q -m gpu -k "lstm_bwd" 2>&1 | tail -3
+timeout 200 python tools/step_time.py --iters 20
+STFB_FUSED_LSTM_BWD=1 timeout 200 python tools/step_time.py --iters 20
