@@ -63,8 +63,25 @@ class GraphedStep:
             if cap_stream is None:
                 cap_stream = _CAPTURE_STREAMS[dev_index] = torch.cuda.Stream(device=self.x.device, priority=engine.MAIN_PRIO)
         # thread_local: NCCL's watchdog thread polls events while the collectives of this step are being captured
-        with torch.cuda.graph(self.graph, stream=cap_stream, capture_error_mode="thread_local" if self._in_graph_comm else "global"):
-            self.loss = fwd_bwd()
+        try:
+            with torch.cuda.graph(self.graph, stream=cap_stream, capture_error_mode="thread_local" if self._in_graph_comm else "global"):
+                self.loss = fwd_bwd()
+        except Exception as e:
+            if not self._in_graph_comm:
+                raise
+            # the collectives could not be captured on this system: keep the step graph, run the exchange after each replay
+            import warnings
+            warnings.warn(f"stf_unet_b200: capturing the gradient all-reduce inside the CUDA graph failed ({type(e).__name__}: {e}); "
+                          "falling back to the exchange after the replay")
+            torch.cuda.synchronize()
+            self._in_graph_comm = False
+            self._seg_hook = model.__dict__.pop("_grad_segment_hook", None)
+            for p in model.parameters():
+                p.grad = None
+            self.graph = torch.cuda.CUDAGraph()
+            n0 = _lib.launch_count()
+            with torch.cuda.graph(self.graph, stream=cap_stream):
+                self.loss = fwd_bwd()
         self.launches_per_replay = _lib.launch_count() - n0      # libstfb200 kernels inside the captured graph
         self.flat_grad = model._last_flat_grad
         # replay runs no Python: the .grad views assigned during capture are re-bound after every replay, so a caller that

@@ -35,7 +35,14 @@ def main():
     base = S.STFLSTMUNet(1, 2, T).to(dev)
     sd = {k: v.detach().clone() for k, v in base.state_dict().items()}
     ok = True
-    for tag, dt, tol in (("fp32", None, 2e-5), ("bf16", torch.bfloat16, 5e-3)):
+    # bf16: the BatchNorm statistics fused into the conv epilogues (and the one-launch BatchNorm backward) meet through fp32
+    # red.adds whose order differs from run to run; on these cold random weights train-mode BatchNorm amplifies that noise to
+    # ~20 % of a gradient (measured: the SAME shard computed twice differs by 2.3e-1), which would hide any exchange bug.  The
+    # data-parallel check therefore runs the deterministic routes (what test_graphed_step_matches_eager[False] also pins).
+    from stf_unet_b200 import engine, ops
+    engine.USE_FUSED_BN_STATS = False
+    ops.USE_FUSED_BN_BWD = False
+    for tag, dt, tol in (("fp32", None, 2e-5), ("bf16", torch.bfloat16, 2e-3)):
         def fresh():
             m = S.STFLSTMUNet(1, 2, T).to(dev)
             m.load_state_dict(sd)
