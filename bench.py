@@ -266,10 +266,10 @@ def gpu_eager_baseline(dev, x_dev, t_dev, steps=3, warmup=2, unet=False):
 CONFIG_NOTE = "BASELINE.json configs[2] = global batch 128 on 8 GPUs"
 
 
-def workload_config(n):
+def workload_config(n, exchange=None):
     return {"workload": f"STF-LSTM-UNet train fwd+CE/Dice+bwd+AdamW, T={T_PHASES} x 1x{HW}x{HW}, batch {BATCH_PER_GPU}/GPU "
                         f"({CONFIG_NOTE})",
-            "global_batch": BATCH_PER_GPU * n, "T": T_PHASES, "hw": HW, "parallelism": f"dp{n}", "launch": "CUDA graph (fwd+loss+bwd) + eager all-reduce + one-launch flat AdamW",
+            "global_batch": BATCH_PER_GPU * n, "T": T_PHASES, "hw": HW, "parallelism": f"dp{n}", "launch": "CUDA graph (fwd+loss+bwd" + (exchange or "") + ") + one-launch flat AdamW",
             "l2": "per-step working set (activations of several GB) far exceeds the 126 MB L2; no flush needed"}
 
 
@@ -313,6 +313,11 @@ def run_own(args, rank, world, local_rank):
         return g
 
     graphed = None if args.no_graph else make_graphed(x_dev)
+    exchange = None
+    if world > 1:
+        in_graph = graphed is not None and graphed._in_graph_comm
+        exchange = (" + per-segment NCCL all-reduce captured in the graph, overlapping the backward pass" if in_graph
+                    else ") + (bucketed NCCL all-reduce after the graph")
 
     def step(x, t):
         if graphed is None:
@@ -540,7 +545,7 @@ def run_own(args, rank, world, local_rank):
         line = {"metric": "train slices/s STF-LSTM-UNet", "value": round(value, 2), "unit": "slices/s", "n_gpus": world,
                 "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": round(ms_per_step, 3),
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-                "config": workload_config(world), "clocks": clk.summary(),
+                "config": workload_config(world, exchange), "clocks": clk.summary(),
                 "e2e": {"value": round(e2e_val, 2), "unit": "slices/s", "h2d_bytes_per_step": int(x_pin.numel() * 4 + t_pin.numel() * 8) * world,
                         "d2h_bytes_per_step": 4 * world, "ms_per_step": round(e2e_ms, 3)},
                 "e2e_u8": e2e_u8, "gpu_launches": int(launches),

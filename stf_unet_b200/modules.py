@@ -68,6 +68,7 @@ class B200Module(nn.Module):
     #: None = follow torch autocast (fp32 unless autocast is on); or force torch.float32 / torch.bfloat16
     compute_dtype = None
     _warned_fp16 = False
+    _warned_eval_grad = False
 
     def _select_dtype(self):
         if self.compute_dtype is not None:
@@ -183,5 +184,13 @@ class B200Module(nn.Module):
         if torch.is_grad_enabled() and self.training and trainable:
             logits = engine.ModelFunction.apply(self, x, *trainable)
         else:
+            if torch.is_grad_enabled() and trainable and not self.training and not B200Module._warned_eval_grad:
+                # eval mode folds every BatchNorm into the conv epilogues and records no tape: the result cannot be
+                # differentiated.  The reference's evaluate() runs under torch.no_grad() (train_and_eval.py:322); say so once
+                # instead of handing back a tensor that silently carries no graph.
+                warnings.warn("stf_unet_b200: eval-mode forward with gradients enabled returns a NON-differentiable result "
+                              "(inference path: folded BatchNorm, no tape). Use torch.no_grad() for evaluation or model.train() "
+                              "to differentiate.")
+                B200Module._warned_eval_grad = True
             _, _, logits = self._run(x, record=False)
         return {"out": logits}

@@ -759,3 +759,20 @@ def test_parameter_hooks_are_refused():
     x, _ = W.synthetic_dce_batch(1, 2, 64, 64, seed=3)
     with pytest.raises(RuntimeError, match="hooks"):
         m(x.to(DEV))
+
+
+def test_eval_forward_with_grad_enabled_warns_once():
+    """eval mode is the folded-BatchNorm inference path with no tape: the result carries no graph, and the module says so."""
+    from stf_unet_b200 import modules as M
+    M.B200Module._warned_eval_grad = False
+    m = S.STFLSTMUNet(1, 2, 2).to(DEV).eval()
+    x, _ = W.synthetic_dce_batch(1, 2, 64, 64, seed=3)
+    with pytest.warns(UserWarning, match="NON-differentiable"):
+        out = m(x.to(DEV))
+    assert not out["out"].requires_grad
+    import warnings as _w
+    with _w.catch_warnings():
+        _w.simplefilter("error")
+        m(x.to(DEV))                      # second call: silent
+        with torch.no_grad():
+            m(x.to(DEV))
