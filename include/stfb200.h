@@ -35,6 +35,14 @@ extern "C" {
 
 #define STFB_F32 0
 #define STFB_BF16 1
+/* Split-precision operand ("bf16 x 3"): an fp32 tensor [rows][C] stored as three bf16 planes side by side on the channel
+ * axis, [rows][3C] = [hi | mid | lo] with hi = bf16(x), mid = bf16(x - hi), lo = bf16(x - hi - mid) -- 24 mantissa bits,
+ * written by stfb_split_bf16x3.  The tcgen05 convolution / weight-gradient families take it as x_dtype / dtype (channel
+ * counts in the call stay the LOGICAL ones) and accumulate the six products lo*hi, hi*lo, mid*mid, mid*hi, hi*mid, hi*hi
+ * (smallest first) in one fp32 TMEM accumulator at 1/6 of the bf16 tensor rate, still several times the FFMA rate of the
+ * fp32 SIMT family.  Accuracy: the dropped terms are <= 2^-25 relative; what remains is the rounding of the tensor core's
+ * fp32 accumulator over the hi*hi chain (toward zero, once per K = 16), ~1e-6 relative per layer (tests/test_split_gpu.py). */
+#define STFB_BF16X3 2
 
 /* conv gather modes */
 #define STFB_CONV_FWD 0        /* iy = oy*stride - pad + ky                       (Conv2d forward, ConvTranspose2d dgrad) */
@@ -76,7 +84,8 @@ typedef struct stfb_conv_params {
   int ldw;              /* row stride (elements) of w: >= Cout (SIMT) / >= kh*kw*(C1+C2) (TCGEN05) */
   int mode;             /* STFB_CONV_FWD / STFB_CONV_TRANSPOSED                    */
   int relu;
-  int x_dtype, y_dtype; /* (f32,f32) (bf16,bf16) (bf16,f32)                        */
+  int x_dtype, y_dtype; /* (f32,f32) (bf16,bf16) (bf16,f32) (bf16x3,f32: x / x2 are [N,H,W,3*C1] / [..,3*C2],
+                           w from stfb_pack_weight_split with ldw >= kh*kw*6*(C1+C2); tcgen05 family only) */
   int impl;             /* STFB_IMPL_*                                             */
   /* Fused train-mode BatchNorm statistics of the OUTPUT (tcgen05 family, bf16 y, no epilogue extras): the epilogue adds
    * per-channel sum / sum of squares of the (bf16-rounded) outputs of image group g = n / (N / stat_groups) into
@@ -141,6 +150,15 @@ int stfb_pack_weight_ex(const float* w, void* wp, int D0, int D1, int kh, int kw
                         int gate_c /* > 0: LSTM [4C][C] matrix, row gate*C + u goes to (u/16)*64 + gate*16 + u%16: each 256-row
                                       block holds gates i,f,g,o of the same 64 hidden units (for stfb_lstm_step_fused) */,
                         int dtype, void* stream);
+
+/* Split-precision forms (STFB_BF16X3).
+ * stfb_split_bf16x3: x [rows][C] fp32 -> y [rows][3C] bf16 = [hi | mid | lo]; C % 8 == 0, 16-byte aligned pointers.
+ * stfb_pack_weight_split: the B operand of a STFB_BF16X3 convolution, always n_major: wp [n][kh*kw*6*K] bf16.  Per filter tap
+ *   the K axis holds six segments of all K source channels (x then x2 for a concat convolution),
+ *   [w_hi, w_lo, w_mid, w_hi, w_mid, w_hi] -- the partners of the activation planes [lo, hi, mid, mid, hi, hi] the kernels
+ *   walk.  k_is_dim1 / flip as in stfb_pack_weight_ex. */
+int stfb_split_bf16x3(const float* x, void* y, long long rows, int C, void* stream);
+int stfb_pack_weight_split(const float* w, void* wp, int D0, int D1, int kh, int kw, int k_is_dim1, int flip, void* stream);
 
 /* Batched form: one launch packs every weight of a step.  `jobs_dev` is a DEVICE array (uploaded once per model);
  * job j covers work items [start_j, start_{j+1}) of `total`, one work item = one (d0, d1) position with all its kh*kw

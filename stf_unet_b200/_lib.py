@@ -12,7 +12,7 @@ import os
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libstfb200.so")
 
-F32, BF16 = 0, 1
+F32, BF16, BF16X3 = 0, 1, 2
 CONV_FWD, CONV_TRANSPOSED = 0, 1
 IMPL_AUTO, IMPL_SIMT, IMPL_TCGEN05 = 0, 1, 2
 
@@ -35,6 +35,8 @@ _SIGS = {
     "stfb_conv2d_wgrad_tcgen05_supported": [_vp, _vp] + [_i] * 12,
     "stfb_pack_weight": [_vp, _vp, _i, _i, _i, _i, _i, _i, _vp],
     "stfb_pack_weight_ex": [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp],
+    "stfb_split_bf16x3": [_vp, _vp, _ll, _i, _vp],
+    "stfb_pack_weight_split": [_vp, _vp] + [_i] * 6 + [_vp],
     "stfb_lstm_step_fused": [_vp] * 9 + [_i, _i, _i, _i, _vp],
     "stfb_set_wgrad_scratch": [_vp, C.c_size_t],
     "stfb_wgrad_scatter_batched": [_vp, _i, _ll, _vp, _vp, _vp],

@@ -6,7 +6,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libstfb200.so")
-SOURCES = ["runtime.cu", "igemm_simt.cu", "conv_tc.cu", "wgrad_tc.cu", "elementwise.cu", "loss.cu", "metrics.cu", "pipeline.cu", "tofts.cu", "augment.cu"]
+SOURCES = ["runtime.cu", "igemm_simt.cu", "conv_tc.cu", "wgrad_tc.cu", "elementwise.cu", "loss.cu", "metrics.cu", "pipeline.cu", "tofts.cu", "augment.cu", "split.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
          "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=default", "-cudart", "static"]

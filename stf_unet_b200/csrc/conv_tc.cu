@@ -53,6 +53,7 @@ struct TcArgs {
   float* stat_partial;   // fused BatchNorm statistics: [stat_slots][2][stat_groups][Cout] fp32 (NULL = off)
   int stat_slots, stat_groups, stat_imgs;   // stat_imgs = images per group
   int w_resident;        // halo kernel: the whole weight matrix sits in the B ring (loaded once, never released)
+  int split_c1, split_c2;  // STFB_BF16X3 (0 = off): logical channels of x / x2; C1 / C2 above are then the virtual 6x counts
   int debug;             // STFB_TC_DEBUG: 1 = no MMAs (TMA pipeline only), 2 = no TMA (MMA issue only); timing experiments
   int ntaps[4];
   signed char dh[4][9], dw[4][9], ktap[4][9];
@@ -86,6 +87,24 @@ __device__ __forceinline__ uint64_t make_kmajor_desc(uint32_t saddr) {
 
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+// Channel coordinate of K position c (a multiple of the k-block) in the activation operand: returns true when it lies in the
+// second concat operand (x2), `chan` = its channel there.  STFB_BF16X3: the K axis is six segments of all C1 + C2 logical
+// channels; segment s reads plane {lo, hi, mid, mid, hi, hi}[s] of the three-plane tensors [hi | mid | lo] (csrc/split.cu packs
+// the weight blocks hi, lo, mid, hi, mid, hi against them: correction terms first, the hi*hi chain last).
+__device__ __forceinline__ bool a_coord(const TcArgs& a, int c, int& chan) {
+  if (a.split_c1 == 0) {
+    if (c < a.C1) { chan = c; return false; }
+    chan = c - a.C1;
+    return true;
+  }
+  const int cin = a.split_c1 + a.split_c2;
+  const int seg = c / cin, cr = c - seg * cin;
+  const int pl = (int)((0x001102u >> (4 * seg)) & 0xFu);
+  if (cr < a.split_c1) { chan = pl * a.split_c1 + cr; return false; }
+  chan = pl * a.split_c2 + cr - a.split_c1;
+  return true;
 }
 
 struct TileCoord {
@@ -423,7 +442,9 @@ __global__ void __launch_bounds__(TC_THREADS, MINB) conv_tc_kernel(const __grid_
         const int wbase = t.wb * a.TW * a.a_scale, hbase = t.hb * a.TH * a.a_scale, i0 = t.nb * a.TN;
         for (int kb = 0; kb < t.num_kb; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
-          const int tp = kb / cpt, chunk = kb - tp * cpt;
+          // k-blocks walk taps outermost; split-precision operands channel blocks outermost (the hi*hi segment comes last)
+          const int ntp = t.num_kb / cpt;
+          const int tp = a.split_c1 ? kb % ntp : kb / cpt, chunk = a.split_c1 ? kb / ntp : kb - tp * cpt;
           const int c = chunk * TC_BK;
           uint8_t* sa = smem + stage * STAGE_BYTES;
           uint8_t* sb = sa + TC_A_BYTES;
@@ -434,8 +455,9 @@ __global__ void __launch_bounds__(TC_THREADS, MINB) conv_tc_kernel(const __grid_
           }
           mbar_arrive_expect_tx(&full_bar[stage], STAGE_BYTES);
           const int w0 = wbase + a.dw[t.ph][tp], h0 = hbase + a.dh[t.ph][tp];
-          if (c < a.C1) tma_load_4d(sa, &tmA, &full_bar[stage], c, w0, h0, i0);
-          else tma_load_4d(sa, &tmA2, &full_bar[stage], c - a.C1, w0, h0, i0);
+          int ach;
+          if (!a_coord(a, c, ach)) tma_load_4d(sa, &tmA, &full_bar[stage], ach, w0, h0, i0);
+          else tma_load_4d(sa, &tmA2, &full_bar[stage], ach, w0, h0, i0);
           tma_load_2d(sb, &tmB, &full_bar[stage], (int)a.ktap[t.ph][tp] * Cin + c, t.n0);
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
@@ -775,8 +797,9 @@ __global__ void __launch_bounds__(TC_THREADS, MINB) conv_halo_kernel(const __gri
               mbar_arrive_expect_tx(&afull[sa], HALO_TX_BYTES);
               uint8_t* dst = smem + sa * HALO_BLK_BYTES;
               const int w0 = t.wb * HALO_TW - 1, h0 = t.hb * HALO_TH - 1;
-              if (cc < a.C1) tma_load_4d(dst, &tmA, &afull[sa], cc, w0, h0, t.nb);
-              else tma_load_4d(dst, &tmA2, &afull[sa], cc - a.C1, w0, h0, t.nb);
+              int ach;
+              if (!a_coord(a, cc, ach)) tma_load_4d(dst, &tmA, &afull[sa], ach, w0, h0, t.nb);
+              else tma_load_4d(dst, &tmA2, &afull[sa], ach, w0, h0, t.nb);
             } else {
               mbar_arrive(&afull[sa]);              // odd tail: the second accumulator is computed on stale data, never stored
             }
@@ -990,8 +1013,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(HALO2_THREADS, 1)
           mbar_wait(&aempty[sa], pa ^ 1);
           const uint32_t af = mapa_shared(smem_u32(&afull[sa]), 0);
           if (leader) mbar_arrive_expect_tx(&afull[sa], 2 * HALO_TX_BYTES);
-          if (cc < a.C1) tma_load_4d_pair(sA + sa * HALO_BLK_BYTES, &tmA, af, cc, w0, h0, t.nb);
-          else tma_load_4d_pair(sA + sa * HALO_BLK_BYTES, &tmA2, af, cc - a.C1, w0, h0, t.nb);
+          int ach;
+          if (!a_coord(a, cc, ach)) tma_load_4d_pair(sA + sa * HALO_BLK_BYTES, &tmA, af, ach, w0, h0, t.nb);
+          else tma_load_4d_pair(sA + sa * HALO_BLK_BYTES, &tmA2, af, ach, w0, h0, t.nb);
           if (++sa == SA) { sa = 0; pa ^= 1; }
           if (!first && a.w_resident) continue;        // the whole (half) weight matrix sits in the 9-slot ring since the first tile
 #pragma unroll
@@ -1373,7 +1397,7 @@ static int pick_bn(int Cout) {
 static bool g_tc_strided_fwd = true;   // TMA elementStrides path (stride-2 forward)
 
 int conv2d_tcgen05_supported(const stfb_conv_params* p) {
-  if (p->x_dtype != STFB_BF16) return 0;
+  if (p->x_dtype != STFB_BF16 && !(p->x_dtype == STFB_BF16X3 && p->y_dtype == STFB_F32)) return 0;
   if (p->kh != p->kw || p->kh > 3) return 0;
   if (p->stride != 1 && p->stride != 2) return 0;
   if (p->mode == STFB_CONV_FWD) {
@@ -1517,7 +1541,11 @@ int conv2d_tcgen05(const stfb_conv_params* p, cudaStream_t st) {
     if (dbg < 0) { const char* e = getenv("STFB_TC_DEBUG"); dbg = e ? atoi(e) : 0; }
     a.debug = dbg;
   }
-  a.N = p->N; a.Hout = p->Ho; a.Wout = p->Wo; a.Cout = p->Cout; a.C1 = p->C1; a.C2 = p->C2; a.relu = p->relu;
+  // STFB_BF16X3: three planes per operand in memory, six segments on the K axis
+  const bool split = p->x_dtype == STFB_BF16X3;
+  const int kmul = split ? 6 : 1, pmul = split ? 3 : 1;
+  a.N = p->N; a.Hout = p->Ho; a.Wout = p->Wo; a.Cout = p->Cout; a.C1 = kmul * p->C1; a.C2 = kmul * p->C2; a.relu = p->relu;
+  a.split_c1 = split ? p->C1 : 0; a.split_c2 = split ? p->C2 : 0;
   if (p->stat_partial) {
     if (p->stat_slots <= 0 || !conv2d_stats_fusable(p, p->stat_groups)) {
       set_error("conv2d(tcgen05): fused BatchNorm statistics not available for this launch (stfb_conv2d_stats_fusable)");
@@ -1564,7 +1592,7 @@ int conv2d_tcgen05(const stfb_conv_params* p, cudaStream_t st) {
   a.tiles_h = (Hl + a.TH - 1) / a.TH;
   const int tiles_n = (p->N + a.TN - 1) / a.TN;
   const int BN = pick_bn(p->Cout);
-  const int Ktot = k * k * (p->C1 + p->C2);
+  const int Ktot = k * k * kmul * (p->C1 + p->C2);
   if (p->ldw < Ktot) { set_error("conv2d(tcgen05): ldw %d < kh*kw*Cin %d", p->ldw, Ktot); return STFB_EINVAL; }
 
   CUtensorMap tA, tA2, tB;
@@ -1573,11 +1601,11 @@ int conv2d_tcgen05(const stfb_conv_params* p, cudaStream_t st) {
   if (halo) { a.TW = HALO_TW; a.TH = HALO_TH; a.TN = 1; a.tiles_w = (Wl + a.TW - 1) / a.TW; a.tiles_h = (Hl + a.TH - 1) / a.TH; }
   const int tiles_n_eff = halo ? p->N : tiles_n;
   const int abox_w = halo ? HALO_TW + 2 : a.TW, abox_h = halo ? HALO_TH + 2 : a.TH;
-  if (!encode_nhwc_map_strided(enc, &tA, p->x, p->N, p->H, p->W, p->C1, abox_w, abox_h, a.TN, a.a_scale, BK)) {
+  if (!encode_nhwc_map_strided(enc, &tA, p->x, p->N, p->H, p->W, pmul * p->C1, abox_w, abox_h, a.TN, a.a_scale, BK)) {
     set_error("conv2d(tcgen05): cuTensorMapEncodeTiled failed for x"); return STFB_ECUDA;
   }
   tA2 = tA;
-  if (p->C2 > 0 && !encode_nhwc_map_strided(enc, &tA2, p->x2, p->N, p->H, p->W, p->C2, abox_w, abox_h, a.TN, a.a_scale, BK)) {
+  if (p->C2 > 0 && !encode_nhwc_map_strided(enc, &tA2, p->x2, p->N, p->H, p->W, pmul * p->C2, abox_w, abox_h, a.TN, a.a_scale, BK)) {
     set_error("conv2d(tcgen05): cuTensorMapEncodeTiled failed for x2"); return STFB_ECUDA;
   }
   {
@@ -1597,7 +1625,7 @@ int conv2d_tcgen05(const stfb_conv_params* p, cudaStream_t st) {
   dim3 grid((unsigned)(a.num_tiles < num_sms() ? a.num_tiles : num_sms()));
   const bool f32out = p->y_dtype == STFB_F32;
   if (halo) {
-    const int cpt = (p->C1 + p->C2) / 64;
+    const int cpt = kmul * (p->C1 + p->C2) / 64;
     // canonical tap order tp = (dh + 1) * 3 + (dw + 1): permute the weight k-block table to match
     {
       signed char kt[9];

@@ -670,7 +670,7 @@ int wgrad_tcgen05_supported(int N, int Hp, int Wp, int Cp, int Hg, int Wg, int C
                             int dtype, const void* P, const void* G);
 int wgrad_tcgen05(const void* P, const void* G, const void* G2, float* dW, int N, int H, int W, int Cp, int Hg, int Wg,
                   int C1, int C2, int cg_off, int cg_total, int kh, int kw, int stride, int pad, float* ws, size_t ws_bytes,
-                  cudaStream_t st);
+                  cudaStream_t st, int split = 0);
 size_t wgrad_tcgen05_workspace_bytes(int N, int H, int W, int Cp, int cg_total, int kh, int kw);
 int wgrad_pairs_supported(int N, int Hp, int Wp, int Cp, int Hg, int Wg, int Cg, int cg_off, int cg_total, int kh, int kw,
                           int stride, int pad, int dtype, const void* P, const void* G);
@@ -693,11 +693,14 @@ static int validate_conv(const stfb_conv_params* p) {
                p->Wo, p->Cout);
   STFB_REQUIRE(p->C2 == 0 || p->x2 != nullptr, "conv2d: C2 > 0 needs x2");
   STFB_REQUIRE(p->kh > 0 && p->kw > 0 && p->stride > 0 && p->pad >= 0, "conv2d: bad kernel geometry");
-  if (p->impl == STFB_IMPL_TCGEN05)
-    STFB_REQUIRE(p->ldw >= p->kh * p->kw * (p->C1 + p->C2) && p->ldw % 8 == 0,
-                 "conv2d(tcgen05): weights are [Cout][ldw] K-major, ldw (%d) must be >= kh*kw*Cin and a multiple of 8", p->ldw);
-  else
+  if (p->impl == STFB_IMPL_TCGEN05) {
+    const int kmul = p->x_dtype == STFB_BF16X3 ? 6 : 1;      // split-precision operands walk six K segments per channel
+    STFB_REQUIRE(p->ldw >= p->kh * p->kw * kmul * (p->C1 + p->C2) && p->ldw % 8 == 0,
+                 "conv2d(tcgen05): weights are [Cout][ldw] K-major, ldw (%d) must be >= kh*kw*Cin (x6 for bf16x3) and a multiple of 8", p->ldw);
+  } else {
+    STFB_REQUIRE(p->x_dtype != STFB_BF16X3, "conv2d: bf16x3 operands need the tcgen05 family (impl = STFB_IMPL_TCGEN05)");
     STFB_REQUIRE(p->ldw >= p->Cout, "conv2d: ldw (%d) < Cout (%d)", p->ldw, p->Cout);
+  }
   STFB_REQUIRE(p->mode == STFB_CONV_FWD || p->mode == STFB_CONV_TRANSPOSED, "conv2d: bad mode %d", p->mode);
   STFB_REQUIRE((p->scale == nullptr) == (p->shift == nullptr), "conv2d: scale and shift come together");
   if (p->mode == STFB_CONV_FWD) {
@@ -777,8 +780,17 @@ extern "C" int stfb_conv2d_wgrad(const void* P, const void* G, float* dW, int N,
   STFB_REQUIRE(N >= 0 && Hp > 0 && Wp > 0 && Cp > 0 && Hg > 0 && Wg > 0 && Cg > 0 && kh > 0 && kw > 0 && stride > 0 && pad >= 0,
                "conv2d_wgrad: bad dims");
   STFB_REQUIRE(cg_off >= 0 && cg_off + Cg <= cg_total, "conv2d_wgrad: channel window [%d,%d) outside %d", cg_off, cg_off + Cg, cg_total);
-  STFB_REQUIRE(dtype == STFB_F32 || dtype == STFB_BF16, "conv2d_wgrad: bad dtype");
+  STFB_REQUIRE(dtype == STFB_F32 || dtype == STFB_BF16 || dtype == STFB_BF16X3, "conv2d_wgrad: bad dtype");
+  STFB_REQUIRE(dtype != STFB_BF16X3 || impl != STFB_IMPL_SIMT, "conv2d_wgrad: bf16x3 operands need the tcgen05 family");
   STFB_DEVICE_OR_RETURN();
+  if (dtype == STFB_BF16X3) {
+    if (!stfb::wgrad_tcgen05_supported(N, Hp, Wp, Cp, Hg, Wg, Cg, kh, kw, stride, pad, dtype, P, G)) {
+      set_error("conv2d_wgrad: bf16x3 shape not supported by the tcgen05 family");
+      return STFB_ENOTSUP;
+    }
+    return stfb::wgrad_tcgen05(P, G, nullptr, dW, N, Hp, Wp, Cp, Hg, Wg, Cg, 0, cg_off, cg_total, kh, kw, stride, pad,
+                               reinterpret_cast<float*>(workspace), ws_bytes, reinterpret_cast<cudaStream_t>(stream), 1);
+  }
   if (impl != STFB_IMPL_SIMT) {
     const int ok = stfb::wgrad_tcgen05_supported(N, Hp, Wp, Cp, Hg, Wg, Cg, kh, kw, stride, pad, dtype, P, G);
     if (ok) return stfb::wgrad_tcgen05(P, G, nullptr, dW, N, Hp, Wp, Cp, Hg, Wg, Cg, 0, cg_off, cg_total, kh, kw, stride, pad,

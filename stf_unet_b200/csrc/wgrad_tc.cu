@@ -33,13 +33,21 @@ struct WgTcArgs {
   int m_chunks;             // kh*kw*(C1+C2)/64 column blocks on the M axis
   float* partial;           // halo kernel: per-split partial tiles [split][pair][576][64] fp32 (NULL: red.add into ws)
   int debug;                // STFB_WG_DEBUG: 1 = no MMAs (TMA pipeline only), 2 = no TMA (MMA issue only); timing experiments
+  int split;                // STFB_BF16X3: P / G hold three planes [hi | mid | lo] of Cp / C1 channels; a CTA walks its patch
+                            // range six times, once per plane pair (wg_plane_g / wg_plane_p)
 };
+
+// pass v over the patch range (0..5): gathered-operand plane lo, hi, mid, mid, hi, hi against per-pixel plane hi, lo, mid, hi,
+// mid, hi -- the five correction terms first, the hi*hi chain last (the TMEM accumulator rounds toward zero once per MMA: the
+// fewer roundings happen at full magnitude the better, see csrc/split.cu)
+__device__ __forceinline__ int wg_plane_g(int v) { return (int)((0x001102u >> (4 * v)) & 0xFu); }
+__device__ __forceinline__ int wg_plane_p(int v) { return (int)((0x010120u >> (4 * v)) & 0xFu); }
 
 int wgrad_tcgen05_supported(int N, int Hp, int Wp, int Cp, int Hg, int Wg, int Cg, int kh, int kw, int stride, int pad,
                             int dtype, const void* P, const void* G);
 int wgrad_tcgen05(const void* P, const void* G, const void* G2, float* dW, int N, int H, int W, int Cp, int Hg, int Wg,
                   int C1, int C2, int cg_off, int cg_total, int kh, int kw, int stride, int pad, float* ws, size_t ws_bytes,
-                  cudaStream_t st);
+                  cudaStream_t st, int split = 0);
 
 constexpr int WG_PIX = 64;                       // K per stage
 constexpr int WG_BLK_BYTES = WG_PIX * 128;       // one 64-ch x 64-pixel column block = 8 KB
@@ -96,7 +104,8 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_kernel(const __grid_co
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const int n_iter = p_end - p_beg;
+  const int n_real = p_end - p_beg;
+  const int n_iter = a.split ? 6 * n_real : n_real;
 
   if (warp == 0) {
     if (n_iter > 0 && elect_one()) {
@@ -106,8 +115,10 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_kernel(const __grid_co
       // (its rows are never written out), so every stage moves the same number of bytes
       const int nload = 2 * nacc;
       const uint32_t bytes = (uint32_t)(nload + NB) * WG_BLK_BYTES;
-      for (int p = p_beg; p < p_end; ++p) {
-        int t = p;
+      for (int it = 0; it < n_iter; ++it) {
+        const int v = it / n_real;
+        int t = p_beg + (it - v * n_real);
+        const int gpl = a.split ? wg_plane_g(v) : 0, ppl = a.split ? wg_plane_p(v) * a.Cp : 0;
         const int wb = t % a.tiles_w; t /= a.tiles_w;
         const int hb = t % a.tiles_h;
         const int nb = t / a.tiles_h;
@@ -125,12 +136,12 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_kernel(const __grid_co
           const int tap = chunk / cpt, cc = (chunk - tap * cpt) * 64;
           const int r = tap / a.kw, sx = tap - r * a.kw;
           const int gw = w0 * a.g_scale - a.pad + sx, gh = h0 * a.g_scale - a.pad + r;
-          if (cc < a.C1) tma_load_4d(sa + j * WG_BLK_BYTES, &tmG, &full_bar[stage], cc, gw, gh, i0);
-          else tma_load_4d(sa + j * WG_BLK_BYTES, &tmG2, &full_bar[stage], cc - a.C1, gw, gh, i0);
+          if (cc < a.C1) tma_load_4d(sa + j * WG_BLK_BYTES, &tmG, &full_bar[stage], gpl * a.C1 + cc, gw, gh, i0);
+          else tma_load_4d(sa + j * WG_BLK_BYTES, &tmG2, &full_bar[stage], gpl * a.C2 + cc - a.C1, gw, gh, i0);
         }
 #pragma unroll
         for (int i = 0; i < NB; ++i)
-          tma_load_4d(sa + (2 * NA + i) * WG_BLK_BYTES, &tmP, &full_bar[stage], n0 + i * 64, w0, h0, i0);
+          tma_load_4d(sa + (2 * NA + i) * WG_BLK_BYTES, &tmP, &full_bar[stage], ppl + n0 + i * 64, w0, h0, i0);
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
     }
@@ -237,7 +248,8 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_halo_kernel(const __grid_
   const int n0 = blockIdx.y * 64;                 // output-channel block
   const int p_beg = blockIdx.z * a.patches_per_split;
   const int p_end = min(a.n_patches, p_beg + a.patches_per_split);
-  const int n_iter = p_end - p_beg;
+  const int n_real = p_end - p_beg;
+  const int n_iter = a.split ? 6 * n_real : n_real;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < WH_STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
@@ -261,8 +273,10 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_halo_kernel(const __grid_
       int stage = 0;
       uint32_t phase = 0;
       const int cc = cblk * 64;
-      for (int p = p_beg; p < p_end; ++p) {
-        int t = p;
+      for (int it = 0; it < n_iter; ++it) {
+        const int v = it / n_real;
+        int t = p_beg + (it - v * n_real);
+        const int gpl = a.split ? wg_plane_g(v) : 0, ppl = a.split ? wg_plane_p(v) * a.Cp : 0;
         const int wb = t % a.tiles_w; t /= a.tiles_w;
         const int hb = t % a.tiles_h;
         const int nb = t / a.tiles_h;
@@ -270,9 +284,9 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_halo_kernel(const __grid_
         mbar_wait(&empty_bar[stage], phase ^ 1);
         uint8_t* sx = smem + stage * WH_STAGE_BYTES;
         mbar_arrive_expect_tx(&full_bar[stage], WH_X_TX + WG_BLK_BYTES);
-        if (cc < a.C1) tma_load_4d(sx, &tmG, &full_bar[stage], cc, w0 - 1, h0 - 1, nb);
-        else tma_load_4d(sx, &tmG2, &full_bar[stage], cc - a.C1, w0 - 1, h0 - 1, nb);
-        tma_load_4d(sx + WH_X_BYTES, &tmP, &full_bar[stage], n0, w0, h0, nb);
+        if (cc < a.C1) tma_load_4d(sx, &tmG, &full_bar[stage], gpl * a.C1 + cc, w0 - 1, h0 - 1, nb);
+        else tma_load_4d(sx, &tmG2, &full_bar[stage], gpl * a.C2 + cc - a.C1, w0 - 1, h0 - 1, nb);
+        tma_load_4d(sx + WH_X_BYTES, &tmP, &full_bar[stage], ppl + n0, w0, h0, nb);
         if (++stage == WH_STAGES) { stage = 0; phase ^= 1; }
       }
     }
@@ -517,7 +531,7 @@ static int wg_pick_bn(int Cp) {
 
 int wgrad_tcgen05_supported(int N, int Hp, int Wp, int Cp, int Hg, int Wg, int Cg, int kh, int kw, int stride, int pad,
                             int dtype, const void* P, const void* G) {
-  if (dtype != STFB_BF16 || kh != kw || kh > 3) return 0;
+  if ((dtype != STFB_BF16 && dtype != STFB_BF16X3) || kh != kw || kh > 3) return 0;
   if (stride == 1) {
     if (2 * pad != kh - 1 || Hp != Hg || Wp != Wg) return 0;
   } else if (stride == 2) {
@@ -636,7 +650,7 @@ int wgrad_scatter_batched(const stfb_scatter_job* jobs_dev, int njobs, long long
 
 int wgrad_tcgen05(const void* P, const void* G, const void* G2, float* dW, int N, int H, int W, int Cp, int Hg, int Wg,
                   int C1, int C2, int cg_off, int cg_total, int kh, int kw, int stride, int pad, float* ws, size_t ws_bytes,
-                  cudaStream_t st) {
+                  cudaStream_t st, int split) {
   EncodeTiledFn enc = get_tensormap_encoder();
   if (!enc) { set_error("conv2d_wgrad(tcgen05): cuTensorMapEncodeTiled not available"); return STFB_ECUDA; }
   if ((long long)N * H * W == 0) return STFB_OK;
@@ -649,6 +663,8 @@ int wgrad_tcgen05(const void* P, const void* G, const void* G2, float* dW, int N
   WgTcArgs a{};
   a.ws = ws; a.N = N; a.H = H; a.W = W; a.Cp = Cp; a.C1 = C1; a.C2 = C2; a.cg_off = cg_off; a.cg_total = cg_total;
   a.kh = kh; a.kw = kw; a.pad = pad; a.g_scale = stride;
+  a.split = split ? 1 : 0;
+  const int pmul = split ? 3 : 1;       // bf16x3: three planes per tensor (the kernels walk their patch range six times)
   {
     static int dbg = -1;
     if (dbg < 0) { const char* e = getenv("STFB_WG_DEBUG"); dbg = e ? atoi(e) : 0; }
@@ -672,10 +688,10 @@ int wgrad_tcgen05(const void* P, const void* G, const void* G2, float* dW, int N
       a.patches_per_split = (int)((a.n_patches + splits - 1) / splits);
       splits = (a.n_patches + a.patches_per_split - 1) / a.patches_per_split;
       CUtensorMap tG, tG2, tP;
-      if (!encode_nhwc_map(enc, &tG, G, N, Hg, Wg, C1, WH_PATCH + 2, WH_PATCH + 2, 1)) { set_error("conv2d_wgrad(halo): tensor map (G) failed"); return STFB_ECUDA; }
+      if (!encode_nhwc_map(enc, &tG, G, N, Hg, Wg, pmul * C1, WH_PATCH + 2, WH_PATCH + 2, 1)) { set_error("conv2d_wgrad(halo): tensor map (G) failed"); return STFB_ECUDA; }
       tG2 = tG;
-      if (C2 > 0 && !encode_nhwc_map(enc, &tG2, G2, N, Hg, Wg, C2, WH_PATCH + 2, WH_PATCH + 2, 1)) { set_error("conv2d_wgrad(halo): tensor map (G2) failed"); return STFB_ECUDA; }
-      if (!encode_nhwc_map(enc, &tP, P, N, H, W, Cp, WH_PATCH, WH_PATCH, 1)) { set_error("conv2d_wgrad(halo): tensor map (P) failed"); return STFB_ECUDA; }
+      if (C2 > 0 && !encode_nhwc_map(enc, &tG2, G2, N, Hg, Wg, pmul * C2, WH_PATCH + 2, WH_PATCH + 2, 1)) { set_error("conv2d_wgrad(halo): tensor map (G2) failed"); return STFB_ECUDA; }
+      if (!encode_nhwc_map(enc, &tP, P, N, H, W, pmul * Cp, WH_PATCH, WH_PATCH, 1)) { set_error("conv2d_wgrad(halo): tensor map (P) failed"); return STFB_ECUDA; }
       static bool configured = false;
       if (!configured) {
         if (cudaFuncSetAttribute(wgrad_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, wh_smem_bytes()) != cudaSuccess) {
@@ -711,14 +727,15 @@ int wgrad_tcgen05(const void* P, const void* G, const void* G2, float* dW, int N
   }
   a.TW = pl.TW; a.TH = pl.TH; a.TN = pl.TN; a.tiles_w = pl.tiles_w; a.tiles_h = pl.tiles_h; a.n_patches = pl.n_patches;
   a.m_chunks = pl.m_chunks; a.patches_per_split = pl.pps;
+
   const int BN = pl.BN, m_tiles = pl.m_tiles, n_tiles = pl.n_tiles;
   const long long splits = pl.splits;
 
   CUtensorMap tG, tG2, tP;
-  if (!encode_nhwc_map_strided(enc, &tG, G, N, Hg, Wg, C1, a.TW, a.TH, a.TN, stride, 64)) { set_error("conv2d_wgrad(tcgen05): tensor map (G) failed"); return STFB_ECUDA; }
+  if (!encode_nhwc_map_strided(enc, &tG, G, N, Hg, Wg, pmul * C1, a.TW, a.TH, a.TN, stride, 64)) { set_error("conv2d_wgrad(tcgen05): tensor map (G) failed"); return STFB_ECUDA; }
   tG2 = tG;
-  if (C2 > 0 && !encode_nhwc_map_strided(enc, &tG2, G2, N, Hg, Wg, C2, a.TW, a.TH, a.TN, stride, 64)) { set_error("conv2d_wgrad(tcgen05): tensor map (G2) failed"); return STFB_ECUDA; }
-  if (!encode_nhwc_map(enc, &tP, P, N, H, W, Cp, a.TW, a.TH, a.TN)) { set_error("conv2d_wgrad(tcgen05): tensor map (P) failed"); return STFB_ECUDA; }
+  if (C2 > 0 && !encode_nhwc_map_strided(enc, &tG2, G2, N, Hg, Wg, pmul * C2, a.TW, a.TH, a.TN, stride, 64)) { set_error("conv2d_wgrad(tcgen05): tensor map (G2) failed"); return STFB_ECUDA; }
+  if (!encode_nhwc_map(enc, &tP, P, N, H, W, pmul * Cp, a.TW, a.TH, a.TN)) { set_error("conv2d_wgrad(tcgen05): tensor map (P) failed"); return STFB_ECUDA; }
   dim3 grid((unsigned)m_tiles, (unsigned)n_tiles, (unsigned)splits);
   if (dW != nullptr) cudaMemsetAsync(ws, 0, need, st);   // immediate mode owns the buffer; deferred mode: the caller zeroed it
   int rc = STFB_ENOTSUP;

@@ -19,6 +19,9 @@ BN_MOMENTUM = 0.1
 #: kill switch for A/B measurements (STFB_NO_TCGEN05=1 keeps every conv on the SIMT family)
 import os as _os
 USE_TCGEN05 = _os.environ.get("STFB_NO_TCGEN05", "0") != "1"
+# fp32 mode: convolutions and weight gradients the tcgen05 family has a shape for run there on split-precision operands
+# (STFB_BF16X3, csrc/split.cu: three bf16 planes per fp32 tensor, six products per MAC, fp32-accurate) instead of the FFMA family
+USE_SPLIT_FP32 = _os.environ.get("STFB_NO_SPLIT_FP32", "0") != "1"
 USE_FUSED_LSTM = _os.environ.get("STFB_NO_FUSED_LSTM", "0") != "1"
 # cell backward in the recurrent GEMM's epilogue (stfb_lstm_bwd_step_fused: one launch per backward time step instead of two,
 # dh never in memory).  Correct (tests/test_ops_gpu.py) but MEASURED SLOWER in the step, three times: 9.88 ms against 9.59 with a
@@ -59,10 +62,11 @@ WGRAD_STREAMS = int(_os.environ.get("STFB_WGRAD_STREAMS", "3" if MAIN_PRIO else 
 
 class Var:
     """An NHWC activation plus (during backward) its gradient."""
-    __slots__ = ("data", "grad", "needs_grad", "grad_dtype", "bn_partial")
+    __slots__ = ("data", "grad", "needs_grad", "grad_dtype", "bn_partial", "split")
 
     def __init__(self, data, needs_grad=True, grad_dtype=None):
         self.bn_partial = None     # fused BatchNorm partial sums produced by the conv that wrote `data`
+        self.split = None          # split-precision copy of `data` (ops.split_bf16x3), made by the first conv that reads it
         self.data = data
         self.grad = None
         self.needs_grad = needs_grad
@@ -194,6 +198,31 @@ class Executor:
             Executor._tc_cache[key] = r
         return r
 
+    def use_split(self, x, Cout, k, stride, pad, x2=None, mode=ops.CONV_FWD, out_hw=None):
+        """fp32 mode: does this convolution run on the tensor cores with split-precision operands?"""
+        if self.dtype != torch.float32 or not (USE_SPLIT_FP32 and USE_TCGEN05) or not x.is_cuda:
+            return False
+        key = ("x3", tuple(x.shape), Cout, k, stride, pad, None if x2 is None else x2.shape[3], mode, out_hw)
+        r = Executor._tc_cache.get(key)
+        if r is None:
+            r = ops.tcgen05_ok(x, Cout, k, stride, pad, mode=mode, x2=x2, out_hw=out_hw, as_split=True)
+            Executor._tc_cache[key] = r
+        return r
+
+    def split_of(self, v: Var):
+        if v.split is None:
+            v.split = ops.split_bf16x3(v.data)
+        return v.split
+
+    def packed_split(self, name, k_is_dim1):
+        key = ("x3", name, bool(k_is_dim1))
+        self._join_late_packs(name)
+        wp = self._packed.get(key)
+        if wp is None:
+            wp = self._packed[key] = ops.pack_weight_split(self.params[name], k_is_dim1)
+            self._split_wait_current()
+        return wp
+
     _sf_cache = {}
 
     def stats_fusable(self, x, Cout, k, stride, pad, G, x2=None):
@@ -264,7 +293,7 @@ class Executor:
                 return fn()
         return fn()
 
-    def wgrad(self, wname, P, G, k, stride, pad, cg_off=0, cg_total=None):
+    def wgrad(self, wname, P, G, k, stride, pad, cg_off=0, cg_total=None, split=False):
         """Weight gradient of `wname`; tcgen05 launches accumulate in the side buffer and are folded in once, at the
         end of the backward pass (Executor.backward).
 
@@ -274,7 +303,7 @@ class Executor:
         alternating with them.  P and G are kept alive until the join at the end of the backward pass."""
         acc = self.acc.get(wname)
         deferred = self.side_launch((P, G), lambda: ops.conv2d_wgrad(P, G, self.grads[wname], k, stride, pad, cg_off, cg_total,
-                                                                     acc=acc))
+                                                                     acc=acc, split=split))
         if deferred:
             w = self.params[wname]
             khw = 1 if w.dim() == 2 else w.shape[2] * w.shape[3]
@@ -320,6 +349,9 @@ class Executor:
         out_hw = ops.conv_out_hw(H, W, k, stride, pad, transposed, out_pad)
         x2d = None if x2 is None else x2.data
         tc = self.use_tc(x.data, Cout, k, stride, pad, x2d, mode, out_hw)
+        x3 = (not tc) and self.use_split(x.data, Cout, k, stride, pad, x2d, mode, out_hw)
+        if x3:
+            return self._conv_split(x, wname, k, stride, pad, transposed, out_hw, bname, x2, scale, shift, residual, relu)
         wp = self.packed(wname, k_is_dim1=not transposed, n_major=tc)
         bias = self.params[bname] if bname else None
         partial = None
@@ -376,6 +408,65 @@ class Executor:
                                out=src.grad, y_dtype=src.grad_dtype, ldw=wpd.shape[1] if tcd else C1 + C2,
                                w_offset=off * wpd.shape[1] if tcd else off,
                                impl=ops.IMPL_TCGEN05 if tcd else ops.IMPL_SIMT)
+                src.grad = g
+
+        self.tape.append(bwd)
+        return out
+
+    def _conv_split(self, x, wname, k, stride, pad, transposed, out_hw, bname, x2, scale, shift, residual, relu):
+        """fp32 mode on the tensor cores: forward, dgrad and wgrad of one convolution over split-precision operands
+        (include/stfb200.h STFB_BF16X3).  Every fp32 tensor that feeds a GEMM is split once (the activation by its first
+        consumer, the output gradient here) and the three-plane copy serves every GEMM that reads it."""
+        w = self.params[wname]
+        Cout = w.shape[1] if transposed else w.shape[0]
+        N, H, W, C1 = x.data.shape
+        C2 = 0 if x2 is None else x2.data.shape[3]
+        mode = ops.CONV_TRANSPOSED if transposed else ops.CONV_FWD
+        xs = self.split_of(x)
+        x2s = None if x2 is None else self.split_of(x2)
+        wp = self.packed_split(wname, k_is_dim1=not transposed)
+        bias = self.params[bname] if bname else None
+        y = ops.conv2d(xs, wp, Cout, k, stride, pad, mode=mode, out_hw=out_hw, x2=x2s, bias=bias, scale=scale, shift=shift,
+                       residual=residual, relu=relu, impl=ops.IMPL_TCGEN05, split=True)
+        out = Var(y, grad_dtype=self.dtype)
+        if not self.record:
+            return out
+        assert scale is None and residual is None and not relu, "fused epilogue is inference-only"
+        lib_ok = ops.wgrad_tcgen05_ok
+
+        def bwd():
+            dy = out.grad
+            out.grad = None
+            if dy is None:
+                return
+            rows = dy.shape[0] * dy.shape[1] * dy.shape[2]
+            if bname and self.wants_grad(bname):
+                ops.colsum(dy, self.grads[bname], rows, Cout)
+            dys = ops.split_bf16x3(dy)
+            if self.wants_grad(wname):
+                if not transposed:
+                    for src, srcs, off in ((x, xs, 0),) + (((x2, x2s, C1),) if x2 is not None else ()):
+                        if lib_ok(dys, srcs, k, stride, pad, split=True):
+                            self.wgrad(wname, dys, srcs, k, stride, pad, off, C1 + C2, split=True)
+                        else:
+                            self.wgrad(wname, dy, src.data, k, stride, pad, off, C1 + C2)
+                elif lib_ok(xs, dys, k, stride, pad, split=True):
+                    self.wgrad(wname, xs, dys, k, stride, pad, 0, Cout, split=True)
+                else:
+                    self.wgrad(wname, x.data, dy, k, stride, pad, 0, Cout)
+            for src, off, csrc in [(x, 0, C1)] + ([(x2, C1, C2)] if x2 is not None else []):
+                if not src.needs_grad:
+                    continue
+                mode_d = ops.CONV_FWD if transposed else ops.CONV_TRANSPOSED
+                if self.use_split(dy, csrc, k, stride, pad, None, mode_d, (H, W)):
+                    # [n = source channel][K = taps x 6 x Cout]: a source window is a row offset
+                    wpd = self.packed_split(wname, k_is_dim1=transposed)
+                    g = ops.conv2d(dys, wpd, csrc, k, stride, pad, mode=mode_d, out_hw=(H, W), residual=src.grad, out=src.grad,
+                                   w_offset=off * wpd.shape[1], impl=ops.IMPL_TCGEN05, split=True)
+                else:
+                    wpd = self.packed(wname, k_is_dim1=transposed, n_major=False)
+                    g = ops.conv2d(dy, wpd, csrc, k, stride, pad, mode=mode_d, out_hw=(H, W), residual=src.grad, out=src.grad,
+                                   y_dtype=src.grad_dtype, ldw=C1 + C2, w_offset=off, impl=ops.IMPL_SIMT)
                 src.grad = g
 
         self.tape.append(bwd)

@@ -110,7 +110,7 @@ class B200Module(nn.Module):
         if record:
             # data parallelism with overlapped exchange: a per-range hook (parallel.DataParallel installs it)
             ex.segment_hook = self.__dict__.get("_grad_segment_hook")
-        if record and flat is not None and ex.dtype == torch.bfloat16:
+        if record and flat is not None and (ex.dtype == torch.bfloat16 or (engine.USE_SPLIT_FP32 and engine.USE_TCGEN05)):
             # side buffer (same offsets as the flat gradient) the tcgen05 weight-gradient kernels accumulate into
             ex.acc_flat = torch.zeros_like(flat)
             ex.acc = {n: ex.acc_flat[o:o + self._numel(n)] for n, o in offsets.items() if self._is_matrix(n)}

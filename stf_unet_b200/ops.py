@@ -11,12 +11,12 @@ import os
 import torch
 
 from . import _lib
-from ._lib import BF16, CONV_FWD, CONV_TRANSPOSED, F32, IMPL_AUTO, IMPL_SIMT, IMPL_TCGEN05, ConvParams, check
+from ._lib import BF16, BF16X3, CONV_FWD, CONV_TRANSPOSED, F32, IMPL_AUTO, IMPL_SIMT, IMPL_TCGEN05, ConvParams, check
 
 __all__ = ["dt_code", "conv2d", "conv2d_wgrad", "pack_weight", "bn_stats", "bn_finalize_train", "bn_fold_eval",
            "bn_apply", "bn_bwd", "colsum", "maxpool_fwd", "maxpool_bwd", "maxpool_fwd_idx", "maxpool_bwd_idx", "bilinear_fwd", "bilinear_bwd",
            "tcgen05_ok", "conv_stats_fusable", "STAT_SLOTS", "im2col_small", "unpad_wgrad", "lstm_step_fused", "lstm_bwd_step_fused", "lstm_seq_fused", "lstm_seq_supported", "pack_lstm_xh", "lstm_cell_fwd", "lstm_cell_bwd", "bn_apply_from_stats", "bn_relu_maxpool_from_stats", "bn_bwd_scratch_floats", "pack_series", "pack_series_u8", "adamw_flat_", "pack_series_maps", "repeat_batch", "nhwc_to_nchw", "nchw_to_nhwc", "add_", "cast",
-           "ce_dice_fwd", "ce_dice_bwd", "CONV_FWD", "CONV_TRANSPOSED", "IMPL_AUTO", "IMPL_SIMT", "IMPL_TCGEN05"]
+           "ce_dice_fwd", "ce_dice_bwd", "split_bf16x3", "pack_weight_split", "CONV_FWD", "CONV_TRANSPOSED", "IMPL_AUTO", "IMPL_SIMT", "IMPL_TCGEN05"]
 
 _DT = {torch.float32: F32, torch.bfloat16: BF16}
 
@@ -124,11 +124,18 @@ STAT_SLOTS = 8   # partial-sum slots of the fused BatchNorm statistics (CTA % sl
 
 def conv2d(x, wp, Cout, k, stride, pad, *, mode=CONV_FWD, out_hw=None, x2=None, bias=None, bias2=None, scale=None,
            shift=None, residual=None, relu=False, y_dtype=None, ldw=None, out=None, w_offset=0, impl=IMPL_AUTO,
-           stat_partial=None, stat_groups=0):
-    """Implicit-GEMM convolution with fused epilogue; see stfb_conv2d in include/stfb200.h."""
+           stat_partial=None, stat_groups=0, split=False):
+    """Implicit-GEMM convolution with fused epilogue; see stfb_conv2d in include/stfb200.h.
+
+    split: x / x2 are split-precision operands (split_bf16x3: bf16 [N, H, W, 3C]), wp comes from pack_weight_split and the
+    result is fp32 (STFB_BF16X3: fp32-accurate convolution on the tensor cores)."""
     _need_cuda(x, wp)
     N, H, W, C1 = x.shape
     C2 = 0 if x2 is None else x2.shape[3]
+    if split:
+        assert x.dtype == torch.bfloat16 and C1 % 3 == 0 and C2 % 3 == 0 and impl == IMPL_TCGEN05
+        C1, C2 = C1 // 3, C2 // 3
+        y_dtype = torch.float32
     kh, kw = (k, k) if isinstance(k, int) else k
     if out_hw is None:
         out_hw = conv_out_hw(H, W, kh, stride, pad, transposed=(mode == CONV_TRANSPOSED))
@@ -141,7 +148,7 @@ def conv2d(x, wp, Cout, k, stride, pad, *, mode=CONV_FWD, out_hw=None, x2=None, 
     p = ConvParams(x=_p(x), x2=_p(x2), w=wp.data_ptr() + w_offset * esz, y=_p(y), bias=_p(bias), bias2=_p(bias2),
                    scale=_p(scale), shift=_p(shift), residual=_p(residual), N=N, H=H, W=W, C1=C1, C2=C2, Ho=Ho, Wo=Wo,
                    Cout=Cout, kh=kh, kw=kw, stride=stride, pad=pad, ldw=ldw if ldw is not None else Cout, mode=mode,
-                   relu=int(bool(relu)), x_dtype=dt_code(x.dtype), y_dtype=dt_code(y.dtype), impl=impl,
+                   relu=int(bool(relu)), x_dtype=BF16X3 if split else dt_code(x.dtype), y_dtype=dt_code(y.dtype), impl=impl,
                    stat_partial=_p(stat_partial), stat_slots=0 if stat_partial is None else stat_partial.shape[0],
                    stat_groups=stat_groups)
     if _prof is None:
@@ -160,6 +167,8 @@ def conv2d(x, wp, Cout, k, stride, pad, *, mode=CONV_FWD, out_hw=None, x2=None, 
     halo = tc and kh == 3 and kw == 3 and stride == 1 and C1 % 64 == 0 and C2 % 64 == 0 and Cout % 64 == 0 and Ho >= 12 and Wo >= 8 \
         and Ho == H and Wo == W
     fam = ("conv3x3_halo_tcgen05" if halo else "conv_other_tcgen05") if tc else "conv_simt_" + ("bf16" if esz == 2 else "f32")
+    if split:
+        fam += "_bf16x3"
     _prof.end(e0, fam, flops, nbytes, f"x{tuple(x.shape)}+{C2} ->{Cout} k{kh} s{stride} m{mode}")
     return y
 
@@ -182,7 +191,7 @@ def _ensure_wgrad_scratch(device):
         _wg_scratch[key] = buf
 
 
-def conv2d_wgrad(P, G, dW, k, stride, pad, cg_off=0, cg_total=None, impl=IMPL_AUTO, acc=None):
+def conv2d_wgrad(P, G, dW, k, stride, pad, cg_off=0, cg_total=None, impl=IMPL_AUTO, acc=None, split=False):
     """dW[cp][cg_off+cg][ky][kx] += sum_pix P[pix,cp] * G[gather(pix),cg]; dW fp32, reference layout.
 
     acc: optional pre-zeroed fp32 accumulation buffer of the whole weight, [(ky,kx,cg_total), Cp].  When given and the
@@ -192,10 +201,13 @@ def conv2d_wgrad(P, G, dW, k, stride, pad, cg_off=0, cg_total=None, impl=IMPL_AU
     _ensure_wgrad_scratch(P.device)
     N, Hp, Wp, Cp = P.shape
     _, Hg, Wg, Cg = G.shape
+    if split:        # split-precision operands (split_bf16x3): three bf16 planes per tensor, fp32-accurate result
+        assert P.dtype == torch.bfloat16 and G.dtype == torch.bfloat16 and Cp % 3 == 0 and Cg % 3 == 0
+        Cp, Cg = Cp // 3, Cg // 3
     kh, kw = (k, k) if isinstance(k, int) else k
     cgt = cg_total if cg_total is not None else Cg
     lib = _lib.load()
-    dt = dt_code(P.dtype)
+    dt = BF16X3 if split else dt_code(P.dtype)
     tc = impl != IMPL_SIMT and lib.stfb_conv2d_wgrad_tcgen05_supported(_p(P), _p(G), N, Hp, Wp, Cp, Hg, Wg, Cg, kh, kw, stride,
                                                                        pad, dt) == 1
     deferred = tc and acc is not None
@@ -213,7 +225,7 @@ def conv2d_wgrad(P, G, dW, k, stride, pad, cg_off=0, cg_total=None, impl=IMPL_AU
         check(lib.stfb_conv2d_wgrad(_p(P), _p(G), _p(dW), N, Hp, Wp, Cp, Hg, Wg, Cg, cg_off, cgt, kh, kw, stride, pad, dt,
                                     impl, _p(ws), ws_bytes, _stream()), "conv2d_wgrad")
     if e0 is not None:
-        fam = "wgrad_tcgen05" if tc else "wgrad_simt_" + ("bf16" if P.element_size() == 2 else "f32")
+        fam = ("wgrad_tcgen05_bf16x3" if split else "wgrad_tcgen05") if tc else "wgrad_simt_" + ("bf16" if P.element_size() == 2 else "f32")
         _prof.end(e0, fam, 2.0 * N * Hp * Wp * Cp * Cg * kh * kw, (P.numel() + G.numel()) * P.element_size(),
                   f"P{tuple(P.shape)} G{tuple(G.shape)} k{kh} s{stride}")
     return deferred
@@ -385,14 +397,60 @@ def unpad_wgrad(dW, src):
     check(_lib.load().stfb_unpad_wgrad(_p(dW), _p(src), Cout, Cin, kh, kw, src.shape[1], _stream()), "unpad_wgrad")
 
 
-def tcgen05_ok(x, Cout, k, stride, pad, mode=CONV_FWD, x2=None, out_hw=None, y_dtype=None):
-    """Shape/dtype check: can the tcgen05 family run this convolution?"""
+def tcgen05_ok(x, Cout, k, stride, pad, mode=CONV_FWD, x2=None, out_hw=None, y_dtype=None, as_split=False):
+    """Shape/dtype check: can the tcgen05 family run this convolution?  as_split: x / x2 are the fp32 tensors whose
+    split-precision form (split_bf16x3) would be the operand."""
     N, H, W, C1 = x.shape
     C2 = 0 if x2 is None else x2.shape[3]
     Ho, Wo = out_hw if out_hw is not None else conv_out_hw(H, W, k, stride, pad, transposed=(mode == CONV_TRANSPOSED))
-    p = ConvParams(x=_p(x), x2=_p(x2), N=N, H=H, W=W, C1=C1, C2=C2, Ho=Ho, Wo=Wo, Cout=Cout, kh=k, kw=k, stride=stride,
-                   pad=pad, mode=mode, x_dtype=dt_code(x.dtype), y_dtype=dt_code(y_dtype or x.dtype))
+    if as_split:
+        if C1 % 8 != 0 or C2 % 8 != 0:
+            return False
+        p = ConvParams(x=None, x2=None, N=N, H=H, W=W, C1=C1, C2=C2, Ho=Ho, Wo=Wo, Cout=Cout, kh=k, kw=k, stride=stride,
+                       pad=pad, mode=mode, x_dtype=BF16X3, y_dtype=F32)
+    else:
+        p = ConvParams(x=_p(x), x2=_p(x2), N=N, H=H, W=W, C1=C1, C2=C2, Ho=Ho, Wo=Wo, Cout=Cout, kh=k, kw=k, stride=stride,
+                       pad=pad, mode=mode, x_dtype=dt_code(x.dtype), y_dtype=dt_code(y_dtype or x.dtype))
     return _lib.load().stfb_conv2d_tcgen05_supported(C.byref(p)) == 1
+
+
+def wgrad_tcgen05_ok(P, G, k, stride, pad, split=False):
+    """Can the tcgen05 family compute this weight gradient?  split: P / G are split-precision operands."""
+    N, Hp, Wp, Cp = P.shape
+    _, Hg, Wg, Cg = G.shape
+    if split:
+        Cp, Cg = Cp // 3, Cg // 3
+    return _lib.load().stfb_conv2d_wgrad_tcgen05_supported(_p(P), _p(G), N, Hp, Wp, Cp, Hg, Wg, Cg, k, k, stride, pad,
+                                                           BF16X3 if split else dt_code(P.dtype)) == 1
+
+
+def split_bf16x3(x, out=None):
+    """fp32 [..., C] -> bf16 [..., 3C] = [hi | mid | lo] (STFB_BF16X3, include/stfb200.h): the operand form of the
+    fp32-accurate tensor-core convolutions."""
+    _need_cuda(x)
+    assert x.dtype == torch.float32 and x.is_contiguous()
+    Cc = x.shape[-1]
+    rows = x.numel() // Cc
+    y = out if out is not None else torch.empty(x.shape[:-1] + (3 * Cc,), dtype=torch.bfloat16, device=x.device)
+    with _timed("split_bf16x3", _nb(x, y), f"C{Cc}"):
+        check(_lib.load().stfb_split_bf16x3(_p(x), _p(y), rows, Cc, _stream()), "split_bf16x3")
+    return y
+
+
+def pack_weight_split(w, k_is_dim1, flip=False):
+    """[D0, D1, kh, kw] (or [D0, D1]) fp32 parameter -> [n, kh*kw*6*K] bf16: the B operand of a split-precision convolution
+    (stfb_pack_weight_split)."""
+    _need_cuda(w)
+    if w.dim() == 2:
+        D0, D1, kh, kw = w.shape[0], w.shape[1], 1, 1
+    else:
+        D0, D1, kh, kw = w.shape
+    Kc, Nc = (D1, D0) if k_is_dim1 else (D0, D1)
+    wp = torch.empty((Nc, kh * kw * 6 * Kc), dtype=torch.bfloat16, device=w.device)
+    with _timed("pack_weight", _nb(w, wp)):
+        check(_lib.load().stfb_pack_weight_split(_p(w), _p(wp), D0, D1, kh, kw, int(k_is_dim1), int(flip), _stream()),
+              "pack_weight_split")
+    return wp
 
 
 def conv_stats_fusable(x, Cout, k, stride, pad, G, x2=None):
