@@ -654,12 +654,21 @@ def run_unet(args, rank, world, local_rank):
             gpu_ref = {"unavailable": f"{type(e).__name__}: {e}"[:200]}
     pk = peaks()
     f32 = results["fp32"]
-    # fp32-accurate mode: FFMA implicit GEMM.  148 SMs x 128 FMA lanes x 2 x 1.965 GHz = 74.4 TFLOP/s is its own ceiling; the
-    # contract's roofline object is quoted against the measured bf16 tensor peak like every GEMM-shaped kernel of this repo
-    roof = {"bound": "tensor", "kernel": "igemm_simt_kernel<float> + wgrad_simt_kernel<float> (whole fp32 step)",
-            "achieved": f32["model_tflops"], "peak": pk["tflops"], "unit": "TFLOP/s", "frac": round(f32["model_tflops"] / pk["tflops"], 4),
-            "traffic": None, "peak_source": pk["src"], "fp32_ffma_peak_tflops": 74.4,
-            "frac_of_fp32_ffma_peak": round(f32["model_tflops"] / 74.4, 4),
+    # fp32 mode: convolutions, dgrads and weight gradients run on the tensor cores over split-precision operands (STFB_BF16X3:
+    # three bf16 planes per fp32 tensor, SIX tcgen05 products per multiply-accumulate), so the ceiling of the scheme is the measured
+    # bf16 dense peak / 6; `achieved` counts the ALGORITHMIC fp32 FLOPs of the step, executed bf16 FLOPs = 6x.
+    # The FFMA family this mode ran on before (STFB_NO_SPLIT_FP32=1) has its own ceiling of 74.4 TFLOP/s.
+    from stf_unet_b200 import engine as _engine
+    split = _engine.USE_SPLIT_FP32 and _engine.USE_TCGEN05
+    peak = pk["tflops"] / 6.0 if split else 74.4
+    roof = {"bound": "tensor",
+            "kernel": ("conv_halo2_kernel / conv_halo_kernel / conv_tc_kernel / wgrad_halo_kernel on bf16x3 operands (whole fp32 step)" if split
+                       else "igemm_simt_kernel<float> + wgrad_simt_kernel<float> (whole fp32 step)"),
+            "achieved": f32["model_tflops"], "peak": round(peak, 1), "unit": "TFLOP/s", "frac": round(f32["model_tflops"] / peak, 4),
+            "traffic": None,
+            "peak_source": (pk["src"] + " bf16 dense peak / 6 products per MAC") if split else "148 SMs x 128 FMA lanes x 2 x 1.965 GHz",
+            "executed_bf16_tflops": round(f32["model_tflops"] * 6, 1) if split else None,
+            "fp32_ffma_peak_tflops": 74.4, "frac_of_fp32_ffma_peak": round(f32["model_tflops"] / 74.4, 4),
             "bf16_tensor_mode": {"tflops": results["bf16"]["model_tflops"], "frac": round(results["bf16"]["model_tflops"] / pk["tflops"], 4)}}
     line = {"metric": "train images/s UNet", "value": f32["images_per_s"], "unit": "images/s", "n_gpus": 1, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": f32["ms_per_step"], "higher_is_better": True, "scaling": "weak",

@@ -1394,6 +1394,34 @@ static int pick_bn(int Cout) {
   return 0;
 }
 
+// Output-channel tile for THIS problem.  The widest tile that divides Cout has the best tensor-pipe efficiency, but small maps
+// (UNet bottleneck at batch 4: 8 pixel tiles x 4 channel tiles of 256 = 32 CTAs on 148 SMs) leave most SMs idle: when the
+// widest tile fills less than half of the last wave, take the width with the best (wave fill x relative tile rate) instead.
+// Large problems (every layer of the headline workload) keep the widest tile.
+static int pick_bn_for(const stfb_conv_params* p) {
+  const int wide = pick_bn(p->Cout);
+  static int occ = -1;
+  if (occ < 0) { const char* e = getenv("STFB_BN_OCC"); occ = e ? atoi(e) : 1; }
+  if (!occ || wide <= 64) return wide;
+  const long long pix = p->mode == STFB_CONV_FWD ? (long long)p->N * p->Ho * p->Wo
+                                                 : (long long)p->N * ((p->Ho + p->stride - 1) / p->stride) * ((p->Wo + p->stride - 1) / p->stride) * p->stride * p->stride;
+  const long long pix_tiles = (pix + TC_BM - 1) / TC_BM;
+  const int sms = num_sms();
+  auto fill = [&](int bn) {
+    const long long tiles = pix_tiles * (p->Cout / bn);
+    return (double)tiles / (double)(((tiles + sms - 1) / sms) * sms);
+  };
+  if (fill(wide) >= 0.5) return wide;
+  int best = wide;
+  double best_score = fill(wide);
+  for (int bn = wide / 2; bn >= 64; bn /= 2) {
+    if (p->Cout % bn != 0) continue;
+    const double score = fill(bn) * (bn == 128 ? 0.9 : 0.6);
+    if (score > best_score) { best_score = score; best = bn; }
+  }
+  return best;
+}
+
 static bool g_tc_strided_fwd = true;   // TMA elementStrides path (stride-2 forward)
 
 int conv2d_tcgen05_supported(const stfb_conv_params* p) {
@@ -1591,7 +1619,7 @@ int conv2d_tcgen05(const stfb_conv_params* p, cudaStream_t st) {
   a.tiles_w = (Wl + a.TW - 1) / a.TW;
   a.tiles_h = (Hl + a.TH - 1) / a.TH;
   const int tiles_n = (p->N + a.TN - 1) / a.TN;
-  const int BN = pick_bn(p->Cout);
+  const int BN = pick_bn_for(p);
   const int Ktot = k * k * kmul * (p->C1 + p->C2);
   if (p->ldw < Ktot) { set_error("conv2d(tcgen05): ldw %d < kh*kw*Cin %d", p->ldw, Ktot); return STFB_EINVAL; }
 

@@ -189,10 +189,15 @@ static void launch_colreduce_t(const ColRedArgs& A, int VEC, dim3 grid, cudaStre
 
 // number of CTAs along the row axis (= number of partial-sum slots per (group, channel)); host-only, deterministic
 static int colreduce_blocks(int G, long long R) {
-  long long want = (2LL * num_sms() + G - 1) / G;     // ~2 waves in total
+  // few groups (UNet: one group per BatchNorm): 64 slots x G CTAs leave most SMs idle (1.2 TB/s on a 67 MB fp32 map,
+  // profiles/r02_unet_fp32_families.txt) -- four CTAs per SM then, up to 512 slots, which the finalize kernels walk with
+  // FIN_WIDE_SL lanes per (group, channel); >= 4 groups keep the 64-slot cap and the one-thread walk
+  const bool few = G < 4;
+  long long want = ((few ? 4LL : 2LL) * num_sms() + G - 1) / G;     // ~2 (4) waves in total
   long long cap = (R + 31) / 32;                      // at least 32 rows per CTA
   long long n = want < cap ? want : cap;
-  if (n > 64) n = 64;
+  const long long lim = few ? 512 : 64;
+  if (n > lim) n = lim;
   if (n < 1) n = 1;
   return (int)n;
 }
@@ -271,24 +276,61 @@ __device__ __forceinline__ void bn_train_coefs(const float* __restrict__ partial
   sh = beta_c - (float)m * sc;
 }
 
+// more than 64 slots (few groups, see colreduce_blocks): FIN_WIDE_SL threads share the slot walk of one (group, channel)
+constexpr int FIN_WIDE_SL = 32;     // one group per pass: blockDim = FIN_CH * FIN_WIDE_SL
+
+// SL = 1: blockDim = FIN_CH * groups per pass.  SL = FIN_WIDE_SL: blockDim = FIN_CH * groups per pass * SL, lane sl of a
+// (group, channel) sums slots sl, sl + SL, ... in fp64 and lane 0 adds the lane sums in order (deterministic).
+template <int SL>
 __global__ void __launch_bounds__(FIN_CH * FIN_MAXG) bn_finalize_train_kernel(
     const float* __restrict__ partial, int nblk, const float* __restrict__ gamma, const float* __restrict__ beta,
     float* running_mean, float* running_var, long long* nbt, float* scale, float* shift, float* mean, float* invstd, int G,
     long long R, int C, float eps, float momentum) {
   __shared__ float sh_m[FIN_MAXG][FIN_CH], sh_v[FIN_MAXG][FIN_CH];
-  const int cl = threadIdx.x % FIN_CH, gl = threadIdx.x / FIN_CH;
+  __shared__ double lane_s[SL > 1 ? FIN_MAXG : 1][FIN_CH], lane_q[SL > 1 ? FIN_MAXG : 1][FIN_CH];
+  const int gpb = blockDim.x / (FIN_CH * SL);
+  const int cl = threadIdx.x % FIN_CH, gl = (threadIdx.x / FIN_CH) % gpb, sl = threadIdx.x / (FIN_CH * gpb);
   const int c = blockIdx.x * FIN_CH + cl;
-  const int gpb = blockDim.x / FIN_CH;
   if (blockIdx.x == 0 && threadIdx.x == 0 && nbt) *nbt += G;
   float rm = 0.f, rv = 1.f;
-  if (gl == 0 && c < C) { rm = running_mean ? running_mean[c] : 0.f; rv = running_var ? running_var[c] : 1.f; }
+  if (gl == 0 && sl == 0 && c < C) { rm = running_mean ? running_mean[c] : 0.f; rv = running_var ? running_var[c] : 1.f; }
   const double n = (double)R;
   for (int g0 = 0; g0 < G; g0 += gpb) {
     const int g = g0 + gl;
-    if (g < G && c < C) {
+    if constexpr (SL > 1) {
+      double ls = 0.0, lq = 0.0;
+      if (g < G && c < C) {
+        const long long slot = 2LL * G * C;
+        const float* p = partial + (long long)g * C + c;
+        double s1 = 0.0, q1 = 0.0;
+        int b = sl;
+        for (; b + SL < nblk; b += 2 * SL) {
+          const float a0 = p[(long long)b * slot], b0 = p[(long long)b * slot + (long long)G * C];
+          const float a1 = p[(long long)(b + SL) * slot], b1 = p[(long long)(b + SL) * slot + (long long)G * C];
+          ls += (double)a0; lq += (double)b0; s1 += (double)a1; q1 += (double)b1;
+        }
+        if (b < nblk) { ls += (double)p[(long long)b * slot]; lq += (double)p[(long long)b * slot + (long long)G * C]; }
+        ls += s1; lq += q1;
+      }
+      lane_s[sl * gpb + gl][cl] = ls;
+      lane_q[sl * gpb + gl][cl] = lq;
+      __syncthreads();
+    }
+    if (sl == 0 && g < G && c < C) {
       float sc, sh, is;
       double m, var;
-      bn_train_coefs(partial, nblk, G, C, g, c, n, gamma[c], beta[c], eps, sc, sh, m, var, is);
+      if constexpr (SL > 1) {
+        double s = 0.0, q = 0.0;
+        for (int j = 0; j < SL; ++j) { s += lane_s[j * gpb + gl][cl]; q += lane_q[j * gpb + gl][cl]; }
+        m = s / n;
+        var = q / n - m * m;
+        if (var < 0.0) var = 0.0;
+        is = rsqrtf((float)var + eps);
+        sc = gamma[c] * is;
+        sh = beta[c] - (float)m * sc;
+      } else {
+        bn_train_coefs(partial, nblk, G, C, g, c, n, gamma[c], beta[c], eps, sc, sh, m, var, is);
+      }
       scale[g * C + c] = sc;
       shift[g * C + c] = sh;
       mean[g * C + c] = (float)m;
@@ -297,7 +339,7 @@ __global__ void __launch_bounds__(FIN_CH * FIN_MAXG) bn_finalize_train_kernel(
       sh_v[gl][cl] = (float)(R > 1 ? var * n / (n - 1.0) : var);
     }
     __syncthreads();
-    if (gl == 0 && c < C) {
+    if (gl == 0 && sl == 0 && c < C) {
       for (int j = 0; j < gpb && g0 + j < G; ++j) {
         rm = (1.f - momentum) * rm + momentum * sh_m[j][cl];
         rv = (1.f - momentum) * rv + momentum * sh_v[j][cl];
@@ -305,7 +347,7 @@ __global__ void __launch_bounds__(FIN_CH * FIN_MAXG) bn_finalize_train_kernel(
     }
     __syncthreads();
   }
-  if (gl == 0 && c < C) {
+  if (gl == 0 && sl == 0 && c < C) {
     if (running_mean) running_mean[c] = rm;
     if (running_var) running_var[c] = rv;
   }
@@ -407,9 +449,8 @@ __global__ void __launch_bounds__(256, 4) bn_apply_kernel(const T* __restrict__ 
 }
 
 // backward finalize: up to 64 partial slots per (group, channel) -> FIN_SL threads share the slot walk
-constexpr int FIN_SL = 4;
-constexpr int FIN_BG = 8;        // groups per block pass (blockDim = FIN_CH * FIN_BG * FIN_SL = 1024)
-
+// (few groups with up to 512 slots: 32 lanes x 1 group per pass)
+template <int FIN_SL, int FIN_BG>   // groups per block pass: blockDim = FIN_CH * FIN_BG * FIN_SL = 1024
 __global__ void __launch_bounds__(FIN_CH * FIN_BG * FIN_SL) bn_bwd_finalize_kernel(const float* __restrict__ partial, int nblk,
                                                                                   const float* __restrict__ gamma,
                                                                                   const float* __restrict__ invstd, float* dgamma,
@@ -1549,8 +1590,12 @@ extern "C" int stfb_bn_finalize_train(const float* partial, int nblk, const floa
                "bn_finalize_train: bad arguments");
   STFB_DEVICE_OR_RETURN();
   const int fin_g = G < FIN_MAXG ? G : FIN_MAXG;
-  bn_finalize_train_kernel<<<ceil_div(C, FIN_CH), FIN_CH * fin_g, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
-      partial, nblk, gamma, beta, running_mean, running_var, nbt, scale, shift, mean, invstd, G, R, C, eps, momentum);
+  if (nblk > 64 && G < 4)
+    bn_finalize_train_kernel<FIN_WIDE_SL><<<ceil_div(C, FIN_CH), FIN_CH * FIN_WIDE_SL, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+        partial, nblk, gamma, beta, running_mean, running_var, nbt, scale, shift, mean, invstd, G, R, C, eps, momentum);
+  else
+    bn_finalize_train_kernel<1><<<ceil_div(C, FIN_CH), FIN_CH * fin_g, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+        partial, nblk, gamma, beta, running_mean, running_var, nbt, scale, shift, mean, invstd, G, R, C, eps, momentum);
   return post_launch("bn_finalize_train");
 }
 
@@ -1617,8 +1662,12 @@ extern "C" int stfb_bn_bwd_finalize(const float* partial, int nblk, const float*
                                     float* dbeta, float* coef, int G, long long R, int C, void* stream) {
   STFB_REQUIRE(partial && nblk > 0 && gamma && invstd && coef && G > 0 && R > 0 && C > 0, "bn_bwd_finalize: bad arguments");
   STFB_DEVICE_OR_RETURN();
-  bn_bwd_finalize_kernel<<<ceil_div(C, FIN_CH), FIN_CH * FIN_BG * FIN_SL, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
-      partial, nblk, gamma, invstd, dgamma, dbeta, coef, G, R, C);
+  if (nblk > 64 && G < 4)
+    bn_bwd_finalize_kernel<32, 1><<<ceil_div(C, FIN_CH), 1024, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+        partial, nblk, gamma, invstd, dgamma, dbeta, coef, G, R, C);
+  else
+    bn_bwd_finalize_kernel<4, 8><<<ceil_div(C, FIN_CH), 1024, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+        partial, nblk, gamma, invstd, dgamma, dbeta, coef, G, R, C);
   return post_launch("bn_bwd_finalize");
 }
 

@@ -22,6 +22,7 @@ USE_TCGEN05 = _os.environ.get("STFB_NO_TCGEN05", "0") != "1"
 # fp32 mode: convolutions and weight gradients the tcgen05 family has a shape for run there on split-precision operands
 # (STFB_BF16X3, csrc/split.cu: three bf16 planes per fp32 tensor, six products per MAC, fp32-accurate) instead of the FFMA family
 USE_SPLIT_FP32 = _os.environ.get("STFB_NO_SPLIT_FP32", "0") != "1"
+USE_FP32_SIDE_STREAMS = _os.environ.get("STFB_NO_FP32_SIDE_STREAMS", "0") != "1"   # fp32 mode: weight gradients on the side streams too
 USE_FUSED_LSTM = _os.environ.get("STFB_NO_FUSED_LSTM", "0") != "1"
 # cell backward in the recurrent GEMM's epilogue (stfb_lstm_bwd_step_fused: one launch per backward time step instead of two,
 # dh never in memory).  Correct (tests/test_ops_gpu.py) but MEASURED SLOWER in the step, three times: 9.88 ms against 9.59 with a
@@ -278,10 +279,10 @@ class Executor:
 
     def side_launch(self, keep, fn):
         """Run fn() -- launches whose results only the optimizer reads (weight / bias gradients) -- on one of the
-        low-priority side streams forked from the current stream (bf16 path; otherwise inline).  `keep`: the tensors the
+        low-priority side streams forked from the current stream (bf16 path and the split-precision fp32 path; otherwise inline).  `keep`: the tensors the
         launches read, kept alive until the join at the end of the backward pass (their Python owners drop them earlier
         and the caching allocator would hand the memory to the main stream)."""
-        if USE_WGRAD_STREAM and self.dtype == torch.bfloat16 and keep[0].is_cuda:
+        if USE_WGRAD_STREAM and keep[0].is_cuda and (self.dtype == torch.bfloat16 or (USE_SPLIT_FP32 and USE_FP32_SIDE_STREAMS)):
             cur = torch.cuda.current_stream()
             pool = Executor._wg_streams.get(cur.device.index)
             if pool is None:
@@ -441,7 +442,7 @@ class Executor:
                 return
             rows = dy.shape[0] * dy.shape[1] * dy.shape[2]
             if bname and self.wants_grad(bname):
-                ops.colsum(dy, self.grads[bname], rows, Cout)
+                self.side_launch((dy,), lambda: ops.colsum(dy, self.grads[bname], rows, Cout))
             dys = ops.split_bf16x3(dy)
             if self.wants_grad(wname):
                 if not transposed:
