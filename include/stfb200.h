@@ -108,6 +108,8 @@ int stfb_conv2d_stats_fusable(const stfb_conv_params* p, int groups);
  *   dW is fp32 in the reference parameter layout ([Cout,Cin,kh,kw] for Conv2d, [Cin,Cout,kh,kw] for
  *   ConvTranspose2d, [4C,C] for the LSTM matrices) and is ACCUMULATED into (caller zeroes it).
  * Replaces: autograd of the operators listed above (loss.backward(), train_utils/train_and_eval.py:397-404).
+ * dtype STFB_BF16X3: P and G are split-precision operands ([.., 3*Cp] / [.., 3*Cg] bf16 from stfb_split_bf16x3; Cp / Cg stay
+ *   the logical counts): fp32-accurate weight gradient on the tensor cores, tcgen05 family only (impl != STFB_IMPL_SIMT).
  * impl: STFB_IMPL_AUTO picks the tcgen05 family when the shape allows (bf16, stride-1 "same" geometry, Cg % 64 == 0,
  * Cp % 64 == 0), else the SIMT family; STFB_IMPL_SIMT / STFB_IMPL_TCGEN05 force one.
  * The tcgen05 family needs a caller-provided fp32 workspace (the [(ky,kx,ci)][co] accumulation buffer the split-K CTAs
@@ -162,7 +164,8 @@ int stfb_pack_weight_split(const float* w, void* wp, int D0, int D1, int kh, int
 
 /* Batched form: one launch packs every weight of a step.  `jobs_dev` is a DEVICE array (uploaded once per model);
  * job j covers work items [start_j, start_{j+1}) of `total`, one work item = one (d0, d1) position with all its kh*kw
- * taps (so a job has D0*D1 items); fields as in stfb_pack_weight_ex. */
+ * taps (so a job has D0*D1 items); fields as in stfb_pack_weight_ex.  flip bit 0 = mirror the taps; flip bit 1 (value 2) = the job
+ * writes a split-precision operand (stfb_pack_weight_split layout, bf16, n_major = 1, ld = kh*kw*6*K) whatever `dtype` says. */
 typedef struct stfb_pack_job {
   const float* src;
   void* dst;

@@ -440,12 +440,15 @@ __global__ void __launch_bounds__(TC_THREADS, MINB) conv_tc_kernel(const __grid_
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         const TileCoord t = decode_tile<BN>(a, tile, n_tiles, cpt);
         const int wbase = t.wb * a.TW * a.a_scale, hbase = t.hb * a.TH * a.a_scale, i0 = t.nb * a.TN;
+        // k-blocks walk taps outermost; split-precision operands channel blocks outermost (the hi*hi segment comes last)
+        const int ntp = a.ntaps[t.ph];
+        int tp = 0, chunk = 0;
         for (int kb = 0; kb < t.num_kb; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
-          // k-blocks walk taps outermost; split-precision operands channel blocks outermost (the hi*hi segment comes last)
-          const int ntp = t.num_kb / cpt;
-          const int tp = a.split_c1 ? kb % ntp : kb / cpt, chunk = a.split_c1 ? kb / ntp : kb - tp * cpt;
           const int c = chunk * TC_BK;
+          const int tp_now = tp;
+          if (a.split_c1) { if (++tp == ntp) { tp = 0; ++chunk; } }
+          else if (++chunk == cpt) { chunk = 0; ++tp; }
           uint8_t* sa = smem + stage * STAGE_BYTES;
           uint8_t* sb = sa + TC_A_BYTES;
           if (a.debug == 2) {
@@ -454,11 +457,11 @@ __global__ void __launch_bounds__(TC_THREADS, MINB) conv_tc_kernel(const __grid_
             continue;
           }
           mbar_arrive_expect_tx(&full_bar[stage], STAGE_BYTES);
-          const int w0 = wbase + a.dw[t.ph][tp], h0 = hbase + a.dh[t.ph][tp];
+          const int w0 = wbase + a.dw[t.ph][tp_now], h0 = hbase + a.dh[t.ph][tp_now];
           int ach;
           if (!a_coord(a, c, ach)) tma_load_4d(sa, &tmA, &full_bar[stage], ach, w0, h0, i0);
           else tma_load_4d(sa, &tmA2, &full_bar[stage], ach, w0, h0, i0);
-          tma_load_2d(sb, &tmB, &full_bar[stage], (int)a.ktap[t.ph][tp] * Cin + c, t.n0);
+          tma_load_2d(sb, &tmB, &full_bar[stage], (int)a.ktap[t.ph][tp_now] * Cin + c, t.n0);
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
@@ -1413,7 +1416,7 @@ static int pick_bn_for(const stfb_conv_params* p) {
   };
   if (fill(wide) >= 0.5) return wide;
   int best = wide;
-  double best_score = fill(wide);
+  double best_score = 1.5 * fill(wide);          // a narrower tile has to promise a clear win (latency-bound small layers do not care)
   for (int bn = wide / 2; bn >= 64; bn /= 2) {
     if (p->Cout % bn != 0) continue;
     const double score = fill(bn) * (bn == 128 ? 0.9 : 0.6);

@@ -4,6 +4,7 @@
 // tensor cores) and the catch-all for shapes the tcgen05 family does not take (7x7 stem with Cin=1,
 // stride-2 convs, transposed convs, Cout=2 head).  Activations NHWC, fp32 accumulate, fused epilogue.
 #include "common.cuh"
+#include "split.cuh"
 
 namespace stfb {
 
@@ -637,9 +638,19 @@ __global__ void pack_weights_batched_kernel(const stfb_pack_job* __restrict__ jo
     int nd = n;
     if (jb.pad_ > 0) { const int gate = n / jb.pad_, u = n - gate * jb.pad_; nd = (u / 64) * 256 + ((u % 64) / 16) * 64 + gate * 16 + (u % 16); }
     const float* sp = jb.src + ((long long)d0 * jb.D1 + d1) * jb.khw;
+    if (jb.flip & 2) {
+      // split-precision operand (STFB_BF16X3, csrc/split.cu): bf16 [n][tap][6 segments][k] whatever T is
+      __nv_bfloat16* d16 = reinterpret_cast<__nv_bfloat16*>(jb.dst) + (long long)n * jb.ld + k;
+      for (int tap = 0; tap < jb.khw; ++tap) {
+        const float v = sp[(jb.flip & 1) ? (jb.khw - 1 - tap) : tap];
+#pragma unroll
+        for (int seg = 0; seg < 6; ++seg) d16[((long long)tap * 6 + seg) * Kc] = __float2bfloat16_rn(weight_plane(v, seg));
+      }
+      continue;
+    }
     T* dp = reinterpret_cast<T*>(jb.dst);
     for (int tap = 0; tap < jb.khw; ++tap) {
-      const int stap = jb.flip ? (jb.khw - 1 - tap) : tap;
+      const int stap = (jb.flip & 1) ? (jb.khw - 1 - tap) : tap;
       const long long di = jb.n_major ? (long long)nd * jb.ld + (long long)tap * Kc + k : ((long long)tap * Kc + k) * Nc + n;
       st1(dp + di, sp[stap]);
     }

@@ -12,19 +12,9 @@
 // 64-channel 3x3 layer (hi*hi first: 216 full-magnitude roundings; last: 36).  What remains is the rounding of the hi*hi chain
 // itself (K/16 roundings), the accuracy the bf16 mode's accumulation has as well.
 // This file holds the two producers of such operands.
-#include "common.cuh"
+#include "split.cuh"
 
 namespace stfb {
-
-__device__ __forceinline__ void split3(float x, float& h, float& m, float& l) {
-  const __nv_bfloat16 bh = __float2bfloat16_rn(x);
-  h = __bfloat162float(bh);
-  const float r1 = x - h;                       // exact
-  const __nv_bfloat16 bm = __float2bfloat16_rn(r1);
-  m = __bfloat162float(bm);
-  const float r2 = r1 - m;                      // exact
-  l = __bfloat162float(__float2bfloat16_rn(r2));
-}
 
 // x [rows][C] fp32 -> y [rows][3C] bf16; one thread = 8 channels of one row (32 B in, 3 x 16 B out)
 __global__ void __launch_bounds__(256) split_bf16x3_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ y,
@@ -43,14 +33,6 @@ __global__ void __launch_bounds__(256) split_bf16x3_kernel(const float* __restri
     st8(row + C, m);
     st8(row + 2 * C, l);
   }
-}
-
-// weight planes that meet the activation planes [lo, hi, mid, mid, hi, hi]
-__device__ __forceinline__ float weight_plane(float w, int seg) {
-  float h, m, l;
-  split3(w, h, m, l);
-  // seg: 0 1 2 3 4 5 -> hi lo mid hi mid hi
-  return (seg == 0 || seg == 3 || seg == 5) ? h : ((seg == 2 || seg == 4) ? m : l);
 }
 
 // destination [n][(tap, seg, k)] bf16; one work item = one (n, k) position with all its taps and segments

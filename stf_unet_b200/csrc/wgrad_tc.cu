@@ -115,10 +115,11 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_kernel(const __grid_co
       // (its rows are never written out), so every stage moves the same number of bytes
       const int nload = 2 * nacc;
       const uint32_t bytes = (uint32_t)(nload + NB) * WG_BLK_BYTES;
-      for (int it = 0; it < n_iter; ++it) {
-        const int v = it / n_real;
-        int t = p_beg + (it - v * n_real);
-        const int gpl = a.split ? wg_plane_g(v) : 0, ppl = a.split ? wg_plane_p(v) * a.Cp : 0;
+      const int visits = a.split ? 6 : 1;
+      for (int v = 0; v < visits; ++v) {
+      const int gpl = a.split ? wg_plane_g(v) : 0, ppl = a.split ? wg_plane_p(v) * a.Cp : 0;
+      for (int p = p_beg; p < p_end; ++p) {
+        int t = p;
         const int wb = t % a.tiles_w; t /= a.tiles_w;
         const int hb = t % a.tiles_h;
         const int nb = t / a.tiles_h;
@@ -143,6 +144,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_kernel(const __grid_co
         for (int i = 0; i < NB; ++i)
           tma_load_4d(sa + (2 * NA + i) * WG_BLK_BYTES, &tmP, &full_bar[stage], ppl + n0 + i * 64, w0, h0, i0);
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
+      }
       }
     }
   } else if (warp == 1) {
@@ -273,10 +275,11 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_halo_kernel(const __grid_
       int stage = 0;
       uint32_t phase = 0;
       const int cc = cblk * 64;
-      for (int it = 0; it < n_iter; ++it) {
-        const int v = it / n_real;
-        int t = p_beg + (it - v * n_real);
-        const int gpl = a.split ? wg_plane_g(v) : 0, ppl = a.split ? wg_plane_p(v) * a.Cp : 0;
+      const int visits = a.split ? 6 : 1;
+      for (int v = 0; v < visits; ++v) {
+      const int gpl = a.split ? wg_plane_g(v) : 0, ppl = a.split ? wg_plane_p(v) * a.Cp : 0;
+      for (int p = p_beg; p < p_end; ++p) {
+        int t = p;
         const int wb = t % a.tiles_w; t /= a.tiles_w;
         const int hb = t % a.tiles_h;
         const int nb = t / a.tiles_h;
@@ -288,6 +291,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_halo_kernel(const __grid_
         else tma_load_4d(sx, &tmG2, &full_bar[stage], gpl * a.C2 + cc - a.C1, w0 - 1, h0 - 1, nb);
         tma_load_4d(sx + WH_X_BYTES, &tmP, &full_bar[stage], ppl + n0, w0, h0, nb);
         if (++stage == WH_STAGES) { stage = 0; phase ^= 1; }
+      }
       }
     }
   } else if (warp == 1) {

@@ -216,11 +216,13 @@ class Executor:
         return v.split
 
     def packed_split(self, name, k_is_dim1):
-        key = ("x3", name, bool(k_is_dim1))
+        """Split-precision B operand of `name` (ops.pack_weight_split); part of the module's batched PackPlan like every pack."""
+        key = (name, bool(k_is_dim1), True, False, None, 0, None, "x3")
         self._join_late_packs(name)
         wp = self._packed.get(key)
         if wp is None:
             wp = self._packed[key] = ops.pack_weight_split(self.params[name], k_is_dim1)
+            self._new_pack_keys.append(key)
             self._split_wait_current()
         return wp
 

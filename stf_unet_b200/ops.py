@@ -309,10 +309,14 @@ class PackPlan:
             name, k_is_dim1, n_major, flip, kpad = key[:5]
             gate_c = key[5] if len(key) > 5 else 0
             cat = key[6] if len(key) > 6 else None       # (buffer name, column offset, row stride): K-concatenated operands
+            x3 = len(key) > 7 and key[7] == "x3"         # split-precision operand (pack_weight_split layout, always bf16)
             w = params[name]
             shape = packed_shape(w, k_is_dim1, n_major, kpad)
             esz = torch.empty((), dtype=dtype).element_size()
-            if cat is not None:
+            if x3:
+                buf = torch.empty((shape[0], 6 * shape[1]), dtype=torch.bfloat16, device=dev)
+                dst, ld = buf.data_ptr(), 6 * shape[1]
+            elif cat is not None:
                 cat_name, col_off, ld = cat
                 buf = cats.get(cat_name)
                 if buf is None:
@@ -324,7 +328,7 @@ class PackPlan:
             self.buffers[key] = buf
             D0, D1 = w.shape[0], w.shape[1]
             khw = 1 if w.dim() == 2 else w.shape[2] * w.shape[3]
-            jobs[j] = (w.data_ptr(), dst, start, D0, D1, khw, int(k_is_dim1), int(n_major), int(flip),
+            jobs[j] = (w.data_ptr(), dst, start, D0, D1, khw, int(k_is_dim1), int(n_major), int(flip) | (2 if x3 else 0),
                        ld if n_major else 0, int(gate_c))
             start += D0 * D1                      # one work item per (d0, d1) position, all taps
         self.total = start

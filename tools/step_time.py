@@ -1,6 +1,6 @@
 """Time the CUDA-graph training step (fwd + CE/Dice + bwd, no optimizer) — a quick A/B harness for kernel changes.
 
-    python tools/step_time.py [--iters 20] [--batch 16] [--T 8] [--hw 256]
+    python tools/step_time.py [--iters 20] [--batch 16] [--T 8] [--hw 256] [--fp32]
 """
 import argparse
 import os
@@ -20,13 +20,14 @@ def main():
     ap.add_argument("--batch", type=int, default=16)
     ap.add_argument("--T", type=int, default=8)
     ap.add_argument("--hw", type=int, default=256)
+    ap.add_argument("--fp32", action="store_true", help="fp32 mode (no autocast): split-precision tensor-core path unless STFB_NO_SPLIT_FP32=1")
     a = ap.parse_args()
     dev = torch.device("cuda", 0)
     torch.manual_seed(0)
     model = S.STFLSTMUNet(1, 2, a.T).to(dev)
     x, t = synthetic_dce_batch(a.batch, a.T, a.hw, a.hw, seed=1234)
     x, t = x.to(dev), t.to(dev)
-    g = GraphedStep(model, S.criterion, x, t)
+    g = GraphedStep(model, S.criterion, x, t, autocast_dtype=None if a.fp32 else torch.bfloat16)
     for _ in range(3):
         g(x, t)
     torch.cuda.synchronize()
