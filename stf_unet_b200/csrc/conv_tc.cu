@@ -128,6 +128,13 @@ __device__ __forceinline__ TileCoord decode_tile(const TcArgs& a, int tile, int 
   return t;
 }
 
+// k-blocks of a tile without the full decode (the MMA issuer needs nothing else: five div/mod per tile sat on its issue path,
+// and an LSTM step tile is only two k-blocks long)
+__device__ __forceinline__ int tile_num_kb(const TcArgs& a, int tile, int n_tiles, int cpt) {
+  if (a.nphase_w == 1) return a.ntaps[0] * cpt;
+  return a.ntaps[tile / (n_tiles * a.tiles_w * a.tiles_h * a.tiles_n)] * cpt;
+}
+
 // Persistent: one CTA per SM walks tiles `blockIdx.x, +gridDim.x, ...`.  The TMA ring keeps streaming across tile
 // boundaries and the accumulator is double-buffered in TMEM (2 x BN columns), so the epilogue of tile i overlaps the
 // main loop of tile i+1 and the per-tile prologue (barrier init, TMEM alloc, first TMA round trip) is paid once.
@@ -472,7 +479,7 @@ __global__ void __launch_bounds__(TC_THREADS, MINB) conv_tc_kernel(const __grid_
     int stage = 0, acc = 0;
     uint32_t phase = 0, acc_phase = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      const TileCoord t = decode_tile<BN>(a, tile, n_tiles, cpt);
+      struct { int num_kb; } t{tile_num_kb(a, tile, n_tiles, cpt)};
       mbar_wait(&tempty_bar[acc], acc_phase ^ 1);       // epilogue has drained this accumulator buffer
       tc_fence_after();
       const uint32_t tmem_acc = tmem_base + (uint32_t)(acc * BN);
@@ -893,8 +900,6 @@ __global__ void __launch_bounds__(TC_THREADS, MINB) conv_halo_kernel(const __gri
     uint32_t acc_phase = 0;
     for (int st = blockIdx.x; st < n_super; st += gridDim.x) {
       const int nt = st % n_tiles, pp = st / n_tiles;
-      mbar_wait(&tfull_bar[acc], acc_phase);
-      tc_fence_after();
 #pragma unroll 1
       for (int m = 0; m < MT; ++m) {
         const int ptile = pp * MT + m;
@@ -912,6 +917,10 @@ __global__ void __launch_bounds__(TC_THREADS, MINB) conv_halo_kernel(const __gri
           cmask |= (ok ? 1u : 0u) << i;
         }
         const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((acc * MT + m) * BN);
+        if (m == 0) {          // after the coordinate arithmetic: it overlaps the main loop instead of delaying the drain
+          mbar_wait(&tfull_bar[acc], acc_phase);
+          tc_fence_after();
+        }
         epilogue_tile<BN, TO>(a, t, taddr, stg, cpix, cmask, valid, on, oh, ow, m == MT - 1 ? &tempty_bar[acc] : nullptr, lane);
       }
       if (NBUF == 2) { if (++acc == 2) { acc = 0; acc_phase ^= 1; } }
@@ -1093,8 +1102,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(HALO2_THREADS, 1)
     for (int st = cid; st < n_super; st += ncl, ++it) {
       if ((int)(it & 1) != g) continue;
       const int nt = st % n_tiles, pp = st / n_tiles;
-      mbar_wait(&tfull_bar[g], (it >> 1) & 1);
-      tc_fence_after();
+      // tile coordinates and row addresses BEFORE the wait: the div/mod chain overlaps the main loop instead of delaying the drain
       const TileCoord t = decode_tile<BN>(a, (pp * 2 + (int)rank) * n_tiles + nt, n_tiles, cpt);
       const int ow = t.wb * HALO_TW + tw, oh = t.hb * HALO_TH + th, on = t.nb;
       const bool valid = ow < a.Wout && oh < a.Hout && on < a.N;
@@ -1108,6 +1116,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(HALO2_THREADS, 1)
         cmask |= (ok ? 1u : 0u) << i;
       }
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(g * BN);
+      mbar_wait(&tfull_bar[g], (it >> 1) & 1);
+      tc_fence_after();
       epilogue_tile<BN, TO>(a, t, taddr, stg, cpix, cmask, valid, on, oh, ow, nullptr, lane, tempty_leader);
     }
   }

@@ -115,15 +115,24 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_kernel(const __grid_co
       // (its rows are never written out), so every stage moves the same number of bytes
       const int nload = 2 * nacc;
       const uint32_t bytes = (uint32_t)(nload + NB) * WG_BLK_BYTES;
+      // per-block constants of this CTA (tap offsets, channel coordinate, which operand): decoded once, not per patch
+      int jcc[2 * NA], jdw[2 * NA], jdh[2 * NA];
+#pragma unroll
+      for (int j = 0; j < 2 * NA; ++j) {
+        const int chunk = min(chunk_lo + j, chunk_hi - 1);
+        const int tap = chunk / cpt, r = tap / a.kw;
+        jcc[j] = (chunk - tap * cpt) * 64;
+        jdw[j] = tap - r * a.kw - a.pad;
+        jdh[j] = r - a.pad;
+      }
       const int visits = a.split ? 6 : 1;
       for (int v = 0; v < visits; ++v) {
       const int gpl = a.split ? wg_plane_g(v) : 0, ppl = a.split ? wg_plane_p(v) * a.Cp : 0;
+      // patch coordinates by counting: the div/mod chain per patch sat on the producer's issue path
+      int wb = p_beg % a.tiles_w, hb = (p_beg / a.tiles_w) % a.tiles_h, nb = p_beg / (a.tiles_w * a.tiles_h);
       for (int p = p_beg; p < p_end; ++p) {
-        int t = p;
-        const int wb = t % a.tiles_w; t /= a.tiles_w;
-        const int hb = t % a.tiles_h;
-        const int nb = t / a.tiles_h;
         const int w0 = wb * a.TW, h0 = hb * a.TH, i0 = nb * a.TN;
+        if (++wb == a.tiles_w) { wb = 0; if (++hb == a.tiles_h) { hb = 0; ++nb; } }
         mbar_wait(&empty_bar[stage], phase ^ 1);
         uint8_t* sa = smem + stage * STAGE_BYTES;
         if (a.debug == 2) {
@@ -132,11 +141,11 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_kernel(const __grid_co
           continue;
         }
         mbar_arrive_expect_tx(&full_bar[stage], bytes);
-        for (int j = 0; j < nload; ++j) {
-          const int chunk = min(chunk_lo + j, chunk_hi - 1);
-          const int tap = chunk / cpt, cc = (chunk - tap * cpt) * 64;
-          const int r = tap / a.kw, sx = tap - r * a.kw;
-          const int gw = w0 * a.g_scale - a.pad + sx, gh = h0 * a.g_scale - a.pad + r;
+#pragma unroll
+        for (int j = 0; j < 2 * NA; ++j) {
+          if (j >= nload) break;
+          const int cc = jcc[j];
+          const int gw = w0 * a.g_scale + jdw[j], gh = h0 * a.g_scale + jdh[j];
           if (cc < a.C1) tma_load_4d(sa + j * WG_BLK_BYTES, &tmG, &full_bar[stage], gpl * a.C1 + cc, gw, gh, i0);
           else tma_load_4d(sa + j * WG_BLK_BYTES, &tmG2, &full_bar[stage], gpl * a.C2 + cc - a.C1, gw, gh, i0);
         }
@@ -278,12 +287,11 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_halo_kernel(const __grid_
       const int visits = a.split ? 6 : 1;
       for (int v = 0; v < visits; ++v) {
       const int gpl = a.split ? wg_plane_g(v) : 0, ppl = a.split ? wg_plane_p(v) * a.Cp : 0;
+      // patch coordinates by counting: the div/mod chain per patch sat on the producer's issue path
+      int wb = p_beg % a.tiles_w, hb = (p_beg / a.tiles_w) % a.tiles_h, nb_ = p_beg / (a.tiles_w * a.tiles_h);
       for (int p = p_beg; p < p_end; ++p) {
-        int t = p;
-        const int wb = t % a.tiles_w; t /= a.tiles_w;
-        const int hb = t % a.tiles_h;
-        const int nb = t / a.tiles_h;
-        const int w0 = wb * WH_PATCH, h0 = hb * WH_PATCH;
+        const int w0 = wb * WH_PATCH, h0 = hb * WH_PATCH, nb = nb_;
+        if (++wb == a.tiles_w) { wb = 0; if (++hb == a.tiles_h) { hb = 0; ++nb_; } }
         mbar_wait(&empty_bar[stage], phase ^ 1);
         uint8_t* sx = smem + stage * WH_STAGE_BYTES;
         mbar_arrive_expect_tx(&full_bar[stage], WH_X_TX + WG_BLK_BYTES);
