@@ -165,7 +165,9 @@ int stfb_pack_weight_split(const float* w, void* wp, int D0, int D1, int kh, int
 /* Batched form: one launch packs every weight of a step.  `jobs_dev` is a DEVICE array (uploaded once per model);
  * job j covers work items [start_j, start_{j+1}) of `total`, one work item = one (d0, d1) position with all its kh*kw
  * taps (so a job has D0*D1 items); fields as in stfb_pack_weight_ex.  flip bit 0 = mirror the taps; flip bit 1 (value 2) = the job
- * writes a split-precision operand (stfb_pack_weight_split layout, bf16, n_major = 1, ld = kh*kw*6*K) whatever `dtype` says. */
+ * writes a split-precision operand (stfb_pack_weight_split layout, bf16, n_major = 1, ld = kh*kw*6*K) whatever `dtype` says;
+ * flip bit 2 (value 4) = vector job: one work item covers EIGHT consecutive k of one n (the job has D0*D1/8 items; needs
+ * n_major = 1, K % 8 == 0, ld % 8 == 0 and a 16-byte aligned dst). */
 typedef struct stfb_pack_job {
   const float* src;
   void* dst;

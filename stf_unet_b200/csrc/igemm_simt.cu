@@ -631,6 +631,36 @@ __global__ void pack_weights_batched_kernel(const stfb_pack_job* __restrict__ jo
     const stfb_pack_job jb = jobs[lo];
     const long long i = gi - jb.start;
     const int Kc = jb.k_is_dim1 ? jb.D1 : jb.D0, Nc = jb.k_is_dim1 ? jb.D0 : jb.D1;
+    if (jb.flip & 4) {
+      // vector item: EIGHT consecutive k of one n (n_major rows, Kc % 8 == 0): one 16-byte store per tap (and segment) instead
+      // of eight 2-byte ones, the job search and the index arithmetic paid once per eight elements
+      const int kc8 = Kc >> 3;
+      const int n = (int)(i / kc8), k0 = (int)(i - (long long)n * kc8) * 8;
+      int nd = n;
+      if (jb.pad_ > 0) { const int gate = n / jb.pad_, u = n - gate * jb.pad_; nd = (u / 64) * 256 + ((u % 64) / 16) * 64 + gate * 16 + (u % 16); }
+      // source of element e: [d0][d1][taps]; with k on dim 1 the eight elements are 8 * khw contiguous floats
+      const long long sbase = jb.k_is_dim1 ? ((long long)n * jb.D1 + k0) * jb.khw : ((long long)k0 * jb.D1 + n) * jb.khw;
+      const long long sstep = jb.k_is_dim1 ? (long long)jb.khw : (long long)jb.D1 * jb.khw;
+      for (int tap = 0; tap < jb.khw; ++tap) {
+        const int stap = (jb.flip & 1) ? (jb.khw - 1 - tap) : tap;
+        float v[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) v[e] = __ldg(jb.src + sbase + e * sstep + stap);
+        if (jb.flip & 2) {
+          __nv_bfloat16* d16 = reinterpret_cast<__nv_bfloat16*>(jb.dst) + (long long)n * jb.ld + (long long)tap * 6 * Kc + k0;
+#pragma unroll
+          for (int seg = 0; seg < 6; ++seg) {
+            float w[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) w[e] = weight_plane(v[e], seg);
+            st8(d16 + (long long)seg * Kc, w);
+          }
+        } else {
+          st8(reinterpret_cast<T*>(jb.dst) + (long long)nd * jb.ld + (long long)tap * Kc + k0, v);
+        }
+      }
+      continue;
+    }
     int n, k;
     if (!jb.n_major) { n = (int)(i % Nc); k = (int)(i / Nc); }      // destination (tap, k, n): n fastest
     else { k = (int)(i % Kc); n = (int)(i / Kc); }                  // destination (n, tap, k): k fastest

@@ -328,13 +328,20 @@ class PackPlan:
             self.buffers[key] = buf
             D0, D1 = w.shape[0], w.shape[1]
             khw = 1 if w.dim() == 2 else w.shape[2] * w.shape[3]
-            jobs[j] = (w.data_ptr(), dst, start, D0, D1, khw, int(k_is_dim1), int(n_major), int(flip) | (2 if x3 else 0),
-                       ld if n_major else 0, int(gate_c))
-            start += D0 * D1                      # one work item per (d0, d1) position, all taps
+            Kc = D1 if k_is_dim1 else D0
+            vec = bool(n_major) and Kc % 8 == 0 and ld % 8 == 0 and dst % 16 == 0     # eight k per work item, 16-byte stores
+            jobs[j] = (w.data_ptr(), dst, start, D0, D1, khw, int(k_is_dim1), int(n_major),
+                       int(flip) | (2 if x3 else 0) | (4 if vec else 0), ld if n_major else 0, int(gate_c))
+            start += PackPlan._items(jobs[j])     # one work item per (d0, d1) position (or eight of them), all taps
         self.total = start
         self._job_dtype = job_t
         self.table = torch.from_numpy(jobs.view(np.uint8)).to(dev)
         self.signature = tuple(params[k[0]].data_ptr() for k in self.keys)
+
+    @staticmethod
+    def _items(job):
+        n = int(job["D0"]) * int(job["D1"])
+        return n // 8 if int(job["flip"]) & 4 else n
 
     def valid_for(self, params, dtype):
         try:
@@ -364,7 +371,7 @@ class PackPlan:
                 start = 0
                 for j in range(len(jobs)):
                     jobs[j]["start"] = start
-                    start += int(jobs[j]["D0"]) * int(jobs[j]["D1"])
+                    start += PackPlan._items(jobs[j])
                 parts.append((torch.from_numpy(jobs.view(np.uint8).copy()).to(self.table.device), len(idx), start))
             split = self._split = parts
         cur = torch.cuda.current_stream()
