@@ -1,4 +1,6 @@
 #!/bin/bash
+# Same-box A/B harness: `mkdir _ab_old && git archive <commit> | tar -x -C _ab_old && (cd _ab_old && python -m stf_unet_b200.build)`
+# puts an older commit (with its own library) beside the working tree; the runs alternate so both see the same box and clocks.
 set -x
 one() { python -c "
 import json,sys
