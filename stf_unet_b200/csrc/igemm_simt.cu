@@ -617,6 +617,56 @@ __global__ void pack_weight_kernel(const float* __restrict__ w, T* __restrict__ 
   }
 }
 
+// One vector work item of the batched pack: EIGHT consecutive k of one n -> one 16-byte store per tap (and split segment) instead of
+// eight 2-byte ones, the job search and the index arithmetic paid once per eight elements.  All taps of the eight source positions
+// are read first (each position's khw floats are contiguous: one or two sectors, fetched once -- a tap-outer order re-touched 256
+// scattered chunks per warp nine times and thrashed L1 on the dgrad packs).  KHW = compile-time tap count (registers), 0 = runtime
+// count <= 9 with the tap-outer order.
+template <typename T, int KHW>
+__device__ __forceinline__ void pack_vec_item(const stfb_pack_job& jb, long long i, int Kc) {
+  const int kc8 = Kc >> 3;
+  const int n = (int)(i / kc8), k0 = (int)(i - (long long)n * kc8) * 8;
+  int nd = n;
+  if (jb.pad_ > 0) { const int gate = n / jb.pad_, u = n - gate * jb.pad_; nd = (u / 64) * 256 + ((u % 64) / 16) * 64 + gate * 16 + (u % 16); }
+  // source of element e: [d0][d1][taps]; with k on dim 1 the eight elements are 8 * khw contiguous floats
+  const long long sbase = jb.k_is_dim1 ? ((long long)n * jb.D1 + k0) * jb.khw : ((long long)k0 * jb.D1 + n) * jb.khw;
+  const long long sstep = jb.k_is_dim1 ? (long long)jb.khw : (long long)jb.D1 * jb.khw;
+  constexpr int NT = KHW > 0 ? KHW : 1;
+  float vv[8][NT];
+  if constexpr (KHW > 0) {
+#pragma unroll
+    for (int e = 0; e < 8; ++e)
+#pragma unroll
+      for (int tp = 0; tp < KHW; ++tp) vv[e][tp] = __ldg(jb.src + sbase + e * sstep + tp);
+  }
+  const int ntap = KHW > 0 ? KHW : jb.khw;
+#pragma unroll
+  for (int tap = 0; tap < ntap; ++tap) {
+    float v[8];
+    if constexpr (KHW > 0) {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) v[e] = (jb.flip & 1) ? vv[e][KHW - 1 - tap] : vv[e][tap];
+    } else {
+      const int stap = (jb.flip & 1) ? (jb.khw - 1 - tap) : tap;
+#pragma unroll
+      for (int e = 0; e < 8; ++e) v[e] = __ldg(jb.src + sbase + e * sstep + stap);
+    }
+    if (jb.flip & 2) {
+      // split-precision operand (STFB_BF16X3, csrc/split.cu): bf16 [n][tap][6 segments][k] whatever T is
+      __nv_bfloat16* d16 = reinterpret_cast<__nv_bfloat16*>(jb.dst) + (long long)n * jb.ld + (long long)tap * 6 * Kc + k0;
+#pragma unroll
+      for (int seg = 0; seg < 6; ++seg) {
+        float w[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) w[e] = weight_plane(v[e], seg);
+        st8(d16 + (long long)seg * Kc, w);
+      }
+    } else {
+      st8(reinterpret_cast<T*>(jb.dst) + (long long)nd * jb.ld + (long long)tap * Kc + k0, v);
+    }
+  }
+}
+
 // all weight packs of a step in ONE launch: job table in device memory, binary search on the work-item offset.
 // One work item = one (d0, d1) position of a weight = its khw filter taps: the taps are contiguous in the source
 // ([D0][D1][kh][kw]), so a warp reads a contiguous run and writes khw coalesced rows of the packed operand.
@@ -632,32 +682,12 @@ __global__ void pack_weights_batched_kernel(const stfb_pack_job* __restrict__ jo
     const long long i = gi - jb.start;
     const int Kc = jb.k_is_dim1 ? jb.D1 : jb.D0, Nc = jb.k_is_dim1 ? jb.D0 : jb.D1;
     if (jb.flip & 4) {
-      // vector item: EIGHT consecutive k of one n (n_major rows, Kc % 8 == 0): one 16-byte store per tap (and segment) instead
-      // of eight 2-byte ones, the job search and the index arithmetic paid once per eight elements
-      const int kc8 = Kc >> 3;
-      const int n = (int)(i / kc8), k0 = (int)(i - (long long)n * kc8) * 8;
-      int nd = n;
-      if (jb.pad_ > 0) { const int gate = n / jb.pad_, u = n - gate * jb.pad_; nd = (u / 64) * 256 + ((u % 64) / 16) * 64 + gate * 16 + (u % 16); }
-      // source of element e: [d0][d1][taps]; with k on dim 1 the eight elements are 8 * khw contiguous floats
-      const long long sbase = jb.k_is_dim1 ? ((long long)n * jb.D1 + k0) * jb.khw : ((long long)k0 * jb.D1 + n) * jb.khw;
-      const long long sstep = jb.k_is_dim1 ? (long long)jb.khw : (long long)jb.D1 * jb.khw;
-      for (int tap = 0; tap < jb.khw; ++tap) {
-        const int stap = (jb.flip & 1) ? (jb.khw - 1 - tap) : tap;
-        float v[8];
-#pragma unroll
-        for (int e = 0; e < 8; ++e) v[e] = __ldg(jb.src + sbase + e * sstep + stap);
-        if (jb.flip & 2) {
-          __nv_bfloat16* d16 = reinterpret_cast<__nv_bfloat16*>(jb.dst) + (long long)n * jb.ld + (long long)tap * 6 * Kc + k0;
-#pragma unroll
-          for (int seg = 0; seg < 6; ++seg) {
-            float w[8];
-#pragma unroll
-            for (int e = 0; e < 8; ++e) w[e] = weight_plane(v[e], seg);
-            st8(d16 + (long long)seg * Kc, w);
-          }
-        } else {
-          st8(reinterpret_cast<T*>(jb.dst) + (long long)nd * jb.ld + (long long)tap * Kc + k0, v);
-        }
+      // vector item: EIGHT consecutive k of one n (n_major rows, Kc % 8 == 0, khw <= 9)
+      switch (jb.khw) {
+        case 9: pack_vec_item<T, 9>(jb, i, Kc); break;
+        case 4: pack_vec_item<T, 4>(jb, i, Kc); break;
+        case 1: pack_vec_item<T, 1>(jb, i, Kc); break;
+        default: pack_vec_item<T, 0>(jb, i, Kc); break;
       }
       continue;
     }

@@ -329,7 +329,7 @@ class PackPlan:
             D0, D1 = w.shape[0], w.shape[1]
             khw = 1 if w.dim() == 2 else w.shape[2] * w.shape[3]
             Kc = D1 if k_is_dim1 else D0
-            vec = bool(n_major) and Kc % 8 == 0 and ld % 8 == 0 and dst % 16 == 0     # eight k per work item, 16-byte stores
+            vec = bool(n_major) and Kc % 8 == 0 and ld % 8 == 0 and dst % 16 == 0 and khw <= 9   # eight k per work item, 16-byte stores
             jobs[j] = (w.data_ptr(), dst, start, D0, D1, khw, int(k_is_dim1), int(n_major),
                        int(flip) | (2 if x3 else 0) | (4 if vec else 0), ld if n_major else 0, int(gate_c))
             start += PackPlan._items(jobs[j])     # one work item per (d0, d1) position (or eight of them), all taps

@@ -1,7 +1,9 @@
-"""fp32-accurate convolutions on the tensor cores (STFB_BF16X3, include/stfb200.h; csrc/split.cu): every fp32 operand as three
-bf16 planes, six tcgen05 products per MAC.  Checked against torch in fp64 (the exact answer) and against the FFMA family the
-fp32 mode used before: the split path must be at least as close to the exact answer as a plain fp32 accumulation is
-(tolerance written per test: rel-L2 <= 2e-6 on single layers; the north_star bar for logits is 1e-4)."""
+"""fp32 mode on the tensor cores (STFB_BF16X3, include/stfb200.h; csrc/split.cu): every fp32 GEMM operand as three bf16 planes,
+six tcgen05 products per MAC, the five correction terms accumulated BEFORE the hi*hi chain (the TMEM accumulator rounds toward zero
+once per K = 16 instruction).  Checked against torch in fp64 (the exact answer) with the FFMA family -- what the fp32 mode ran on
+before -- measured beside it on the same inputs.  Measured on B200: forward 3.6e-7 (K = 576) .. 1.5e-6 (K = 2304) against
+3.0e-7 .. 5.5e-7 for FFMA; weight gradients 0.6e-7 .. 2.4e-7 against 0.9e-7 .. 3.0e-7.  Bars: TOL = 4e-6 rel-L2 on a forward
+layer, 4 x TOL on dgrad / wgrad (north_star's bar for whole-model logits is 1e-4, held by tests/test_models_gpu.py)."""
 import pytest
 import torch
 import torch.nn.functional as F
@@ -11,7 +13,7 @@ pytestmark = pytest.mark.gpu
 from stf_unet_b200 import ops  # noqa: E402
 
 DEV = "cuda"
-TOL = 1e-5
+TOL = 4e-6
 
 
 @pytest.fixture(autouse=True, scope="module")

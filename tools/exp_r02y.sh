@@ -1,8 +1,8 @@
 #!/bin/bash
 set -x
-timeout 1500 python -m pytest tests -q -m gpu --timeout 300 -x 2>&1 | tail -5
-timeout 300 python bench.py --workload unet --steps 20 --warmup 5 > gpurun_out/r02_bench_unet_split.json 2> gpurun_out/r02_bench_unet_split.err
-echo "bench rc=$?"; python -c "
-import json
-d=json.loads(open('gpurun_out/r02_bench_unet_split.json').read().strip().splitlines()[-1]); print(d['modes'], d['gpu_launches'])"
-timeout 300 python bench.py --workload infer --steps 20 --warmup 5 > gpurun_out/r02_bench_infer_b.json 2>/dev/null; cut -c1-160 gpurun_out/r02_bench_infer_b.json
+timeout 1200 python -m pytest tests -q -m gpu --timeout 300 -x 2>&1 | tail -4
+timeout 300 python bench.py --steps 20 --warmup 5 --no-cpu-baseline --no-gpu-baseline > gpurun_out/r02_bench_train_c.json 2>/dev/null; echo "rc=$?"; cut -c1-200 gpurun_out/r02_bench_train_c.json
+timeout 300 python bench.py --workload unet --steps 20 --warmup 5 --no-cpu-baseline --no-gpu-baseline 2>/dev/null | python -c "
+import json,sys
+d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print('UNET', {k:v['ms_per_step'] for k,v in d['modes'].items()})"
+timeout 120 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -3 | cut -c1-300
