@@ -39,6 +39,22 @@ def test_argument_validation_needs_no_device():
     assert b"null" in lib.stfb_last_error()
     assert lib.stfb_maxpool_fwd(None, None, 1, 4, 4, 4, 2, 2, 2, 2, 0, 0, None) == -1
     assert lib.stfb_ce_dice_fwd(None, None, None, None, 1, 2, 4, 1e-6, None) == -1
+    # split-precision (bf16 x 3) entry points: channel counts must be multiples of 8; the operands belong to the tcgen05 family
+    buf = (ctypes.c_float * 64)()
+    addr = ctypes.addressof(buf)
+    assert lib.stfb_split_bf16x3(addr, addr, 4, 12, None) == -1 and b"multiple of 8" in lib.stfb_last_error()
+    assert lib.stfb_split_bf16x3(None, None, 0, 64, None) == 0                      # empty input: nothing to do, no device needed
+    assert lib.stfb_pack_weight_split(None, None, 8, 8, 3, 3, 1, 0, None) == -1
+    p = _lib.ConvParams(x=addr, w=addr, y=addr, N=1, H=8, W=8, C1=64, C2=0, Ho=8, Wo=8, Cout=64, kh=3, kw=3, stride=1, pad=1, ldw=64,
+                        mode=0, x_dtype=_lib.BF16X3, y_dtype=_lib.F32, impl=_lib.IMPL_SIMT)
+    assert lib.stfb_conv2d(ctypes.byref(p), None) == -1 and b"tcgen05" in lib.stfb_last_error()
+    p.impl, p.ldw = _lib.IMPL_TCGEN05, 9 * 64                                       # six K segments per channel: ldw too small
+    assert lib.stfb_conv2d(ctypes.byref(p), None) == -1 and b"x6" in lib.stfb_last_error()
+    p.ldw = 9 * 6 * 64
+    assert lib.stfb_conv2d_tcgen05_supported(ctypes.byref(p)) == 1
+    p.y_dtype = _lib.BF16                                                            # bf16x3 operands always produce fp32
+    assert lib.stfb_conv2d_tcgen05_supported(ctypes.byref(p)) == 0
+    assert lib.stfb_conv2d_wgrad(addr, addr, addr, 1, 8, 8, 64, 8, 8, 64, 0, 64, 3, 3, 1, 1, _lib.BF16X3, _lib.IMPL_SIMT, None, 0, None) == -1
 
 
 @pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-device error path")
