@@ -107,4 +107,29 @@ __device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + expf(-
 
 static inline int ceil_div(long long a, long long b) { return (int)((a + b - 1) / b); }
 
+// ---- programmatic dependent launch (PDL) -----------------------------------------------------------------------------
+// A kernel launched with the programmatic-serialization attribute may START while the previous kernel of its stream is still
+// draining (block scheduling, barrier init, TMEM allocation, tensor-map prefetch overlap the predecessor's last wave); it must
+// call pdl_wait() before it touches anything the predecessor wrote.  pdl_trigger() lets the successor start early.  Both are
+// no-ops for a kernel launched without the attribute.  STFB_PDL = bit mask of the kernel families whose launches carry the
+// attribute (1 = convolutions, 2 = BatchNorm apply / backward, 3 = both); 0 = off, the default.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+bool pdl_enabled(int family);   // family bit: 1 = tensor-core convolution kernels, 2 = BatchNorm elementwise kernels
+
+template <int FAMILY, typename... KArgs, typename... Args>
+static inline cudaError_t launch_ex(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  int n = 0;
+  if (pdl_enabled(FAMILY)) {
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    n = 1;
+  }
+  cfg.attrs = attr; cfg.numAttrs = n;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 }  // namespace stfb

@@ -408,6 +408,7 @@ __global__ void __launch_bounds__(TC_THREADS, MINB) conv_tc_kernel(const __grid_
   constexpr int STAGE_BYTES = TC_A_BYTES + B_BYTES;
   constexpr int TMEM_COLS = (2 * BN < 32) ? 32 : 2 * BN;
   extern __shared__ uint8_t smem_raw[];
+  pdl_trigger();       // the next kernel of the stream may start its prologue while this one runs (it waits before reading)
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   // layout: [STAGES x (A, B)] [4 epilogue warps x staging segments] [mbarriers, TMEM slot]
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES + 4 * tc_stg_segs<EPI>() * TC_SEG_BYTES);
@@ -438,6 +439,7 @@ __global__ void __launch_bounds__(TC_THREADS, MINB) conv_tc_kernel(const __grid_
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();          // prologue done (barriers, TMEM, tensor maps): only now anything the previous kernel wrote may be touched
 
   if (warp == 0) {
     // ================= TMA producer =================
@@ -751,6 +753,7 @@ __global__ void __launch_bounds__(TC_THREADS, MINB) conv_halo_kernel(const __gri
   constexpr int TMEM_COLS = (NBUF * MT * BN < 32) ? 32 : NBUF * MT * BN;
   constexpr int WRAPS = 9 / SB;                       // ring wraps per channel block
   extern __shared__ uint8_t smem_raw[];
+  pdl_trigger();       // the next kernel of the stream may start its prologue while this one runs (it waits before reading)
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const uint32_t sA = smem_u32(smem);
   const uint32_t sB = sA + SA * HALO_BLK_BYTES;
@@ -787,6 +790,7 @@ __global__ void __launch_bounds__(TC_THREADS, MINB) conv_halo_kernel(const __gri
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();          // prologue done (barriers, TMEM, tensor maps): only now anything the previous kernel wrote may be touched
 
   if (warp == 0) {
     // ================= TMA producer =================
@@ -965,6 +969,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(HALO2_THREADS, 1)
   constexpr int TMEM_COLS = (2 * BN < 32) ? 32 : 2 * BN;
   constexpr int WRAPS = 9 / SB;
   extern __shared__ uint8_t smem_raw[];
+  pdl_trigger();       // the next kernel of the stream may start its prologue while this one runs (it waits before reading)
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const uint32_t sA = smem_u32(smem);
   const uint32_t sB = sA + SA * HALO_BLK_BYTES;
@@ -1009,6 +1014,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(HALO2_THREADS, 1)
   cluster_sync_all();               // the peer's barriers are initialised before anything arrives on them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();          // prologue done (barriers, TMEM, tensor maps): only now anything the previous kernel wrote may be touched
 
   if (warp == 0) {
     // ================= TMA producer (both CTAs: own halo block, own half of the weights) =================
@@ -1485,7 +1491,7 @@ static int launch_tc(const CUtensorMap& tA, const CUtensorMap& tA2, const CUtens
     }
     configured = true;
   }
-  conv_tc_kernel<BN, STAGES, TO, BK, EPI, MINB><<<grid, TC_THREADS, smem, st>>>(tA, tA2, tB, a);
+  launch_ex<1>(conv_tc_kernel<BN, STAGES, TO, BK, EPI, MINB>, grid, dim3(TC_THREADS), smem, st, tA, tA2, tB, a);
   return post_launch("conv2d(tcgen05)");
 }
 
@@ -1503,7 +1509,7 @@ static int launch_halo(const CUtensorMap& tA, const CUtensorMap& tA2, const CUte
     }
     configured = true;
   }
-  conv_halo_kernel<BN, MT, SA, SB, TO, MINB><<<grid, TC_THREADS, smem, st>>>(tA, tA2, tB, a);
+  launch_ex<1>(conv_halo_kernel<BN, MT, SA, SB, TO, MINB>, grid, dim3(TC_THREADS), smem, st, tA, tA2, tB, a);
   return post_launch("conv2d(tcgen05 halo)");
 }
 
@@ -1536,7 +1542,7 @@ static int launch_halo2(const CUtensorMap& tA, const CUtensorMap& tA2, const CUt
     max_clusters = nc < num_sms() / 2 ? nc : num_sms() / 2;
   }
   const int ncl = n_super < max_clusters ? n_super : max_clusters;
-  conv_halo2_kernel<BN, SA, SB, TO><<<dim3((unsigned)(2 * ncl)), HALO2_THREADS, smem, st>>>(tA, tA2, tB, a);
+  launch_ex<1>(conv_halo2_kernel<BN, SA, SB, TO>, dim3((unsigned)(2 * ncl)), dim3(HALO2_THREADS), smem, st, tA, tA2, tB, a);
   return post_launch("conv2d(tcgen05 pair)");
 }
 

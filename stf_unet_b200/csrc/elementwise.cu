@@ -397,6 +397,8 @@ __global__ void __launch_bounds__(256, 4) bn_apply_kernel(const T* __restrict__ 
                                                        const float* __restrict__ partial, int nblk,
                                                        const float* __restrict__ gamma, const float* __restrict__ beta, float eps) {
   extern __shared__ float coef_sm[];                 // [2][C]: scale, shift of this CTA's group
+  pdl_trigger();                                     // programmatic dependent launch (common.cuh): no-ops without the attribute
+  pdl_wait();
   constexpr int U = 2;
   const int lanes = 256 / tpr;
   const int cl = threadIdx.x % tpr, rl = threadIdx.x / tpr;
@@ -609,6 +611,8 @@ __global__ void __launch_bounds__(256, 2) bn_bwd_fused_kernel(const T* __restric
                                                               float* dgamma, float* dbeta, T* dx, T* dres, long long R, int C,
                                                               long long rows_per_block, int tpr, int relu, int accum_dres) {
   __shared__ float red[256 * VEC * 2];
+  pdl_trigger();                                     // programmatic dependent launch (common.cuh): no-ops without the attribute
+  pdl_wait();
   const int tid = threadIdx.x;
   const int lanes = 256 / tpr;
   const int cl = tid % tpr, rl = tid / tpr;
@@ -1616,7 +1620,7 @@ static int bn_apply_launch(const void* x, const float* scale, const float* shift
   const RowTile rt = row_tile(G, R, C, v, 2);
   const size_t sm = (size_t)2 * C * sizeof(float);
   STFB_REQUIRE(sm <= 48 * 1024, "bn_apply: %d channels exceed the shared-memory coefficient table", C);
-#define BN_APPLY(V) bn_apply_kernel<T, V><<<rt.grid, 256, sm, s>>>((const T*)x, scale, shift, (const T*)residual, (T*)y, R, C, rt.rows_per_block, rt.tpr, relu, partial, nblk, gamma, beta, eps)
+#define BN_APPLY(V) launch_ex<2>(bn_apply_kernel<T, V>, rt.grid, dim3(256), sm, s, (const T*)x, scale, shift, (const T*)residual, (T*)y, R, C, rt.rows_per_block, rt.tpr, relu, partial, nblk, gamma, beta, eps)
   DISPATCH_T(dtype, {
     if (v == 8) BN_APPLY(8);
     else if (v == 4) BN_APPLY(4);
@@ -1745,7 +1749,7 @@ extern "C" int stfb_bn_bwd_fused(const void* dy, const void* y, const void* x, c
   unsigned* counters = reinterpret_cast<unsigned*>(scratch + (size_t)2 * G * C);
   dim3 grid((unsigned)nblk, (unsigned)G);
   const bool lean = !dres && (!relu || !y);                   // nothing but dy and x is read
-#define BN_FUSED(V, L) bn_bwd_fused_kernel<T, V, L><<<grid, 256, 0, s>>>((const T*)dy, (const T*)y, (const T*)x, mean, invstd, gamma, shift, acc, counters, dgamma, dbeta, (T*)dx, (T*)dres, R, C, rpb, tpr, relu, accum_dres)
+#define BN_FUSED(V, L) launch_ex<2>(bn_bwd_fused_kernel<T, V, L>, grid, dim3(256), 0, s, (const T*)dy, (const T*)y, (const T*)x, mean, invstd, gamma, shift, acc, counters, dgamma, dbeta, (T*)dx, (T*)dres, R, C, rpb, tpr, relu, accum_dres)
   DISPATCH_T(dtype, {
     if (lean) { if (v == 8) BN_FUSED(8, true); else if (v == 4) BN_FUSED(4, true); else BN_FUSED(1, true); }
     else { if (v == 8) BN_FUSED(8, false); else if (v == 4) BN_FUSED(4, false); else BN_FUSED(1, false); }

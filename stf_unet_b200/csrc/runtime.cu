@@ -1,5 +1,6 @@
 // Library-wide state: last error, device probe, launch counter.
 #include "common.cuh"
+#include <stdlib.h>
 #include <atomic>
 #include <string.h>
 
@@ -45,6 +46,12 @@ int check_device() {
 }
 
 int num_sms() { return g_num_sms > 0 ? g_num_sms : 148; }
+
+// STFB_PDL: bit mask of the kernel families launch_ex() marks for programmatic dependent launch (read per call: tests switch it)
+bool pdl_enabled(int family) {
+  const char* e = getenv("STFB_PDL");
+  return e != nullptr && (atoi(e) & family) != 0;
+}
 
 void count_launch(int n) { g_launches.fetch_add((unsigned long long)n, std::memory_order_relaxed); }
 
