@@ -922,3 +922,31 @@ def test_bn_relu_maxpool_one_pass_equals_two_launches(G, B, H, W, C, k, s, p):
     # and the apply kernel's in-kernel coefficients are those of the finalize kernel
     st = ops.bn_finalize_train(slots, gamma, beta, None, None, None, G, R, C)
     assert torch.equal(ops.bn_apply(xn, st[0], st[1], G, R, C, True), y_full)
+
+
+@pytest.mark.parametrize("mask", ["1", "2", "3"])
+def test_programmatic_dependent_launch_switch_is_bit_identical(mask, monkeypatch):
+    """STFB_PDL marks the convolution (1) / BatchNorm (2) launches for programmatic dependent launch: the kernels wait
+    (griddepcontrol.wait) before they touch what their predecessor wrote, so a conv -> BN-apply -> conv chain must give the same
+    bits with and without it."""
+    dtype = torch.bfloat16
+    x = nhwc(q(rnd(8, 64, 32, 32, seed=1), dtype), dtype)
+    w1 = ops.pack_weight(q(rnd(64, 64, 3, 3, seed=2, scale=0.05), dtype).contiguous(), True, dtype, n_major=True)
+    w2 = ops.pack_weight(q(rnd(128, 64, 3, 3, seed=3, scale=0.05), dtype).contiguous(), True, dtype, n_major=True)
+    scale, shift = rnd(1, 64, seed=4).abs() + 0.5, rnd(1, 64, seed=5)
+
+    def chain():
+        y = x
+        for _ in range(3):
+            y = ops.conv2d(y, w1, 64, 3, 1, 1, impl=ops.IMPL_TCGEN05)
+            y = ops.bn_apply(y, scale, shift, 1, 8 * 32 * 32, 64, relu=True)
+        return ops.conv2d(y, w2, 128, 3, 1, 1, impl=ops.IMPL_TCGEN05)
+
+    monkeypatch.setenv("STFB_PDL", "0")
+    ref = chain()
+    torch.cuda.synchronize()
+    monkeypatch.setenv("STFB_PDL", mask)
+    got = chain()
+    torch.cuda.synchronize()
+    assert torch.equal(ref, got)
+    assert torch.isfinite(got.float()).all() and got.float().abs().max() > 0
