@@ -1,3 +1,3 @@
 #!/bin/bash
 set -x
-timeout 300 python -m pytest tests/test_ops_gpu.py -q -m gpu --timeout 120 -k "programmatic or conv_fused_bn" 2>&1 | tail -5
+timeout 200 python bench.py > gpurun_out/r02_bench_default.json 2> gpurun_out/r02_bench_default.err; echo "rc=$?"; cut -c1-260 gpurun_out/r02_bench_default.json; tail -2 gpurun_out/r02_bench_default.err | cut -c1-200
